@@ -1,0 +1,37 @@
+"""CPU: the oracle restatement reproduces the reference outputs frozen in tests/golden (pins the oracle)."""
+import numpy as np
+import pytest
+import torch
+
+from cases import AE_CASES, PRED_CASES, build_ae_case, build_predictor_case, golden_sample
+from oracle import npvp_oracle as O
+
+torch.set_grad_enabled(False)
+
+
+@pytest.mark.parametrize("name", PRED_CASES)
+def test_predictor_oracle_matches_reference(name):
+    mod, x, eps, stoch, z = build_predictor_case(name)
+    sd = mod.state_dict()
+    out = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], stoch, eps if stoch else None)
+    assert list(out.shape) == list(z["shape"])
+    np.testing.assert_allclose(golden_sample(out, z), z["sample"], atol=5e-5, rtol=0)
+    assert abs(float(out.double().mean()) - float(z["mean"])) < 1e-5
+
+
+@pytest.mark.parametrize("name", AE_CASES)
+def test_autoencoder_oracle_matches_reference(name):
+    enc, dec, x, f_in, cfg, ze, zd = build_ae_case(name)
+    feats = O.resnet_encoder(enc.state_dict(), x, cfg["n_down"], cfg["n_res"])
+    frames = O.resnet_decoder(dec.state_dict(), f_in, cfg["n_down"], cfg["out_layer"])
+    assert list(feats.shape) == list(ze["shape"]) and list(frames.shape) == list(zd["shape"])
+    np.testing.assert_allclose(golden_sample(feats, ze), ze["sample"], atol=5e-4 * max(1.0, float(ze["absmax"])), rtol=0)
+    np.testing.assert_allclose(golden_sample(frames, zd), zd["sample"], atol=5e-5, rtol=0)
+
+
+def test_coordinate_asserts():
+    hl = torch.linspace(0, 7, 8)
+    with pytest.raises(AssertionError):
+        O.coor_generator(torch.tensor([0., 13.]), hl, hl, 12, 8, 8)
+    c = O.coor_generator(torch.tensor([1.5]), hl, hl, 12, 8, 8)
+    assert c.shape == (64, 3) and abs(float(c[9, 0]) - 0.125) < 1e-7 and float(c[9, 1]) == 0.125 and float(c[9, 2]) == 0.125
