@@ -1,0 +1,173 @@
+/* npvp_b200 C-ABI: sm_100a kernels for the NPVP inference hot path.
+ *
+ * Drop-in boundary: the reference (XiYe20/NPVP) is pure PyTorch and owns no
+ * native code, so there is no existing FFI to mirror; each entry point below replaces the
+ * eager torch op sequence cited next to it (file:line into the reference tree).  The Python
+ * modules in npvp_b200/ (same class names / signatures as models/Predictor.py and
+ * models/ResNetAutoEncoder.py) bind these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - every function returns NPVP_OK (0) or a negative error code; the message is available
+ *     from npvp_last_error() (thread-local);  no exceptions cross the boundary;
+ *   - token layout: activations are channels-last, a "frame" is 64 tokens (8x8 grid) x C;
+ *     bf16 buffers are GEMM/conv operands, fp32 buffers carry residual streams and statistics.
+ */
+#ifndef NPVP_B200_H
+#define NPVP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPVP_OK 0
+#define NPVP_ERR_INVALID (-1)
+#define NPVP_ERR_CUDA (-2)
+
+#define NPVP_ACT_NONE 0
+#define NPVP_ACT_RELU 1
+#define NPVP_ACT_GELU 2 /* exact erf GELU, nn.GELU() default (models/VidHRFormer.py:73,337) */
+#define NPVP_ACT_TANH 3
+#define NPVP_ACT_SIGMOID 4
+
+#define NPVP_GEMM_AUTO 0
+#define NPVP_GEMM_TCGEN05 1 /* TMA-fed tcgen05.mma, TMEM accumulators */
+#define NPVP_GEMM_SIMT 2    /* CUDA-core reference path for debugging / odd shapes */
+
+#define NPVP_PAD_ZERO 0
+#define NPVP_PAD_REFLECT 1
+#define NPVP_PAD_REPLICATE 2
+
+#define NPVP_ATTN_SPATIAL_WINDOW 0 /* 4x4 windows on the 8x8 grid, L = 16 */
+#define NPVP_ATTN_TEMPORAL 1       /* per-pixel sequences over time, Lq = Tq, Lk = Tk */
+
+/* Fused GEMM epilogue:  v = acc + bias[n];  v = act(v);  v *= alpha;  v += res1[m,n];  v += res2[m,n];
+ * v = post_relu ? max(v,0) : v;  stored to out_f32 and/or out_bf16 (row stride ld_out elements). */
+typedef struct npvp_epilogue {
+  const void* bias; /* fp32 [N] or NULL */
+  const void* res1; /* [M, ld_res] or NULL */
+  const void* res2; /* [M, ld_res] or NULL */
+  void* out_f32;    /* fp32 [M, ld_out] or NULL */
+  void* out_bf16;   /* bf16 [M, ld_out] or NULL */
+  float alpha;
+  int32_t act;
+  int32_t res1_bf16; /* 1: res1 is bf16, 0: fp32 */
+  int32_t res2_bf16;
+  int32_t post_relu;
+  int64_t ld_out;
+  int64_t ld_res;
+} npvp_epilogue_t;
+
+const char* npvp_last_error(void);
+int npvp_version(void);
+/* number of kernels launched through this library since the last reset (bench accounting) */
+int64_t npvp_launch_count(void);
+void npvp_reset_launch_count(void);
+
+/* ---- dense contractions -------------------------------------------------------------------
+ * D[M,N] = A[M,K] (bf16, row stride lda) x W[N,K]^T (bf16, row stride ldw), fp32 accumulate.
+ * Replaces every nn.Linear / 1x1 conv / MHA in- and out-projection on the path
+ * (models/VidHRFormer.py:104,111,221,225,239,298,380,387; models/submodules.py:148-162,396-403)
+ * and, together with npvp_im2col_nhwc, the 3x3 / strided / transposed convs of the autoencoder
+ * (models/ResNetAutoEncoder.py:75-87,169-183,241,254; models/submodules.py:25). */
+int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                   const npvp_epilogue_t* ep, int backend, void* stream);
+/* fp32 CUDA-core GEMM for the tiny, precision-critical NRMLP (models/submodules.py:299-314). */
+int npvp_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                  const float* bias, int act, float* out, int64_t ldo, void* stream);
+
+/* ---- predictor: positional code, per-token / per-frame normalisation --------------------------
+ * Fourier features [cos(2 pi x B^T), sin(2 pi x B^T)]  (NRMLP.gaussian_mapping, submodules.py:317-327).
+ * coor fp32 [rows,3], B fp32 [half,3], out fp32 [rows, 2*half]. */
+int npvp_fourier_features(const float* coor, const float* B, float* out, int64_t rows, int half, void* stream);
+
+/* Fused  a = LayerNorm_C(x) ; u = a + qe ; fused = GroupNorm1(u over the frame) * (1+gamma) + beta
+ * (VidHRFormer.py:87-88,95-96,210-212,218-219,229,236 + PosFeatFuser submodules.py:432-454).
+ * x fp32 [n_clips*T, 64, 512]; ln_w/ln_b fp32 [512] or NULL (no LayerNorm: a = x);
+ * qe fp32 [n_clips, 64, 512] or NULL; beta fp32 [T,64,512]; gamma fp32 [T,64,512] or NULL;
+ * out_ln (bf16, optional) receives a; out_fused (bf16, optional) receives fused. */
+int npvp_ln_posfuse(const float* x, const float* ln_w, const float* ln_b, const float* qe, const float* beta,
+                    const float* gamma, void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T,
+                    void* stream);
+/* LayerNorm over C=512 per token (VidHRFormer.py:91,110,214,224,243; final norm :48,:151 with relu=1 for :159).
+ * Outputs optional fp32 and/or bf16. */
+int npvp_layernorm_rows(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16,
+                        int64_t rows, int relu, void* stream);
+/* y += GELU(LayerNorm_(C,8,8)(h))  - MlpDWBN norm3 + act3 + the block's residual add
+ * (VidHRFormer.py:388-389 with :91/:214/:243).  h fp32 [frames,64,512]; w,b fp32 [64,512] (hw-major). */
+int npvp_frame_ln_gelu_residual(const float* h, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,
+                                void* stream);
+/* mean over time of the memory (Predictor.py:346): mem fp32 [n,T,64*512] -> evt fp32 [n,64*512]. */
+int npvp_temporal_mean(const float* mem, float* evt, int64_t n_clips, int64_t T, int64_t frame_elems, void* stream);
+
+/* ---- predictor: conv-FFN middle  (MlpDWBN norm1/act1/dw3x3/norm2/act2, VidHRFormer.py:381-385) ----
+ * step 1: per-frame (sum, sumsq) of h1 bf16 [frames,64,Ch] -> stats fp32 [frames,2] = (mean, rstd) */
+int npvp_ffn_frame_stats(const void* h_bf16, float* stats, int64_t frames, int64_t Ch, void* stream);
+/* step 2: y = dw3x3(GELU(LN1(h1))) + b; also per-(frame,chunk) partial (sum,sumsq) of y.
+ * n1w/n1b fp32 [64,Ch] (hw-major elementwise affine), dw_w fp32 [9,Ch], dw_b fp32 [Ch];
+ * y bf16 [frames,64,Ch]; partial fp32 [frames, Ch/256, 2]. */
+int npvp_ffn_dwconv(const void* h_bf16, const float* stats1, const float* n1w, const float* n1b,
+                    const float* dw_w, const float* dw_b, void* y_bf16, float* partial2, int64_t frames,
+                    int64_t Ch, void* stream);
+/* step 3: out = GELU(LN2(y)) bf16, statistics from the partials of step 2. */
+int npvp_ffn_norm2(const void* y_bf16, const float* partial2, const float* n2w, const float* n2b, void* out_bf16,
+                   int64_t frames, int64_t Ch, void* stream);
+
+/* ---- predictor: attention cores (8 heads x 64) ---------------------------------------------
+ * softmax(Q K^T / 8 [+mask]) V for the short sequences of the factorised attention
+ * (nn.MultiheadAttention cores at VidHRFormer.py:104,221,239,298 + window permutes :447-475).
+ * q/k/v/out are bf16 token matrices (row = token, 512 used columns, row strides ld*).
+ * SPATIAL_WINDOW: q,k,v have n_clips*Tq*64 rows; TEMPORAL: q/out have n_clips*Tq*64 rows,
+ * k/v have n_clips*Tk*64 rows.  mask_last=1 reproduces the encoder quirk (:100-102):
+ * queries 0..Tq-2 may not attend to key Tk-1. */
+int npvp_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                   int64_t ldo, int mode, int64_t n_clips, int Tq, int Tk, int mask_last, void* stream);
+
+/* ---- predictor: event encoder / latent (models/submodules.py:388-410) --------------------------
+ * depthwise 3x3 (zero pad) on the 8x8 grid, channels-last, folded BN scale in w, shift + optional ReLU.
+ * x fp32 [frames,64,C]; w fp32 [9,C]; shift fp32 [C]; out bf16 [frames,64,C]. */
+int npvp_dwconv3x3_tokens(const float* x, const float* w, const float* shift, void* out_bf16, int64_t frames,
+                          int64_t C, int relu, void* stream);
+/* z = mu + exp(0.5*logvar) * eps.  mulv fp32 [n*64, 2*C] = (mu | logvar) token-major; eps fp32 NCHW [n,C,8,8]
+ * (the reference's layout, submodules.py:408-410) or NULL (z = mu); z fp32 [n,64,C] token-major. */
+int npvp_latent_reparam(const float* mulv, int64_t ld, const float* eps_nchw, float* z, int64_t n_clips, int64_t C,
+                        void* stream);
+
+/* ---- layout changes at the module boundary --------------------------------------------------
+ * (N,T,C,H,W) fp32  <->  channels-last tokens.  frames = N*T, HW = H*W. */
+int npvp_nchw_to_tokens(const float* x, float* out_f32, void* out_bf16, int64_t frames, int64_t C, int64_t HW,
+                        void* stream);
+int npvp_tokens_to_nchw(const float* x_f32, const void* x_bf16, float* out, int64_t frames, int64_t C, int64_t HW,
+                        int relu, void* stream);
+
+/* ---- autoencoder ---------------------------------------------------------------------------
+ * 7x7 stem: reflect-pad 3, conv (no bias) + folded BN + ReLU  (ResNetAutoEncoder.py:70-73).
+ * x fp32 NCHW [frames,Cin,H,W]; w fp32 [49*Cin, Cout] (tap-major, BN scale folded); shift fp32 [Cout];
+ * out bf16 NHWC [frames,H,W,Cout]. */
+int npvp_conv7x7_stem(const float* x, const float* w, const float* shift, void* out_bf16, int64_t frames, int Cin,
+                      int Cout, int H, int W, void* stream);
+/* 7x7 head: reflect-pad 3, conv + bias + Tanh|Sigmoid (ResNetAutoEncoder.py:184-189).
+ * x bf16 [frames,H,W,Cin] (phase_major=1: stored [frames,H/2,W/2,4,Cin], the ConvT GEMM's native output);
+ * w fp32 [49*Cin, Cout]; bias fp32 [Cout]; out fp32 NCHW [frames,Cout,H,W]. */
+int npvp_conv7x7_head(const void* x_bf16, const float* w, const float* bias, float* out, int64_t frames, int Cin,
+                      int Cout, int H, int W, int phase_major, int act, void* stream);
+/* Patch gather for conv-as-GEMM: out[(f,oy,ox), (ky,kx,c)] = x[f, oy*stride - pad + ky, ox*stride - pad + kx, c].
+ * x bf16 NHWC (or phase-major), out bf16 [frames*Ho*Wo, KH*KW*C]. */
+int npvp_im2col_nhwc(const void* x_bf16, void* out_bf16, int64_t frames, int H, int W, int C, int KH, int KW,
+                     int stride, int pad, int pad_mode, int Ho, int Wo, int phase_major, void* stream);
+/* 2x2/stride-2 max-pool of a column slice of a token matrix (NonLocalAttenion2D k/v pooling, submodules.py:151,158).
+ * x bf16 [frames*H*W, ldx], columns [col0, col0+Cn) -> out bf16 [frames*(H/2)*(W/2), Cn]. */
+int npvp_maxpool2x2_cols(const void* x_bf16, int64_t ldx, int col0, int Cn, void* out_bf16, int64_t frames, int H,
+                         int W, void* stream);
+/* Non-local attention core: softmax(q k^T) v, UNSCALED (submodules.py:153-160).
+ * q bf16 [frames*HW, ldq] (first dq columns); kv bf16 [frames*HWk, dq+dv] (k | v); out bf16 [frames*HW, dv]. */
+int npvp_nonlocal_attention(const void* q, int64_t ldq, const void* kv, void* out, int64_t frames, int HW, int HWk,
+                            int dq, int dv, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPVP_B200_H */

@@ -1,0 +1,306 @@
+"""ctypes binding of ``libnpvp_b200.so`` (the C-ABI declared in ``include/npvp_b200.h``).
+
+``ops()`` returns the singleton :class:`Ops`, whose methods take torch CUDA tensors, pass raw device
+pointers + sizes + the current CUDA stream across the C boundary and raise ``RuntimeError`` with
+``npvp_last_error()`` on a non-zero return code.  There is no fallback: if the library is missing or
+the tensors are not on a CUDA device the call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
+GEMM_AUTO, GEMM_TCGEN05, GEMM_SIMT = 0, 1, 2
+PAD_ZERO, PAD_REFLECT, PAD_REPLICATE = 0, 1, 2
+ATTN_SPATIAL, ATTN_TEMPORAL = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnpvp_b200.so")
+
+_i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("bias", _vp), ("res1", _vp), ("res2", _vp), ("out_f32", _vp), ("out_bf16", _vp),
+                ("alpha", _f32), ("act", C.c_int32), ("res1_bf16", C.c_int32), ("res2_bf16", C.c_int32),
+                ("post_relu", C.c_int32), ("ld_out", _i64), ("ld_res", _i64)]
+
+
+# symbol -> argtypes; every function returns int.  Kept in one table so tests can check the export list.
+SIGNATURES = {
+    "npvp_gemm_bf16": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _vp],
+    "npvp_gemm_f32": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i32, _vp, _i64, _vp],
+    "npvp_fourier_features": [_vp, _vp, _vp, _i64, _i32, _vp],
+    "npvp_ln_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "npvp_layernorm_rows": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "npvp_frame_ln_gelu_residual": [_vp, _vp, _vp, _vp, _i64, _vp],
+    "npvp_temporal_mean": [_vp, _vp, _i64, _i64, _i64, _vp],
+    "npvp_ffn_frame_stats": [_vp, _vp, _i64, _i64, _vp],
+    "npvp_ffn_dwconv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "npvp_ffn_norm2": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "npvp_attention": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i64, _i32, _i32, _i32, _vp],
+    "npvp_dwconv3x3_tokens": [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp],
+    "npvp_latent_reparam": [_vp, _i64, _vp, _vp, _i64, _i64, _vp],
+    "npvp_nchw_to_tokens": [_vp, _vp, _vp, _i64, _i64, _i64, _vp],
+    "npvp_tokens_to_nchw": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp],
+    "npvp_conv7x7_stem": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
+    "npvp_conv7x7_head": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "npvp_im2col_nhwc": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "npvp_maxpool2x2_cols": [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _i32, _vp],
+    "npvp_nonlocal_attention": [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
+}
+AUX_SYMBOLS = ["npvp_last_error", "npvp_version", "npvp_launch_count", "npvp_reset_launch_count"]
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with `python -m npvp_b200.build` (nvcc, sm_100a). "
+                           "npvp_b200 has no CPU or eager fallback.")
+    lib = C.CDLL(path)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = argtypes, C.c_int
+    lib.npvp_last_error.restype = C.c_char_p
+    lib.npvp_version.restype = C.c_int
+    lib.npvp_launch_count.restype = C.c_int64
+    lib.npvp_reset_launch_count.restype = None
+    return lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: Optional[torch.Tensor], dtype, name: str, contiguous: bool = True):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"npvp_b200: tensor '{name}' must live on a CUDA device (no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"npvp_b200: tensor '{name}' must be {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise ValueError(f"npvp_b200: tensor '{name}' must be contiguous")
+
+
+def _rowmajor(t: torch.Tensor, name: str):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"npvp_b200: '{name}' must be a 2-D view with unit inner stride")
+    return t.stride(0)
+
+
+class Ops:
+    """Tensor-level wrappers over the C-ABI.  All outputs are preallocated by the caller."""
+
+    def __init__(self, lib: Optional[C.CDLL] = None):
+        self.lib = lib or load_library()
+        self.gemm_backend = {"auto": GEMM_AUTO, "tcgen05": GEMM_TCGEN05, "simt": GEMM_SIMT}[
+            os.environ.get("NPVP_B200_GEMM", "auto")]
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _call(self, name, *args):
+        rc = getattr(self.lib, name)(*args)
+        if rc != 0:
+            raise RuntimeError(f"{name} failed ({rc}): {self.lib.npvp_last_error().decode()}")
+
+    def launch_count(self) -> int:
+        return int(self.lib.npvp_launch_count())
+
+    def reset_launch_count(self):
+        self.lib.npvp_reset_launch_count()
+
+    # -- contractions ---------------------------------------------------------------------------
+    def gemm(self, a, w, *, bias=None, act=ACT_NONE, alpha=1.0, res1=None, res2=None, out_f32=None, out_bf16=None,
+             post_relu=False, backend=None):
+        _chk(a, torch.bfloat16, "a", False); _chk(w, torch.bfloat16, "w", False)
+        _chk(bias, torch.float32, "bias"); _chk(out_f32, torch.float32, "out_f32", False)
+        _chk(out_bf16, torch.bfloat16, "out_bf16", False)
+        lda, ldw = _rowmajor(a, "a"), _rowmajor(w, "w")
+        M, K = a.shape
+        N = w.shape[0]
+        assert w.shape[1] == K, (a.shape, w.shape)
+        outs = [o for o in (out_f32, out_bf16) if o is not None]
+        assert outs and all(o.shape == (M, N) for o in outs), "gemm: output shape mismatch"
+        ld_out = _rowmajor(outs[0], "out")
+        assert all(_rowmajor(o, "out") == ld_out for o in outs)
+        ld_res = 0
+        for r in (res1, res2):
+            if r is not None:
+                assert r.is_cuda and r.shape == (M, N) and r.dtype in (torch.float32, torch.bfloat16)
+                ld = _rowmajor(r, "res")
+                assert ld_res in (0, ld), "gemm: residuals must share a row stride"
+                ld_res = ld
+        ep = Epilogue(_ptr(bias), _ptr(res1), _ptr(res2), _ptr(out_f32), _ptr(out_bf16), float(alpha), int(act),
+                      int(res1 is not None and res1.dtype == torch.bfloat16),
+                      int(res2 is not None and res2.dtype == torch.bfloat16), int(bool(post_relu)), ld_out, ld_res)
+        self._call("npvp_gemm_bf16", a.data_ptr(), lda, w.data_ptr(), ldw, M, N, K, C.byref(ep),
+                   self.gemm_backend if backend is None else backend, self._stream())
+
+    def gemm_f32(self, a, w, bias, act, out):
+        for t, n in ((a, "a"), (w, "w"), (out, "out")):
+            _chk(t, torch.float32, n, False)
+        _chk(bias, torch.float32, "bias")
+        M, K = a.shape
+        N = w.shape[0]
+        assert w.shape[1] == K and out.shape == (M, N)
+        self._call("npvp_gemm_f32", a.data_ptr(), _rowmajor(a, "a"), w.data_ptr(), _rowmajor(w, "w"), M, N, K, _ptr(bias),
+                   int(act), out.data_ptr(), _rowmajor(out, "out"), self._stream())
+
+    # -- predictor ------------------------------------------------------------------------------
+    def fourier_features(self, coor, B, out):
+        _chk(coor, torch.float32, "coor"); _chk(B, torch.float32, "B"); _chk(out, torch.float32, "out")
+        rows, half = coor.shape[0], B.shape[0]
+        assert coor.shape[1] == 3 and B.shape[1] == 3 and out.shape == (rows, 2 * half)
+        self._call("npvp_fourier_features", coor.data_ptr(), B.data_ptr(), out.data_ptr(), rows, half, self._stream())
+
+    def ln_posfuse(self, x, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, n_clips, T):
+        _chk(x, torch.float32, "x"); _chk(ln_w, torch.float32, "ln_w"); _chk(ln_b, torch.float32, "ln_b")
+        _chk(qe, torch.float32, "qe"); _chk(beta, torch.float32, "beta"); _chk(gamma, torch.float32, "gamma")
+        _chk(out_ln, torch.bfloat16, "out_ln"); _chk(out_fused, torch.bfloat16, "out_fused")
+        assert x.numel() == n_clips * T * 64 * 512
+        assert qe is None or qe.numel() == n_clips * 64 * 512
+        assert beta is None or beta.numel() == T * 64 * 512
+        self._call("npvp_ln_posfuse", x.data_ptr(), _ptr(ln_w), _ptr(ln_b), _ptr(qe), _ptr(beta), _ptr(gamma), _ptr(out_ln),
+                   _ptr(out_fused), n_clips, T, self._stream())
+
+    def layernorm_rows(self, x, w, b, out_f32=None, out_bf16=None, relu=False):
+        _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(b, torch.float32, "b")
+        _chk(out_f32, torch.float32, "out_f32"); _chk(out_bf16, torch.bfloat16, "out_bf16")
+        rows = x.numel() // 512
+        self._call("npvp_layernorm_rows", x.data_ptr(), w.data_ptr(), b.data_ptr(), _ptr(out_f32), _ptr(out_bf16), rows,
+                   int(relu), self._stream())
+
+    def frame_ln_gelu_residual(self, h, w_hwc, b_hwc, y):
+        for t, n in ((h, "h"), (w_hwc, "w"), (b_hwc, "b"), (y, "y")):
+            _chk(t, torch.float32, n)
+        frames = h.numel() // (64 * 512)
+        assert y.numel() == h.numel() and w_hwc.numel() == 64 * 512
+        self._call("npvp_frame_ln_gelu_residual", h.data_ptr(), w_hwc.data_ptr(), b_hwc.data_ptr(), y.data_ptr(), frames,
+                   self._stream())
+
+    def temporal_mean(self, mem, evt, n_clips, T):
+        _chk(mem, torch.float32, "mem"); _chk(evt, torch.float32, "evt")
+        fe = mem.numel() // (n_clips * T)
+        assert evt.numel() == n_clips * fe
+        self._call("npvp_temporal_mean", mem.data_ptr(), evt.data_ptr(), n_clips, T, fe, self._stream())
+
+    def ffn_frame_stats(self, h, stats):
+        _chk(h, torch.bfloat16, "h"); _chk(stats, torch.float32, "stats")
+        frames, Ch = stats.shape[0], h.shape[-1]
+        assert h.numel() == frames * 64 * Ch
+        self._call("npvp_ffn_frame_stats", h.data_ptr(), stats.data_ptr(), frames, Ch, self._stream())
+
+    def ffn_dwconv(self, h, stats1, n1w, n1b, dw_w, dw_b, y, partial2):
+        _chk(h, torch.bfloat16, "h"); _chk(y, torch.bfloat16, "y")
+        for t, n in ((stats1, "stats1"), (n1w, "n1w"), (n1b, "n1b"), (dw_w, "dw_w"), (dw_b, "dw_b"), (partial2, "partial2")):
+            _chk(t, torch.float32, n)
+        frames, Ch = stats1.shape[0], h.shape[-1]
+        assert partial2.shape == (frames, Ch // 256, 2) and dw_w.shape == (9, Ch) and n1w.shape == (64, Ch)
+        self._call("npvp_ffn_dwconv", h.data_ptr(), stats1.data_ptr(), n1w.data_ptr(), n1b.data_ptr(), dw_w.data_ptr(),
+                   dw_b.data_ptr(), y.data_ptr(), partial2.data_ptr(), frames, Ch, self._stream())
+
+    def ffn_norm2(self, y, partial2, n2w, n2b, out):
+        _chk(y, torch.bfloat16, "y"); _chk(out, torch.bfloat16, "out")
+        for t, n in ((partial2, "partial2"), (n2w, "n2w"), (n2b, "n2b")):
+            _chk(t, torch.float32, n)
+        frames, Ch = partial2.shape[0], y.shape[-1]
+        self._call("npvp_ffn_norm2", y.data_ptr(), partial2.data_ptr(), n2w.data_ptr(), n2b.data_ptr(), out.data_ptr(), frames,
+                   Ch, self._stream())
+
+    def attention(self, q, k, v, out, mode, n_clips, Tq, Tk, mask_last=False):
+        for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+            _chk(t, torch.bfloat16, n, False)
+            assert t.shape[1] == 512
+        assert q.shape[0] == n_clips * Tq * 64 and k.shape[0] == n_clips * Tk * 64 and v.shape[0] == k.shape[0]
+        self._call("npvp_attention", q.data_ptr(), _rowmajor(q, "q"), k.data_ptr(), _rowmajor(k, "k"), v.data_ptr(),
+                   _rowmajor(v, "v"), out.data_ptr(), _rowmajor(out, "out"), int(mode), n_clips, int(Tq), int(Tk),
+                   int(bool(mask_last)), self._stream())
+
+    def dwconv3x3_tokens(self, x, w, shift, out, relu=True):
+        _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(shift, torch.float32, "shift"); _chk(out, torch.bfloat16, "out")
+        Cc = x.shape[-1]
+        frames = x.numel() // (64 * Cc)
+        assert w.shape == (9, Cc) and out.numel() == x.numel()
+        self._call("npvp_dwconv3x3_tokens", x.data_ptr(), w.data_ptr(), shift.data_ptr(), out.data_ptr(), frames, Cc, int(relu),
+                   self._stream())
+
+    def latent_reparam(self, mulv, eps_nchw, z, n_clips, Cc):
+        _chk(mulv, torch.float32, "mulv", False); _chk(eps_nchw, torch.float32, "eps"); _chk(z, torch.float32, "z")
+        assert mulv.shape[0] == n_clips * 64 and z.numel() == n_clips * 64 * Cc
+        assert eps_nchw is None or eps_nchw.numel() == z.numel()
+        self._call("npvp_latent_reparam", mulv.data_ptr(), _rowmajor(mulv, "mulv"), _ptr(eps_nchw), z.data_ptr(), n_clips, Cc,
+                   self._stream())
+
+    # -- layouts --------------------------------------------------------------------------------
+    def nchw_to_tokens(self, x, out_f32=None, out_bf16=None):
+        """x: (frames, C, HW) fp32 -> (frames, HW, C)."""
+        _chk(x, torch.float32, "x"); _chk(out_f32, torch.float32, "out_f32"); _chk(out_bf16, torch.bfloat16, "out_bf16")
+        frames, Cc, HW = x.shape
+        self._call("npvp_nchw_to_tokens", x.data_ptr(), _ptr(out_f32), _ptr(out_bf16), frames, Cc, HW, self._stream())
+
+    def tokens_to_nchw(self, x, out, relu=False):
+        """x: (frames, HW, C) fp32 or bf16 -> out (frames, C, HW) fp32."""
+        assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
+        _chk(out, torch.float32, "out")
+        frames, HW, Cc = x.shape
+        xf, xb = (x.data_ptr(), None) if x.dtype == torch.float32 else (None, x.data_ptr())
+        self._call("npvp_tokens_to_nchw", xf, xb, out.data_ptr(), frames, Cc, HW, int(relu), self._stream())
+
+    # -- autoencoder ----------------------------------------------------------------------------
+    def conv7x7_stem(self, x, w, shift, out, Cin, Cout, H, W):
+        _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(shift, torch.float32, "shift"); _chk(out, torch.bfloat16, "out")
+        frames = x.numel() // (Cin * H * W)
+        assert out.numel() == frames * H * W * Cout and w.shape == (49 * Cin, Cout)
+        per = max(1, 65535 // (Cout // 16))
+        for f0 in range(0, frames, per):      # grid.z limit
+            n = min(per, frames - f0)
+            self._call("npvp_conv7x7_stem", x.data_ptr() + f0 * Cin * H * W * 4, w.data_ptr(), shift.data_ptr(),
+                       out.data_ptr() + f0 * H * W * Cout * 2, n, Cin, Cout, H, W, self._stream())
+
+    def conv7x7_head(self, x, w, bias, out, Cin, Cout, H, W, phase_major, act):
+        _chk(x, torch.bfloat16, "x"); _chk(w, torch.float32, "w"); _chk(bias, torch.float32, "bias"); _chk(out, torch.float32, "out")
+        frames = x.numel() // (Cin * H * W)
+        assert out.numel() == frames * Cout * H * W and w.shape == (49 * Cin, Cout)
+        for f0 in range(0, frames, 65535):
+            n = min(65535, frames - f0)
+            self._call("npvp_conv7x7_head", x.data_ptr() + f0 * Cin * H * W * 2, w.data_ptr(), bias.data_ptr(),
+                       out.data_ptr() + f0 * Cout * H * W * 4, n, Cin, Cout, H, W, int(phase_major), int(act), self._stream())
+
+    def im2col(self, x, out, frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo, phase_major=False):
+        _chk(x, torch.bfloat16, "x"); _chk(out, torch.bfloat16, "out")
+        assert x.numel() == frames * H * W * Cc and out.shape == (frames * Ho * Wo, KH * KW * Cc)
+        self._call("npvp_im2col_nhwc", x.data_ptr(), out.data_ptr(), frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo,
+                   int(phase_major), self._stream())
+
+    def maxpool2x2_cols(self, x, col0, Cn, out, frames, H, W):
+        _chk(x, torch.bfloat16, "x", False); _chk(out, torch.bfloat16, "out")
+        assert x.shape[0] == frames * H * W and out.shape == (frames * (H // 2) * (W // 2), Cn)
+        self._call("npvp_maxpool2x2_cols", x.data_ptr(), _rowmajor(x, "x"), col0, Cn, out.data_ptr(), frames, H, W, self._stream())
+
+    def nonlocal_attention(self, q, kv, out, frames, HW, HWk, dq, dv):
+        _chk(q, torch.bfloat16, "q", False); _chk(kv, torch.bfloat16, "kv"); _chk(out, torch.bfloat16, "out")
+        assert q.shape[0] == frames * HW and kv.shape == (frames * HWk, dq + dv) and out.shape == (frames * HW, dv)
+        self._call("npvp_nonlocal_attention", q.data_ptr(), _rowmajor(q, "q"), kv.data_ptr(), out.data_ptr(), frames, HW, HWk, dq,
+                   dv, self._stream())
+
+
+_OPS: Optional[Ops] = None
+
+
+def ops() -> Ops:
+    """The process-wide kernel binding.  Tests may replace it with ``set_ops`` (kernel-spec emulation on CPU)."""
+    global _OPS
+    if _OPS is None:
+        _OPS = Ops()
+    return _OPS
+
+
+def set_ops(obj) -> None:
+    global _OPS
+    _OPS = obj

@@ -1,0 +1,434 @@
+// Dense contractions for the NPVP hot path on sm_100a.
+//
+//   npvp_gemm_bf16 : D[M,N] = A[M,K] * W[N,K]^T, bf16 operands, fp32 accumulate, fused epilogue.
+//       TCGEN05 backend: TMA (cp.async.bulk.tensor, 128B swizzle) -> 3/4-stage smem ring ->
+//       tcgen05.mma (cta_group::1, 128 x BN x 16, one elected issuing thread) -> TMEM accumulator ->
+//       tcgen05.ld epilogue (bias / act / alpha / residuals / relu; fp32 and/or bf16 stores).
+//       SIMT backend: shared-memory tiled CUDA-core kernel with the same epilogue, kept for debugging the
+//       tensor path and for shapes the TMA descriptors cannot express.
+//   npvp_gemm_f32  : fp32 CUDA-core GEMM for the NRMLP positional MLP (precision critical, tiny).
+#include "common.cuh"
+#include <cuda.h>
+
+// =============================================================================================
+// PTX wrappers
+// =============================================================================================
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a lost arrival traps (reported as a CUDA error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 6000000000LL) {   // ~3 s at 2 GHz
+        printf("npvp gemm: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace ptx
+
+// =============================================================================================
+// tcgen05 GEMM kernel
+// =============================================================================================
+// Tile: BLOCK_M = 128 (one UMMA M), BLOCK_N = BN (UMMA N), BLOCK_K = 64 bf16 = one 128-byte swizzle row.
+// smem per stage: A 128x64 bf16 (16 KB) + B BNx64 bf16.  K-major, SWIZZLE_128B (matches the TMA maps).
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5: epilogue
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN >= 256) ? 4 : 3;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;  // power of two >= 32 (BN is 64/128/256)
+};
+
+// Shared-memory matrix descriptor: K-major, 128B swizzle, 8-row groups 1024 B apart (SBO), version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major; canonical 1)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    int64_t M, int64_t N, int64_t K, EpiParams ep) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment required by the 128B swizzle atoms
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::kStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.y, n_blk = blockIdx.x;
+  const int num_k_blocks = (int)((K + kBK - 1) / kBK);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        ptx::tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
+        ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, n_blk * BN);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (one thread) ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint64_t adesc = make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
+        const uint64_t bdesc = make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
+          ptx::umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        ptx::umma_commit(&empty_bar[stage]);     // frees this smem stage when the MMAs have read it
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      ptx::umma_commit(tmem_full_bar);           // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: 4 warps, TMEM lane quadrant = warp % 4 ----------------
+    const int quad = warp & 3;
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    const int64_t m = (int64_t)m_blk * kBM + quad * 32 + lane;
+    const bool row_ok = m < M;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, r);
+      ptx::tmem_ld_wait();
+      const int64_t n0 = (int64_t)n_blk * BN + c;
+      if (row_ok && n0 < N) {
+        if (n0 + 32 <= N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = epi_value(ep, __uint_as_float(r[j]), m, n0 + j);
+          if (ep.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(ep.out_f32 + m * ep.ld_out + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (ep.out_bf16) {
+            uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * ep.ld_out + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          }
+        } else {
+          for (int j = 0; j < 32 && n0 + j < N; ++j) {
+            const float v = epi_value(ep, __uint_as_float(r[j]), m, n0 + j);
+            if (ep.out_f32) ep.out_f32[m * ep.ld_out + n0 + j] = v;
+            if (ep.out_bf16) ep.out_bf16[m * ep.ld_out + n0 + j] = __float2bfloat16(v);
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// =============================================================================================
+// SIMT kernels
+// =============================================================================================
+// 64x64 tile, 16-deep k-slab, 256 threads, 4x4 outputs per thread.  TA in {bf16, float}.
+template <typename TA>
+__device__ __forceinline__ float to_f32(TA v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename TA>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const TA* __restrict__ A, int64_t lda, const TA* __restrict__ W, int64_t ldw, int64_t M, int64_t N,
+                 int64_t K, EpiParams ep) {
+  __shared__ float As[16][64 + 1];
+  __shared__ float Ws[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * 64, n0 = (int64_t)blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int64_t k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, c = i & 15;
+      const int64_t m = m0 + r, n = n0 + r, k = k0 + c;
+      As[c][r] = (m < M && k < K) ? to_f32<TA>(A[m * lda + k]) : 0.0f;
+      Ws[c][r] = (n < N && k < K) ? to_f32<TA>(W[n * ldw + k]) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Ws[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      const float v = epi_value(ep, acc[i][j], m, n);
+      if (ep.out_f32) ep.out_f32[m * ep.ld_out + n] = v;
+      if (ep.out_bf16) ep.out_bf16[m * ep.ld_out + n] = __float2bfloat16(v);
+    }
+  }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner dim = K (contiguous), outer dim = rows; box = 64 x box_rows; 128B swizzle; OOB -> 0.
+static int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { npvp_set_error("cuTensorMapEncodeTiled entry point unavailable"); return NPVP_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { npvp_set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld K=%lld ld=%lld", (int)r, (long long)rows, (long long)K, (long long)ld); return NPVP_ERR_CUDA; }
+  return NPVP_OK;
+}
+
+template <int BN>
+static int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                          const EpiParams& e, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (err != cudaSuccess) { npvp_set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
+    attr_set = true;
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(&ta, A, M, K, lda, kBM);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tb, W, N, K, ldw, BN);
+  if (rc) return rc;
+  NPVP_REQUIRE(ceil_div64(M, kBM) <= 65535, "gemm_tcgen05: M chunk too large");
+  dim3 grid((unsigned)ceil_div64(N, BN), (unsigned)ceil_div64(M, kBM));
+  gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K, e);
+  NPVP_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return NPVP_OK;
+}
+
+static bool tma_compatible(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t K) {
+  return ((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && (lda % 8 == 0) && (ldw % 8 == 0) && (K % 8 == 0);
+}
+
+extern "C" int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                              const npvp_epilogue_t* ep, int backend, void* stream) {
+  NPVP_REQUIRE(A && W && ep, "npvp_gemm_bf16: null pointer");
+  NPVP_REQUIRE(M > 0 && N > 0 && K > 0, "npvp_gemm_bf16: empty problem M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  NPVP_REQUIRE(lda >= K && ldw >= K, "npvp_gemm_bf16: leading dimension smaller than K");
+  NPVP_REQUIRE(ep->out_f32 || ep->out_bf16, "npvp_gemm_bf16: no output buffer");
+  NPVP_REQUIRE(ep->ld_out >= N, "npvp_gemm_bf16: ld_out < N");
+  NPVP_REQUIRE(!(ep->res1 || ep->res2) || ep->ld_res >= N, "npvp_gemm_bf16: ld_res < N");
+  cudaStream_t st = (cudaStream_t)stream;
+  constexpr int64_t kMaxRows = 65535LL * 64;   // grid.y limit of either backend
+  if (M > kMaxRows) {                          // split along M: rows are independent
+    for (int64_t m0 = 0; m0 < M; m0 += kMaxRows) {
+      npvp_epilogue_t sub = *ep;
+      const int64_t rows = (M - m0 < kMaxRows) ? (M - m0) : kMaxRows;
+      if (sub.res1) sub.res1 = (const char*)sub.res1 + m0 * sub.ld_res * (sub.res1_bf16 ? 2 : 4);
+      if (sub.res2) sub.res2 = (const char*)sub.res2 + m0 * sub.ld_res * (sub.res2_bf16 ? 2 : 4);
+      if (sub.out_f32) sub.out_f32 = (char*)sub.out_f32 + m0 * sub.ld_out * 4;
+      if (sub.out_bf16) sub.out_bf16 = (char*)sub.out_bf16 + m0 * sub.ld_out * 2;
+      int rc = npvp_gemm_bf16((const char*)A + m0 * lda * 2, lda, W, ldw, rows, N, K, &sub, backend, stream);
+      if (rc) return rc;
+    }
+    return NPVP_OK;
+  }
+  EpiParams e = make_epi(ep);
+  const bool vec_ok = (ep->ld_out % 8 == 0) && (!ep->out_f32 || (uintptr_t)ep->out_f32 % 16 == 0) &&
+                      (!ep->out_bf16 || (uintptr_t)ep->out_bf16 % 16 == 0);
+  // AUTO: tensor path whenever the TMA boxes (128 x 64 for A, BN x 64 for W) fit inside the operands; tiny problems stay on CUDA cores
+  if (backend == NPVP_GEMM_AUTO)
+    backend = (tma_compatible(A, lda, W, ldw, K) && vec_ok && M >= kBM && N >= 64 && K >= kBK) ? NPVP_GEMM_TCGEN05 : NPVP_GEMM_SIMT;
+  if (backend == NPVP_GEMM_TCGEN05) {
+    NPVP_REQUIRE(tma_compatible(A, lda, W, ldw, K) && vec_ok, "npvp_gemm_bf16: operands not 16-byte aligned / K,ld not multiples of 8 for the TMA path");
+    if (N > 64) return launch_tcgen05<128>(A, lda, W, ldw, M, N, K, e, st);
+    return launch_tcgen05<64>(A, lda, W, ldw, M, N, K, e, st);
+  }
+  NPVP_REQUIRE(backend == NPVP_GEMM_SIMT, "npvp_gemm_bf16: unknown backend %d", backend);
+  dim3 grid((unsigned)ceil_div64(N, 64), (unsigned)ceil_div64(M, 64));
+  gemm_simt_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, e);
+  NPVP_LAUNCH_CHECK("gemm_simt_kernel<bf16>");
+  return NPVP_OK;
+}
+
+extern "C" int npvp_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                             const float* bias, int act, float* out, int64_t ldo, void* stream) {
+  NPVP_REQUIRE(A && W && out, "npvp_gemm_f32: null pointer");
+  NPVP_REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldo >= N, "npvp_gemm_f32: bad shape");
+  EpiParams e = {};
+  e.bias = bias;
+  e.out_f32 = out;
+  e.alpha = 1.0f;
+  e.act = act;
+  e.ld_out = ldo;
+  dim3 grid((unsigned)ceil_div64(N, 64), (unsigned)ceil_div64(M, 64));
+  gemm_simt_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, W, ldw, M, N, K, e);
+  NPVP_LAUNCH_CHECK("gemm_simt_kernel<float>");
+  return NPVP_OK;
+}

@@ -1,0 +1,535 @@
+// Memory-bound kernels of the NP predictor: fused LayerNorm + positional GroupNorm fuse, per-frame
+// LayerNorm(C,8,8)+GELU+residual, the conv-FFN middle (LN -> GELU -> depthwise 3x3 -> LN -> GELU),
+// Fourier features, event-encoder pieces and layout changes.  Geometry is the reference's only one:
+// 8x8 token grid (64 tokens per frame), embed dim C = 512.  All statistics are fp32 (double for the
+// final mean/variance combine); bf16 is used only for buffers that feed tensor-core GEMMs.
+#include "common.cuh"
+
+constexpr int kC = 512;       // embed dim
+constexpr int kTok = 64;      // tokens per frame (8x8)
+constexpr float kEps = 1e-5f;
+
+// thread layout used by the per-frame kernels: 512 threads = 16 warps, warp w owns tokens 4w..4w+3,
+// lane l owns channels {128*j + 4*l + i}: one float4 per j => fully coalesced 512-byte warp accesses.
+struct FrameRegs { float v[4][16]; };
+
+__device__ __forceinline__ void frame_load(const float* __restrict__ x, FrameRegs& r, int warp, int lane) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float4* row = reinterpret_cast<const float4*>(x + (size_t)(warp * 4 + t) * kC);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 q = __ldg(row + j * 32 + lane);
+      r.v[t][4 * j + 0] = q.x; r.v[t][4 * j + 1] = q.y; r.v[t][4 * j + 2] = q.z; r.v[t][4 * j + 3] = q.w;
+    }
+  }
+}
+
+__device__ __forceinline__ void frame_store_bf16(bf16* __restrict__ out, const FrameRegs& r, int warp, int lane) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    uint2* row = reinterpret_cast<uint2*>(out + (size_t)(warp * 4 + t) * kC);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      row[j * 32 + lane] = make_uint2(pack_bf16x2(r.v[t][4 * j], r.v[t][4 * j + 1]), pack_bf16x2(r.v[t][4 * j + 2], r.v[t][4 * j + 3]));
+  }
+}
+
+// per-token LayerNorm over 512 channels held as 16 values per lane
+__device__ __forceinline__ void token_layernorm(float (&v)[16], const float4 (&w)[4], const float4 (&b)[4]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  const float mu = warp_sum(s) * (1.0f / kC);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { const float d = v[i] - mu; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / kC) + kEps);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[4 * j + 0] = (v[4 * j + 0] - mu) * rstd * w[j].x + b[j].x;
+    v[4 * j + 1] = (v[4 * j + 1] - mu) * rstd * w[j].y + b[j].y;
+    v[4 * j + 2] = (v[4 * j + 2] - mu) * rstd * w[j].z + b[j].z;
+    v[4 * j + 3] = (v[4 * j + 3] - mu) * rstd * w[j].w + b[j].w;
+  }
+}
+
+// two-pass mean / rstd over the whole frame held in registers by 512 threads
+__device__ __forceinline__ void frame_stats(const FrameRegs& r, float* red, float& mean, float& rstd) {
+  float s = 0.f, dummy = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += r.v[t][i];
+  block_sum2(s, dummy, red);
+  mean = s * (1.0f / (kTok * kC));
+  float q = 0.f;
+  dummy = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float d = r.v[t][i] - mean; q = fmaf(d, d, q); }
+  block_sum2(q, dummy, red);
+  rstd = rsqrtf(q * (1.0f / (kTok * kC)) + kEps);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a = LN(x); u = a + qe; fused = GN1(u) * (1 + gamma) + beta
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+ln_posfuse_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                  const float* __restrict__ qe, const float* __restrict__ beta, const float* __restrict__ gamma,
+                  bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int T) {
+  __shared__ float red[64];
+  const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = f / T, t_idx = f % T;
+  FrameRegs r;
+  frame_load(x + (size_t)f * kTok * kC, r, warp, lane);
+  if (ln_w) {
+    float4 w[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      w[j] = __ldg(reinterpret_cast<const float4*>(ln_w) + j * 32 + lane);
+      b[j] = __ldg(reinterpret_cast<const float4*>(ln_b) + j * 32 + lane);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) token_layernorm(r.v[t], w, b);
+  }
+  if (out_ln) frame_store_bf16(out_ln + (size_t)f * kTok * kC, r, warp, lane);
+  if (!out_fused) return;
+  if (qe) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float4* row = reinterpret_cast<const float4*>(qe + ((size_t)n * kTok + warp * 4 + t) * kC);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 q = __ldg(row + j * 32 + lane);
+        r.v[t][4 * j] += q.x; r.v[t][4 * j + 1] += q.y; r.v[t][4 * j + 2] += q.z; r.v[t][4 * j + 3] += q.w;
+      }
+    }
+  }
+  float mean, rstd;
+  frame_stats(r, red, mean, rstd);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const size_t off = ((size_t)t_idx * kTok + warp * 4 + t) * kC;
+    const float4* brow = reinterpret_cast<const float4*>(beta + off);
+    const float4* grow = gamma ? reinterpret_cast<const float4*>(gamma + off) : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 be = __ldg(brow + j * 32 + lane);
+      float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (grow) ga = __ldg(grow + j * 32 + lane);
+      r.v[t][4 * j + 0] = (r.v[t][4 * j + 0] - mean) * rstd * (1.0f + ga.x) + be.x;
+      r.v[t][4 * j + 1] = (r.v[t][4 * j + 1] - mean) * rstd * (1.0f + ga.y) + be.y;
+      r.v[t][4 * j + 2] = (r.v[t][4 * j + 2] - mean) * rstd * (1.0f + ga.z) + be.z;
+      r.v[t][4 * j + 3] = (r.v[t][4 * j + 3] - mean) * rstd * (1.0f + ga.w) + be.w;
+    }
+  }
+  frame_store_bf16(out_fused + (size_t)f * kTok * kC, r, warp, lane);
+}
+
+extern "C" int npvp_ln_posfuse(const float* x, const float* ln_w, const float* ln_b, const float* qe, const float* beta,
+                               const float* gamma, void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T,
+                               void* stream) {
+  NPVP_REQUIRE(x && (out_ln_bf16 || out_fused_bf16), "npvp_ln_posfuse: null pointer");
+  NPVP_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "npvp_ln_posfuse: ln_w/ln_b must both be set or both NULL");
+  NPVP_REQUIRE(!out_fused_bf16 || beta, "npvp_ln_posfuse: beta required for the fused output");
+  NPVP_REQUIRE(n_clips > 0 && T > 0, "npvp_ln_posfuse: empty input");
+  ln_posfuse_kernel<<<(unsigned)(n_clips * T), 512, 0, (cudaStream_t)stream>>>(x, ln_w, ln_b, qe, beta, gamma, (bf16*)out_ln_bf16,
+                                                                              (bf16*)out_fused_bf16, (int)T);
+  NPVP_LAUNCH_CHECK("ln_posfuse_kernel");
+  return NPVP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm(512) per token: one warp per row
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                      float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int64_t rows, int relu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[16];
+  float4 wv[4], bv[4];
+  const float4* src = reinterpret_cast<const float4*>(x + row * kC);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 q = __ldg(src + j * 32 + lane);
+    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+    wv[j] = __ldg(reinterpret_cast<const float4*>(w) + j * 32 + lane);
+    bv[j] = __ldg(reinterpret_cast<const float4*>(b) + j * 32 + lane);
+  }
+  token_layernorm(v, wv, bv);
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + row * kC)[j * 32 + lane] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    if (out_bf16) reinterpret_cast<uint2*>(out_bf16 + row * kC)[j * 32 + lane] = make_uint2(pack_bf16x2(v[4 * j], v[4 * j + 1]), pack_bf16x2(v[4 * j + 2], v[4 * j + 3]));
+  }
+}
+
+extern "C" int npvp_layernorm_rows(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16,
+                                   int64_t rows, int relu, void* stream) {
+  NPVP_REQUIRE(x && w && b && (out_f32 || out_bf16) && rows > 0, "npvp_layernorm_rows: bad arguments");
+  layernorm_rows_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, w, b, out_f32, (bf16*)out_bf16, rows, relu);
+  NPVP_LAUNCH_CHECK("layernorm_rows_kernel");
+  return NPVP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// y += GELU(LayerNorm_(C,8,8)(h) * w + b)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+frame_ln_gelu_residual_kernel(const float* __restrict__ h, const float* __restrict__ w_hwc, const float* __restrict__ b_hwc,
+                              float* __restrict__ y) {
+  __shared__ float red[64];
+  const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  FrameRegs r;
+  frame_load(h + (size_t)f * kTok * kC, r, warp, lane);
+  float mean, rstd;
+  frame_stats(r, red, mean, rstd);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const size_t tok = warp * 4 + t;
+    const float4* wrow = reinterpret_cast<const float4*>(w_hwc + tok * kC);
+    const float4* brow = reinterpret_cast<const float4*>(b_hwc + tok * kC);
+    float4* yrow = reinterpret_cast<float4*>(y + ((size_t)f * kTok + tok) * kC);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 ww = __ldg(wrow + j * 32 + lane), bb = __ldg(brow + j * 32 + lane);
+      float4 yy = yrow[j * 32 + lane];
+      yy.x += gelu_erf((r.v[t][4 * j + 0] - mean) * rstd * ww.x + bb.x);
+      yy.y += gelu_erf((r.v[t][4 * j + 1] - mean) * rstd * ww.y + bb.y);
+      yy.z += gelu_erf((r.v[t][4 * j + 2] - mean) * rstd * ww.z + bb.z);
+      yy.w += gelu_erf((r.v[t][4 * j + 3] - mean) * rstd * ww.w + bb.w);
+      yrow[j * 32 + lane] = yy;
+    }
+  }
+}
+
+extern "C" int npvp_frame_ln_gelu_residual(const float* h, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,
+                                           void* stream) {
+  NPVP_REQUIRE(h && w_hwc && b_hwc && y && frames > 0, "npvp_frame_ln_gelu_residual: bad arguments");
+  frame_ln_gelu_residual_kernel<<<(unsigned)frames, 512, 0, (cudaStream_t)stream>>>(h, w_hwc, b_hwc, y);
+  NPVP_LAUNCH_CHECK("frame_ln_gelu_residual_kernel");
+  return NPVP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// temporal mean of the memory
+// ---------------------------------------------------------------------------------------------
+__global__ void temporal_mean_kernel(const float4* __restrict__ mem, float4* __restrict__ evt, int64_t n_clips, int T, int64_t fe4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_clips * fe4) return;
+  const int64_t n = i / fe4, e = i % fe4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < T; ++t) {
+    const float4 q = __ldg(mem + (n * T + t) * fe4 + e);
+    s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+  }
+  const float inv = 1.0f / (float)T;
+  evt[i] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+}
+
+extern "C" int npvp_temporal_mean(const float* mem, float* evt, int64_t n_clips, int64_t T, int64_t frame_elems, void* stream) {
+  NPVP_REQUIRE(mem && evt && n_clips > 0 && T > 0 && frame_elems % 4 == 0, "npvp_temporal_mean: bad arguments");
+  const int64_t total = n_clips * (frame_elems / 4);
+  temporal_mean_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)mem, (float4*)evt, n_clips, (int)T, frame_elems / 4);
+  NPVP_LAUNCH_CHECK("temporal_mean_kernel");
+  return NPVP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv-FFN middle
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ffn_frame_stats_kernel(const bf16* __restrict__ h, float* __restrict__ stats, int64_t elems) {
+  __shared__ float red[64];
+  const uint4* src = reinterpret_cast<const uint4*>(h + (size_t)blockIdx.x * elems);
+  float s = 0.f, q = 0.f;
+  for (int64_t i = threadIdx.x; i < elems / 8; i += 256) {
+    const uint4 u = __ldg(src + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 p = unpack_bf16x2(w[k]);
+      s += p.x + p.y;
+      q = fmaf(p.x, p.x, q);
+      q = fmaf(p.y, p.y, q);
+    }
+  }
+  block_sum2(s, q, red);
+  if (threadIdx.x == 0) {
+    const double mean = (double)s / (double)elems;
+    const double var = fmax((double)q / (double)elems - mean * mean, 0.0);
+    stats[2 * blockIdx.x] = (float)mean;
+    stats[2 * blockIdx.x + 1] = (float)(1.0 / sqrt(var + (double)kEps));
+  }
+}
+
+extern "C" int npvp_ffn_frame_stats(const void* h_bf16, float* stats, int64_t frames, int64_t Ch, void* stream) {
+  NPVP_REQUIRE(h_bf16 && stats && frames > 0 && Ch % 8 == 0, "npvp_ffn_frame_stats: bad arguments");
+  ffn_frame_stats_kernel<<<(unsigned)frames, 256, 0, (cudaStream_t)stream>>>((const bf16*)h_bf16, stats, kTok * Ch);
+  NPVP_LAUNCH_CHECK("ffn_frame_stats_kernel");
+  return NPVP_OK;
+}
+
+// depthwise 3x3, zero padding 1, on an 8x8 map held in registers (a[p], p = y*8+x); taps w[ky*3+kx]
+__device__ __forceinline__ float dw3x3_at(const float (&a)[64], const float (&w)[9], int y, int x) {
+  float acc = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy > 7) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = x + kx - 1;
+      if (xx < 0 || xx > 7) continue;
+      acc = fmaf(a[yy * 8 + xx], w[ky * 3 + kx], acc);
+    }
+  }
+  return acc;
+}
+
+// one thread per channel: normalise + GELU the 8x8 map, depthwise conv, write bf16, per-block partial stats
+__global__ void __launch_bounds__(256)
+ffn_dwconv_kernel(const bf16* __restrict__ h, const float* __restrict__ stats1, const float* __restrict__ n1w,
+                  const float* __restrict__ n1b, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                  bf16* __restrict__ y, float* __restrict__ partial2, int Ch) {
+  __shared__ float red[64];
+  const int f = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+  const float mean = __ldg(stats1 + 2 * f), rstd = __ldg(stats1 + 2 * f + 1);
+  float a[64];
+  const bf16* src = h + (size_t)f * kTok * Ch + c;
+#pragma unroll
+  for (int p = 0; p < 64; ++p) {
+    const float v = __bfloat162float(src[(size_t)p * Ch]);
+    a[p] = gelu_erf((v - mean) * rstd * __ldg(n1w + (size_t)p * Ch + c) + __ldg(n1b + (size_t)p * Ch + c));
+  }
+  float w[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w[k] = __ldg(dw_w + (size_t)k * Ch + c);
+  const float bias = __ldg(dw_b + c);
+  bf16* dst = y + (size_t)f * kTok * Ch + c;
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int yy = 0; yy < 8; ++yy)
+#pragma unroll
+    for (int xx = 0; xx < 8; ++xx) {
+      const float o = dw3x3_at(a, w, yy, xx) + bias;
+      const bf16 ob = __float2bfloat16(o);
+      dst[(size_t)(yy * 8 + xx) * Ch] = ob;
+      const float orr = __bfloat162float(ob);   // statistics of what the consumer will actually read
+      s += orr;
+      q = fmaf(orr, orr, q);
+    }
+  block_sum2(s, q, red);
+  if (threadIdx.x == 0) {
+    float* p = partial2 + ((size_t)f * gridDim.x + blockIdx.x) * 2;
+    p[0] = s;
+    p[1] = q;
+  }
+}
+
+extern "C" int npvp_ffn_dwconv(const void* h_bf16, const float* stats1, const float* n1w, const float* n1b, const float* dw_w,
+                               const float* dw_b, void* y_bf16, float* partial2, int64_t frames, int64_t Ch, void* stream) {
+  NPVP_REQUIRE(h_bf16 && stats1 && n1w && n1b && dw_w && dw_b && y_bf16 && partial2, "npvp_ffn_dwconv: null pointer");
+  NPVP_REQUIRE(frames > 0 && frames <= 65535 && Ch % 256 == 0, "npvp_ffn_dwconv: frames in (0,65535], Ch multiple of 256");
+  dim3 grid((unsigned)(Ch / 256), (unsigned)frames);
+  ffn_dwconv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)h_bf16, stats1, n1w, n1b, dw_w, dw_b, (bf16*)y_bf16, partial2, (int)Ch);
+  NPVP_LAUNCH_CHECK("ffn_dwconv_kernel");
+  return NPVP_OK;
+}
+
+// out = GELU(LN2(y)); block = (frame, 8-pixel group); thread handles 8 channels per pixel
+__global__ void __launch_bounds__(256)
+ffn_norm2_kernel(const bf16* __restrict__ y, const float* __restrict__ partial2, int nchunk, const float* __restrict__ n2w,
+                 const float* __restrict__ n2b, bf16* __restrict__ out, int Ch) {
+  const int f = blockIdx.y;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < nchunk; ++k) {
+    s += (double)__ldg(partial2 + ((size_t)f * nchunk + k) * 2);
+    q += (double)__ldg(partial2 + ((size_t)f * nchunk + k) * 2 + 1);
+  }
+  const double n = (double)kTok * (double)Ch;
+  const double mean_d = s / n;
+  const float mean = (float)mean_d;
+  const float rstd = (float)(1.0 / sqrt(fmax(q / n - mean_d * mean_d, 0.0) + (double)kEps));
+  const int vec_per_px = Ch / 8;
+  for (int i = threadIdx.x; i < 8 * vec_per_px; i += 256) {
+    const int p = blockIdx.x * 8 + i / vec_per_px, cv = i % vec_per_px;
+    const size_t off = ((size_t)f * kTok + p) * Ch + (size_t)cv * 8;
+    const size_t aoff = (size_t)p * Ch + (size_t)cv * 8;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(y + off));
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(n2w + aoff)), w1 = __ldg(reinterpret_cast<const float4*>(n2w + aoff + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(n2b + aoff)), b1 = __ldg(reinterpret_cast<const float4*>(n2b + aoff + 4));
+    const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+    uint4 o;
+    o.x = pack_bf16x2(gelu_erf((p0.x - mean) * rstd * w0.x + b0.x), gelu_erf((p0.y - mean) * rstd * w0.y + b0.y));
+    o.y = pack_bf16x2(gelu_erf((p1.x - mean) * rstd * w0.z + b0.z), gelu_erf((p1.y - mean) * rstd * w0.w + b0.w));
+    o.z = pack_bf16x2(gelu_erf((p2.x - mean) * rstd * w1.x + b1.x), gelu_erf((p2.y - mean) * rstd * w1.y + b1.y));
+    o.w = pack_bf16x2(gelu_erf((p3.x - mean) * rstd * w1.z + b1.z), gelu_erf((p3.y - mean) * rstd * w1.w + b1.w));
+    *reinterpret_cast<uint4*>(out + off) = o;
+  }
+}
+
+extern "C" int npvp_ffn_norm2(const void* y_bf16, const float* partial2, const float* n2w, const float* n2b, void* out_bf16,
+                              int64_t frames, int64_t Ch, void* stream) {
+  NPVP_REQUIRE(y_bf16 && partial2 && n2w && n2b && out_bf16, "npvp_ffn_norm2: null pointer");
+  NPVP_REQUIRE(frames > 0 && frames <= 65535 && Ch % 256 == 0, "npvp_ffn_norm2: frames in (0,65535], Ch multiple of 256");
+  dim3 grid(8, (unsigned)frames);
+  ffn_norm2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y_bf16, partial2, (int)(Ch / 256), n2w, n2b, (bf16*)out_bf16, (int)Ch);
+  NPVP_LAUNCH_CHECK("ffn_norm2_kernel");
+  return NPVP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fourier features
+// ---------------------------------------------------------------------------------------------
+__global__ void fourier_features_kernel(const float* __restrict__ coor, const float* __restrict__ B, float* __restrict__ out,
+                                        int64_t rows, int half) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * half) return;
+  const int64_t r = i / half;
+  const int j = (int)(i % half);
+  const float two_pi = 2.0f * 3.14159265358979323846f;   // matches 2. * float(math.pi) rounded to fp32 operands
+  const float x0 = two_pi * coor[r * 3], x1 = two_pi * coor[r * 3 + 1], x2 = two_pi * coor[r * 3 + 2];
+  float p = x0 * B[j * 3];
+  p = fmaf(x1, B[j * 3 + 1], p);
+  p = fmaf(x2, B[j * 3 + 2], p);
+  out[r * 2 * half + j] = cosf(p);
+  out[r * 2 * half + half + j] = sinf(p);
+}
+
+extern "C" int npvp_fourier_features(const float* coor, const float* B, float* out, int64_t rows, int half, void* stream) {
+  NPVP_REQUIRE(coor && B && out && rows > 0 && half > 0, "npvp_fourier_features: bad arguments");
+  fourier_features_kernel<<<(unsigned)ceil_div64(rows * half, 256), 256, 0, (cudaStream_t)stream>>>(coor, B, out, rows, half);
+  NPVP_LAUNCH_CHECK("fourier_features_kernel");
+  return NPVP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// event encoder pieces
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dwconv3x3_tokens_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
+                        bf16* __restrict__ out, int C, int relu) {
+  const int f = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float a[64], wk[9];
+  const float* src = x + (size_t)f * kTok * C + c;
+#pragma unroll
+  for (int p = 0; p < 64; ++p) a[p] = __ldg(src + (size_t)p * C);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wk[k] = __ldg(w + (size_t)k * C + c);
+  const float sh = __ldg(shift + c);
+  bf16* dst = out + (size_t)f * kTok * C + c;
+#pragma unroll
+  for (int yy = 0; yy < 8; ++yy)
+#pragma unroll
+    for (int xx = 0; xx < 8; ++xx) {
+      float o = dw3x3_at(a, wk, yy, xx) + sh;
+      if (relu) o = fmaxf(o, 0.f);
+      dst[(size_t)(yy * 8 + xx) * C] = __float2bfloat16(o);
+    }
+}
+
+extern "C" int npvp_dwconv3x3_tokens(const float* x, const float* w, const float* shift, void* out_bf16, int64_t frames,
+                                     int64_t C, int relu, void* stream) {
+  NPVP_REQUIRE(x && w && shift && out_bf16 && frames > 0 && frames <= 65535 && C > 0, "npvp_dwconv3x3_tokens: bad arguments");
+  dim3 grid((unsigned)ceil_div64(C, 256), (unsigned)frames);
+  dwconv3x3_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, shift, (bf16*)out_bf16, (int)C, relu);
+  NPVP_LAUNCH_CHECK("dwconv3x3_tokens_kernel");
+  return NPVP_OK;
+}
+
+__global__ void latent_reparam_kernel(const float* __restrict__ mulv, int64_t ld, const float* __restrict__ eps,
+                                      float* __restrict__ z, int64_t n_clips, int C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_clips * kTok * C) return;
+  const int c = (int)(i % C);
+  const int64_t tok = i / C;           // n*64 + p
+  const int64_t n = tok / kTok;
+  const int p = (int)(tok % kTok);
+  const float mu = mulv[tok * ld + c];
+  float v = mu;
+  if (eps) {
+    const float lv = mulv[tok * ld + C + c];
+    v = fmaf(expf(0.5f * lv), eps[(n * C + c) * kTok + p], mu);
+  }
+  z[i] = v;
+}
+
+extern "C" int npvp_latent_reparam(const float* mulv, int64_t ld, const float* eps_nchw, float* z, int64_t n_clips, int64_t C,
+                                   void* stream) {
+  NPVP_REQUIRE(mulv && z && n_clips > 0 && C > 0 && ld >= (eps_nchw ? 2 * C : C), "npvp_latent_reparam: bad arguments");
+  const int64_t total = n_clips * kTok * C;
+  latent_reparam_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(mulv, ld, eps_nchw, z, n_clips, (int)C);
+  NPVP_LAUNCH_CHECK("latent_reparam_kernel");
+  return NPVP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout changes: per frame [C, HW] <-> [HW, C] through 32x32 smem tiles
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nchw_to_tokens_kernel(const float* __restrict__ x, float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int C, int HW) {
+  __shared__ float tile[32][33];
+  const size_t base = (size_t)blockIdx.z * C * HW;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    tile[r][tx] = (c < C && p < HW) ? __ldg(x + base + (size_t)c * HW + p) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    if (p < HW && c < C) {
+      const float v = tile[tx][r];
+      if (out_f32) out_f32[base + (size_t)p * C + c] = v;
+      if (out_bf16) out_bf16[base + (size_t)p * C + c] = __float2bfloat16(v);
+    }
+  }
+}
+
+extern "C" int npvp_nchw_to_tokens(const float* x, float* out_f32, void* out_bf16, int64_t frames, int64_t C, int64_t HW, void* stream) {
+  NPVP_REQUIRE(x && (out_f32 || out_bf16) && frames > 0 && frames <= 65535 && C > 0 && HW > 0, "npvp_nchw_to_tokens: bad arguments");
+  dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)ceil_div64(C, 32), (unsigned)frames);
+  nchw_to_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out_f32, (bf16*)out_bf16, (int)C, (int)HW);
+  NPVP_LAUNCH_CHECK("nchw_to_tokens_kernel");
+  return NPVP_OK;
+}
+
+__global__ void __launch_bounds__(256)
+tokens_to_nchw_kernel(const float* __restrict__ x_f32, const bf16* __restrict__ x_bf16, float* __restrict__ out, int C, int HW, int relu) {
+  __shared__ float tile[32][33];
+  const size_t base = (size_t)blockIdx.z * C * HW;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    float v = 0.f;
+    if (p < HW && c < C) v = x_f32 ? __ldg(x_f32 + base + (size_t)p * C + c) : __bfloat162float(x_bf16[base + (size_t)p * C + c]);
+    tile[r][tx] = relu ? fmaxf(v, 0.f) : v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    if (c < C && p < HW) out[base + (size_t)c * HW + p] = tile[tx][r];
+  }
+}
+
+extern "C" int npvp_tokens_to_nchw(const float* x_f32, const void* x_bf16, float* out, int64_t frames, int64_t C, int64_t HW,
+                                   int relu, void* stream) {
+  NPVP_REQUIRE((x_f32 || x_bf16) && out && frames > 0 && frames <= 65535 && C > 0 && HW > 0, "npvp_tokens_to_nchw: bad arguments");
+  dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)ceil_div64(C, 32), (unsigned)frames);
+  tokens_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_f32, (const bf16*)x_bf16, out, (int)C, (int)HW, relu);
+  NPVP_LAUNCH_CHECK("tokens_to_nchw_kernel");
+  return NPVP_OK;
+}

@@ -1,0 +1,344 @@
+"""Host-side driver of the NP predictor: packs the module's weights once and sequences the sm_100a kernels.
+
+Data layout in HBM (per forward, N clips, T frames, 64 tokens/frame, C = 512):
+  * residual streams  fp32  [N*T*64, 512]      (token-major, channels-last; never leaves fp32)
+  * GEMM operands     bf16  [N*T*64, 512|1024|2048]
+  * positional code   fp32  beta/gamma [T*64, 512]  (batch independent, from the NRMLP kernels)
+  * per-frame stats   fp32  [frames, 2] / [frames, 8, 2]
+Weights are packed at first use (and re-packed when any parameter's version changes):
+bf16 [out, in] matrices for the tensor-core GEMMs, fp32 biases / LayerNorm affines, the (C,8,8)
+LayerNorm affines transposed to token-major [64, C], depthwise taps as [9, C], BatchNorm folded.
+
+Reference call graph being reproduced: models/Predictor.py:301-350 -> models/VidHRFormer.py:25-52,
+79-116, 126-161, 198-245 (see SURVEY.md Appendix A for the math).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ATTN_SPATIAL, ATTN_TEMPORAL, PAD_ZERO
+from .workspace import Workspace
+
+C = 512
+TOK = 64
+
+
+def _bf(t):
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def _f(t):
+    return t.detach().float().contiguous()
+
+
+def _bn_fold(bn):
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale, shift
+
+
+def _chw_affine(ln):
+    """LayerNorm((C,8,8)) elementwise affine -> token-major [64, C]."""
+    w = ln.weight.detach().float().permute(1, 2, 0).reshape(TOK, -1).contiguous()
+    b = ln.bias.detach().float().permute(1, 2, 0).reshape(TOK, -1).contiguous()
+    return w, b
+
+
+class _MHA:
+    """Packed nn.MultiheadAttention weights: q|k fused [1024,512] (same source), v [512,512], out [512,512]."""
+
+    def __init__(self, mha, split_q=False):
+        W, b = mha.in_proj_weight.detach(), mha.in_proj_bias.detach()
+        if split_q:      # encoder-decoder attention: q, k, v all read different sources
+            self.wq, self.bq = _bf(W[:C]), _f(b[:C])
+            self.wk, self.bk = _bf(W[C:2 * C]), _f(b[C:2 * C])
+        else:
+            self.wqk, self.bqk = _bf(W[:2 * C]), _f(b[:2 * C])
+        self.wv, self.bv = _bf(W[2 * C:]), _f(b[2 * C:])
+        self.wo, self.bo = _bf(mha.out_proj.weight), _f(mha.out_proj.bias)
+
+
+class _ConvFFN:
+    def __init__(self, m):
+        hid = m.fc1.weight.shape[0]
+        self.hid = hid
+        self.w1, self.b1 = _bf(m.fc1.weight.reshape(hid, C)), _f(m.fc1.bias)
+        self.n1w, self.n1b = _chw_affine(m.norm1)
+        self.dw_w = _f(m.dw3x3.weight.reshape(hid, 9).t())
+        self.dw_b = _f(m.dw3x3.bias)
+        self.n2w, self.n2b = _chw_affine(m.norm2)
+        self.w2, self.b2 = _bf(m.fc2.weight.reshape(-1, hid)), _f(m.fc2.bias)
+        self.n3w, self.n3b = _chw_affine(m.norm3)
+
+
+class _LN:
+    def __init__(self, ln):
+        self.w, self.b = _f(ln.weight), _f(ln.bias)
+
+
+class _EncLayer:
+    def __init__(self, blk):
+        self.attn_s = _MHA(blk.SLMHSA.attn)
+        self.ffn_s = _ConvFFN(blk.SpatialFFN)
+        self.attn_t = _MHA(blk.temporal_MHSA)
+        self.n1, self.n2, self.n3, self.n4 = _LN(blk.norm1), _LN(blk.norm2), _LN(blk.norm3), _LN(blk.norm4)
+        self.l1w, self.l1b = _bf(blk.linear1.weight), _f(blk.linear1.bias)
+        self.l2w, self.l2b = _bf(blk.linear2.weight), _f(blk.linear2.bias)
+
+
+class _DecLayer(_EncLayer):
+    def __init__(self, blk):
+        super().__init__(blk)
+        self.attn_x = _MHA(blk.EncDecAttn, split_q=True)
+        self.ffn_x = _ConvFFN(blk.SpatialFFN1)
+        self.n5, self.n6 = _LN(blk.norm5), _LN(blk.norm6)
+
+
+class _EventEnc:
+    def __init__(self, m, stochastic):
+        s1, sh1 = _bn_fold(m.conv1[1])
+        self.dw_w = (m.conv1[0].weight.detach().float().reshape(C, 9) * s1[:, None]).t().contiguous()   # [9, C]
+        self.dw_shift = sh1.contiguous()
+        s2, sh2 = _bn_fold(m.conv2[1])
+        w2 = m.conv2[0].weight.detach().float() * s2[:, None, None, None]                                # [256,512,3,3]
+        self.w2 = _bf(w2.permute(0, 2, 3, 1).reshape(w2.shape[0], -1))                                  # [(ky,kx,ci)]
+        self.b2 = sh2.contiguous()
+        s3, sh3 = _bn_fold(m.MLP_0[1])
+        self.w3 = _bf(m.MLP_0[0].weight.detach().float().reshape(s3.numel(), -1) * s3[:, None])
+        self.b3 = sh3.contiguous()
+        ws, bs = [m.mu_net.weight.detach().float().reshape(C, -1)], [m.mu_net.bias.detach().float()]
+        if stochastic:
+            ws.append(m.logvar_net.weight.detach().float().reshape(C, -1))
+            bs.append(m.logvar_net.bias.detach().float())
+        self.w_head, self.b_head = _bf(torch.cat(ws, 0)), torch.cat(bs, 0).contiguous()
+        self.hidden = self.w3.shape[0]
+        self.stochastic = stochastic
+
+
+class PredictorEngine:
+    def __init__(self, mod):
+        self.mod = mod
+        dev = next(mod.parameters()).device
+        self.device = dev
+        self.ws = Workspace(dev)
+        self.stochastic = bool(mod.stochastic)
+        self.enc_layers = [_EncLayer(b) for b in mod.EVT_Former.layers]
+        self.dec_layers = [_DecLayer(b) for b in mod.transformer.layers]
+        self.norm_enc = _LN(mod.EVT_Former.norm)
+        self.norm_dec = _LN(mod.transformer.norm)
+        latent = mod.evt_prior if self.stochastic else mod.evt_posterior      # Predictor.py:310 / :330
+        self.evt = _EventEnc(latent, self.stochastic)
+        nr = mod.nrmlp
+        self.nr_B = _f(nr.B)
+        self.nr_mlp = [(_f(l.weight), _f(l.bias)) for l in nr.linears()]
+        self.nr_beta = (_f(nr.mlp_beta.weight), _f(nr.mlp_beta.bias))
+        self.nr_gamma = (_f(nr.mlp_gamma.weight), _f(nr.mlp_gamma.bias)) if nr.fuse_method == 'SPADE' else None
+
+    # ------------------------------------------------------------------------------------------
+    # positional code
+    # ------------------------------------------------------------------------------------------
+    def positional(self, coor, tag):
+        """NRMLP (submodules.py:299-327): coor fp32 [R,3] -> (beta [R,512], gamma [R,512] | None)."""
+        op, ws = _lib.ops(), self.ws
+        coor = coor.detach().to(self.device, torch.float32).contiguous()
+        R = coor.shape[0]
+        half = self.nr_B.shape[0]
+        cur = ws.f32(f"nr_ff_{tag}", R, 2 * half)
+        op.fourier_features(coor, self.nr_B, cur)
+        for i, (w, b) in enumerate(self.nr_mlp):
+            nxt = ws.f32(f"nr_h{i}_{tag}", R, w.shape[0])
+            op.gemm_f32(cur, w, b, ACT_RELU, nxt)
+            cur = nxt
+        beta = ws.f32(f"nr_beta_{tag}", R, C)
+        op.gemm_f32(cur, self.nr_beta[0], self.nr_beta[1], ACT_NONE, beta)
+        gamma = None
+        if self.nr_gamma is not None:
+            gamma = ws.f32(f"nr_gamma_{tag}", R, C)
+            op.gemm_f32(cur, self.nr_gamma[0], self.nr_gamma[1], ACT_NONE, gamma)
+        return beta, gamma
+
+    # ------------------------------------------------------------------------------------------
+    # building blocks (x: fp32 residual stream [M,512], updated in place)
+    # ------------------------------------------------------------------------------------------
+    def _self_attention(self, x, a_bf, f_bf, w: _MHA, mode, n, T, mask_last, tag):
+        op, ws = _lib.ops(), self.ws
+        M = x.shape[0]
+        qk = ws.bf16(f"qk_{tag}", M, 2 * C)
+        v = ws.bf16(f"v_{tag}", M, C)
+        o = ws.bf16(f"o_{tag}", M, C)
+        op.gemm(f_bf, w.wqk, bias=w.bqk, out_bf16=qk)
+        op.gemm(a_bf, w.wv, bias=w.bv, out_bf16=v)
+        op.attention(qk[:, :C], qk[:, C:], v, o, mode, n, T, T, mask_last)
+        op.gemm(o, w.wo, bias=w.bo, res1=x, out_f32=x)
+
+    def _conv_ffn(self, x, a_bf, w: _ConvFFN, frames, tag):
+        """x += MlpDWBN(a)  (VidHRFormer.py:374-392)."""
+        op, ws = _lib.ops(), self.ws
+        M = x.shape[0]
+        h1 = ws.bf16(f"h1_{tag}", M, w.hid)
+        y2 = ws.bf16(f"y2_{tag}", M, w.hid)
+        h3 = ws.f32(f"h3_{tag}", M, C)
+        st1 = ws.f32(f"st1_{tag}", frames, 2)
+        pt2 = ws.f32(f"pt2_{tag}", frames, w.hid // 256, 2)
+        op.gemm(a_bf, w.w1, bias=w.b1, out_bf16=h1)
+        op.ffn_frame_stats(h1, st1)
+        op.ffn_dwconv(h1, st1, w.n1w, w.n1b, w.dw_w, w.dw_b, y2, pt2)
+        op.ffn_norm2(y2, pt2, w.n2w, w.n2b, h1)                 # h1 is dead: reuse it for GELU(LN2(.))
+        op.gemm(h1, w.w2, bias=w.b2, out_f32=h3)
+        op.frame_ln_gelu_residual(h3, w.n3w, w.n3b, x)
+
+    def _mlp_ffn(self, x, a_bf, L, tag):
+        op, ws = _lib.ops(), self.ws
+        f1 = ws.bf16(f"f1_{tag}", x.shape[0], L.l1w.shape[0])
+        op.gemm(a_bf, L.l1w, bias=L.l1b, act=ACT_GELU, out_bf16=f1)
+        op.gemm(f1, L.l2w, bias=L.l2b, res1=x, out_f32=x)
+
+    # ------------------------------------------------------------------------------------------
+    # EVT_Former (VidHRFormer.py:25-52, 79-116)
+    # ------------------------------------------------------------------------------------------
+    def encode(self, x_tokens, beta, gamma, n, T):
+        """x_tokens fp32 [n*T*64, 512] (consumed in place) -> (memory fp32, memory bf16) [n*T*64,512]."""
+        op, ws = _lib.ops(), self.ws
+        M = n * T * TOK
+        x = x_tokens
+        a = ws.bf16("a_enc", M, C)
+        f = ws.bf16("f_enc", M, C)
+        for L in self.enc_layers:
+            op.ln_posfuse(x, L.n1.w, L.n1.b, None, beta, gamma, a, f, n, T)
+            self._self_attention(x, a, f, L.attn_s, ATTN_SPATIAL, n, T, False, "enc")
+            op.layernorm_rows(x, L.n2.w, L.n2.b, out_bf16=a)
+            self._conv_ffn(x, a, L.ffn_s, n * T, "enc")
+            op.ln_posfuse(x, L.n3.w, L.n3.b, None, beta, gamma, a, f, n, T)
+            self._self_attention(x, a, f, L.attn_t, ATTN_TEMPORAL, n, T, True, "enc")    # mask quirk :100-102
+            op.layernorm_rows(x, L.n4.w, L.n4.b, out_bf16=a)
+            self._mlp_ffn(x, a, L, "enc")
+        mem = ws.f32("mem_f32", M, C)
+        mem_bf = ws.bf16("mem_bf16", M, C)
+        op.layernorm_rows(x, self.norm_enc.w, self.norm_enc.b, out_f32=mem, out_bf16=mem_bf)
+        return mem, mem_bf
+
+    # ------------------------------------------------------------------------------------------
+    # latent event code (submodules.py:388-410)
+    # ------------------------------------------------------------------------------------------
+    def latent(self, evt, n, eps):
+        """evt fp32 [n*64,512] token-major -> z fp32 [n*64,512]; keeps (mu|logvar) in the workspace."""
+        op, ws, E = _lib.ops(), self.ws, self.evt
+        M = n * TOK
+        e1 = ws.bf16("evt_e1", M, C)
+        op.dwconv3x3_tokens(evt, E.dw_w, E.dw_shift, e1, relu=True)
+        col = ws.bf16("evt_col", M, 9 * C)
+        op.im2col(e1, col, n, 8, 8, C, 3, 3, 1, 1, PAD_ZERO, 8, 8)
+        e2 = ws.bf16("evt_e2", M, E.hidden)
+        op.gemm(col, E.w2, bias=E.b2, act=ACT_RELU, out_bf16=e2)
+        e3 = ws.bf16("evt_e3", M, E.hidden)
+        op.gemm(e2, E.w3, bias=E.b3, act=ACT_RELU, out_bf16=e3)
+        mulv = ws.f32("evt_mulv", M, E.w_head.shape[0])
+        op.gemm(e3, E.w_head, bias=E.b_head, out_f32=mulv)
+        z = ws.f32("evt_z", M, C)
+        op.latent_reparam(mulv, eps if E.stochastic else None, z, n, C)
+        return z, mulv
+
+    # ------------------------------------------------------------------------------------------
+    # NAR decoder (VidHRFormer.py:126-161, 198-245)
+    # ------------------------------------------------------------------------------------------
+    def decode(self, z, mem, mem_bf, beta_o, gamma_o, beta_p, gamma_p, n, To, Tp, relu_out=True):
+        op, ws = _lib.ops(), self.ws
+        M, Mo = n * Tp * TOK, n * To * TOK
+        y = ws.f32("y_dec", M, C)
+        y.zero_()                                               # tgt = zeros (VidHRFormer.py:139)
+        a = ws.bf16("a_dec", M, C)
+        f = ws.bf16("f_dec", M, C)
+        keyf = ws.bf16("keyf", Mo, C)
+        op.ln_posfuse(mem, None, None, None, beta_o, gamma_o, None, keyf, n, To)   # fuse(memory): layer invariant
+        kx = ws.bf16("kx", Mo, C)
+        vx = ws.bf16("vx", Mo, C)
+        qx = ws.bf16("qx", M, C)
+        ox = ws.bf16("o_dec", M, C)
+        for L in self.dec_layers:
+            op.ln_posfuse(y, L.n1.w, L.n1.b, z, beta_p, gamma_p, a, f, n, Tp)
+            self._self_attention(y, a, f, L.attn_s, ATTN_SPATIAL, n, Tp, False, "dec")
+            op.layernorm_rows(y, L.n2.w, L.n2.b, out_bf16=a)
+            self._conv_ffn(y, a, L.ffn_s, n * Tp, "dec")
+            op.ln_posfuse(y, L.n3.w, L.n3.b, None, beta_p, gamma_p, a, f, n, Tp)
+            self._self_attention(y, a, f, L.attn_t, ATTN_TEMPORAL, n, Tp, False, "dec")
+            op.layernorm_rows(y, L.n4.w, L.n4.b, out_bf16=a)
+            self._mlp_ffn(y, a, L, "dec")
+            # encoder-decoder attention over time
+            op.ln_posfuse(y, L.n5.w, L.n5.b, z, beta_p, gamma_p, None, f, n, Tp)
+            X = L.attn_x
+            op.gemm(f, X.wq, bias=X.bq, out_bf16=qx)
+            op.gemm(keyf, X.wk, bias=X.bk, out_bf16=kx)
+            op.gemm(mem_bf, X.wv, bias=X.bv, out_bf16=vx)
+            op.attention(qx, kx, vx, ox, ATTN_TEMPORAL, n, Tp, To, False)
+            op.gemm(ox, X.wo, bias=X.bo, res1=y, out_f32=y)
+            op.layernorm_rows(y, L.n6.w, L.n6.b, out_bf16=a)
+            self._conv_ffn(y, a, L.ffn_x, n * Tp, "dec")
+        out = ws.f32("dec_out", M, C)
+        out_bf = ws.bf16("dec_out_bf16", M, C)
+        op.layernorm_rows(y, self.norm_dec.w, self.norm_dec.b, out_f32=out, out_bf16=out_bf, relu=relu_out)
+        return out, out_bf
+
+    # ------------------------------------------------------------------------------------------
+    # entry points used by the Predictor module
+    # ------------------------------------------------------------------------------------------
+    def _to_tokens(self, x, channels_last, name):
+        """(N,T,C,H,W) or channels-last (N,T,H,W,C) fp32 -> private fp32 token matrix [N*T*64, 512]."""
+        op, ws = _lib.ops(), self.ws
+        n, T = x.shape[0], x.shape[1]
+        tok = ws.f32(name, n * T * TOK, C)
+        x = x.detach().to(torch.float32).contiguous()
+        if channels_last:
+            assert tuple(x.shape[2:]) == (8, 8, C), x.shape
+            tok.copy_(x.reshape(-1, C))
+        else:
+            assert tuple(x.shape[2:]) == (C, 8, 8), x.shape
+            op.nchw_to_tokens(x.reshape(n * T, C, TOK), out_f32=tok.view(n * T, TOK, C))
+        return tok, n, T
+
+    def _from_tokens(self, tok, n, T, channels_last):
+        op = _lib.ops()
+        if channels_last:
+            return tok.view(n, T, 8, 8, C).clone()
+        out = torch.empty(n, T, C, 8, 8, dtype=torch.float32, device=tok.device)
+        op.tokens_to_nchw(tok.view(n * T, TOK, C), out.view(n * T, C, TOK))
+        return out
+
+    def run(self, observed, channels_last=False, bf16_out=False):
+        mod = self.mod
+        x, n, To = self._to_tokens(observed, channels_last, "x_enc")
+        oc, pc = mod.observed_coor, mod.predict_coor
+        assert oc.shape[0] == To * TOK, f"observed_coor has {oc.shape[0] // TOK} timestamps but the input has {To} frames"
+        Tp = pc.shape[0] // TOK
+        assert Tp <= 32 and To <= 32, "temporal attention kernels hold at most 32 timestamps per sequence"
+        beta_o, gamma_o = self.positional(oc, "o")
+        beta_p, gamma_p = self.positional(pc, "p")
+        mem, mem_bf = self.encode(x, beta_o, gamma_o, n, To)
+        evt = self.ws.f32("evt", n * TOK, C)
+        _lib.ops().temporal_mean(mem, evt, n, To)
+        eps = None
+        if self.stochastic:
+            eps = mod.injected_eps
+            if eps is None:
+                eps = torch.randn((n, C, 8, 8), device=self.device)           # submodules.py:409
+            eps = eps.detach().to(self.device, torch.float32).contiguous()
+            assert tuple(eps.shape) == (n, C, 8, 8), f"latent noise must be {(n, C, 8, 8)}, got {tuple(eps.shape)}"
+        z, mulv = self.latent(evt, n, eps)
+        mod.last_latent = (z, mulv)
+        out, out_bf = self.decode(z, mem, mem_bf, beta_o, gamma_o, beta_p, gamma_p, n, To, Tp)
+        if bf16_out:        # engine-internal hand-off to the frame decoder (a view of the workspace, consumed at once)
+            assert channels_last
+            return out_bf.view(n, Tp, 8, 8, C)
+        return self._from_tokens(out, n, Tp, channels_last)
+
+    def evt_coding(self, x, pos_beta, pos_gamma):
+        """Predictor.evt_coding_forward (Predictor.py:337-350): returns (memory (N,T,C,H,W), evt_coding (N,C,H,W))."""
+        tok, n, T = self._to_tokens(x, False, "x_enc")
+        beta = pos_beta.detach().to(self.device, torch.float32).contiguous()
+        gamma = pos_gamma.detach().to(self.device, torch.float32).contiguous() if pos_gamma is not None else None
+        if gamma is not None and not bool((gamma != 0).any()):
+            gamma = None
+        mem, _ = self.encode(tok, beta, gamma, n, T)
+        evt = self.ws.f32("evt", n * TOK, C)
+        _lib.ops().temporal_mean(mem, evt, n, T)
+        return self._from_tokens(mem, n, T, False), self._from_tokens(evt, n, 1, False)[:, 0]

@@ -1,0 +1,131 @@
+"""Lightning-free inference wrapper around the three hot-path modules.
+
+``NPVPInference`` mirrors what ``LitPredictor`` does at inference time (models/Predictor.py:13-86):
+it owns ``VPTR_Enc``, ``VPTR_Dec`` and ``predictor`` under the same attribute names (so a Lightning
+checkpoint's ``state_dict`` loads after nothing more than ``torch.load(path)['state_dict']``), builds the
+context / target timestamp lists from the YAML exactly like ``LitPredictor.__init__`` (:28-41) and exposes
+
+  * ``forward(past, future=None)``  -> (rec_past, rec_future, pred_future)   the reference's triple (:72-86)
+  * ``predict(past)``               -> predicted frames only, staying channels-last between the modules
+  * ``rollout(past, num_future)``   -> block-autoregressive prediction beyond max_T (the shipped YAMLs ask for
+                                       2 -> 28 frames with max_T 12)
+Clips are independent, so multi-GPU inference shards the batch (``npvp_b200.distributed``).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .autoencoder import ResnetDecoder, ResnetEncoder
+from .config import RENORM, AttrDict, load_config, preset
+from .predictor import Predictor
+
+
+def timestamp_lists(cfg):
+    """(to_list, tp_list) as LitPredictor.__init__ builds them (Predictor.py:30-40)."""
+    P, D = cfg.Predictor, cfg.Dataset
+    if P.get("VFI", False):
+        cp, cf, nv = P.context_num_p, P.context_num_f, P.num_interpolate
+        clip = cp + cf + nv
+        assert D.num_past_frames + D.num_future_frames == clip, "Imcompatible VFI configurations"
+        idx = torch.linspace(0, clip - 1, clip, dtype=torch.int64)
+        return torch.cat([idx[0:cp], idx[-cf:]]), idx[cp:-cf]
+    to = torch.linspace(0, D.num_past_frames - 1, D.num_past_frames)
+    tp = torch.linspace(D.num_past_frames, D.num_past_frames + D.num_future_frames - 1, D.num_future_frames)
+    return to, tp
+
+
+class NPVPInference(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        if isinstance(cfg, str):
+            cfg = load_config(cfg) if cfg.endswith((".yaml", ".yml")) else preset(cfg)
+        self.cfg = cfg
+        A, D, P = cfg.AE, cfg.Dataset, cfg.Predictor
+        self.VPTR_Enc = ResnetEncoder(D.img_channels, ngf=A.ngf, n_downsampling=A.n_downsampling,
+                                      num_res_blocks=A.num_res_blocks, norm_layer=nn.BatchNorm2d,
+                                      norm_layer1d=nn.BatchNorm1d, learn_3d=A.learn_3d)
+        self.VPTR_Dec = ResnetDecoder(D.img_channels, ngf=A.ngf, n_downsampling=A.n_downsampling,
+                                      out_layer=A.out_layer, norm_layer=nn.BatchNorm2d)
+        self.h_list = torch.linspace(0, P.max_H - 1, P.max_H)
+        self.w_list = torch.linspace(0, P.max_W - 1, P.max_W)
+        self.to_list, self.tp_list = timestamp_lists(cfg)
+        assert P.max_T == D.num_past_frames + D.num_future_frames, "Incompatible max_T and clip length"
+        self.predictor = Predictor(P.max_H, P.max_W, P.max_T, self.h_list, self.w_list, self.to_list, self.tp_list,
+                                   P.embed_dim, P.fuse_method, P.param_free_norm_type, P.evt_hidden_channels,
+                                   1, P.stochastic, P.transformer_layers,
+                                   evt_former=P.evt_former, learn_evt_token=False,
+                                   evt_former_num_layers=P.evt_former_num_layers, rand_context=P.rand_context)
+        if P.rand_context:
+            self.predictor.reset_pos_coor(self.to_list, self.tp_list)
+        self.eval()
+
+    # -- checkpoints --------------------------------------------------------------------------------
+    def load_lightning_ckpt(self, path: str, strict: bool = True):
+        """Load a reference Lightning ``.ckpt`` (keys VPTR_Enc.*, VPTR_Dec.*, predictor.*; Predictor.py:18-19,43)."""
+        blob = torch.load(path, map_location="cpu")
+        sd = blob.get("state_dict", blob)
+        keep = {k: v for k, v in sd.items() if k.split(".")[0] in ("VPTR_Enc", "VPTR_Dec", "predictor")}
+        return self.load_state_dict(keep, strict=strict)
+
+    # -- reference-faithful forward -----------------------------------------------------------------
+    def forward(self, past_frames, future_frames=None):
+        past_feats = self.VPTR_Enc(past_frames)
+        rec_past = self.VPTR_Dec(past_feats)
+        rec_future = None
+        if future_frames is not None:
+            rec_future = self.VPTR_Dec(self.VPTR_Enc(future_frames))
+        pred = self.VPTR_Dec(self.predictor(past_feats))
+        return rec_past, rec_future, pred
+
+    # -- throughput path: Enc(context) -> Predictor -> Dec(predictions), channels-last in between ----
+    def predict(self, past_frames, eps: Optional[torch.Tensor] = None):
+        """past_frames (N,To,Cimg,H,W) fp32 CUDA -> predicted frames (N,Tp,Cimg,H,W) fp32.
+        ``eps``: optional injected latent noise (N,512,8,8) for NPVP-S (default: torch.randn like the reference)."""
+        if eps is not None:
+            self.predictor.injected_eps = eps
+        try:
+            feats = self.VPTR_Enc.forward_tokens(past_frames)
+            pred = self.predictor.forward_tokens(feats, bf16_out=True)
+            return self.VPTR_Dec.forward_tokens(pred)
+        finally:
+            if eps is not None:
+                self.predictor.injected_eps = None
+
+    def rollout(self, past_frames, num_future: int, eps_list: Optional[Sequence[torch.Tensor]] = None):
+        """Block-autoregressive VFP: predict len(tp_list) frames, feed the last To predictions back as context
+        (image space), repeat until ``num_future`` frames exist; the last block is truncated."""
+        To, Tp = past_frames.shape[1], int(self.tp_list.shape[0])
+        assert To == int(self.to_list.shape[0])
+        outs, ctx, done, blk = [], past_frames, 0, 0
+        while done < num_future:
+            eps = None if eps_list is None else eps_list[blk]
+            pred = self.predict(ctx, eps)
+            take = min(Tp, num_future - done)
+            outs.append(pred[:, :take])
+            done += take
+            blk += 1
+            if Tp >= To:
+                ctx = pred[:, Tp - To:Tp]
+            else:
+                ctx = torch.cat([ctx[:, Tp:], pred], dim=1)
+        return torch.cat(outs, dim=1)
+
+    # -- pixel space (utils/dataset.py:860-886, utils/train_summary.py:244-245) ----------------------
+    def to_pixels(self, frames):
+        """Model output -> [0,1] image space: Sigmoid outputs as is, Tanh outputs through VidReNormalize + clamp."""
+        if self.cfg.AE.out_layer == "Sigmoid":
+            return frames.clamp(0, 1)
+        mean, std = RENORM[self.cfg.Dataset.name]
+        m = torch.tensor(mean, device=frames.device, dtype=frames.dtype).view(1, 1, -1, 1, 1)
+        s = torch.tensor(std, device=frames.device, dtype=frames.dtype).view(1, 1, -1, 1, 1)
+        return (frames * s + m).clamp(0, 1)
+
+
+def build_from_config(cfg, device="cuda", seed: Optional[int] = 0) -> NPVPInference:
+    """Random-init model of a config (YAML path, preset name or AttrDict), built in the order Enc, Dec, Predictor."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    return NPVPInference(cfg).to(device).eval()

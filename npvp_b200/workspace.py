@@ -1,0 +1,36 @@
+"""Named scratch buffers, cached by (name, shape, dtype, device).
+
+Repeated forwards with the same shapes reuse the same device memory, which keeps pointers stable
+(a prerequisite for CUDA-graph replay) and avoids allocator traffic on the hot path.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+
+class Workspace:
+    def __init__(self, device: torch.device):
+        self.device = device
+        self._bufs: Dict[Tuple, torch.Tensor] = {}
+
+    def get(self, name: str, shape, dtype) -> torch.Tensor:
+        key = (name, tuple(int(s) for s in shape), dtype)
+        buf = self._bufs.get(key)
+        if buf is None:
+            # drop stale shapes of the same name so long-running processes do not accumulate dead buffers
+            for k in [k for k in self._bufs if k[0] == name]:
+                del self._bufs[k]
+            buf = torch.empty(key[1], dtype=dtype, device=self.device)
+            self._bufs[key] = buf
+        return buf
+
+    def bf16(self, name, *shape):
+        return self.get(name, shape, torch.bfloat16)
+
+    def f32(self, name, *shape):
+        return self.get(name, shape, torch.float32)
+
+    def bytes(self) -> int:
+        return sum(b.numel() * b.element_size() for b in self._bufs.values())

@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 import npvp_b200
-from util_init import fingerprint, seeded_rand, seeded_randn, stress_init_
+from util_init import fingerprint, reset_shared_norm, seeded_rand, seeded_randn, stress_init_
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PRED_CASES = ["pred_S_stress_realT", "pred_D_default", "pred_D_stress_vfi"]
@@ -38,6 +38,7 @@ def build_predictor_case(name):
     to = torch.tensor(m["to"], dtype=torch.float32)
     tp = torch.tensor(m["tp"], dtype=torch.float32)
     hl = torch.linspace(0, 7, 8)
+    reset_shared_norm(npvp_b200.Predictor)
     torch.manual_seed(seed)
     mod = npvp_b200.Predictor(8, 8, int(m["max_T"]), hl, hl, to, tp, 512, 'Add', 'layer', 256, 1, stoch, 8,
                               evt_former=True, learn_evt_token=False, evt_former_num_layers=4, rand_context=False).eval()

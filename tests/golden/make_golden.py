@@ -75,7 +75,7 @@ def sample(t: torch.Tensor, max_n: int = 30000):
 def main():
     import warnings
     warnings.filterwarnings("ignore")
-    from util_init import fingerprint, stress_init_, seeded_randn, seeded_rand
+    from util_init import fingerprint, stress_init_, seeded_randn, seeded_rand, reset_shared_norm
     RefPredictor, RefEnc, RefDec, ref_sub = import_reference()
     import npvp_b200
     from oracle import npvp_oracle as O
@@ -115,6 +115,8 @@ def main():
         to_t, tp_t = torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32)
         args = (8, 8, max_T, hl, hl, to_t, tp_t, 512, 'Add', 'layer', 256, 1, stoch, 8)
         kw = dict(evt_former=True, learn_evt_token=False, evt_former_num_layers=4, rand_context=False)
+        reset_shared_norm(RefPredictor)
+        reset_shared_norm(npvp_b200.Predictor)
         torch.manual_seed(seed)
         ref = RefPredictor(*args, **kw).eval()
         torch.manual_seed(seed)

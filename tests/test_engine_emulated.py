@@ -1,0 +1,52 @@
+"""CPU: run the host-side engines end to end with the kernel *specifications* standing in for the CUDA
+kernels (tests/kernel_specs.SpecOps) and compare with the oracle.  This validates weight packing, buffer
+plumbing and the kernel sequence without a GPU; the CUDA kernels themselves are checked against the same
+specs in the -m gpu tests."""
+import pytest
+import torch
+
+import npvp_b200._lib as _lib
+from cases import AE_CASES, PRED_CASES, build_ae_case, build_predictor_case
+from kernel_specs import SpecOps
+from oracle import npvp_oracle as O
+
+torch.set_grad_enabled(False)
+
+
+@pytest.fixture(autouse=True)
+def spec_ops():
+    old = _lib._OPS
+    _lib.set_ops(SpecOps())
+    yield
+    _lib.set_ops(old)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+
+
+@pytest.mark.parametrize("name", PRED_CASES)
+def test_predictor_engine_vs_oracle(name):
+    from npvp_b200.engine_predictor import PredictorEngine
+    mod, x, eps, stoch, _ = build_predictor_case(name)
+    sd = mod.state_dict()
+    ref = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], stoch, eps if stoch else None)
+    mod.injected_eps = eps if stoch else None
+    out = PredictorEngine(mod).run(x)
+    assert out.shape == ref.shape
+    assert _rel(out, ref) < 3e-2, _rel(out, ref)
+    out_cl = PredictorEngine(mod).run(x.permute(0, 1, 3, 4, 2).contiguous(), channels_last=True)
+    assert torch.equal(out_cl.permute(0, 1, 4, 2, 3), out)
+
+
+@pytest.mark.parametrize("name", AE_CASES)
+def test_autoencoder_engine_vs_oracle(name):
+    from npvp_b200.engine_autoencoder import DecoderEngine, EncoderEngine
+    enc, dec, x, f_in, cfg, _, _ = build_ae_case(name)
+    feats_ref = O.resnet_encoder(enc.state_dict(), x, cfg["n_down"], cfg["n_res"])
+    frames_ref = O.resnet_decoder(dec.state_dict(), f_in, cfg["n_down"], cfg["out_layer"])
+    feats = EncoderEngine(enc).run(x)
+    frames = DecoderEngine(dec).run(f_in)
+    assert feats.shape == feats_ref.shape and frames.shape == frames_ref.shape
+    assert _rel(feats, feats_ref) < 3e-2, _rel(feats, feats_ref)
+    assert float((frames - frames_ref).abs().max()) < 2e-2

@@ -1,0 +1,238 @@
+"""GPU: every C-ABI kernel against its torch specification (tests/kernel_specs.py) on seeded inputs."""
+import pytest
+import torch
+
+from kernel_specs import SpecOps
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def op():
+    from npvp_b200 import _lib
+    return _lib.Ops()
+
+
+@pytest.fixture(scope="module")
+def spec():
+    return SpecOps()
+
+
+def rn(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def close(a, b, rel, what=""):
+    a, b = a.float(), b.float()
+    err = float((a - b).abs().max())
+    ref = float(b.abs().max())
+    assert err <= rel * max(ref, 1e-6), f"{what}: max err {err:.4e} vs ref max {ref:.4e} (rel {err / max(ref, 1e-6):.3e} > {rel})"
+
+
+GEMM_SHAPES = [(256, 512, 512), (192, 1024, 512), (128, 2048, 512), (1024, 512, 2048), (4096, 256, 4608),
+               (130, 64, 64), (1000, 48, 64), (640, 384, 512), (300, 512, 128), (64, 1024, 256), (4096, 128, 288)]
+
+
+@pytest.mark.parametrize("backend", [2, 1, 0])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain(op, spec, backend, M, N, K):
+    a, w = rn(M, K, seed=1, dtype=torch.bfloat16), rn(N, K, seed=2, scale=K ** -0.5, dtype=torch.bfloat16)
+    bias = rn(N, seed=3)
+    o1, o2 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    b1, b2 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16), torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    op.gemm(a, w, bias=bias, out_f32=o1, out_bf16=b1, backend=backend)
+    spec.gemm(a, w, bias=bias, out_f32=o2, out_bf16=b2)
+    torch.cuda.synchronize()
+    close(o1, o2, 2e-3, f"gemm f32 backend={backend}")
+    close(b1, b2, 1e-2, f"gemm bf16 backend={backend}")
+
+
+@pytest.mark.parametrize("backend", [2, 1])
+def test_gemm_epilogues(op, spec, backend):
+    M, N, K = 384, 512, 1024
+    a, w = rn(M, K, seed=1, dtype=torch.bfloat16), rn(N, K, seed=2, scale=K ** -0.5, dtype=torch.bfloat16)
+    bias, r1, r2 = rn(N, seed=3), rn(M, N, seed=4), rn(M, N, seed=5, dtype=torch.bfloat16)
+    for kw in (dict(act=2), dict(act=1, alpha=0.6, res1=r1, res2=r2), dict(res1=r2, post_relu=True), dict(act=1, res1=r1)):
+        o1, o2 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+        op.gemm(a, w, bias=bias, out_f32=o1, backend=backend, **kw)
+        spec.gemm(a, w, bias=bias, out_f32=o2, **kw)
+        close(o1, o2, 2e-3, f"epilogue {kw.keys()} backend={backend}")
+    # in-place residual stream update (out aliases res1), strided A view
+    x = rn(M, N, seed=6)
+    x2 = x.clone()
+    big = rn(M, 2 * K, seed=7, dtype=torch.bfloat16)
+    op.gemm(big[:, K:], w, bias=bias, res1=x, out_f32=x, backend=backend)
+    spec.gemm(big[:, K:], w, bias=bias, res1=x2, out_f32=x2)
+    close(x, x2, 2e-3, "in-place residual")
+
+
+def test_gemm_f32_and_fourier(op, spec):
+    a, w, b = rn(700, 512, seed=1), rn(256, 512, seed=2, scale=0.05), rn(256, seed=3)
+    o1, o2 = torch.empty(700, 256, device=DEV), torch.empty(700, 256, device=DEV)
+    op.gemm_f32(a, w, b, 1, o1)
+    spec.gemm_f32(a, w, b, 1, o2)
+    close(o1, o2, 1e-5, "gemm_f32")
+    coor = torch.rand(320, 3, device=DEV)
+    B = rn(256, 3, seed=5, scale=10.0)
+    f1, f2 = torch.empty(320, 512, device=DEV), torch.empty(320, 512, device=DEV)
+    op.fourier_features(coor, B, f1)
+    spec.fourier_features(coor, B, f2)
+    assert float((f1 - f2).abs().max()) < 2e-4       # fp32 rounding of a ~240 rad argument
+
+
+@pytest.mark.parametrize("n,T,use_ln,use_qe,use_gamma", [(2, 3, True, True, False), (1, 5, True, False, True), (3, 2, False, False, False)])
+def test_ln_posfuse(op, spec, n, T, use_ln, use_qe, use_gamma):
+    x = rn(n * T * 64, 512, seed=1, scale=2.0) + 0.5
+    lw, lb = (rn(512, seed=2) * 0.3 + 1, rn(512, seed=3) * 0.3) if use_ln else (None, None)
+    qe = rn(n * 64, 512, seed=4) if use_qe else None
+    beta = rn(T * 64, 512, seed=5)
+    gamma = rn(T * 64, 512, seed=6, scale=0.2) if use_gamma else None
+    outs = [[torch.empty(n * T * 64, 512, device=DEV, dtype=torch.bfloat16) for _ in range(2)] for _ in range(2)]
+    op.ln_posfuse(x, lw, lb, qe, beta, gamma, outs[0][0], outs[0][1], n, T)
+    spec.ln_posfuse(x, lw, lb, qe, beta, gamma, outs[1][0], outs[1][1], n, T)
+    close(outs[0][0], outs[1][0], 1e-2, "ln out")
+    close(outs[0][1], outs[1][1], 1e-2, "fused out")
+
+
+def test_layernorm_rows_and_frame_ln(op, spec):
+    x = rn(1000, 512, seed=1, scale=3.0) - 1.0
+    w, b = rn(512, seed=2) * 0.3 + 1, rn(512, seed=3) * 0.3
+    for relu in (False, True):
+        o1, o2 = torch.empty_like(x), torch.empty_like(x)
+        b1, b2 = torch.empty_like(x, dtype=torch.bfloat16), torch.empty_like(x, dtype=torch.bfloat16)
+        op.layernorm_rows(x, w, b, o1, b1, relu)
+        spec.layernorm_rows(x, w, b, o2, b2, relu)
+        close(o1, o2, 1e-5, "layernorm f32")
+        close(b1, b2, 1e-2, "layernorm bf16")
+    h = rn(5 * 64, 512, seed=4, scale=2.0) + 0.3
+    aw, ab = rn(64, 512, seed=5) * 0.3 + 1, rn(64, 512, seed=6) * 0.3
+    y1 = rn(5 * 64, 512, seed=7)
+    y2 = y1.clone()
+    op.frame_ln_gelu_residual(h, aw, ab, y1)
+    spec.frame_ln_gelu_residual(h, aw, ab, y2)
+    close(y1, y2, 1e-5, "frame_ln_gelu_residual")
+    mem = rn(3 * 4 * 64, 512, seed=8)
+    e1, e2 = torch.empty(3 * 64, 512, device=DEV), torch.empty(3 * 64, 512, device=DEV)
+    op.temporal_mean(mem, e1, 3, 4)
+    spec.temporal_mean(mem, e2, 3, 4)
+    close(e1, e2, 1e-6, "temporal_mean")
+
+
+def test_conv_ffn_middle(op, spec):
+    frames, Ch = 3, 2048
+    h = (rn(frames * 64, Ch, seed=1, scale=1.5) + 0.2).to(torch.bfloat16)
+    n1w, n1b = rn(64, Ch, seed=2) * 0.3 + 1, rn(64, Ch, seed=3) * 0.3
+    n2w, n2b = rn(64, Ch, seed=4) * 0.3 + 1, rn(64, Ch, seed=5) * 0.3
+    dw_w, dw_b = rn(9, Ch, seed=6, scale=0.4), rn(Ch, seed=7, scale=0.2)
+    res = []
+    for o in (op, spec):
+        st = torch.empty(frames, 2, device=DEV)
+        y = torch.empty_like(h)
+        pt = torch.empty(frames, Ch // 256, 2, device=DEV)
+        g = torch.empty_like(h)
+        o.ffn_frame_stats(h, st)
+        o.ffn_dwconv(h, st, n1w, n1b, dw_w, dw_b, y, pt)
+        o.ffn_norm2(y, pt, n2w, n2b, g)
+        res.append((st, y, pt, g))
+    close(res[0][0], res[1][0], 1e-4, "ffn stats")
+    close(res[0][1], res[1][1], 1e-2, "ffn dwconv")
+    close(res[0][2], res[1][2], 2e-2, "ffn partial stats")
+    close(res[0][3], res[1][3], 2e-2, "ffn norm2")
+
+
+@pytest.mark.parametrize("mode,n,Tq,Tk,mask", [(0, 2, 3, 3, False), (1, 2, 5, 5, True), (1, 2, 5, 5, False), (1, 1, 7, 3, False),
+                                               (1, 1, 2, 2, True), (1, 1, 28, 2, False), (1, 1, 23, 10, False), (1, 1, 1, 1, True)])
+def test_attention(op, spec, mode, n, Tq, Tk, mask):
+    qk = rn(n * Tq * 64, 1024, seed=1, scale=1.5, dtype=torch.bfloat16)
+    kk = qk[:, 512:] if Tq == Tk else rn(n * Tk * 64, 512, seed=4, scale=1.5, dtype=torch.bfloat16)
+    v = rn(n * Tk * 64, 512, seed=2, dtype=torch.bfloat16)
+    o1 = torch.empty(n * Tq * 64, 512, device=DEV, dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    op.attention(qk[:, :512], kk, v, o1, mode, n, Tq, Tk, mask)
+    spec.attention(qk[:, :512], kk, v, o2, mode, n, Tq, Tk, mask)
+    close(o1, o2, 1.5e-2, f"attention mode={mode}")
+
+
+def test_event_encoder_pieces(op, spec):
+    n, Cc = 3, 512
+    x = rn(n * 64, Cc, seed=1)
+    w, sh = rn(9, Cc, seed=2, scale=0.4), rn(Cc, seed=3, scale=0.2)
+    o1 = torch.empty(n * 64, Cc, device=DEV, dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    op.dwconv3x3_tokens(x, w, sh, o1, True)
+    spec.dwconv3x3_tokens(x, w, sh, o2, True)
+    close(o1, o2, 1e-2, "dwconv3x3_tokens")
+    mulv = rn(n * 64, 2 * Cc, seed=4)
+    eps = rn(n, Cc, 8, 8, seed=5)
+    for e in (eps, None):
+        z1, z2 = torch.empty(n * 64, Cc, device=DEV), torch.empty(n * 64, Cc, device=DEV)
+        op.latent_reparam(mulv, e, z1, n, Cc)
+        spec.latent_reparam(mulv, e, z2, n, Cc)
+        close(z1, z2, 1e-5, "latent_reparam")
+
+
+def test_layout_kernels(op, spec):
+    x = rn(5, 512, 64, seed=1)
+    t1, t2 = torch.empty(5, 64, 512, device=DEV), torch.empty(5, 64, 512, device=DEV)
+    b1 = torch.empty(5, 64, 512, device=DEV, dtype=torch.bfloat16)
+    op.nchw_to_tokens(x, t1, b1)
+    spec.nchw_to_tokens(x, t2, None)
+    assert torch.equal(t1, t2) and torch.equal(b1, t2.to(torch.bfloat16))
+    back = torch.empty(5, 512, 64, device=DEV)
+    op.tokens_to_nchw(t1, back)
+    assert torch.equal(back, x)
+    op.tokens_to_nchw(b1, back, relu=True)
+    assert torch.equal(back, torch.relu(b1.float()).permute(0, 2, 1))
+
+
+@pytest.mark.parametrize("Cin,Cout,HW", [(3, 32, 128), (1, 64, 64), (3, 64, 40)])
+def test_conv7x7_stem(op, spec, Cin, Cout, HW):
+    x = rn(3, Cin, HW, HW, seed=1)
+    w, sh = rn(49 * Cin, Cout, seed=2, scale=0.1), rn(Cout, seed=3, scale=0.2)
+    o1 = torch.empty(3 * HW * HW, Cout, device=DEV, dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    op.conv7x7_stem(x, w, sh, o1, Cin, Cout, HW, HW)
+    spec.conv7x7_stem(x, w, sh, o2, Cin, Cout, HW, HW)
+    close(o1, o2, 1e-2, "conv7x7_stem")
+
+
+@pytest.mark.parametrize("Cin,Cout,HW,phase,act", [(32, 3, 128, True, 3), (64, 1, 64, True, 4), (32, 3, 48, False, 3)])
+def test_conv7x7_head(op, spec, Cin, Cout, HW, phase, act):
+    x = rn(2 * HW * HW, Cin, seed=1, dtype=torch.bfloat16)
+    w, b = rn(49 * Cin, Cout, seed=2, scale=0.03), rn(Cout, seed=3, scale=0.2)
+    o1, o2 = torch.empty(2, Cout, HW, HW, device=DEV), torch.empty(2, Cout, HW, HW, device=DEV)
+    op.conv7x7_head(x, w, b, o1, Cin, Cout, HW, HW, phase, act)
+    spec.conv7x7_head(x, w, b, o2, Cin, Cout, HW, HW, phase, act)
+    assert float((o1 - o2).abs().max()) < 2e-4, float((o1 - o2).abs().max())
+
+
+@pytest.mark.parametrize("H,C,KH,stride,pad,mode,phase", [(16, 64, 3, 1, 1, 0, False), (16, 64, 3, 2, 1, 0, False), (8, 512, 3, 1, 1, 1, False),
+                                                          (8, 128, 3, 1, 1, 2, False), (16, 32, 2, 1, 0, 0, True), (8, 256, 2, 1, 0, 0, False)])
+def test_im2col(op, spec, H, C, KH, stride, pad, mode, phase):
+    frames = 3
+    x = rn(frames * H * H, C, seed=1, dtype=torch.bfloat16)
+    Ho = H // stride
+    o1 = torch.empty(frames * Ho * Ho, KH * KH * C, device=DEV, dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    op.im2col(x, o1, frames, H, H, C, KH, KH, stride, pad, mode, Ho, Ho, phase)
+    spec.im2col(x, o2, frames, H, H, C, KH, KH, stride, pad, mode, Ho, Ho, phase)
+    assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("C,H", [(64, 64), (128, 32), (256, 16), (512, 8)])
+def test_nonlocal_pieces(op, spec, C, H):
+    frames, dq, dv = 2, C // 8, C // 2
+    qkv = rn(frames * H * H, 2 * dq + dv, seed=1, scale=0.7, dtype=torch.bfloat16)
+    kv1 = torch.empty(frames * H * H // 4, dq + dv, device=DEV, dtype=torch.bfloat16)
+    kv2 = torch.empty_like(kv1)
+    op.maxpool2x2_cols(qkv, dq, dq + dv, kv1, frames, H, H)
+    spec.maxpool2x2_cols(qkv, dq, dq + dv, kv2, frames, H, H)
+    assert torch.equal(kv1, kv2)
+    o1 = torch.empty(frames * H * H, dv, device=DEV, dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    op.nonlocal_attention(qkv[:, :dq], kv1, o1, frames, H * H, H * H // 4, dq, dv)
+    spec.nonlocal_attention(qkv[:, :dq], kv1, o2, frames, H * H, H * H // 4, dq, dv)
+    close(o1, o2, 1.5e-2, "nonlocal_attention")

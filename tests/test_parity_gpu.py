@@ -1,0 +1,115 @@
+"""GPU: the shipped modules (CUDA path through the C-ABI) against the CPU oracle and the reference goldens.
+
+Tolerances (BASELINE.json north_star): max |pixel error| <= 1e-2 on [0,1] frames and |delta PSNR| <= 0.1 dB for the
+end-to-end path; feature-space blocks are held to 3e-2 of the tensor's max (bf16 operands, fp32 accumulate)."""
+import numpy as np
+import pytest
+import torch
+
+from cases import AE_CASES, PRED_CASES, build_ae_case, build_predictor_case, golden_sample
+from oracle import npvp_oracle as O
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+
+
+@pytest.mark.parametrize("name", PRED_CASES)
+def test_predictor_matches_oracle_and_golden(name):
+    mod, x, eps, stoch, z = build_predictor_case(name)
+    sd = mod.state_dict()
+    ref = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], stoch, eps if stoch else None)
+    mod = mod.cuda()
+    mod.injected_eps = eps.cuda() if stoch else None
+    out = mod(x.cuda()).cpu()
+    assert out.shape == ref.shape
+    r = _rel(out, ref)
+    print(f"{name}: rel err vs oracle {r:.3e}, abs {float((out - ref).abs().max()):.3e}")
+    assert r < 3e-2
+    g = torch.from_numpy(z["sample"])
+    assert float((torch.from_numpy(golden_sample(out, z)) - g).abs().max()) < 3e-2 * float(z["absmax"])
+
+
+@pytest.mark.parametrize("name", AE_CASES)
+def test_autoencoder_matches_oracle_and_golden(name):
+    enc, dec, x, f_in, cfg, ze, zd = build_ae_case(name)
+    feats_ref = O.resnet_encoder(enc.state_dict(), x, cfg["n_down"], cfg["n_res"])
+    frames_ref = O.resnet_decoder(dec.state_dict(), f_in, cfg["n_down"], cfg["out_layer"])
+    feats = enc.cuda()(x.cuda()).cpu()
+    frames = dec.cuda()(f_in.cuda()).cpu()
+    print(f"{name}: enc rel {_rel(feats, feats_ref):.3e}  dec abs {float((frames - frames_ref).abs().max()):.3e}")
+    assert _rel(feats, feats_ref) < 3e-2
+    assert float((frames - frames_ref).abs().max()) < 1e-2
+    assert float(np.abs(golden_sample(frames, zd) - zd["sample"]).max()) < 1e-2
+
+
+@pytest.mark.parametrize("preset_name,N,stress", [("KITTI_VFP_NPVP-S", 2, True), ("SMMNIST_VFP_NPVP-D", 2, True),
+                                                  ("Cityscapes_VFP_NPVP-S", 1, False), ("BAIR_VFP_NPVP-S", 2, True)])
+def test_end_to_end_pixels(preset_name, N, stress):
+    from npvp_b200.pipeline import build_from_config
+    from util_init import reset_shared_norm, seeded_rand, seeded_randn, stress_init_
+    import npvp_b200
+    reset_shared_norm(npvp_b200.Predictor)
+    model = build_from_config(preset_name, device="cpu", seed=0)
+    if stress:
+        stress_init_(model.VPTR_Enc, 1)
+        stress_init_(model.VPTR_Dec, 2)
+        stress_init_(model.predictor, 3)
+    cfg = model.cfg
+    To, Tp = cfg.Dataset.num_past_frames, cfg.Dataset.num_future_frames
+    hw, ch = cfg.Dataset.img_size, cfg.Dataset.img_channels
+    x = seeded_rand((N, To, ch, hw, hw), 1234)
+    if cfg.AE.out_layer == "Tanh":
+        x = x * 2 - 1
+    eps = seeded_randn((N, 512, 8, 8), 4321)
+    ocfg = dict(n_downsampling=cfg.AE.n_downsampling, num_res_blocks=cfg.AE.num_res_blocks, out_layer=cfg.AE.out_layer,
+                stochastic=cfg.Predictor.stochastic)
+    psd = model.predictor.state_dict()
+    ref = O.npvp_predict_frames(model.VPTR_Enc.state_dict(), psd, model.VPTR_Dec.state_dict(), x, ocfg,
+                                psd["observed_coor"], psd["predict_coor"], eps if cfg.Predictor.stochastic else None)
+    model = model.cuda()
+    out = model.predict(x.cuda(), eps.cuda() if cfg.Predictor.stochastic else None)
+    # the reference-faithful triple must agree with the throughput path
+    model.predictor.injected_eps = eps.cuda() if cfg.Predictor.stochastic else None
+    rec_past, rec_future, pred = model(x.cuda())
+    model.predictor.injected_eps = None
+    assert rec_future is None and rec_past.shape == x.shape
+    assert float((pred - out).abs().max()) < 5e-3
+    px, px_ref = model.to_pixels(out).cpu(), model.to_pixels(ref)
+    err = float((px - px_ref).abs().max())
+    gt = seeded_rand(tuple(px_ref.shape), 99)
+    dpsnr = abs(float(O.psnr(px, gt)) - float(O.psnr(px_ref, gt)))
+    print(f"{preset_name}: max pixel err {err:.3e}  dPSNR {dpsnr:.4f} dB  pixel range [{float(px_ref.min()):.3f},{float(px_ref.max()):.3f}]")
+    assert out.shape == (N, Tp, ch, hw, hw)
+    assert err <= 1e-2 and dpsnr <= 0.1
+
+
+def test_rollout_block_autoregressive():
+    from npvp_b200.pipeline import build_from_config
+    from util_init import seeded_rand
+    model = build_from_config("BAIR_VFP_NPVP-S", device="cuda", seed=0)
+    x = (seeded_rand((2, 2, 3, 64, 64), 5) * 2 - 1).cuda()
+    eps = [torch.randn(2, 512, 8, 8, device="cuda", generator=torch.Generator("cuda").manual_seed(i)) for i in range(3)]
+    out = model.rollout(x, 28, eps)
+    assert out.shape == (2, 28, 3, 64, 64) and bool(torch.isfinite(out).all())
+    first = model.predict(x, eps[0])
+    assert torch.equal(out[:, :10], first)
+    second = model.predict(first[:, 8:10], eps[1])
+    assert torch.equal(out[:, 10:20], second)
+
+
+def test_batch_invariance_and_determinism():
+    """Per-clip math never mixes clips: clip 0 alone == clip 0 inside a batch, bit for bit (basis of the multi-GPU check)."""
+    from npvp_b200.pipeline import build_from_config
+    from util_init import seeded_rand
+    model = build_from_config("KITTI_VFP_NPVP-S", device="cuda", seed=0)
+    x = (seeded_rand((3, 4, 3, 128, 128), 7) * 2 - 1).cuda()
+    eps = torch.randn(3, 512, 8, 8, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    full = model.predict(x, eps)
+    again = model.predict(x, eps)
+    solo = model.predict(x[:1], eps[:1])
+    assert torch.equal(full, again)
+    assert torch.equal(full[:1], solo)

@@ -86,3 +86,14 @@ def seeded_randn(shape, seed: int) -> torch.Tensor:
 
 def seeded_rand(shape, seed: int) -> torch.Tensor:
     return torch.rand(shape, generator=torch.Generator().manual_seed(seed), dtype=torch.float32)
+
+
+@torch.no_grad()
+def reset_shared_norm(predictor_cls) -> None:
+    """``Predictor.__init__`` has ``norm=nn.LayerNorm(512)`` as a *shared default instance* (reference quirk,
+    models/Predictor.py:270): every Predictor built in the process aliases it.  Reset it to identity so a test
+    case does not depend on which cases ran before."""
+    import inspect
+    norm = inspect.signature(predictor_cls.__init__).parameters["norm"].default
+    norm.weight.fill_(1.0)
+    norm.bias.zero_()
