@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""NPVP inference benchmark (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--clips B]
+
+Workload (BASELINE.json metric "predicted frames/sec ... Cityscapes 128^2 NPVP-S"): config_Cityscapes_VFP_NPVP-S,
+128x128 RGB, 2 context frames -> 28 predicted frames per clip by block-autoregressive rollout (2->10, 2->10, 2->8;
+max_T = 12 forbids a one-shot 2->28), random-init weights, synthetic clips.  A step = one rollout of B clips per GPU
+(weak scaling: B fixed per GPU); for N > 1 the step ends with the NCCL all-gather of the predicted frames.
+
+One JSON line on rank 0:  value = device-resident throughput, e2e = through model.rollout with pinned host buffers
+(H2D of the context frames + D2H of the predicted frames inside the timed region), roofline = the tcgen05 GEMM
+(dominant kernel) timed per launch with CUDA events in an instrumented pass, cpu_baseline = the oracle on host cores.
+``--impl reference`` times the CPU restatement of the reference path (oracle/) on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+PRESET = "Cityscapes_VFP_NPVP-S"
+N_FUTURE = 28
+WORKLOAD = "Cityscapes 128x128 RGB NPVP-S VFP 2->28 (block-autoregressive 2->10,2->10,2->8; config_Cityscapes_VFP_NPVP-S.yaml)"
+METRIC = "predicted frames/sec"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, reasons, smax = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        busy = [s for s in sm if smax and s > 0.3 * smax] or sm
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ----------------------------------------------------------------------------------------------------------------
+def oracle_rollout_fn(clips: int):
+    """Returns (fn, frames_per_call): fn() runs the CPU oracle's block-AR 2->28 rollout for `clips` clips."""
+    from npvp_b200.pipeline import build_from_config
+    from oracle import npvp_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    model = build_from_config(PRESET, device="cpu", seed=0)
+    cfg = model.cfg
+    ocfg = dict(n_downsampling=cfg.AE.n_downsampling, num_res_blocks=cfg.AE.num_res_blocks, out_layer=cfg.AE.out_layer, stochastic=True)
+    esd, psd, dsd = model.VPTR_Enc.state_dict(), model.predictor.state_dict(), model.VPTR_Dec.state_dict()
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand((clips, 2, 3, 128, 128), generator=g) * 2 - 1
+
+    def fn():
+        ctx, done, outs = x, 0, []
+        while done < N_FUTURE:
+            eps = torch.randn((clips, 512, 8, 8), generator=g)
+            pred = O.npvp_predict_frames(esd, psd, dsd, ctx, ocfg, psd["observed_coor"], psd["predict_coor"], eps)
+            take = min(10, N_FUTURE - done)
+            outs.append(pred[:, :take])
+            done += take
+            ctx = pred[:, 8:10]
+        return torch.cat(outs, 1)
+    return fn, clips * N_FUTURE
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_grad_enabled(False)
+    clips = 2
+    fn, frames = oracle_rollout_fn(clips)
+    for _ in range(args.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    fps = frames * args.steps / dt
+    cores = os.cpu_count()
+    sample = f"{clips} clips x 28 frames per step (oracle port of the reference path, torch {torch.__version__} fp32, {cores} threads)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "clips_per_step": clips, "device": "host CPU"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+class GemmTimer:
+    """Instrumented pass: wraps Ops.gemm with CUDA events on the launching stream, per-launch algorithmic FLOPs."""
+
+    def __init__(self, ops):
+        self.ops, self.records, self._orig = ops, [], ops.gemm
+
+    def __enter__(self):
+        def timed(a, w, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._orig(a, w, **kw)
+            e1.record()
+            M, K = a.shape
+            self.records.append((e0, e1, 2.0 * M * K * w.shape[0], (M, w.shape[0], K)))
+        self.ops.gemm = timed
+        return self
+
+    def __exit__(self, *exc):
+        self.ops.gemm = self._orig
+
+    def summary(self):
+        torch.cuda.synchronize()
+        rows = [(e0.elapsed_time(e1) * 1e-3, fl, shp) for e0, e1, fl, shp in self.records]
+        big = [r for r in rows if r[2][0] >= 128 and r[2][1] >= 64 and r[2][2] >= 64]      # launches on the tcgen05 path
+        t, f = sum(r[0] for r in big), sum(r[1] for r in big)
+        return {"launches": len(big), "seconds": t, "flops": f, "all_gemm_seconds": sum(r[0] for r in rows)}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from npvp_b200 import _lib
+    from npvp_b200.distributed import gather_frames
+    from npvp_b200.pipeline import build_from_config
+
+    torch.set_grad_enabled(False)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.clips
+    model = build_from_config(PRESET, device=dev, seed=0)
+    ops = _lib.ops()
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host_in = (torch.rand((B, 2, 3, 128, 128), generator=g) * 2 - 1).pin_memory()
+    host_out = torch.empty((B, N_FUTURE, 3, 128, 128), dtype=torch.float32).pin_memory()
+    x_dev = host_in.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > 126 MB L2
+
+    def step_device():
+        out = model.rollout(x_dev, N_FUTURE)
+        if world > 1:
+            out = gather_frames(out, B * world)
+        return out
+
+    def step_e2e():
+        xd = host_in.to(dev, non_blocking=True)
+        out = model.rollout(xd, N_FUTURE)
+        if world > 1:
+            out = gather_frames(out, B * world)[rank * B:(rank + 1) * B]
+        host_out.copy_(out, non_blocking=True)
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()                                      # L2 flush between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    step_device()                                              # build engines / first-touch allocations
+    ops.reset_launch_count()
+    step_device()
+    launches_per_step = ops.launch_count()
+    total_ms = timed(step_device, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms = timed(step_e2e, max(2, min(args.steps, 10)), 1)
+    e2e_steps = max(2, min(args.steps, 10))
+
+    roof = None
+    if rank == 0:
+        with GemmTimer(ops) as gt:
+            model.rollout(x_dev, N_FUTURE)
+        s = gt.summary()
+        hbm, tf, which = load_peaks()
+        ach = s["flops"] / s["seconds"] / 1e12 if s["seconds"] > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
+                "traffic": None, "peak_source": f"{which} (bf16 sustained)", "launches_per_step": s["launches"],
+                "kernel_ms_per_step": 1e3 * s["seconds"], "all_gemm_ms_per_step": 1e3 * s["all_gemm_seconds"]}
+
+    if rank == 0:
+        frames_step = B * world * N_FUTURE
+        value = frames_step * args.steps / (total_ms * 1e-3)
+        e2e = frames_step * e2e_steps / (e2e_ms * 1e-3)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            fn, frames = oracle_rollout_fn(4)
+            fn()
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            cpu = {"value": frames / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"4 clips x 28 frames, one rollout after one warm-up (oracle port, fp32, {os.cpu_count()} torch threads)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clips_per_gpu": B, "global_clips": B * world, "frames_per_clip": N_FUTURE,
+                       "parallelism": f"dp{world} batch-sharded, all_gather of frames" if world > 1 else "single GPU",
+                       "l2": "256 MiB buffer written between timed steps; per-step activations also exceed the 126 MB L2",
+                       "arith": "bf16 operands, fp32 accumulate / residual / statistics"},
+            "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
+                    "steps": e2e_steps, "api": "NPVPInference.rollout on pinned host tensors"},
+            "roofline": roof,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

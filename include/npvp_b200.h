@@ -12,7 +12,10 @@
  *   - every function returns NPVP_OK (0) or a negative error code; the message is available
  *     from npvp_last_error() (thread-local);  no exceptions cross the boundary;
  *   - token layout: activations are channels-last, a "frame" is 64 tokens (8x8 grid) x C;
- *     bf16 buffers are GEMM/conv operands, fp32 buffers carry residual streams and statistics.
+ *     16-bit buffers are GEMM/conv operands, fp32 buffers carry residual streams and statistics;
+ *   - "bf16" in a parameter name means "16-bit operand buffer": entry points with an `fp16` flag (and the
+ *     `fp16` field of npvp_epilogue_t) read/write IEEE half instead of bfloat16 when it is 1.  The autoencoder
+ *     runs in half (its rounding errors land directly in pixels), the predictor in bfloat16 (range safety).
  */
 #ifndef NPVP_B200_H
 #define NPVP_B200_H
@@ -57,6 +60,8 @@ typedef struct npvp_epilogue {
   int32_t res1_bf16; /* 1: res1 is bf16, 0: fp32 */
   int32_t res2_bf16;
   int32_t post_relu;
+  int32_t fp16;      /* 16-bit type of A, W, out_bf16 and 16-bit residuals: 0 = bfloat16, 1 = IEEE half */
+  int32_t reserved;
   int64_t ld_out;
   int64_t ld_res;
 } npvp_epilogue_t;
@@ -95,7 +100,7 @@ int npvp_ln_posfuse(const float* x, const float* ln_w, const float* ln_b, const 
 /* LayerNorm over C=512 per token (VidHRFormer.py:91,110,214,224,243; final norm :48,:151 with relu=1 for :159).
  * Outputs optional fp32 and/or bf16. */
 int npvp_layernorm_rows(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16,
-                        int64_t rows, int relu, void* stream);
+                        int64_t rows, int relu, int fp16, void* stream);
 /* y += GELU(LayerNorm_(C,8,8)(h))  - MlpDWBN norm3 + act3 + the block's residual add
  * (VidHRFormer.py:388-389 with :91/:214/:243).  h fp32 [frames,64,512]; w,b fp32 [64,512] (hw-major). */
 int npvp_frame_ln_gelu_residual(const float* h, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,
@@ -139,21 +144,21 @@ int npvp_latent_reparam(const float* mulv, int64_t ld, const float* eps_nchw, fl
 /* ---- layout changes at the module boundary --------------------------------------------------
  * (N,T,C,H,W) fp32  <->  channels-last tokens.  frames = N*T, HW = H*W. */
 int npvp_nchw_to_tokens(const float* x, float* out_f32, void* out_bf16, int64_t frames, int64_t C, int64_t HW,
-                        void* stream);
+                        int fp16, void* stream);
 int npvp_tokens_to_nchw(const float* x_f32, const void* x_bf16, float* out, int64_t frames, int64_t C, int64_t HW,
-                        int relu, void* stream);
+                        int relu, int fp16, void* stream);
 
 /* ---- autoencoder ---------------------------------------------------------------------------
  * 7x7 stem: reflect-pad 3, conv (no bias) + folded BN + ReLU  (ResNetAutoEncoder.py:70-73).
  * x fp32 NCHW [frames,Cin,H,W]; w fp32 [49*Cin, Cout] (tap-major, BN scale folded); shift fp32 [Cout];
  * out bf16 NHWC [frames,H,W,Cout]. */
 int npvp_conv7x7_stem(const float* x, const float* w, const float* shift, void* out_bf16, int64_t frames, int Cin,
-                      int Cout, int H, int W, void* stream);
+                      int Cout, int H, int W, int fp16, void* stream);
 /* 7x7 head: reflect-pad 3, conv + bias + Tanh|Sigmoid (ResNetAutoEncoder.py:184-189).
  * x bf16 [frames,H,W,Cin] (phase_major=1: stored [frames,H/2,W/2,4,Cin], the ConvT GEMM's native output);
  * w fp32 [49*Cin, Cout]; bias fp32 [Cout]; out fp32 NCHW [frames,Cout,H,W]. */
 int npvp_conv7x7_head(const void* x_bf16, const float* w, const float* bias, float* out, int64_t frames, int Cin,
-                      int Cout, int H, int W, int phase_major, int act, void* stream);
+                      int Cout, int H, int W, int phase_major, int act, int fp16, void* stream);
 /* Patch gather for conv-as-GEMM: out[(f,oy,ox), (ky,kx,c)] = x[f, oy*stride - pad + ky, ox*stride - pad + kx, c].
  * x bf16 NHWC (or phase-major), out bf16 [frames*Ho*Wo, KH*KW*C]. */
 int npvp_im2col_nhwc(const void* x_bf16, void* out_bf16, int64_t frames, int H, int W, int C, int KH, int KW,
@@ -161,11 +166,11 @@ int npvp_im2col_nhwc(const void* x_bf16, void* out_bf16, int64_t frames, int H, 
 /* 2x2/stride-2 max-pool of a column slice of a token matrix (NonLocalAttenion2D k/v pooling, submodules.py:151,158).
  * x bf16 [frames*H*W, ldx], columns [col0, col0+Cn) -> out bf16 [frames*(H/2)*(W/2), Cn]. */
 int npvp_maxpool2x2_cols(const void* x_bf16, int64_t ldx, int col0, int Cn, void* out_bf16, int64_t frames, int H,
-                         int W, void* stream);
+                         int W, int fp16, void* stream);
 /* Non-local attention core: softmax(q k^T) v, UNSCALED (submodules.py:153-160).
  * q bf16 [frames*HW, ldq] (first dq columns); kv bf16 [frames*HWk, dq+dv] (k | v); out bf16 [frames*HW, dv]. */
 int npvp_nonlocal_attention(const void* q, int64_t ldq, const void* kv, void* out, int64_t frames, int HW, int HWk,
-                            int dq, int dv, void* stream);
+                            int dq, int dv, int fp16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ _i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
 class Epilogue(C.Structure):
     _fields_ = [("bias", _vp), ("res1", _vp), ("res2", _vp), ("out_f32", _vp), ("out_bf16", _vp),
                 ("alpha", _f32), ("act", C.c_int32), ("res1_bf16", C.c_int32), ("res2_bf16", C.c_int32),
-                ("post_relu", C.c_int32), ("ld_out", _i64), ("ld_res", _i64)]
+                ("post_relu", C.c_int32), ("fp16", C.c_int32), ("reserved", C.c_int32), ("ld_out", _i64), ("ld_res", _i64)]
 
 
 # symbol -> argtypes; every function returns int.  Kept in one table so tests can check the export list.
@@ -36,7 +36,7 @@ SIGNATURES = {
     "npvp_gemm_f32": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i32, _vp, _i64, _vp],
     "npvp_fourier_features": [_vp, _vp, _vp, _i64, _i32, _vp],
     "npvp_ln_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
-    "npvp_layernorm_rows": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "npvp_layernorm_rows": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "npvp_frame_ln_gelu_residual": [_vp, _vp, _vp, _vp, _i64, _vp],
     "npvp_temporal_mean": [_vp, _vp, _i64, _i64, _i64, _vp],
     "npvp_ffn_frame_stats": [_vp, _vp, _i64, _i64, _vp],
@@ -45,13 +45,13 @@ SIGNATURES = {
     "npvp_attention": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i64, _i32, _i32, _i32, _vp],
     "npvp_dwconv3x3_tokens": [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp],
     "npvp_latent_reparam": [_vp, _i64, _vp, _vp, _i64, _i64, _vp],
-    "npvp_nchw_to_tokens": [_vp, _vp, _vp, _i64, _i64, _i64, _vp],
-    "npvp_tokens_to_nchw": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp],
-    "npvp_conv7x7_stem": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
-    "npvp_conv7x7_head": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "npvp_nchw_to_tokens": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp],
+    "npvp_tokens_to_nchw": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp],
+    "npvp_conv7x7_stem": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
+    "npvp_conv7x7_head": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "npvp_im2col_nhwc": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
-    "npvp_maxpool2x2_cols": [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _i32, _vp],
-    "npvp_nonlocal_attention": [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
+    "npvp_maxpool2x2_cols": [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _vp],
+    "npvp_nonlocal_attention": [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
 }
 AUX_SYMBOLS = ["npvp_last_error", "npvp_version", "npvp_launch_count", "npvp_reset_launch_count"]
 
@@ -86,6 +86,27 @@ def _chk(t: Optional[torch.Tensor], dtype, name: str, contiguous: bool = True):
         raise ValueError(f"npvp_b200: tensor '{name}' must be contiguous")
 
 
+H16 = (torch.bfloat16, torch.float16)
+
+
+def _chk16(t: Optional[torch.Tensor], name: str, contiguous: bool = True, like: Optional[torch.Tensor] = None):
+    """16-bit operand buffer: bfloat16 or float16 (all 16-bit operands of one call must agree)."""
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"npvp_b200: tensor '{name}' must live on a CUDA device (no CPU path)")
+    if t.dtype not in H16:
+        raise TypeError(f"npvp_b200: tensor '{name}' must be bfloat16 or float16, got {t.dtype}")
+    if like is not None and t.dtype != like.dtype:
+        raise TypeError(f"npvp_b200: tensor '{name}' is {t.dtype} but the call's operands are {like.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise ValueError(f"npvp_b200: tensor '{name}' must be contiguous")
+
+
+def _is_fp16(t: torch.Tensor) -> int:
+    return int(t.dtype == torch.float16)
+
+
 def _rowmajor(t: torch.Tensor, name: str):
     if t.dim() != 2 or t.stride(1) != 1:
         raise ValueError(f"npvp_b200: '{name}' must be a 2-D view with unit inner stride")
@@ -118,9 +139,9 @@ class Ops:
     # -- contractions ---------------------------------------------------------------------------
     def gemm(self, a, w, *, bias=None, act=ACT_NONE, alpha=1.0, res1=None, res2=None, out_f32=None, out_bf16=None,
              post_relu=False, backend=None):
-        _chk(a, torch.bfloat16, "a", False); _chk(w, torch.bfloat16, "w", False)
+        _chk16(a, "a", False); _chk16(w, "w", False, like=a)
         _chk(bias, torch.float32, "bias"); _chk(out_f32, torch.float32, "out_f32", False)
-        _chk(out_bf16, torch.bfloat16, "out_bf16", False)
+        _chk16(out_bf16, "out_bf16", False, like=a)
         lda, ldw = _rowmajor(a, "a"), _rowmajor(w, "w")
         M, K = a.shape
         N = w.shape[0]
@@ -132,13 +153,13 @@ class Ops:
         ld_res = 0
         for r in (res1, res2):
             if r is not None:
-                assert r.is_cuda and r.shape == (M, N) and r.dtype in (torch.float32, torch.bfloat16)
+                assert r.is_cuda and r.shape == (M, N) and r.dtype in (torch.float32, a.dtype)
                 ld = _rowmajor(r, "res")
                 assert ld_res in (0, ld), "gemm: residuals must share a row stride"
                 ld_res = ld
         ep = Epilogue(_ptr(bias), _ptr(res1), _ptr(res2), _ptr(out_f32), _ptr(out_bf16), float(alpha), int(act),
-                      int(res1 is not None and res1.dtype == torch.bfloat16),
-                      int(res2 is not None and res2.dtype == torch.bfloat16), int(bool(post_relu)), ld_out, ld_res)
+                      int(res1 is not None and res1.dtype in H16),
+                      int(res2 is not None and res2.dtype in H16), int(bool(post_relu)), _is_fp16(a), 0, ld_out, ld_res)
         self._call("npvp_gemm_bf16", a.data_ptr(), lda, w.data_ptr(), ldw, M, N, K, C.byref(ep),
                    self.gemm_backend if backend is None else backend, self._stream())
 
@@ -171,10 +192,10 @@ class Ops:
 
     def layernorm_rows(self, x, w, b, out_f32=None, out_bf16=None, relu=False):
         _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(b, torch.float32, "b")
-        _chk(out_f32, torch.float32, "out_f32"); _chk(out_bf16, torch.bfloat16, "out_bf16")
+        _chk(out_f32, torch.float32, "out_f32"); _chk16(out_bf16, "out_bf16")
         rows = x.numel() // 512
         self._call("npvp_layernorm_rows", x.data_ptr(), w.data_ptr(), b.data_ptr(), _ptr(out_f32), _ptr(out_bf16), rows,
-                   int(relu), self._stream())
+                   int(relu), 0 if out_bf16 is None else _is_fp16(out_bf16), self._stream())
 
     def frame_ln_gelu_residual(self, h, w_hwc, b_hwc, y):
         for t, n in ((h, "h"), (w_hwc, "w"), (b_hwc, "b"), (y, "y")):
@@ -240,54 +261,56 @@ class Ops:
     # -- layouts --------------------------------------------------------------------------------
     def nchw_to_tokens(self, x, out_f32=None, out_bf16=None):
         """x: (frames, C, HW) fp32 -> (frames, HW, C)."""
-        _chk(x, torch.float32, "x"); _chk(out_f32, torch.float32, "out_f32"); _chk(out_bf16, torch.bfloat16, "out_bf16")
+        _chk(x, torch.float32, "x"); _chk(out_f32, torch.float32, "out_f32"); _chk16(out_bf16, "out_bf16")
         frames, Cc, HW = x.shape
-        self._call("npvp_nchw_to_tokens", x.data_ptr(), _ptr(out_f32), _ptr(out_bf16), frames, Cc, HW, self._stream())
+        self._call("npvp_nchw_to_tokens", x.data_ptr(), _ptr(out_f32), _ptr(out_bf16), frames, Cc, HW,
+                   0 if out_bf16 is None else _is_fp16(out_bf16), self._stream())
 
     def tokens_to_nchw(self, x, out, relu=False):
         """x: (frames, HW, C) fp32 or bf16 -> out (frames, C, HW) fp32."""
-        assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
+        assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32,) + H16
         _chk(out, torch.float32, "out")
         frames, HW, Cc = x.shape
         xf, xb = (x.data_ptr(), None) if x.dtype == torch.float32 else (None, x.data_ptr())
-        self._call("npvp_tokens_to_nchw", xf, xb, out.data_ptr(), frames, Cc, HW, int(relu), self._stream())
+        self._call("npvp_tokens_to_nchw", xf, xb, out.data_ptr(), frames, Cc, HW, int(relu), _is_fp16(x), self._stream())
 
     # -- autoencoder ----------------------------------------------------------------------------
     def conv7x7_stem(self, x, w, shift, out, Cin, Cout, H, W):
-        _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(shift, torch.float32, "shift"); _chk(out, torch.bfloat16, "out")
+        _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(shift, torch.float32, "shift"); _chk16(out, "out")
         frames = x.numel() // (Cin * H * W)
         assert out.numel() == frames * H * W * Cout and w.shape == (49 * Cin, Cout)
         per = max(1, 65535 // (Cout // 16))
         for f0 in range(0, frames, per):      # grid.z limit
             n = min(per, frames - f0)
             self._call("npvp_conv7x7_stem", x.data_ptr() + f0 * Cin * H * W * 4, w.data_ptr(), shift.data_ptr(),
-                       out.data_ptr() + f0 * H * W * Cout * 2, n, Cin, Cout, H, W, self._stream())
+                       out.data_ptr() + f0 * H * W * Cout * 2, n, Cin, Cout, H, W, _is_fp16(out), self._stream())
 
     def conv7x7_head(self, x, w, bias, out, Cin, Cout, H, W, phase_major, act):
-        _chk(x, torch.bfloat16, "x"); _chk(w, torch.float32, "w"); _chk(bias, torch.float32, "bias"); _chk(out, torch.float32, "out")
+        _chk16(x, "x"); _chk(w, torch.float32, "w"); _chk(bias, torch.float32, "bias"); _chk(out, torch.float32, "out")
         frames = x.numel() // (Cin * H * W)
         assert out.numel() == frames * Cout * H * W and w.shape == (49 * Cin, Cout)
         for f0 in range(0, frames, 65535):
             n = min(65535, frames - f0)
             self._call("npvp_conv7x7_head", x.data_ptr() + f0 * Cin * H * W * 2, w.data_ptr(), bias.data_ptr(),
-                       out.data_ptr() + f0 * Cout * H * W * 4, n, Cin, Cout, H, W, int(phase_major), int(act), self._stream())
+                       out.data_ptr() + f0 * Cout * H * W * 4, n, Cin, Cout, H, W, int(phase_major), int(act), _is_fp16(x), self._stream())
 
     def im2col(self, x, out, frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo, phase_major=False):
-        _chk(x, torch.bfloat16, "x"); _chk(out, torch.bfloat16, "out")
+        _chk16(x, "x"); _chk16(out, "out", like=x)
         assert x.numel() == frames * H * W * Cc and out.shape == (frames * Ho * Wo, KH * KW * Cc)
         self._call("npvp_im2col_nhwc", x.data_ptr(), out.data_ptr(), frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo,
                    int(phase_major), self._stream())
 
     def maxpool2x2_cols(self, x, col0, Cn, out, frames, H, W):
-        _chk(x, torch.bfloat16, "x", False); _chk(out, torch.bfloat16, "out")
+        _chk16(x, "x", False); _chk16(out, "out", like=x)
         assert x.shape[0] == frames * H * W and out.shape == (frames * (H // 2) * (W // 2), Cn)
-        self._call("npvp_maxpool2x2_cols", x.data_ptr(), _rowmajor(x, "x"), col0, Cn, out.data_ptr(), frames, H, W, self._stream())
+        self._call("npvp_maxpool2x2_cols", x.data_ptr(), _rowmajor(x, "x"), col0, Cn, out.data_ptr(), frames, H, W, _is_fp16(x),
+                   self._stream())
 
     def nonlocal_attention(self, q, kv, out, frames, HW, HWk, dq, dv):
-        _chk(q, torch.bfloat16, "q", False); _chk(kv, torch.bfloat16, "kv"); _chk(out, torch.bfloat16, "out")
+        _chk16(q, "q", False); _chk16(kv, "kv", like=q); _chk16(out, "out", like=q)
         assert q.shape[0] == frames * HW and kv.shape == (frames * HWk, dq + dv) and out.shape == (frames * HW, dv)
         self._call("npvp_nonlocal_attention", q.data_ptr(), _rowmajor(q, "q"), kv.data_ptr(), out.data_ptr(), frames, HW, HWk, dq,
-                   dv, self._stream())
+                   dv, _is_fp16(q), self._stream())
 
 
 _OPS: Optional[Ops] = None

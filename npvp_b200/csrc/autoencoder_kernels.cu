@@ -23,7 +23,7 @@ __device__ __forceinline__ size_t pixel_offset(int64_t f, int y, int x, int H, i
 template <int CIN>
 __global__ void __launch_bounds__(256)
 conv7x7_stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
-                    bf16* __restrict__ out, int Cout, int H, int W) {
+                    h16* __restrict__ out, int Cout, int H, int W, int fp16) {
   __shared__ float tile[CIN][22][23];
   __shared__ __align__(16) float ws[49 * CIN][16];
   const int f = blockIdx.z / (Cout / 16), cg = blockIdx.z % (Cout / 16);
@@ -58,7 +58,7 @@ conv7x7_stem_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     uint32_t pk[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      pk[j] = pack_bf16x2(fmaxf(acc[2 * j] + __ldg(shift + cg * 16 + 2 * j), 0.f), fmaxf(acc[2 * j + 1] + __ldg(shift + cg * 16 + 2 * j + 1), 0.f));
+      pk[j] = pack_h16x2(fmaxf(acc[2 * j] + __ldg(shift + cg * 16 + 2 * j), 0.f), fmaxf(acc[2 * j + 1] + __ldg(shift + cg * 16 + 2 * j + 1), 0.f), fp16);
     uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)f * H + oy) * W + ox) * Cout + cg * 16);
     dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -66,14 +66,14 @@ conv7x7_stem_kernel(const float* __restrict__ x, const float* __restrict__ w, co
 }
 
 extern "C" int npvp_conv7x7_stem(const float* x, const float* w, const float* shift, void* out_bf16, int64_t frames, int Cin,
-                                 int Cout, int H, int W, void* stream) {
+                                 int Cout, int H, int W, int fp16, void* stream) {
   NPVP_REQUIRE(x && w && shift && out_bf16 && frames > 0, "npvp_conv7x7_stem: bad arguments");
   NPVP_REQUIRE(Cout % 16 == 0 && H >= 4 && W >= 4, "npvp_conv7x7_stem: Cout must be a multiple of 16, H/W >= 4");
   NPVP_REQUIRE(frames * (Cout / 16) <= 65535, "npvp_conv7x7_stem: too many frames per launch (%lld)", (long long)frames);
   dim3 grid((unsigned)(((H + 15) / 16) * ((W + 15) / 16)), 1, (unsigned)(frames * (Cout / 16)));
   cudaStream_t st = (cudaStream_t)stream;
-  if (Cin == 1) conv7x7_stem_kernel<1><<<grid, 256, 0, st>>>(x, w, shift, (bf16*)out_bf16, Cout, H, W);
-  else if (Cin == 3) conv7x7_stem_kernel<3><<<grid, 256, 0, st>>>(x, w, shift, (bf16*)out_bf16, Cout, H, W);
+  if (Cin == 1) conv7x7_stem_kernel<1><<<grid, 256, 0, st>>>(x, w, shift, (h16*)out_bf16, Cout, H, W, fp16);
+  else if (Cin == 3) conv7x7_stem_kernel<3><<<grid, 256, 0, st>>>(x, w, shift, (h16*)out_bf16, Cout, H, W, fp16);
   else NPVP_REQUIRE(false, "npvp_conv7x7_stem: Cin must be 1 or 3 (got %d)", Cin);
   NPVP_LAUNCH_CHECK("conv7x7_stem_kernel");
   return NPVP_OK;
@@ -85,8 +85,8 @@ extern "C" int npvp_conv7x7_stem(const float* x, const float* w, const float* sh
 // ---------------------------------------------------------------------------------------------
 template <int COUT>
 __global__ void __launch_bounds__(256)
-conv7x7_head_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
-                    int Cin, int H, int W, int phase_major, int act) {
+conv7x7_head_kernel(const h16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+                    int Cin, int H, int W, int phase_major, int act, int fp16) {
   constexpr int CCH = 4;
   __shared__ __align__(16) float tile[CCH][22][72];          // 70 used columns, padded to 72
   __shared__ float ws[CCH][49][COUT];
@@ -105,7 +105,7 @@ conv7x7_head_kernel(const bf16* __restrict__ x, const float* __restrict__ w, con
       const int r = i / 70, col = i % 70;
       const int yy = reflect_idx(ty0 + r - 3, H), xx = reflect_idx(tx0 + col - 3, W);
       const uint2 u = __ldg(reinterpret_cast<const uint2*>(x + pixel_offset(f, yy, xx, H, W, phase_major) * Cin + c0));
-      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      const float2 a = unpack_h16x2(u.x, fp16), b = unpack_h16x2(u.y, fp16);
       tile[0][r][col] = a.x; tile[1][r][col] = a.y; tile[2][r][col] = b.x; tile[3][r][col] = b.y;
     }
     for (int i = threadIdx.x; i < CCH * 49 * COUT; i += 256) {
@@ -152,13 +152,13 @@ conv7x7_head_kernel(const bf16* __restrict__ x, const float* __restrict__ w, con
 }
 
 extern "C" int npvp_conv7x7_head(const void* x_bf16, const float* w, const float* bias, float* out, int64_t frames, int Cin,
-                                 int Cout, int H, int W, int phase_major, int act, void* stream) {
+                                 int Cout, int H, int W, int phase_major, int act, int fp16, void* stream) {
   NPVP_REQUIRE(x_bf16 && w && bias && out && frames > 0 && frames <= 65535, "npvp_conv7x7_head: bad arguments");
   NPVP_REQUIRE(Cin % 4 == 0 && H >= 4 && W >= 4 && (!phase_major || (H % 2 == 0 && W % 2 == 0)), "npvp_conv7x7_head: Cin %% 4, H/W >= 4, even H/W for phase-major input");
   dim3 grid((unsigned)(((H + 15) / 16) * ((W + 63) / 64)), 1, (unsigned)frames);
   cudaStream_t st = (cudaStream_t)stream;
-  if (Cout == 1) conv7x7_head_kernel<1><<<grid, 256, 0, st>>>((const bf16*)x_bf16, w, bias, out, Cin, H, W, phase_major, act);
-  else if (Cout == 3) conv7x7_head_kernel<3><<<grid, 256, 0, st>>>((const bf16*)x_bf16, w, bias, out, Cin, H, W, phase_major, act);
+  if (Cout == 1) conv7x7_head_kernel<1><<<grid, 256, 0, st>>>((const h16*)x_bf16, w, bias, out, Cin, H, W, phase_major, act, fp16);
+  else if (Cout == 3) conv7x7_head_kernel<3><<<grid, 256, 0, st>>>((const h16*)x_bf16, w, bias, out, Cin, H, W, phase_major, act, fp16);
   else NPVP_REQUIRE(false, "npvp_conv7x7_head: Cout must be 1 or 3 (got %d)", Cout);
   NPVP_LAUNCH_CHECK("conv7x7_head_kernel");
   return NPVP_OK;
@@ -207,8 +207,8 @@ extern "C" int npvp_im2col_nhwc(const void* x_bf16, void* out_bf16, int64_t fram
 // ---------------------------------------------------------------------------------------------
 // 2x2 max-pool of a column slice
 // ---------------------------------------------------------------------------------------------
-__global__ void maxpool2x2_cols_kernel(const bf16* __restrict__ x, int64_t ldx, int col0, int Cn, bf16* __restrict__ out,
-                                       int64_t total, int H, int W) {
+__global__ void maxpool2x2_cols_kernel(const h16* __restrict__ x, int64_t ldx, int col0, int Cn, h16* __restrict__ out,
+                                       int64_t total, int H, int W, int fp16) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % Cn);
@@ -218,17 +218,17 @@ __global__ void maxpool2x2_cols_kernel(const bf16* __restrict__ x, int64_t ldx, 
   rest /= Wo;
   const int oy = (int)(rest % Ho);
   const int64_t f = rest / Ho;
-  const bf16* p = x + (((size_t)f * H + 2 * oy) * W + 2 * ox) * ldx + col0 + c;
-  const float a = __bfloat162float(p[0]), b = __bfloat162float(p[ldx]);
-  const float d = __bfloat162float(p[(size_t)W * ldx]), e = __bfloat162float(p[(size_t)W * ldx + ldx]);
-  out[i] = __float2bfloat16(fmaxf(fmaxf(a, b), fmaxf(d, e)));
+  const h16* p = x + (((size_t)f * H + 2 * oy) * W + 2 * ox) * ldx + col0 + c;
+  const float a = h16_to_float(p[0], fp16), b = h16_to_float(p[ldx], fp16);
+  const float d = h16_to_float(p[(size_t)W * ldx], fp16), e = h16_to_float(p[(size_t)W * ldx + ldx], fp16);
+  out[i] = float_to_h16(fmaxf(fmaxf(a, b), fmaxf(d, e)), fp16);
 }
 
 extern "C" int npvp_maxpool2x2_cols(const void* x_bf16, int64_t ldx, int col0, int Cn, void* out_bf16, int64_t frames, int H, int W,
-                                    void* stream) {
+                                    int fp16, void* stream) {
   NPVP_REQUIRE(x_bf16 && out_bf16 && frames > 0 && Cn > 0 && col0 >= 0 && H % 2 == 0 && W % 2 == 0, "npvp_maxpool2x2_cols: bad arguments");
   const int64_t total = frames * (H / 2) * (W / 2) * Cn;
-  maxpool2x2_cols_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x_bf16, ldx, col0, Cn, (bf16*)out_bf16, total, H, W);
+  maxpool2x2_cols_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>((const h16*)x_bf16, ldx, col0, Cn, (h16*)out_bf16, total, H, W, fp16);
   NPVP_LAUNCH_CHECK("maxpool2x2_cols_kernel");
   return NPVP_OK;
 }
@@ -238,9 +238,9 @@ extern "C" int npvp_maxpool2x2_cols(const void* x_bf16, int64_t ldx, int col0, i
 // ---------------------------------------------------------------------------------------------
 template <int DQ>
 __global__ void __launch_bounds__(256)
-nonlocal_attention_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ kv, bf16* __restrict__ out, int HW, int HWk) {
+nonlocal_attention_kernel(const h16* __restrict__ q, int64_t ldq, const h16* __restrict__ kv, h16* __restrict__ out, int HW, int HWk, int fp16) {
   constexpr int DV = 4 * DQ, S = DV / 32, QB = 256 / S, KT = 64, ROW = DQ + DV;
-  __shared__ __align__(16) bf16 skv[KT][ROW];
+  __shared__ __align__(16) h16 skv[KT][ROW];
   const int blocks_per_frame = (HW + QB - 1) / QB;
   const int64_t f = blockIdx.x / blocks_per_frame;
   const int qi = (blockIdx.x % blocks_per_frame) * QB + (threadIdx.x % QB);
@@ -248,10 +248,10 @@ nonlocal_attention_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* _
   const bool active = qi < HW;
   float qr[DQ];
   if (active) {
-    const bf16* qp = q + ((size_t)f * HW + qi) * ldq;
+    const h16* qp = q + ((size_t)f * HW + qi) * ldq;
 #pragma unroll
     for (int d = 0; d < DQ; d += 2) {
-      const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qp + d));
+      const float2 t = unpack_h16x2(*reinterpret_cast<const uint32_t*>(qp + d), fp16);
       qr[d] = t.x; qr[d + 1] = t.y;
     }
   } else {
@@ -272,7 +272,7 @@ nonlocal_attention_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* _
       float s = 0.f;
 #pragma unroll
       for (int d = 0; d < DQ; d += 2) {
-        const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&skv[j][d]));
+        const float2 t = unpack_h16x2(*reinterpret_cast<const uint32_t*>(&skv[j][d]), fp16);
         s = fmaf(qr[d], t.x, s);
         s = fmaf(qr[d + 1], t.y, s);
       }
@@ -282,7 +282,7 @@ nonlocal_attention_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* _
       m = mn;
 #pragma unroll
       for (int d = 0; d < 32; d += 2) {
-        const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&skv[j][DQ + slice * 32 + d]));
+        const float2 t = unpack_h16x2(*reinterpret_cast<const uint32_t*>(&skv[j][DQ + slice * 32 + d]), fp16);
         o[d] = fmaf(o[d], corr, p * t.x);
         o[d + 1] = fmaf(o[d + 1], corr, p * t.y);
       }
@@ -293,27 +293,27 @@ nonlocal_attention_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* _
     uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)f * HW + qi) * DV + slice * 32);
 #pragma unroll
     for (int t = 0; t < 4; ++t)
-      dst[t] = make_uint4(pack_bf16x2(o[8 * t] * inv, o[8 * t + 1] * inv), pack_bf16x2(o[8 * t + 2] * inv, o[8 * t + 3] * inv),
-                          pack_bf16x2(o[8 * t + 4] * inv, o[8 * t + 5] * inv), pack_bf16x2(o[8 * t + 6] * inv, o[8 * t + 7] * inv));
+      dst[t] = make_uint4(pack_h16x2(o[8 * t] * inv, o[8 * t + 1] * inv, fp16), pack_h16x2(o[8 * t + 2] * inv, o[8 * t + 3] * inv, fp16),
+                          pack_h16x2(o[8 * t + 4] * inv, o[8 * t + 5] * inv, fp16), pack_h16x2(o[8 * t + 6] * inv, o[8 * t + 7] * inv, fp16));
   }
 }
 
 extern "C" int npvp_nonlocal_attention(const void* q, int64_t ldq, const void* kv, void* out, int64_t frames, int HW, int HWk, int dq,
-                                       int dv, void* stream) {
+                                       int dv, int fp16, void* stream) {
   NPVP_REQUIRE(q && kv && out && frames > 0 && HW > 0 && HWk > 0, "npvp_nonlocal_attention: bad arguments");
   NPVP_REQUIRE(dv == 4 * dq, "npvp_nonlocal_attention: expects dv = 4*dq (C/2 and C/8)");
   NPVP_REQUIRE(ldq % 2 == 0 && (uintptr_t)q % 4 == 0 && (uintptr_t)kv % 16 == 0 && (uintptr_t)out % 16 == 0, "npvp_nonlocal_attention: alignment");
   cudaStream_t st = (cudaStream_t)stream;
   const int S = dv / 32, QB = 256 / (S > 0 ? S : 1);
   const int64_t blocks = frames * ((HW + QB - 1) / QB);
-  const bf16* qq = (const bf16*)q;
-  const bf16* kk = (const bf16*)kv;
-  bf16* oo = (bf16*)out;
+  const h16* qq = (const h16*)q;
+  const h16* kk = (const h16*)kv;
+  h16* oo = (h16*)out;
   switch (dq) {
-    case 8: nonlocal_attention_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(qq, ldq, kk, oo, HW, HWk); break;
-    case 16: nonlocal_attention_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(qq, ldq, kk, oo, HW, HWk); break;
-    case 32: nonlocal_attention_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(qq, ldq, kk, oo, HW, HWk); break;
-    case 64: nonlocal_attention_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(qq, ldq, kk, oo, HW, HWk); break;
+    case 8: nonlocal_attention_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(qq, ldq, kk, oo, HW, HWk, fp16); break;
+    case 16: nonlocal_attention_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(qq, ldq, kk, oo, HW, HWk, fp16); break;
+    case 32: nonlocal_attention_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(qq, ldq, kk, oo, HW, HWk, fp16); break;
+    case 64: nonlocal_attention_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(qq, ldq, kk, oo, HW, HWk, fp16); break;
     default: NPVP_REQUIRE(false, "npvp_nonlocal_attention: dq must be 8, 16, 32 or 64 (got %d)", dq);
   }
   NPVP_LAUNCH_CHECK("nonlocal_attention_kernel");

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
@@ -81,6 +82,30 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// 16-bit storage type chosen at run time: fp16 = 0 -> bfloat16, fp16 = 1 -> IEEE half (saturating stores).
+// The autoencoder runs in half (its errors go straight to pixels), the predictor in bfloat16 (range safety).
+typedef uint16_t h16;
+__device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi, int fp16) {
+  if (fp16) {
+    __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack_h16x2(uint32_t u, int fp16) {
+  if (fp16) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return unpack_bf16x2(u);
+}
+__device__ __forceinline__ float h16_to_float(h16 v, int fp16) {
+  if (fp16) return __half2float(*reinterpret_cast<__half*>(&v));
+  return __uint_as_float((uint32_t)v << 16);
+}
+__device__ __forceinline__ h16 float_to_h16(float v, int fp16) {
+  if (fp16) { __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); return *reinterpret_cast<h16*>(&h); }
+  bf16 b = __float2bfloat16(v);
+  return *reinterpret_cast<h16*>(&b);
+}
+
 // ---------------------------------------------------------------------------------------------
 // shared GEMM epilogue: v = acc (+bias[n]) -> act -> *alpha -> +res1 -> +res2 -> relu? ; store f32 / bf16
 // ---------------------------------------------------------------------------------------------
@@ -89,9 +114,9 @@ struct EpiParams {
   const void* res1;
   const void* res2;
   float* out_f32;
-  bf16* out_bf16;
+  h16* out_bf16;      // 16-bit output (bf16 or half, see fp16)
   float alpha;
-  int act, res1_bf16, res2_bf16, post_relu;
+  int act, res1_bf16, res2_bf16, post_relu, fp16;
   int64_t ld_out, ld_res;
 };
 
@@ -100,8 +125,8 @@ __device__ __forceinline__ float epi_value(const EpiParams& e, float acc, int64_
   if (e.bias) v += __ldg(e.bias + n);
   v = apply_act(v, e.act);
   v *= e.alpha;
-  if (e.res1) v += e.res1_bf16 ? __bfloat162float(((const bf16*)e.res1)[m * e.ld_res + n]) : ((const float*)e.res1)[m * e.ld_res + n];
-  if (e.res2) v += e.res2_bf16 ? __bfloat162float(((const bf16*)e.res2)[m * e.ld_res + n]) : ((const float*)e.res2)[m * e.ld_res + n];
+  if (e.res1) v += e.res1_bf16 ? h16_to_float(((const h16*)e.res1)[m * e.ld_res + n], e.fp16) : ((const float*)e.res1)[m * e.ld_res + n];
+  if (e.res2) v += e.res2_bf16 ? h16_to_float(((const h16*)e.res2)[m * e.ld_res + n], e.fp16) : ((const float*)e.res2)[m * e.ld_res + n];
   if (e.post_relu) v = fmaxf(v, 0.0f);
   return v;
 }
@@ -112,7 +137,8 @@ static inline EpiParams make_epi(const npvp_epilogue_t* ep) {
   e.res1 = ep->res1;
   e.res2 = ep->res2;
   e.out_f32 = (float*)ep->out_f32;
-  e.out_bf16 = (bf16*)ep->out_bf16;
+  e.out_bf16 = (h16*)ep->out_bf16;
+  e.fp16 = ep->fp16;
   e.alpha = ep->alpha;
   e.act = ep->act;
   e.res1_bf16 = ep->res1_bf16;

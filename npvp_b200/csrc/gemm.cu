@@ -136,9 +136,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor, kind::f16: D=f32 (bit 4), A/B format at [7,10)/[10,13) (0 = f16, 1 = bf16), both K-major,
+// N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_f16kind(int M, int N, int fp16) {
+  return (1u << 4) | (fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 template <int BN>
@@ -197,7 +198,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ---------------- MMA issuer (one thread) ----------------
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+      const uint32_t idesc = make_idesc_f16kind(kBM, BN, ep.fp16);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_k_blocks; ++kb) {
@@ -242,14 +243,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * ep.ld_out + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+              dst[j] = make_uint4(pack_h16x2(v[8 * j], v[8 * j + 1], ep.fp16), pack_h16x2(v[8 * j + 2], v[8 * j + 3], ep.fp16),
+                                  pack_h16x2(v[8 * j + 4], v[8 * j + 5], ep.fp16), pack_h16x2(v[8 * j + 6], v[8 * j + 7], ep.fp16));
           }
         } else {
           for (int j = 0; j < 32 && n0 + j < N; ++j) {
             const float v = epi_value(ep, __uint_as_float(r[j]), m, n0 + j);
             if (ep.out_f32) ep.out_f32[m * ep.ld_out + n0 + j] = v;
-            if (ep.out_bf16) ep.out_bf16[m * ep.ld_out + n0 + j] = __float2bfloat16(v);
+            if (ep.out_bf16) ep.out_bf16[m * ep.ld_out + n0 + j] = float_to_h16(v, ep.fp16);
           }
         }
       }
@@ -268,9 +269,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // =============================================================================================
 // 64x64 tile, 16-deep k-slab, 256 threads, 4x4 outputs per thread.  TA in {bf16, float}.
 template <typename TA>
-__device__ __forceinline__ float to_f32(TA v);
-template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
-template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(TA v, int fp16);
+template <> __device__ __forceinline__ float to_f32<float>(float v, int) { return v; }
+template <> __device__ __forceinline__ float to_f32<h16>(h16 v, int fp16) { return h16_to_float(v, fp16); }
 
 template <typename TA>
 __global__ void __launch_bounds__(256)
@@ -285,8 +286,8 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t lda, const TA* __restrict__ W
     for (int i = threadIdx.x; i < 64 * 16; i += 256) {
       const int r = i >> 4, c = i & 15;
       const int64_t m = m0 + r, n = n0 + r, k = k0 + c;
-      As[c][r] = (m < M && k < K) ? to_f32<TA>(A[m * lda + k]) : 0.0f;
-      Ws[c][r] = (n < N && k < K) ? to_f32<TA>(W[n * ldw + k]) : 0.0f;
+      As[c][r] = (m < M && k < K) ? to_f32<TA>(A[m * lda + k], ep.fp16) : 0.0f;
+      Ws[c][r] = (n < N && k < K) ? to_f32<TA>(W[n * ldw + k], ep.fp16) : 0.0f;
     }
     __syncthreads();
 #pragma unroll
@@ -311,7 +312,7 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t lda, const TA* __restrict__ W
       if (n >= N) continue;
       const float v = epi_value(ep, acc[i][j], m, n);
       if (ep.out_f32) ep.out_f32[m * ep.ld_out + n] = v;
-      if (ep.out_bf16) ep.out_bf16[m * ep.ld_out + n] = __float2bfloat16(v);
+      if (ep.out_bf16) ep.out_bf16[m * ep.ld_out + n] = float_to_h16(v, ep.fp16);
     }
   }
 }
@@ -336,14 +337,14 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // 2-D bf16 tensor map: inner dim = K (contiguous), outer dim = rows; box = 64 x box_rows; 128B swizzle; OOB -> 0.
-static int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+static int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows, int fp16) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) { npvp_set_error("cuTensorMapEncodeTiled entry point unavailable"); return NPVP_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { npvp_set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld K=%lld ld=%lld", (int)r, (long long)rows, (long long)K, (long long)ld); return NPVP_ERR_CUDA; }
@@ -361,9 +362,9 @@ static int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw
     attr_set = true;
   }
   CUtensorMap ta, tb;
-  int rc = make_tmap_2d(&ta, A, M, K, lda, kBM);
+  int rc = make_tmap_2d(&ta, A, M, K, lda, kBM, e.fp16);
   if (rc) return rc;
-  rc = make_tmap_2d(&tb, W, N, K, ldw, BN);
+  rc = make_tmap_2d(&tb, W, N, K, ldw, BN, e.fp16);
   if (rc) return rc;
   NPVP_REQUIRE(ceil_div64(M, kBM) <= 65535, "gemm_tcgen05: M chunk too large");
   dim3 grid((unsigned)ceil_div64(N, BN), (unsigned)ceil_div64(M, kBM));
@@ -402,9 +403,10 @@ extern "C" int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   EpiParams e = make_epi(ep);
   const bool vec_ok = (ep->ld_out % 8 == 0) && (!ep->out_f32 || (uintptr_t)ep->out_f32 % 16 == 0) &&
                       (!ep->out_bf16 || (uintptr_t)ep->out_bf16 % 16 == 0);
-  // AUTO: tensor path whenever the TMA boxes (128 x 64 for A, BN x 64 for W) fit inside the operands; tiny problems stay on CUDA cores
+  // AUTO: tensor path whenever the operands are TMA-expressible.  The choice must not depend on M (the batch), otherwise a
+  // clip would be computed differently alone and inside a batch; TMA zero-fills boxes that overhang small operands.
   if (backend == NPVP_GEMM_AUTO)
-    backend = (tma_compatible(A, lda, W, ldw, K) && vec_ok && M >= kBM && N >= 64 && K >= kBK) ? NPVP_GEMM_TCGEN05 : NPVP_GEMM_SIMT;
+    backend = (tma_compatible(A, lda, W, ldw, K) && vec_ok && K >= kBK) ? NPVP_GEMM_TCGEN05 : NPVP_GEMM_SIMT;
   if (backend == NPVP_GEMM_TCGEN05) {
     NPVP_REQUIRE(tma_compatible(A, lda, W, ldw, K) && vec_ok, "npvp_gemm_bf16: operands not 16-byte aligned / K,ld not multiples of 8 for the TMA path");
     if (N > 64) return launch_tcgen05<128>(A, lda, W, ldw, M, N, K, e, st);
@@ -412,8 +414,8 @@ extern "C" int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   }
   NPVP_REQUIRE(backend == NPVP_GEMM_SIMT, "npvp_gemm_bf16: unknown backend %d", backend);
   dim3 grid((unsigned)ceil_div64(N, 64), (unsigned)ceil_div64(M, 64));
-  gemm_simt_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, e);
-  NPVP_LAUNCH_CHECK("gemm_simt_kernel<bf16>");
+  gemm_simt_kernel<h16><<<grid, 256, 0, st>>>((const h16*)A, lda, (const h16*)W, ldw, M, N, K, e);
+  NPVP_LAUNCH_CHECK("gemm_simt_kernel<h16>");
   return NPVP_OK;
 }
 

@@ -147,7 +147,7 @@ extern "C" int npvp_ln_posfuse(const float* x, const float* ln_w, const float* l
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                      float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int64_t rows, int relu) {
+                      float* __restrict__ out_f32, h16* __restrict__ out_bf16, int64_t rows, int relu, int fp16) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -169,14 +169,14 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     if (out_f32) reinterpret_cast<float4*>(out_f32 + row * kC)[j * 32 + lane] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    if (out_bf16) reinterpret_cast<uint2*>(out_bf16 + row * kC)[j * 32 + lane] = make_uint2(pack_bf16x2(v[4 * j], v[4 * j + 1]), pack_bf16x2(v[4 * j + 2], v[4 * j + 3]));
+    if (out_bf16) reinterpret_cast<uint2*>(out_bf16 + row * kC)[j * 32 + lane] = make_uint2(pack_h16x2(v[4 * j], v[4 * j + 1], fp16), pack_h16x2(v[4 * j + 2], v[4 * j + 3], fp16));
   }
 }
 
 extern "C" int npvp_layernorm_rows(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16,
-                                   int64_t rows, int relu, void* stream) {
+                                   int64_t rows, int relu, int fp16, void* stream) {
   NPVP_REQUIRE(x && w && b && (out_f32 || out_bf16) && rows > 0, "npvp_layernorm_rows: bad arguments");
-  layernorm_rows_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, w, b, out_f32, (bf16*)out_bf16, rows, relu);
+  layernorm_rows_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, w, b, out_f32, (h16*)out_bf16, rows, relu, fp16);
   NPVP_LAUNCH_CHECK("layernorm_rows_kernel");
   return NPVP_OK;
 }
@@ -478,7 +478,7 @@ extern "C" int npvp_latent_reparam(const float* mulv, int64_t ld, const float* e
 // layout changes: per frame [C, HW] <-> [HW, C] through 32x32 smem tiles
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-nchw_to_tokens_kernel(const float* __restrict__ x, float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int C, int HW) {
+nchw_to_tokens_kernel(const float* __restrict__ x, float* __restrict__ out_f32, h16* __restrict__ out_bf16, int C, int HW, int fp16) {
   __shared__ float tile[32][33];
   const size_t base = (size_t)blockIdx.z * C * HW;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -493,21 +493,21 @@ nchw_to_tokens_kernel(const float* __restrict__ x, float* __restrict__ out_f32, 
     if (p < HW && c < C) {
       const float v = tile[tx][r];
       if (out_f32) out_f32[base + (size_t)p * C + c] = v;
-      if (out_bf16) out_bf16[base + (size_t)p * C + c] = __float2bfloat16(v);
+      if (out_bf16) out_bf16[base + (size_t)p * C + c] = float_to_h16(v, fp16);
     }
   }
 }
 
-extern "C" int npvp_nchw_to_tokens(const float* x, float* out_f32, void* out_bf16, int64_t frames, int64_t C, int64_t HW, void* stream) {
+extern "C" int npvp_nchw_to_tokens(const float* x, float* out_f32, void* out_bf16, int64_t frames, int64_t C, int64_t HW, int fp16, void* stream) {
   NPVP_REQUIRE(x && (out_f32 || out_bf16) && frames > 0 && frames <= 65535 && C > 0 && HW > 0, "npvp_nchw_to_tokens: bad arguments");
   dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)ceil_div64(C, 32), (unsigned)frames);
-  nchw_to_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out_f32, (bf16*)out_bf16, (int)C, (int)HW);
+  nchw_to_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out_f32, (h16*)out_bf16, (int)C, (int)HW, fp16);
   NPVP_LAUNCH_CHECK("nchw_to_tokens_kernel");
   return NPVP_OK;
 }
 
 __global__ void __launch_bounds__(256)
-tokens_to_nchw_kernel(const float* __restrict__ x_f32, const bf16* __restrict__ x_bf16, float* __restrict__ out, int C, int HW, int relu) {
+tokens_to_nchw_kernel(const float* __restrict__ x_f32, const h16* __restrict__ x_bf16, float* __restrict__ out, int C, int HW, int relu, int fp16) {
   __shared__ float tile[32][33];
   const size_t base = (size_t)blockIdx.z * C * HW;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -515,7 +515,7 @@ tokens_to_nchw_kernel(const float* __restrict__ x_f32, const bf16* __restrict__ 
   for (int r = ty; r < 32; r += 8) {
     const int p = p0 + r, c = c0 + tx;
     float v = 0.f;
-    if (p < HW && c < C) v = x_f32 ? __ldg(x_f32 + base + (size_t)p * C + c) : __bfloat162float(x_bf16[base + (size_t)p * C + c]);
+    if (p < HW && c < C) v = x_f32 ? __ldg(x_f32 + base + (size_t)p * C + c) : h16_to_float(x_bf16[base + (size_t)p * C + c], fp16);
     tile[r][tx] = relu ? fmaxf(v, 0.f) : v;
   }
   __syncthreads();
@@ -526,10 +526,10 @@ tokens_to_nchw_kernel(const float* __restrict__ x_f32, const bf16* __restrict__ 
 }
 
 extern "C" int npvp_tokens_to_nchw(const float* x_f32, const void* x_bf16, float* out, int64_t frames, int64_t C, int64_t HW,
-                                   int relu, void* stream) {
+                                   int relu, int fp16, void* stream) {
   NPVP_REQUIRE((x_f32 || x_bf16) && out && frames > 0 && frames <= 65535 && C > 0 && HW > 0, "npvp_tokens_to_nchw: bad arguments");
   dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)ceil_div64(C, 32), (unsigned)frames);
-  tokens_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_f32, (const bf16*)x_bf16, out, (int)C, (int)HW, relu);
+  tokens_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_f32, (const h16*)x_bf16, out, (int)C, (int)HW, relu, fp16);
   NPVP_LAUNCH_CHECK("tokens_to_nchw_kernel");
   return NPVP_OK;
 }

@@ -242,7 +242,7 @@ class PredictorEngine:
     # ------------------------------------------------------------------------------------------
     # NAR decoder (VidHRFormer.py:126-161, 198-245)
     # ------------------------------------------------------------------------------------------
-    def decode(self, z, mem, mem_bf, beta_o, gamma_o, beta_p, gamma_p, n, To, Tp, relu_out=True):
+    def decode(self, z, mem, mem_bf, beta_o, gamma_o, beta_p, gamma_p, n, To, Tp, relu_out=True, out16=torch.bfloat16):
         op, ws = _lib.ops(), self.ws
         M, Mo = n * Tp * TOK, n * To * TOK
         y = ws.f32("y_dec", M, C)
@@ -275,7 +275,7 @@ class PredictorEngine:
             op.layernorm_rows(y, L.n6.w, L.n6.b, out_bf16=a)
             self._conv_ffn(y, a, L.ffn_x, n * Tp, "dec")
         out = ws.f32("dec_out", M, C)
-        out_bf = ws.bf16("dec_out_bf16", M, C)
+        out_bf = ws.h16("dec_out_16", out16, M, C)
         op.layernorm_rows(y, self.norm_dec.w, self.norm_dec.b, out_f32=out, out_bf16=out_bf, relu=relu_out)
         return out, out_bf
 
@@ -304,7 +304,7 @@ class PredictorEngine:
         op.tokens_to_nchw(tok.view(n * T, TOK, C), out.view(n * T, C, TOK))
         return out
 
-    def run(self, observed, channels_last=False, bf16_out=False):
+    def run(self, observed, channels_last=False, out16=None):
         mod = self.mod
         x, n, To = self._to_tokens(observed, channels_last, "x_enc")
         oc, pc = mod.observed_coor, mod.predict_coor
@@ -325,8 +325,9 @@ class PredictorEngine:
             assert tuple(eps.shape) == (n, C, 8, 8), f"latent noise must be {(n, C, 8, 8)}, got {tuple(eps.shape)}"
         z, mulv = self.latent(evt, n, eps)
         mod.last_latent = (z, mulv)
-        out, out_bf = self.decode(z, mem, mem_bf, beta_o, gamma_o, beta_p, gamma_p, n, To, Tp)
-        if bf16_out:        # engine-internal hand-off to the frame decoder (a view of the workspace, consumed at once)
+        out, out_bf = self.decode(z, mem, mem_bf, beta_o, gamma_o, beta_p, gamma_p, n, To, Tp,
+                                  out16=out16 or torch.bfloat16)
+        if out16 is not None:   # engine-internal hand-off to the frame decoder (a view of the workspace, consumed at once)
             assert channels_last
             return out_bf.view(n, Tp, 8, 8, C)
         return self._from_tokens(out, n, Tp, channels_last)

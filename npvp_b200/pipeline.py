@@ -88,7 +88,7 @@ class NPVPInference(nn.Module):
             self.predictor.injected_eps = eps
         try:
             feats = self.VPTR_Enc.forward_tokens(past_frames)
-            pred = self.predictor.forward_tokens(feats, bf16_out=True)
+            pred = self.predictor.forward_tokens(feats, out16=self.VPTR_Dec._engine().dt)
             return self.VPTR_Dec.forward_tokens(pred)
         finally:
             if eps is not None:

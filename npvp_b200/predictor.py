@@ -108,12 +108,12 @@ class Predictor(_EngineModule):
                                       "Predictor.py:311-327) is not on the inference hot path")
         return self._engine().run(observed_features)
 
-    def forward_tokens(self, observed_tokens, bf16_out=False):
-        """Engine-internal: channels-last (N,To,H,W,C) in -> channels-last (N,Tp,H,W,C) out (fp32, or the bf16
-        workspace view the frame decoder consumes directly when ``bf16_out``)."""
+    def forward_tokens(self, observed_tokens, out16=None):
+        """Engine-internal: channels-last (N,To,H,W,C) in -> channels-last (N,Tp,H,W,C) out (fp32, or the 16-bit
+        workspace view of dtype ``out16`` that the frame decoder consumes directly)."""
         self._guard(observed_tokens)
         self._coords_ready()
-        return self._engine().run(observed_tokens, channels_last=True, bf16_out=bf16_out)
+        return self._engine().run(observed_tokens, channels_last=True, out16=out16)
 
     def evt_coding_forward(self, x, pos_beta, pos_gamma):
         """EVT_Former + temporal mean (Predictor.py:337-350).  x (N,T,C,H,W); pos_beta/gamma (T*H*W, C)."""

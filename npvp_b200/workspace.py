@@ -29,6 +29,9 @@ class Workspace:
     def bf16(self, name, *shape):
         return self.get(name, shape, torch.bfloat16)
 
+    def h16(self, name, dtype, *shape):
+        return self.get(name, shape, dtype)
+
     def f32(self, name, *shape):
         return self.get(name, shape, torch.float32)
 

@@ -17,6 +17,10 @@ import torch.nn.functional as F
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 EPS = 1e-5
 
+# the specification is fp32: keep cuDNN / cuBLAS from silently using TF32 when the specs run on a GPU
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 
 def _act(v, act):
     if act == ACT_RELU:
@@ -49,7 +53,7 @@ class SpecOps:
     def gemm(self, a, w, *, bias=None, act=ACT_NONE, alpha=1.0, res1=None, res2=None, out_f32=None, out_bf16=None,
              post_relu=False, backend=None):
         self.launches += 1
-        assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+        assert a.dtype in (torch.bfloat16, torch.float16) and w.dtype == a.dtype
         v = a.float() @ w.float().t()
         if bias is not None:
             v = v + bias
@@ -63,7 +67,7 @@ class SpecOps:
         if out_f32 is not None:
             out_f32.copy_(v)
         if out_bf16 is not None:
-            out_bf16.copy_(v.to(torch.bfloat16))
+            out_bf16.copy_(v.clamp(-65504, 65504).to(out_bf16.dtype))
 
     def gemm_f32(self, a, w, bias, act, out):
         self.launches += 1
@@ -105,7 +109,7 @@ class SpecOps:
         if out_f32 is not None:
             out_f32.copy_(v.reshape(out_f32.shape))
         if out_bf16 is not None:
-            out_bf16.copy_(v.reshape(out_bf16.shape).to(torch.bfloat16))
+            out_bf16.copy_(v.reshape(out_bf16.shape).to(out_bf16.dtype))
 
     def frame_ln_gelu_residual(self, h, w_hwc, b_hwc, y):
         self.launches += 1
@@ -207,7 +211,7 @@ class SpecOps:
         if out_f32 is not None:
             out_f32.copy_(t.reshape(out_f32.shape))
         if out_bf16 is not None:
-            out_bf16.copy_(t.reshape(out_bf16.shape).to(torch.bfloat16))
+            out_bf16.copy_(t.reshape(out_bf16.shape).to(out_bf16.dtype))
 
     def tokens_to_nchw(self, x, out, relu=False):
         self.launches += 1
@@ -226,7 +230,7 @@ class SpecOps:
         img = x.reshape(-1, Cin, H, W)
         wt = w.reshape(7, 7, Cin, Cout).permute(3, 2, 0, 1)
         o = F.conv2d(F.pad(img, (3, 3, 3, 3), mode="reflect"), wt, shift)
-        out.copy_(torch.relu(o).permute(0, 2, 3, 1).reshape(out.shape).to(torch.bfloat16))
+        out.copy_(torch.relu(o).permute(0, 2, 3, 1).reshape(out.shape).to(out.dtype))
 
     def conv7x7_head(self, x, w, bias, out, Cin, Cout, H, W, phase_major, act):
         self.launches += 1
@@ -258,7 +262,7 @@ class SpecOps:
     def maxpool2x2_cols(self, x, col0, Cn, out, frames, H, W):
         self.launches += 1
         t = x[:, col0:col0 + Cn].float().reshape(frames, H // 2, 2, W // 2, 2, Cn)
-        out.copy_(t.amax(dim=(2, 4)).reshape(out.shape).to(torch.bfloat16))
+        out.copy_(t.amax(dim=(2, 4)).reshape(out.shape).to(out.dtype))
 
     def nonlocal_attention(self, q, kv, out, frames, HW, HWk, dq, dv):
         self.launches += 1
@@ -266,4 +270,4 @@ class SpecOps:
         K = kv[:, :dq].float().reshape(frames, HWk, dq)
         V = kv[:, dq:].float().reshape(frames, HWk, dv)
         a = torch.softmax(Q @ K.transpose(1, 2), dim=-1)
-        out.copy_((a @ V).reshape(out.shape).to(torch.bfloat16))
+        out.copy_((a @ V).reshape(out.shape).to(out.dtype))

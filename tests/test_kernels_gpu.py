@@ -33,28 +33,33 @@ def close(a, b, rel, what=""):
 
 
 GEMM_SHAPES = [(256, 512, 512), (192, 1024, 512), (128, 2048, 512), (1024, 512, 2048), (4096, 256, 4608),
-               (130, 64, 64), (1000, 48, 64), (640, 384, 512), (300, 512, 128), (64, 1024, 256), (4096, 128, 288)]
+               (130, 64, 64), (1000, 48, 64), (512, 64, 32), (64, 256, 40), (640, 384, 512), (300, 512, 128), (64, 1024, 256), (4096, 128, 288)]
 
 
+H16 = [torch.bfloat16, torch.float16]
+
+
+@pytest.mark.parametrize("dt", H16)
 @pytest.mark.parametrize("backend", [2, 1, 0])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-def test_gemm_plain(op, spec, backend, M, N, K):
-    a, w = rn(M, K, seed=1, dtype=torch.bfloat16), rn(N, K, seed=2, scale=K ** -0.5, dtype=torch.bfloat16)
+def test_gemm_plain(op, spec, backend, M, N, K, dt):
+    a, w = rn(M, K, seed=1, dtype=dt), rn(N, K, seed=2, scale=K ** -0.5, dtype=dt)
     bias = rn(N, seed=3)
     o1, o2 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
-    b1, b2 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16), torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    b1, b2 = torch.empty(M, N, device=DEV, dtype=dt), torch.empty(M, N, device=DEV, dtype=dt)
     op.gemm(a, w, bias=bias, out_f32=o1, out_bf16=b1, backend=backend)
     spec.gemm(a, w, bias=bias, out_f32=o2, out_bf16=b2)
     torch.cuda.synchronize()
     close(o1, o2, 2e-3, f"gemm f32 backend={backend}")
-    close(b1, b2, 1e-2, f"gemm bf16 backend={backend}")
+    close(b1, b2, 1e-2 if dt == torch.bfloat16 else 2e-3, f"gemm 16-bit backend={backend}")
 
 
+@pytest.mark.parametrize("dt", H16)
 @pytest.mark.parametrize("backend", [2, 1])
-def test_gemm_epilogues(op, spec, backend):
+def test_gemm_epilogues(op, spec, backend, dt):
     M, N, K = 384, 512, 1024
-    a, w = rn(M, K, seed=1, dtype=torch.bfloat16), rn(N, K, seed=2, scale=K ** -0.5, dtype=torch.bfloat16)
-    bias, r1, r2 = rn(N, seed=3), rn(M, N, seed=4), rn(M, N, seed=5, dtype=torch.bfloat16)
+    a, w = rn(M, K, seed=1, dtype=dt), rn(N, K, seed=2, scale=K ** -0.5, dtype=dt)
+    bias, r1, r2 = rn(N, seed=3), rn(M, N, seed=4), rn(M, N, seed=5, dtype=dt)
     for kw in (dict(act=2), dict(act=1, alpha=0.6, res1=r1, res2=r2), dict(res1=r2, post_relu=True), dict(act=1, res1=r1)):
         o1, o2 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
         op.gemm(a, w, bias=bias, out_f32=o1, backend=backend, **kw)
@@ -63,7 +68,7 @@ def test_gemm_epilogues(op, spec, backend):
     # in-place residual stream update (out aliases res1), strided A view
     x = rn(M, N, seed=6)
     x2 = x.clone()
-    big = rn(M, 2 * K, seed=7, dtype=torch.bfloat16)
+    big = rn(M, 2 * K, seed=7, dtype=dt)
     op.gemm(big[:, K:], w, bias=bias, res1=x, out_f32=x, backend=backend)
     spec.gemm(big[:, K:], w, bias=bias, res1=x2, out_f32=x2)
     close(x, x2, 2e-3, "in-place residual")
@@ -174,13 +179,18 @@ def test_event_encoder_pieces(op, spec):
         close(z1, z2, 1e-5, "latent_reparam")
 
 
-def test_layout_kernels(op, spec):
+@pytest.mark.parametrize("dt", H16)
+def test_layout_kernels(op, spec, dt):
     x = rn(5, 512, 64, seed=1)
     t1, t2 = torch.empty(5, 64, 512, device=DEV), torch.empty(5, 64, 512, device=DEV)
-    b1 = torch.empty(5, 64, 512, device=DEV, dtype=torch.bfloat16)
+    b1 = torch.empty(5, 64, 512, device=DEV, dtype=dt)
     op.nchw_to_tokens(x, t1, b1)
     spec.nchw_to_tokens(x, t2, None)
-    assert torch.equal(t1, t2) and torch.equal(b1, t2.to(torch.bfloat16))
+    assert torch.equal(t1, t2) and torch.equal(b1, t2.to(dt))
+    l1, l2 = torch.empty(320, 512, device=DEV, dtype=dt), torch.empty(320, 512, device=DEV, dtype=dt)
+    op.layernorm_rows(x.reshape(320, 512), torch.ones(512, device=DEV), torch.zeros(512, device=DEV), None, l1, True)
+    spec.layernorm_rows(x.reshape(320, 512), torch.ones(512, device=DEV), torch.zeros(512, device=DEV), None, l2, True)
+    close(l1, l2, 1e-2, "layernorm 16-bit out")
     back = torch.empty(5, 512, 64, device=DEV)
     op.tokens_to_nchw(t1, back)
     assert torch.equal(back, x)
@@ -188,20 +198,22 @@ def test_layout_kernels(op, spec):
     assert torch.equal(back, torch.relu(b1.float()).permute(0, 2, 1))
 
 
+@pytest.mark.parametrize("dt", H16)
 @pytest.mark.parametrize("Cin,Cout,HW", [(3, 32, 128), (1, 64, 64), (3, 64, 40)])
-def test_conv7x7_stem(op, spec, Cin, Cout, HW):
+def test_conv7x7_stem(op, spec, Cin, Cout, HW, dt):
     x = rn(3, Cin, HW, HW, seed=1)
     w, sh = rn(49 * Cin, Cout, seed=2, scale=0.1), rn(Cout, seed=3, scale=0.2)
-    o1 = torch.empty(3 * HW * HW, Cout, device=DEV, dtype=torch.bfloat16)
+    o1 = torch.empty(3 * HW * HW, Cout, device=DEV, dtype=dt)
     o2 = torch.empty_like(o1)
     op.conv7x7_stem(x, w, sh, o1, Cin, Cout, HW, HW)
     spec.conv7x7_stem(x, w, sh, o2, Cin, Cout, HW, HW)
     close(o1, o2, 1e-2, "conv7x7_stem")
 
 
+@pytest.mark.parametrize("dt", H16)
 @pytest.mark.parametrize("Cin,Cout,HW,phase,act", [(32, 3, 128, True, 3), (64, 1, 64, True, 4), (32, 3, 48, False, 3)])
-def test_conv7x7_head(op, spec, Cin, Cout, HW, phase, act):
-    x = rn(2 * HW * HW, Cin, seed=1, dtype=torch.bfloat16)
+def test_conv7x7_head(op, spec, Cin, Cout, HW, phase, act, dt):
+    x = rn(2 * HW * HW, Cin, seed=1, dtype=dt)
     w, b = rn(49 * Cin, Cout, seed=2, scale=0.03), rn(Cout, seed=3, scale=0.2)
     o1, o2 = torch.empty(2, Cout, HW, HW, device=DEV), torch.empty(2, Cout, HW, HW, device=DEV)
     op.conv7x7_head(x, w, b, o1, Cin, Cout, HW, HW, phase, act)
@@ -222,16 +234,17 @@ def test_im2col(op, spec, H, C, KH, stride, pad, mode, phase):
     assert torch.equal(o1, o2)
 
 
+@pytest.mark.parametrize("dt", H16)
 @pytest.mark.parametrize("C,H", [(64, 64), (128, 32), (256, 16), (512, 8)])
-def test_nonlocal_pieces(op, spec, C, H):
+def test_nonlocal_pieces(op, spec, C, H, dt):
     frames, dq, dv = 2, C // 8, C // 2
-    qkv = rn(frames * H * H, 2 * dq + dv, seed=1, scale=0.7, dtype=torch.bfloat16)
-    kv1 = torch.empty(frames * H * H // 4, dq + dv, device=DEV, dtype=torch.bfloat16)
+    qkv = rn(frames * H * H, 2 * dq + dv, seed=1, scale=0.7, dtype=dt)
+    kv1 = torch.empty(frames * H * H // 4, dq + dv, device=DEV, dtype=dt)
     kv2 = torch.empty_like(kv1)
     op.maxpool2x2_cols(qkv, dq, dq + dv, kv1, frames, H, H)
     spec.maxpool2x2_cols(qkv, dq, dq + dv, kv2, frames, H, H)
     assert torch.equal(kv1, kv2)
-    o1 = torch.empty(frames * H * H, dv, device=DEV, dtype=torch.bfloat16)
+    o1 = torch.empty(frames * H * H, dv, device=DEV, dtype=dt)
     o2 = torch.empty_like(o1)
     op.nonlocal_attention(qkv[:, :dq], kv1, o1, frames, H * H, H * H // 4, dq, dv)
     spec.nonlocal_attention(qkv[:, :dq], kv1, o2, frames, H * H, H * H // 4, dq, dv)

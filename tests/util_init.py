@@ -95,5 +95,6 @@ def reset_shared_norm(predictor_cls) -> None:
     case does not depend on which cases ran before."""
     import inspect
     norm = inspect.signature(predictor_cls.__init__).parameters["norm"].default
+    norm.to("cpu")        # a previous .cuda() of any Predictor moved the shared instance too
     norm.weight.fill_(1.0)
     norm.bias.zero_()
