@@ -227,13 +227,24 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    if args.profile:          # one warm rollout + one profiled rollout, nothing else (for `ncu -k ...` / launch lists)
+        model.rollout(x_dev, N_FUTURE)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        model.rollout(x_dev, N_FUTURE)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     step_device()                                              # build engines / first-touch allocations
     ops.reset_launch_count()
     step_device()
-    launches_per_step = ops.launch_count()
+    launches_per_step = ops.launch_count()        # kernels of one step; graph replays launch the same kernels
+    if args.graphs:
+        model.use_cuda_graphs(True)
+        step_device()                              # capture
     total_ms = timed(step_device, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = timed(step_e2e, max(2, min(args.steps, 10)), 1)
@@ -241,6 +252,7 @@ def run_ours(args):
 
     roof = None
     if rank == 0:
+        model.use_cuda_graphs(False)                           # per-launch events need eager launches
         with GemmTimer(ops) as gt:
             model.rollout(x_dev, N_FUTURE)
         s = gt.summary()
@@ -270,7 +282,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "clips_per_gpu": B, "global_clips": B * world, "frames_per_clip": N_FUTURE,
                        "parallelism": f"dp{world} batch-sharded, all_gather of frames" if world > 1 else "single GPU",
                        "l2": "256 MiB buffer written between timed steps; per-step activations also exceed the 126 MB L2",
-                       "arith": "bf16 operands, fp32 accumulate / residual / statistics"},
+                       "arith": "predictor bf16 / autoencoder fp16 operands, fp32 accumulate / residual / statistics",
+                       "cuda_graphs": bool(args.graphs)},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
                     "steps": e2e_steps, "api": "NPVPInference.rollout on pinned host tensors"},
@@ -291,6 +304,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="run one warm-up + one rollout between cudaProfilerStart/Stop and exit")
+    ap.add_argument("--graphs", type=int, default=1, help="replay each forward as a CUDA graph (1) or launch eagerly (0)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

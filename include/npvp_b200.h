@@ -39,6 +39,7 @@ extern "C" {
 #define NPVP_GEMM_AUTO 0
 #define NPVP_GEMM_TCGEN05 1 /* TMA-fed tcgen05.mma, TMEM accumulators */
 #define NPVP_GEMM_SIMT 2    /* CUDA-core reference path for debugging / odd shapes */
+#define NPVP_GEMM_TCGEN05_V1 3 /* first-generation (non-persistent, one tile per CTA) tcgen05 kernel, kept for A/B runs */
 
 #define NPVP_PAD_ZERO 0
 #define NPVP_PAD_REFLECT 1

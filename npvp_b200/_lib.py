@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
-GEMM_AUTO, GEMM_TCGEN05, GEMM_SIMT = 0, 1, 2
+GEMM_AUTO, GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_V1 = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT, PAD_REPLICATE = 0, 1, 2
 ATTN_SPATIAL, ATTN_TEMPORAL = 0, 1
 
@@ -118,7 +118,7 @@ class Ops:
 
     def __init__(self, lib: Optional[C.CDLL] = None):
         self.lib = lib or load_library()
-        self.gemm_backend = {"auto": GEMM_AUTO, "tcgen05": GEMM_TCGEN05, "simt": GEMM_SIMT}[
+        self.gemm_backend = {"auto": GEMM_AUTO, "tcgen05": GEMM_TCGEN05, "simt": GEMM_SIMT, "tcgen05_v1": GEMM_TCGEN05_V1}[
             os.environ.get("NPVP_B200_GEMM", "auto")]
 
     # -- plumbing -------------------------------------------------------------------------------

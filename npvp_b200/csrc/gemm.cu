@@ -264,6 +264,202 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+
+// =============================================================================================
+// tcgen05 GEMM kernel, v2: persistent + warp-specialised + double-buffered TMEM + coalesced epilogue
+// =============================================================================================
+// One CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so the CTAs running at any moment
+// share A row-blocks in L2 and the whole W).  Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4-7 = epilogue.  The accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile
+// i overlaps the main loop of tile i+1.  Epilogue: tcgen05.ld (row per thread) -> bias/act/alpha -> XOR-swizzled smem
+// transpose -> 4 rows x 128 B per warp instruction: residual loads and fp32 / 16-bit stores are fully coalesced.
+constexpr int kGemm2Threads = 256;
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 5 : 6);
+  static constexpr int kStagingBytes = 4 * 32 * 32 * 4;                     // one 32x32 fp32 tile per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;          // 128 / 256 / 512
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemm2Threads, 1)
+gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       int64_t M, int64_t N, int64_t K, EpiParams ep) {
+  using Cfg = Gemm2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  float* staging = (float*)(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bars = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;        // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * Cfg::kStages + 2;   // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_k_blocks = (int)((K + kBK - 1) / kBK);
+  const int n_tiles = (int)((N + BN - 1) / BN);
+  const int64_t m_tiles = (M + kBM - 1) / kBM;
+  const int64_t num_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 4);      // one arrival per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          ptx::tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
+          ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, n_blk * BN);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16kind(kBM, BN, ep.fp16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t bdesc = make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue ----------------
+    const int quad = warp & 3;                                      // TMEM lane quadrant of this warp
+    float* stg = staging + quad * (32 * 32);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int sub_row = lane >> 3, chunk = lane & 7;                // coalesced layout: 4 rows x 8 float4 per instruction
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int64_t m_base = (int64_t)m_blk * kBM + quad * 32;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        const int64_t n0 = (int64_t)n_blk * BN + c;
+        if (n0 >= N) break;                                          // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c), r);
+        ptx::tmem_ld_wait();
+        // bias / activation / alpha in the row-per-thread layout, then swizzled store (float4 chunk j -> j ^ (lane & 7))
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float vv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v = __uint_as_float(r[4 * j + e]);
+            const int64_t n = n0 + 4 * j + e;
+            if (ep.bias && n < N) v += __ldg(ep.bias + n);
+            vv[e] = apply_act(v, ep.act) * ep.alpha;
+          }
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + sub_row;
+          const int64_t m = m_base + row;
+          const int64_t n = n0 + chunk * 4;
+          float4 q = *reinterpret_cast<const float4*>(stg + row * 32 + ((chunk ^ (row & 7)) << 2));
+          if (m < M && n < N) {                                      // N % 4 == 0 on this path
+            if (ep.res1) {
+              if (ep.res1_bf16) {
+                const uint2 u = *reinterpret_cast<const uint2*>((const h16*)ep.res1 + m * ep.ld_res + n);
+                const float2 a = unpack_h16x2(u.x, ep.fp16), b = unpack_h16x2(u.y, ep.fp16);
+                q.x += a.x; q.y += a.y; q.z += b.x; q.w += b.y;
+              } else {
+                const float4 a = *reinterpret_cast<const float4*>((const float*)ep.res1 + m * ep.ld_res + n);
+                q.x += a.x; q.y += a.y; q.z += a.z; q.w += a.w;
+              }
+            }
+            if (ep.res2) {
+              if (ep.res2_bf16) {
+                const uint2 u = *reinterpret_cast<const uint2*>((const h16*)ep.res2 + m * ep.ld_res + n);
+                const float2 a = unpack_h16x2(u.x, ep.fp16), b = unpack_h16x2(u.y, ep.fp16);
+                q.x += a.x; q.y += a.y; q.z += b.x; q.w += b.y;
+              } else {
+                const float4 a = *reinterpret_cast<const float4*>((const float*)ep.res2 + m * ep.ld_res + n);
+                q.x += a.x; q.y += a.y; q.z += a.z; q.w += a.w;
+              }
+            }
+            if (ep.post_relu) { q.x = fmaxf(q.x, 0.f); q.y = fmaxf(q.y, 0.f); q.z = fmaxf(q.z, 0.f); q.w = fmaxf(q.w, 0.f); }
+            if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + m * ep.ld_out + n) = q;
+            if (ep.out_bf16)
+              *reinterpret_cast<uint2*>(ep.out_bf16 + m * ep.ld_out + n) = make_uint2(pack_h16x2(q.x, q.y, ep.fp16), pack_h16x2(q.z, q.w, ep.fp16));
+          }
+        }
+        __syncwarp();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // =============================================================================================
 // SIMT kernels
 // =============================================================================================
@@ -373,6 +569,37 @@ static int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw
   return NPVP_OK;
 }
 
+
+static int g_num_sms = 0;
+
+template <int BN>
+static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                             const EpiParams& e, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_v2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (err != cudaSuccess) { npvp_set_error("cudaFuncSetAttribute(v2, smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(&ta, A, M, K, lda, kBM, e.fp16);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tb, W, N, K, ldw, BN, e.fp16);
+  if (rc) return rc;
+  const int64_t tiles = ceil_div64(M, kBM) * ceil_div64(N, BN);
+  const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
+  gemm_tcgen05_v2_kernel<BN><<<grid, kGemm2Threads, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K, e);
+  NPVP_LAUNCH_CHECK("gemm_tcgen05_v2_kernel");
+  return NPVP_OK;
+}
+
 static bool tma_compatible(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t K) {
   return ((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && (lda % 8 == 0) && (ldw % 8 == 0) && (K % 8 == 0);
 }
@@ -407,8 +634,14 @@ extern "C" int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   // clip would be computed differently alone and inside a batch; TMA zero-fills boxes that overhang small operands.
   if (backend == NPVP_GEMM_AUTO)
     backend = (tma_compatible(A, lda, W, ldw, K) && vec_ok && K >= kBK) ? NPVP_GEMM_TCGEN05 : NPVP_GEMM_SIMT;
-  if (backend == NPVP_GEMM_TCGEN05) {
+  if (backend == NPVP_GEMM_TCGEN05 || backend == NPVP_GEMM_TCGEN05_V1) {
     NPVP_REQUIRE(tma_compatible(A, lda, W, ldw, K) && vec_ok, "npvp_gemm_bf16: operands not 16-byte aligned / K,ld not multiples of 8 for the TMA path");
+    const bool res_ok = (!(ep->res1 || ep->res2)) || (ep->ld_res % 4 == 0 && (uintptr_t)ep->res1 % 16 == 0 && (uintptr_t)ep->res2 % 16 == 0);
+    if (backend == NPVP_GEMM_TCGEN05 && N % 4 == 0 && res_ok) {       // persistent kernel; tile width never depends on M
+      if (N >= 256) return launch_tcgen05_v2<256>(A, lda, W, ldw, M, N, K, e, st);
+      if (N > 64) return launch_tcgen05_v2<128>(A, lda, W, ldw, M, N, K, e, st);
+      return launch_tcgen05_v2<64>(A, lda, W, ldw, M, N, K, e, st);
+    }
     if (N > 64) return launch_tcgen05<128>(A, lda, W, ldw, M, N, K, e, st);
     return launch_tcgen05<64>(A, lda, W, ldw, M, N, K, e, st);
   }

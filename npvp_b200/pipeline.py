@@ -81,37 +81,59 @@ class NPVPInference(nn.Module):
         return rec_past, rec_future, pred
 
     # -- throughput path: Enc(context) -> Predictor -> Dec(predictions), channels-last in between ----
-    def predict(self, past_frames, eps: Optional[torch.Tensor] = None):
-        """past_frames (N,To,Cimg,H,W) fp32 CUDA -> predicted frames (N,Tp,Cimg,H,W) fp32.
-        ``eps``: optional injected latent noise (N,512,8,8) for NPVP-S (default: torch.randn like the reference)."""
-        if eps is not None:
-            self.predictor.injected_eps = eps
+    def _predict_eager(self, past_frames, eps):
+        self.predictor.injected_eps = eps
         try:
             feats = self.VPTR_Enc.forward_tokens(past_frames)
             pred = self.predictor.forward_tokens(feats, out16=self.VPTR_Dec._engine().dt)
             return self.VPTR_Dec.forward_tokens(pred)
         finally:
-            if eps is not None:
-                self.predictor.injected_eps = None
+            self.predictor.injected_eps = None
+
+    def use_cuda_graphs(self, enabled: bool = True):
+        """Replay ``predict`` as one CUDA graph per (batch shape, timestamps, weights version): the ~430 kernel launches
+        of a forward are launch-bound at small batch.  The returned tensor is then a graph-owned buffer that the next
+        ``predict`` call with the same shapes overwrites."""
+        self._graphs = {} if enabled else None
+        return self
+
+    def _graph_key(self, x):
+        p = self.predictor
+        return (tuple(x.shape), x.device, p.observed_coor.data_ptr(), p.predict_coor.data_ptr(), tuple(p.observed_coor.shape),
+                tuple(p.predict_coor.shape), self.VPTR_Enc._weights_version(), self.VPTR_Dec._weights_version(), p._weights_version())
+
+    def predict(self, past_frames, eps: Optional[torch.Tensor] = None):
+        """past_frames (N,To,Cimg,H,W) fp32 CUDA -> predicted frames (N,Tp,Cimg,H,W) fp32.
+        ``eps``: optional injected latent noise (N,512,8,8) for NPVP-S (default: torch.randn like the reference)."""
+        graphs = getattr(self, "_graphs", None)
+        if graphs is None:
+            return self._predict_eager(past_frames, eps)
+        key = self._graph_key(past_frames)
+        g = graphs.get(key)
+        if g is None:
+            g = graphs[key] = _GraphedPredict(self, past_frames)
+        return g(past_frames, eps)
 
     def rollout(self, past_frames, num_future: int, eps_list: Optional[Sequence[torch.Tensor]] = None):
         """Block-autoregressive VFP: predict len(tp_list) frames, feed the last To predictions back as context
         (image space), repeat until ``num_future`` frames exist; the last block is truncated."""
         To, Tp = past_frames.shape[1], int(self.tp_list.shape[0])
         assert To == int(self.to_list.shape[0])
-        outs, ctx, done, blk = [], past_frames, 0, 0
+        out, ctx, done, blk = None, past_frames, 0, 0
         while done < num_future:
             eps = None if eps_list is None else eps_list[blk]
-            pred = self.predict(ctx, eps)
+            pred = self.predict(ctx, eps)                    # may be a graph-owned buffer: copy out before the next block
+            if out is None:
+                out = torch.empty((pred.shape[0], num_future) + tuple(pred.shape[2:]), dtype=pred.dtype, device=pred.device)
             take = min(Tp, num_future - done)
-            outs.append(pred[:, :take])
+            out[:, done:done + take].copy_(pred[:, :take])
             done += take
             blk += 1
             if Tp >= To:
-                ctx = pred[:, Tp - To:Tp]
+                ctx = out[:, done - To:done] if take == Tp else pred[:, Tp - To:Tp]
             else:
                 ctx = torch.cat([ctx[:, Tp:], pred], dim=1)
-        return torch.cat(outs, dim=1)
+        return out
 
     # -- pixel space (utils/dataset.py:860-886, utils/train_summary.py:244-245) ----------------------
     def to_pixels(self, frames):
@@ -122,6 +144,37 @@ class NPVPInference(nn.Module):
         m = torch.tensor(mean, device=frames.device, dtype=frames.dtype).view(1, 1, -1, 1, 1)
         s = torch.tensor(std, device=frames.device, dtype=frames.dtype).view(1, 1, -1, 1, 1)
         return (frames * s + m).clamp(0, 1)
+
+
+class _GraphedPredict:
+    """One captured forward: static input / noise buffers, graph-owned output."""
+
+    def __init__(self, model: NPVPInference, example: torch.Tensor):
+        self.stochastic = bool(model.predictor.stochastic)
+        self.x = torch.empty_like(example, dtype=torch.float32).contiguous()
+        self.x.copy_(example)
+        n = example.shape[0]
+        self.eps = torch.zeros((n, 512, 8, 8), device=example.device) if self.stochastic else None
+        side = torch.cuda.Stream(device=example.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up: builds engines, workspaces, kernel attributes
+            for _ in range(2):
+                model._predict_eager(self.x, self.eps)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = model._predict_eager(self.x, self.eps)
+
+    def __call__(self, x, eps):
+        self.x.copy_(x)
+        if self.stochastic:
+            if eps is None:
+                self.eps.normal_()                          # sampled outside the graph, like torch.randn in the reference
+            else:
+                self.eps.copy_(eps)
+        self.graph.replay()
+        return self.out
 
 
 def build_from_config(cfg, device="cuda", seed: Optional[int] = 0) -> NPVPInference:

@@ -32,7 +32,7 @@ def close(a, b, rel, what=""):
     assert err <= rel * max(ref, 1e-6), f"{what}: max err {err:.4e} vs ref max {ref:.4e} (rel {err / max(ref, 1e-6):.3e} > {rel})"
 
 
-GEMM_SHAPES = [(256, 512, 512), (192, 1024, 512), (128, 2048, 512), (1024, 512, 2048), (4096, 256, 4608),
+GEMM_SHAPES = [(40000, 512, 512), (20480, 2048, 512), (256, 512, 512), (192, 1024, 512), (128, 2048, 512), (1024, 512, 2048), (4096, 256, 4608),
                (130, 64, 64), (1000, 48, 64), (512, 64, 32), (64, 256, 40), (640, 384, 512), (300, 512, 128), (64, 1024, 256), (4096, 128, 288)]
 
 
@@ -40,7 +40,7 @@ H16 = [torch.bfloat16, torch.float16]
 
 
 @pytest.mark.parametrize("dt", H16)
-@pytest.mark.parametrize("backend", [2, 1, 0])
+@pytest.mark.parametrize("backend", [2, 1, 3, 0])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_plain(op, spec, backend, M, N, K, dt):
     a, w = rn(M, K, seed=1, dtype=dt), rn(N, K, seed=2, scale=K ** -0.5, dtype=dt)
@@ -55,7 +55,7 @@ def test_gemm_plain(op, spec, backend, M, N, K, dt):
 
 
 @pytest.mark.parametrize("dt", H16)
-@pytest.mark.parametrize("backend", [2, 1])
+@pytest.mark.parametrize("backend", [2, 1, 3])
 def test_gemm_epilogues(op, spec, backend, dt):
     M, N, K = 384, 512, 1024
     a, w = rn(M, K, seed=1, dtype=dt), rn(N, K, seed=2, scale=K ** -0.5, dtype=dt)
