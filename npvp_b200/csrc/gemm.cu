@@ -266,22 +266,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
 
 // =============================================================================================
-// tcgen05 GEMM kernel, v2: persistent + warp-specialised + double-buffered TMEM + coalesced epilogue
+// tcgen05 GEMM kernel, v2: persistent + warp-specialised + double-buffered TMEM + coalesced, specialised epilogue
 // =============================================================================================
 // One CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so the CTAs running at any moment
 // share A row-blocks in L2 and the whole W).  Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4-7 = epilogue.  The accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile
-// i overlaps the main loop of tile i+1.  Epilogue: tcgen05.ld (row per thread) -> bias/act/alpha -> XOR-swizzled smem
-// transpose -> 4 rows x 128 B per warp instruction: residual loads and fp32 / 16-bit stores are fully coalesced.
-constexpr int kGemm2Threads = 256;
+// allocator, warps 4-11 = epilogue (two warps per TMEM lane quadrant, each owning half of the tile's columns).
+// The accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the main loop of tile i+1.
+// Epilogue data path: tcgen05.ld (row per thread) -> raw accumulators through an XOR-swizzled 32x32 smem transpose ->
+// "coalesced" layout (a warp instruction covers 4 rows x 128 B) where bias (one float4 per lane per chunk), activation,
+// alpha, residual loads and the fp32 / 16-bit stores all happen.  ACT / RES / OUT are compile-time (r01 profile: the
+// first version spent >100 instructions per element on run-time flag checks and was epilogue-bound at 6 % tensor-active).
+constexpr int kGemm2Threads = 384;
+constexpr int kEpiWarps = 8;
 
+// RES: 0 none, 1 res1 fp32, 2 res1 16-bit, 3 res1 + res2 16-bit, -1 run-time.   OUT: 0 16-bit, 1 fp32, 2 both, -1 run-time.
 template <int BN>
 struct Gemm2Cfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 5 : 6);
-  static constexpr int kStagingBytes = 4 * 32 * 32 * 4;                     // one 32x32 fp32 tile per epilogue warp
+  static constexpr int kStagingBytes = kEpiWarps * 32 * 32 * 4;             // one 32x32 fp32 tile per epilogue warp
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;          // 128 / 256 / 512
 };
@@ -290,7 +295,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
 }
 
-template <int BN>
+template <int ACT>
+__device__ __forceinline__ float act_ct(float v, int act_rt) {
+  if (ACT == NPVP_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == NPVP_ACT_GELU) return gelu_erf(v);
+  if (ACT < 0) return apply_act(v, act_rt);
+  return v;
+}
+
+__device__ __forceinline__ void add_res(float4& q, const void* res, int is16, int fp16, int64_t off) {
+  if (is16) {
+    const uint2 u = *reinterpret_cast<const uint2*>((const h16*)res + off);
+    const float2 a = unpack_h16x2(u.x, fp16), b = unpack_h16x2(u.y, fp16);
+    q.x += a.x; q.y += a.y; q.z += b.x; q.w += b.y;
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>((const float*)res + off);
+    q.x += a.x; q.y += a.y; q.z += a.z; q.w += a.w;
+  }
+}
+
+template <int BN, int ACT, int RES, int OUT>
 __global__ void __launch_bounds__(kGemm2Threads, 1)
 gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        int64_t M, int64_t N, int64_t K, EpiParams ep) {
@@ -323,7 +347,7 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 4);      // one arrival per epilogue warp
+      ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps);      // one arrival per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -382,67 +406,71 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
     const int quad = warp & 3;                                      // TMEM lane quadrant of this warp
-    float* stg = staging + quad * (32 * 32);
+    const int half = (warp - 4) >> 2;                               // which half of the tile's columns
+    float* stg = staging + (warp - 4) * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
     const int sub_row = lane >> 3, chunk = lane & 7;                // coalesced layout: 4 rows x 8 float4 per instruction
+    const bool has_bias = ep.bias != nullptr;
+    const int fp16 = ep.fp16;
+    const float alpha = ep.alpha;
+    constexpr int kColsPerWarp = BN / 2;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const int64_t m_base = (int64_t)m_blk * kBM + quad * 32;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * kColsPerWarp; c < (half + 1) * kColsPerWarp; c += 32) {
         const int64_t n0 = (int64_t)n_blk * BN + c;
         if (n0 >= N) break;                                          // warp-uniform
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c), r);
         ptx::tmem_ld_wait();
-        // bias / activation / alpha in the row-per-thread layout, then swizzled store (float4 chunk j -> j ^ (lane & 7))
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float vv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float v = __uint_as_float(r[4 * j + e]);
-            const int64_t n = n0 + 4 * j + e;
-            if (ep.bias && n < N) v += __ldg(ep.bias + n);
-            vv[e] = apply_act(v, ep.act) * ep.alpha;
-          }
-          *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-        }
+        for (int j = 0; j < 8; ++j)                                  // float4 chunk j of row `lane` -> slot j ^ (lane & 7)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
+        const int64_t n = n0 + chunk * 4;
+        const bool col_ok = n < N;                                   // N % 4 == 0 on this path
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+        // Residuals may alias the output (in-place residual-stream update), so the compiler cannot hoist their loads
+        // above the stores: fetch all of this chunk's residual vectors first (8 independent 128-bit loads in flight).
+        float4 rs[8];
+        if (RES != 0) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int64_t m = m_base + it * 4 + sub_row;
+            rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && col_ok) {
+              const int64_t roff = m * ep.ld_res + n;
+              if (RES == 1) add_res(rs[it], ep.res1, 0, fp16, roff);
+              if (RES == 2 || RES == 3) add_res(rs[it], ep.res1, 1, fp16, roff);
+              if (RES == 3) add_res(rs[it], ep.res2, 1, fp16, roff);
+              if (RES < 0) {
+                if (ep.res1) add_res(rs[it], ep.res1, ep.res1_bf16, fp16, roff);
+                if (ep.res2) add_res(rs[it], ep.res2, ep.res2_bf16, fp16, roff);
+              }
+            }
+          }
+        }
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + sub_row;
           const int64_t m = m_base + row;
-          const int64_t n = n0 + chunk * 4;
           float4 q = *reinterpret_cast<const float4*>(stg + row * 32 + ((chunk ^ (row & 7)) << 2));
-          if (m < M && n < N) {                                      // N % 4 == 0 on this path
-            if (ep.res1) {
-              if (ep.res1_bf16) {
-                const uint2 u = *reinterpret_cast<const uint2*>((const h16*)ep.res1 + m * ep.ld_res + n);
-                const float2 a = unpack_h16x2(u.x, ep.fp16), b = unpack_h16x2(u.y, ep.fp16);
-                q.x += a.x; q.y += a.y; q.z += b.x; q.w += b.y;
-              } else {
-                const float4 a = *reinterpret_cast<const float4*>((const float*)ep.res1 + m * ep.ld_res + n);
-                q.x += a.x; q.y += a.y; q.z += a.z; q.w += a.w;
-              }
-            }
-            if (ep.res2) {
-              if (ep.res2_bf16) {
-                const uint2 u = *reinterpret_cast<const uint2*>((const h16*)ep.res2 + m * ep.ld_res + n);
-                const float2 a = unpack_h16x2(u.x, ep.fp16), b = unpack_h16x2(u.y, ep.fp16);
-                q.x += a.x; q.y += a.y; q.z += b.x; q.w += b.y;
-              } else {
-                const float4 a = *reinterpret_cast<const float4*>((const float*)ep.res2 + m * ep.ld_res + n);
-                q.x += a.x; q.y += a.y; q.z += a.z; q.w += a.w;
-              }
-            }
+          if (m < M && col_ok) {
+            q.x = act_ct<ACT>(q.x + b4.x, ep.act) * alpha;
+            q.y = act_ct<ACT>(q.y + b4.y, ep.act) * alpha;
+            q.z = act_ct<ACT>(q.z + b4.z, ep.act) * alpha;
+            q.w = act_ct<ACT>(q.w + b4.w, ep.act) * alpha;
+            if (RES != 0) { q.x += rs[it].x; q.y += rs[it].y; q.z += rs[it].z; q.w += rs[it].w; }
             if (ep.post_relu) { q.x = fmaxf(q.x, 0.f); q.y = fmaxf(q.y, 0.f); q.z = fmaxf(q.z, 0.f); q.w = fmaxf(q.w, 0.f); }
-            if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + m * ep.ld_out + n) = q;
-            if (ep.out_bf16)
-              *reinterpret_cast<uint2*>(ep.out_bf16 + m * ep.ld_out + n) = make_uint2(pack_h16x2(q.x, q.y, ep.fp16), pack_h16x2(q.z, q.w, ep.fp16));
+            const int64_t ooff = m * ep.ld_out + n;
+            if (OUT == 1 || OUT == 2 || (OUT < 0 && ep.out_f32)) *reinterpret_cast<float4*>(ep.out_f32 + ooff) = q;
+            if (OUT == 0 || OUT == 2 || (OUT < 0 && ep.out_bf16))
+              *reinterpret_cast<uint2*>(ep.out_bf16 + ooff) = make_uint2(pack_h16x2(q.x, q.y, fp16), pack_h16x2(q.z, q.w, fp16));
           }
         }
         __syncwarp();
@@ -572,16 +600,25 @@ static int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw
 
 static int g_num_sms = 0;
 
-template <int BN>
-static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
-                             const EpiParams& e, cudaStream_t st) {
+template <int BN, int ACT, int RES, int OUT>
+static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, int64_t M, int64_t N, int64_t K, const EpiParams& e,
+                          unsigned grid, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_v2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_v2_kernel<BN, ACT, RES, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (err != cudaSuccess) { npvp_set_error("cudaFuncSetAttribute(v2, smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
     attr_set = true;
   }
+  gemm_tcgen05_v2_kernel<BN, ACT, RES, OUT><<<grid, kGemm2Threads, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K, e);
+  NPVP_LAUNCH_CHECK("gemm_tcgen05_v2_kernel");
+  return NPVP_OK;
+}
+
+// Epilogue specialisations used by the engines; anything else runs the run-time-flag instantiation <-1,-1,-1>.
+template <int BN>
+static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                             const EpiParams& e, cudaStream_t st) {
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -595,9 +632,21 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
   if (rc) return rc;
   const int64_t tiles = ceil_div64(M, kBM) * ceil_div64(N, BN);
   const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
-  gemm_tcgen05_v2_kernel<BN><<<grid, kGemm2Threads, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K, e);
-  NPVP_LAUNCH_CHECK("gemm_tcgen05_v2_kernel");
-  return NPVP_OK;
+  const int res = !e.res1 ? (e.res2 ? -1 : 0) : (!e.res2 ? (e.res1_bf16 ? 2 : 1) : ((e.res1_bf16 && e.res2_bf16) ? 3 : -1));
+  const int out = (e.out_f32 && e.out_bf16) ? 2 : (e.out_f32 ? 1 : 0);
+  const int act = e.act;
+#define NPVP_V2_CASE(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_>(ta, tb, M, N, K, e, grid, st)
+  NPVP_V2_CASE(NPVP_ACT_NONE, 0, 0);   // projections -> 16-bit
+  NPVP_V2_CASE(NPVP_ACT_GELU, 0, 0);   // linear1
+  NPVP_V2_CASE(NPVP_ACT_RELU, 0, 0);   // conv + BN + ReLU
+  NPVP_V2_CASE(NPVP_ACT_NONE, 1, 1);   // out-proj / linear2: fp32 residual stream update
+  NPVP_V2_CASE(NPVP_ACT_NONE, 0, 1);   // fc2 -> h3, latent heads
+  NPVP_V2_CASE(NPVP_ACT_RELU, 2, 0);   // F3D conv: ReLU(BN(conv)) + x
+  NPVP_V2_CASE(NPVP_ACT_RELU, 3, 0);   // non-local out_proj: y + gamma*ReLU(BN(.)) + x
+  NPVP_V2_CASE(NPVP_ACT_NONE, 2, 0);   // ResnetBlock second conv + skip
+  NPVP_V2_CASE(NPVP_ACT_NONE, 2, 1);   // ... last block: fp32 tokens out
+#undef NPVP_V2_CASE
+  return launch_v2_inst<BN, -1, -1, -1>(ta, tb, M, N, K, e, grid, st);
 }
 
 static bool tma_compatible(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t K) {

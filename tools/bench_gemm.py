@@ -10,6 +10,9 @@ def main():
     M = int(os.environ.get("M", 40960))
     shapes = [(M, 512, 512, "res"), (M, 1024, 512, "bf16"), (M, 2048, 512, "bf16"), (M, 512, 2048, "f32"), (M, 1024, 512, "gelu"),
               (M, 512, 1024, "res"), (M // 5, 512, 512, "bf16"), (8192, 256, 4608, "bf16"), (M * 8, 128, 256, "bf16"), (M * 8, 64, 576, "bf16")]
+    if os.environ.get("SHAPES"):
+        shapes = [shapes[int(i)] for i in os.environ["SHAPES"].split(",")]
+    backends = [b for b in (("v1", 3), ("v2", 1)) if os.environ.get("ONLY", b[0]) == b[0]]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for (m, n, k, kind) in shapes:
         a = torch.randn(m, k, device=dev).to(torch.bfloat16)
@@ -25,7 +28,7 @@ def main():
         else: kw.update(out_bf16=ob)
         line = f"M={m:7d} N={n:5d} K={k:5d} {kind:5s}"
         ref = None
-        for name, be in (("v1", 3), ("v2", 1)):
+        for name, be in backends:
             for _ in range(3):
                 op.gemm(a, w, backend=be, **kw)
             ts = []

@@ -38,7 +38,8 @@ def main():
         esd, psd, dsd = model.VPTR_Enc.state_dict(), model.predictor.state_dict(), model.VPTR_Dec.state_dict()
         nd, nr, outl = cfg.AE.n_downsampling, cfg.AE.num_res_blocks, cfg.AE.out_layer
         f_ref = O.resnet_encoder(esd, x, nd, nr)
-        p_ref = O.predictor_forward(psd, f_ref, psd["observed_coor"], psd["predict_coor"], stoch, eps if stoch else None)
+        oc, pc = model.predictor.observed_coor, model.predictor.predict_coor      # (buffers are absent from the state_dict with rand_context)
+        p_ref = O.predictor_forward(psd, f_ref, oc, pc, stoch, eps if stoch else None)
         o_ref = O.resnet_decoder(dsd, p_ref, nd, outl)
         model = model.cuda()
         model.predictor.injected_eps = eps.cuda() if stoch else None
