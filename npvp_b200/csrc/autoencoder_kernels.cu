@@ -252,7 +252,7 @@ nonlocal_attention_kernel(const h16* __restrict__ q, int64_t ldq, const h16* __r
 #pragma unroll
     for (int d = 0; d < DQ; d += 2) {
       const float2 t = unpack_h16x2(*reinterpret_cast<const uint32_t*>(qp + d), fp16);
-      qr[d] = t.x; qr[d + 1] = t.y;
+      qr[d] = t.x * 1.4426950408889634f; qr[d + 1] = t.y * 1.4426950408889634f;   // scores in log2 units
     }
   } else {
 #pragma unroll
@@ -268,23 +268,45 @@ nonlocal_attention_kernel(const h16* __restrict__ q, int64_t ldq, const h16* __r
     const uint4* src = reinterpret_cast<const uint4*>(kv + ((size_t)f * HWk + k0) * ROW);
     for (int i = threadIdx.x; i < nk * ROW / 8; i += 256) reinterpret_cast<uint4*>(&skv[0][0])[i] = __ldg(src + i);
     __syncthreads();
-    for (int j = 0; j < nk; ++j) {
-      float s = 0.f;
+    // keys in blocks of 8: one running-max update / accumulator rescale per block instead of per key, and exp2 on
+    // log2(e)-prescaled scores (softmax is shift-invariant, the scale folds into q): halves the MUFU work.
+    for (int j0 = 0; j0 < nk; j0 += 8) {
+      float sc[8];
+      float bm = -INFINITY;
 #pragma unroll
-      for (int d = 0; d < DQ; d += 2) {
-        const float2 t = unpack_h16x2(*reinterpret_cast<const uint32_t*>(&skv[j][d]), fp16);
-        s = fmaf(qr[d], t.x, s);
-        s = fmaf(qr[d + 1], t.y, s);
+      for (int jj = 0; jj < 8; ++jj) {
+        float s = 0.f;
+        if (j0 + jj < nk) {
+#pragma unroll
+          for (int d = 0; d < DQ; d += 2) {
+            const float2 t = unpack_h16x2(*reinterpret_cast<const uint32_t*>(&skv[j0 + jj][d]), fp16);
+            s = fmaf(qr[d], t.x, s);
+            s = fmaf(qr[d + 1], t.y, s);
+          }
+        } else {
+          s = -INFINITY;
+        }
+        sc[jj] = s;
+        bm = fmaxf(bm, s);
       }
-      const float mn = fmaxf(m, s);
-      const float corr = expf(m - mn), p = expf(s - mn);
-      l = l * corr + p;
+      const float mn = fmaxf(m, bm);
+      const float corr = ex2_approx(m - mn);          // m = -inf on the first block -> 0
       m = mn;
+      l *= corr;
 #pragma unroll
-      for (int d = 0; d < 32; d += 2) {
-        const float2 t = unpack_h16x2(*reinterpret_cast<const uint32_t*>(&skv[j][DQ + slice * 32 + d]), fp16);
-        o[d] = fmaf(o[d], corr, p * t.x);
-        o[d + 1] = fmaf(o[d + 1], corr, p * t.y);
+      for (int d = 0; d < 32; ++d) o[d] *= corr;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        if (j0 + jj < nk) {
+          const float p = ex2_approx(sc[jj] - mn);
+          l += p;
+#pragma unroll
+          for (int d = 0; d < 32; d += 2) {
+            const float2 t = unpack_h16x2(*reinterpret_cast<const uint32_t*>(&skv[j0 + jj][DQ + slice * 32 + d]), fp16);
+            o[d] = fmaf(p, t.x, o[d]);
+            o[d + 1] = fmaf(p, t.y, o[d + 1]);
+          }
+        }
       }
     }
   }

@@ -38,8 +38,22 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // ---------------------------------------------------------------------------------------------
 // math
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_erf(float x) {   // nn.GELU() default: exact erf form
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// nn.GELU() default (erf form): x * Phi(x).  erf via Abramowitz-Stegun 7.1.26 (one rcp + one ex2 + 5 FMA): measured
+// max |gelu - exact| = 4.1e-7 over [-8, 8], i.e. below fp32 round-off of the surrounding LayerNorms, at ~22 instructions
+// instead of ~38 for erff().  The conv-FFN evaluates 2 x 131072 GELUs per frame, which made erff the single largest
+// instruction consumer of the memory-bound kernels (r01 profile).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float h = 0.5f * p * t * ex2_approx(-z * z * 1.4426950408889634f);   // 0.5 * erfc(|x| / sqrt 2)
+  return x * (x >= 0.f ? 1.0f - h : h);
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
