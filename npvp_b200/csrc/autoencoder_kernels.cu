@@ -80,88 +80,125 @@ extern "C" int npvp_conv7x7_stem(const float* x, const float* w, const float* sh
 }
 
 // ---------------------------------------------------------------------------------------------
-// head: bf16 NHWC (or phase-major) features -> fp32 NCHW image, + bias + tanh/sigmoid.
-// block = 16 rows x 64 cols of output; thread = 4 adjacent pixels x COUT channels; input staged 4 channels at a time.
+// head: 16-bit NHWC (or phase-major) features -> fp32 NCHW image, reflect-pad 3, + bias + tanh/sigmoid.
+// Cout is 1 or 3, so a 128-row UMMA tile would stream 3 KB of A per output pixel for almost no math; instead the
+// input tile (8 rows x 64 cols + halo, all channels) is staged ONCE in shared memory and every warp walks the 49 taps
+// with warp-level mma.sync.m16n8k16: A = 16 consecutive pixels x 16 channels straight out of the tile (ldmatrix.x4,
+// pixel stride padded by 16 B so the 8 row addresses hit distinct banks), B = the tap's weights (N padded to 8),
+// fp32 accumulators.  The first SIMT version was FMA-bound at 2.6 ms per launch (r01 profile).
 // ---------------------------------------------------------------------------------------------
-template <int COUT>
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816_ae(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int fp16) {
+  if (fp16) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
+
+constexpr int kHeadTY = 8, kHeadTX = 64;                       // output tile per block (8 warps: one output row each)
+
+template <int CIN>
 __global__ void __launch_bounds__(256)
 conv7x7_head_kernel(const h16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
-                    int Cin, int H, int W, int phase_major, int act, int fp16) {
-  constexpr int CCH = 4;
-  __shared__ __align__(16) float tile[CCH][22][72];          // 70 used columns, padded to 72
-  __shared__ float ws[CCH][49][COUT];
+                    int Cout, int H, int W, int phase_major, int act, int fp16) {
+  constexpr int PS = CIN + 8;                                   // padded pixel stride (halves)
+  constexpr int TW = kHeadTX + 6, TH = kHeadTY + 6, CB = CIN / 16;
+  extern __shared__ __align__(16) uint8_t head_smem[];
+  h16* tile = reinterpret_cast<h16*>(head_smem);                // [TH][TW][PS]
+  h16* wb = tile + TH * TW * PS;                                // [49][CB][8][16]  B fragments: [n][k]
   const int f = blockIdx.z;
-  const int tiles_x = (W + 63) / 64;
-  const int ty0 = (blockIdx.x / tiles_x) * 16, tx0 = (blockIdx.x % tiles_x) * 64;
-  const int ly = threadIdx.x / 16, lx4 = (threadIdx.x % 16) * 4;
-  float acc[4][COUT];
-#pragma unroll
-  for (int p = 0; p < 4; ++p)
-#pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[p][co] = 0.f;
-  for (int c0 = 0; c0 < Cin; c0 += CCH) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 22 * 70; i += 256) {
-      const int r = i / 70, col = i % 70;
-      const int yy = reflect_idx(ty0 + r - 3, H), xx = reflect_idx(tx0 + col - 3, W);
-      const uint2 u = __ldg(reinterpret_cast<const uint2*>(x + pixel_offset(f, yy, xx, H, W, phase_major) * Cin + c0));
-      const float2 a = unpack_h16x2(u.x, fp16), b = unpack_h16x2(u.y, fp16);
-      tile[0][r][col] = a.x; tile[1][r][col] = a.y; tile[2][r][col] = b.x; tile[3][r][col] = b.y;
-    }
-    for (int i = threadIdx.x; i < CCH * 49 * COUT; i += 256) {
-      const int c = i / (49 * COUT), t = (i / COUT) % 49, co = i % COUT;
-      ws[c][t][co] = __ldg(w + ((size_t)t * Cin + c0 + c) * COUT + co);
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int c = 0; c < CCH; ++c)
-#pragma unroll 1
-      for (int ky = 0; ky < 7; ++ky) {
-        float in[10];
-        const float* row = &tile[c][ly + ky][lx4];
-        const float4 q0 = *reinterpret_cast<const float4*>(row), q1 = *reinterpret_cast<const float4*>(row + 4);
-        const float2 q2 = *reinterpret_cast<const float2*>(row + 8);
-        in[0] = q0.x; in[1] = q0.y; in[2] = q0.z; in[3] = q0.w; in[4] = q1.x; in[5] = q1.y; in[6] = q1.z; in[7] = q1.w;
-        in[8] = q2.x; in[9] = q2.y;
-#pragma unroll
-        for (int kx = 0; kx < 7; ++kx)
-#pragma unroll
-          for (int co = 0; co < COUT; ++co) {
-            const float wv = ws[c][ky * 7 + kx][co];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) acc[p][co] = fmaf(in[p + kx], wv, acc[p][co]);
-          }
-      }
+  const int tiles_x = (W + kHeadTX - 1) / kHeadTX;
+  const int ty0 = (blockIdx.x / tiles_x) * kHeadTY, tx0 = (blockIdx.x % tiles_x) * kHeadTX;
+  // stage the input tile (16-byte vectors of 8 channels), reflect padding resolved here
+  constexpr int VPP = CIN / 8;
+  for (int i = threadIdx.x; i < TH * TW * VPP; i += 256) {
+    const int v = i % VPP, px = i / VPP;
+    const int r = px / TW, c = px % TW;
+    const int yy = reflect_idx(ty0 + r - 3, H), xx = reflect_idx(tx0 + c - 3, W);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + pixel_offset(f, yy, xx, H, W, phase_major) * CIN) + v);
+    *reinterpret_cast<uint4*>(tile + (size_t)px * PS + v * 8) = u;
   }
-  const int oy = ty0 + ly;
-  if (oy < H) {
+  // weights fp32 [(tap, ci), Cout] -> 16-bit [tap][cb][n][k], zero for n >= Cout
+  for (int i = threadIdx.x; i < 49 * CB * 8 * 16; i += 256) {
+    const int k = i & 15, n = (i >> 4) & 7, cb = (i >> 7) % CB, tap = i / (128 * CB);
+    const float v = (n < Cout) ? __ldg(w + ((size_t)tap * CIN + cb * 16 + k) * Cout + n) : 0.f;
+    wb[i] = float_to_h16(v, fp16);
+  }
+  __syncthreads();
+  const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int lm_px = ((lane >> 3) & 1) * 8 + (lane & 7);        // ldmatrix.x4 row supplied by this lane: pixel within the group
+  const int lm_ch = (lane >> 4) * 8;                            //                                     channel half
+  float acc[4][4];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) {
-      const float b = __ldg(bias + co);
+  for (int g = 0; g < 4; ++g) { acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f; }
+#pragma unroll 1
+  for (int ky = 0; ky < 7; ++ky) {
+    const h16* trow = tile + (size_t)(wrp + ky) * TW * PS;
+#pragma unroll 1
+    for (int kx = 0; kx < 7; ++kx) {
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int ox = tx0 + lx4 + p;
-        if (ox < W) {
-          float v = acc[p][co] + b;
-          v = (act == NPVP_ACT_TANH) ? tanhf(v) : (act == NPVP_ACT_SIGMOID ? 1.0f / (1.0f + expf(-v)) : v);
-          out[(((size_t)f * COUT + co) * H + oy) * W + ox] = v;
+      for (int cb = 0; cb < CB; ++cb) {
+        const uint32_t* bp = reinterpret_cast<const uint32_t*>(wb + (((ky * 7 + kx) * CB + cb) * 8 + gid) * 16);
+        const uint32_t b0 = bp[tig], b1 = bp[4 + tig];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t a[4];
+          ldsm_x4(a, trow + (size_t)(g * 16 + lm_px + kx) * PS + cb * 16 + lm_ch);
+          mma_16816_ae(acc[g], a, b0, b1, fp16);
         }
       }
     }
   }
+  const int oy = ty0 + wrp;
+  if (oy < H) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int co = 2 * tig + (e & 1), ox = tx0 + g * 16 + gid + (e >> 1) * 8;
+        if (co < Cout && ox < W) {
+          float v = acc[g][e] + __ldg(bias + co);
+          v = (act == NPVP_ACT_TANH) ? tanhf(v) : (act == NPVP_ACT_SIGMOID ? 1.0f / (1.0f + expf(-v)) : v);
+          out[(((size_t)f * Cout + co) * H + oy) * W + ox] = v;
+        }
+      }
+  }
+}
+
+template <int CIN>
+static int launch_head(const void* x, const float* w, const float* bias, float* out, int64_t frames, int Cout, int H, int W,
+                       int phase_major, int act, int fp16, cudaStream_t st) {
+  constexpr int smem = ((kHeadTY + 6) * (kHeadTX + 6) * (CIN + 8) + 49 * (CIN / 16) * 128) * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(conv7x7_head_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) { npvp_set_error("conv7x7_head: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(((H + kHeadTY - 1) / kHeadTY) * ((W + kHeadTX - 1) / kHeadTX)), 1, (unsigned)frames);
+  conv7x7_head_kernel<CIN><<<grid, 256, smem, st>>>((const h16*)x, w, bias, out, Cout, H, W, phase_major, act, fp16);
+  NPVP_LAUNCH_CHECK("conv7x7_head_kernel");
+  return NPVP_OK;
 }
 
 extern "C" int npvp_conv7x7_head(const void* x_bf16, const float* w, const float* bias, float* out, int64_t frames, int Cin,
                                  int Cout, int H, int W, int phase_major, int act, int fp16, void* stream) {
   NPVP_REQUIRE(x_bf16 && w && bias && out && frames > 0 && frames <= 65535, "npvp_conv7x7_head: bad arguments");
-  NPVP_REQUIRE(Cin % 4 == 0 && H >= 4 && W >= 4 && (!phase_major || (H % 2 == 0 && W % 2 == 0)), "npvp_conv7x7_head: Cin %% 4, H/W >= 4, even H/W for phase-major input");
-  dim3 grid((unsigned)(((H + 15) / 16) * ((W + 63) / 64)), 1, (unsigned)frames);
+  NPVP_REQUIRE(H >= 4 && W >= 4 && (!phase_major || (H % 2 == 0 && W % 2 == 0)), "npvp_conv7x7_head: H/W >= 4, even H/W for phase-major input");
+  NPVP_REQUIRE(Cout >= 1 && Cout <= 8, "npvp_conv7x7_head: Cout must be in [1, 8] (got %d)", Cout);
   cudaStream_t st = (cudaStream_t)stream;
-  if (Cout == 1) conv7x7_head_kernel<1><<<grid, 256, 0, st>>>((const h16*)x_bf16, w, bias, out, Cin, H, W, phase_major, act, fp16);
-  else if (Cout == 3) conv7x7_head_kernel<3><<<grid, 256, 0, st>>>((const h16*)x_bf16, w, bias, out, Cin, H, W, phase_major, act, fp16);
-  else NPVP_REQUIRE(false, "npvp_conv7x7_head: Cout must be 1 or 3 (got %d)", Cout);
-  NPVP_LAUNCH_CHECK("conv7x7_head_kernel");
-  return NPVP_OK;
+  if (Cin == 32) return launch_head<32>(x_bf16, w, bias, out, frames, Cout, H, W, phase_major, act, fp16, st);
+  if (Cin == 64) return launch_head<64>(x_bf16, w, bias, out, frames, Cout, H, W, phase_major, act, fp16, st);
+  NPVP_REQUIRE(false, "npvp_conv7x7_head: Cin must be 32 or 64 (got %d)", Cin);
+  return NPVP_ERR_INVALID;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -234,89 +271,140 @@ extern "C" int npvp_maxpool2x2_cols(const void* x_bf16, int64_t ldx, int col0, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// non-local attention core: thread = (query, 32-wide slice of dv); keys/values streamed through smem
+// non-local attention core (flash style, UNSCALED softmax): one warp = 16 queries x one <=64-wide slice of dv.
+// Keys/values stream through smem in tiles of 64; S = Q K^T and O += P V run on warp-level mma.sync.m16n8k16
+// (fp16 or bf16 operands to match the activations, fp32 accumulate), the online softmax lives in the accumulator
+// registers (row max / sum via quad shuffles, exp2 on log2(e)-scaled scores).  The first SIMT version was FMA-bound
+// (40 FMA per query-key pair, 2.3 ms per launch at the 64x64 stage); the tensor path needs ~1/25 of the instructions.
 // ---------------------------------------------------------------------------------------------
-template <int DQ>
-__global__ void __launch_bounds__(256)
-nonlocal_attention_kernel(const h16* __restrict__ q, int64_t ldq, const h16* __restrict__ kv, h16* __restrict__ out, int HW, int HWk, int fp16) {
-  constexpr int DV = 4 * DQ, S = DV / 32, QB = 256 / S, KT = 64, ROW = DQ + DV;
-  __shared__ __align__(16) h16 skv[KT][ROW];
-  const int blocks_per_frame = (HW + QB - 1) / QB;
-  const int64_t f = blockIdx.x / blocks_per_frame;
-  const int qi = (blockIdx.x % blocks_per_frame) * QB + (threadIdx.x % QB);
-  const int slice = threadIdx.x / QB;
-  const bool active = qi < HW;
-  float qr[DQ];
-  if (active) {
-    const h16* qp = q + ((size_t)f * HW + qi) * ldq;
-#pragma unroll
-    for (int d = 0; d < DQ; d += 2) {
-      const float2 t = unpack_h16x2(*reinterpret_cast<const uint32_t*>(qp + d), fp16);
-      qr[d] = t.x * 1.4426950408889634f; qr[d + 1] = t.y * 1.4426950408889634f;   // scores in log2 units
-    }
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int fp16) {
+  if (fp16) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
   } else {
-#pragma unroll
-    for (int d = 0; d < DQ; ++d) qr[d] = 0.f;
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
   }
-  float o[32];
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+template <int DQ>
+__global__ void __launch_bounds__(128)
+nonlocal_attention_kernel(const h16* __restrict__ q, int64_t ldq, const h16* __restrict__ kv, h16* __restrict__ out, int HW, int HWk, int fp16) {
+  constexpr int DV = 4 * DQ, DVS = DV < 64 ? DV : 64, NT = DVS / 8, KT = 64, ROW = DQ + DV;
+  constexpr int QK_STEPS = DQ < 16 ? 1 : DQ / 16;
+  __shared__ __align__(16) h16 skv[KT][ROW];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int blocks_per_frame = (HW + 63) / 64;
+  const int64_t f = blockIdx.x / blocks_per_frame;
+  const int q_base = (blockIdx.x % blocks_per_frame) * 64 + w * 16;
+  const int dv0 = blockIdx.y * DVS;                        // dv slice of this block
+  const int r0 = q_base + gid, r1 = q_base + gid + 8;
+  const bool ok0 = r0 < HW, ok1 = r1 < HW;
+  // Q as A fragments (rows = queries, k = d); DQ = 8 pads k 8..15 with zeros
+  uint32_t qa[QK_STEPS][4];
+  {
+    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(q + ((size_t)f * HW + (ok0 ? r0 : 0)) * ldq);
+    const uint32_t* q1 = reinterpret_cast<const uint32_t*>(q + ((size_t)f * HW + (ok1 ? r1 : 0)) * ldq);
 #pragma unroll
-  for (int d = 0; d < 32; ++d) o[d] = 0.f;
-  float m = -INFINITY, l = 0.f;
+    for (int ks = 0; ks < QK_STEPS; ++ks) {
+      qa[ks][0] = ok0 ? __ldg(q0 + 8 * ks + tig) : 0u;
+      qa[ks][1] = ok1 ? __ldg(q1 + 8 * ks + tig) : 0u;
+      qa[ks][2] = (DQ >= 16 && ok0) ? __ldg(q0 + 8 * ks + 4 + tig) : 0u;
+      qa[ks][3] = (DQ >= 16 && ok1) ? __ldg(q1 + 8 * ks + 4 + tig) : 0u;
+    }
+  }
+  float o[NT][4];
+#pragma unroll
+  for (int d = 0; d < NT; ++d) { o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  constexpr float kLog2e = 1.4426950408889634f;
+
   for (int k0 = 0; k0 < HWk; k0 += KT) {
     const int nk = min(KT, HWk - k0);
     __syncthreads();
-    const uint4* src = reinterpret_cast<const uint4*>(kv + ((size_t)f * HWk + k0) * ROW);
-    for (int i = threadIdx.x; i < nk * ROW / 8; i += 256) reinterpret_cast<uint4*>(&skv[0][0])[i] = __ldg(src + i);
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(kv + ((size_t)f * HWk + k0) * ROW);
+      constexpr int VEC_PER_TILE = KT * ROW / 8;
+      for (int i = threadIdx.x; i < VEC_PER_TILE; i += 128)
+        reinterpret_cast<uint4*>(&skv[0][0])[i] = (i < nk * ROW / 8) ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);   // zero-fill dead keys
+    }
     __syncthreads();
-    // keys in blocks of 8: one running-max update / accumulator rescale per block instead of per key, and exp2 on
-    // log2(e)-prescaled scores (softmax is shift-invariant, the scale folds into q): halves the MUFU work.
-    for (int j0 = 0; j0 < nk; j0 += 8) {
-      float sc[8];
-      float bm = -INFINITY;
+    // ---- S = Q K^T for 64 keys: 8 key tiles ----
+    float sc[8][4];
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        float s = 0.f;
-        if (j0 + jj < nk) {
+    for (int t = 0; t < 8; ++t) {
+      sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.f;
+      const uint32_t* krow = reinterpret_cast<const uint32_t*>(&skv[8 * t + gid][0]);
 #pragma unroll
-          for (int d = 0; d < DQ; d += 2) {
-            const float2 t = unpack_h16x2(*reinterpret_cast<const uint32_t*>(&skv[j0 + jj][d]), fp16);
-            s = fmaf(qr[d], t.x, s);
-            s = fmaf(qr[d + 1], t.y, s);
-          }
-        } else {
-          s = -INFINITY;
-        }
-        sc[jj] = s;
-        bm = fmaxf(bm, s);
+      for (int ks = 0; ks < QK_STEPS; ++ks) {
+        const uint32_t b0 = krow[8 * ks + tig];
+        const uint32_t b1 = (DQ >= 16) ? krow[8 * ks + 4 + tig] : 0u;
+        mma_16816(sc[t], qa[ks], b0, b1, fp16);
       }
-      const float mn = fmaxf(m, bm);
-      const float corr = ex2_approx(m - mn);          // m = -inf on the first block -> 0
-      m = mn;
-      l *= corr;
+    }
+    // ---- online softmax (log2 domain) ----
+    float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) o[d] *= corr;
+    for (int t = 0; t < 8; ++t)
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        if (j0 + jj < nk) {
-          const float p = ex2_approx(sc[jj] - mn);
-          l += p;
+      for (int e = 0; e < 2; ++e) {
+        const bool dead = (8 * t + 2 * tig + e) >= nk;
+        sc[t][e] = dead ? -INFINITY : sc[t][e] * kLog2e;
+        sc[t][2 + e] = dead ? -INFINITY : sc[t][2 + e] * kLog2e;
+        bm0 = fmaxf(bm0, sc[t][e]);
+        bm1 = fmaxf(bm1, sc[t][2 + e]);
+      }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+    const float c0 = ex2_approx(m0 - mn0), c1 = ex2_approx(m1 - mn1);     // 0 on the first tile (m = -inf)
+    m0 = mn0; m1 = mn1;
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-          for (int d = 0; d < 32; d += 2) {
-            const float2 t = unpack_h16x2(*reinterpret_cast<const uint32_t*>(&skv[j0 + jj][DQ + slice * 32 + d]), fp16);
-            o[d] = fmaf(p, t.x, o[d]);
-            o[d + 1] = fmaf(p, t.y, o[d + 1]);
-          }
-        }
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float p0 = ex2_approx(sc[t][e] - mn0), p1 = ex2_approx(sc[t][2 + e] - mn1);   // ex2(-inf) = 0 for dead keys
+        sc[t][e] = p0; sc[t][2 + e] = p1;
+        s0 += p0; s1 += p1;
+      }
+    l0 = l0 * c0 + s0;       // per-thread partial row sums; quad-reduced once at the end
+    l1 = l1 * c1 + s1;
+#pragma unroll
+    for (int d = 0; d < NT; ++d) { o[d][0] *= c0; o[d][1] *= c0; o[d][2] *= c1; o[d][3] *= c1; }
+    // ---- O += P V: 4 steps of 16 keys ----
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_h16x2(sc[2 * kk][0], sc[2 * kk][1], fp16);
+      a[1] = pack_h16x2(sc[2 * kk][2], sc[2 * kk][3], fp16);
+      a[2] = pack_h16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1], fp16);
+      a[3] = pack_h16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3], fp16);
+#pragma unroll
+      for (int d = 0; d < NT; ++d) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, &skv[16 * kk + (lane & 15)][DQ + dv0 + 8 * d]);
+        mma_16816(o[d], a, b0, b1, fp16);
       }
     }
   }
-  if (active) {
-    const float inv = 1.0f / l;
-    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)f * HW + qi) * DV + slice * 32);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
-      dst[t] = make_uint4(pack_h16x2(o[8 * t] * inv, o[8 * t + 1] * inv, fp16), pack_h16x2(o[8 * t + 2] * inv, o[8 * t + 3] * inv, fp16),
-                          pack_h16x2(o[8 * t + 4] * inv, o[8 * t + 5] * inv, fp16), pack_h16x2(o[8 * t + 6] * inv, o[8 * t + 7] * inv, fp16));
+  for (int d = 0; d < NT; ++d) {
+    if (ok0) reinterpret_cast<uint32_t*>(out + ((size_t)f * HW + r0) * DV + dv0)[4 * d + tig] = pack_h16x2(o[d][0] * inv0, o[d][1] * inv0, fp16);
+    if (ok1) reinterpret_cast<uint32_t*>(out + ((size_t)f * HW + r1) * DV + dv0)[4 * d + tig] = pack_h16x2(o[d][2] * inv1, o[d][3] * inv1, fp16);
   }
 }
 
@@ -326,16 +414,16 @@ extern "C" int npvp_nonlocal_attention(const void* q, int64_t ldq, const void* k
   NPVP_REQUIRE(dv == 4 * dq, "npvp_nonlocal_attention: expects dv = 4*dq (C/2 and C/8)");
   NPVP_REQUIRE(ldq % 2 == 0 && (uintptr_t)q % 4 == 0 && (uintptr_t)kv % 16 == 0 && (uintptr_t)out % 16 == 0, "npvp_nonlocal_attention: alignment");
   cudaStream_t st = (cudaStream_t)stream;
-  const int S = dv / 32, QB = 256 / (S > 0 ? S : 1);
-  const int64_t blocks = frames * ((HW + QB - 1) / QB);
+  const int dvs = dv < 64 ? dv : 64;
+  const dim3 grid((unsigned)(frames * ((HW + 63) / 64)), (unsigned)(dv / dvs));
   const h16* qq = (const h16*)q;
   const h16* kk = (const h16*)kv;
   h16* oo = (h16*)out;
   switch (dq) {
-    case 8: nonlocal_attention_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(qq, ldq, kk, oo, HW, HWk, fp16); break;
-    case 16: nonlocal_attention_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(qq, ldq, kk, oo, HW, HWk, fp16); break;
-    case 32: nonlocal_attention_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(qq, ldq, kk, oo, HW, HWk, fp16); break;
-    case 64: nonlocal_attention_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(qq, ldq, kk, oo, HW, HWk, fp16); break;
+    case 8: nonlocal_attention_kernel<8><<<grid, 128, 0, st>>>(qq, ldq, kk, oo, HW, HWk, fp16); break;
+    case 16: nonlocal_attention_kernel<16><<<grid, 128, 0, st>>>(qq, ldq, kk, oo, HW, HWk, fp16); break;
+    case 32: nonlocal_attention_kernel<32><<<grid, 128, 0, st>>>(qq, ldq, kk, oo, HW, HWk, fp16); break;
+    case 64: nonlocal_attention_kernel<64><<<grid, 128, 0, st>>>(qq, ldq, kk, oo, HW, HWk, fp16); break;
     default: NPVP_REQUIRE(false, "npvp_nonlocal_attention: dq must be 8, 16, 32 or 64 (got %d)", dq);
   }
   NPVP_LAUNCH_CHECK("nonlocal_attention_kernel");
