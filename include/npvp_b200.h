@@ -81,6 +81,14 @@ void npvp_reset_launch_count(void);
  * (models/ResNetAutoEncoder.py:75-87,169-183,241,254; models/submodules.py:25). */
 int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                    const npvp_epilogue_t* ep, int backend, void* stream);
+/* Convolution as an IMPLICIT GEMM on the same tcgen05 kernel: rows = output pixels (f,oy,ox), K = (ky,kx,ci); the A operand
+ * is gathered from the channels-last activations by producer warps (cp.async into the 128B-swizzled smem layout), so no
+ * im2col buffer is written or read.  x 16-bit [frames,H,W,C] (phase_major=1: [frames,H/2,W/2,4,C]); Wt 16-bit [N, KH*KW*C];
+ * C must be 32 or a multiple of 64.  Replaces the 3x3 / stride-2 / transposed convolutions of the autoencoder and the
+ * event encoder (models/ResNetAutoEncoder.py:75-87,169-183,241,254; models/submodules.py:25,376). */
+int npvp_conv_gemm_bf16(const void* x, int64_t frames, int H, int W, int C, int KH, int KW, int stride, int pad,
+                        int pad_mode, int Ho, int Wo, int phase_major, const void* Wt, int64_t ldw, int64_t N,
+                        const npvp_epilogue_t* ep, void* stream);
 /* fp32 CUDA-core GEMM for the tiny, precision-critical NRMLP (models/submodules.py:299-314). */
 int npvp_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                   const float* bias, int act, float* out, int64_t ldo, void* stream);
@@ -106,6 +114,11 @@ int npvp_layernorm_rows(const float* x, const float* w, const float* b, float* o
  * (VidHRFormer.py:388-389 with :91/:214/:243).  h fp32 [frames,64,512]; w,b fp32 [64,512] (hw-major). */
 int npvp_frame_ln_gelu_residual(const float* h, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,
                                 void* stream);
+/* The same, fused with the consumer that follows it in every block: after y is updated in registers the kernel also runs
+ * npvp_ln_posfuse on the new y (VidHRFormer.py:91 -> :95-96, :214 -> :218-219, :243 -> next layer's :210-212). */
+int npvp_frame_ln_gelu_residual_posfuse(const float* h, const float* w_hwc, const float* b_hwc, float* y, const float* ln_w,
+                                        const float* ln_b, const float* qe, const float* beta, const float* gamma,
+                                        void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T, void* stream);
 /* mean over time of the memory (Predictor.py:346): mem fp32 [n,T,64*512] -> evt fp32 [n,64*512]. */
 int npvp_temporal_mean(const float* mem, float* evt, int64_t n_clips, int64_t T, int64_t frame_elems, void* stream);
 

@@ -33,11 +33,14 @@ class Epilogue(C.Structure):
 # symbol -> argtypes; every function returns int.  Kept in one table so tests can check the export list.
 SIGNATURES = {
     "npvp_gemm_bf16": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _vp],
+    "npvp_conv_gemm_bf16": [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _i64,
+                            C.POINTER(Epilogue), _vp],
     "npvp_gemm_f32": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i32, _vp, _i64, _vp],
     "npvp_fourier_features": [_vp, _vp, _vp, _i64, _i32, _vp],
     "npvp_ln_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_layernorm_rows": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "npvp_frame_ln_gelu_residual": [_vp, _vp, _vp, _vp, _i64, _vp],
+    "npvp_frame_ln_gelu_residual_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_temporal_mean": [_vp, _vp, _i64, _i64, _i64, _vp],
     "npvp_ffn_frame_stats": [_vp, _vp, _i64, _i64, _vp],
     "npvp_ffn_dwconv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
@@ -163,6 +166,29 @@ class Ops:
         self._call("npvp_gemm_bf16", a.data_ptr(), lda, w.data_ptr(), ldw, M, N, K, C.byref(ep),
                    self.gemm_backend if backend is None else backend, self._stream())
 
+    def conv_gemm(self, x, w, frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo, phase_major=False, *, bias=None,
+                  act=ACT_NONE, alpha=1.0, res1=None, res2=None, out_f32=None, out_bf16=None, post_relu=False):
+        """Implicit-GEMM convolution: x 16-bit [frames*H*W, C] (NHWC or phase-major), w 16-bit [N, KH*KW*C]."""
+        _chk16(x, "x"); _chk16(w, "w", False, like=x)
+        _chk(bias, torch.float32, "bias"); _chk(out_f32, torch.float32, "out_f32", False); _chk16(out_bf16, "out_bf16", False, like=x)
+        assert x.numel() == frames * H * W * Cc and w.shape[1] == KH * KW * Cc
+        M, N = frames * Ho * Wo, w.shape[0]
+        outs = [o for o in (out_f32, out_bf16) if o is not None]
+        assert outs and all(o.shape == (M, N) for o in outs), "conv_gemm: output shape mismatch"
+        ld_out = _rowmajor(outs[0], "out")
+        ld_res = 0
+        for r in (res1, res2):
+            if r is not None:
+                assert r.is_cuda and r.shape == (M, N) and r.dtype in (torch.float32, x.dtype)
+                ld = _rowmajor(r, "res")
+                assert ld_res in (0, ld)
+                ld_res = ld
+        ep = Epilogue(_ptr(bias), _ptr(res1), _ptr(res2), _ptr(out_f32), _ptr(out_bf16), float(alpha), int(act),
+                      int(res1 is not None and res1.dtype in H16), int(res2 is not None and res2.dtype in H16),
+                      int(bool(post_relu)), _is_fp16(x), 0, ld_out, ld_res)
+        self._call("npvp_conv_gemm_bf16", x.data_ptr(), frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo, int(phase_major),
+                   w.data_ptr(), _rowmajor(w, "w"), N, C.byref(ep), self._stream())
+
     def gemm_f32(self, a, w, bias, act, out):
         for t, n in ((a, "a"), (w, "w"), (out, "out")):
             _chk(t, torch.float32, n, False)
@@ -204,6 +230,15 @@ class Ops:
         assert y.numel() == h.numel() and w_hwc.numel() == 64 * 512
         self._call("npvp_frame_ln_gelu_residual", h.data_ptr(), w_hwc.data_ptr(), b_hwc.data_ptr(), y.data_ptr(), frames,
                    self._stream())
+
+    def frame_ln_gelu_residual_posfuse(self, h, w_hwc, b_hwc, y, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, n_clips, T):
+        for t, n in ((h, "h"), (w_hwc, "w"), (b_hwc, "b"), (y, "y"), (ln_w, "ln_w"), (ln_b, "ln_b"), (qe, "qe"), (beta, "beta"),
+                     (gamma, "gamma")):
+            _chk(t, torch.float32, n)
+        _chk(out_ln, torch.bfloat16, "out_ln"); _chk(out_fused, torch.bfloat16, "out_fused")
+        assert h.numel() == n_clips * T * 64 * 512 and y.numel() == h.numel()
+        self._call("npvp_frame_ln_gelu_residual_posfuse", h.data_ptr(), w_hwc.data_ptr(), b_hwc.data_ptr(), y.data_ptr(), _ptr(ln_w),
+                   _ptr(ln_b), _ptr(qe), _ptr(beta), _ptr(gamma), _ptr(out_ln), _ptr(out_fused), n_clips, T, self._stream())
 
     def temporal_mean(self, mem, evt, n_clips, T):
         _chk(mem, torch.float32, "mem"); _chk(evt, torch.float32, "evt")

@@ -76,15 +76,12 @@ __device__ __forceinline__ void frame_stats(const FrameRegs& r, float* red, floa
 // ---------------------------------------------------------------------------------------------
 // a = LN(x); u = a + qe; fused = GN1(u) * (1 + gamma) + beta
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512)
-ln_posfuse_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                  const float* __restrict__ qe, const float* __restrict__ beta, const float* __restrict__ gamma,
-                  bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int T) {
-  __shared__ float red[64];
-  const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// r holds the frame's fp32 values; applies the optional token LayerNorm, writes `a`, then the positional fuse.
+__device__ __forceinline__ void posfuse_from_regs(FrameRegs& r, float* red, int f, int T, const float* __restrict__ ln_w,
+                                                  const float* __restrict__ ln_b, const float* __restrict__ qe,
+                                                  const float* __restrict__ beta, const float* __restrict__ gamma,
+                                                  bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int warp, int lane) {
   const int n = f / T, t_idx = f % T;
-  FrameRegs r;
-  frame_load(x + (size_t)f * kTok * kC, r, warp, lane);
   if (ln_w) {
     float4 w[4], b[4];
 #pragma unroll
@@ -127,6 +124,17 @@ ln_posfuse_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, c
     }
   }
   frame_store_bf16(out_fused + (size_t)f * kTok * kC, r, warp, lane);
+}
+
+__global__ void __launch_bounds__(512)
+ln_posfuse_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                  const float* __restrict__ qe, const float* __restrict__ beta, const float* __restrict__ gamma,
+                  bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int T) {
+  __shared__ float red[64];
+  const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  FrameRegs r;
+  frame_load(x + (size_t)f * kTok * kC, r, warp, lane);
+  posfuse_from_regs(r, red, f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, warp, lane);
 }
 
 extern "C" int npvp_ln_posfuse(const float* x, const float* ln_w, const float* ln_b, const float* qe, const float* beta,
@@ -184,9 +192,12 @@ extern "C" int npvp_layernorm_rows(const float* x, const float* w, const float* 
 // ---------------------------------------------------------------------------------------------
 // y += GELU(LayerNorm_(C,8,8)(h) * w + b)
 // ---------------------------------------------------------------------------------------------
+template <bool TAIL>
 __global__ void __launch_bounds__(512)
 frame_ln_gelu_residual_kernel(const float* __restrict__ h, const float* __restrict__ w_hwc, const float* __restrict__ b_hwc,
-                              float* __restrict__ y) {
+                              float* __restrict__ y, int T, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                              const float* __restrict__ qe, const float* __restrict__ beta, const float* __restrict__ gamma,
+                              bf16* __restrict__ out_ln, bf16* __restrict__ out_fused) {
   __shared__ float red[64];
   const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FrameRegs r;
@@ -208,15 +219,31 @@ frame_ln_gelu_residual_kernel(const float* __restrict__ h, const float* __restri
       yy.z += gelu_erf((r.v[t][4 * j + 2] - mean) * rstd * ww.z + bb.z);
       yy.w += gelu_erf((r.v[t][4 * j + 3] - mean) * rstd * ww.w + bb.w);
       yrow[j * 32 + lane] = yy;
+      if (TAIL) { r.v[t][4 * j] = yy.x; r.v[t][4 * j + 1] = yy.y; r.v[t][4 * j + 2] = yy.z; r.v[t][4 * j + 3] = yy.w; }
     }
   }
+  // fused consumer: the next op of every block is LayerNorm + positional fuse of the stream just updated
+  if (TAIL) posfuse_from_regs(r, red, f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, warp, lane);
 }
 
 extern "C" int npvp_frame_ln_gelu_residual(const float* h, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,
                                            void* stream) {
   NPVP_REQUIRE(h && w_hwc && b_hwc && y && frames > 0, "npvp_frame_ln_gelu_residual: bad arguments");
-  frame_ln_gelu_residual_kernel<<<(unsigned)frames, 512, 0, (cudaStream_t)stream>>>(h, w_hwc, b_hwc, y);
+  frame_ln_gelu_residual_kernel<false><<<(unsigned)frames, 512, 0, (cudaStream_t)stream>>>(h, w_hwc, b_hwc, y, 1, nullptr, nullptr, nullptr,
+                                                                                          nullptr, nullptr, nullptr, nullptr);
   NPVP_LAUNCH_CHECK("frame_ln_gelu_residual_kernel");
+  return NPVP_OK;
+}
+
+extern "C" int npvp_frame_ln_gelu_residual_posfuse(const float* h, const float* w_hwc, const float* b_hwc, float* y, const float* ln_w,
+                                                   const float* ln_b, const float* qe, const float* beta, const float* gamma,
+                                                   void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T, void* stream) {
+  NPVP_REQUIRE(h && w_hwc && b_hwc && y && n_clips > 0 && T > 0, "npvp_frame_ln_gelu_residual_posfuse: bad arguments");
+  NPVP_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "npvp_frame_ln_gelu_residual_posfuse: ln_w/ln_b must both be set or both NULL");
+  NPVP_REQUIRE((out_ln_bf16 || out_fused_bf16) && (!out_fused_bf16 || beta), "npvp_frame_ln_gelu_residual_posfuse: outputs / beta missing");
+  frame_ln_gelu_residual_kernel<true><<<(unsigned)(n_clips * T), 512, 0, (cudaStream_t)stream>>>(
+      h, w_hwc, b_hwc, y, (int)T, ln_w, ln_b, qe, beta, gamma, (bf16*)out_ln_bf16, (bf16*)out_fused_bf16);
+  NPVP_LAUNCH_CHECK("frame_ln_gelu_residual_kernel<posfuse>");
   return NPVP_OK;
 }
 

@@ -11,17 +11,20 @@ The 7x7 stem / head convolutions (Cin or Cout in {1,3}) are direct kernels.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
 from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, PAD_REFLECT, PAD_REPLICATE, PAD_ZERO
-import os
 
 from .engine_predictor import _bn_fold, _f
 from .workspace import Workspace
 
 _PAD = {"reflect": PAD_REFLECT, "replicate": PAD_REPLICATE, "zero": PAD_ZERO}
+# NPVP_B200_CONV=im2col switches back to the explicit patch-matrix path (kept for A/B measurements)
+_IMPLICIT_GEMM = os.environ.get("NPVP_B200_CONV", "implicit") != "im2col"
 
 
 def ae_dtype() -> torch.dtype:
@@ -95,12 +98,15 @@ class EncoderEngine:
     def _conv3x3(self, x, frames, H, W, C, wb, stride, pad_mode, tag, **epi):
         op, ws = _lib.ops(), self.ws
         Ho, Wo = H // stride, W // stride
-        col = ws.h16("col", self.dt, frames * Ho * Wo, 9 * C)
-        op.im2col(x, col, frames, H, W, C, 3, 3, stride, 1, pad_mode, Ho, Wo)
         w, b = wb
         if "out_f32" not in epi:
             epi["out_bf16"] = ws.h16(tag, self.dt, frames * Ho * Wo, w.shape[0])
-        op.gemm(col, w, bias=b, **epi)
+        if _IMPLICIT_GEMM:          # A operand gathered inside the GEMM (no patch matrix in HBM)
+            op.conv_gemm(x, w, frames, H, W, C, 3, 3, stride, 1, pad_mode, Ho, Wo, bias=b, **epi)
+        else:
+            col = ws.h16("col", self.dt, frames * Ho * Wo, 9 * C)
+            op.im2col(x, col, frames, H, W, C, 3, 3, stride, 1, pad_mode, Ho, Wo)
+            op.gemm(col, w, bias=b, **epi)
         return epi.get("out_bf16", epi.get("out_f32"))
 
     def _f3d(self, x, frames, H, W, p: _F3D, tag):
@@ -205,10 +211,13 @@ class DecoderEngine:
         assert C == self.ups[0][2], f"decoder expects {self.ups[0][2]} feature channels, got {C}"
         phase = False
         for i, (w, b, Cin, Cout) in enumerate(self.ups):
-            col = ws.h16("col", self.dt, frames * H * W, 4 * Cin)
-            op.im2col(cur, col, frames, H, W, Cin, 2, 2, 1, 0, PAD_ZERO, H, W, phase_major=phase)
             nxt = ws.h16(f"up{i}", self.dt, frames * H * W, 4 * Cout)
-            op.gemm(col, w, bias=b, act=ACT_RELU, out_bf16=nxt)
+            if _IMPLICIT_GEMM:
+                op.conv_gemm(cur, w, frames, H, W, Cin, 2, 2, 1, 0, PAD_ZERO, H, W, phase, bias=b, act=ACT_RELU, out_bf16=nxt)
+            else:
+                col = ws.h16("col", self.dt, frames * H * W, 4 * Cin)
+                op.im2col(cur, col, frames, H, W, Cin, 2, 2, 1, 0, PAD_ZERO, H, W, phase_major=phase)
+                op.gemm(col, w, bias=b, act=ACT_RELU, out_bf16=nxt)
             cur, H, W, phase = nxt, 2 * H, 2 * W, True
         out = torch.empty(N, T, self.cout, H, W, dtype=torch.float32, device=self.device)
         op.conv7x7_head(cur, self.head_w, self.head_b, out, self.head_cin, self.cout, H, W, phase, self.act)

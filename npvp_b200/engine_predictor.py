@@ -172,8 +172,9 @@ class PredictorEngine:
         op.attention(qk[:, :C], qk[:, C:], v, o, mode, n, T, T, mask_last)
         op.gemm(o, w.wo, bias=w.bo, res1=x, out_f32=x)
 
-    def _conv_ffn(self, x, a_bf, w: _ConvFFN, frames, tag):
-        """x += MlpDWBN(a)  (VidHRFormer.py:374-392)."""
+    def _conv_ffn(self, x, a_bf, w: _ConvFFN, frames, tag, tail=None):
+        """x += MlpDWBN(a)  (VidHRFormer.py:374-392).  ``tail`` = (ln, qe, beta, gamma, out_ln, out_fused, n, T): the
+        LayerNorm + positional fuse that consumes the updated stream next, fused into the last kernel."""
         op, ws = _lib.ops(), self.ws
         M = x.shape[0]
         h1 = ws.bf16(f"h1_{tag}", M, w.hid)
@@ -186,7 +187,11 @@ class PredictorEngine:
         op.ffn_dwconv(h1, st1, w.n1w, w.n1b, w.dw_w, w.dw_b, y2, pt2)
         op.ffn_norm2(y2, pt2, w.n2w, w.n2b, h1)                 # h1 is dead: reuse it for GELU(LN2(.))
         op.gemm(h1, w.w2, bias=w.b2, out_f32=h3)
-        op.frame_ln_gelu_residual(h3, w.n3w, w.n3b, x)
+        if tail is None:
+            op.frame_ln_gelu_residual(h3, w.n3w, w.n3b, x)
+        else:
+            ln, qe, beta, gamma, out_ln, out_fused, n, T = tail
+            op.frame_ln_gelu_residual_posfuse(h3, w.n3w, w.n3b, x, ln.w, ln.b, qe, beta, gamma, out_ln, out_fused, n, T)
 
     def _mlp_ffn(self, x, a_bf, L, tag):
         op, ws = _lib.ops(), self.ws
@@ -208,8 +213,7 @@ class PredictorEngine:
             op.ln_posfuse(x, L.n1.w, L.n1.b, None, beta, gamma, a, f, n, T)
             self._self_attention(x, a, f, L.attn_s, ATTN_SPATIAL, n, T, False, "enc")
             op.layernorm_rows(x, L.n2.w, L.n2.b, out_bf16=a)
-            self._conv_ffn(x, a, L.ffn_s, n * T, "enc")
-            op.ln_posfuse(x, L.n3.w, L.n3.b, None, beta, gamma, a, f, n, T)
+            self._conv_ffn(x, a, L.ffn_s, n * T, "enc", tail=(L.n3, None, beta, gamma, a, f, n, T))   # + LN3 / fuse
             self._self_attention(x, a, f, L.attn_t, ATTN_TEMPORAL, n, T, True, "enc")    # mask quirk :100-102
             op.layernorm_rows(x, L.n4.w, L.n4.b, out_bf16=a)
             self._mlp_ffn(x, a, L, "enc")
@@ -227,10 +231,8 @@ class PredictorEngine:
         M = n * TOK
         e1 = ws.bf16("evt_e1", M, C)
         op.dwconv3x3_tokens(evt, E.dw_w, E.dw_shift, e1, relu=True)
-        col = ws.bf16("evt_col", M, 9 * C)
-        op.im2col(e1, col, n, 8, 8, C, 3, 3, 1, 1, PAD_ZERO, 8, 8)
         e2 = ws.bf16("evt_e2", M, E.hidden)
-        op.gemm(col, E.w2, bias=E.b2, act=ACT_RELU, out_bf16=e2)
+        op.conv_gemm(e1, E.w2, n, 8, 8, C, 3, 3, 1, 1, PAD_ZERO, 8, 8, bias=E.b2, act=ACT_RELU, out_bf16=e2)
         e3 = ws.bf16("evt_e3", M, E.hidden)
         op.gemm(e2, E.w3, bias=E.b3, act=ACT_RELU, out_bf16=e3)
         mulv = ws.f32("evt_mulv", M, E.w_head.shape[0])
@@ -255,12 +257,12 @@ class PredictorEngine:
         vx = ws.bf16("vx", Mo, C)
         qx = ws.bf16("qx", M, C)
         ox = ws.bf16("o_dec", M, C)
-        for L in self.dec_layers:
-            op.ln_posfuse(y, L.n1.w, L.n1.b, z, beta_p, gamma_p, a, f, n, Tp)
+        for li, L in enumerate(self.dec_layers):
+            if li == 0:      # later layers get this from the previous layer's last kernel
+                op.ln_posfuse(y, L.n1.w, L.n1.b, z, beta_p, gamma_p, a, f, n, Tp)
             self._self_attention(y, a, f, L.attn_s, ATTN_SPATIAL, n, Tp, False, "dec")
             op.layernorm_rows(y, L.n2.w, L.n2.b, out_bf16=a)
-            self._conv_ffn(y, a, L.ffn_s, n * Tp, "dec")
-            op.ln_posfuse(y, L.n3.w, L.n3.b, None, beta_p, gamma_p, a, f, n, Tp)
+            self._conv_ffn(y, a, L.ffn_s, n * Tp, "dec", tail=(L.n3, None, beta_p, gamma_p, a, f, n, Tp))   # + LN3 / fuse
             self._self_attention(y, a, f, L.attn_t, ATTN_TEMPORAL, n, Tp, False, "dec")
             op.layernorm_rows(y, L.n4.w, L.n4.b, out_bf16=a)
             self._mlp_ffn(y, a, L, "dec")
@@ -273,7 +275,9 @@ class PredictorEngine:
             op.attention(qx, kx, vx, ox, ATTN_TEMPORAL, n, Tp, To, False)
             op.gemm(ox, X.wo, bias=X.bo, res1=y, out_f32=y)
             op.layernorm_rows(y, L.n6.w, L.n6.b, out_bf16=a)
-            self._conv_ffn(y, a, L.ffn_x, n * Tp, "dec")
+            nxt = self.dec_layers[li + 1] if li + 1 < len(self.dec_layers) else None
+            self._conv_ffn(y, a, L.ffn_x, n * Tp, "dec",          # + next layer's LN1 / (+ query_evt) / fuse
+                           tail=None if nxt is None else (nxt.n1, z, beta_p, gamma_p, a, f, n, Tp))
         out = ws.f32("dec_out", M, C)
         out_bf = ws.h16("dec_out_16", out16, M, C)
         op.layernorm_rows(y, self.norm_dec.w, self.norm_dec.b, out_f32=out, out_bf16=out_bf, relu=relu_out)

@@ -69,6 +69,12 @@ class SpecOps:
         if out_bf16 is not None:
             out_bf16.copy_(v.clamp(-65504, 65504).to(out_bf16.dtype))
 
+    def conv_gemm(self, x, w, frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo, phase_major=False, **epi):
+        col = torch.empty(frames * Ho * Wo, KH * KW * Cc, dtype=x.dtype, device=x.device)
+        self.im2col(x, col, frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo, phase_major)
+        self.launches -= 1
+        self.gemm(col, w, **epi)
+
     def gemm_f32(self, a, w, bias, act, out):
         self.launches += 1
         v = a @ w.t()
@@ -118,6 +124,11 @@ class SpecOps:
         var = ((hh - mu) ** 2).mean(-1, keepdim=True)
         v = (hh - mu) * torch.rsqrt(var + EPS) * w_hwc.reshape(1, -1) + b_hwc.reshape(1, -1)
         y.add_(_act(v, ACT_GELU).reshape(y.shape))
+
+    def frame_ln_gelu_residual_posfuse(self, h, w_hwc, b_hwc, y, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, n_clips, T):
+        self.frame_ln_gelu_residual(h, w_hwc, b_hwc, y)
+        self.launches -= 1
+        self.ln_posfuse(y, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, n_clips, T)
 
     def temporal_mean(self, mem, evt, n_clips, T):
         self.launches += 1

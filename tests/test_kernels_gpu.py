@@ -249,3 +249,31 @@ def test_nonlocal_pieces(op, spec, C, H, dt):
     op.nonlocal_attention(qkv[:, :dq], kv1, o1, frames, H * H, H * H // 4, dq, dv)
     spec.nonlocal_attention(qkv[:, :dq], kv1, o2, frames, H * H, H * H // 4, dq, dv)
     close(o1, o2, 1.5e-2, "nonlocal_attention")
+
+
+@pytest.mark.parametrize("dt", H16)
+@pytest.mark.parametrize("frames,H,C,N,KH,stride,pad,mode,phase,epi", [
+    (3, 16, 64, 128, 3, 1, 1, 0, False, "relu_res"), (5, 16, 32, 64, 3, 2, 1, 0, False, "relu"), (9, 8, 512, 512, 3, 1, 1, 1, False, "res_f32"),
+    (2, 8, 128, 64, 3, 1, 1, 2, False, "relu"), (3, 16, 64, 128, 2, 1, 0, 0, True, "relu"), (70, 8, 512, 1024, 2, 1, 0, 0, False, "relu"),
+    (2, 64, 64, 64, 3, 1, 1, 0, False, "relu_res"), (3, 32, 32, 256, 2, 1, 0, 0, True, "relu")])
+def test_conv_gemm_implicit(op, spec, dt, frames, H, C, N, KH, stride, pad, mode, phase, epi):
+    x = rn(frames * H * H, C, seed=1, dtype=dt)
+    K = KH * KH * C
+    w = rn(N, K, seed=2, scale=K ** -0.5, dtype=dt)
+    bias = rn(N, seed=3)
+    Ho = H // stride
+    M = frames * Ho * Ho
+    kw = dict(bias=bias)
+    outs = []
+    for o in (op, spec):
+        if epi == "relu":
+            out = torch.empty(M, N, device=DEV, dtype=dt)
+            o.conv_gemm(x, w, frames, H, H, C, KH, KH, stride, pad, mode, Ho, Ho, phase, act=1, out_bf16=out, **kw)
+        elif epi == "relu_res":
+            out = torch.empty(M, N, device=DEV, dtype=dt)
+            o.conv_gemm(x, w, frames, H, H, C, KH, KH, stride, pad, mode, Ho, Ho, phase, act=1, res1=rn(M, N, seed=4, dtype=dt), out_bf16=out, **kw)
+        else:
+            out = torch.empty(M, N, device=DEV)
+            o.conv_gemm(x, w, frames, H, H, C, KH, KH, stride, pad, mode, Ho, Ho, phase, res1=rn(M, N, seed=4, dtype=dt), post_relu=True, out_f32=out, **kw)
+        outs.append(out)
+    close(outs[0], outs[1], 1e-2 if dt == torch.bfloat16 else 2e-3, "conv_gemm")
