@@ -295,6 +295,32 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
 }
 
+// Implicit-GEMM convolution: the A operand (rows = output pixels, K = (ky, kx, ci)) is gathered by two producer warps
+// straight from the channels-last activations with 16-byte cp.async into the same 128B-swizzled layout TMA would
+// produce (row r at r*128 B, 16-byte chunk c stored at chunk c ^ (r & 7)), so the MMA side is unchanged and no
+// im2col buffer exists.  Zero / reflect / replicate padding, stride and the phase-major layout left by the transposed
+// convolutions are resolved in the address math; out-of-range taps are zero-filled (cp.async src-size 0).
+// (A variant with 8 lanes per 128-byte row segment - fully coalesced sectors - was measured 2.3x SLOWER: the gather is
+// bound by its address arithmetic, so each thread keeps two whole rows and amortises the decode over 8 chunks.)
+struct ConvGather {
+  const h16* x;
+  int H, W, C, KH, KW, stride, pad, pad_mode, Ho, Wo, phase_major;
+};
+constexpr int kGatherThreads = 64;     // warps 2 and 3
+constexpr int kGatherLag = 2;          // cp.async groups kept in flight per thread before the stage is published
+
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ int conv_reflect(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_ct(float v, int act_rt) {
   if (ACT == NPVP_ACT_RELU) return fmaxf(v, 0.f);
@@ -314,10 +340,10 @@ __device__ __forceinline__ void add_res(float4& q, const void* res, int is16, in
   }
 }
 
-template <int BN, int ACT, int RES, int OUT>
+template <int BN, int ACT, int RES, int OUT, int CONV>
 __global__ void __launch_bounds__(kGemm2Threads, 1)
 gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                       int64_t M, int64_t N, int64_t K, EpiParams ep) {
+                       int64_t M, int64_t N, int64_t K, EpiParams ep, ConvGather cg) {
   using Cfg = Gemm2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -342,7 +368,7 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
     for (int s = 0; s < Cfg::kStages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&full_bar[s], CONV ? 1 + kGatherThreads : 1);   // TMA thread (+ every gather thread in conv mode)
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -369,12 +395,85 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          ptx::tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], CONV ? Cfg::kBBytes : Cfg::kStageBytes);
+          if (!CONV) ptx::tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
           ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, n_blk * BN);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
+    }
+  } else if (CONV && (warp == 2 || warp == 3)) {
+    // ---------------- implicit-GEMM A gather (64 threads, two rows of the 128-row tile each) ----------------
+    const int pt = threadIdx.x - 64;
+    const int seg = cg.C < kBK ? cg.C : kBK;                         // channels per contiguous segment (32 or 64)
+    const int segs_per_kb = kBK / seg;
+    const int chunks_per_seg = seg >> 3;
+    const int taps = cg.KH * cg.KW;
+    const int64_t hw_out = (int64_t)cg.Ho * cg.Wo;
+    int stage = 0, trail = 0, inflight = 0;
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = (int)(t / n_tiles);
+      int64_t fr[2];
+      int iy0[2], ix0[2];
+      bool rok[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t m = (int64_t)m_blk * kBM + pt + 64 * h;
+        rok[h] = m < M;
+        const int64_t mm = rok[h] ? m : 0;
+        fr[h] = mm / hw_out;
+        const int rem = (int)(mm - fr[h] * hw_out);
+        iy0[h] = (rem / cg.Wo) * cg.stride - cg.pad;
+        ix0[h] = (rem % cg.Wo) * cg.stride - cg.pad;
+      }
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        const uint32_t a_base = ptx::smem_u32(smem_a + stage * Cfg::kABytes);
+        for (int sg = 0; sg < segs_per_kb; ++sg) {
+          const int k = kb * kBK + sg * seg;
+          const int tap = k / cg.C, c0 = k - tap * cg.C;
+          const int ky = tap / cg.KW, kx = tap - ky * cg.KW;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = pt + 64 * h;
+            int iy = iy0[h] + ky, ix = ix0[h] + kx;
+            bool valid = rok[h] && tap < taps;
+            if (cg.pad_mode == NPVP_PAD_REFLECT) { iy = conv_reflect(iy, cg.H); ix = conv_reflect(ix, cg.W); }
+            else if (cg.pad_mode == NPVP_PAD_REPLICATE) { iy = min(max(iy, 0), cg.H - 1); ix = min(max(ix, 0), cg.W - 1); }
+            else valid = valid && iy >= 0 && iy < cg.H && ix >= 0 && ix < cg.W;
+            const h16* src = cg.x;
+            if (valid) {
+              const size_t pix = cg.phase_major
+                  ? ((((size_t)fr[h] * (cg.H >> 1) + (iy >> 1)) * (cg.W >> 1) + (ix >> 1)) * 4 + ((iy & 1) << 1) + (ix & 1))
+                  : (((size_t)fr[h] * cg.H + iy) * cg.W + ix);
+              src = cg.x + pix * cg.C + c0;
+            }
+            const uint32_t row_base = a_base + (uint32_t)r * 128u;
+            for (int c = 0; c < chunks_per_seg; ++c) {
+              const int chunk = sg * chunks_per_seg + c;
+              cp_async_16(row_base + (uint32_t)((chunk ^ (r & 7)) << 4), src + (valid ? c * 8 : 0), valid ? 16u : 0u);
+            }
+          }
+        }
+        cp_async_commit();
+        ++inflight;
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        if (inflight > kGatherLag) {                                  // oldest group has landed: publish its stage
+          cp_async_wait<kGatherLag>();
+          ptx::fence_proxy_async();
+          mbar_arrive(&full_bar[trail]);
+          if (++trail == Cfg::kStages) trail = 0;
+          --inflight;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    ptx::fence_proxy_async();
+    while (inflight > 0) {
+      mbar_arrive(&full_bar[trail]);
+      if (++trail == Cfg::kStages) trail = 0;
+      --inflight;
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
@@ -600,25 +699,25 @@ static int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw
 
 static int g_num_sms = 0;
 
-template <int BN, int ACT, int RES, int OUT>
+template <int BN, int ACT, int RES, int OUT, int CONV>
 static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, int64_t M, int64_t N, int64_t K, const EpiParams& e,
-                          unsigned grid, cudaStream_t st) {
+                          const ConvGather& cg, unsigned grid, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_v2_kernel<BN, ACT, RES, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_v2_kernel<BN, ACT, RES, OUT, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (err != cudaSuccess) { npvp_set_error("cudaFuncSetAttribute(v2, smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
     attr_set = true;
   }
-  gemm_tcgen05_v2_kernel<BN, ACT, RES, OUT><<<grid, kGemm2Threads, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K, e);
-  NPVP_LAUNCH_CHECK("gemm_tcgen05_v2_kernel");
+  gemm_tcgen05_v2_kernel<BN, ACT, RES, OUT, CONV><<<grid, kGemm2Threads, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K, e, cg);
+  NPVP_LAUNCH_CHECK(CONV ? "gemm_tcgen05_v2_kernel<conv>" : "gemm_tcgen05_v2_kernel");
   return NPVP_OK;
 }
 
 // Epilogue specialisations used by the engines; anything else runs the run-time-flag instantiation <-1,-1,-1>.
 template <int BN>
 static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
-                             const EpiParams& e, cudaStream_t st) {
+                             const EpiParams& e, cudaStream_t st, const ConvGather* conv = nullptr) {
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -626,16 +725,26 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   CUtensorMap ta, tb;
-  int rc = make_tmap_2d(&ta, A, M, K, lda, kBM, e.fp16);
+  int rc = make_tmap_2d(&tb, W, N, K, ldw, BN, e.fp16);
   if (rc) return rc;
-  rc = make_tmap_2d(&tb, W, N, K, ldw, BN, e.fp16);
-  if (rc) return rc;
+  if (conv) ta = tb;                                   // unused in conv mode (A is gathered), keep the parameter valid
+  else if ((rc = make_tmap_2d(&ta, A, M, K, lda, kBM, e.fp16))) return rc;
   const int64_t tiles = ceil_div64(M, kBM) * ceil_div64(N, BN);
   const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
+  const ConvGather cg0 = conv ? *conv : ConvGather{};
   const int res = !e.res1 ? (e.res2 ? -1 : 0) : (!e.res2 ? (e.res1_bf16 ? 2 : 1) : ((e.res1_bf16 && e.res2_bf16) ? 3 : -1));
   const int out = (e.out_f32 && e.out_bf16) ? 2 : (e.out_f32 ? 1 : 0);
   const int act = e.act;
-#define NPVP_V2_CASE(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_>(ta, tb, M, N, K, e, grid, st)
+  if (conv) {
+#define NPVP_V2_CONV(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_, 1>(ta, tb, M, N, K, e, cg0, grid, st)
+    NPVP_V2_CONV(NPVP_ACT_RELU, 0, 0);   // conv / transposed conv + BN + ReLU
+    NPVP_V2_CONV(NPVP_ACT_RELU, 2, 0);   // F3D conv: ReLU(BN(conv)) + x
+    NPVP_V2_CONV(NPVP_ACT_NONE, 2, 0);   // ResnetBlock second conv + skip
+    NPVP_V2_CONV(NPVP_ACT_NONE, 2, 1);   // ... last block: fp32 tokens out
+#undef NPVP_V2_CONV
+    return launch_v2_inst<BN, -1, -1, -1, 1>(ta, tb, M, N, K, e, cg0, grid, st);
+  }
+#define NPVP_V2_CASE(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_, 0>(ta, tb, M, N, K, e, cg0, grid, st)
   NPVP_V2_CASE(NPVP_ACT_NONE, 0, 0);   // projections -> 16-bit
   NPVP_V2_CASE(NPVP_ACT_GELU, 0, 0);   // linear1
   NPVP_V2_CASE(NPVP_ACT_RELU, 0, 0);   // conv + BN + ReLU
@@ -646,7 +755,7 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
   NPVP_V2_CASE(NPVP_ACT_NONE, 2, 0);   // ResnetBlock second conv + skip
   NPVP_V2_CASE(NPVP_ACT_NONE, 2, 1);   // ... last block: fp32 tokens out
 #undef NPVP_V2_CASE
-  return launch_v2_inst<BN, -1, -1, -1>(ta, tb, M, N, K, e, grid, st);
+  return launch_v2_inst<BN, -1, -1, -1, 0>(ta, tb, M, N, K, e, cg0, grid, st);
 }
 
 static bool tma_compatible(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t K) {
@@ -715,4 +824,32 @@ extern "C" int npvp_gemm_f32(const float* A, int64_t lda, const float* W, int64_
   gemm_simt_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, W, ldw, M, N, K, e);
   NPVP_LAUNCH_CHECK("gemm_simt_kernel<float>");
   return NPVP_OK;
+}
+
+
+// Convolution as an implicit GEMM: out[(f,oy,ox), n] = epilogue( sum_{ky,kx,ci} x[f, oy*stride-pad+ky, ox*stride-pad+kx, ci] * W[n, (ky,kx,ci)] ).
+extern "C" int npvp_conv_gemm_bf16(const void* x, int64_t frames, int H, int W, int C, int KH, int KW, int stride, int pad,
+                                   int pad_mode, int Ho, int Wo, int phase_major, const void* Wt, int64_t ldw, int64_t N,
+                                   const npvp_epilogue_t* ep, void* stream) {
+  NPVP_REQUIRE(x && Wt && ep && frames > 0, "npvp_conv_gemm_bf16: null pointer");
+  NPVP_REQUIRE(C % 32 == 0 && (C < 64 || C % 64 == 0), "npvp_conv_gemm_bf16: C must be 32 or a multiple of 64 (got %d)", C);
+  NPVP_REQUIRE(KH > 0 && KW > 0 && stride > 0 && Ho > 0 && Wo > 0 && N > 0, "npvp_conv_gemm_bf16: bad geometry");
+  NPVP_REQUIRE(!phase_major || (H % 2 == 0 && W % 2 == 0), "npvp_conv_gemm_bf16: phase-major input needs even H, W");
+  NPVP_REQUIRE(pad_mode == NPVP_PAD_ZERO || (pad < H && pad < W), "npvp_conv_gemm_bf16: reflect/replicate pad must be smaller than the image");
+  const int64_t M = frames * Ho * Wo, K = (int64_t)KH * KW * C;
+  NPVP_REQUIRE(ldw >= K && ldw % 8 == 0 && (uintptr_t)Wt % 16 == 0 && (uintptr_t)x % 16 == 0, "npvp_conv_gemm_bf16: weight/activation alignment");
+  NPVP_REQUIRE(ep->out_f32 || ep->out_bf16, "npvp_conv_gemm_bf16: no output buffer");
+  NPVP_REQUIRE(ep->ld_out >= N && ep->ld_out % 8 == 0 && N % 4 == 0, "npvp_conv_gemm_bf16: ld_out >= N, ld_out %% 8 == 0, N %% 4 == 0 required");
+  NPVP_REQUIRE((!ep->out_f32 || (uintptr_t)ep->out_f32 % 16 == 0) && (!ep->out_bf16 || (uintptr_t)ep->out_bf16 % 16 == 0), "npvp_conv_gemm_bf16: output alignment");
+  NPVP_REQUIRE(!(ep->res1 || ep->res2) || (ep->ld_res >= N && ep->ld_res % 4 == 0 && (uintptr_t)ep->res1 % 16 == 0 && (uintptr_t)ep->res2 % 16 == 0),
+               "npvp_conv_gemm_bf16: residual alignment");
+  ConvGather cg;
+  cg.x = (const h16*)x;
+  cg.H = H; cg.W = W; cg.C = C; cg.KH = KH; cg.KW = KW; cg.stride = stride; cg.pad = pad; cg.pad_mode = pad_mode;
+  cg.Ho = Ho; cg.Wo = Wo; cg.phase_major = phase_major;
+  EpiParams e = make_epi(ep);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N >= 256) return launch_tcgen05_v2<256>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);
+  if (N > 64) return launch_tcgen05_v2<128>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);
+  return launch_tcgen05_v2<64>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);
 }
