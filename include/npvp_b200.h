@@ -169,9 +169,10 @@ int npvp_tokens_to_nchw(const float* x_f32, const void* x_bf16, float* out, int6
 int npvp_conv7x7_stem(const float* x, const float* w, const float* shift, void* out_bf16, int64_t frames, int Cin,
                       int Cout, int H, int W, int fp16, void* stream);
 /* 7x7 head: reflect-pad 3, conv + bias + Tanh|Sigmoid (ResNetAutoEncoder.py:184-189).
- * x bf16 [frames,H,W,Cin] (phase_major=1: stored [frames,H/2,W/2,4,Cin], the ConvT GEMM's native output);
- * w fp32 [49*Cin, Cout]; bias fp32 [Cout]; out fp32 NCHW [frames,Cout,H,W]. */
-int npvp_conv7x7_head(const void* x_bf16, const float* w, const float* bias, float* out, int64_t frames, int Cin,
+ * x 16-bit [frames,H,W,Cin] (phase_major=1: stored [frames,H/2,W/2,4,Cin], the ConvT GEMM's native output), Cin 32 or 64;
+ * w 16-bit, pre-packed as mma B fragments [49 taps][Cin/16][8 (cout, zero-padded)][16 (cin)]; bias fp32 [Cout];
+ * out fp32 NCHW [frames,Cout,H,W]. */
+int npvp_conv7x7_head(const void* x_bf16, const void* w, const float* bias, float* out, int64_t frames, int Cin,
                       int Cout, int H, int W, int phase_major, int act, int fp16, void* stream);
 /* Patch gather for conv-as-GEMM: out[(f,oy,ox), (ky,kx,c)] = x[f, oy*stride - pad + ky, ox*stride - pad + kx, c].
  * x bf16 NHWC (or phase-major), out bf16 [frames*Ho*Wo, KH*KW*C]. */

@@ -321,9 +321,10 @@ class Ops:
                        out.data_ptr() + f0 * H * W * Cout * 2, n, Cin, Cout, H, W, _is_fp16(out), self._stream())
 
     def conv7x7_head(self, x, w, bias, out, Cin, Cout, H, W, phase_major, act):
-        _chk16(x, "x"); _chk(w, torch.float32, "w"); _chk(bias, torch.float32, "bias"); _chk(out, torch.float32, "out")
+        """w: 16-bit weights packed by :func:`pack_head_weights` ([49, Cin/16, 8, 16])."""
+        _chk16(x, "x"); _chk16(w, "w", like=x); _chk(bias, torch.float32, "bias"); _chk(out, torch.float32, "out")
         frames = x.numel() // (Cin * H * W)
-        assert out.numel() == frames * Cout * H * W and w.shape == (49 * Cin, Cout)
+        assert out.numel() == frames * Cout * H * W and tuple(w.shape) == (49, Cin // 16, 8, 16)
         for f0 in range(0, frames, 65535):
             n = min(65535, frames - f0)
             self._call("npvp_conv7x7_head", x.data_ptr() + f0 * Cin * H * W * 2, w.data_ptr(), bias.data_ptr(),
@@ -346,6 +347,22 @@ class Ops:
         assert q.shape[0] == frames * HW and kv.shape == (frames * HWk, dq + dv) and out.shape == (frames * HW, dv)
         self._call("npvp_nonlocal_attention", q.data_ptr(), _rowmajor(q, "q"), kv.data_ptr(), out.data_ptr(), frames, HW, HWk, dq,
                    dv, _is_fp16(q), self._stream())
+
+
+def pack_head_weights(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """[(ky,kx,ci), Cout] fp32 -> 16-bit mma.sync B fragments [49 taps, Cin/16, 8 (cout, zero padded), 16 (cin)]."""
+    K, Cout = w.shape
+    Cin = K // 49
+    assert Cin % 16 == 0 and Cout <= 8
+    p = torch.zeros(49, Cin // 16, 8, 16, dtype=torch.float32, device=w.device)
+    p[:, :, :Cout, :] = w.reshape(49, Cin // 16, 16, Cout).permute(0, 1, 3, 2)
+    return p.to(dtype).contiguous()
+
+
+def unpack_head_weights(p: torch.Tensor, Cout: int) -> torch.Tensor:
+    """Inverse of :func:`pack_head_weights` (used by the kernel specification)."""
+    taps, cb, _, _ = p.shape
+    return p.float()[:, :, :Cout, :].permute(0, 1, 3, 2).reshape(taps * cb * 16, Cout)
 
 
 _OPS: Optional[Ops] = None

@@ -107,7 +107,7 @@ constexpr int kHeadTY = 8, kHeadTX = 64;                       // output tile pe
 
 template <int CIN>
 __global__ void __launch_bounds__(256)
-conv7x7_head_kernel(const h16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+conv7x7_head_kernel(const h16* __restrict__ x, const h16* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
                     int Cout, int H, int W, int phase_major, int act, int fp16) {
   constexpr int PS = CIN + 8;                                   // padded pixel stride (halves)
   constexpr int TW = kHeadTX + 6, TH = kHeadTY + 6, CB = CIN / 16;
@@ -126,12 +126,9 @@ conv7x7_head_kernel(const h16* __restrict__ x, const float* __restrict__ w, cons
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + pixel_offset(f, yy, xx, H, W, phase_major) * CIN) + v);
     *reinterpret_cast<uint4*>(tile + (size_t)px * PS + v * 8) = u;
   }
-  // weights fp32 [(tap, ci), Cout] -> 16-bit [tap][cb][n][k], zero for n >= Cout
-  for (int i = threadIdx.x; i < 49 * CB * 8 * 16; i += 256) {
-    const int k = i & 15, n = (i >> 4) & 7, cb = (i >> 7) % CB, tap = i / (128 * CB);
-    const float v = (n < Cout) ? __ldg(w + ((size_t)tap * CIN + cb * 16 + k) * Cout + n) : 0.f;
-    wb[i] = float_to_h16(v, fp16);
-  }
+  // weights arrive pre-packed as 16-bit B fragments [tap][cb][n = 8][k = 16] (zero rows for n >= Cout): plain vector copy
+  for (int i = threadIdx.x; i < 49 * CB * 16; i += 256)
+    reinterpret_cast<uint4*>(wb)[i] = __ldg(reinterpret_cast<const uint4*>(w) + i);
   __syncthreads();
   const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
   const int lm_px = ((lane >> 3) & 1) * 8 + (lane & 7);        // ldmatrix.x4 row supplied by this lane: pixel within the group
@@ -174,7 +171,7 @@ conv7x7_head_kernel(const h16* __restrict__ x, const float* __restrict__ w, cons
 }
 
 template <int CIN>
-static int launch_head(const void* x, const float* w, const float* bias, float* out, int64_t frames, int Cout, int H, int W,
+static int launch_head(const void* x, const void* w, const float* bias, float* out, int64_t frames, int Cout, int H, int W,
                        int phase_major, int act, int fp16, cudaStream_t st) {
   constexpr int smem = ((kHeadTY + 6) * (kHeadTX + 6) * (CIN + 8) + 49 * (CIN / 16) * 128) * 2;
   static bool attr_set = false;
@@ -184,16 +181,17 @@ static int launch_head(const void* x, const float* w, const float* bias, float* 
     attr_set = true;
   }
   dim3 grid((unsigned)(((H + kHeadTY - 1) / kHeadTY) * ((W + kHeadTX - 1) / kHeadTX)), 1, (unsigned)frames);
-  conv7x7_head_kernel<CIN><<<grid, 256, smem, st>>>((const h16*)x, w, bias, out, Cout, H, W, phase_major, act, fp16);
+  conv7x7_head_kernel<CIN><<<grid, 256, smem, st>>>((const h16*)x, (const h16*)w, bias, out, Cout, H, W, phase_major, act, fp16);
   NPVP_LAUNCH_CHECK("conv7x7_head_kernel");
   return NPVP_OK;
 }
 
-extern "C" int npvp_conv7x7_head(const void* x_bf16, const float* w, const float* bias, float* out, int64_t frames, int Cin,
+extern "C" int npvp_conv7x7_head(const void* x_bf16, const void* w, const float* bias, float* out, int64_t frames, int Cin,
                                  int Cout, int H, int W, int phase_major, int act, int fp16, void* stream) {
   NPVP_REQUIRE(x_bf16 && w && bias && out && frames > 0 && frames <= 65535, "npvp_conv7x7_head: bad arguments");
   NPVP_REQUIRE(H >= 4 && W >= 4 && (!phase_major || (H % 2 == 0 && W % 2 == 0)), "npvp_conv7x7_head: H/W >= 4, even H/W for phase-major input");
   NPVP_REQUIRE(Cout >= 1 && Cout <= 8, "npvp_conv7x7_head: Cout must be in [1, 8] (got %d)", Cout);
+  NPVP_REQUIRE((uintptr_t)w % 16 == 0 && (uintptr_t)x_bf16 % 16 == 0, "npvp_conv7x7_head: x / w must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 32) return launch_head<32>(x_bf16, w, bias, out, frames, Cout, H, W, phase_major, act, fp16, st);
   if (Cin == 64) return launch_head<64>(x_bf16, w, bias, out, frames, Cout, H, W, phase_major, act, fp16, st);

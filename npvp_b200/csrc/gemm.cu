@@ -516,11 +516,20 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     constexpr int kColsPerWarp = BN / 2;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
+      // bias of the first column chunk: fetched BEFORE waiting for the accumulator, later chunks one iteration ahead, so the
+      // L2 latency never sits on the epilogue's critical path (r01 profile: long-scoreboard stalls on the per-chunk bias load)
+      auto load_bias = [&](int c) {
+        const int64_t nb = (int64_t)n_blk * BN + c + chunk * 4;
+        return (has_bias && nb < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      float4 b_next = load_bias(half * kColsPerWarp);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const int64_t m_base = (int64_t)m_blk * kBM + quad * 32;
 #pragma unroll 1
       for (int c = half * kColsPerWarp; c < (half + 1) * kColsPerWarp; c += 32) {
+        const float4 b4 = b_next;
+        if (c + 32 < (half + 1) * kColsPerWarp) b_next = load_bias(c + 32);
         const int64_t n0 = (int64_t)n_blk * BN + c;
         if (n0 >= N) break;                                          // warp-uniform
         uint32_t r[32];
@@ -532,8 +541,6 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         __syncwarp();
         const int64_t n = n0 + chunk * 4;
         const bool col_ok = n < N;                                   // N % 4 == 0 on this path
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
         // Residuals may alias the output (in-place residual-stream update), so the compiler cannot hoist their loads
         // above the stores: fetch all of this chunk's residual vectors first (8 independent 128-bit loads in flight).
         float4 rs[8];

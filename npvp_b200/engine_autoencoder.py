@@ -168,7 +168,7 @@ class DecoderEngine:
             convt, bn = mod.model[3 * i], mod.model[3 * i + 1]
             self.ups.append(self._pack_convT(convt, bn, self.dt))
         head = mod.model[3 * mod.n_downsampling + 1]
-        self.head_w = _pack_conv7x7(head)
+        self.head_w = _lib.pack_head_weights(_pack_conv7x7(head), self.dt)
         self.head_b = _f(head.bias)
         self.head_cin, self.cout = head.weight.shape[1], head.weight.shape[0]
         self.act = ACT_TANH if mod.out_layer == 'Tanh' else ACT_SIGMOID

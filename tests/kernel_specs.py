@@ -247,7 +247,8 @@ class SpecOps:
         self.launches += 1
         frames = x.numel() // (Cin * H * W)
         img = self._unphase(x.float(), frames, H, W, Cin, phase_major).permute(0, 3, 1, 2)
-        wt = w.to(x.dtype).float().reshape(7, 7, Cin, Cout).permute(3, 2, 0, 1)     # the kernel feeds 16-bit weights to the MMA
+        from npvp_b200._lib import unpack_head_weights
+        wt = unpack_head_weights(w, Cout).reshape(7, 7, Cin, Cout).permute(3, 2, 0, 1)   # 16-bit packed weights (mma B fragments)
         o = F.conv2d(F.pad(img, (3, 3, 3, 3), mode="reflect"), wt, bias)
         out.copy_(_act(o, act).reshape(out.shape))
 

@@ -213,8 +213,9 @@ def test_conv7x7_stem(op, spec, Cin, Cout, HW, dt):
 @pytest.mark.parametrize("dt", H16)
 @pytest.mark.parametrize("Cin,Cout,HW,phase,act", [(32, 3, 128, True, 3), (64, 1, 64, True, 4), (32, 3, 48, False, 3)])
 def test_conv7x7_head(op, spec, Cin, Cout, HW, phase, act, dt):
+    from npvp_b200._lib import pack_head_weights
     x = rn(2 * HW * HW, Cin, seed=1, dtype=dt)
-    w, b = rn(49 * Cin, Cout, seed=2, scale=0.03), rn(Cout, seed=3, scale=0.2)
+    w, b = pack_head_weights(rn(49 * Cin, Cout, seed=2, scale=0.03), dt), rn(Cout, seed=3, scale=0.2)
     o1, o2 = torch.empty(2, Cout, HW, HW, device=DEV), torch.empty(2, Cout, HW, HW, device=DEV)
     op.conv7x7_head(x, w, b, o1, Cin, Cout, HW, HW, phase, act)
     spec.conv7x7_head(x, w, b, o2, Cin, Cout, HW, HW, phase, act)

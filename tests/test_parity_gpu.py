@@ -113,3 +113,68 @@ def test_batch_invariance_and_determinism():
     solo = model.predict(x[:1], eps[:1])
     assert torch.equal(full, again)
     assert torch.equal(full[:1], solo)
+
+
+KTH_TASKS = {
+    # the five inference tasks of the reference notebook (Inference.ipynb:115-147): context / target timestamps
+    "VFP": (list(range(10)), list(range(10, 20))),
+    "VPE": (list(range(10, 20)), list(range(10))),
+    "VFI": (list(range(6)) + list(range(14, 20)), list(range(6, 14))),
+    "VRC": ([0, 1, 2, 3, 6, 7, 10, 14, 15, 16], [4, 5, 8, 9, 11, 12, 13, 17, 18, 19]),
+    "continuous": ([0, 1, 2, 3, 6, 7, 10, 14, 15, 16],
+                   [4, 4.25, 4.5, 5, 5.25, 5.5, 5.75, 8, 8.5, 9, 9.5, 11, 11.5, 12, 12.5, 13, 13.5, 17, 17.25, 17.5, 18, 18.5, 19]),
+}
+
+
+@pytest.mark.parametrize("task", list(KTH_TASKS))
+def test_kth_unified_continuous_time_tasks(task):
+    """BASELINE config 2: one unified NPVP-S model queried for prediction / past extrapolation / interpolation / random
+    completion / fractional timestamps via reset_pos_coor, injected latent noise, vs the oracle in pixel space."""
+    from npvp_b200.pipeline import build_from_config
+    from util_init import reset_shared_norm, seeded_rand, seeded_randn, stress_init_
+    import npvp_b200
+    reset_shared_norm(npvp_b200.Predictor)
+    model = build_from_config("KTH_Unified_NPVP-S", device="cpu", seed=0)
+    stress_init_(model.VPTR_Enc, 1)
+    stress_init_(model.VPTR_Dec, 2)
+    stress_init_(model.predictor, 3)
+    to, tp = KTH_TASKS[task]
+    to_t, tp_t = torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32)
+    model.predictor.reset_pos_coor(to_t, tp_t)
+    N = 2
+    clip = seeded_rand((N, 20, 1, 64, 64), 77) * 2 - 1
+    x = clip[:, to]                                              # context frames in the order given (never sorted)
+    eps = seeded_randn((N, 512, 8, 8), 78)
+    cfg = model.cfg
+    ocfg = dict(n_downsampling=cfg.AE.n_downsampling, num_res_blocks=cfg.AE.num_res_blocks, out_layer=cfg.AE.out_layer, stochastic=True)
+    ref = O.npvp_predict_frames(model.VPTR_Enc.state_dict(), model.predictor.state_dict(), model.VPTR_Dec.state_dict(), x, ocfg,
+                                model.predictor.observed_coor, model.predictor.predict_coor, eps)
+    model = model.cuda()
+    model.predictor.reset_pos_coor(to_t, tp_t)
+    out = model.predict(x.cuda(), eps.cuda())
+    assert out.shape == (N, len(tp), 1, 64, 64)
+    err = float((model.to_pixels(out).cpu() - model.to_pixels(ref)).abs().max())
+    print(f"KTH {task}: To={len(to)} Tp={len(tp)} max pixel err {err:.3e}")
+    assert err <= 1e-2
+
+
+def test_bair_multiple_stochastic_samples():
+    """BASELINE config 3: 8 stochastic samples per clip = 8 different injected eps; each must match the oracle and differ from the others."""
+    from npvp_b200.pipeline import build_from_config
+    from util_init import reset_shared_norm, seeded_rand, seeded_randn, stress_init_
+    import npvp_b200
+    reset_shared_norm(npvp_b200.Predictor)
+    model = build_from_config("BAIR_VFP_NPVP-S", device="cpu", seed=0)
+    stress_init_(model.predictor, 3)
+    x = seeded_rand((1, 2, 3, 64, 64), 5) * 2 - 1
+    cfg = model.cfg
+    ocfg = dict(n_downsampling=cfg.AE.n_downsampling, num_res_blocks=cfg.AE.num_res_blocks, out_layer=cfg.AE.out_layer, stochastic=True)
+    esd, psd, dsd = model.VPTR_Enc.state_dict(), model.predictor.state_dict(), model.VPTR_Dec.state_dict()
+    eps = [seeded_randn((1, 512, 8, 8), 100 + i) for i in range(8)]
+    refs = [O.npvp_predict_frames(esd, psd, dsd, x, ocfg, psd["observed_coor"], psd["predict_coor"], e) for e in eps[:2]]
+    model = model.cuda()
+    # the 8 samples of one clip run as one batch of 8 (clip replicated, per-sample noise)
+    outs = model.predict(x.cuda().expand(8, -1, -1, -1, -1).contiguous(), torch.cat(eps).cuda())
+    for i, r in enumerate(refs):
+        assert float((model.to_pixels(outs[i:i + 1]).cpu() - model.to_pixels(r)).abs().max()) <= 1e-2
+    assert float((outs[0] - outs[1]).abs().max()) > 0
