@@ -40,6 +40,7 @@ extern "C" {
 #define NPVP_GEMM_TCGEN05 1 /* TMA-fed tcgen05.mma, TMEM accumulators */
 #define NPVP_GEMM_SIMT 2    /* CUDA-core reference path for debugging / odd shapes */
 #define NPVP_GEMM_TCGEN05_V1 3 /* first-generation (non-persistent, one tile per CTA) tcgen05 kernel, kept for A/B runs */
+#define NPVP_GEMM_TCGEN05_2CTA 4 /* cluster of 2 CTAs, tcgen05.mma.cta_group::2, 256x256 tiles */
 
 #define NPVP_PAD_ZERO 0
 #define NPVP_PAD_REFLECT 1
@@ -72,6 +73,8 @@ int npvp_version(void);
 /* number of kernels launched through this library since the last reset (bench accounting) */
 int64_t npvp_launch_count(void);
 void npvp_reset_launch_count(void);
+/* library-wide switches: "gemm_2cta" = 1 routes N >= 256 GEMMs of the default back-end to the 2-CTA cluster kernel */
+int npvp_set_option(const char* name, int value);
 
 /* ---- dense contractions -------------------------------------------------------------------
  * D[M,N] = A[M,K] (bf16, row stride lda) x W[N,K]^T (bf16, row stride ldw), fp32 accumulate.

@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
-GEMM_AUTO, GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_V1 = 0, 1, 2, 3
+GEMM_AUTO, GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_V1, GEMM_TCGEN05_2CTA = 0, 1, 2, 3, 4
 PAD_ZERO, PAD_REFLECT, PAD_REPLICATE = 0, 1, 2
 ATTN_SPATIAL, ATTN_TEMPORAL = 0, 1
 
@@ -56,7 +56,7 @@ SIGNATURES = {
     "npvp_maxpool2x2_cols": [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _vp],
     "npvp_nonlocal_attention": [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
 }
-AUX_SYMBOLS = ["npvp_last_error", "npvp_version", "npvp_launch_count", "npvp_reset_launch_count"]
+AUX_SYMBOLS = ["npvp_last_error", "npvp_version", "npvp_launch_count", "npvp_reset_launch_count", "npvp_set_option"]
 
 
 def load_library(path: str = LIB_PATH) -> C.CDLL:
@@ -71,6 +71,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.npvp_version.restype = C.c_int
     lib.npvp_launch_count.restype = C.c_int64
     lib.npvp_reset_launch_count.restype = None
+    lib.npvp_set_option.argtypes, lib.npvp_set_option.restype = [C.c_char_p, C.c_int], C.c_int
     return lib
 
 
@@ -121,8 +122,9 @@ class Ops:
 
     def __init__(self, lib: Optional[C.CDLL] = None):
         self.lib = lib or load_library()
-        self.gemm_backend = {"auto": GEMM_AUTO, "tcgen05": GEMM_TCGEN05, "simt": GEMM_SIMT, "tcgen05_v1": GEMM_TCGEN05_V1}[
-            os.environ.get("NPVP_B200_GEMM", "auto")]
+        self.gemm_backend = {"auto": GEMM_AUTO, "tcgen05": GEMM_TCGEN05, "simt": GEMM_SIMT, "tcgen05_v1": GEMM_TCGEN05_V1,
+                             "tcgen05_2cta": GEMM_TCGEN05_2CTA}[os.environ.get("NPVP_B200_GEMM", "auto")]
+        self.lib.npvp_set_option(b"gemm_2cta", int(os.environ.get("NPVP_B200_GEMM_2CTA", "0")))
 
     # -- plumbing -------------------------------------------------------------------------------
     def _stream(self):

@@ -9,6 +9,7 @@
 //   npvp_gemm_f32  : fp32 CUDA-core GEMM for the NRMLP positional MLP (precision critical, tiny).
 #include "common.cuh"
 #include <cuda.h>
+#include <string.h>
 
 // =============================================================================================
 // PTX wrappers
@@ -595,6 +596,246 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 }
 
 // =============================================================================================
+// tcgen05 GEMM kernel, 2-CTA variant (cta_group::2): a pair of SMs computes a 256 x 256 tile
+// =============================================================================================
+// r01 finding: the 1-CTA kernel is bound by shared-memory bandwidth (per 64-wide k-block a 128x256 tile makes TMA
+// write 48 KB and the tensor core read 48 KB, the epilogue transpose adds ~33 KB: 129 KB against 128 B/clk x 512 clk).
+// With cta_group::2 the two CTAs of a cluster each stage their own 128 rows of A and HALF of the B tile (128 of the 256
+// N-rows); one tcgen05.mma issued by the leader drives both tensor cores (UMMA M = 256) and B is shared between the
+// pair in hardware, so operand traffic per SM drops from 96 KB to 64 KB per k-block.
+//   - both CTAs run a TMA producer; all complete_tx land on the LEADER's full barrier (peer bit cleared in the address)
+//   - only the leader issues MMAs; tcgen05.commit ... multicast::cluster releases the smem stage / publishes the
+//     accumulator in both CTAs
+//   - each CTA's 8 epilogue warps drain their own TMEM half and arrive (remotely for the follower) on the leader's
+//     tmem_empty barrier
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+struct Gemm3Cfg {
+  static constexpr int BN = 256;
+  static constexpr int kABytes = kBM * kBK * 2;            // this CTA's 128 rows of A
+  static constexpr int kBBytes = (BN / 2) * kBK * 2;       // this CTA's half of the B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;    // 32 KB
+  static constexpr int kStages = 6;
+  static constexpr int kStagingBytes = kEpiWarps * 32 * 32 * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
+  static constexpr uint32_t kTmemCols = 512;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(ptx::smem_u32(smem_dst)), "l"(map), "r"(ptx::smem_u32(bar) & kPeerBitMask), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {     // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(ptx::smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+template <int ACT, int RES, int OUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         int64_t M, int64_t N, int64_t K, EpiParams ep) {
+  using Cfg = Gemm3Cfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  float* staging = (float*)(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bars = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;        // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * Cfg::kStages + 2;   // [2]  (the leader's copy is the live one)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_k_blocks = (int)((K + kBK - 1) / kBK);
+  const int n_tiles = (int)((N + BN - 1) / BN);
+  const int64_t m_tiles = (M + 2 * kBM - 1) / (2 * kBM);
+  const int64_t num_tiles = m_tiles * n_tiles;
+  const int64_t pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 2 * kEpiWarps);   // epilogue warps of both CTAs
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(tmem_slot)), "r"(Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  ptx::tc_fence_before();
+  cluster_sync_all();                                        // barriers of both CTAs are initialised before any remote arrive
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer (both CTAs) ----------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = pair; t < num_tiles; t += num_pairs) {
+        const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
+        const int m_row = m_blk * 2 * kBM + (int)rank * kBM;
+        const int n_row = n_blk * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_row);
+          tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, n_row);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (leader CTA only) ----------------
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_f16kind(2 * kBM, BN, ep.fp16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = pair; t < num_tiles; t += num_pairs) {
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t bdesc = make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_bf16_2cta(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit_2cta(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(&tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue (both CTAs, own 128 rows) ----------------
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    float* stg = staging + (warp - 4) * (32 * 32);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int sub_row = lane >> 3, chunk = lane & 7;
+    const bool has_bias = ep.bias != nullptr;
+    const int fp16 = ep.fp16;
+    const float alpha = ep.alpha;
+    constexpr int kColsPerWarp = BN / 2;
+    const uint32_t empty_remote[2] = {mapa_u32(ptx::smem_u32(&tmem_empty_bar[0]), 0), mapa_u32(ptx::smem_u32(&tmem_empty_bar[1]), 0)};
+    for (int64_t t = pair; t < num_tiles; t += num_pairs) {
+      const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
+      auto load_bias = [&](int c) {
+        const int64_t nb = (int64_t)n_blk * BN + c + chunk * 4;
+        return (has_bias && nb < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      float4 b_next = load_bias(half * kColsPerWarp);
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int64_t m_base = (int64_t)m_blk * 2 * kBM + (int64_t)rank * kBM + quad * 32;
+#pragma unroll 1
+      for (int c = half * kColsPerWarp; c < (half + 1) * kColsPerWarp; c += 32) {
+        const float4 b4 = b_next;
+        if (c + 32 < (half + 1) * kColsPerWarp) b_next = load_bias(c + 32);
+        const int64_t n0 = (int64_t)n_blk * BN + c;
+        if (n0 >= N) break;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        const int64_t n = n0 + chunk * 4;
+        const bool col_ok = n < N;
+        float4 rs[8];
+        if (RES != 0) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int64_t m = m_base + it * 4 + sub_row;
+            rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && col_ok) {
+              const int64_t roff = m * ep.ld_res + n;
+              if (RES == 1) add_res(rs[it], ep.res1, 0, fp16, roff);
+              if (RES == 2 || RES == 3) add_res(rs[it], ep.res1, 1, fp16, roff);
+              if (RES == 3) add_res(rs[it], ep.res2, 1, fp16, roff);
+              if (RES < 0) {
+                if (ep.res1) add_res(rs[it], ep.res1, ep.res1_bf16, fp16, roff);
+                if (ep.res2) add_res(rs[it], ep.res2, ep.res2_bf16, fp16, roff);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + sub_row;
+          const int64_t m = m_base + row;
+          float4 q = *reinterpret_cast<const float4*>(stg + row * 32 + ((chunk ^ (row & 7)) << 2));
+          if (m < M && col_ok) {
+            q.x = act_ct<ACT>(q.x + b4.x, ep.act) * alpha;
+            q.y = act_ct<ACT>(q.y + b4.y, ep.act) * alpha;
+            q.z = act_ct<ACT>(q.z + b4.z, ep.act) * alpha;
+            q.w = act_ct<ACT>(q.w + b4.w, ep.act) * alpha;
+            if (RES != 0) { q.x += rs[it].x; q.y += rs[it].y; q.z += rs[it].z; q.w += rs[it].w; }
+            if (ep.post_relu) { q.x = fmaxf(q.x, 0.f); q.y = fmaxf(q.y, 0.f); q.z = fmaxf(q.z, 0.f); q.w = fmaxf(q.w, 0.f); }
+            const int64_t ooff = m * ep.ld_out + n;
+            if (OUT == 1 || OUT == 2 || (OUT < 0 && ep.out_f32)) *reinterpret_cast<float4*>(ep.out_f32 + ooff) = q;
+            if (OUT == 0 || OUT == 2 || (OUT < 0 && ep.out_bf16))
+              *reinterpret_cast<uint2*>(ep.out_bf16 + ooff) = make_uint2(pack_h16x2(q.x, q.y, fp16), pack_h16x2(q.z, q.w, fp16));
+          }
+        }
+        __syncwarp();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(empty_remote[acc]);       // the leader's barrier counts both CTAs' epilogue warps
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  ptx::tc_fence_before();
+  cluster_sync_all();                                              // peer smem / TMEM stay valid until both CTAs are done
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// =============================================================================================
 // SIMT kernels
 // =============================================================================================
 // 64x64 tile, 16-deep k-slab, 256 threads, 4x4 outputs per thread.  TA in {bf16, float}.
@@ -705,6 +946,7 @@ static int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw
 
 
 static int g_num_sms = 0;
+static int g_use_2cta = 0;      // npvp_set_option("gemm_2cta", 1): route N >= 256 GEMMs of the default path to the cluster kernel
 
 template <int BN, int ACT, int RES, int OUT, int CONV>
 static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, int64_t M, int64_t N, int64_t K, const EpiParams& e,
@@ -765,6 +1007,49 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
   return launch_v2_inst<BN, -1, -1, -1, 0>(ta, tb, M, N, K, e, cg0, grid, st);
 }
 
+template <int ACT, int RES, int OUT>
+static int launch_2cta_inst(const CUtensorMap& ta, const CUtensorMap& tb, int64_t M, int64_t N, int64_t K, const EpiParams& e,
+                            unsigned grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<ACT, RES, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm3Cfg::kSmemBytes);
+    if (err != cudaSuccess) { npvp_set_error("cudaFuncSetAttribute(2cta, smem=%d): %s", Gemm3Cfg::kSmemBytes, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
+    attr_set = true;
+  }
+  gemm_tcgen05_2cta_kernel<ACT, RES, OUT><<<grid, kGemm2Threads, Gemm3Cfg::kSmemBytes, st>>>(ta, tb, M, N, K, e);
+  NPVP_LAUNCH_CHECK("gemm_tcgen05_2cta_kernel");
+  return NPVP_OK;
+}
+
+static int launch_tcgen05_2cta(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                               const EpiParams& e, cudaStream_t st) {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(&ta, A, M, K, lda, kBM, e.fp16);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tb, W, N, K, ldw, Gemm3Cfg::BN / 2, e.fp16);
+  if (rc) return rc;
+  const int64_t tiles = ceil_div64(M, 2 * kBM) * ceil_div64(N, Gemm3Cfg::BN);
+  const int64_t pairs = g_num_sms / 2;
+  const unsigned grid = 2u * (unsigned)(tiles < pairs ? tiles : pairs);
+  const int res = !e.res1 ? (e.res2 ? -1 : 0) : (!e.res2 ? (e.res1_bf16 ? 2 : 1) : ((e.res1_bf16 && e.res2_bf16) ? 3 : -1));
+  const int out = (e.out_f32 && e.out_bf16) ? 2 : (e.out_f32 ? 1 : 0);
+  const int act = e.act;
+#define NPVP_V3_CASE(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_2cta_inst<A_, R_, O_>(ta, tb, M, N, K, e, grid, st)
+  NPVP_V3_CASE(NPVP_ACT_NONE, 0, 0);
+  NPVP_V3_CASE(NPVP_ACT_GELU, 0, 0);
+  NPVP_V3_CASE(NPVP_ACT_RELU, 0, 0);
+  NPVP_V3_CASE(NPVP_ACT_NONE, 1, 1);
+  NPVP_V3_CASE(NPVP_ACT_NONE, 0, 1);
+#undef NPVP_V3_CASE
+  return launch_2cta_inst<-1, -1, -1>(ta, tb, M, N, K, e, grid, st);
+}
+
 static bool tma_compatible(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t K) {
   return ((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && (lda % 8 == 0) && (ldw % 8 == 0) && (K % 8 == 0);
 }
@@ -799,10 +1084,15 @@ extern "C" int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   // clip would be computed differently alone and inside a batch; TMA zero-fills boxes that overhang small operands.
   if (backend == NPVP_GEMM_AUTO)
     backend = (tma_compatible(A, lda, W, ldw, K) && vec_ok && K >= kBK) ? NPVP_GEMM_TCGEN05 : NPVP_GEMM_SIMT;
-  if (backend == NPVP_GEMM_TCGEN05 || backend == NPVP_GEMM_TCGEN05_V1) {
+  if (backend == NPVP_GEMM_TCGEN05 || backend == NPVP_GEMM_TCGEN05_V1 || backend == NPVP_GEMM_TCGEN05_2CTA) {
     NPVP_REQUIRE(tma_compatible(A, lda, W, ldw, K) && vec_ok, "npvp_gemm_bf16: operands not 16-byte aligned / K,ld not multiples of 8 for the TMA path");
     const bool res_ok = (!(ep->res1 || ep->res2)) || (ep->ld_res % 4 == 0 && (uintptr_t)ep->res1 % 16 == 0 && (uintptr_t)ep->res2 % 16 == 0);
+    if (backend == NPVP_GEMM_TCGEN05_2CTA) {
+      NPVP_REQUIRE(N % 4 == 0 && res_ok, "npvp_gemm_bf16: 2-CTA path needs N %% 4 == 0 and 16-byte aligned residuals");
+      return launch_tcgen05_2cta(A, lda, W, ldw, M, N, K, e, st);
+    }
     if (backend == NPVP_GEMM_TCGEN05 && N % 4 == 0 && res_ok) {       // persistent kernel; tile width never depends on M
+      if (N >= 256 && g_use_2cta) return launch_tcgen05_2cta(A, lda, W, ldw, M, N, K, e, st);
       if (N >= 256) return launch_tcgen05_v2<256>(A, lda, W, ldw, M, N, K, e, st);
       if (N > 64) return launch_tcgen05_v2<128>(A, lda, W, ldw, M, N, K, e, st);
       return launch_tcgen05_v2<64>(A, lda, W, ldw, M, N, K, e, st);
@@ -859,4 +1149,12 @@ extern "C" int npvp_conv_gemm_bf16(const void* x, int64_t frames, int H, int W, 
   if (N >= 256) return launch_tcgen05_v2<256>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);
   if (N > 64) return launch_tcgen05_v2<128>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);
   return launch_tcgen05_v2<64>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);
+}
+
+
+extern "C" int npvp_set_option(const char* name, int value) {
+  NPVP_REQUIRE(name != nullptr, "npvp_set_option: null name");
+  if (strcmp(name, "gemm_2cta") == 0) { g_use_2cta = value; return NPVP_OK; }
+  NPVP_REQUIRE(false, "npvp_set_option: unknown option '%s'", name);
+  return NPVP_ERR_INVALID;
 }

@@ -40,7 +40,7 @@ H16 = [torch.bfloat16, torch.float16]
 
 
 @pytest.mark.parametrize("dt", H16)
-@pytest.mark.parametrize("backend", [2, 1, 3, 0])
+@pytest.mark.parametrize("backend", [2, 1, 3, 4, 0])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_plain(op, spec, backend, M, N, K, dt):
     a, w = rn(M, K, seed=1, dtype=dt), rn(N, K, seed=2, scale=K ** -0.5, dtype=dt)
@@ -55,7 +55,7 @@ def test_gemm_plain(op, spec, backend, M, N, K, dt):
 
 
 @pytest.mark.parametrize("dt", H16)
-@pytest.mark.parametrize("backend", [2, 1, 3])
+@pytest.mark.parametrize("backend", [2, 1, 3, 4])
 def test_gemm_epilogues(op, spec, backend, dt):
     M, N, K = 384, 512, 1024
     a, w = rn(M, K, seed=1, dtype=dt), rn(N, K, seed=2, scale=K ** -0.5, dtype=dt)

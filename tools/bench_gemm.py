@@ -12,7 +12,7 @@ def main():
               (M, 512, 1024, "res"), (M // 5, 512, 512, "bf16"), (8192, 256, 4608, "bf16"), (M * 8, 128, 256, "bf16"), (M * 8, 64, 576, "bf16")]
     if os.environ.get("SHAPES"):
         shapes = [shapes[int(i)] for i in os.environ["SHAPES"].split(",")]
-    backends = [b for b in (("v1", 3), ("v2", 1)) if os.environ.get("ONLY", b[0]) == b[0]]
+    backends = [b for b in (("v1", 3), ("v2", 1), ("2cta", 4)) if os.environ.get("ONLY", b[0]) == b[0]]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for (m, n, k, kind) in shapes:
         a = torch.randn(m, k, device=dev).to(torch.bfloat16)
@@ -42,7 +42,7 @@ def main():
             out = (of if "out_f32" in kw else ob).float().clone()
             if ref is None: ref = out
             line += f" | {name}: {t*1e3:8.1f} us {2*m*n*k/t/1e9:7.1f} TFLOP/s"
-            if name == "v2": line += f" | maxdiff v1-v2 {float((out-ref).abs().max()):.2e}"
+            if name != backends[0][0]: line += f" (maxdiff vs {backends[0][0]} {float((out-ref).abs().max()):.1e})"
         print(line, flush=True)
 
 if __name__ == "__main__":
