@@ -164,7 +164,7 @@ class Ops:
                 ld_res = ld
         ep = Epilogue(_ptr(bias), _ptr(res1), _ptr(res2), _ptr(out_f32), _ptr(out_bf16), float(alpha), int(act),
                       int(res1 is not None and res1.dtype in H16),
-                      int(res2 is not None and res2.dtype in H16), int(bool(post_relu)), _is_fp16(a), 0, ld_out, ld_res)
+                      int(res2 is not None and res2.dtype in H16), int(post_relu), _is_fp16(a), 0, ld_out, ld_res)
         self._call("npvp_gemm_bf16", a.data_ptr(), lda, w.data_ptr(), ldw, M, N, K, C.byref(ep),
                    self.gemm_backend if backend is None else backend, self._stream())
 

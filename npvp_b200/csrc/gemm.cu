@@ -295,6 +295,16 @@ struct Gemm2Cfg {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
 }
+// Explicit shared-space accesses for the epilogue staging tile: through a generic pointer carved out of the dynamic smem
+// block the compiler emitted generic ST.E / LD.E (long-scoreboard latency, r01 profile) instead of STS / LDS.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 
 // Implicit-GEMM convolution: the A operand (rows = output pixels, K = (ky, kx, ci)) is gathered by two producer warps
 // straight from the channels-last activations with 16-byte cp.async into the same 128B-swizzled layout TMA would
@@ -338,6 +348,60 @@ __device__ __forceinline__ void add_res(float4& q, const void* res, int is16, in
   } else {
     const float4 a = *reinterpret_cast<const float4*>((const float*)res + off);
     q.x += a.x; q.y += a.y; q.z += a.z; q.w += a.w;
+  }
+}
+
+// One 32x32 chunk of the epilogue in the coalesced layout (4 rows x 128 B per warp instruction).  Written branch-free:
+// all eight swizzled LDS.128 and all residual loads are issued first, the math is straight-line, and the bounds checks
+// only predicate the loads / stores.  (r01: with a per-row `if` the compiler emitted one BSSY/BSYNC region per row, the
+// rows serialised at ~100 cycles each and the epilogue - not the 98 %-of-peak main loop - set the tile time.)
+template <int ACT, int RES, int OUT, bool FP16>
+__device__ __forceinline__ void epi_chunk(uint32_t stg_addr, int sub_row, int chunk, int64_t m_base, int64_t M, bool col_ok,
+                                          int64_t n, const float4 b4, float alpha, float relu_floor, const EpiParams& ep) {
+  constexpr int fp16 = FP16 ? 1 : 0;
+  float4 q[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + sub_row;
+    q[it] = lds128(stg_addr + (uint32_t)((row * 32 + ((chunk ^ (row & 7)) << 2)) * 4));
+  }
+  float4 rs[8];
+  if (RES != 0) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int64_t m = m_base + it * 4 + sub_row;
+      rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M && col_ok) {
+        const int64_t roff = m * ep.ld_res + n;
+        if (RES == 1) add_res(rs[it], ep.res1, 0, fp16, roff);
+        if (RES == 2 || RES == 3) add_res(rs[it], ep.res1, 1, fp16, roff);
+        if (RES == 3) add_res(rs[it], ep.res2, 1, fp16, roff);
+        if (RES < 0) {
+          if (ep.res1) add_res(rs[it], ep.res1, ep.res1_bf16, fp16, roff);
+          if (ep.res2) add_res(rs[it], ep.res2, ep.res2_bf16, fp16, roff);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    float4& v = q[it];
+    v.x = act_ct<ACT>(v.x + b4.x, ep.act) * alpha;
+    v.y = act_ct<ACT>(v.y + b4.y, ep.act) * alpha;
+    v.z = act_ct<ACT>(v.z + b4.z, ep.act) * alpha;
+    v.w = act_ct<ACT>(v.w + b4.w, ep.act) * alpha;
+    if (RES != 0) { v.x += rs[it].x; v.y += rs[it].y; v.z += rs[it].z; v.w += rs[it].w; }
+    v.x = fmaxf(v.x, relu_floor); v.y = fmaxf(v.y, relu_floor); v.z = fmaxf(v.z, relu_floor); v.w = fmaxf(v.w, relu_floor);
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int64_t m = m_base + it * 4 + sub_row;
+    if (m < M && col_ok) {
+      const int64_t ooff = m * ep.ld_out + n;
+      if (OUT == 1 || OUT == 2 || (OUT < 0 && ep.out_f32)) *reinterpret_cast<float4*>(ep.out_f32 + ooff) = q[it];
+      if (OUT == 0 || OUT == 2 || (OUT < 0 && ep.out_bf16))
+        *reinterpret_cast<uint2*>(ep.out_bf16 + ooff) = make_uint2(pack_h16x2(q[it].x, q[it].y, fp16), pack_h16x2(q[it].z, q[it].w, fp16));
+    }
   }
 }
 
@@ -507,13 +571,14 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     // ---------------- epilogue ----------------
     const int quad = warp & 3;                                      // TMEM lane quadrant of this warp
     const int half = (warp - 4) >> 2;                               // which half of the tile's columns
-    float* stg = staging + (warp - 4) * (32 * 32);
+    const uint32_t stg_addr = ptx::smem_u32(staging + (warp - 4) * (32 * 32));
     int acc = 0;
     uint32_t acc_phase = 0;
     const int sub_row = lane >> 3, chunk = lane & 7;                // coalesced layout: 4 rows x 8 float4 per instruction
     const bool has_bias = ep.bias != nullptr;
     const int fp16 = ep.fp16;
     const float alpha = ep.alpha;
+    const float relu_floor = ep.post_relu ? 0.f : -INFINITY;
     constexpr int kColsPerWarp = BN / 2;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
@@ -538,48 +603,13 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j)                                  // float4 chunk j of row `lane` -> slot j ^ (lane & 7)
-          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          sts128(stg_addr + (uint32_t)((lane * 32 + ((j ^ (lane & 7)) << 2)) * 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
         const int64_t n = n0 + chunk * 4;
         const bool col_ok = n < N;                                   // N % 4 == 0 on this path
-        // Residuals may alias the output (in-place residual-stream update), so the compiler cannot hoist their loads
-        // above the stores: fetch all of this chunk's residual vectors first (8 independent 128-bit loads in flight).
-        float4 rs[8];
-        if (RES != 0) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int64_t m = m_base + it * 4 + sub_row;
-            rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < M && col_ok) {
-              const int64_t roff = m * ep.ld_res + n;
-              if (RES == 1) add_res(rs[it], ep.res1, 0, fp16, roff);
-              if (RES == 2 || RES == 3) add_res(rs[it], ep.res1, 1, fp16, roff);
-              if (RES == 3) add_res(rs[it], ep.res2, 1, fp16, roff);
-              if (RES < 0) {
-                if (ep.res1) add_res(rs[it], ep.res1, ep.res1_bf16, fp16, roff);
-                if (ep.res2) add_res(rs[it], ep.res2, ep.res2_bf16, fp16, roff);
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = it * 4 + sub_row;
-          const int64_t m = m_base + row;
-          float4 q = *reinterpret_cast<const float4*>(stg + row * 32 + ((chunk ^ (row & 7)) << 2));
-          if (m < M && col_ok) {
-            q.x = act_ct<ACT>(q.x + b4.x, ep.act) * alpha;
-            q.y = act_ct<ACT>(q.y + b4.y, ep.act) * alpha;
-            q.z = act_ct<ACT>(q.z + b4.z, ep.act) * alpha;
-            q.w = act_ct<ACT>(q.w + b4.w, ep.act) * alpha;
-            if (RES != 0) { q.x += rs[it].x; q.y += rs[it].y; q.z += rs[it].z; q.w += rs[it].w; }
-            if (ep.post_relu) { q.x = fmaxf(q.x, 0.f); q.y = fmaxf(q.y, 0.f); q.z = fmaxf(q.z, 0.f); q.w = fmaxf(q.w, 0.f); }
-            const int64_t ooff = m * ep.ld_out + n;
-            if (OUT == 1 || OUT == 2 || (OUT < 0 && ep.out_f32)) *reinterpret_cast<float4*>(ep.out_f32 + ooff) = q;
-            if (OUT == 0 || OUT == 2 || (OUT < 0 && ep.out_bf16))
-              *reinterpret_cast<uint2*>(ep.out_bf16 + ooff) = make_uint2(pack_h16x2(q.x, q.y, fp16), pack_h16x2(q.z, q.w, fp16));
-          }
-        }
+        // (residuals may alias the output - in-place residual-stream update - so epi_chunk loads them before any store)
+        if (fp16) epi_chunk<ACT, RES, OUT, true>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep);
+        else      epi_chunk<ACT, RES, OUT, false>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep);
         __syncwarp();
       }
       ptx::tc_fence_before();
@@ -749,13 +779,14 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ---------------- epilogue (both CTAs, own 128 rows) ----------------
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;
-    float* stg = staging + (warp - 4) * (32 * 32);
+    const uint32_t stg_addr = ptx::smem_u32(staging + (warp - 4) * (32 * 32));
     int acc = 0;
     uint32_t acc_phase = 0;
     const int sub_row = lane >> 3, chunk = lane & 7;
     const bool has_bias = ep.bias != nullptr;
     const int fp16 = ep.fp16;
     const float alpha = ep.alpha;
+    const float relu_floor = ep.post_relu ? 0.f : -INFINITY;
     constexpr int kColsPerWarp = BN / 2;
     const uint32_t empty_remote[2] = {mapa_u32(ptx::smem_u32(&tmem_empty_bar[0]), 0), mapa_u32(ptx::smem_u32(&tmem_empty_bar[1]), 0)};
     for (int64_t t = pair; t < num_tiles; t += num_pairs) {
@@ -779,46 +810,12 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          sts128(stg_addr + (uint32_t)((lane * 32 + ((j ^ (lane & 7)) << 2)) * 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
         const int64_t n = n0 + chunk * 4;
         const bool col_ok = n < N;
-        float4 rs[8];
-        if (RES != 0) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int64_t m = m_base + it * 4 + sub_row;
-            rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < M && col_ok) {
-              const int64_t roff = m * ep.ld_res + n;
-              if (RES == 1) add_res(rs[it], ep.res1, 0, fp16, roff);
-              if (RES == 2 || RES == 3) add_res(rs[it], ep.res1, 1, fp16, roff);
-              if (RES == 3) add_res(rs[it], ep.res2, 1, fp16, roff);
-              if (RES < 0) {
-                if (ep.res1) add_res(rs[it], ep.res1, ep.res1_bf16, fp16, roff);
-                if (ep.res2) add_res(rs[it], ep.res2, ep.res2_bf16, fp16, roff);
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = it * 4 + sub_row;
-          const int64_t m = m_base + row;
-          float4 q = *reinterpret_cast<const float4*>(stg + row * 32 + ((chunk ^ (row & 7)) << 2));
-          if (m < M && col_ok) {
-            q.x = act_ct<ACT>(q.x + b4.x, ep.act) * alpha;
-            q.y = act_ct<ACT>(q.y + b4.y, ep.act) * alpha;
-            q.z = act_ct<ACT>(q.z + b4.z, ep.act) * alpha;
-            q.w = act_ct<ACT>(q.w + b4.w, ep.act) * alpha;
-            if (RES != 0) { q.x += rs[it].x; q.y += rs[it].y; q.z += rs[it].z; q.w += rs[it].w; }
-            if (ep.post_relu) { q.x = fmaxf(q.x, 0.f); q.y = fmaxf(q.y, 0.f); q.z = fmaxf(q.z, 0.f); q.w = fmaxf(q.w, 0.f); }
-            const int64_t ooff = m * ep.ld_out + n;
-            if (OUT == 1 || OUT == 2 || (OUT < 0 && ep.out_f32)) *reinterpret_cast<float4*>(ep.out_f32 + ooff) = q;
-            if (OUT == 0 || OUT == 2 || (OUT < 0 && ep.out_bf16))
-              *reinterpret_cast<uint2*>(ep.out_bf16 + ooff) = make_uint2(pack_h16x2(q.x, q.y, fp16), pack_h16x2(q.z, q.w, fp16));
-          }
-        }
+        if (fp16) epi_chunk<ACT, RES, OUT, true>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep);
+        else      epi_chunk<ACT, RES, OUT, false>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep);
         __syncwarp();
       }
       ptx::tc_fence_before();

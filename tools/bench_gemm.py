@@ -22,6 +22,7 @@ def main():
         of = torch.empty(m, n, device=dev)
         ob = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
         kw = dict(bias=bias)
+        if os.environ.get("POST_RELU"): kw["post_relu"] = int(os.environ["POST_RELU"])
         if kind == "res": kw.update(res1=res, out_f32=of)
         elif kind == "f32": kw.update(out_f32=of)
         elif kind == "gelu": kw.update(act=2, out_bf16=ob)
