@@ -113,6 +113,13 @@ int npvp_ln_posfuse(const float* x, const float* ln_w, const float* ln_b, const 
  * Outputs optional fp32 and/or bf16. */
 int npvp_layernorm_rows(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16,
                         int64_t rows, int relu, int fp16, void* stream);
+/* Deferred residual add: a residual branch's GEMM leaves its output `delta` in bf16 [rows,512] instead of read-modify-writing
+ * the fp32 stream in its (latency-sensitive) epilogue; the LayerNorm kernel that reads the stream next performs
+ * x += delta (written back, fp32) before normalising.  Same arguments as the functions above plus x in-out and delta. */
+int npvp_add_layernorm_rows(float* x, const void* delta_bf16, const float* w, const float* b, float* out_f32, void* out_bf16,
+                            int64_t rows, int relu, int fp16, void* stream);
+int npvp_add_ln_posfuse(float* x, const void* delta_bf16, const float* ln_w, const float* ln_b, const float* qe, const float* beta,
+                        const float* gamma, void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T, void* stream);
 /* y += GELU(LayerNorm_(C,8,8)(h))  - MlpDWBN norm3 + act3 + the block's residual add
  * (VidHRFormer.py:388-389 with :91/:214/:243).  h fp32 [frames,64,512]; w,b fp32 [64,512] (hw-major). */
 int npvp_frame_ln_gelu_residual(const float* h, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,

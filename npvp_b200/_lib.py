@@ -38,6 +38,8 @@ SIGNATURES = {
     "npvp_gemm_f32": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i32, _vp, _i64, _vp],
     "npvp_fourier_features": [_vp, _vp, _vp, _i64, _i32, _vp],
     "npvp_ln_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "npvp_add_layernorm_rows": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
+    "npvp_add_ln_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_layernorm_rows": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "npvp_frame_ln_gelu_residual": [_vp, _vp, _vp, _vp, _i64, _vp],
     "npvp_frame_ln_gelu_residual_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
@@ -217,6 +219,23 @@ class Ops:
         assert beta is None or beta.numel() == T * 64 * 512
         self._call("npvp_ln_posfuse", x.data_ptr(), _ptr(ln_w), _ptr(ln_b), _ptr(qe), _ptr(beta), _ptr(gamma), _ptr(out_ln),
                    _ptr(out_fused), n_clips, T, self._stream())
+
+    def add_layernorm_rows(self, x, delta, w, b, out_f32=None, out_bf16=None, relu=False):
+        """x += delta (deferred residual, written back), then LayerNorm(512) of the updated rows."""
+        _chk(x, torch.float32, "x"); _chk(delta, torch.bfloat16, "delta"); _chk(w, torch.float32, "w"); _chk(b, torch.float32, "b")
+        _chk(out_f32, torch.float32, "out_f32"); _chk16(out_bf16, "out_bf16")
+        assert delta.numel() == x.numel()
+        self._call("npvp_add_layernorm_rows", x.data_ptr(), delta.data_ptr(), w.data_ptr(), b.data_ptr(), _ptr(out_f32), _ptr(out_bf16),
+                   x.numel() // 512, int(relu), 0 if out_bf16 is None else _is_fp16(out_bf16), self._stream())
+
+    def add_ln_posfuse(self, x, delta, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, n_clips, T):
+        """x += delta (deferred residual, written back), then ln_posfuse of the updated frames."""
+        _chk(x, torch.float32, "x"); _chk(delta, torch.bfloat16, "delta"); _chk(ln_w, torch.float32, "ln_w"); _chk(ln_b, torch.float32, "ln_b")
+        _chk(qe, torch.float32, "qe"); _chk(beta, torch.float32, "beta"); _chk(gamma, torch.float32, "gamma")
+        _chk(out_ln, torch.bfloat16, "out_ln"); _chk(out_fused, torch.bfloat16, "out_fused")
+        assert x.numel() == n_clips * T * 64 * 512 and delta.numel() == x.numel()
+        self._call("npvp_add_ln_posfuse", x.data_ptr(), delta.data_ptr(), _ptr(ln_w), _ptr(ln_b), _ptr(qe), _ptr(beta), _ptr(gamma),
+                   _ptr(out_ln), _ptr(out_fused), n_clips, T, self._stream())
 
     def layernorm_rows(self, x, w, b, out_f32=None, out_bf16=None, relu=False):
         _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(b, torch.float32, "b")

@@ -126,14 +126,31 @@ __device__ __forceinline__ void posfuse_from_regs(FrameRegs& r, float* red, int 
   frame_store_bf16(out_fused + (size_t)f * kTok * kC, r, warp, lane);
 }
 
+// x += delta (a residual branch's output left in bf16 by its GEMM), written back in fp32, for the frame held in registers
+__device__ __forceinline__ void frame_add_delta(float* __restrict__ x, const bf16* __restrict__ delta, FrameRegs& r, int warp, int lane) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const uint2* drow = reinterpret_cast<const uint2*>(delta + (size_t)(warp * 4 + t) * kC);
+    float4* xrow = reinterpret_cast<float4*>(x + (size_t)(warp * 4 + t) * kC);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint2 u = __ldg(drow + j * 32 + lane);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      r.v[t][4 * j] += a.x; r.v[t][4 * j + 1] += a.y; r.v[t][4 * j + 2] += b.x; r.v[t][4 * j + 3] += b.y;
+      xrow[j * 32 + lane] = make_float4(r.v[t][4 * j], r.v[t][4 * j + 1], r.v[t][4 * j + 2], r.v[t][4 * j + 3]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(512)
-ln_posfuse_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+ln_posfuse_kernel(float* __restrict__ x, const bf16* __restrict__ delta, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                   const float* __restrict__ qe, const float* __restrict__ beta, const float* __restrict__ gamma,
                   bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int T) {
   __shared__ float red[64];
   const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FrameRegs r;
   frame_load(x + (size_t)f * kTok * kC, r, warp, lane);
+  if (delta) frame_add_delta(x + (size_t)f * kTok * kC, delta + (size_t)f * kTok * kC, r, warp, lane);
   posfuse_from_regs(r, red, f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, warp, lane);
 }
 
@@ -144,9 +161,22 @@ extern "C" int npvp_ln_posfuse(const float* x, const float* ln_w, const float* l
   NPVP_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "npvp_ln_posfuse: ln_w/ln_b must both be set or both NULL");
   NPVP_REQUIRE(!out_fused_bf16 || beta, "npvp_ln_posfuse: beta required for the fused output");
   NPVP_REQUIRE(n_clips > 0 && T > 0, "npvp_ln_posfuse: empty input");
-  ln_posfuse_kernel<<<(unsigned)(n_clips * T), 512, 0, (cudaStream_t)stream>>>(x, ln_w, ln_b, qe, beta, gamma, (bf16*)out_ln_bf16,
-                                                                              (bf16*)out_fused_bf16, (int)T);
+  ln_posfuse_kernel<<<(unsigned)(n_clips * T), 512, 0, (cudaStream_t)stream>>>(const_cast<float*>(x), nullptr, ln_w, ln_b, qe, beta, gamma,
+                                                                              (bf16*)out_ln_bf16, (bf16*)out_fused_bf16, (int)T);
   NPVP_LAUNCH_CHECK("ln_posfuse_kernel");
+  return NPVP_OK;
+}
+
+extern "C" int npvp_add_ln_posfuse(float* x, const void* delta_bf16, const float* ln_w, const float* ln_b, const float* qe,
+                                   const float* beta, const float* gamma, void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips,
+                                   int64_t T, void* stream) {
+  NPVP_REQUIRE(x && delta_bf16 && (out_ln_bf16 || out_fused_bf16), "npvp_add_ln_posfuse: null pointer");
+  NPVP_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "npvp_add_ln_posfuse: ln_w/ln_b must both be set or both NULL");
+  NPVP_REQUIRE(!out_fused_bf16 || beta, "npvp_add_ln_posfuse: beta required for the fused output");
+  NPVP_REQUIRE(n_clips > 0 && T > 0, "npvp_add_ln_posfuse: empty input");
+  ln_posfuse_kernel<<<(unsigned)(n_clips * T), 512, 0, (cudaStream_t)stream>>>(x, (const bf16*)delta_bf16, ln_w, ln_b, qe, beta, gamma,
+                                                                              (bf16*)out_ln_bf16, (bf16*)out_fused_bf16, (int)T);
+  NPVP_LAUNCH_CHECK("ln_posfuse_kernel<add>");
   return NPVP_OK;
 }
 
@@ -154,17 +184,23 @@ extern "C" int npvp_ln_posfuse(const float* x, const float* ln_w, const float* l
 // LayerNorm(512) per token: one warp per row
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+layernorm_rows_kernel(float* __restrict__ x, const bf16* __restrict__ delta, const float* __restrict__ w, const float* __restrict__ b,
                       float* __restrict__ out_f32, h16* __restrict__ out_bf16, int64_t rows, int relu, int fp16) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   float v[16];
   float4 wv[4], bv[4];
-  const float4* src = reinterpret_cast<const float4*>(x + row * kC);
+  float4* src = reinterpret_cast<float4*>(x + row * kC);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float4 q = __ldg(src + j * 32 + lane);
+    float4 q = src[j * 32 + lane];
+    if (delta) {                                   // deferred residual add: x += delta, written back
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(delta + row * kC) + j * 32 + lane);
+      const float2 da = unpack_bf16x2(u.x), db = unpack_bf16x2(u.y);
+      q.x += da.x; q.y += da.y; q.z += db.x; q.w += db.y;
+      src[j * 32 + lane] = q;
+    }
     v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
     wv[j] = __ldg(reinterpret_cast<const float4*>(w) + j * 32 + lane);
     bv[j] = __ldg(reinterpret_cast<const float4*>(b) + j * 32 + lane);
@@ -184,8 +220,17 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 extern "C" int npvp_layernorm_rows(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16,
                                    int64_t rows, int relu, int fp16, void* stream) {
   NPVP_REQUIRE(x && w && b && (out_f32 || out_bf16) && rows > 0, "npvp_layernorm_rows: bad arguments");
-  layernorm_rows_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, w, b, out_f32, (h16*)out_bf16, rows, relu, fp16);
+  layernorm_rows_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(x), nullptr, w, b, out_f32, (h16*)out_bf16, rows, relu, fp16);
   NPVP_LAUNCH_CHECK("layernorm_rows_kernel");
+  return NPVP_OK;
+}
+
+extern "C" int npvp_add_layernorm_rows(float* x, const void* delta_bf16, const float* w, const float* b, float* out_f32, void* out_bf16,
+                                       int64_t rows, int relu, int fp16, void* stream) {
+  NPVP_REQUIRE(x && delta_bf16 && w && b && (out_f32 || out_bf16) && rows > 0, "npvp_add_layernorm_rows: bad arguments");
+  NPVP_REQUIRE(out_f32 != x, "npvp_add_layernorm_rows: out_f32 must not alias x (x receives x + delta)");
+  layernorm_rows_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)delta_bf16, w, b, out_f32, (h16*)out_bf16, rows, relu, fp16);
+  NPVP_LAUNCH_CHECK("layernorm_rows_kernel<add>");
   return NPVP_OK;
 }
 

@@ -16,12 +16,17 @@ from __future__ import annotations
 
 import torch
 
+import os
+
 from . import _lib
 from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ATTN_SPATIAL, ATTN_TEMPORAL, PAD_ZERO
 from .workspace import Workspace
 
 C = 512
 TOK = 64
+# Deferred residual adds (default on): a residual branch's GEMM writes its bf16 output and the LayerNorm kernel that reads the
+# stream next performs x += delta, instead of a read-modify-write of the fp32 stream in the GEMM epilogue.
+_DEFER = os.environ.get("NPVP_B200_DEFER_RESIDUAL", "1") != "0"
 
 
 def _bf(t):
@@ -170,7 +175,31 @@ class PredictorEngine:
         op.gemm(f_bf, w.wqk, bias=w.bqk, out_bf16=qk)
         op.gemm(a_bf, w.wv, bias=w.bv, out_bf16=v)
         op.attention(qk[:, :C], qk[:, C:], v, o, mode, n, T, T, mask_last)
-        op.gemm(o, w.wo, bias=w.bo, res1=x, out_f32=x)
+        return self._residual_gemm(x, o, w.wo, w.bo, tag)
+
+    def _residual_gemm(self, x, a_bf, w, b, tag):
+        """x += a @ w^T + b.  Deferred mode returns the bf16 branch output for the next LayerNorm kernel to add."""
+        op = _lib.ops()
+        if not _DEFER:
+            op.gemm(a_bf, w, bias=b, res1=x, out_f32=x)
+            return None
+        d = self.ws.bf16(f"delta_{tag}", x.shape[0], C)
+        op.gemm(a_bf, w, bias=b, out_bf16=d)
+        return d
+
+    def _ln_rows(self, x, delta, ln, **kw):
+        op = _lib.ops()
+        if delta is None:
+            op.layernorm_rows(x, ln.w, ln.b, **kw)
+        else:
+            op.add_layernorm_rows(x, delta, ln.w, ln.b, **kw)
+
+    def _ln_fuse(self, x, delta, ln, qe, beta, gamma, out_ln, out_fused, n, T):
+        op = _lib.ops()
+        if delta is None:
+            op.ln_posfuse(x, ln.w, ln.b, qe, beta, gamma, out_ln, out_fused, n, T)
+        else:
+            op.add_ln_posfuse(x, delta, ln.w, ln.b, qe, beta, gamma, out_ln, out_fused, n, T)
 
     def _conv_ffn(self, x, a_bf, w: _ConvFFN, frames, tag, tail=None):
         """x += MlpDWBN(a)  (VidHRFormer.py:374-392).  ``tail`` = (ln, qe, beta, gamma, out_ln, out_fused, n, T): the
@@ -197,7 +226,7 @@ class PredictorEngine:
         op, ws = _lib.ops(), self.ws
         f1 = ws.bf16(f"f1_{tag}", x.shape[0], L.l1w.shape[0])
         op.gemm(a_bf, L.l1w, bias=L.l1b, act=ACT_GELU, out_bf16=f1)
-        op.gemm(f1, L.l2w, bias=L.l2b, res1=x, out_f32=x)
+        return self._residual_gemm(x, f1, L.l2w, L.l2b, tag)
 
     # ------------------------------------------------------------------------------------------
     # EVT_Former (VidHRFormer.py:25-52, 79-116)
@@ -209,17 +238,18 @@ class PredictorEngine:
         x = x_tokens
         a = ws.bf16("a_enc", M, C)
         f = ws.bf16("f_enc", M, C)
+        d = None                                                 # pending (deferred) residual of the previous branch
         for L in self.enc_layers:
-            op.ln_posfuse(x, L.n1.w, L.n1.b, None, beta, gamma, a, f, n, T)
-            self._self_attention(x, a, f, L.attn_s, ATTN_SPATIAL, n, T, False, "enc")
-            op.layernorm_rows(x, L.n2.w, L.n2.b, out_bf16=a)
+            self._ln_fuse(x, d, L.n1, None, beta, gamma, a, f, n, T)
+            d = self._self_attention(x, a, f, L.attn_s, ATTN_SPATIAL, n, T, False, "enc")
+            self._ln_rows(x, d, L.n2, out_bf16=a)
             self._conv_ffn(x, a, L.ffn_s, n * T, "enc", tail=(L.n3, None, beta, gamma, a, f, n, T))   # + LN3 / fuse
-            self._self_attention(x, a, f, L.attn_t, ATTN_TEMPORAL, n, T, True, "enc")    # mask quirk :100-102
-            op.layernorm_rows(x, L.n4.w, L.n4.b, out_bf16=a)
-            self._mlp_ffn(x, a, L, "enc")
+            d = self._self_attention(x, a, f, L.attn_t, ATTN_TEMPORAL, n, T, True, "enc")    # mask quirk :100-102
+            self._ln_rows(x, d, L.n4, out_bf16=a)
+            d = self._mlp_ffn(x, a, L, "enc")
         mem = ws.f32("mem_f32", M, C)
         mem_bf = ws.bf16("mem_bf16", M, C)
-        op.layernorm_rows(x, self.norm_enc.w, self.norm_enc.b, out_f32=mem, out_bf16=mem_bf)
+        self._ln_rows(x, d, self.norm_enc, out_f32=mem, out_bf16=mem_bf)
         return mem, mem_bf
 
     # ------------------------------------------------------------------------------------------
@@ -260,21 +290,21 @@ class PredictorEngine:
         for li, L in enumerate(self.dec_layers):
             if li == 0:      # later layers get this from the previous layer's last kernel
                 op.ln_posfuse(y, L.n1.w, L.n1.b, z, beta_p, gamma_p, a, f, n, Tp)
-            self._self_attention(y, a, f, L.attn_s, ATTN_SPATIAL, n, Tp, False, "dec")
-            op.layernorm_rows(y, L.n2.w, L.n2.b, out_bf16=a)
+            d = self._self_attention(y, a, f, L.attn_s, ATTN_SPATIAL, n, Tp, False, "dec")
+            self._ln_rows(y, d, L.n2, out_bf16=a)
             self._conv_ffn(y, a, L.ffn_s, n * Tp, "dec", tail=(L.n3, None, beta_p, gamma_p, a, f, n, Tp))   # + LN3 / fuse
-            self._self_attention(y, a, f, L.attn_t, ATTN_TEMPORAL, n, Tp, False, "dec")
-            op.layernorm_rows(y, L.n4.w, L.n4.b, out_bf16=a)
-            self._mlp_ffn(y, a, L, "dec")
+            d = self._self_attention(y, a, f, L.attn_t, ATTN_TEMPORAL, n, Tp, False, "dec")
+            self._ln_rows(y, d, L.n4, out_bf16=a)
+            d = self._mlp_ffn(y, a, L, "dec")
             # encoder-decoder attention over time
-            op.ln_posfuse(y, L.n5.w, L.n5.b, z, beta_p, gamma_p, None, f, n, Tp)
+            self._ln_fuse(y, d, L.n5, z, beta_p, gamma_p, None, f, n, Tp)
             X = L.attn_x
             op.gemm(f, X.wq, bias=X.bq, out_bf16=qx)
             op.gemm(keyf, X.wk, bias=X.bk, out_bf16=kx)
             op.gemm(mem_bf, X.wv, bias=X.bv, out_bf16=vx)
             op.attention(qx, kx, vx, ox, ATTN_TEMPORAL, n, Tp, To, False)
-            op.gemm(ox, X.wo, bias=X.bo, res1=y, out_f32=y)
-            op.layernorm_rows(y, L.n6.w, L.n6.b, out_bf16=a)
+            d = self._residual_gemm(y, ox, X.wo, X.bo, "dec")
+            self._ln_rows(y, d, L.n6, out_bf16=a)
             nxt = self.dec_layers[li + 1] if li + 1 < len(self.dec_layers) else None
             self._conv_ffn(y, a, L.ffn_x, n * Tp, "dec",          # + next layer's LN1 / (+ query_evt) / fuse
                            tail=None if nxt is None else (nxt.n1, z, beta_p, gamma_p, a, f, n, Tp))

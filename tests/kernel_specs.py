@@ -107,6 +107,14 @@ class SpecOps:
         g = 0.0 if gamma is None else gamma.reshape(1, T, 64, 512)
         out_fused.copy_((nrm * (1.0 + g) + beta.reshape(1, T, 64, 512)).reshape(out_fused.shape).to(torch.bfloat16))
 
+    def add_layernorm_rows(self, x, delta, w, b, out_f32=None, out_bf16=None, relu=False):
+        x.add_(delta.float().reshape(x.shape))
+        self.layernorm_rows(x, w, b, out_f32, out_bf16, relu)
+
+    def add_ln_posfuse(self, x, delta, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, n_clips, T):
+        x.add_(delta.float().reshape(x.shape))
+        self.ln_posfuse(x, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, n_clips, T)
+
     def layernorm_rows(self, x, w, b, out_f32=None, out_bf16=None, relu=False):
         self.launches += 1
         v = F.layer_norm(x.reshape(-1, 512).float(), (512,), w, b, EPS)

@@ -278,3 +278,25 @@ def test_conv_gemm_implicit(op, spec, dt, frames, H, C, N, KH, stride, pad, mode
             o.conv_gemm(x, w, frames, H, H, C, KH, KH, stride, pad, mode, Ho, Ho, phase, res1=rn(M, N, seed=4, dtype=dt), post_relu=True, out_f32=out, **kw)
         outs.append(out)
     close(outs[0], outs[1], 1e-2 if dt == torch.bfloat16 else 2e-3, "conv_gemm")
+
+
+def test_deferred_residual_layernorms(op, spec):
+    n, T = 2, 3
+    rows = n * T * 64
+    x1 = rn(rows, 512, seed=1, scale=2.0)
+    x2 = x1.clone()
+    delta = rn(rows, 512, seed=2, dtype=torch.bfloat16)
+    w, b = rn(512, seed=3) * 0.3 + 1, rn(512, seed=4) * 0.3
+    o1, o2 = torch.empty(rows, 512, device=DEV, dtype=torch.bfloat16), torch.empty(rows, 512, device=DEV, dtype=torch.bfloat16)
+    op.add_layernorm_rows(x1, delta, w, b, None, o1, False)
+    spec.add_layernorm_rows(x2, delta, w, b, None, o2, False)
+    assert torch.equal(x1, x2)                         # the fp32 stream update is exact
+    close(o1, o2, 1e-2, "add_layernorm_rows")
+    qe, beta = rn(n * 64, 512, seed=5), rn(T * 64, 512, seed=6)
+    a1, f1 = torch.empty_like(o1), torch.empty_like(o1)
+    a2, f2 = torch.empty_like(o1), torch.empty_like(o1)
+    op.add_ln_posfuse(x1, delta, w, b, qe, beta, None, a1, f1, n, T)
+    spec.add_ln_posfuse(x2, delta, w, b, qe, beta, None, a2, f2, n, T)
+    assert torch.equal(x1, x2)
+    close(a1, a2, 1e-2, "add_ln_posfuse ln")
+    close(f1, f2, 1e-2, "add_ln_posfuse fused")
