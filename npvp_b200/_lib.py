@@ -335,7 +335,7 @@ class Ops:
         _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(shift, torch.float32, "shift"); _chk16(out, "out")
         frames = x.numel() // (Cin * H * W)
         assert out.numel() == frames * H * W * Cout and w.shape == (49 * Cin, Cout)
-        per = max(1, 65535 // (Cout // 16))
+        per = max(1, 65535 // (Cout // 32))
         for f0 in range(0, frames, per):      # grid.z limit
             n = min(per, frames - f0)
             self._call("npvp_conv7x7_stem", x.data_ptr() + f0 * Cin * H * W * 4, w.data_ptr(), shift.data_ptr(),

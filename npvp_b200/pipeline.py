@@ -114,11 +114,23 @@ class NPVPInference(nn.Module):
             g = graphs[key] = _GraphedPredict(self, past_frames)
         return g(past_frames, eps)
 
-    def rollout(self, past_frames, num_future: int, eps_list: Optional[Sequence[torch.Tensor]] = None):
+    def rollout(self, past_frames, num_future: int, eps_list: Optional[Sequence[torch.Tensor]] = None,
+                out_host: Optional[torch.Tensor] = None):
         """Block-autoregressive VFP: predict len(tp_list) frames, feed the last To predictions back as context
-        (image space), repeat until ``num_future`` frames exist; the last block is truncated."""
+        (image space), repeat until ``num_future`` frames exist; the last block is truncated.
+
+        ``past_frames`` may be a (pinned) host tensor: it is uploaded asynchronously.  With ``out_host`` (a pinned host
+        tensor (N, num_future, C, H, W)) every block's frames are streamed to the host on a copy stream while the next block
+        computes, and the caller's stream waits for the last copy before the call returns control of ``out_host``."""
+        dev = next(self.parameters()).device
+        if not past_frames.is_cuda:
+            past_frames = past_frames.to(dev, non_blocking=True)
         To, Tp = past_frames.shape[1], int(self.tp_list.shape[0])
         assert To == int(self.to_list.shape[0])
+        copy_stream = None
+        if out_host is not None:
+            assert not out_host.is_cuda and out_host.shape[1] == num_future
+            copy_stream = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=dev))
         out, ctx, done, blk = None, past_frames, 0, 0
         while done < num_future:
             eps = None if eps_list is None else eps_list[blk]
@@ -127,12 +139,24 @@ class NPVPInference(nn.Module):
                 out = torch.empty((pred.shape[0], num_future) + tuple(pred.shape[2:]), dtype=pred.dtype, device=pred.device)
             take = min(Tp, num_future - done)
             out[:, done:done + take].copy_(pred[:, :take])
+            if copy_stream is not None:                      # D2H of this block overlaps the next block's kernels
+                ready = torch.cuda.Event()
+                ready.record()
+                copy_stream.wait_event(ready)
+                with torch.cuda.stream(copy_stream):
+                    # per-clip copies: each (take, C, H, W) slab is contiguous on both sides, so every copy is one plain
+                    # async memcpy (a strided (N, take, ...) slice would make torch stage through a temporary and synchronise)
+                    for i in range(out.shape[0]):
+                        out_host[i, done:done + take].copy_(out[i, done:done + take], non_blocking=True)
             done += take
             blk += 1
             if Tp >= To:
                 ctx = out[:, done - To:done] if take == Tp else pred[:, Tp - To:Tp]
             else:
                 ctx = torch.cat([ctx[:, Tp:], pred], dim=1)
+        if copy_stream is not None:
+            torch.cuda.current_stream().wait_stream(copy_stream)
+            out.record_stream(copy_stream)
         return out
 
     # -- pixel space (utils/dataset.py:860-886, utils/train_summary.py:244-245) ----------------------

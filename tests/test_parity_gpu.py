@@ -99,6 +99,16 @@ def test_rollout_block_autoregressive():
     assert torch.equal(out[:, :10], first)
     second = model.predict(first[:, 8:10], eps[1])
     assert torch.equal(out[:, 10:20], second)
+    # host-buffer API: pinned input, frames streamed to a pinned output while the next block computes; with CUDA graphs too
+    host_in, host_out = x.cpu().pin_memory(), torch.empty(2, 28, 3, 64, 64).pin_memory()
+    out2 = model.rollout(host_in, 28, eps, out_host=host_out)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out) and torch.equal(host_out, out.cpu())
+    model.use_cuda_graphs(True)
+    host_out.zero_()
+    out3 = model.rollout(host_in, 28, eps, out_host=host_out)
+    torch.cuda.synchronize()
+    assert torch.equal(out3, out) and torch.equal(host_out, out.cpu())
 
 
 def test_batch_invariance_and_determinism():
