@@ -73,7 +73,8 @@ int npvp_version(void);
 /* number of kernels launched through this library since the last reset (bench accounting) */
 int64_t npvp_launch_count(void);
 void npvp_reset_launch_count(void);
-/* library-wide switches: "gemm_2cta" = 1 routes N >= 256 GEMMs of the default back-end to the 2-CTA cluster kernel */
+/* library-wide switches: "gemm_2cta": 1 = N >= 256 GEMMs of the default back-end always use the 2-CTA cluster kernel,
+ * 0 = never, -1 (default) = when K >= 1024 (where the main loop dominates and the halved operand traffic pays) */
 int npvp_set_option(const char* name, int value);
 
 /* ---- dense contractions -------------------------------------------------------------------
@@ -121,12 +122,13 @@ int npvp_add_layernorm_rows(float* x, const void* delta_bf16, const float* w, co
 int npvp_add_ln_posfuse(float* x, const void* delta_bf16, const float* ln_w, const float* ln_b, const float* qe, const float* beta,
                         const float* gamma, void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T, void* stream);
 /* y += GELU(LayerNorm_(C,8,8)(h))  - MlpDWBN norm3 + act3 + the block's residual add
- * (VidHRFormer.py:388-389 with :91/:214/:243).  h fp32 [frames,64,512]; w,b fp32 [64,512] (hw-major). */
-int npvp_frame_ln_gelu_residual(const float* h, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,
+ * (VidHRFormer.py:388-389 with :91/:214/:243).  h [frames,64,512] fp32 (h_is_bf16 = 0) or bf16 (1: the fc2 GEMM's 16-bit
+ * output; h is normalised right here, so its rounding is harmless); w,b fp32 [64,512] (hw-major). */
+int npvp_frame_ln_gelu_residual(const void* h, int h_is_bf16, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,
                                 void* stream);
 /* The same, fused with the consumer that follows it in every block: after y is updated in registers the kernel also runs
  * npvp_ln_posfuse on the new y (VidHRFormer.py:91 -> :95-96, :214 -> :218-219, :243 -> next layer's :210-212). */
-int npvp_frame_ln_gelu_residual_posfuse(const float* h, const float* w_hwc, const float* b_hwc, float* y, const float* ln_w,
+int npvp_frame_ln_gelu_residual_posfuse(const void* h, int h_is_bf16, const float* w_hwc, const float* b_hwc, float* y, const float* ln_w,
                                         const float* ln_b, const float* qe, const float* beta, const float* gamma,
                                         void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T, void* stream);
 /* mean over time of the memory (Predictor.py:346): mem fp32 [n,T,64*512] -> evt fp32 [n,64*512]. */

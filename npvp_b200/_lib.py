@@ -41,8 +41,8 @@ SIGNATURES = {
     "npvp_add_layernorm_rows": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "npvp_add_ln_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_layernorm_rows": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
-    "npvp_frame_ln_gelu_residual": [_vp, _vp, _vp, _vp, _i64, _vp],
-    "npvp_frame_ln_gelu_residual_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "npvp_frame_ln_gelu_residual": [_vp, _i32, _vp, _vp, _vp, _i64, _vp],
+    "npvp_frame_ln_gelu_residual_posfuse": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_temporal_mean": [_vp, _vp, _i64, _i64, _i64, _vp],
     "npvp_ffn_frame_stats": [_vp, _vp, _i64, _i64, _vp],
     "npvp_ffn_dwconv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
@@ -126,7 +126,7 @@ class Ops:
         self.lib = lib or load_library()
         self.gemm_backend = {"auto": GEMM_AUTO, "tcgen05": GEMM_TCGEN05, "simt": GEMM_SIMT, "tcgen05_v1": GEMM_TCGEN05_V1,
                              "tcgen05_2cta": GEMM_TCGEN05_2CTA}[os.environ.get("NPVP_B200_GEMM", "auto")]
-        self.lib.npvp_set_option(b"gemm_2cta", int(os.environ.get("NPVP_B200_GEMM_2CTA", "0")))
+        self.lib.npvp_set_option(b"gemm_2cta", int(os.environ.get("NPVP_B200_GEMM_2CTA", "-1")))
 
     # -- plumbing -------------------------------------------------------------------------------
     def _stream(self):
@@ -245,20 +245,23 @@ class Ops:
                    int(relu), 0 if out_bf16 is None else _is_fp16(out_bf16), self._stream())
 
     def frame_ln_gelu_residual(self, h, w_hwc, b_hwc, y):
-        for t, n in ((h, "h"), (w_hwc, "w"), (b_hwc, "b"), (y, "y")):
+        for t, n in ((w_hwc, "w"), (b_hwc, "b"), (y, "y")):
             _chk(t, torch.float32, n)
+        assert h.is_cuda and h.is_contiguous() and h.dtype in (torch.float32, torch.bfloat16)
         frames = h.numel() // (64 * 512)
         assert y.numel() == h.numel() and w_hwc.numel() == 64 * 512
-        self._call("npvp_frame_ln_gelu_residual", h.data_ptr(), w_hwc.data_ptr(), b_hwc.data_ptr(), y.data_ptr(), frames,
-                   self._stream())
+        self._call("npvp_frame_ln_gelu_residual", h.data_ptr(), int(h.dtype == torch.bfloat16), w_hwc.data_ptr(), b_hwc.data_ptr(),
+                   y.data_ptr(), frames, self._stream())
 
     def frame_ln_gelu_residual_posfuse(self, h, w_hwc, b_hwc, y, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, n_clips, T):
-        for t, n in ((h, "h"), (w_hwc, "w"), (b_hwc, "b"), (y, "y"), (ln_w, "ln_w"), (ln_b, "ln_b"), (qe, "qe"), (beta, "beta"),
+        for t, n in ((w_hwc, "w"), (b_hwc, "b"), (y, "y"), (ln_w, "ln_w"), (ln_b, "ln_b"), (qe, "qe"), (beta, "beta"),
                      (gamma, "gamma")):
             _chk(t, torch.float32, n)
+        assert h.is_cuda and h.is_contiguous() and h.dtype in (torch.float32, torch.bfloat16)
         _chk(out_ln, torch.bfloat16, "out_ln"); _chk(out_fused, torch.bfloat16, "out_fused")
         assert h.numel() == n_clips * T * 64 * 512 and y.numel() == h.numel()
-        self._call("npvp_frame_ln_gelu_residual_posfuse", h.data_ptr(), w_hwc.data_ptr(), b_hwc.data_ptr(), y.data_ptr(), _ptr(ln_w),
+        self._call("npvp_frame_ln_gelu_residual_posfuse", h.data_ptr(), int(h.dtype == torch.bfloat16), w_hwc.data_ptr(), b_hwc.data_ptr(),
+                   y.data_ptr(), _ptr(ln_w),
                    _ptr(ln_b), _ptr(qe), _ptr(beta), _ptr(gamma), _ptr(out_ln), _ptr(out_fused), n_clips, T, self._stream())
 
     def temporal_mean(self, mem, evt, n_clips, T):

@@ -943,7 +943,7 @@ static int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw
 
 
 static int g_num_sms = 0;
-static int g_use_2cta = 0;      // npvp_set_option("gemm_2cta", 1): route N >= 256 GEMMs of the default path to the cluster kernel
+static int g_use_2cta = -1;     // npvp_set_option("gemm_2cta", v): 1 = always for N >= 256, 0 = never, -1 (default) = when K >= 1024
 
 template <int BN, int ACT, int RES, int OUT, int CONV>
 static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, int64_t M, int64_t N, int64_t K, const EpiParams& e,
@@ -1089,7 +1089,9 @@ extern "C" int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
       return launch_tcgen05_2cta(A, lda, W, ldw, M, N, K, e, st);
     }
     if (backend == NPVP_GEMM_TCGEN05 && N % 4 == 0 && res_ok) {       // persistent kernel; tile width never depends on M
-      if (N >= 256 && g_use_2cta) return launch_tcgen05_2cta(A, lda, W, ldw, M, N, K, e, st);
+      // 2-CTA (cta_group::2) tiles pay off once the main loop dominates the tile: measured 1150 vs 1011 TFLOP/s at K = 2048,
+      // 912 vs 1013 at K = 512 (M = 40960).  The choice depends on N and K only, never on M (batch invariance).
+      if (N >= 256 && (g_use_2cta == 1 || (g_use_2cta < 0 && K >= 1024))) return launch_tcgen05_2cta(A, lda, W, ldw, M, N, K, e, st);
       if (N >= 256) return launch_tcgen05_v2<256>(A, lda, W, ldw, M, N, K, e, st);
       if (N > 64) return launch_tcgen05_v2<128>(A, lda, W, ldw, M, N, K, e, st);
       return launch_tcgen05_v2<64>(A, lda, W, ldw, M, N, K, e, st);

@@ -25,6 +25,19 @@ __device__ __forceinline__ void frame_load(const float* __restrict__ x, FrameReg
   }
 }
 
+__device__ __forceinline__ void frame_load_bf16(const bf16* __restrict__ x, FrameRegs& r, int warp, int lane) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const uint2* row = reinterpret_cast<const uint2*>(x + (size_t)(warp * 4 + t) * kC);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint2 u = __ldg(row + j * 32 + lane);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      r.v[t][4 * j + 0] = a.x; r.v[t][4 * j + 1] = a.y; r.v[t][4 * j + 2] = b.x; r.v[t][4 * j + 3] = b.y;
+    }
+  }
+}
+
 __device__ __forceinline__ void frame_store_bf16(bf16* __restrict__ out, const FrameRegs& r, int warp, int lane) {
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
@@ -239,14 +252,15 @@ extern "C" int npvp_add_layernorm_rows(float* x, const void* delta_bf16, const f
 // ---------------------------------------------------------------------------------------------
 template <bool TAIL>
 __global__ void __launch_bounds__(512)
-frame_ln_gelu_residual_kernel(const float* __restrict__ h, const float* __restrict__ w_hwc, const float* __restrict__ b_hwc,
+frame_ln_gelu_residual_kernel(const void* __restrict__ h, int h_is_bf16, const float* __restrict__ w_hwc, const float* __restrict__ b_hwc,
                               float* __restrict__ y, int T, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                               const float* __restrict__ qe, const float* __restrict__ beta, const float* __restrict__ gamma,
                               bf16* __restrict__ out_ln, bf16* __restrict__ out_fused) {
   __shared__ float red[64];
   const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FrameRegs r;
-  frame_load(h + (size_t)f * kTok * kC, r, warp, lane);
+  if (h_is_bf16) frame_load_bf16((const bf16*)h + (size_t)f * kTok * kC, r, warp, lane);
+  else frame_load((const float*)h + (size_t)f * kTok * kC, r, warp, lane);
   float mean, rstd;
   frame_stats(r, red, mean, rstd);
 #pragma unroll
@@ -271,23 +285,23 @@ frame_ln_gelu_residual_kernel(const float* __restrict__ h, const float* __restri
   if (TAIL) posfuse_from_regs(r, red, f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, warp, lane);
 }
 
-extern "C" int npvp_frame_ln_gelu_residual(const float* h, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,
+extern "C" int npvp_frame_ln_gelu_residual(const void* h, int h_is_bf16, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,
                                            void* stream) {
   NPVP_REQUIRE(h && w_hwc && b_hwc && y && frames > 0, "npvp_frame_ln_gelu_residual: bad arguments");
-  frame_ln_gelu_residual_kernel<false><<<(unsigned)frames, 512, 0, (cudaStream_t)stream>>>(h, w_hwc, b_hwc, y, 1, nullptr, nullptr, nullptr,
+  frame_ln_gelu_residual_kernel<false><<<(unsigned)frames, 512, 0, (cudaStream_t)stream>>>(h, h_is_bf16, w_hwc, b_hwc, y, 1, nullptr, nullptr, nullptr,
                                                                                           nullptr, nullptr, nullptr, nullptr);
   NPVP_LAUNCH_CHECK("frame_ln_gelu_residual_kernel");
   return NPVP_OK;
 }
 
-extern "C" int npvp_frame_ln_gelu_residual_posfuse(const float* h, const float* w_hwc, const float* b_hwc, float* y, const float* ln_w,
+extern "C" int npvp_frame_ln_gelu_residual_posfuse(const void* h, int h_is_bf16, const float* w_hwc, const float* b_hwc, float* y, const float* ln_w,
                                                    const float* ln_b, const float* qe, const float* beta, const float* gamma,
                                                    void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T, void* stream) {
   NPVP_REQUIRE(h && w_hwc && b_hwc && y && n_clips > 0 && T > 0, "npvp_frame_ln_gelu_residual_posfuse: bad arguments");
   NPVP_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "npvp_frame_ln_gelu_residual_posfuse: ln_w/ln_b must both be set or both NULL");
   NPVP_REQUIRE((out_ln_bf16 || out_fused_bf16) && (!out_fused_bf16 || beta), "npvp_frame_ln_gelu_residual_posfuse: outputs / beta missing");
   frame_ln_gelu_residual_kernel<true><<<(unsigned)(n_clips * T), 512, 0, (cudaStream_t)stream>>>(
-      h, w_hwc, b_hwc, y, (int)T, ln_w, ln_b, qe, beta, gamma, (bf16*)out_ln_bf16, (bf16*)out_fused_bf16);
+      h, h_is_bf16, w_hwc, b_hwc, y, (int)T, ln_w, ln_b, qe, beta, gamma, (bf16*)out_ln_bf16, (bf16*)out_fused_bf16);
   NPVP_LAUNCH_CHECK("frame_ln_gelu_residual_kernel<posfuse>");
   return NPVP_OK;
 }

@@ -98,6 +98,13 @@ class Predictor(_EngineModule):
         if self.observed_coor is None or self.predict_coor is None:
             raise RuntimeError("Predictor built with rand_context=True has no coordinates yet: call "
                                "reset_pos_coor(to_list, tp_list) before forward()")
+        # with rand_context=True the coordinates are plain attributes (reference quirk vii): module.to(device) does not
+        # move them.  Move them once here so no host->device copy happens on the hot path (or inside a CUDA-graph capture).
+        dev = self.nrmlp.B.device
+        if self.observed_coor.device != dev or self.observed_coor.dtype != torch.float32:
+            self.observed_coor = self.observed_coor.to(dev, torch.float32)
+        if self.predict_coor.device != dev or self.predict_coor.dtype != torch.float32:
+            self.predict_coor = self.predict_coor.to(dev, torch.float32)
 
     def forward(self, observed_features, predict_features_gt=None):
         """observed_features: (N, To, C, H, W) fp32 CUDA -> predicted features (N, Tp, C, H, W)."""

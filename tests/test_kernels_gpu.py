@@ -119,6 +119,11 @@ def test_layernorm_rows_and_frame_ln(op, spec):
     op.frame_ln_gelu_residual(h, aw, ab, y1)
     spec.frame_ln_gelu_residual(h, aw, ab, y2)
     close(y1, y2, 1e-5, "frame_ln_gelu_residual")
+    hb = h.to(torch.bfloat16)
+    y1, y2 = rn(5 * 64, 512, seed=7), rn(5 * 64, 512, seed=7)
+    op.frame_ln_gelu_residual(hb, aw, ab, y1)
+    spec.frame_ln_gelu_residual(hb, aw, ab, y2)
+    close(y1, y2, 1e-5, "frame_ln_gelu_residual (bf16 h)")
     mem = rn(3 * 4 * 64, 512, seed=8)
     e1, e2 = torch.empty(3 * 64, 512, device=DEV), torch.empty(3 * 64, 512, device=DEV)
     op.temporal_mean(mem, e1, 3, 4)

@@ -1,0 +1,67 @@
+"""Throughput of every BASELINE.json configuration + the KITTI batch sweep (config 5), one GPU.
+usage: python tools/bench_configs.py [--cpu]   ->  markdown tables on stdout"""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+torch.set_grad_enabled(False)
+from npvp_b200.pipeline import build_from_config  # noqa: E402
+
+
+def gpu_fps(model, x, n_future, iters=5, rollout=False):
+    fn = (lambda: model.rollout(x, n_future)) if rollout else (lambda: model.predict(x))
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return x.shape[0] * n_future * iters / (e0.elapsed_time(e1) * 1e-3)
+
+
+def cpu_fps(preset, n, to, tp_n, rollout_frames=None):
+    from oracle import npvp_oracle as O
+    m = build_from_config(preset, device="cpu", seed=0)
+    c = m.cfg
+    oc = dict(n_downsampling=c.AE.n_downsampling, num_res_blocks=c.AE.num_res_blocks, out_layer=c.AE.out_layer, stochastic=c.Predictor.stochastic)
+    esd, psd, dsd = m.VPTR_Enc.state_dict(), m.predictor.state_dict(), m.VPTR_Dec.state_dict()
+    x = torch.rand(n, to, c.Dataset.img_channels, c.Dataset.img_size, c.Dataset.img_size)
+    f = lambda: O.npvp_predict_frames(esd, psd, dsd, x, oc, m.predictor.observed_coor, m.predictor.predict_coor)
+    f()
+    t0 = time.perf_counter()
+    f()
+    return n * tp_n / (time.perf_counter() - t0)
+
+
+def main():
+    do_cpu = "--cpu" in sys.argv
+    print("| config | clips | frames/s (B200, CUDA graphs) | CPU oracle frames/s |\n|---|---:|---:|---:|")
+    rows = [("SMMNIST_VFP_NPVP-D", 8, 10, False), ("SMMNIST_VFP_NPVP-D", 64, 10, False), ("KTH_Unified_NPVP-S", 8, 10, False), ("KTH_Unified_NPVP-S", 64, 10, False),
+            ("BAIR_VFP_NPVP-S", 64, 28, True), ("Cityscapes_VFP_NPVP-D", 64, 28, True), ("Cityscapes_VFP_NPVP-S", 64, 28, True)]
+    for preset, n, nf, roll in rows:
+        model = build_from_config(preset, device="cuda", seed=0).use_cuda_graphs(True)
+        c = model.cfg
+        x = torch.rand(n, c.Dataset.num_past_frames, c.Dataset.img_channels, c.Dataset.img_size, c.Dataset.img_size, device="cuda") * 2 - 1
+        fps = gpu_fps(model, x, nf, rollout=roll)
+        cpu = f"{cpu_fps(preset, min(n, 8), c.Dataset.num_past_frames, c.Dataset.num_future_frames):.1f}" if do_cpu and n == 8 else ""
+        print(f"| {preset} ({c.Dataset.num_past_frames}->{nf}{' block-AR' if roll else ''}) | {n} | {fps:,.0f} | {cpu} |", flush=True)
+        del model
+        torch.cuda.empty_cache()
+    print("\nKITTI VFP NPVP-S 4->5, 128x128 RGB, batch sweep (one B200):\n\n| clips | frames/s | ms / forward |\n|---:|---:|---:|")
+    model = build_from_config("KITTI_VFP_NPVP-S", device="cuda", seed=0).use_cuda_graphs(True)
+    for n in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512):
+        x = torch.rand(n, 4, 3, 128, 128, device="cuda") * 2 - 1
+        fps = gpu_fps(model, x, 5, iters=5 if n >= 64 else 20)
+        print(f"| {n} | {fps:,.0f} | {1e3 * n * 5 / fps:.2f} |", flush=True)
+    if do_cpu:
+        print(f"\nCPU oracle on this host ({os.cpu_count()} threads), KITTI 4->5: N=1 {cpu_fps('KITTI_VFP_NPVP-S', 1, 4, 5):.1f} frames/s, N=8 {cpu_fps('KITTI_VFP_NPVP-S', 8, 4, 5):.1f} frames/s")
+
+
+if __name__ == "__main__":
+    main()
