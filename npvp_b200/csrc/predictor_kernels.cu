@@ -432,23 +432,32 @@ extern "C" int npvp_ffn_dwconv(const void* h_bf16, const float* stats1, const fl
   return NPVP_OK;
 }
 
-// out = GELU(LN2(y)); block = (frame, 8-pixel group); thread handles 8 channels per pixel
+// out = GELU(LN2(y)); block = (frame, 16-pixel group); thread handles 8 channels per pixel.  The fp64 reduction of the
+// per-chunk partial sums runs on one thread and is broadcast through shared memory: done by every thread it was ~130
+// fp64 instructions each, 15% of the kernel's issue slots.
+constexpr int kNorm2Px = 16;
 __global__ void __launch_bounds__(256)
 ffn_norm2_kernel(const bf16* __restrict__ y, const float* __restrict__ partial2, int nchunk, const float* __restrict__ n2w,
                  const float* __restrict__ n2b, bf16* __restrict__ out, int Ch) {
+  __shared__ float s_stats[2];
   const int f = blockIdx.y;
-  double s = 0.0, q = 0.0;
-  for (int k = 0; k < nchunk; ++k) {
-    s += (double)__ldg(partial2 + ((size_t)f * nchunk + k) * 2);
-    q += (double)__ldg(partial2 + ((size_t)f * nchunk + k) * 2 + 1);
+  if (threadIdx.x == 0) {
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < nchunk; ++k) {
+      s += (double)__ldg(partial2 + ((size_t)f * nchunk + k) * 2);
+      q += (double)__ldg(partial2 + ((size_t)f * nchunk + k) * 2 + 1);
+    }
+    const double n = (double)kTok * (double)Ch;
+    const double mean_d = s / n;
+    s_stats[0] = (float)mean_d;
+    s_stats[1] = (float)(1.0 / sqrt(fmax(q / n - mean_d * mean_d, 0.0) + (double)kEps));
   }
-  const double n = (double)kTok * (double)Ch;
-  const double mean_d = s / n;
-  const float mean = (float)mean_d;
-  const float rstd = (float)(1.0 / sqrt(fmax(q / n - mean_d * mean_d, 0.0) + (double)kEps));
+  __syncthreads();
+  const float mean = s_stats[0], rstd = s_stats[1];
   const int vec_per_px = Ch / 8;
-  for (int i = threadIdx.x; i < 8 * vec_per_px; i += 256) {
-    const int p = blockIdx.x * 8 + i / vec_per_px, cv = i % vec_per_px;
+#pragma unroll 2
+  for (int i = threadIdx.x; i < kNorm2Px * vec_per_px; i += 256) {
+    const int p = blockIdx.x * kNorm2Px + i / vec_per_px, cv = i % vec_per_px;
     const size_t off = ((size_t)f * kTok + p) * Ch + (size_t)cv * 8;
     const size_t aoff = (size_t)p * Ch + (size_t)cv * 8;
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(y + off));
@@ -468,7 +477,7 @@ extern "C" int npvp_ffn_norm2(const void* y_bf16, const float* partial2, const f
                               int64_t frames, int64_t Ch, void* stream) {
   NPVP_REQUIRE(y_bf16 && partial2 && n2w && n2b && out_bf16, "npvp_ffn_norm2: null pointer");
   NPVP_REQUIRE(frames > 0 && frames <= 65535 && Ch % 256 == 0, "npvp_ffn_norm2: frames in (0,65535], Ch multiple of 256");
-  dim3 grid(8, (unsigned)frames);
+  dim3 grid(kTok / kNorm2Px, (unsigned)frames);
   ffn_norm2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y_bf16, partial2, (int)(Ch / 256), n2w, n2b, (bf16*)out_bf16, (int)Ch);
   NPVP_LAUNCH_CHECK("ffn_norm2_kernel");
   return NPVP_OK;
