@@ -182,7 +182,8 @@ int npvp_conv7x7_stem(const float* x, const float* w, const float* shift, void* 
                       int Cout, int H, int W, int fp16, void* stream);
 /* 7x7 head: reflect-pad 3, conv + bias + Tanh|Sigmoid (ResNetAutoEncoder.py:184-189).
  * x 16-bit [frames,H,W,Cin] (phase_major=1: stored [frames,H/2,W/2,4,Cin], the ConvT GEMM's native output), Cin 32 or 64;
- * w 16-bit, pre-packed as mma B fragments [49 taps][Cin/16][8 (cout, zero-padded)][16 (cin)]; bias fp32 [Cout];
+ * w 16-bit, pre-packed as mma.sync B fragments [Cin/32][14 k-steps = (ky, 16-channel half)][NT = ceil(7 Cout / 8)][32 lanes][4]
+ * of the matrix B[(ky,ci), n = kx*Cout + co] (see pack_head_weights in npvp_b200/_lib.py); Cout in [1,3]; bias fp32 [Cout];
  * out fp32 NCHW [frames,Cout,H,W]. */
 int npvp_conv7x7_head(const void* x_bf16, const void* w, const float* bias, float* out, int64_t frames, int Cin,
                       int Cout, int H, int W, int phase_major, int act, int fp16, void* stream);

@@ -345,10 +345,10 @@ class Ops:
                        out.data_ptr() + f0 * H * W * Cout * 2, n, Cin, Cout, H, W, _is_fp16(out), self._stream())
 
     def conv7x7_head(self, x, w, bias, out, Cin, Cout, H, W, phase_major, act):
-        """w: 16-bit weights packed by :func:`pack_head_weights` ([49, Cin/16, 8, 16])."""
+        """w: 16-bit weights packed by :func:`pack_head_weights` ([Cin/32, 14, NT, 32, 4])."""
         _chk16(x, "x"); _chk16(w, "w", like=x); _chk(bias, torch.float32, "bias"); _chk(out, torch.float32, "out")
         frames = x.numel() // (Cin * H * W)
-        assert out.numel() == frames * Cout * H * W and tuple(w.shape) == (49, Cin // 16, 8, 16)
+        assert out.numel() == frames * Cout * H * W and tuple(w.shape) == (Cin // 32, 14, head_n_tiles(Cout), 32, 4)
         for f0 in range(0, frames, 65535):
             n = min(65535, frames - f0)
             self._call("npvp_conv7x7_head", x.data_ptr() + f0 * Cin * H * W * 2, w.data_ptr(), bias.data_ptr(),
@@ -373,20 +373,41 @@ class Ops:
                    dv, _is_fp16(q), self._stream())
 
 
+def _head_frag_index(device) -> torch.Tensor:
+    """k indices held by thread-in-group ``tig`` of an m16n8k16 B fragment: b0 = (2t, 2t+1), b1 = (2t+8, 2t+9)."""
+    t = torch.arange(4, device=device)
+    return torch.stack([2 * t, 2 * t + 1, 2 * t + 8, 2 * t + 9], dim=1)
+
+
+def head_n_tiles(Cout: int) -> int:
+    return (7 * Cout + 7) // 8
+
+
 def pack_head_weights(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """[(ky,kx,ci), Cout] fp32 -> 16-bit mma.sync B fragments [49 taps, Cin/16, 8 (cout, zero padded), 16 (cin)]."""
+    """[(ky,kx,ci), Cout] fp32 -> 16-bit mma.sync B fragments [Cin/32 passes, 14 k-steps, NT n-tiles, 32 lanes, 4].
+
+    The head kernel computes Z[x', (kx,co)] = sum_{ky,ci} X[oy+ky, x', ci] W[ky,kx,ci,co]: GEMM column n = kx*Cout + co
+    (zero-padded to NT*8), k-step s = (ky, 16-channel half) within a 32-channel pass.  Lane (gid, tig) of n-tile j holds
+    B[k, n = 8j + gid] for k in (2tig, 2tig+1, 2tig+8, 2tig+9)."""
     K, Cout = w.shape
     Cin = K // 49
-    assert Cin % 16 == 0 and Cout <= 8
-    p = torch.zeros(49, Cin // 16, 8, 16, dtype=torch.float32, device=w.device)
-    p[:, :, :Cout, :] = w.reshape(49, Cin // 16, 16, Cout).permute(0, 1, 3, 2)
-    return p.to(dtype).contiguous()
+    assert Cin % 32 == 0 and 1 <= Cout <= 3
+    P, NT = Cin // 32, head_n_tiles(Cout)
+    full = torch.zeros(7, Cin, NT * 8, dtype=torch.float32, device=w.device)
+    full[:, :, :7 * Cout] = w.reshape(7, 7, Cin, Cout).permute(0, 2, 1, 3).reshape(7, Cin, 7 * Cout)
+    b5 = full.reshape(7, P, 2, 16, NT * 8).permute(1, 0, 2, 3, 4).reshape(P, 14, 16, NT, 8)
+    frag = b5[:, :, _head_frag_index(w.device), :, :]                       # [P, 14, tig, e, NT, gid]
+    return frag.permute(0, 1, 4, 5, 2, 3).reshape(P, 14, NT, 32, 4).to(dtype).contiguous()
 
 
 def unpack_head_weights(p: torch.Tensor, Cout: int) -> torch.Tensor:
     """Inverse of :func:`pack_head_weights` (used by the kernel specification)."""
-    taps, cb, _, _ = p.shape
-    return p.float()[:, :, :Cout, :].permute(0, 1, 3, 2).reshape(taps * cb * 16, Cout)
+    P, _, NT, _, _ = p.shape
+    frag = p.float().reshape(P, 14, NT, 8, 4, 4).permute(0, 1, 4, 5, 2, 3)  # [P, 14, tig, e, NT, gid]
+    b5 = torch.zeros(P, 14, 16, NT, 8, dtype=torch.float32, device=p.device)
+    b5[:, :, _head_frag_index(p.device), :, :] = frag
+    full = b5.reshape(P, 7, 2, 16, NT * 8).permute(1, 0, 2, 3, 4).reshape(7, P * 32, NT * 8)[:, :, :7 * Cout]
+    return full.reshape(7, P * 32, 7, Cout).permute(0, 2, 1, 3).reshape(49 * P * 32, Cout).contiguous()
 
 
 _OPS: Optional[Ops] = None

@@ -134,18 +134,26 @@ extern "C" int npvp_conv7x7_stem(const float* x, const float* w, const float* sh
 
 // ---------------------------------------------------------------------------------------------
 // head: 16-bit NHWC (or phase-major) features -> fp32 NCHW image, reflect-pad 3, + bias + tanh/sigmoid.
-// Cout is 1 or 3, so a 128-row UMMA tile would stream 3 KB of A per output pixel for almost no math; instead the
-// input tile (8 rows x 64 cols + halo, all channels) is staged ONCE in shared memory and every warp walks the 49 taps
-// with warp-level mma.sync.m16n8k16: A = 16 consecutive pixels x 16 channels straight out of the tile (ldmatrix.x4,
-// pixel stride padded by 16 B so the 8 row addresses hit distinct banks), B = the tap's weights (N padded to 8),
-// fp32 accumulators.  The first SIMT version was FMA-bound at 2.6 ms per launch (r01 profile).
+// Cout is 1 or 3, so a 128-row UMMA tile would stream 3 KB of A per output pixel for almost no math, and a per-tap
+// mma (N = Cout padded to 8) re-reads every A fragment 49 times from shared memory (the second version of this kernel:
+// ldmatrix-bound, 1.93 ms per 640 Cityscapes frames).  This version folds the horizontal taps into N and the vertical
+// taps into K:
+//     Z[x', (kx, co)] = sum_{ky, ci} X[oy + ky, x', ci] * W[ky, kx, ci, co]        one GEMM per output row,
+//                                                                                  M = staged pixels, N = 7 Cout (-> 8 NT),
+//                                                                                  K = 7 x 32 channels per pass
+//     out[oy, ox, co]  = bias[co] + sum_kx Z[ox + kx, (kx, co)]                     shift-sum through shared memory
+// so each A fragment (16 pixels x 16 channels, one ldmatrix.x4) feeds NT mma.sync.m16n8k16 and is read once per ky
+// instead of once per tap: 5.6x fewer ldmatrix and 1.9x fewer mma for Cout = 3.
+// Block = 8 x 64 output tile, 8 warps (one output row each); the input tile (14 rows x 70 pixels, 32 channels per pass,
+// 64-byte pixels with a 16-byte-chunk XOR swizzle so the 8 ldmatrix rows hit distinct banks) is staged with cp.async;
+// Cin = 64 takes two passes over the same buffers.  The per-warp Z scratch aliases the tile after the last pass.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* smem_row) {
-  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-__device__ __forceinline__ void mma_16816_ae(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int fp16) {
-  if (fp16) {
+template <bool FP16>
+__device__ __forceinline__ void mma_16816_head(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (FP16) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -155,86 +163,109 @@ __device__ __forceinline__ void mma_16816_ae(float (&c)[4], const uint32_t (&a)[
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
   }
 }
+__device__ __forceinline__ void head_cp_async_16(uint32_t smem_dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(src) : "memory");
+}
 
 constexpr int kHeadTY = 8, kHeadTX = 64;                       // output tile per block (8 warps: one output row each)
+constexpr int kHeadRows = kHeadTY + 6;                         // staged input rows
+constexpr int kHeadCols = kHeadTX + 6;                         // staged input pixels per row that feed valid outputs
+constexpr int kHeadGroups = (kHeadCols + 15) / 16;             // 16-pixel mma row groups per output row (5)
+constexpr int kHeadTW = kHeadGroups * 16;                      // smem row pitch in pixels (80; the last 10 are never staged)
+constexpr int kHeadTileBytes = kHeadRows * kHeadTW * 64;       // 32 channels x 2 B per pixel
 
-template <int CIN>
-__global__ void __launch_bounds__(256)
-conv7x7_head_kernel(const h16* __restrict__ x, const h16* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
-                    int Cout, int H, int W, int phase_major, int act, int fp16) {
-  constexpr int PS = CIN + 8;                                   // padded pixel stride (halves)
-  constexpr int TW = kHeadTX + 6, TH = kHeadTY + 6, CB = CIN / 16;
-  extern __shared__ __align__(16) uint8_t head_smem[];
-  h16* tile = reinterpret_cast<h16*>(head_smem);                // [TH][TW][PS]
-  h16* wb = tile + TH * TW * PS;                                // [49][CB][8][16]  B fragments: [n][k]
+template <int NT, bool FP16>
+__global__ void __launch_bounds__(256, 2)
+conv7x7_head_kernel(const h16* __restrict__ x, const uint2* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+                    int Cin, int Cout, int H, int W, int phase_major, int act) {
+  constexpr int SST = NT * 8 + 1;                               // scratch row stride (floats), odd: conflict-free shift-sum
+  static_assert(8 * kHeadTW * SST * 4 <= kHeadTileBytes, "Z scratch must fit in the tile it aliases");
+  extern __shared__ __align__(128) uint8_t head_smem[];
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(head_smem);
+  uint2* wb = reinterpret_cast<uint2*>(head_smem + kHeadTileBytes);    // [pass][14 k-steps][NT][32 lanes] B fragments
+  const uint32_t wb_s = tile_s + kHeadTileBytes;
+  const int passes = Cin / 32;
   const int f = blockIdx.z;
   const int tiles_x = (W + kHeadTX - 1) / kHeadTX;
   const int ty0 = (blockIdx.x / tiles_x) * kHeadTY, tx0 = (blockIdx.x % tiles_x) * kHeadTX;
-  // stage the input tile (16-byte vectors of 8 channels), reflect padding resolved here
-  constexpr int VPP = CIN / 8;
-  for (int i = threadIdx.x; i < TH * TW * VPP; i += 256) {
-    const int v = i % VPP, px = i / VPP;
-    const int r = px / TW, c = px % TW;
-    const int yy = reflect_idx(ty0 + r - 3, H), xx = reflect_idx(tx0 + c - 3, W);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + pixel_offset(f, yy, xx, H, W, phase_major) * CIN) + v);
-    *reinterpret_cast<uint4*>(tile + (size_t)px * PS + v * 8) = u;
-  }
-  // weights arrive pre-packed as 16-bit B fragments [tap][cb][n = 8][k = 16] (zero rows for n >= Cout): plain vector copy
-  for (int i = threadIdx.x; i < 49 * CB * 16; i += 256)
-    reinterpret_cast<uint4*>(wb)[i] = __ldg(reinterpret_cast<const uint4*>(w) + i);
-  __syncthreads();
   const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
-  const int lm_px = ((lane >> 3) & 1) * 8 + (lane & 7);        // ldmatrix.x4 row supplied by this lane: pixel within the group
-  const int lm_ch = (lane >> 4) * 8;                            //                                     channel half
-  float acc[4][4];
+
+  for (int i = threadIdx.x; i < passes * 14 * NT * 16; i += 256)          // 16-byte vectors of the packed weights
+    head_cp_async_16(wb_s + i * 16, reinterpret_cast<const uint4*>(w) + i);
+
+  // per-lane ldmatrix.x4 source: pixel lm_px of the group, 16-byte chunk (2 cb + lm_hi) XOR-swizzled by the pixel index
+  const int lm_px = ((lane >> 3) & 1) * 8 + (lane & 7), lm_hi = lane >> 4, lm_sw = (lm_px >> 1) & 3;
+  float acc[kHeadGroups][NT][4];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) { acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f; }
-#pragma unroll 1
-  for (int ky = 0; ky < 7; ++ky) {
-    const h16* trow = tile + (size_t)(wrp + ky) * TW * PS;
-#pragma unroll 1
-    for (int kx = 0; kx < 7; ++kx) {
+  for (int g = 0; g < kHeadGroups; ++g)
 #pragma unroll
-      for (int cb = 0; cb < CB; ++cb) {
-        const uint32_t* bp = reinterpret_cast<const uint32_t*>(wb + (((ky * 7 + kx) * CB + cb) * 8 + gid) * 16);
-        const uint32_t b0 = bp[tig], b1 = bp[4 + tig];
+    for (int j = 0; j < NT; ++j) { acc[g][j][0] = acc[g][j][1] = acc[g][j][2] = acc[g][j][3] = 0.f; }
+
+  for (int pass = 0; pass < passes; ++pass) {
+    if (pass) __syncthreads();                                  // every warp is done with the previous channel slice
+    for (int i = threadIdx.x; i < kHeadRows * kHeadCols; i += 256) {
+      const int r = i / kHeadCols, c = i % kHeadCols;
+      const int yy = min(reflect_idx(ty0 + r - 3, H), H - 1), xx = min(reflect_idx(tx0 + c - 3, W), W - 1);
+      const h16* src = x + pixel_offset(f, yy, xx, H, W, phase_major) * Cin + pass * 32;
+      const uint32_t dst = tile_s + (uint32_t)(r * kHeadTW + c) * 64;
+      const int sw = (c >> 1) & 3;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t a[4];
-          ldsm_x4(a, trow + (size_t)(g * 16 + lm_px + kx) * PS + cb * 16 + lm_ch);
-          mma_16816_ae(acc[g], a, b0, b1, fp16);
-        }
+      for (int v = 0; v < 4; ++v) head_cp_async_16(dst + ((v ^ sw) << 4), src + v * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const uint2* wp = wb + (size_t)pass * 14 * NT * 32 + lane;
+#pragma unroll
+    for (int s = 0; s < 14; ++s) {                              // k-step = (ky, 16-channel half)
+      const int ky = s >> 1, cb = s & 1;
+      uint2 b[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) b[j] = wp[(s * NT + j) * 32];
+      const uint32_t a_row = tile_s + (uint32_t)((wrp + ky) * kHeadTW + lm_px) * 64 + (uint32_t)(((cb * 2 + lm_hi) ^ lm_sw) << 4);
+#pragma unroll
+      for (int g = 0; g < kHeadGroups; ++g) {
+        uint32_t a[4];
+        ldsm_x4(a, a_row + g * 16 * 64);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) mma_16816_head<FP16>(acc[g][j], a, b[j].x, b[j].y);
       }
     }
   }
+  __syncthreads();                                              // the tile is dead: reuse it as per-warp Z scratch
+  float* S = reinterpret_cast<float*>(head_smem) + (size_t)wrp * kHeadTW * SST;
+#pragma unroll
+  for (int g = 0; g < kHeadGroups; ++g)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) S[(g * 16 + gid + (e >> 1) * 8) * SST + j * 8 + 2 * tig + (e & 1)] = acc[g][j][e];
+  __syncwarp();
   const int oy = ty0 + wrp;
-  if (oy < H) {
+  if (oy >= H) return;
+  for (int i = lane; i < kHeadTX * Cout; i += 32) {
+    const int co = i / kHeadTX, ox = i % kHeadTX;
+    if (tx0 + ox >= W) continue;
+    float v = __ldg(bias + co);
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int co = 2 * tig + (e & 1), ox = tx0 + g * 16 + gid + (e >> 1) * 8;
-        if (co < Cout && ox < W) {
-          float v = acc[g][e] + __ldg(bias + co);
-          v = (act == NPVP_ACT_TANH) ? tanhf(v) : (act == NPVP_ACT_SIGMOID ? 1.0f / (1.0f + expf(-v)) : v);
-          out[(((size_t)f * Cout + co) * H + oy) * W + ox] = v;
-        }
-      }
+    for (int kx = 0; kx < 7; ++kx) v += S[(ox + kx) * SST + kx * Cout + co];
+    v = (act == NPVP_ACT_TANH) ? tanhf(v) : (act == NPVP_ACT_SIGMOID ? 1.0f / (1.0f + expf(-v)) : v);
+    out[(((size_t)f * Cout + co) * H + oy) * W + tx0 + ox] = v;
   }
 }
 
-template <int CIN>
-static int launch_head(const void* x, const void* w, const float* bias, float* out, int64_t frames, int Cout, int H, int W,
-                       int phase_major, int act, int fp16, cudaStream_t st) {
-  constexpr int smem = ((kHeadTY + 6) * (kHeadTX + 6) * (CIN + 8) + 49 * (CIN / 16) * 128) * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(conv7x7_head_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+template <int NT, bool FP16>
+static int launch_head(const void* x, const void* w, const float* bias, float* out, int64_t frames, int Cin, int Cout, int H, int W,
+                       int phase_major, int act, cudaStream_t st) {
+  const int smem = kHeadTileBytes + (Cin / 32) * 14 * NT * 32 * 8;
+  static int attr_smem = 0;
+  if (attr_smem < smem) {
+    cudaError_t err = cudaFuncSetAttribute(conv7x7_head_kernel<NT, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) { npvp_set_error("conv7x7_head: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
-    attr_set = true;
+    attr_smem = smem;
   }
   dim3 grid((unsigned)(((H + kHeadTY - 1) / kHeadTY) * ((W + kHeadTX - 1) / kHeadTX)), 1, (unsigned)frames);
-  conv7x7_head_kernel<CIN><<<grid, 256, smem, st>>>((const h16*)x, (const h16*)w, bias, out, Cout, H, W, phase_major, act, fp16);
+  conv7x7_head_kernel<NT, FP16><<<grid, 256, smem, st>>>((const h16*)x, (const uint2*)w, bias, out, Cin, Cout, H, W, phase_major, act);
   NPVP_LAUNCH_CHECK("conv7x7_head_kernel");
   return NPVP_OK;
 }
@@ -243,12 +274,19 @@ extern "C" int npvp_conv7x7_head(const void* x_bf16, const void* w, const float*
                                  int Cout, int H, int W, int phase_major, int act, int fp16, void* stream) {
   NPVP_REQUIRE(x_bf16 && w && bias && out && frames > 0 && frames <= 65535, "npvp_conv7x7_head: bad arguments");
   NPVP_REQUIRE(H >= 4 && W >= 4 && (!phase_major || (H % 2 == 0 && W % 2 == 0)), "npvp_conv7x7_head: H/W >= 4, even H/W for phase-major input");
-  NPVP_REQUIRE(Cout >= 1 && Cout <= 8, "npvp_conv7x7_head: Cout must be in [1, 8] (got %d)", Cout);
+  NPVP_REQUIRE(Cout >= 1 && Cout <= 3, "npvp_conv7x7_head: Cout must be in [1, 3] (got %d)", Cout);
+  NPVP_REQUIRE(Cin == 32 || Cin == 64, "npvp_conv7x7_head: Cin must be 32 or 64 (got %d)", Cin);
   NPVP_REQUIRE((uintptr_t)w % 16 == 0 && (uintptr_t)x_bf16 % 16 == 0, "npvp_conv7x7_head: x / w must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (Cin == 32) return launch_head<32>(x_bf16, w, bias, out, frames, Cout, H, W, phase_major, act, fp16, st);
-  if (Cin == 64) return launch_head<64>(x_bf16, w, bias, out, frames, Cout, H, W, phase_major, act, fp16, st);
-  NPVP_REQUIRE(false, "npvp_conv7x7_head: Cin must be 32 or 64 (got %d)", Cin);
+  const int nt = (7 * Cout + 7) / 8;
+#define NPVP_HEAD_CASE(NTV)                                                                                                   \
+  if (nt == NTV)                                                                                                              \
+    return fp16 ? launch_head<NTV, true>(x_bf16, w, bias, out, frames, Cin, Cout, H, W, phase_major, act, st)                 \
+                : launch_head<NTV, false>(x_bf16, w, bias, out, frames, Cin, Cout, H, W, phase_major, act, st);
+  NPVP_HEAD_CASE(1)
+  NPVP_HEAD_CASE(2)
+  NPVP_HEAD_CASE(3)
+#undef NPVP_HEAD_CASE
   return NPVP_ERR_INVALID;
 }
 

@@ -216,7 +216,8 @@ def test_conv7x7_stem(op, spec, Cin, Cout, HW, dt):
 
 
 @pytest.mark.parametrize("dt", H16)
-@pytest.mark.parametrize("Cin,Cout,HW,phase,act", [(32, 3, 128, True, 3), (64, 1, 64, True, 4), (32, 3, 48, False, 3)])
+@pytest.mark.parametrize("Cin,Cout,HW,phase,act", [(32, 3, 128, True, 3), (64, 1, 64, True, 4), (32, 3, 48, False, 3), (64, 3, 64, True, 3),
+                                                  (32, 2, 36, False, 0), (64, 1, 76, False, 4)])
 def test_conv7x7_head(op, spec, Cin, Cout, HW, phase, act, dt):
     from npvp_b200._lib import pack_head_weights
     x = rn(2 * HW * HW, Cin, seed=1, dtype=dt)
