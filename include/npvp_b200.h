@@ -139,7 +139,7 @@ int npvp_temporal_mean(const float* mem, float* evt, int64_t n_clips, int64_t T,
 int npvp_ffn_frame_stats(const void* h_bf16, float* stats, int64_t frames, int64_t Ch, void* stream);
 /* step 2: y = dw3x3(GELU(LN1(h1))) + b; also per-(frame,chunk) partial (sum,sumsq) of y.
  * n1w/n1b fp32 [64,Ch] (hw-major elementwise affine), dw_w fp32 [9,Ch], dw_b fp32 [Ch];
- * y bf16 [frames,64,Ch]; partial fp32 [frames, Ch/256, 2]. */
+ * y bf16 [frames,64,Ch]; partial fp32 [frames, Ch/128, 2] (Ch a multiple of 128). */
 int npvp_ffn_dwconv(const void* h_bf16, const float* stats1, const float* n1w, const float* n1b,
                     const float* dw_w, const float* dw_b, void* y_bf16, float* partial2, int64_t frames,
                     int64_t Ch, void* stream);

@@ -281,7 +281,7 @@ class Ops:
         for t, n in ((stats1, "stats1"), (n1w, "n1w"), (n1b, "n1b"), (dw_w, "dw_w"), (dw_b, "dw_b"), (partial2, "partial2")):
             _chk(t, torch.float32, n)
         frames, Ch = stats1.shape[0], h.shape[-1]
-        assert partial2.shape == (frames, Ch // 256, 2) and dw_w.shape == (9, Ch) and n1w.shape == (64, Ch)
+        assert partial2.shape == (frames, Ch // FFN_CHUNK, 2) and dw_w.shape == (9, Ch) and n1w.shape == (64, Ch)
         self._call("npvp_ffn_dwconv", h.data_ptr(), stats1.data_ptr(), n1w.data_ptr(), n1b.data_ptr(), dw_w.data_ptr(),
                    dw_b.data_ptr(), y.data_ptr(), partial2.data_ptr(), frames, Ch, self._stream())
 
@@ -409,6 +409,8 @@ def unpack_head_weights(p: torch.Tensor, Cout: int) -> torch.Tensor:
     full = b5.reshape(P, 7, 2, 16, NT * 8).permute(1, 0, 2, 3, 4).reshape(7, P * 32, NT * 8)[:, :, :7 * Cout]
     return full.reshape(7, P * 32, 7, Cout).permute(0, 2, 1, 3).reshape(49 * P * 32, Cout).contiguous()
 
+
+FFN_CHUNK = 128        # channels per partial-statistics chunk of the conv-FFN middle (kFfnChunk in predictor_kernels.cu)
 
 _OPS: Optional[Ops] = None
 

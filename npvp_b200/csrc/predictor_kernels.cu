@@ -382,87 +382,116 @@ __device__ __forceinline__ float dw3x3_at(const float (&a)[64], const float (&w)
   return acc;
 }
 
-// one thread per channel: normalise + GELU the 8x8 map, depthwise conv, write bf16, per-block partial stats
-__global__ void __launch_bounds__(256)
+// One thread per channel: normalise + GELU the 8x8 map, depthwise conv, write bf16, per-block partial stats.
+// LayerNorm((Ch,8,8)) has a weight and a bias PER ELEMENT of the frame, i.e. 8 B of fp32 parameters for every 2 B activation;
+// read per frame from L2 they, not HBM, bounded the first version (146 us per 640 frames, 2.8x the HBM time).  Here a block
+// owns kFfnChunk channels, parks their 64 x 2 parameters in shared memory once (each thread only ever reads its own
+// column, so no barrier is needed) and walks over frames blockIdx.y, blockIdx.y + gridDim.y, ...
+constexpr int kFfnChunk = 128;
+__global__ void __launch_bounds__(kFfnChunk)
 ffn_dwconv_kernel(const bf16* __restrict__ h, const float* __restrict__ stats1, const float* __restrict__ n1w,
                   const float* __restrict__ n1b, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
-                  bf16* __restrict__ y, float* __restrict__ partial2, int Ch) {
+                  bf16* __restrict__ y, float* __restrict__ partial2, int Ch, int frames) {
+  extern __shared__ float2 ffn_wb[];                             // [64 px][kFfnChunk] (weight, bias)
   __shared__ float red[64];
-  const int f = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
-  const float mean = __ldg(stats1 + 2 * f), rstd = __ldg(stats1 + 2 * f + 1);
-  float a[64];
-  const bf16* src = h + (size_t)f * kTok * Ch + c;
-#pragma unroll
-  for (int p = 0; p < 64; ++p) {
-    const float v = __bfloat162float(src[(size_t)p * Ch]);
-    a[p] = gelu_erf((v - mean) * rstd * __ldg(n1w + (size_t)p * Ch + c) + __ldg(n1b + (size_t)p * Ch + c));
-  }
+  const int c = blockIdx.x * kFfnChunk + threadIdx.x;
+#pragma unroll 8
+  for (int p = 0; p < 64; ++p)
+    ffn_wb[p * kFfnChunk + threadIdx.x] = make_float2(__ldg(n1w + (size_t)p * Ch + c), __ldg(n1b + (size_t)p * Ch + c));
   float w[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) w[k] = __ldg(dw_w + (size_t)k * Ch + c);
   const float bias = __ldg(dw_b + c);
-  bf16* dst = y + (size_t)f * kTok * Ch + c;
-  float s = 0.f, q = 0.f;
+  for (int f = blockIdx.y; f < frames; f += gridDim.y) {
+    const float mean = __ldg(stats1 + 2 * f), rstd = __ldg(stats1 + 2 * f + 1);
+    float a[64];
+    const bf16* src = h + (size_t)f * kTok * Ch + c;
 #pragma unroll
-  for (int yy = 0; yy < 8; ++yy)
+    for (int p = 0; p < 64; ++p) a[p] = __bfloat162float(src[(size_t)p * Ch]);
 #pragma unroll
-    for (int xx = 0; xx < 8; ++xx) {
-      const float o = dw3x3_at(a, w, yy, xx) + bias;
-      const bf16 ob = __float2bfloat16(o);
-      dst[(size_t)(yy * 8 + xx) * Ch] = ob;
-      const float orr = __bfloat162float(ob);   // statistics of what the consumer will actually read
-      s += orr;
-      q = fmaf(orr, orr, q);
+    for (int p = 0; p < 64; ++p) {
+      const float2 wb = ffn_wb[p * kFfnChunk + threadIdx.x];
+      a[p] = gelu_erf((a[p] - mean) * rstd * wb.x + wb.y);
     }
-  block_sum2(s, q, red);
-  if (threadIdx.x == 0) {
-    float* p = partial2 + ((size_t)f * gridDim.x + blockIdx.x) * 2;
-    p[0] = s;
-    p[1] = q;
+    bf16* dst = y + (size_t)f * kTok * Ch + c;
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int yy = 0; yy < 8; ++yy)
+#pragma unroll
+      for (int xx = 0; xx < 8; ++xx) {
+        const float o = dw3x3_at(a, w, yy, xx) + bias;
+        const bf16 ob = __float2bfloat16(o);
+        dst[(size_t)(yy * 8 + xx) * Ch] = ob;
+        const float orr = __bfloat162float(ob);   // statistics of what the consumer will actually read
+        s += orr;
+        q = fmaf(orr, orr, q);
+      }
+    block_sum2(s, q, red);
+    if (threadIdx.x == 0) {
+      float* p = partial2 + ((size_t)f * gridDim.x + blockIdx.x) * 2;
+      p[0] = s;
+      p[1] = q;
+    }
   }
 }
 
 extern "C" int npvp_ffn_dwconv(const void* h_bf16, const float* stats1, const float* n1w, const float* n1b, const float* dw_w,
                                const float* dw_b, void* y_bf16, float* partial2, int64_t frames, int64_t Ch, void* stream) {
   NPVP_REQUIRE(h_bf16 && stats1 && n1w && n1b && dw_w && dw_b && y_bf16 && partial2, "npvp_ffn_dwconv: null pointer");
-  NPVP_REQUIRE(frames > 0 && frames <= 65535 && Ch % 256 == 0, "npvp_ffn_dwconv: frames in (0,65535], Ch multiple of 256");
-  dim3 grid((unsigned)(Ch / 256), (unsigned)frames);
-  ffn_dwconv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)h_bf16, stats1, n1w, n1b, dw_w, dw_b, (bf16*)y_bf16, partial2, (int)Ch);
+  NPVP_REQUIRE(frames > 0 && frames < (1ll << 31) && Ch % kFfnChunk == 0, "npvp_ffn_dwconv: frames > 0, Ch multiple of %d", kFfnChunk);
+  constexpr int smem = kTok * kFfnChunk * (int)sizeof(float2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(ffn_dwconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) { npvp_set_error("ffn_dwconv: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
+    attr_set = true;
+  }
+  // 3 resident blocks per SM (64 KB of parameters each): one wave of blocks, each striding over the frames
+  const int64_t chunks = Ch / kFfnChunk;
+  int64_t gy = (148 * 3) / chunks;
+  gy = gy < 1 ? 1 : (gy > frames ? frames : gy);
+  dim3 grid((unsigned)chunks, (unsigned)gy);
+  ffn_dwconv_kernel<<<grid, kFfnChunk, smem, (cudaStream_t)stream>>>((const bf16*)h_bf16, stats1, n1w, n1b, dw_w, dw_b, (bf16*)y_bf16,
+                                                                      partial2, (int)Ch, (int)frames);
   NPVP_LAUNCH_CHECK("ffn_dwconv_kernel");
   return NPVP_OK;
 }
 
-// out = GELU(LN2(y)); block = (frame, 16-pixel group); thread handles 8 channels per pixel.  The fp64 reduction of the
-// per-chunk partial sums runs on one thread and is broadcast through shared memory: done by every thread it was ~130
-// fp64 instructions each, 15% of the kernel's issue slots.
-constexpr int kNorm2Px = 16;
+// out = GELU(LN2(y)).  Same parameter-traffic argument as above: a thread owns 8 channels of one pixel, keeps their 16
+// LayerNorm parameters in registers and strides over frames blockIdx.y, blockIdx.y + gridDim.y, ...  The fp64 reduction of
+// the per-chunk partial sums (one frame per thread) runs once per block and is kept in shared memory.
+constexpr int kNorm2MaxFrames = 256;                             // frames per block (host sizes gridDim.y accordingly)
 __global__ void __launch_bounds__(256)
 ffn_norm2_kernel(const bf16* __restrict__ y, const float* __restrict__ partial2, int nchunk, const float* __restrict__ n2w,
-                 const float* __restrict__ n2b, bf16* __restrict__ out, int Ch) {
-  __shared__ float s_stats[2];
-  const int f = blockIdx.y;
-  if (threadIdx.x == 0) {
-    double s = 0.0, q = 0.0;
-    for (int k = 0; k < nchunk; ++k) {
-      s += (double)__ldg(partial2 + ((size_t)f * nchunk + k) * 2);
-      q += (double)__ldg(partial2 + ((size_t)f * nchunk + k) * 2 + 1);
+                 const float* __restrict__ n2b, bf16* __restrict__ out, int Ch, int frames) {
+  __shared__ float2 s_stats[kNorm2MaxFrames];
+  const int vec_per_px = Ch / 8, vblocks = (vec_per_px + 255) / 256;
+  const int p = blockIdx.x / vblocks, cv = (blockIdx.x % vblocks) * 256 + threadIdx.x;
+  {
+    const int f = blockIdx.y + threadIdx.x * gridDim.y;
+    if (f < frames) {
+      double s = 0.0, q = 0.0;
+      for (int k = 0; k < nchunk; ++k) {
+        s += (double)__ldg(partial2 + ((size_t)f * nchunk + k) * 2);
+        q += (double)__ldg(partial2 + ((size_t)f * nchunk + k) * 2 + 1);
+      }
+      const double n = (double)kTok * (double)Ch;
+      const double mean_d = s / n;
+      s_stats[threadIdx.x] = make_float2((float)mean_d, (float)(1.0 / sqrt(fmax(q / n - mean_d * mean_d, 0.0) + (double)kEps)));
     }
-    const double n = (double)kTok * (double)Ch;
-    const double mean_d = s / n;
-    s_stats[0] = (float)mean_d;
-    s_stats[1] = (float)(1.0 / sqrt(fmax(q / n - mean_d * mean_d, 0.0) + (double)kEps));
   }
   __syncthreads();
-  const float mean = s_stats[0], rstd = s_stats[1];
-  const int vec_per_px = Ch / 8;
-#pragma unroll 2
-  for (int i = threadIdx.x; i < kNorm2Px * vec_per_px; i += 256) {
-    const int p = blockIdx.x * kNorm2Px + i / vec_per_px, cv = i % vec_per_px;
+  if (cv >= vec_per_px) return;
+  const size_t aoff = (size_t)p * Ch + (size_t)cv * 8;
+  const float4 w0 = __ldg(reinterpret_cast<const float4*>(n2w + aoff)), w1 = __ldg(reinterpret_cast<const float4*>(n2w + aoff + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(n2b + aoff)), b1 = __ldg(reinterpret_cast<const float4*>(n2b + aoff + 4));
+  int k = 0;
+#pragma unroll 4
+  for (int f = blockIdx.y; f < frames; f += gridDim.y, ++k) {
+    const float2 st = s_stats[k];
+    const float mean = st.x, rstd = st.y;
     const size_t off = ((size_t)f * kTok + p) * Ch + (size_t)cv * 8;
-    const size_t aoff = (size_t)p * Ch + (size_t)cv * 8;
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(y + off));
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(n2w + aoff)), w1 = __ldg(reinterpret_cast<const float4*>(n2w + aoff + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(n2b + aoff)), b1 = __ldg(reinterpret_cast<const float4*>(n2b + aoff + 4));
     const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
     uint4 o;
     o.x = pack_bf16x2(gelu_erf((p0.x - mean) * rstd * w0.x + b0.x), gelu_erf((p0.y - mean) * rstd * w0.y + b0.y));
@@ -476,9 +505,16 @@ ffn_norm2_kernel(const bf16* __restrict__ y, const float* __restrict__ partial2,
 extern "C" int npvp_ffn_norm2(const void* y_bf16, const float* partial2, const float* n2w, const float* n2b, void* out_bf16,
                               int64_t frames, int64_t Ch, void* stream) {
   NPVP_REQUIRE(y_bf16 && partial2 && n2w && n2b && out_bf16, "npvp_ffn_norm2: null pointer");
-  NPVP_REQUIRE(frames > 0 && frames <= 65535 && Ch % 256 == 0, "npvp_ffn_norm2: frames in (0,65535], Ch multiple of 256");
-  dim3 grid(kTok / kNorm2Px, (unsigned)frames);
-  ffn_norm2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y_bf16, partial2, (int)(Ch / 256), n2w, n2b, (bf16*)out_bf16, (int)Ch);
+  NPVP_REQUIRE(frames > 0 && frames < (1ll << 31) && Ch % kFfnChunk == 0, "npvp_ffn_norm2: frames > 0, Ch multiple of %d", kFfnChunk);
+  const int64_t gx = kTok * ((Ch / 8 + 255) / 256);
+  int64_t gy = (148 * 8 + gx - 1) / gx;                          // one wave of 8 resident blocks per SM ...
+  const int64_t gy_min = (frames + kNorm2MaxFrames - 1) / kNorm2MaxFrames;   // ... unless a block would exceed its stats table
+  gy = gy < gy_min ? gy_min : gy;
+  gy = gy > frames ? frames : gy;
+  NPVP_REQUIRE(gy <= 65535, "npvp_ffn_norm2: too many frames per launch (%lld)", (long long)frames);
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  ffn_norm2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y_bf16, partial2, (int)(Ch / kFfnChunk), n2w, n2b, (bf16*)out_bf16,
+                                                          (int)Ch, (int)frames);
   NPVP_LAUNCH_CHECK("ffn_norm2_kernel");
   return NPVP_OK;
 }

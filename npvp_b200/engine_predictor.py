@@ -210,7 +210,7 @@ class PredictorEngine:
         y2 = ws.bf16(f"y2_{tag}", M, w.hid)
         h3 = ws.bf16(f"h3_{tag}", M, C)       # 16-bit is enough: h3 is re-normalised by LayerNorm((C,8,8)) immediately
         st1 = ws.f32(f"st1_{tag}", frames, 2)
-        pt2 = ws.f32(f"pt2_{tag}", frames, w.hid // 256, 2)
+        pt2 = ws.f32(f"pt2_{tag}", frames, w.hid // _lib.FFN_CHUNK, 2)
         op.gemm(a_bf, w.w1, bias=w.b1, out_bf16=h1)
         op.ffn_frame_stats(h1, st1)
         op.ffn_dwconv(h1, st1, w.n1w, w.n1b, w.dw_w, w.dw_b, y2, pt2)

@@ -12,6 +12,7 @@ from __future__ import annotations
 import math
 
 import torch
+from npvp_b200._lib import FFN_CHUNK
 import torch.nn.functional as F
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
@@ -161,7 +162,7 @@ class SpecOps:
         o = F.conv2d(img, wt, dw_b, padding=1, groups=Ch).permute(0, 2, 3, 1).reshape(frames, 64, Ch)
         ob = o.to(torch.bfloat16)
         y.copy_(ob.reshape(y.shape))
-        of = ob.float().reshape(frames, 64, Ch // 256, 256)
+        of = ob.float().reshape(frames, 64, Ch // FFN_CHUNK, FFN_CHUNK)
         partial2[:, :, 0] = of.sum(dim=(1, 3))
         partial2[:, :, 1] = (of * of).sum(dim=(1, 3))
 

@@ -1,6 +1,7 @@
 """GPU: every C-ABI kernel against its torch specification (tests/kernel_specs.py) on seeded inputs."""
 import pytest
 import torch
+from npvp_b200._lib import FFN_CHUNK
 
 from kernel_specs import SpecOps
 
@@ -141,7 +142,7 @@ def test_conv_ffn_middle(op, spec):
     for o in (op, spec):
         st = torch.empty(frames, 2, device=DEV)
         y = torch.empty_like(h)
-        pt = torch.empty(frames, Ch // 256, 2, device=DEV)
+        pt = torch.empty(frames, Ch // FFN_CHUNK, 2, device=DEV)
         g = torch.empty_like(h)
         o.ffn_frame_stats(h, st)
         o.ffn_dwconv(h, st, n1w, n1b, dw_w, dw_b, y, pt)
