@@ -9,14 +9,36 @@ constexpr int kC = 512;       // embed dim
 constexpr int kTok = 64;      // tokens per frame (8x8)
 constexpr float kEps = 1e-5f;
 
-// thread layout used by the per-frame kernels: 512 threads = 16 warps, warp w owns tokens 4w..4w+3,
-// lane l owns channels {128*j + 4*l + i}: one float4 per j => fully coalesced 512-byte warp accesses.
-struct FrameRegs { float v[4][16]; };
+// Per-frame kernels (statistics over a whole 64 x 512 frame).  The first version held a frame in the registers of ONE
+// 512-thread block (64 values per thread, 110-128 registers): one block per SM, so the load -> reduce -> compute -> store
+// chain of a frame never overlapped with anything (24% warps active, 3.5 TB/s, r01 ncu).  A frame is now owned by a
+// CLUSTER of kFrameCL blocks of 256 threads: block `rank` holds tokens 16 rank .. 16 rank + 15 (32 values per thread), the
+// whole-frame mean / variance is merged across the cluster through distributed shared memory, and four such blocks of
+// different frames share an SM.
+// Thread layout: warp w of block `rank` owns tokens tok0 = 16 rank + 2 w and tok0 + 1; lane l owns channels
+// {128 j + 4 l + i}: one float4 per j => fully coalesced 512-byte warp accesses.
+constexpr int kFrameCL = 4;                                   // blocks per frame (cluster size)
+constexpr int kTPW = 2;                                       // tokens per warp
+constexpr int kFrameThreads = kTok / kFrameCL / kTPW * 32;    // 256
+struct FrameRegs { float v[kTPW][16]; };
 
-__device__ __forceinline__ void frame_load(const float* __restrict__ x, FrameRegs& r, int warp, int lane) {
+__device__ __forceinline__ uint32_t frame_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void frame_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void frame_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float2 ld_cluster_f2(const float2* local, uint32_t rank) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(local);
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
+  return v;
+}
+
+// x: first token of this warp (row pointer arithmetic is done by the callers through tok0)
+__device__ __forceinline__ void frame_load(const float* __restrict__ x, FrameRegs& r, int tok0, int lane) {
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const float4* row = reinterpret_cast<const float4*>(x + (size_t)(warp * 4 + t) * kC);
+  for (int t = 0; t < kTPW; ++t) {
+    const float4* row = reinterpret_cast<const float4*>(x + (size_t)(tok0 + t) * kC);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float4 q = __ldg(row + j * 32 + lane);
@@ -25,10 +47,10 @@ __device__ __forceinline__ void frame_load(const float* __restrict__ x, FrameReg
   }
 }
 
-__device__ __forceinline__ void frame_load_bf16(const bf16* __restrict__ x, FrameRegs& r, int warp, int lane) {
+__device__ __forceinline__ void frame_load_bf16(const bf16* __restrict__ x, FrameRegs& r, int tok0, int lane) {
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const uint2* row = reinterpret_cast<const uint2*>(x + (size_t)(warp * 4 + t) * kC);
+  for (int t = 0; t < kTPW; ++t) {
+    const uint2* row = reinterpret_cast<const uint2*>(x + (size_t)(tok0 + t) * kC);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint2 u = __ldg(row + j * 32 + lane);
@@ -38,10 +60,10 @@ __device__ __forceinline__ void frame_load_bf16(const bf16* __restrict__ x, Fram
   }
 }
 
-__device__ __forceinline__ void frame_store_bf16(bf16* __restrict__ out, const FrameRegs& r, int warp, int lane) {
+__device__ __forceinline__ void frame_store_bf16(bf16* __restrict__ out, const FrameRegs& r, int tok0, int lane) {
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    uint2* row = reinterpret_cast<uint2*>(out + (size_t)(warp * 4 + t) * kC);
+  for (int t = 0; t < kTPW; ++t) {
+    uint2* row = reinterpret_cast<uint2*>(out + (size_t)(tok0 + t) * kC);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       row[j * 32 + lane] = make_uint2(pack_bf16x2(r.v[t][4 * j], r.v[t][4 * j + 1]), pack_bf16x2(r.v[t][4 * j + 2], r.v[t][4 * j + 3]));
@@ -67,33 +89,51 @@ __device__ __forceinline__ void token_layernorm(float (&v)[16], const float4 (&w
   }
 }
 
-// two-pass mean / rstd over the whole frame held in registers by 512 threads
-__device__ __forceinline__ void frame_stats(const FrameRegs& r, float* red, float& mean, float& rstd) {
+// Mean / rstd over the whole frame.  Each block reduces its quarter with a two-pass (mean, centred sum of squares),
+// publishes (mean_k, M2_k) in `slot` of its own shared memory, and after one cluster barrier every thread merges the four
+// quarters (equal counts: M2 = sum M2_k + n_k sum (mean_k - mean)^2).  A slot is written once per kernel, so the only
+// other cluster-wide ordering needed is "nobody exits while its slot may still be read": callers arrive after their last
+// frame_stats and wait before returning (frame_cluster_arrive / frame_cluster_wait).
+__device__ __forceinline__ void frame_stats(const FrameRegs& r, float* red, float2* slot, float& mean, float& rstd) {
+  constexpr float inv_nk = 1.0f / (kTok / kFrameCL * kC);
   float s = 0.f, dummy = 0.f;
 #pragma unroll
-  for (int t = 0; t < 4; ++t)
+  for (int t = 0; t < kTPW; ++t)
 #pragma unroll
     for (int i = 0; i < 16; ++i) s += r.v[t][i];
   block_sum2(s, dummy, red);
-  mean = s * (1.0f / (kTok * kC));
+  const float mk = s * inv_nk;
   float q = 0.f;
   dummy = 0.f;
 #pragma unroll
-  for (int t = 0; t < 4; ++t)
+  for (int t = 0; t < kTPW; ++t)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { const float d = r.v[t][i] - mean; q = fmaf(d, d, q); }
+    for (int i = 0; i < 16; ++i) { const float d = r.v[t][i] - mk; q = fmaf(d, d, q); }
   block_sum2(q, dummy, red);
-  rstd = rsqrtf(q * (1.0f / (kTok * kC)) + kEps);
+  if (threadIdx.x == 0) *slot = make_float2(mk, q);
+  frame_cluster_arrive();
+  frame_cluster_wait();
+  float2 part[kFrameCL];
+#pragma unroll
+  for (int k = 0; k < kFrameCL; ++k) part[k] = ld_cluster_f2(slot, k);
+  float m = 0.f;
+#pragma unroll
+  for (int k = 0; k < kFrameCL; ++k) m += part[k].x;
+  mean = m * (1.0f / kFrameCL);
+  float m2 = 0.f, dm = 0.f;
+#pragma unroll
+  for (int k = 0; k < kFrameCL; ++k) { m2 += part[k].y; const float d = part[k].x - mean; dm = fmaf(d, d, dm); }
+  rstd = rsqrtf(m2 * (1.0f / (kTok * kC)) + dm * (1.0f / kFrameCL) + kEps);
 }
 
 // ---------------------------------------------------------------------------------------------
 // a = LN(x); u = a + qe; fused = GN1(u) * (1 + gamma) + beta
 // ---------------------------------------------------------------------------------------------
-// r holds the frame's fp32 values; applies the optional token LayerNorm, writes `a`, then the positional fuse.
-__device__ __forceinline__ void posfuse_from_regs(FrameRegs& r, float* red, int f, int T, const float* __restrict__ ln_w,
+// r holds this block's quarter of the frame in fp32; applies the optional token LayerNorm, writes `a`, then the positional fuse.
+__device__ __forceinline__ void posfuse_from_regs(FrameRegs& r, float* red, float2* slot, int f, int T, const float* __restrict__ ln_w,
                                                   const float* __restrict__ ln_b, const float* __restrict__ qe,
                                                   const float* __restrict__ beta, const float* __restrict__ gamma,
-                                                  bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int warp, int lane) {
+                                                  bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int tok0, int lane) {
   const int n = f / T, t_idx = f % T;
   if (ln_w) {
     float4 w[4], b[4];
@@ -103,14 +143,14 @@ __device__ __forceinline__ void posfuse_from_regs(FrameRegs& r, float* red, int 
       b[j] = __ldg(reinterpret_cast<const float4*>(ln_b) + j * 32 + lane);
     }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) token_layernorm(r.v[t], w, b);
+    for (int t = 0; t < kTPW; ++t) token_layernorm(r.v[t], w, b);
   }
-  if (out_ln) frame_store_bf16(out_ln + (size_t)f * kTok * kC, r, warp, lane);
+  if (out_ln) frame_store_bf16(out_ln + (size_t)f * kTok * kC, r, tok0, lane);
   if (!out_fused) return;
   if (qe) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float4* row = reinterpret_cast<const float4*>(qe + ((size_t)n * kTok + warp * 4 + t) * kC);
+    for (int t = 0; t < kTPW; ++t) {
+      const float4* row = reinterpret_cast<const float4*>(qe + ((size_t)n * kTok + tok0 + t) * kC);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 q = __ldg(row + j * 32 + lane);
@@ -119,10 +159,10 @@ __device__ __forceinline__ void posfuse_from_regs(FrameRegs& r, float* red, int 
     }
   }
   float mean, rstd;
-  frame_stats(r, red, mean, rstd);
+  frame_stats(r, red, slot, mean, rstd);
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const size_t off = ((size_t)t_idx * kTok + warp * 4 + t) * kC;
+  for (int t = 0; t < kTPW; ++t) {
+    const size_t off = ((size_t)t_idx * kTok + tok0 + t) * kC;
     const float4* brow = reinterpret_cast<const float4*>(beta + off);
     const float4* grow = gamma ? reinterpret_cast<const float4*>(gamma + off) : nullptr;
 #pragma unroll
@@ -136,15 +176,15 @@ __device__ __forceinline__ void posfuse_from_regs(FrameRegs& r, float* red, int 
       r.v[t][4 * j + 3] = (r.v[t][4 * j + 3] - mean) * rstd * (1.0f + ga.w) + be.w;
     }
   }
-  frame_store_bf16(out_fused + (size_t)f * kTok * kC, r, warp, lane);
+  frame_store_bf16(out_fused + (size_t)f * kTok * kC, r, tok0, lane);
 }
 
-// x += delta (a residual branch's output left in bf16 by its GEMM), written back in fp32, for the frame held in registers
-__device__ __forceinline__ void frame_add_delta(float* __restrict__ x, const bf16* __restrict__ delta, FrameRegs& r, int warp, int lane) {
+// x += delta (a residual branch's output left in bf16 by its GEMM), written back in fp32, for the quarter held in registers
+__device__ __forceinline__ void frame_add_delta(float* __restrict__ x, const bf16* __restrict__ delta, FrameRegs& r, int tok0, int lane) {
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const uint2* drow = reinterpret_cast<const uint2*>(delta + (size_t)(warp * 4 + t) * kC);
-    float4* xrow = reinterpret_cast<float4*>(x + (size_t)(warp * 4 + t) * kC);
+  for (int t = 0; t < kTPW; ++t) {
+    const uint2* drow = reinterpret_cast<const uint2*>(delta + (size_t)(tok0 + t) * kC);
+    float4* xrow = reinterpret_cast<float4*>(x + (size_t)(tok0 + t) * kC);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint2 u = __ldg(drow + j * 32 + lane);
@@ -155,16 +195,20 @@ __device__ __forceinline__ void frame_add_delta(float* __restrict__ x, const bf1
   }
 }
 
-__global__ void __launch_bounds__(512)
+__global__ void __cluster_dims__(kFrameCL, 1, 1) __launch_bounds__(kFrameThreads, 4)
 ln_posfuse_kernel(float* __restrict__ x, const bf16* __restrict__ delta, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                   const float* __restrict__ qe, const float* __restrict__ beta, const float* __restrict__ gamma,
                   bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int T) {
   __shared__ float red[64];
-  const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float2 slots[2];
+  const int f = blockIdx.x / kFrameCL, lane = threadIdx.x & 31;
+  const int tok0 = (int)frame_cluster_rank() * (kTok / kFrameCL) + (threadIdx.x >> 5) * kTPW;
   FrameRegs r;
-  frame_load(x + (size_t)f * kTok * kC, r, warp, lane);
-  if (delta) frame_add_delta(x + (size_t)f * kTok * kC, delta + (size_t)f * kTok * kC, r, warp, lane);
-  posfuse_from_regs(r, red, f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, warp, lane);
+  frame_load(x + (size_t)f * kTok * kC, r, tok0, lane);
+  if (delta) frame_add_delta(x + (size_t)f * kTok * kC, delta + (size_t)f * kTok * kC, r, tok0, lane);
+  posfuse_from_regs(r, red, &slots[1], f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, tok0, lane);
+  frame_cluster_arrive();                                     // keep `slots` alive until every block of the frame has read them
+  frame_cluster_wait();
 }
 
 extern "C" int npvp_ln_posfuse(const float* x, const float* ln_w, const float* ln_b, const float* qe, const float* beta,
@@ -174,7 +218,7 @@ extern "C" int npvp_ln_posfuse(const float* x, const float* ln_w, const float* l
   NPVP_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "npvp_ln_posfuse: ln_w/ln_b must both be set or both NULL");
   NPVP_REQUIRE(!out_fused_bf16 || beta, "npvp_ln_posfuse: beta required for the fused output");
   NPVP_REQUIRE(n_clips > 0 && T > 0, "npvp_ln_posfuse: empty input");
-  ln_posfuse_kernel<<<(unsigned)(n_clips * T), 512, 0, (cudaStream_t)stream>>>(const_cast<float*>(x), nullptr, ln_w, ln_b, qe, beta, gamma,
+  ln_posfuse_kernel<<<(unsigned)(n_clips * T * kFrameCL), kFrameThreads, 0, (cudaStream_t)stream>>>(const_cast<float*>(x), nullptr, ln_w, ln_b, qe, beta, gamma,
                                                                               (bf16*)out_ln_bf16, (bf16*)out_fused_bf16, (int)T);
   NPVP_LAUNCH_CHECK("ln_posfuse_kernel");
   return NPVP_OK;
@@ -187,7 +231,7 @@ extern "C" int npvp_add_ln_posfuse(float* x, const void* delta_bf16, const float
   NPVP_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "npvp_add_ln_posfuse: ln_w/ln_b must both be set or both NULL");
   NPVP_REQUIRE(!out_fused_bf16 || beta, "npvp_add_ln_posfuse: beta required for the fused output");
   NPVP_REQUIRE(n_clips > 0 && T > 0, "npvp_add_ln_posfuse: empty input");
-  ln_posfuse_kernel<<<(unsigned)(n_clips * T), 512, 0, (cudaStream_t)stream>>>(x, (const bf16*)delta_bf16, ln_w, ln_b, qe, beta, gamma,
+  ln_posfuse_kernel<<<(unsigned)(n_clips * T * kFrameCL), kFrameThreads, 0, (cudaStream_t)stream>>>(x, (const bf16*)delta_bf16, ln_w, ln_b, qe, beta, gamma,
                                                                               (bf16*)out_ln_bf16, (bf16*)out_fused_bf16, (int)T);
   NPVP_LAUNCH_CHECK("ln_posfuse_kernel<add>");
   return NPVP_OK;
@@ -251,21 +295,23 @@ extern "C" int npvp_add_layernorm_rows(float* x, const void* delta_bf16, const f
 // y += GELU(LayerNorm_(C,8,8)(h) * w + b)
 // ---------------------------------------------------------------------------------------------
 template <bool TAIL>
-__global__ void __launch_bounds__(512)
+__global__ void __cluster_dims__(kFrameCL, 1, 1) __launch_bounds__(kFrameThreads, 4)
 frame_ln_gelu_residual_kernel(const void* __restrict__ h, int h_is_bf16, const float* __restrict__ w_hwc, const float* __restrict__ b_hwc,
                               float* __restrict__ y, int T, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                               const float* __restrict__ qe, const float* __restrict__ beta, const float* __restrict__ gamma,
                               bf16* __restrict__ out_ln, bf16* __restrict__ out_fused) {
   __shared__ float red[64];
-  const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float2 slots[2];
+  const int f = blockIdx.x / kFrameCL, lane = threadIdx.x & 31;
+  const int tok0 = (int)frame_cluster_rank() * (kTok / kFrameCL) + (threadIdx.x >> 5) * kTPW;
   FrameRegs r;
-  if (h_is_bf16) frame_load_bf16((const bf16*)h + (size_t)f * kTok * kC, r, warp, lane);
-  else frame_load((const float*)h + (size_t)f * kTok * kC, r, warp, lane);
+  if (h_is_bf16) frame_load_bf16((const bf16*)h + (size_t)f * kTok * kC, r, tok0, lane);
+  else frame_load((const float*)h + (size_t)f * kTok * kC, r, tok0, lane);
   float mean, rstd;
-  frame_stats(r, red, mean, rstd);
+  frame_stats(r, red, &slots[0], mean, rstd);
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const size_t tok = warp * 4 + t;
+  for (int t = 0; t < kTPW; ++t) {
+    const size_t tok = tok0 + t;
     const float4* wrow = reinterpret_cast<const float4*>(w_hwc + tok * kC);
     const float4* brow = reinterpret_cast<const float4*>(b_hwc + tok * kC);
     float4* yrow = reinterpret_cast<float4*>(y + ((size_t)f * kTok + tok) * kC);
@@ -282,13 +328,15 @@ frame_ln_gelu_residual_kernel(const void* __restrict__ h, int h_is_bf16, const f
     }
   }
   // fused consumer: the next op of every block is LayerNorm + positional fuse of the stream just updated
-  if (TAIL) posfuse_from_regs(r, red, f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, warp, lane);
+  if (TAIL) posfuse_from_regs(r, red, &slots[1], f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, tok0, lane);
+  frame_cluster_arrive();                                     // keep `slots` alive until every block of the frame has read them
+  frame_cluster_wait();
 }
 
 extern "C" int npvp_frame_ln_gelu_residual(const void* h, int h_is_bf16, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,
                                            void* stream) {
   NPVP_REQUIRE(h && w_hwc && b_hwc && y && frames > 0, "npvp_frame_ln_gelu_residual: bad arguments");
-  frame_ln_gelu_residual_kernel<false><<<(unsigned)frames, 512, 0, (cudaStream_t)stream>>>(h, h_is_bf16, w_hwc, b_hwc, y, 1, nullptr, nullptr, nullptr,
+  frame_ln_gelu_residual_kernel<false><<<(unsigned)(frames * kFrameCL), kFrameThreads, 0, (cudaStream_t)stream>>>(h, h_is_bf16, w_hwc, b_hwc, y, 1, nullptr, nullptr, nullptr,
                                                                                           nullptr, nullptr, nullptr, nullptr);
   NPVP_LAUNCH_CHECK("frame_ln_gelu_residual_kernel");
   return NPVP_OK;
@@ -300,7 +348,7 @@ extern "C" int npvp_frame_ln_gelu_residual_posfuse(const void* h, int h_is_bf16,
   NPVP_REQUIRE(h && w_hwc && b_hwc && y && n_clips > 0 && T > 0, "npvp_frame_ln_gelu_residual_posfuse: bad arguments");
   NPVP_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "npvp_frame_ln_gelu_residual_posfuse: ln_w/ln_b must both be set or both NULL");
   NPVP_REQUIRE((out_ln_bf16 || out_fused_bf16) && (!out_fused_bf16 || beta), "npvp_frame_ln_gelu_residual_posfuse: outputs / beta missing");
-  frame_ln_gelu_residual_kernel<true><<<(unsigned)(n_clips * T), 512, 0, (cudaStream_t)stream>>>(
+  frame_ln_gelu_residual_kernel<true><<<(unsigned)(n_clips * T * kFrameCL), kFrameThreads, 0, (cudaStream_t)stream>>>(
       h, h_is_bf16, w_hwc, b_hwc, y, (int)T, ln_w, ln_b, qe, beta, gamma, (bf16*)out_ln_bf16, (bf16*)out_fused_bf16);
   NPVP_LAUNCH_CHECK("frame_ln_gelu_residual_kernel<posfuse>");
   return NPVP_OK;
