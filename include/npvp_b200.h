@@ -74,7 +74,9 @@ int npvp_version(void);
 int64_t npvp_launch_count(void);
 void npvp_reset_launch_count(void);
 /* library-wide switches: "gemm_2cta": 1 = N >= 256 GEMMs of the default back-end always use the 2-CTA cluster kernel,
- * 0 = never, -1 (default) = when K >= 1024 (where the main loop dominates and the halved operand traffic pays) */
+ * 0 = never, -1 (default) = when K >= 1024 (where the main loop dominates and the halved operand traffic pays);
+ * "gemm_epi_direct": 1 = 16-bit outputs without residuals are stored straight from the accumulator layout with 32-byte
+ * sector stores, 0 (default) = transposed through shared memory for row-coalesced stores (A/B switch, identical results) */
 int npvp_set_option(const char* name, int value);
 
 /* ---- dense contractions -------------------------------------------------------------------

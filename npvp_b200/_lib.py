@@ -127,6 +127,7 @@ class Ops:
         self.gemm_backend = {"auto": GEMM_AUTO, "tcgen05": GEMM_TCGEN05, "simt": GEMM_SIMT, "tcgen05_v1": GEMM_TCGEN05_V1,
                              "tcgen05_2cta": GEMM_TCGEN05_2CTA}[os.environ.get("NPVP_B200_GEMM", "auto")]
         self.lib.npvp_set_option(b"gemm_2cta", int(os.environ.get("NPVP_B200_GEMM_2CTA", "-1")))
+        self.lib.npvp_set_option(b"gemm_epi_direct", int(os.environ.get("NPVP_B200_GEMM_EPI_DIRECT", "0")))
 
     # -- plumbing -------------------------------------------------------------------------------
     def _stream(self):

@@ -103,6 +103,23 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld that also "redefines" the destination registers of an earlier tcgen05.ld, so the compiler can neither read
+// nor copy them before the wait when the load was issued a whole loop iteration ahead (software-pipelined epilogue)
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+// 256-bit global store (sm_100: STG.256): one full 32-byte sector per thread
+__device__ __forceinline__ void stg256(void* dst, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 
 }  // namespace ptx
 
@@ -405,6 +422,36 @@ __device__ __forceinline__ void epi_chunk(uint32_t stg_addr, int sub_row, int ch
   }
 }
 
+// OUT == 3 (opt-in, npvp_set_option("gemm_epi_direct", 1)): 16-bit output without residuals, written straight from the
+// accumulator layout (thread = row, 32 consecutive columns): bias / activation / rounding in registers, then two 32-byte
+// sector stores per thread, tcgen05.ld of the next chunk in flight meanwhile.  No shared-memory transpose.
+// Measured r01 (tools/bench_gemm.py, M=40960): identical to the staged epilogue within noise on every shape (fc1 84.0 vs
+// 85.0 us).  The ablation that explains it: dropping the global stores takes fc1 from 84 to 65.5 us, dropping the
+// tcgen05.ld changes nothing - the kernel is bound by L2 traffic (operand re-reads + output sectors, ~235 sectors/clk on
+// every shape), not by how the epilogue moves data inside the SM.  Kept as an A/B switch, off by default.
+constexpr int kOutDirect16 = 3;
+template <int ACT, bool FP16>
+__device__ __forceinline__ void epi_direct16(const uint32_t (&r)[32], const float* __restrict__ bias_n0, float alpha, float relu_floor,
+                                             h16* __restrict__ dst, bool row_ok, int act_rt) {
+  constexpr int fp16 = FP16 ? 1 : 0;
+  uint32_t p[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias_n0) b = __ldg(reinterpret_cast<const float4*>(bias_n0) + j);       // warp-uniform address: one L1 broadcast
+    const float v0 = fmaxf(act_ct<ACT>(__uint_as_float(r[4 * j + 0]) + b.x, act_rt) * alpha, relu_floor);
+    const float v1 = fmaxf(act_ct<ACT>(__uint_as_float(r[4 * j + 1]) + b.y, act_rt) * alpha, relu_floor);
+    const float v2 = fmaxf(act_ct<ACT>(__uint_as_float(r[4 * j + 2]) + b.z, act_rt) * alpha, relu_floor);
+    const float v3 = fmaxf(act_ct<ACT>(__uint_as_float(r[4 * j + 3]) + b.w, act_rt) * alpha, relu_floor);
+    p[2 * j] = pack_h16x2(v0, v1, fp16);
+    p[2 * j + 1] = pack_h16x2(v2, v3, fp16);
+  }
+  if (row_ok) {
+    ptx::stg256(dst, p);
+    ptx::stg256(dst + 16, p + 8);
+  }
+}
+
 template <int BN, int ACT, int RES, int OUT, int CONV>
 __global__ void __launch_bounds__(kGemm2Threads, 1)
 gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -588,6 +635,36 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int64_t nb = (int64_t)n_blk * BN + c + chunk * 4;
         return (has_bias && nb < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
+      if (OUT == kOutDirect16) {
+        // software-pipelined: the tcgen05.ld of chunk i+1 is in flight while chunk i is converted and stored
+        constexpr int kChunks = kColsPerWarp / 32;
+        const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp);
+        const int64_t m = (int64_t)m_blk * kBM + quad * 32 + lane;
+        const int64_t nw = (int64_t)n_blk * BN + half * kColsPerWarp;
+        h16* drow = ep.out_bf16 + m * ep.ld_out + nw;
+        ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+        ptx::tc_fence_after();
+        uint32_t r[2][32];
+        ptx::tmem_ld_32x32(t0, r[0]);
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+          ptx::tmem_ld_wait_regs(r[i & 1]);
+          if (i + 1 < kChunks) {
+            ptx::tmem_ld_32x32(t0 + 32 * (i + 1), r[(i + 1) & 1]);
+          } else {                                                   // this warp's part of the accumulator is in registers
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          const int64_t n0 = nw + 32 * i;
+          if (n0 < N) {                                              // warp-uniform; N % 32 == 0 on this path
+            if (fp16) epi_direct16<ACT, true>(r[i & 1], has_bias ? ep.bias + n0 : nullptr, alpha, relu_floor, drow + 32 * i, m < M, ep.act);
+            else      epi_direct16<ACT, false>(r[i & 1], has_bias ? ep.bias + n0 : nullptr, alpha, relu_floor, drow + 32 * i, m < M, ep.act);
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       float4 b_next = load_bias(half * kColsPerWarp);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
@@ -943,6 +1020,7 @@ static int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw
 
 
 static int g_num_sms = 0;
+static int g_epi_direct = 0;   // npvp_set_option("gemm_epi_direct", 1): store 16-bit outputs straight from the accumulator layout (see epi_direct16)
 static int g_use_2cta = -1;     // npvp_set_option("gemm_2cta", v): 1 = always for N >= 256, 0 = never, -1 (default) = when K >= 1024
 
 template <int BN, int ACT, int RES, int OUT, int CONV>
@@ -981,7 +1059,11 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
   const int res = !e.res1 ? (e.res2 ? -1 : 0) : (!e.res2 ? (e.res1_bf16 ? 2 : 1) : ((e.res1_bf16 && e.res2_bf16) ? 3 : -1));
   const int out = (e.out_f32 && e.out_bf16) ? 2 : (e.out_f32 ? 1 : 0);
   const int act = e.act;
+  // 16-bit output without residuals: store straight from the accumulator layout when every 32-column chunk of a row is a
+  // whole, 32-byte aligned run of sectors
+  const bool direct = g_epi_direct && res == 0 && out == 0 && N % 32 == 0 && e.ld_out % 16 == 0 && ((uintptr_t)e.out_bf16 % 32) == 0;
   if (conv) {
+    if (direct && act == NPVP_ACT_RELU) return launch_v2_inst<BN, NPVP_ACT_RELU, 0, kOutDirect16, 1>(ta, tb, M, N, K, e, cg0, grid, st);
 #define NPVP_V2_CONV(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_, 1>(ta, tb, M, N, K, e, cg0, grid, st)
     NPVP_V2_CONV(NPVP_ACT_RELU, 0, 0);   // conv / transposed conv + BN + ReLU
     NPVP_V2_CONV(NPVP_ACT_RELU, 2, 0);   // F3D conv: ReLU(BN(conv)) + x
@@ -989,6 +1071,11 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
     NPVP_V2_CONV(NPVP_ACT_NONE, 2, 1);   // ... last block: fp32 tokens out
 #undef NPVP_V2_CONV
     return launch_v2_inst<BN, -1, -1, -1, 1>(ta, tb, M, N, K, e, cg0, grid, st);
+  }
+  if (direct) {
+    if (act == NPVP_ACT_NONE) return launch_v2_inst<BN, NPVP_ACT_NONE, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, grid, st);
+    if (act == NPVP_ACT_GELU) return launch_v2_inst<BN, NPVP_ACT_GELU, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, grid, st);
+    if (act == NPVP_ACT_RELU) return launch_v2_inst<BN, NPVP_ACT_RELU, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, grid, st);
   }
 #define NPVP_V2_CASE(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_, 0>(ta, tb, M, N, K, e, cg0, grid, st)
   NPVP_V2_CASE(NPVP_ACT_NONE, 0, 0);   // projections -> 16-bit
@@ -1154,6 +1241,7 @@ extern "C" int npvp_conv_gemm_bf16(const void* x, int64_t frames, int H, int W, 
 extern "C" int npvp_set_option(const char* name, int value) {
   NPVP_REQUIRE(name != nullptr, "npvp_set_option: null name");
   if (strcmp(name, "gemm_2cta") == 0) { g_use_2cta = value; return NPVP_OK; }
+  if (strcmp(name, "gemm_epi_direct") == 0) { g_epi_direct = value; return NPVP_OK; }
   NPVP_REQUIRE(false, "npvp_set_option: unknown option '%s'", name);
   return NPVP_ERR_INVALID;
 }

@@ -75,6 +75,25 @@ def test_gemm_epilogues(op, spec, backend, dt):
     close(x, x2, 2e-3, "in-place residual")
 
 
+@pytest.mark.parametrize("dt", H16)
+@pytest.mark.parametrize("M,N,K,act", [(1000, 512, 512, 0), (384, 1024, 512, 2), (300, 128, 256, 1), (4096, 64, 576, 1)])
+def test_gemm_direct_epilogue_matches_staged(op, M, N, K, act, dt):
+    """The opt-in store-from-accumulator-layout epilogue (gemm_epi_direct) must be bit-identical to the staged one."""
+    a, w = rn(M, K, seed=1, dtype=dt), rn(N, K, seed=2, scale=K ** -0.5, dtype=dt)
+    bias = rn(N, seed=3)
+    outs = []
+    try:
+        for direct in (0, 1):
+            op.lib.npvp_set_option(b"gemm_epi_direct", direct)
+            o = torch.zeros(M, N, device=DEV, dtype=dt)
+            op.gemm(a, w, bias=bias, act=act, out_bf16=o, backend=1)
+            torch.cuda.synchronize()
+            outs.append(o)
+    finally:
+        op.lib.npvp_set_option(b"gemm_epi_direct", 0)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_gemm_f32_and_fourier(op, spec):
     a, w, b = rn(700, 512, seed=1), rn(256, 512, seed=2, scale=0.05), rn(256, seed=3)
     o1, o2 = torch.empty(700, 256, device=DEV), torch.empty(700, 256, device=DEV)

@@ -8,8 +8,9 @@ def main():
     op = _lib.Ops()
     dev = "cuda"
     M = int(os.environ.get("M", 40960))
-    shapes = [(M, 512, 512, "res"), (M, 1024, 512, "bf16"), (M, 2048, 512, "bf16"), (M, 512, 2048, "f32"), (M, 1024, 512, "gelu"),
-              (M, 512, 1024, "res"), (M // 5, 512, 512, "bf16"), (8192, 256, 4608, "bf16"), (M * 8, 128, 256, "bf16"), (M * 8, 64, 576, "bf16")]
+    shapes = [(M, 2048, 512, "bf16"), (M, 512, 2048, "bf16"), (M, 512, 512, "bf16"), (M, 1024, 512, "bf16"), (M, 1024, 512, "gelu"),
+              (M, 512, 1024, "bf16"), (M // 5, 512, 512, "bf16"), (M // 5, 2048, 512, "bf16"), (8192, 256, 4608, "bf16"),
+              (M * 8, 128, 256, "bf16"), (M * 8, 64, 576, "bf16"), (M, 512, 512, "res"), (M, 512, 2048, "f32")]
     if os.environ.get("SHAPES"):
         shapes = [shapes[int(i)] for i in os.environ["SHAPES"].split(",")]
     backends = [b for b in (("v1", 3), ("v2", 1), ("2cta", 4)) if os.environ.get("ONLY", b[0]) == b[0]]
