@@ -305,7 +305,8 @@ struct Gemm2Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 5 : 6);
   static constexpr int kStagingBytes = kEpiWarps * 32 * 32 * 4;             // one 32x32 fp32 tile per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTableBytes = (BN == 256) ? 1024 : 2048;             // conv gather: [2 buffers][taps per k-block][128 rows] source pixels
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/ + kTableBytes;
   static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;          // 128 / 256 / 512
 };
 
@@ -515,60 +516,84 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       }
     }
   } else if (CONV && (warp == 2 || warp == 3)) {
-    // ---------------- implicit-GEMM A gather (64 threads, two rows of the 128-row tile each) ----------------
+    // ---------------- implicit-GEMM A gather (64 threads) ----------------
+    // Lane layout: 8 lanes cover the 128 bytes of one A row (one 16-byte chunk each), 8 rows per pass, 16 passes per
+    // k-block, so every cp.async warp instruction touches 4 full 128-byte lines.  (The first version gave each thread two
+    // whole rows: 32 different lines per instruction, and the LSU tag stage - not L2 or the tensor pipe - set the pace:
+    // 2150 clk per k-block against 540 clk of MMA work, r01 ncu of the decoder layers.)  The per-row address arithmetic
+    // that sank an earlier coalesced attempt is hoisted into a table: whenever the k-loop enters a new filter tap the 64
+    // threads compute the source pixel of all 128 rows for that tap once (two rows each) into shared memory.
     const int pt = threadIdx.x - 64;
-    const int seg = cg.C < kBK ? cg.C : kBK;                         // channels per contiguous segment (32 or 64)
-    const int segs_per_kb = kBK / seg;
-    const int chunks_per_seg = seg >> 3;
+    const int chunk = pt & 7, rslot = pt >> 3;
+    const int C = cg.C;
+    const int tpk = C < kBK ? kBK / C : 1;                           // taps per k-block (2 when C == 32)
+    const int kb_per_tap = C > kBK ? C / kBK : 1;                    // k-blocks per tap (C > 64)
     const int taps = cg.KH * cg.KW;
-    const int64_t hw_out = (int64_t)cg.Ho * cg.Wo;
-    int stage = 0, trail = 0, inflight = 0;
+    const uint32_t hw_out = (uint32_t)(cg.Ho * cg.Wo);
+    uint32_t* table = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes + 256);   // [2][tpk][128]
+    const int my_tt = C < kBK ? (chunk * 8) / C : 0;                 // which of the k-block's taps this lane's chunk belongs to
+    const int my_c = C < kBK ? (chunk * 8) % C : chunk * 8;          // channel offset of the chunk inside that tap
+    const uint32_t dst_off = (uint32_t)(rslot * 128 + ((chunk ^ rslot) << 4));   // row & 7 == rslot for every pass
+    constexpr uint32_t kNoPixel = 0xffffffffu;
+    const int H = cg.H, W = cg.W, H2 = cg.H >> 1, W2 = cg.W >> 1;
+    int stage = 0, trail = 0, inflight = 0, buf = 0;
     uint32_t phase = 0;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = (int)(t / n_tiles);
-      int64_t fr[2];
+      uint32_t fbase[2];                                              // first pixel of the row's frame (all pixel indices fit 32 bits)
       int iy0[2], ix0[2];
       bool rok[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int64_t m = (int64_t)m_blk * kBM + pt + 64 * h;
         rok[h] = m < M;
-        const int64_t mm = rok[h] ? m : 0;
-        fr[h] = mm / hw_out;
-        const int rem = (int)(mm - fr[h] * hw_out);
-        iy0[h] = (rem / cg.Wo) * cg.stride - cg.pad;
-        ix0[h] = (rem % cg.Wo) * cg.stride - cg.pad;
+        const uint32_t mm = rok[h] ? (uint32_t)m : 0u;
+        const uint32_t f = mm / hw_out, rem = mm - f * hw_out;
+        const uint32_t oy = rem / (uint32_t)cg.Wo;
+        fbase[h] = f * (uint32_t)(H * W);
+        iy0[h] = (int)oy * cg.stride - cg.pad;
+        ix0[h] = (int)(rem - oy * (uint32_t)cg.Wo) * cg.stride - cg.pad;
       }
+      int tap_next = 0, ky = 0, kx = 0, kb_left = 0, c_base = 0;     // (ky, kx) of tap_next
       for (int kb = 0; kb < num_k_blocks; ++kb) {
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        const uint32_t a_base = ptx::smem_u32(smem_a + stage * Cfg::kABytes);
-        for (int sg = 0; sg < segs_per_kb; ++sg) {
-          const int k = kb * kBK + sg * seg;
-          const int tap = k / cg.C, c0 = k - tap * cg.C;
-          const int ky = tap / cg.KW, kx = tap - ky * cg.KW;
+        if (kb_left == 0) {                                           // the k-loop enters new tap(s): rebuild the pixel table
+          buf ^= 1;
+          for (int tt = 0; tt < tpk; ++tt) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int r = pt + 64 * h;
-            int iy = iy0[h] + ky, ix = ix0[h] + kx;
-            bool valid = rok[h] && tap < taps;
-            if (cg.pad_mode == NPVP_PAD_REFLECT) { iy = conv_reflect(iy, cg.H); ix = conv_reflect(ix, cg.W); }
-            else if (cg.pad_mode == NPVP_PAD_REPLICATE) { iy = min(max(iy, 0), cg.H - 1); ix = min(max(ix, 0), cg.W - 1); }
-            else valid = valid && iy >= 0 && iy < cg.H && ix >= 0 && ix < cg.W;
-            const h16* src = cg.x;
-            if (valid) {
-              const size_t pix = cg.phase_major
-                  ? ((((size_t)fr[h] * (cg.H >> 1) + (iy >> 1)) * (cg.W >> 1) + (ix >> 1)) * 4 + ((iy & 1) << 1) + (ix & 1))
-                  : (((size_t)fr[h] * cg.H + iy) * cg.W + ix);
-              src = cg.x + pix * cg.C + c0;
+            for (int h = 0; h < 2; ++h) {
+              int iy = iy0[h] + ky, ix = ix0[h] + kx;
+              bool valid = rok[h] && tap_next < taps;
+              if (cg.pad_mode == NPVP_PAD_REFLECT) { iy = conv_reflect(iy, H); ix = conv_reflect(ix, W); }
+              else if (cg.pad_mode == NPVP_PAD_REPLICATE) { iy = min(max(iy, 0), H - 1); ix = min(max(ix, 0), W - 1); }
+              else valid = valid && (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+              const uint32_t pix = cg.phase_major
+                  ? fbase[h] + (uint32_t)((((iy >> 1) * W2 + (ix >> 1)) << 2) + ((iy & 1) << 1) + (ix & 1))
+                  : fbase[h] + (uint32_t)(iy * W + ix);
+              table[(buf * tpk + tt) * kBM + pt + 64 * h] = valid ? pix : kNoPixel;
             }
-            const uint32_t row_base = a_base + (uint32_t)r * 128u;
-            for (int c = 0; c < chunks_per_seg; ++c) {
-              const int chunk = sg * chunks_per_seg + c;
-              cp_async_16(row_base + (uint32_t)((chunk ^ (r & 7)) << 4), src + (valid ? c * 8 : 0), valid ? 16u : 0u);
-            }
+            ++tap_next;
+            if (++kx == cg.KW) { kx = 0; ++ky; }
           }
+          asm volatile("bar.sync 1, 64;" ::: "memory");              // the two gather warps only
+          kb_left = kb_per_tap;
+          c_base = 0;
+        }
+        // all 16 source pixels first: the cp.async asm statements below are compiler barriers for shared-memory loads
+        const uint32_t* tb = table + (buf * tpk + my_tt) * kBM + rslot;
+        uint32_t pix[kBM / 8];
+#pragma unroll
+        for (int p = 0; p < kBM / 8; ++p) pix[p] = tb[p * 8];
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        const uint32_t a_dst = ptx::smem_u32(smem_a + stage * Cfg::kABytes) + dst_off;
+        const h16* xb = cg.x + c_base + my_c;
+#pragma unroll
+        for (int p = 0; p < kBM / 8; ++p) {
+          const bool valid = pix[p] != kNoPixel;
+          cp_async_16(a_dst + (uint32_t)p * 1024u, xb + (size_t)(valid ? pix[p] : 0u) * (uint32_t)C, valid ? 16u : 0u);
         }
         cp_async_commit();
+        --kb_left;
+        c_base += kBK;
         ++inflight;
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         if (inflight > kGatherLag) {                                  // oldest group has landed: publish its stage
@@ -1232,7 +1257,8 @@ extern "C" int npvp_conv_gemm_bf16(const void* x, int64_t frames, int H, int W, 
   cg.Ho = Ho; cg.Wo = Wo; cg.phase_major = phase_major;
   EpiParams e = make_epi(ep);
   cudaStream_t st = (cudaStream_t)stream;
-  if (N >= 256) return launch_tcgen05_v2<256>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);
+  NPVP_REQUIRE((int64_t)frames * H * W < 0xffffffffll && M < 0xffffffffll, "npvp_conv_gemm_bf16: more than 2^32 - 1 input or output pixels per launch");
+  if (N >= 256 && C >= 64) return launch_tcgen05_v2<256>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);   // (C == 32 needs the 2-tap table)
   if (N > 64) return launch_tcgen05_v2<128>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);
   return launch_tcgen05_v2<64>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);
 }

@@ -45,6 +45,20 @@ def main():
             if ref is None: ref = out
             line += f" | {name}: {t*1e3:8.1f} us {2*m*n*k/t/1e9:7.1f} TFLOP/s"
             if name != backends[0][0]: line += f" (maxdiff vs {backends[0][0]} {float((out-ref).abs().max()):.1e})"
+        if os.environ.get("CUBLAS", "1") == "1":          # library yardstick on the same shape (never used by the product)
+            import torch.nn.functional as F
+            bb = bias.to(torch.bfloat16)
+            for _ in range(3):
+                F.linear(a, w, bb)
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); F.linear(a, w, bb); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            t = sorted(ts)[len(ts) // 2]
+            line += f" | cuBLASLt: {t*1e3:8.1f} us {2*m*n*k/t/1e9:7.1f} TFLOP/s"
         print(line, flush=True)
 
 if __name__ == "__main__":
