@@ -335,7 +335,8 @@ struct ConvGather {
   const h16* x;
   int H, W, C, KH, KW, stride, pad, pad_mode, Ho, Wo, phase_major;
 };
-constexpr int kGatherThreads = 64;     // warps 2 and 3
+constexpr int kGatherThreads = 128;    // warps 2, 3 and (conv kernels only) the two extra warps 12, 13
+constexpr int kGatherRowsPerPass = kGatherThreads / 8;
 constexpr int kGatherLag = 2;          // cp.async groups kept in flight per thread before the stage is published
 
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* src, uint32_t src_bytes) {
@@ -454,7 +455,7 @@ __device__ __forceinline__ void epi_direct16(const uint32_t (&r)[32], const floa
 }
 
 template <int BN, int ACT, int RES, int OUT, int CONV>
-__global__ void __launch_bounds__(kGemm2Threads, 1)
+__global__ void __launch_bounds__(CONV ? kGemm2Threads + 64 : kGemm2Threads, 1)
 gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        int64_t M, int64_t N, int64_t K, EpiParams ep, ConvGather cg) {
   using Cfg = Gemm2Cfg<BN>;
@@ -515,16 +516,17 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         }
       }
     }
-  } else if (CONV && (warp == 2 || warp == 3)) {
-    // ---------------- implicit-GEMM A gather (64 threads) ----------------
-    // Lane layout: 8 lanes cover the 128 bytes of one A row (one 16-byte chunk each), 8 rows per pass, 16 passes per
-    // k-block, so every cp.async warp instruction touches 4 full 128-byte lines.  (The first version gave each thread two
-    // whole rows: 32 different lines per instruction, and the LSU tag stage - not L2 or the tensor pipe - set the pace:
-    // 2150 clk per k-block against 540 clk of MMA work, r01 ncu of the decoder layers.)  The per-row address arithmetic
-    // that sank an earlier coalesced attempt is hoisted into a table: whenever the k-loop enters a new filter tap the 64
-    // threads compute the source pixel of all 128 rows for that tap once (two rows each) into shared memory.
-    const int pt = threadIdx.x - 64;
-    const int chunk = pt & 7, rslot = pt >> 3;
+  } else if (CONV && (warp == 2 || warp == 3 || warp >= 12)) {
+    // ---------------- implicit-GEMM A gather (128 threads: warps 2, 3, 12, 13) ----------------
+    // Lane layout: 8 lanes cover the 128 bytes of one A row (one 16-byte chunk each), 16 rows per pass, 8 passes per
+    // k-block.  The producer is bound by the latency of its own instruction stream, not by memory: the first version
+    // (64 threads, two whole rows each, full address arithmetic per row and k-block) executed ~470 dependent instructions
+    // per k-block = 2150 clk against 540 clk of MMA work (r01 ncu of the decoder layers, tensor pipe 26% active, MMA warp
+    // spinning on the full barrier).  So the per-row arithmetic is hoisted into a table - whenever the k-loop enters a new
+    // filter tap each thread computes the source pixel of ONE row for that tap into shared memory - and the per-k-block
+    // work is 8 table reads + 8 cp.async per thread.
+    const int pt = warp < 4 ? (int)threadIdx.x - 64 : (int)threadIdx.x - kGemm2Threads + 64;
+    const int chunk = pt & 7, rslot = pt >> 3;                       // rslot: row within a 16-row pass
     const int C = cg.C;
     const int tpk = C < kBK ? kBK / C : 1;                           // taps per k-block (2 when C == 32)
     const int kb_per_tap = C > kBK ? C / kBK : 1;                    // k-blocks per tap (C > 64)
@@ -533,63 +535,61 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     uint32_t* table = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes + 256);   // [2][tpk][128]
     const int my_tt = C < kBK ? (chunk * 8) / C : 0;                 // which of the k-block's taps this lane's chunk belongs to
     const int my_c = C < kBK ? (chunk * 8) % C : chunk * 8;          // channel offset of the chunk inside that tap
-    const uint32_t dst_off = (uint32_t)(rslot * 128 + ((chunk ^ rslot) << 4));   // row & 7 == rslot for every pass
+    const uint32_t dst_off = (uint32_t)(rslot * 128 + ((chunk ^ (rslot & 7)) << 4));   // row & 7 == rslot & 7 for every pass
     constexpr uint32_t kNoPixel = 0xffffffffu;
     const int H = cg.H, W = cg.W, H2 = cg.H >> 1, W2 = cg.W >> 1;
     int stage = 0, trail = 0, inflight = 0, buf = 0;
     uint32_t phase = 0;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = (int)(t / n_tiles);
-      uint32_t fbase[2];                                              // first pixel of the row's frame (all pixel indices fit 32 bits)
-      int iy0[2], ix0[2];
-      bool rok[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int64_t m = (int64_t)m_blk * kBM + pt + 64 * h;
-        rok[h] = m < M;
-        const uint32_t mm = rok[h] ? (uint32_t)m : 0u;
+      uint32_t fbase;                                                 // first pixel of the row's frame (all pixel indices fit 32 bits)
+      int iy0, ix0;
+      bool rok;
+      {
+        const int64_t m = (int64_t)m_blk * kBM + pt;                  // this thread's table row
+        rok = m < M;
+        const uint32_t mm = rok ? (uint32_t)m : 0u;
         const uint32_t f = mm / hw_out, rem = mm - f * hw_out;
         const uint32_t oy = rem / (uint32_t)cg.Wo;
-        fbase[h] = f * (uint32_t)(H * W);
-        iy0[h] = (int)oy * cg.stride - cg.pad;
-        ix0[h] = (int)(rem - oy * (uint32_t)cg.Wo) * cg.stride - cg.pad;
+        fbase = f * (uint32_t)(H * W);
+        iy0 = (int)oy * cg.stride - cg.pad;
+        ix0 = (int)(rem - oy * (uint32_t)cg.Wo) * cg.stride - cg.pad;
       }
       int tap_next = 0, ky = 0, kx = 0, kb_left = 0, c_base = 0;     // (ky, kx) of tap_next
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         if (kb_left == 0) {                                           // the k-loop enters new tap(s): rebuild the pixel table
           buf ^= 1;
           for (int tt = 0; tt < tpk; ++tt) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              int iy = iy0[h] + ky, ix = ix0[h] + kx;
-              bool valid = rok[h] && tap_next < taps;
+            {
+              int iy = iy0 + ky, ix = ix0 + kx;
+              bool valid = rok && tap_next < taps;
               if (cg.pad_mode == NPVP_PAD_REFLECT) { iy = conv_reflect(iy, H); ix = conv_reflect(ix, W); }
               else if (cg.pad_mode == NPVP_PAD_REPLICATE) { iy = min(max(iy, 0), H - 1); ix = min(max(ix, 0), W - 1); }
               else valid = valid && (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
               const uint32_t pix = cg.phase_major
-                  ? fbase[h] + (uint32_t)((((iy >> 1) * W2 + (ix >> 1)) << 2) + ((iy & 1) << 1) + (ix & 1))
-                  : fbase[h] + (uint32_t)(iy * W + ix);
-              table[(buf * tpk + tt) * kBM + pt + 64 * h] = valid ? pix : kNoPixel;
+                  ? fbase + (uint32_t)((((iy >> 1) * W2 + (ix >> 1)) << 2) + ((iy & 1) << 1) + (ix & 1))
+                  : fbase + (uint32_t)(iy * W + ix);
+              table[(buf * tpk + tt) * kBM + pt] = valid ? pix : kNoPixel;
             }
             ++tap_next;
             if (++kx == cg.KW) { kx = 0; ++ky; }
           }
-          asm volatile("bar.sync 1, 64;" ::: "memory");              // the two gather warps only
+          asm volatile("bar.sync 1, 128;" ::: "memory");             // the four gather warps only
           kb_left = kb_per_tap;
           c_base = 0;
         }
-        // all 16 source pixels first: the cp.async asm statements below are compiler barriers for shared-memory loads
+        // all 8 source pixels first: the cp.async asm statements below are compiler barriers for shared-memory loads
         const uint32_t* tb = table + (buf * tpk + my_tt) * kBM + rslot;
-        uint32_t pix[kBM / 8];
+        uint32_t pix[kBM / kGatherRowsPerPass];
 #pragma unroll
-        for (int p = 0; p < kBM / 8; ++p) pix[p] = tb[p * 8];
+        for (int p = 0; p < kBM / kGatherRowsPerPass; ++p) pix[p] = tb[p * kGatherRowsPerPass];
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         const uint32_t a_dst = ptx::smem_u32(smem_a + stage * Cfg::kABytes) + dst_off;
         const h16* xb = cg.x + c_base + my_c;
 #pragma unroll
-        for (int p = 0; p < kBM / 8; ++p) {
+        for (int p = 0; p < kBM / kGatherRowsPerPass; ++p) {
           const bool valid = pix[p] != kNoPixel;
-          cp_async_16(a_dst + (uint32_t)p * 1024u, xb + (size_t)(valid ? pix[p] : 0u) * (uint32_t)C, valid ? 16u : 0u);
+          cp_async_16(a_dst + (uint32_t)p * (kGatherRowsPerPass * 128u), xb + (size_t)(valid ? pix[p] : 0u) * (uint32_t)C, valid ? 16u : 0u);
         }
         cp_async_commit();
         --kb_left;
@@ -639,7 +639,7 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // ---------------- epilogue ----------------
     const int quad = warp & 3;                                      // TMEM lane quadrant of this warp
     const int half = (warp - 4) >> 2;                               // which half of the tile's columns
@@ -1058,7 +1058,7 @@ static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, int64_t 
     if (err != cudaSuccess) { npvp_set_error("cudaFuncSetAttribute(v2, smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
     attr_set = true;
   }
-  gemm_tcgen05_v2_kernel<BN, ACT, RES, OUT, CONV><<<grid, kGemm2Threads, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K, e, cg);
+  gemm_tcgen05_v2_kernel<BN, ACT, RES, OUT, CONV><<<grid, CONV ? kGemm2Threads + 64 : kGemm2Threads, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K, e, cg);
   NPVP_LAUNCH_CHECK(CONV ? "gemm_tcgen05_v2_kernel<conv>" : "gemm_tcgen05_v2_kernel");
   return NPVP_OK;
 }
