@@ -414,8 +414,8 @@ extern "C" int npvp_ffn_frame_stats(const void* h_bf16, float* stats, int64_t fr
 }
 
 // depthwise 3x3, zero padding 1, on an 8x8 map held in registers (a[p], p = y*8+x); taps w[ky*3+kx]
-__device__ __forceinline__ float dw3x3_at(const float (&a)[64], const float (&w)[9], int y, int x) {
-  float acc = 0.f;
+__device__ __forceinline__ float dw3x3_at(const float (&a)[64], const float (&w)[9], float bias, int y, int x) {
+  float acc = bias;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int yy = y + ky - 1;
@@ -436,12 +436,14 @@ __device__ __forceinline__ float dw3x3_at(const float (&a)[64], const float (&w)
 // owns kFfnChunk channels, parks their 64 x 2 parameters in shared memory once (each thread only ever reads its own
 // column, so no barrier is needed) and walks over frames blockIdx.y, blockIdx.y + gridDim.y, ...
 constexpr int kFfnChunk = 128;
+template <int CH>                                                 // CH > 0: compile-time channel count (row stride becomes an immediate)
 __global__ void __launch_bounds__(kFfnChunk)
 ffn_dwconv_kernel(const bf16* __restrict__ h, const float* __restrict__ stats1, const float* __restrict__ n1w,
                   const float* __restrict__ n1b, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
-                  bf16* __restrict__ y, float* __restrict__ partial2, int Ch, int frames) {
+                  bf16* __restrict__ y, float* __restrict__ partial2, int Ch_rt, int frames) {
   extern __shared__ float2 ffn_wb[];                             // [64 px][kFfnChunk] (weight, bias)
   __shared__ float red[64];
+  const int Ch = CH > 0 ? CH : Ch_rt;
   const int c = blockIdx.x * kFfnChunk + threadIdx.x;
 #pragma unroll 8
   for (int p = 0; p < 64; ++p)
@@ -451,7 +453,7 @@ ffn_dwconv_kernel(const bf16* __restrict__ h, const float* __restrict__ stats1, 
   for (int k = 0; k < 9; ++k) w[k] = __ldg(dw_w + (size_t)k * Ch + c);
   const float bias = __ldg(dw_b + c);
   for (int f = blockIdx.y; f < frames; f += gridDim.y) {
-    const float mean = __ldg(stats1 + 2 * f), rstd = __ldg(stats1 + 2 * f + 1);
+    const float rstd = __ldg(stats1 + 2 * f + 1), nmr = -__ldg(stats1 + 2 * f) * rstd;
     float a[64];
     const bf16* src = h + (size_t)f * kTok * Ch + c;
 #pragma unroll
@@ -459,7 +461,7 @@ ffn_dwconv_kernel(const bf16* __restrict__ h, const float* __restrict__ stats1, 
 #pragma unroll
     for (int p = 0; p < 64; ++p) {
       const float2 wb = ffn_wb[p * kFfnChunk + threadIdx.x];
-      a[p] = gelu_erf((a[p] - mean) * rstd * wb.x + wb.y);
+      a[p] = gelu_erf(fmaf(fmaf(a[p], rstd, nmr), wb.x, wb.y));   // LN1 affine in two FMAs
     }
     bf16* dst = y + (size_t)f * kTok * Ch + c;
     float s = 0.f, q = 0.f;
@@ -467,12 +469,10 @@ ffn_dwconv_kernel(const bf16* __restrict__ h, const float* __restrict__ stats1, 
     for (int yy = 0; yy < 8; ++yy)
 #pragma unroll
       for (int xx = 0; xx < 8; ++xx) {
-        const float o = dw3x3_at(a, w, yy, xx) + bias;
-        const bf16 ob = __float2bfloat16(o);
-        dst[(size_t)(yy * 8 + xx) * Ch] = ob;
-        const float orr = __bfloat162float(ob);   // statistics of what the consumer will actually read
-        s += orr;
-        q = fmaf(orr, orr, q);
+        const float o = dw3x3_at(a, w, bias, yy, xx);
+        dst[(size_t)(yy * 8 + xx) * Ch] = __float2bfloat16(o);
+        s += o;
+        q = fmaf(o, o, q);
       }
     block_sum2(s, q, red);
     if (threadIdx.x == 0) {
@@ -483,14 +483,13 @@ ffn_dwconv_kernel(const bf16* __restrict__ h, const float* __restrict__ stats1, 
   }
 }
 
-extern "C" int npvp_ffn_dwconv(const void* h_bf16, const float* stats1, const float* n1w, const float* n1b, const float* dw_w,
-                               const float* dw_b, void* y_bf16, float* partial2, int64_t frames, int64_t Ch, void* stream) {
-  NPVP_REQUIRE(h_bf16 && stats1 && n1w && n1b && dw_w && dw_b && y_bf16 && partial2, "npvp_ffn_dwconv: null pointer");
-  NPVP_REQUIRE(frames > 0 && frames < (1ll << 31) && Ch % kFfnChunk == 0, "npvp_ffn_dwconv: frames > 0, Ch multiple of %d", kFfnChunk);
+template <int CH>
+static int launch_ffn_dwconv(const void* h_bf16, const float* stats1, const float* n1w, const float* n1b, const float* dw_w,
+                             const float* dw_b, void* y_bf16, float* partial2, int64_t frames, int64_t Ch, cudaStream_t st) {
   constexpr int smem = kTok * kFfnChunk * (int)sizeof(float2);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(ffn_dwconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t err = cudaFuncSetAttribute(ffn_dwconv_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) { npvp_set_error("ffn_dwconv: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
     attr_set = true;
   }
@@ -499,10 +498,19 @@ extern "C" int npvp_ffn_dwconv(const void* h_bf16, const float* stats1, const fl
   int64_t gy = (148 * 3) / chunks;
   gy = gy < 1 ? 1 : (gy > frames ? frames : gy);
   dim3 grid((unsigned)chunks, (unsigned)gy);
-  ffn_dwconv_kernel<<<grid, kFfnChunk, smem, (cudaStream_t)stream>>>((const bf16*)h_bf16, stats1, n1w, n1b, dw_w, dw_b, (bf16*)y_bf16,
-                                                                      partial2, (int)Ch, (int)frames);
+  ffn_dwconv_kernel<CH><<<grid, kFfnChunk, smem, st>>>((const bf16*)h_bf16, stats1, n1w, n1b, dw_w, dw_b, (bf16*)y_bf16, partial2, (int)Ch,
+                                                       (int)frames);
   NPVP_LAUNCH_CHECK("ffn_dwconv_kernel");
   return NPVP_OK;
+}
+
+extern "C" int npvp_ffn_dwconv(const void* h_bf16, const float* stats1, const float* n1w, const float* n1b, const float* dw_w,
+                               const float* dw_b, void* y_bf16, float* partial2, int64_t frames, int64_t Ch, void* stream) {
+  NPVP_REQUIRE(h_bf16 && stats1 && n1w && n1b && dw_w && dw_b && y_bf16 && partial2, "npvp_ffn_dwconv: null pointer");
+  NPVP_REQUIRE(frames > 0 && frames < (1ll << 31) && Ch % kFfnChunk == 0, "npvp_ffn_dwconv: frames > 0, Ch multiple of %d", kFfnChunk);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Ch == 2048) return launch_ffn_dwconv<2048>(h_bf16, stats1, n1w, n1b, dw_w, dw_b, y_bf16, partial2, frames, Ch, st);   // NPVP's only width
+  return launch_ffn_dwconv<0>(h_bf16, stats1, n1w, n1b, dw_w, dw_b, y_bf16, partial2, frames, Ch, st);
 }
 
 // out = GELU(LN2(y)).  Same parameter-traffic argument as above: a thread owns 8 channels of one pixel, keeps their 16
@@ -612,7 +620,7 @@ dwconv3x3_tokens_kernel(const float* __restrict__ x, const float* __restrict__ w
   for (int yy = 0; yy < 8; ++yy)
 #pragma unroll
     for (int xx = 0; xx < 8; ++xx) {
-      float o = dw3x3_at(a, wk, yy, xx) + sh;
+      float o = dw3x3_at(a, wk, sh, yy, xx);
       if (relu) o = fmaxf(o, 0.f);
       dst[(size_t)(yy * 8 + xx) * C] = __float2bfloat16(o);
     }

@@ -162,7 +162,7 @@ class SpecOps:
         o = F.conv2d(img, wt, dw_b, padding=1, groups=Ch).permute(0, 2, 3, 1).reshape(frames, 64, Ch)
         ob = o.to(torch.bfloat16)
         y.copy_(ob.reshape(y.shape))
-        of = ob.float().reshape(frames, 64, Ch // FFN_CHUNK, FFN_CHUNK)
+        of = o.reshape(frames, 64, Ch // FFN_CHUNK, FFN_CHUNK)      # statistics of the fp32 conv output (before rounding to bf16)
         partial2[:, :, 0] = of.sum(dim=(1, 3))
         partial2[:, :, 1] = (of * of).sum(dim=(1, 3))
 
