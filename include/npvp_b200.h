@@ -66,6 +66,11 @@ typedef struct npvp_epilogue {
   int32_t reserved;
   int64_t ld_out;
   int64_t ld_res;
+  /* optional (NULL = off): per-frame partial statistics of the stored values, a frame being 64 consecutive rows.
+   * fp32 [M/64][P = 4 * N/256][2] = (sum, sum of squares) over one 32-row x 128-column block each; reduce them with
+   * npvp_ffn_stats_finalize.  Requires M % 64 == 0, N % 256 == 0, 16-bit output only, act NONE, no residuals
+   * (the conv-FFN's fc1: LayerNorm((Ch,8,8)) statistics for free instead of a second pass over h1). */
+  float* frame_stats;
 } npvp_epilogue_t;
 
 const char* npvp_last_error(void);
@@ -139,6 +144,8 @@ int npvp_temporal_mean(const float* mem, float* evt, int64_t n_clips, int64_t T,
 /* ---- predictor: conv-FFN middle  (MlpDWBN norm1/act1/dw3x3/norm2/act2, VidHRFormer.py:381-385) ----
  * step 1: per-frame (sum, sumsq) of h1 bf16 [frames,64,Ch] -> stats fp32 [frames,2] = (mean, rstd) */
 int npvp_ffn_frame_stats(const void* h_bf16, float* stats, int64_t frames, int64_t Ch, void* stream);
+/* step 1 fused into the producing GEMM (npvp_epilogue_t.frame_stats): partial fp32 [frames,P,2] -> stats fp32 [frames,2] */
+int npvp_ffn_stats_finalize(const float* partial, int64_t P, float* stats, int64_t frames, int64_t elems_per_frame, void* stream);
 /* step 2: y = dw3x3(GELU(LN1(h1))) + b; also per-(frame,chunk) partial (sum,sumsq) of y.
  * n1w/n1b fp32 [64,Ch] (hw-major elementwise affine), dw_w fp32 [9,Ch], dw_b fp32 [Ch];
  * y bf16 [frames,64,Ch]; partial fp32 [frames, Ch/128, 2] (Ch a multiple of 128). */

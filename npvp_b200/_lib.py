@@ -27,7 +27,8 @@ _i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
 class Epilogue(C.Structure):
     _fields_ = [("bias", _vp), ("res1", _vp), ("res2", _vp), ("out_f32", _vp), ("out_bf16", _vp),
                 ("alpha", _f32), ("act", C.c_int32), ("res1_bf16", C.c_int32), ("res2_bf16", C.c_int32),
-                ("post_relu", C.c_int32), ("fp16", C.c_int32), ("reserved", C.c_int32), ("ld_out", _i64), ("ld_res", _i64)]
+                ("post_relu", C.c_int32), ("fp16", C.c_int32), ("reserved", C.c_int32), ("ld_out", _i64), ("ld_res", _i64),
+                ("frame_stats", _vp)]
 
 
 # symbol -> argtypes; every function returns int.  Kept in one table so tests can check the export list.
@@ -45,6 +46,7 @@ SIGNATURES = {
     "npvp_frame_ln_gelu_residual_posfuse": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_temporal_mean": [_vp, _vp, _i64, _i64, _i64, _vp],
     "npvp_ffn_frame_stats": [_vp, _vp, _i64, _i64, _vp],
+    "npvp_ffn_stats_finalize": [_vp, _i64, _vp, _i64, _i64, _vp],
     "npvp_ffn_dwconv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_ffn_norm2": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_attention": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i64, _i32, _i32, _i32, _vp],
@@ -146,7 +148,8 @@ class Ops:
 
     # -- contractions ---------------------------------------------------------------------------
     def gemm(self, a, w, *, bias=None, act=ACT_NONE, alpha=1.0, res1=None, res2=None, out_f32=None, out_bf16=None,
-             post_relu=False, backend=None):
+             post_relu=False, backend=None, frame_stats=None):
+        """``frame_stats``: fp32 [M/64, 4*N/256, 2] receiving partial (sum, sumsq) of the outputs per 64-row frame."""
         _chk16(a, "a", False); _chk16(w, "w", False, like=a)
         _chk(bias, torch.float32, "bias"); _chk(out_f32, torch.float32, "out_f32", False)
         _chk16(out_bf16, "out_bf16", False, like=a)
@@ -167,7 +170,10 @@ class Ops:
                 ld_res = ld
         ep = Epilogue(_ptr(bias), _ptr(res1), _ptr(res2), _ptr(out_f32), _ptr(out_bf16), float(alpha), int(act),
                       int(res1 is not None and res1.dtype in H16),
-                      int(res2 is not None and res2.dtype in H16), int(post_relu), _is_fp16(a), 0, ld_out, ld_res)
+                      int(res2 is not None and res2.dtype in H16), int(post_relu), _is_fp16(a), 0, ld_out, ld_res, _ptr(frame_stats))
+        if frame_stats is not None:
+            _chk(frame_stats, torch.float32, "frame_stats")
+            assert M % 64 == 0 and N % 256 == 0 and tuple(frame_stats.shape) == (M // 64, 4 * N // 256, 2)
         self._call("npvp_gemm_bf16", a.data_ptr(), lda, w.data_ptr(), ldw, M, N, K, C.byref(ep),
                    self.gemm_backend if backend is None else backend, self._stream())
 
@@ -276,6 +282,12 @@ class Ops:
         frames, Ch = stats.shape[0], h.shape[-1]
         assert h.numel() == frames * 64 * Ch
         self._call("npvp_ffn_frame_stats", h.data_ptr(), stats.data_ptr(), frames, Ch, self._stream())
+
+    def ffn_stats_finalize(self, partial, stats, elems_per_frame):
+        _chk(partial, torch.float32, "partial"); _chk(stats, torch.float32, "stats")
+        frames, P = partial.shape[0], partial.shape[1]
+        assert partial.shape == (frames, P, 2) and stats.shape == (frames, 2)
+        self._call("npvp_ffn_stats_finalize", partial.data_ptr(), P, stats.data_ptr(), frames, int(elems_per_frame), self._stream())
 
     def ffn_dwconv(self, h, stats1, n1w, n1b, dw_w, dw_b, y, partial2):
         _chk(h, torch.bfloat16, "h"); _chk(y, torch.bfloat16, "y")

@@ -136,6 +136,7 @@ struct EpiParams {
   float alpha;
   int act, res1_bf16, res2_bf16, post_relu, fp16;
   int64_t ld_out, ld_res;
+  float* frame_stats;  // see npvp_epilogue_t
 };
 
 __device__ __forceinline__ float epi_value(const EpiParams& e, float acc, int64_t m, int64_t n) {
@@ -164,5 +165,6 @@ static inline EpiParams make_epi(const npvp_epilogue_t* ep) {
   e.post_relu = ep->post_relu;
   e.ld_out = ep->ld_out;
   e.ld_res = ep->ld_res;
+  e.frame_stats = ep->frame_stats;
   return e;
 }

@@ -297,7 +297,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 constexpr int kGemm2Threads = 384;
 constexpr int kEpiWarps = 8;
 
-// RES: 0 none, 1 res1 fp32, 2 res1 16-bit, 3 res1 + res2 16-bit, -1 run-time.   OUT: 0 16-bit, 1 fp32, 2 both, -1 run-time.
+// RES: 0 none, 1 res1 fp32, 2 res1 16-bit, 3 res1 + res2 16-bit, -1 run-time.   OUT: 0 16-bit, 1 fp32, 2 both, -1 run-time,
+// 3 16-bit stored straight from the accumulator layout (opt-in), 4 16-bit + per-frame partial statistics (EpiParams::frame_stats).
+constexpr int kOutStats16 = 4;
 template <int BN>
 struct Gemm2Cfg {
   static constexpr int kABytes = kBM * kBK * 2;
@@ -376,7 +378,8 @@ __device__ __forceinline__ void add_res(float4& q, const void* res, int is16, in
 // rows serialised at ~100 cycles each and the epilogue - not the 98 %-of-peak main loop - set the tile time.)
 template <int ACT, int RES, int OUT, bool FP16>
 __device__ __forceinline__ void epi_chunk(uint32_t stg_addr, int sub_row, int chunk, int64_t m_base, int64_t M, bool col_ok,
-                                          int64_t n, const float4 b4, float alpha, float relu_floor, const EpiParams& ep) {
+                                          int64_t n, const float4 b4, float alpha, float relu_floor, const EpiParams& ep,
+                                          float& st_s, float& st_q) {
   constexpr int fp16 = FP16 ? 1 : 0;
   float4 q[8];
 #pragma unroll
@@ -411,6 +414,10 @@ __device__ __forceinline__ void epi_chunk(uint32_t stg_addr, int sub_row, int ch
     v.w = act_ct<ACT>(v.w + b4.w, ep.act) * alpha;
     if (RES != 0) { v.x += rs[it].x; v.y += rs[it].y; v.z += rs[it].z; v.w += rs[it].w; }
     v.x = fmaxf(v.x, relu_floor); v.y = fmaxf(v.y, relu_floor); v.z = fmaxf(v.z, relu_floor); v.w = fmaxf(v.w, relu_floor);
+    if (OUT == kOutStats16) {                                        // every row / column is valid on this path (M % 64 == N % 256 == 0)
+      st_s += (v.x + v.y) + (v.z + v.w);
+      st_q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, st_q))));
+    }
   }
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
@@ -418,7 +425,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t stg_addr, int sub_row, int ch
     if (m < M && col_ok) {
       const int64_t ooff = m * ep.ld_out + n;
       if (OUT == 1 || OUT == 2 || (OUT < 0 && ep.out_f32)) *reinterpret_cast<float4*>(ep.out_f32 + ooff) = q[it];
-      if (OUT == 0 || OUT == 2 || (OUT < 0 && ep.out_bf16))
+      if (OUT == 0 || OUT == 2 || OUT == kOutStats16 || (OUT < 0 && ep.out_bf16))
         *reinterpret_cast<uint2*>(ep.out_bf16 + ooff) = make_uint2(pack_h16x2(q[it].x, q[it].y, fp16), pack_h16x2(q[it].z, q[it].w, fp16));
     }
   }
@@ -694,6 +701,7 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const int64_t m_base = (int64_t)m_blk * kBM + quad * 32;
+      float st_s = 0.f, st_q = 0.f;                                  // OUT == kOutStats16 only
 #pragma unroll 1
       for (int c = half * kColsPerWarp; c < (half + 1) * kColsPerWarp; c += 32) {
         const float4 b4 = b_next;
@@ -710,14 +718,25 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int64_t n = n0 + chunk * 4;
         const bool col_ok = n < N;                                   // N % 4 == 0 on this path
         // (residuals may alias the output - in-place residual-stream update - so epi_chunk loads them before any store)
-        if (fp16) epi_chunk<ACT, RES, OUT, true>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep);
-        else      epi_chunk<ACT, RES, OUT, false>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep);
+        if (fp16) epi_chunk<ACT, RES, OUT, true>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep, st_s, st_q);
+        else      epi_chunk<ACT, RES, OUT, false>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep, st_s, st_q);
         __syncwarp();
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (OUT == kOutStats16) {
+        // this warp's 32 rows x 128 columns lie inside one 64-row frame: one (sum, sum of squares) slot per warp and tile
+        st_s = warp_sum(st_s);
+        st_q = warp_sum(st_q);
+        if (lane == 0 && m_base < M) {                               // (the last tile may hold a single frame)
+          const int64_t frame = (int64_t)m_blk * 2 + (quad >> 1);
+          const int slot = ((n_blk * 2 + half) << 1) + (quad & 1);
+          float2* dst = reinterpret_cast<float2*>(ep.frame_stats) + frame * (n_tiles * 4) + slot;
+          *dst = make_float2(st_s, st_q);
+        }
+      }
     }
   }
   __syncthreads();
@@ -901,6 +920,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const int64_t m_base = (int64_t)m_blk * 2 * kBM + (int64_t)rank * kBM + quad * 32;
+      float st_s = 0.f, st_q = 0.f;                                  // (frame statistics are a 1-CTA kernel feature)
 #pragma unroll 1
       for (int c = half * kColsPerWarp; c < (half + 1) * kColsPerWarp; c += 32) {
         const float4 b4 = b_next;
@@ -916,8 +936,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         __syncwarp();
         const int64_t n = n0 + chunk * 4;
         const bool col_ok = n < N;
-        if (fp16) epi_chunk<ACT, RES, OUT, true>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep);
-        else      epi_chunk<ACT, RES, OUT, false>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep);
+        if (fp16) epi_chunk<ACT, RES, OUT, true>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep, st_s, st_q);
+        else      epi_chunk<ACT, RES, OUT, false>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep, st_s, st_q);
         __syncwarp();
       }
       ptx::tc_fence_before();
@@ -1097,6 +1117,12 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
 #undef NPVP_V2_CONV
     return launch_v2_inst<BN, -1, -1, -1, 1>(ta, tb, M, N, K, e, cg0, grid, st);
   }
+  if (e.frame_stats) {
+    if (BN == 256 && act == NPVP_ACT_NONE && res == 0 && out == 0)
+      return launch_v2_inst<256, NPVP_ACT_NONE, 0, kOutStats16, 0>(ta, tb, M, N, K, e, cg0, grid, st);
+    npvp_set_error("gemm: frame_stats needs the 256-wide tile, act NONE, no residual, 16-bit output only");
+    return NPVP_ERR_INVALID;
+  }
   if (direct) {
     if (act == NPVP_ACT_NONE) return launch_v2_inst<BN, NPVP_ACT_NONE, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, grid, st);
     if (act == NPVP_ACT_GELU) return launch_v2_inst<BN, NPVP_ACT_GELU, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, grid, st);
@@ -1181,12 +1207,21 @@ extern "C" int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
       if (sub.res2) sub.res2 = (const char*)sub.res2 + m0 * sub.ld_res * (sub.res2_bf16 ? 2 : 4);
       if (sub.out_f32) sub.out_f32 = (char*)sub.out_f32 + m0 * sub.ld_out * 4;
       if (sub.out_bf16) sub.out_bf16 = (char*)sub.out_bf16 + m0 * sub.ld_out * 2;
+      if (sub.frame_stats) sub.frame_stats += (m0 / 64) * (N / 256) * 4 * 2;
       int rc = npvp_gemm_bf16((const char*)A + m0 * lda * 2, lda, W, ldw, rows, N, K, &sub, backend, stream);
       if (rc) return rc;
     }
     return NPVP_OK;
   }
   EpiParams e = make_epi(ep);
+  if (ep->frame_stats) {                        // fused per-frame statistics: one fixed route (persistent 1-CTA kernel, 256-wide tiles)
+    NPVP_REQUIRE(M % 64 == 0 && N % 256 == 0 && ep->out_bf16 && !ep->out_f32 && !ep->res1 && !ep->res2 && ep->act == NPVP_ACT_NONE,
+                 "npvp_gemm_bf16: frame_stats needs M %% 64 == 0, N %% 256 == 0, 16-bit output only, act NONE, no residuals");
+    NPVP_REQUIRE(backend == NPVP_GEMM_AUTO || backend == NPVP_GEMM_TCGEN05, "npvp_gemm_bf16: frame_stats is implemented by the default back-end only");
+    NPVP_REQUIRE(tma_compatible(A, lda, W, ldw, K) && ep->ld_out % 8 == 0 && (uintptr_t)ep->out_bf16 % 16 == 0 && K >= kBK,
+                 "npvp_gemm_bf16: frame_stats needs TMA-compatible operands");
+    return launch_tcgen05_v2<256>(A, lda, W, ldw, M, N, K, e, st);
+  }
   const bool vec_ok = (ep->ld_out % 8 == 0) && (!ep->out_f32 || (uintptr_t)ep->out_f32 % 16 == 0) &&
                       (!ep->out_bf16 || (uintptr_t)ep->out_bf16 % 16 == 0);
   // AUTO: tensor path whenever the operands are TMA-expressible.  The choice must not depend on M (the batch), otherwise a

@@ -413,6 +413,29 @@ extern "C" int npvp_ffn_frame_stats(const void* h_bf16, float* stats, int64_t fr
   return NPVP_OK;
 }
 
+// (mean, rstd) of a frame from the partial sums a GEMM epilogue left behind (npvp_epilogue_t.frame_stats): one thread per frame
+__global__ void ffn_stats_finalize_kernel(const float2* __restrict__ partial, int P, float* __restrict__ stats, int64_t frames, double inv_n) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= frames) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < P; ++k) {
+    const float2 v = __ldg(partial + f * P + k);
+    s += (double)v.x;
+    q += (double)v.y;
+  }
+  const double mean = s * inv_n;
+  stats[2 * f] = (float)mean;
+  stats[2 * f + 1] = (float)(1.0 / sqrt(fmax(q * inv_n - mean * mean, 0.0) + (double)kEps));
+}
+
+extern "C" int npvp_ffn_stats_finalize(const float* partial, int64_t P, float* stats, int64_t frames, int64_t elems_per_frame, void* stream) {
+  NPVP_REQUIRE(partial && stats && P > 0 && frames > 0 && elems_per_frame > 0, "npvp_ffn_stats_finalize: bad arguments");
+  ffn_stats_finalize_kernel<<<(unsigned)ceil_div64(frames, 128), 128, 0, (cudaStream_t)stream>>>((const float2*)partial, (int)P, stats, frames,
+                                                                                                 1.0 / (double)elems_per_frame);
+  NPVP_LAUNCH_CHECK("ffn_stats_finalize_kernel");
+  return NPVP_OK;
+}
+
 // depthwise 3x3, zero padding 1, on an 8x8 map held in registers (a[p], p = y*8+x); taps w[ky*3+kx]
 __device__ __forceinline__ float dw3x3_at(const float (&a)[64], const float (&w)[9], float bias, int y, int x) {
   float acc = bias;

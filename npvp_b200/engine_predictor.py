@@ -211,8 +211,9 @@ class PredictorEngine:
         h3 = ws.bf16(f"h3_{tag}", M, C)       # 16-bit is enough: h3 is re-normalised by LayerNorm((C,8,8)) immediately
         st1 = ws.f32(f"st1_{tag}", frames, 2)
         pt2 = ws.f32(f"pt2_{tag}", frames, w.hid // _lib.FFN_CHUNK, 2)
-        op.gemm(a_bf, w.w1, bias=w.b1, out_bf16=h1)
-        op.ffn_frame_stats(h1, st1)
+        pt1 = ws.f32(f"pt1_{tag}", frames, 4 * w.hid // 256, 2)
+        op.gemm(a_bf, w.w1, bias=w.b1, out_bf16=h1, frame_stats=pt1)     # LayerNorm((hid,8,8)) statistics from the fc1 epilogue
+        op.ffn_stats_finalize(pt1, st1, 64 * w.hid)
         op.ffn_dwconv(h1, st1, w.n1w, w.n1b, w.dw_w, w.dw_b, y2, pt2)
         op.ffn_norm2(y2, pt2, w.n2w, w.n2b, h1)                 # h1 is dead: reuse it for GELU(LN2(.))
         op.gemm(h1, w.w2, bias=w.b2, out_bf16=h3)

@@ -52,7 +52,7 @@ class SpecOps:
 
     # -- contractions ---------------------------------------------------------------------------
     def gemm(self, a, w, *, bias=None, act=ACT_NONE, alpha=1.0, res1=None, res2=None, out_f32=None, out_bf16=None,
-             post_relu=False, backend=None):
+             post_relu=False, backend=None, frame_stats=None):
         self.launches += 1
         assert a.dtype in (torch.bfloat16, torch.float16) and w.dtype == a.dtype
         v = a.float() @ w.float().t()
@@ -69,6 +69,12 @@ class SpecOps:
             out_f32.copy_(v)
         if out_bf16 is not None:
             out_bf16.copy_(v.clamp(-65504, 65504).to(out_bf16.dtype))
+        if frame_stats is not None:
+            # same slot layout as the kernel: slot = ((n_tile * 2 + column half) * 2 + row half), blocks of 32 rows x 128 columns
+            M, N = v.shape
+            blk = v.reshape(M // 64, 2, 32, N // 256, 2, 128).permute(0, 3, 4, 1, 2, 5).reshape(M // 64, 4 * N // 256, 32 * 128)
+            frame_stats[:, :, 0] = blk.sum(-1)
+            frame_stats[:, :, 1] = (blk * blk).sum(-1)
 
     def conv_gemm(self, x, w, frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo, phase_major=False, **epi):
         col = torch.empty(frames * Ho * Wo, KH * KW * Cc, dtype=x.dtype, device=x.device)
@@ -151,6 +157,13 @@ class SpecOps:
         var = (hh * hh).mean(-1) - mean * mean
         stats[:, 0] = mean.float()
         stats[:, 1] = (1.0 / torch.sqrt(var.clamp_min(0) + EPS)).float()
+
+    def ffn_stats_finalize(self, partial, stats, elems_per_frame):
+        self.launches += 1
+        s = partial[:, :, 0].double().sum(-1) / elems_per_frame
+        q = partial[:, :, 1].double().sum(-1) / elems_per_frame
+        stats[:, 0] = s.float()
+        stats[:, 1] = (1.0 / torch.sqrt((q - s * s).clamp_min(0) + EPS)).float()
 
     def ffn_dwconv(self, h, stats1, n1w, n1b, dw_w, dw_b, y, partial2):
         self.launches += 1

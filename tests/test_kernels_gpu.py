@@ -94,6 +94,29 @@ def test_gemm_direct_epilogue_matches_staged(op, M, N, K, act, dt):
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("M,N,K", [(640, 2048, 512), (128, 256, 64), (1216, 512, 192)])
+def test_gemm_frame_stats(op, spec, M, N, K):
+    """fc1 epilogue leaves per-frame partial (sum, sumsq); finalised they must match a separate pass over the output."""
+    a, w = rn(M, K, seed=1, dtype=torch.bfloat16), rn(N, K, seed=2, scale=K ** -0.5, dtype=torch.bfloat16)
+    bias = rn(N, seed=3) + 0.3
+    res = []
+    for o in (op, spec):
+        out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        pt = torch.full((M // 64, 4 * N // 256, 2), float("nan"), device=DEV)
+        st = torch.empty(M // 64, 2, device=DEV)
+        o.gemm(a, w, bias=bias, out_bf16=out, frame_stats=pt)
+        o.ffn_stats_finalize(pt, st, 64 * N)
+        res.append((out, pt, st))
+    close(res[0][0], res[1][0], 1e-2, "gemm out")
+    close(res[0][1], res[1][1], 2e-3, "partials")
+    close(res[0][2], res[1][2], 1e-4, "finalised stats")
+    ref = torch.empty(M // 64, 2, device=DEV)
+    spec.ffn_frame_stats(res[0][0].reshape(M // 64, 64, N), ref)       # statistics of the rounded output, second pass
+    close(res[0][2], ref, 2e-3, "stats vs second pass")
+    with pytest.raises(RuntimeError):
+        op.gemm(a, w, bias=bias, act=2, out_bf16=res[0][0], frame_stats=res[0][1])
+
+
 def test_gemm_f32_and_fourier(op, spec):
     a, w, b = rn(700, 512, seed=1), rn(256, 512, seed=2, scale=0.05), rn(256, seed=3)
     o1, o2 = torch.empty(700, 256, device=DEV), torch.empty(700, 256, device=DEV)
