@@ -1218,7 +1218,7 @@ extern "C" int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
     NPVP_REQUIRE(M % 64 == 0 && N % 256 == 0 && ep->out_bf16 && !ep->out_f32 && !ep->res1 && !ep->res2 && ep->act == NPVP_ACT_NONE,
                  "npvp_gemm_bf16: frame_stats needs M %% 64 == 0, N %% 256 == 0, 16-bit output only, act NONE, no residuals");
     NPVP_REQUIRE(backend == NPVP_GEMM_AUTO || backend == NPVP_GEMM_TCGEN05, "npvp_gemm_bf16: frame_stats is implemented by the default back-end only");
-    NPVP_REQUIRE(tma_compatible(A, lda, W, ldw, K) && ep->ld_out % 8 == 0 && (uintptr_t)ep->out_bf16 % 16 == 0 && K >= kBK,
+    NPVP_REQUIRE(tma_compatible(A, lda, W, ldw, K) && ep->ld_out % 8 == 0 && (uintptr_t)ep->out_bf16 % 16 == 0,
                  "npvp_gemm_bf16: frame_stats needs TMA-compatible operands");
     return launch_tcgen05_v2<256>(A, lda, W, ldw, M, N, K, e, st);
   }
@@ -1227,7 +1227,7 @@ extern "C" int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   // AUTO: tensor path whenever the operands are TMA-expressible.  The choice must not depend on M (the batch), otherwise a
   // clip would be computed differently alone and inside a batch; TMA zero-fills boxes that overhang small operands.
   if (backend == NPVP_GEMM_AUTO)
-    backend = (tma_compatible(A, lda, W, ldw, K) && vec_ok && K >= kBK) ? NPVP_GEMM_TCGEN05 : NPVP_GEMM_SIMT;
+    backend = (tma_compatible(A, lda, W, ldw, K) && vec_ok) ? NPVP_GEMM_TCGEN05 : NPVP_GEMM_SIMT;   // K < 64: TMA zero-fills the k-block
   if (backend == NPVP_GEMM_TCGEN05 || backend == NPVP_GEMM_TCGEN05_V1 || backend == NPVP_GEMM_TCGEN05_2CTA) {
     NPVP_REQUIRE(tma_compatible(A, lda, W, ldw, K) && vec_ok, "npvp_gemm_bf16: operands not 16-byte aligned / K,ld not multiples of 8 for the TMA path");
     const bool res_ok = (!(ep->res1 || ep->res2)) || (ep->ld_res % 4 == 0 && (uintptr_t)ep->res1 % 16 == 0 && (uintptr_t)ep->res2 % 16 == 0);

@@ -163,6 +163,29 @@ class PredictorEngine:
             op.gemm_f32(cur, self.nr_gamma[0], self.nr_gamma[1], ACT_NONE, gamma)
         return beta, gamma
 
+    def positional_async(self, oc, pc):
+        """Fork: compute both positional codes on a side stream (ordered after everything already queued on the current
+        stream, so the previous forward has finished with the buffers).  ``run`` joins.  Works under CUDA-graph capture,
+        where it becomes a parallel branch of the graph."""
+        cur = torch.cuda.current_stream(self.device)
+        side = self.__dict__.get("_pos_stream")
+        if side is None:
+            side = self._pos_stream = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            bo = self.positional(oc, "o")
+            bp = self.positional(pc, "p")
+        self._pos_pending = (oc, pc, bo, bp, side)
+
+    def _positional_pair(self, oc, pc):
+        pend = self.__dict__.pop("_pos_pending", None)
+        if pend is not None and pend[0] is oc and pend[1] is pc:
+            torch.cuda.current_stream(self.device).wait_stream(pend[4])      # join
+            return pend[2], pend[3]
+        if pend is not None:                                                  # stale prefetch (coordinates replaced): still join
+            torch.cuda.current_stream(self.device).wait_stream(pend[4])
+        return self.positional(oc, "o"), self.positional(pc, "p")
+
     # ------------------------------------------------------------------------------------------
     # building blocks (x: fp32 residual stream [M,512], updated in place)
     # ------------------------------------------------------------------------------------------
@@ -346,8 +369,7 @@ class PredictorEngine:
         assert oc.shape[0] == To * TOK, f"observed_coor has {oc.shape[0] // TOK} timestamps but the input has {To} frames"
         Tp = pc.shape[0] // TOK
         assert Tp <= 32 and To <= 32, "temporal attention kernels hold at most 32 timestamps per sequence"
-        beta_o, gamma_o = self.positional(oc, "o")
-        beta_p, gamma_p = self.positional(pc, "p")
+        (beta_o, gamma_o), (beta_p, gamma_p) = self._positional_pair(oc, pc)
         mem, mem_bf = self.encode(x, beta_o, gamma_o, n, To)
         evt = self.ws.f32("evt", n * TOK, C)
         _lib.ops().temporal_mean(mem, evt, n, To)

@@ -84,6 +84,7 @@ class NPVPInference(nn.Module):
     def _predict_eager(self, past_frames, eps):
         self.predictor.injected_eps = eps
         try:
+            self.predictor.prefetch_positional()       # side stream: overlaps with the frame encoder
             feats = self.VPTR_Enc.forward_tokens(past_frames)
             pred = self.predictor.forward_tokens(feats, out16=self.VPTR_Dec._engine().dt)
             return self.VPTR_Dec.forward_tokens(pred)

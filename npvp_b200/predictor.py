@@ -122,6 +122,12 @@ class Predictor(_EngineModule):
         self._coords_ready()
         return self._engine().run(observed_tokens, channels_last=True, out16=out16)
 
+    def prefetch_positional(self):
+        """Start the NRMLP positional code (input independent: 8 small fp32 GEMMs on a handful of SMs) on a side stream.
+        Callers that run other work first - the pipeline runs the frame encoder - overlap it; the next forward joins."""
+        self._coords_ready()
+        self._engine().positional_async(self.observed_coor, self.predict_coor)
+
     def evt_coding_forward(self, x, pos_beta, pos_gamma):
         """EVT_Former + temporal mean (Predictor.py:337-350).  x (N,T,C,H,W); pos_beta/gamma (T*H*W, C)."""
         self._guard(x)
