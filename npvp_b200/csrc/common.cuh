@@ -60,6 +60,31 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-u, ex2_approx(p), r);
 }
 
+// the same GELU on 8 values with the 8 Horner chains interleaved step by step (for kernels with few warps per scheduler)
+__device__ __forceinline__ void gelu_erf_x8(float (&x)[8]) {
+  float u[8], p[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { u[j] = fminf(fabsf(x[j]), 5.5f); p[j] = fmaf(3.309290792e-05f, u[j], -7.692205073e-04f); }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p[j] = fmaf(p[j], u[j], 8.080719144e-03f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p[j] = fmaf(p[j], u[j], -5.341210813e-02f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p[j] = fmaf(p[j], u[j], -4.587709705e-01f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p[j] = fmaf(p[j], u[j], -1.151201703e+00f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p[j] = fmaf(p[j], u[j], -9.999930609e-01f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p[j] = ex2_approx(p[j]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x[j]));
+    x[j] = fmaf(-u[j], p[j], r);
+  }
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == NPVP_ACT_RELU) return fmaxf(v, 0.0f);
   if (act == NPVP_ACT_GELU) return gelu_erf(v);

@@ -458,50 +458,86 @@ __device__ __forceinline__ float dw3x3_at(const float (&a)[64], const float (&w)
 // read per frame from L2 they, not HBM, bounded the first version (146 us per 640 frames, 2.8x the HBM time).  Here a block
 // owns kFfnChunk channels, parks their 64 x 2 parameters in shared memory once (each thread only ever reads its own
 // column, so no barrier is needed) and walks over frames blockIdx.y, blockIdx.y + gridDim.y, ...
-constexpr int kFfnChunk = 128;
+constexpr int kFfnChunk = 128;                                    // channels per block
+constexpr int kFfnGroups = 5;                                     // frames in flight per block (128 threads each)
 template <int CH>                                                 // CH > 0: compile-time channel count (row stride becomes an immediate)
-__global__ void __launch_bounds__(kFfnChunk)
+__global__ void __launch_bounds__(kFfnChunk * kFfnGroups, 1)
 ffn_dwconv_kernel(const bf16* __restrict__ h, const float* __restrict__ stats1, const float* __restrict__ n1w,
                   const float* __restrict__ n1b, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
                   bf16* __restrict__ y, float* __restrict__ partial2, int Ch_rt, int frames) {
+  // The 64 KB of LayerNorm parameters of a 128-channel chunk are shared by kFfnGroups groups of 128 threads, each walking
+  // over its own frames: 20 warps per SM instead of the 12 that three independent 128-thread blocks (3 x 64 KB) allowed -
+  // the kernel is bound by per-warp instruction latency (r01 ncu: 2.9 warps per scheduler, 52% issue slots used).
   extern __shared__ float2 ffn_wb[];                             // [64 px][kFfnChunk] (weight, bias)
-  __shared__ float red[64];
+  __shared__ float red[2][kFfnGroups][8];
   const int Ch = CH > 0 ? CH : Ch_rt;
-  const int c = blockIdx.x * kFfnChunk + threadIdx.x;
-#pragma unroll 8
-  for (int p = 0; p < 64; ++p)
-    ffn_wb[p * kFfnChunk + threadIdx.x] = make_float2(__ldg(n1w + (size_t)p * Ch + c), __ldg(n1b + (size_t)p * Ch + c));
+  const int grp = threadIdx.x / kFfnChunk, tc = threadIdx.x % kFfnChunk, gw = tc >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kFfnChunk + tc;
+  for (int i = threadIdx.x; i < kTok * kFfnChunk; i += kFfnChunk * kFfnGroups) {
+    const int p = i / kFfnChunk, cc = i % kFfnChunk;
+    const size_t off = (size_t)p * Ch + blockIdx.x * kFfnChunk + cc;
+    ffn_wb[i] = make_float2(__ldg(n1w + off), __ldg(n1b + off));
+  }
   float w[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) w[k] = __ldg(dw_w + (size_t)k * Ch + c);
   const float bias = __ldg(dw_b + c);
-  for (int f = blockIdx.y; f < frames; f += gridDim.y) {
+  __syncthreads();
+  int it = 0;
+  for (int f = blockIdx.y * kFfnGroups + grp; f < frames; f += gridDim.y * kFfnGroups, it ^= 1) {
     const float rstd = __ldg(stats1 + 2 * f + 1), nmr = -__ldg(stats1 + 2 * f) * rstd;
     float a[64];
     const bf16* src = h + (size_t)f * kTok * Ch + c;
 #pragma unroll
     for (int p = 0; p < 64; ++p) a[p] = __bfloat162float(src[(size_t)p * Ch]);
 #pragma unroll
-    for (int p = 0; p < 64; ++p) {
-      const float2 wb = ffn_wb[p * kFfnChunk + threadIdx.x];
-      a[p] = gelu_erf(fmaf(fmaf(a[p], rstd, nmr), wb.x, wb.y));   // LN1 affine in two FMAs
+    for (int r = 0; r < 8; ++r) {                                   // one image row (8 independent chains) at a time
+      float2 wb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wb[j] = ffn_wb[(r * 8 + j) * kFfnChunk + tc];
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(fmaf(a[r * 8 + j], rstd, nmr), wb[j].x, wb[j].y);   // LN1 affine in two FMAs
+      gelu_erf_x8(v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[r * 8 + j] = v[j];
     }
     bf16* dst = y + (size_t)f * kTok * Ch + c;
     float s = 0.f, q = 0.f;
 #pragma unroll
-    for (int yy = 0; yy < 8; ++yy)
+    for (int yy = 0; yy < 8; ++yy) {
+      float o[8];
+#pragma unroll
+      for (int xx = 0; xx < 8; ++xx) o[xx] = bias;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = yy + ky - 1;
+        if (iy < 0 || iy > 7) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int xx = 0; xx < 8; ++xx) {
+            const int ix = xx + kx - 1;
+            if (ix >= 0 && ix <= 7) o[xx] = fmaf(a[iy * 8 + ix], w[ky * 3 + kx], o[xx]);
+          }
+      }
 #pragma unroll
       for (int xx = 0; xx < 8; ++xx) {
-        const float o = dw3x3_at(a, w, bias, yy, xx);
-        dst[(size_t)(yy * 8 + xx) * Ch] = __float2bfloat16(o);
-        s += o;
-        q = fmaf(o, o, q);
+        dst[(size_t)(yy * 8 + xx) * Ch] = __float2bfloat16(o[xx]);
+        s += o[xx];
+        q = fmaf(o[xx], o[xx], q);
       }
-    block_sum2(s, q, red);
-    if (threadIdx.x == 0) {
+    }
+    // per-group reduction (the groups run different frames, so no block-wide barrier): named barrier 1 + grp, buffers
+    // alternate so a warp one iteration ahead cannot overwrite what thread 0 of the group is still reading
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) { red[it][grp][gw] = s; red[it][grp][4 + gw] = q; }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kFfnChunk) : "memory");
+    if (tc == 0) {
       float* p = partial2 + ((size_t)f * gridDim.x + blockIdx.x) * 2;
-      p[0] = s;
-      p[1] = q;
+      p[0] = (red[it][grp][0] + red[it][grp][1]) + (red[it][grp][2] + red[it][grp][3]);
+      p[1] = (red[it][grp][4] + red[it][grp][5]) + (red[it][grp][6] + red[it][grp][7]);
     }
   }
 }
@@ -516,13 +552,14 @@ static int launch_ffn_dwconv(const void* h_bf16, const float* stats1, const floa
     if (err != cudaSuccess) { npvp_set_error("ffn_dwconv: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
     attr_set = true;
   }
-  // 3 resident blocks per SM (64 KB of parameters each): one wave of blocks, each striding over the frames
+  // one resident 640-thread block per SM: a single wave of blocks, each group striding over the frames
   const int64_t chunks = Ch / kFfnChunk;
-  int64_t gy = (148 * 3) / chunks;
-  gy = gy < 1 ? 1 : (gy > frames ? frames : gy);
+  int64_t gy = 148 / chunks;
+  const int64_t gy_max = (frames + kFfnGroups - 1) / kFfnGroups;
+  gy = gy < 1 ? 1 : (gy > gy_max ? gy_max : gy);
   dim3 grid((unsigned)chunks, (unsigned)gy);
-  ffn_dwconv_kernel<CH><<<grid, kFfnChunk, smem, st>>>((const bf16*)h_bf16, stats1, n1w, n1b, dw_w, dw_b, (bf16*)y_bf16, partial2, (int)Ch,
-                                                       (int)frames);
+  ffn_dwconv_kernel<CH><<<grid, kFfnChunk * kFfnGroups, smem, st>>>((const bf16*)h_bf16, stats1, n1w, n1b, dw_w, dw_b, (bf16*)y_bf16, partial2,
+                                                                    (int)Ch, (int)frames);
   NPVP_LAUNCH_CHECK("ffn_dwconv_kernel");
   return NPVP_OK;
 }
