@@ -212,6 +212,12 @@ def run_ours(args):
         if world > 1:
             gather_frames(out, B * world)
 
+    host_out_u8 = torch.empty(host_out.shape, dtype=torch.uint8).pin_memory()
+
+    def step_e2e_u8():
+        # same call with a uint8 host buffer: pixel-space frames (VidReNormalize + clamp + uint8 on the device), D2H / 4
+        model.rollout(host_in, N_FUTURE, out_host=host_out_u8)
+
     def timed(step_fn, steps, warmup):
         for _ in range(warmup):
             step_fn()
@@ -257,6 +263,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = timed(step_e2e, max(2, min(args.steps, 10)), 1)
     e2e_steps = max(2, min(args.steps, 10))
+    e2e_u8_ms = timed(step_e2e_u8, e2e_steps, 1) if world == 1 else None
 
     roof = None
     if rank == 0:
@@ -302,7 +309,10 @@ def run_ours(args):
                        "cuda_graphs": bool(args.graphs)},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
-                    "steps": e2e_steps, "api": "NPVPInference.rollout(host_in, 28, out_host=host_out): pinned host tensors, D2H overlapped per AR block"},
+                    "steps": e2e_steps, "api": "NPVPInference.rollout(host_in, 28, out_host=host_out): pinned host tensors, D2H overlapped per AR block",
+                    "uint8_pixels": None if e2e_u8_ms is None else {
+                        "value": frames_step * e2e_steps / (e2e_u8_ms * 1e-3), "d2h_bytes_per_step": host_out_u8.numel(),
+                        "note": "same call with a uint8 out_host: frames leave the device as pixel-space bytes"}},
             "roofline": roof,
         }
         if cpu is not None:

@@ -209,6 +209,24 @@ int npvp_maxpool2x2_cols(const void* x_bf16, int64_t ldx, int col0, int Cn, void
 int npvp_nonlocal_attention(const void* q, int64_t ldq, const void* kv, void* out, int64_t frames, int HW, int HWk,
                             int dq, int dv, int fp16, void* stream);
 
+/* ---- pixel-space post-processing and evaluation metrics (the consumers of the predicted frames) ----------------
+ * Model space -> [0,1] pixel space, fp32 NCHW [n_images,C,HW]:  v = clamp(x / inv_std[c] - inv_mean[c], 0, 1), exactly
+ * the fp32 operation order of VidReNormalize + clamp (utils/dataset.py:860-886, utils/train_summary.py:243-245) with
+ * inv_std = 1/std, inv_mean = -mean (HOST arrays of C floats).  out_f32 and / or out_u8 (= trunc(v * 255), what ToPILImage
+ * writes, train_summary.py:246-248) may be NULL. */
+int npvp_frames_to_pixels(const float* frames, const float* inv_std, const float* inv_mean, float* out_f32, void* out_u8,
+                          int64_t n_images, int C, int64_t HW, void* stream);
+/* uint8 pixels NCHW -> model space fp32: ((u / 255) - mean[c]) / std[c]  (VidToTensor + VidNormalize, utils/dataset.py:835-858);
+ * mean / std are HOST arrays of C floats. */
+int npvp_pixels_to_frames(const void* in_u8, const float* mean, const float* std, float* out, int64_t n_images, int C,
+                          int64_t HW, void* stream);
+/* PSNR per image (utils/metrics.py:12-30, mean_flag=False): -10 log10(mean((x/r - y/r)^2) + 1e-8); x, y fp32 [n_images, elems]. */
+int npvp_psnr(const float* x, const float* y, float* out, int64_t n_images, int64_t elems, float data_range, void* stream);
+/* SSIM per image (utils/metrics.py:47-109, mean_flag=False): depthwise 11x11 Gaussian window, zero padding 5, mean over
+ * (C,H,W).  window11: HOST array, the normalised 1-D Gaussian (the reference's 2-D window is its outer product). */
+int npvp_ssim(const float* x, const float* y, const float* window11, float* out, int64_t n_images, int C, int H, int W,
+              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

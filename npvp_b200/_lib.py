@@ -47,6 +47,10 @@ SIGNATURES = {
     "npvp_temporal_mean": [_vp, _vp, _i64, _i64, _i64, _vp],
     "npvp_ffn_frame_stats": [_vp, _vp, _i64, _i64, _vp],
     "npvp_ffn_stats_finalize": [_vp, _i64, _vp, _i64, _i64, _vp],
+    "npvp_frames_to_pixels": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _vp],
+    "npvp_pixels_to_frames": [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _vp],
+    "npvp_psnr": [_vp, _vp, _vp, _i64, _i64, _f32, _vp],
+    "npvp_ssim": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp],
     "npvp_ffn_dwconv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_ffn_norm2": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_attention": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i64, _i32, _i32, _i32, _vp],
@@ -282,6 +286,43 @@ class Ops:
         frames, Ch = stats.shape[0], h.shape[-1]
         assert h.numel() == frames * 64 * Ch
         self._call("npvp_ffn_frame_stats", h.data_ptr(), stats.data_ptr(), frames, Ch, self._stream())
+
+    # -- pixel space / metrics ------------------------------------------------------------------
+    @staticmethod
+    def _host_f32(vals):
+        return (C.c_float * len(vals))(*[float(v) for v in vals])
+
+    def frames_to_pixels(self, frames, mean, std, out_f32=None, out_u8=None):
+        """frames fp32 (..., C, H, W) model space -> clamp(x*std+mean, 0, 1) as fp32 and / or uint8 (reference op order)."""
+        _chk(frames, torch.float32, "frames"); _chk(out_f32, torch.float32, "out_f32", False)
+        Cc, H, W = frames.shape[-3:]
+        assert len(mean) == Cc and len(std) == Cc and (out_f32 is not None or out_u8 is not None)
+        for o, dt in ((out_f32, torch.float32), (out_u8, torch.uint8)):
+            assert o is None or (o.is_cuda and o.is_contiguous() and o.dtype == dt and o.shape == frames.shape)
+        n = frames.numel() // (Cc * H * W)
+        inv_std = self._host_f32([1.0 / float(s) for s in std])
+        inv_mean = self._host_f32([-float(m) for m in mean])
+        self._call("npvp_frames_to_pixels", frames.data_ptr(), inv_std, inv_mean, _ptr(out_f32), _ptr(out_u8), n, Cc, H * W, self._stream())
+
+    def pixels_to_frames(self, u8, mean, std, out):
+        assert u8.is_cuda and u8.is_contiguous() and u8.dtype == torch.uint8
+        _chk(out, torch.float32, "out")
+        Cc, H, W = u8.shape[-3:]
+        assert len(mean) == Cc and len(std) == Cc and out.shape == u8.shape
+        self._call("npvp_pixels_to_frames", u8.data_ptr(), self._host_f32(mean), self._host_f32(std), out.data_ptr(),
+                   u8.numel() // (Cc * H * W), Cc, H * W, self._stream())
+
+    def psnr(self, x, y, out, data_range=1.0):
+        _chk(x, torch.float32, "x"); _chk(y, torch.float32, "y"); _chk(out, torch.float32, "out")
+        n = x.shape[0]
+        assert x.shape == y.shape and out.shape == (n,)
+        self._call("npvp_psnr", x.data_ptr(), y.data_ptr(), out.data_ptr(), n, x.numel() // n, float(data_range), self._stream())
+
+    def ssim(self, x, y, window11, out):
+        _chk(x, torch.float32, "x"); _chk(y, torch.float32, "y"); _chk(out, torch.float32, "out")
+        n, Cc, H, W = x.shape
+        assert x.shape == y.shape and out.shape == (n,) and len(window11) == 11
+        self._call("npvp_ssim", x.data_ptr(), y.data_ptr(), self._host_f32(window11), out.data_ptr(), n, Cc, H, W, self._stream())
 
     def ffn_stats_finalize(self, partial, stats, elems_per_frame):
         _chk(partial, torch.float32, "partial"); _chk(stats, torch.float32, "stats")

@@ -60,6 +60,12 @@ RENORM = {
 }
 
 
+# VidNormalize constants (utils/dataset.py:34-58): identical to RENORM except for KITTI, where the reference normalises and
+# re-normalises with slightly different statistics.
+NORM = dict(RENORM)
+NORM["KITTI"] = ((0.44812047, 0.47147775, 0.4677183), (1.5147436, 1.5871466, 1.5925455))
+
+
 def _preset(name, ch, hw, past, future, ngf, nd, nr, out_layer, max_T, stochastic, rand_context=False, batch=8,
             test_future=None, vfi=False):
     return _wrap({

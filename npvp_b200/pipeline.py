@@ -19,7 +19,8 @@ import torch
 import torch.nn as nn
 
 from .autoencoder import ResnetDecoder, ResnetEncoder
-from .config import RENORM, AttrDict, load_config, preset
+from . import _lib
+from .config import NORM, RENORM, AttrDict, load_config, preset
 from .predictor import Predictor
 
 
@@ -122,7 +123,9 @@ class NPVPInference(nn.Module):
 
         ``past_frames`` may be a (pinned) host tensor: it is uploaded asynchronously.  With ``out_host`` (a pinned host
         tensor (N, num_future, C, H, W)) every block's frames are streamed to the host on a copy stream while the next block
-        computes, and the caller's stream waits for the last copy before the call returns control of ``out_host``."""
+        computes, and the caller's stream waits for the last copy before the call returns control of ``out_host``.
+        A ``torch.uint8`` ``out_host`` receives pixel-space frames (``to_pixels(uint8=True)``, converted on the device block
+        by block): a quarter of the D2H bytes of the fp32 model-space frames."""
         dev = next(self.parameters()).device
         if not past_frames.is_cuda:
             past_frames = past_frames.to(dev, non_blocking=True)
@@ -131,7 +134,10 @@ class NPVPInference(nn.Module):
         copy_stream = None
         if out_host is not None:
             assert not out_host.is_cuda and out_host.shape[1] == num_future
+            assert out_host.dtype in (torch.float32, torch.uint8), "out_host must be fp32 (model space) or uint8 (pixel space)"
             copy_stream = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=dev))
+        as_u8 = out_host is not None and out_host.dtype == torch.uint8
+        out_u8 = None
         out, ctx, done, blk = None, past_frames, 0, 0
         while done < num_future:
             eps = None if eps_list is None else eps_list[blk]
@@ -140,6 +146,12 @@ class NPVPInference(nn.Module):
                 out = torch.empty((pred.shape[0], num_future) + tuple(pred.shape[2:]), dtype=pred.dtype, device=pred.device)
             take = min(Tp, num_future - done)
             out[:, done:done + take].copy_(pred[:, :take])
+            src, s0 = out, done
+            if as_u8:                                        # one kernel per block on the whole (N, Tp, C, H, W) prediction
+                mean, std = self._renorm_constants()
+                out_u8 = torch.empty(pred.shape, dtype=torch.uint8, device=pred.device)
+                _lib.ops().frames_to_pixels(pred.contiguous(), mean, std, out_u8=out_u8)
+                src, s0 = out_u8, 0
             if copy_stream is not None:                      # D2H of this block overlaps the next block's kernels
                 ready = torch.cuda.Event()
                 ready.record()
@@ -148,7 +160,9 @@ class NPVPInference(nn.Module):
                     # per-clip copies: each (take, C, H, W) slab is contiguous on both sides, so every copy is one plain
                     # async memcpy (a strided (N, take, ...) slice would make torch stage through a temporary and synchronise)
                     for i in range(out.shape[0]):
-                        out_host[i, done:done + take].copy_(out[i, done:done + take], non_blocking=True)
+                        out_host[i, done:done + take].copy_(src[i, s0:s0 + take], non_blocking=True)
+                    if as_u8:
+                        out_u8.record_stream(copy_stream)
             done += take
             blk += 1
             if Tp >= To:
@@ -161,14 +175,36 @@ class NPVPInference(nn.Module):
         return out
 
     # -- pixel space (utils/dataset.py:860-886, utils/train_summary.py:244-245) ----------------------
-    def to_pixels(self, frames):
-        """Model output -> [0,1] image space: Sigmoid outputs as is, Tanh outputs through VidReNormalize + clamp."""
+    def _renorm_constants(self):
         if self.cfg.AE.out_layer == "Sigmoid":
-            return frames.clamp(0, 1)
-        mean, std = RENORM[self.cfg.Dataset.name]
-        m = torch.tensor(mean, device=frames.device, dtype=frames.dtype).view(1, 1, -1, 1, 1)
-        s = torch.tensor(std, device=frames.device, dtype=frames.dtype).view(1, 1, -1, 1, 1)
-        return (frames * s + m).clamp(0, 1)
+            c = int(self.cfg.Dataset.img_channels)
+            return (0.0,) * c, (1.0,) * c
+        return RENORM[self.cfg.Dataset.name]
+
+    def to_pixels(self, frames, uint8: bool = False):
+        """Model output (..., C, H, W) -> [0,1] pixel space: VidReNormalize + clamp (utils/dataset.py:860-886,
+        utils/train_summary.py:243-245; Sigmoid models: clamp only); ``uint8=True`` returns what the reference writes to
+        image files (ToPILImage: trunc(v * 255)).  One CUDA kernel, reference operation order (bit-identical)."""
+        if not frames.is_cuda:
+            raise NotImplementedError("NPVPInference.to_pixels: frames must be a CUDA tensor (there is no CPU fallback)")
+        mean, std = self._renorm_constants()
+        x = frames.detach().to(torch.float32).contiguous()
+        out = torch.empty_like(x, dtype=torch.uint8 if uint8 else torch.float32)
+        _lib.ops().frames_to_pixels(x, mean, std, out_u8=out if uint8 else None, out_f32=None if uint8 else out)
+        return out
+
+    def from_pixels(self, frames_u8):
+        """uint8 frames (..., C, H, W) -> model-space fp32 input: VidToTensor + VidNormalize (utils/dataset.py:835-858)."""
+        if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8:
+            raise NotImplementedError("NPVPInference.from_pixels: expects a CUDA uint8 tensor")
+        if self.cfg.AE.out_layer == "Sigmoid":
+            mean, std = self._renorm_constants()
+        else:
+            mean, std = NORM.get(self.cfg.Dataset.name, RENORM[self.cfg.Dataset.name])
+        x = frames_u8.contiguous()
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+        _lib.ops().pixels_to_frames(x, mean, std, out)
+        return out
 
 
 class _GraphedPredict:

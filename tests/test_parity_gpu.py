@@ -13,6 +13,14 @@ pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
 
 
+
+def _ref_pixels(model, frames_cpu):
+    """Reference-side pixel space: the oracle restatement of VidReNormalize + clamp (checker only)."""
+    from oracle import post_oracle as P
+    mean, std = model._renorm_constants()
+    return P.renormalize_clamp(frames_cpu, mean, std)
+
+
 def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
 
@@ -78,7 +86,7 @@ def test_end_to_end_pixels(preset_name, N, stress):
     model.predictor.injected_eps = None
     assert rec_future is None and rec_past.shape == x.shape
     assert float((pred - out).abs().max()) < 5e-3
-    px, px_ref = model.to_pixels(out).cpu(), model.to_pixels(ref)
+    px, px_ref = model.to_pixels(out).cpu(), _ref_pixels(model, ref)
     err = float((px - px_ref).abs().max())
     gt = seeded_rand(tuple(px_ref.shape), 99)
     dpsnr = abs(float(O.psnr(px, gt)) - float(O.psnr(px_ref, gt)))
@@ -163,7 +171,7 @@ def test_kth_unified_continuous_time_tasks(task):
     model.predictor.reset_pos_coor(to_t, tp_t)
     out = model.predict(x.cuda(), eps.cuda())
     assert out.shape == (N, len(tp), 1, 64, 64)
-    err = float((model.to_pixels(out).cpu() - model.to_pixels(ref)).abs().max())
+    err = float((model.to_pixels(out).cpu() - _ref_pixels(model, ref)).abs().max())
     print(f"KTH {task}: To={len(to)} Tp={len(tp)} max pixel err {err:.3e}")
     assert err <= 1e-2
 
@@ -186,5 +194,5 @@ def test_bair_multiple_stochastic_samples():
     # the 8 samples of one clip run as one batch of 8 (clip replicated, per-sample noise)
     outs = model.predict(x.cuda().expand(8, -1, -1, -1, -1).contiguous(), torch.cat(eps).cuda())
     for i, r in enumerate(refs):
-        assert float((model.to_pixels(outs[i:i + 1]).cpu() - model.to_pixels(r)).abs().max()) <= 1e-2
+        assert float((model.to_pixels(outs[i:i + 1]).cpu() - _ref_pixels(model, r)).abs().max()) <= 1e-2
     assert float((outs[0] - outs[1]).abs().max()) > 0

@@ -1,0 +1,98 @@
+"""GPU: pixel-space post-processing and metrics kernels (through the C-ABI) against the reference fixtures and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["post_cityscapes", "post_kth", "post_smmnist"]
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+@pytest.fixture(scope="module")
+def op():
+    from npvp_b200 import _lib
+    return _lib.ops()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pixels_bit_exact_vs_reference(op, name):
+    g = load(name)
+    mean, std = g["mean"].tolist(), g["std"].tolist()
+    x = g["frames"].to(DEV)
+    f32, u8 = torch.empty_like(x), torch.empty(x.shape, dtype=torch.uint8, device=DEV)
+    op.frames_to_pixels(x, mean, std, out_f32=f32, out_u8=u8)
+    assert torch.equal(f32.cpu(), g["pix"])
+    assert torch.equal(u8.cpu(), g["u8"])
+    back = torch.empty_like(x)
+    op.pixels_to_frames(u8, mean, std, back)
+    assert float((back.cpu() - g["back"]).abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize("hw", [(128, 128), (37, 53)])
+def test_pixels_vector_and_scalar_paths_vs_oracle(op, hw):
+    from oracle import post_oracle as P
+    mean, std = (0.31604213, 0.35114038, 0.3104223), (1.2172801, 1.3219808, 1.2082524)
+    x = torch.randn(3, 2, 3, *hw, generator=torch.Generator().manual_seed(3)) * 0.7
+    f32, u8 = torch.empty_like(x, device=DEV), torch.empty(x.shape, dtype=torch.uint8, device=DEV)
+    op.frames_to_pixels(x.to(DEV), mean, std, out_f32=f32, out_u8=u8)
+    ref = P.renormalize_clamp(x, mean, std)
+    assert torch.equal(f32.cpu(), ref) and torch.equal(u8.cpu(), P.to_uint8(ref))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_metrics_vs_reference(name):
+    from npvp_b200.metrics import PSNR, SSIM
+    g = load(name)
+    n = g["pix"].shape[0] * g["pix"].shape[1]
+    x, y = g["pix"].reshape(n, *g["pix"].shape[2:]).to(DEV), g["gt"].reshape(n, *g["pix"].shape[2:]).to(DEV)
+    ps = PSNR(x, y, mean_flag=False)
+    ss = SSIM()(x, y, mean_flag=False)
+    assert float((ps.cpu() - g["psnr"]).abs().max()) <= 1e-4          # dB
+    assert float((ss.cpu() - g["ssim"]).abs().max()) <= 1e-5
+    assert abs(PSNR(x, y) - float(g["psnr"].mean())) <= 1e-4
+    assert abs(float(SSIM()(x, y)) - float(g["ssim"].mean())) <= 1e-5
+
+
+def test_metrics_full_size_properties():
+    """Full Cityscapes frame size: identical images -> SSIM 1, PSNR = 80 dB (the 1e-8 floor); symmetry; range scaling."""
+    from npvp_b200.metrics import PSNR, SSIM
+    from oracle import post_oracle as P
+    g = torch.Generator().manual_seed(5)
+    x, y = torch.rand(6, 3, 128, 128, generator=g), torch.rand(6, 3, 128, 128, generator=g)
+    xd, yd = x.to(DEV), y.to(DEV)
+    assert float((SSIM()(xd, xd, mean_flag=False) - 1).abs().max()) <= 1e-6
+    assert float((PSNR(xd, xd, mean_flag=False) - 80.0).abs().max()) <= 1e-4
+    a, b = SSIM()(xd, yd, mean_flag=False), SSIM()(yd, xd, mean_flag=False)
+    assert float((a - b).abs().max()) <= 1e-6
+    assert float((a.cpu() - P.ssim(x, y)).abs().max()) <= 1e-5
+    assert float((PSNR(xd, yd, mean_flag=False).cpu() - P.psnr(x, y)).abs().max()) <= 1e-4
+    assert float((PSNR(xd * 255, yd * 255, data_range=255, mean_flag=False) - PSNR(xd, yd, mean_flag=False)).abs().max()) <= 1e-3
+    with pytest.raises(NotImplementedError):
+        PSNR(x, y)
+
+
+def test_rollout_uint8_host_output():
+    """rollout(out_host=uint8) == to_pixels(uint8=True) of the fp32 rollout, and to_pixels matches the oracle bit for bit."""
+    from npvp_b200 import build_from_config
+    from npvp_b200.config import preset
+    from oracle import post_oracle as P
+    model = build_from_config(preset("KITTI_VFP_NPVP-S"), device=DEV, seed=0)
+    x = torch.rand(2, 4, 3, 128, 128, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    eps = [torch.randn(2, 512, 8, 8, generator=torch.Generator().manual_seed(10 + i)).to(DEV) for i in range(2)]
+    host = torch.empty(2, 7, 3, 128, 128, dtype=torch.uint8).pin_memory()
+    frames = model.rollout(x.to(DEV), 7, eps_list=eps, out_host=host)
+    torch.cuda.synchronize()
+    ref_u8 = model.to_pixels(frames, uint8=True)
+    assert torch.equal(host, ref_u8.cpu())
+    mean, std = model._renorm_constants()
+    assert torch.equal(model.to_pixels(frames).cpu(), P.renormalize_clamp(frames.cpu(), mean, std))
+    back = model.from_pixels(ref_u8)
+    assert back.shape == frames.shape and back.dtype == torch.float32
