@@ -279,8 +279,9 @@ class PredictorEngine:
     # ------------------------------------------------------------------------------------------
     # latent event code (submodules.py:388-410)
     # ------------------------------------------------------------------------------------------
-    def latent(self, evt, n, eps):
-        """evt fp32 [n*64,512] token-major -> z fp32 [n*64,512]; keeps (mu|logvar) in the workspace."""
+    def latent(self, evt, n, eps, n_samples=1):
+        """evt fp32 [n*64,512] token-major -> z fp32 [n*K*64,512]; keeps (mu|logvar) of the n clips in the workspace.
+        K > 1: the prior (mu, logvar) is computed once per clip and re-parameterised with K noise tensors."""
         op, ws, E = _lib.ops(), self.ws, self.evt
         M = n * TOK
         e1 = ws.bf16("evt_e1", M, C)
@@ -291,8 +292,14 @@ class PredictorEngine:
         op.gemm(e2, E.w3, bias=E.b3, act=ACT_RELU, out_bf16=e3)
         mulv = ws.f32("evt_mulv", M, E.w_head.shape[0])
         op.gemm(e3, E.w_head, bias=E.b_head, out_f32=mulv)
-        z = ws.f32("evt_z", M, C)
-        op.latent_reparam(mulv, eps if E.stochastic else None, z, n, C)
+        K = int(n_samples)
+        src = mulv
+        if K > 1:
+            W2 = mulv.shape[1]
+            src = ws.f32("evt_mulv_rep", M * K, W2)
+            src.view(n, K, TOK, W2).copy_(mulv.view(n, 1, TOK, W2).expand(n, K, TOK, W2))
+        z = ws.f32("evt_z", M * K, C)
+        op.latent_reparam(src, eps if E.stochastic else None, z, n * K, C)
         return z, mulv
 
     # ------------------------------------------------------------------------------------------
@@ -362,8 +369,12 @@ class PredictorEngine:
         op.tokens_to_nchw(tok.view(n * T, TOK, C), out.view(n * T, C, TOK))
         return out
 
-    def run(self, observed, channels_last=False, out16=None):
+    def run(self, observed, channels_last=False, out16=None, n_samples=1):
+        """``n_samples`` = K > 1 (NPVP-S): K stochastic futures per clip from ONE pass of the EVT_Former and the prior (only the
+        latent and the NAR decoder run per sample); the batch dimension of the result is clip-major (clip 0 sample 0..K-1, ...)."""
         mod = self.mod
+        K = int(n_samples)
+        assert K >= 1 and (K == 1 or self.stochastic), "several samples per clip only make sense for the stochastic model (NPVP-S)"
         x, n, To = self._to_tokens(observed, channels_last, "x_enc")
         oc, pc = mod.observed_coor, mod.predict_coor
         assert oc.shape[0] == To * TOK, f"observed_coor has {oc.shape[0] // TOK} timestamps but the input has {To} frames"
@@ -377,17 +388,21 @@ class PredictorEngine:
         if self.stochastic:
             eps = mod.injected_eps
             if eps is None:
-                eps = torch.randn((n, C, 8, 8), device=self.device)           # submodules.py:409
+                eps = torch.randn((n * K, C, 8, 8), device=self.device)       # submodules.py:409
             eps = eps.detach().to(self.device, torch.float32).contiguous()
-            assert tuple(eps.shape) == (n, C, 8, 8), f"latent noise must be {(n, C, 8, 8)}, got {tuple(eps.shape)}"
-        z, mulv = self.latent(evt, n, eps)
+            assert tuple(eps.shape) == (n * K, C, 8, 8), f"latent noise must be {(n * K, C, 8, 8)}, got {tuple(eps.shape)}"
+        z, mulv = self.latent(evt, n, eps, K)
         mod.last_latent = (z, mulv)
-        out, out_bf = self.decode(z, mem, mem_bf, beta_o, gamma_o, beta_p, gamma_p, n, To, Tp,
+        if K > 1:            # the decoder sees n*K clips: replicate the (small) encoder memory, clip-major
+            rep = lambda t, name, dt: self.ws.get(name, (n * K * To * TOK, C), dt).view(n, K, To * TOK, C).copy_(
+                t.view(n, 1, To * TOK, C).expand(n, K, To * TOK, C)).view(n * K * To * TOK, C)
+            mem, mem_bf = rep(mem, "mem_rep", torch.float32), rep(mem_bf, "mem_bf_rep", torch.bfloat16)
+        out, out_bf = self.decode(z, mem, mem_bf, beta_o, gamma_o, beta_p, gamma_p, n * K, To, Tp,
                                   out16=out16 or torch.bfloat16)
         if out16 is not None:   # engine-internal hand-off to the frame decoder (a view of the workspace, consumed at once)
             assert channels_last
-            return out_bf.view(n, Tp, 8, 8, C)
-        return self._from_tokens(out, n, Tp, channels_last)
+            return out_bf.view(n * K, Tp, 8, 8, C)
+        return self._from_tokens(out, n * K, Tp, channels_last)
 
     def evt_coding(self, x, pos_beta, pos_gamma):
         """Predictor.evt_coding_forward (Predictor.py:337-350): returns (memory (N,T,C,H,W), evt_coding (N,C,H,W))."""

@@ -92,6 +92,20 @@ class NPVPInference(nn.Module):
         finally:
             self.predictor.injected_eps = None
 
+    def predict_samples(self, past_frames, n_samples: int, eps: Optional[torch.Tensor] = None):
+        """NPVP-S: ``n_samples`` futures per clip -> (N, n_samples, Tp, Cimg, H, W).  The frame encoder, the EVT_Former and
+        the prior run once per clip; latent sampling, the NAR decoder and the frame decoder run per sample (BASELINE
+        config 3: 8 samples per clip).  ``eps``: optional (N*n_samples, 512, 8, 8) noise, clip-major."""
+        self.predictor.injected_eps = eps
+        try:
+            self.predictor.prefetch_positional()
+            feats = self.VPTR_Enc.forward_tokens(past_frames)
+            pred = self.predictor.forward_tokens(feats, out16=self.VPTR_Dec._engine().dt, n_samples=n_samples)
+            frames = self.VPTR_Dec.forward_tokens(pred)
+            return frames.view(past_frames.shape[0], n_samples, *frames.shape[1:])
+        finally:
+            self.predictor.injected_eps = None
+
     def use_cuda_graphs(self, enabled: bool = True):
         """Replay ``predict`` as one CUDA graph per (batch shape, timestamps, weights version): the ~430 kernel launches
         of a forward are launch-bound at small batch.  The returned tensor is then a graph-owned buffer that the next

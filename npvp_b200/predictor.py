@@ -115,12 +115,21 @@ class Predictor(_EngineModule):
                                       "Predictor.py:311-327) is not on the inference hot path")
         return self._engine().run(observed_features)
 
-    def forward_tokens(self, observed_tokens, out16=None):
-        """Engine-internal: channels-last (N,To,H,W,C) in -> channels-last (N,Tp,H,W,C) out (fp32, or the 16-bit
+    def forward_tokens(self, observed_tokens, out16=None, n_samples=1):
+        """Engine-internal: channels-last (N,To,H,W,C) in -> channels-last (N*n_samples,Tp,H,W,C) out (fp32, or the 16-bit
         workspace view of dtype ``out16`` that the frame decoder consumes directly)."""
         self._guard(observed_tokens)
         self._coords_ready()
-        return self._engine().run(observed_tokens, channels_last=True, out16=out16)
+        return self._engine().run(observed_tokens, channels_last=True, out16=out16, n_samples=n_samples)
+
+    def forward_samples(self, observed_features, n_samples: int):
+        """NPVP-S: ``n_samples`` stochastic futures per clip, (N, To, C, H, W) -> (N, n_samples, Tp, C, H, W).  Equivalent to
+        ``n_samples`` reference forwards on the same clips with different noise (``injected_eps``: (N*n_samples,512,8,8),
+        clip-major), but the EVT_Former and the prior run once."""
+        self._guard(observed_features)
+        self._coords_ready()
+        out = self._engine().run(observed_features, n_samples=n_samples)
+        return out.view(observed_features.shape[0], n_samples, *out.shape[1:])
 
     def prefetch_positional(self):
         """Start the NRMLP positional code (input independent: 8 small fp32 GEMMs on a handful of SMs) on a side stream.

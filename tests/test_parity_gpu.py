@@ -196,3 +196,14 @@ def test_bair_multiple_stochastic_samples():
     for i, r in enumerate(refs):
         assert float((model.to_pixels(outs[i:i + 1]).cpu() - _ref_pixels(model, r)).abs().max()) <= 1e-2
     assert float((outs[0] - outs[1]).abs().max()) > 0
+    # shared-encoder sampling API: one pass of Enc / EVT_Former / prior, 8 latents -> bit-identical to the replicated batch
+    # (per-clip arithmetic is batch invariant), for 2 clips x 4 samples as well
+    smp = model.predict_samples(x.cuda(), 8, torch.cat(eps).cuda())
+    assert smp.shape == (1, 8) + tuple(outs.shape[1:])
+    assert torch.equal(smp[0], outs)
+    x2 = torch.cat([x, seeded_rand((1, 2, 3, 64, 64), 6) * 2 - 1]).cuda()
+    e2 = torch.cat(eps).cuda()                      # clip-major: clip 0 gets eps[0:4], clip 1 eps[4:8]
+    smp2 = model.predict_samples(x2, 4, e2)
+    rep = model.predict(x2.repeat_interleave(4, dim=0), e2)
+    assert torch.equal(smp2.reshape(rep.shape), rep)
+    assert torch.equal(smp2[0], smp[0, :4])
