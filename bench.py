@@ -201,16 +201,12 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > 126 MB L2
 
     def step_device():
-        out = model.rollout(x_dev, N_FUTURE)
-        if world > 1:
-            out = gather_frames(out, B * world)
-        return out
+        # N > 1: the all-gather of each AR block's frames is issued asynchronously and overlaps the next block's kernels
+        return model.rollout(x_dev, N_FUTURE, gather_group=True if world > 1 else None)
 
     def step_e2e():
         # public API on host buffers: async H2D of the context frames, per-block D2H of the frames on a copy stream
-        out = model.rollout(host_in, N_FUTURE, out_host=host_out)
-        if world > 1:
-            gather_frames(out, B * world)
+        model.rollout(host_in, N_FUTURE, out_host=host_out, gather_group=True if world > 1 else None)
 
     host_out_u8 = torch.empty(host_out.shape, dtype=torch.uint8).pin_memory()
 

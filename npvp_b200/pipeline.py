@@ -131,7 +131,7 @@ class NPVPInference(nn.Module):
         return g(past_frames, eps)
 
     def rollout(self, past_frames, num_future: int, eps_list: Optional[Sequence[torch.Tensor]] = None,
-                out_host: Optional[torch.Tensor] = None):
+                out_host: Optional[torch.Tensor] = None, gather_group=None):
         """Block-autoregressive VFP: predict len(tp_list) frames, feed the last To predictions back as context
         (image space), repeat until ``num_future`` frames exist; the last block is truncated.
 
@@ -139,7 +139,12 @@ class NPVPInference(nn.Module):
         tensor (N, num_future, C, H, W)) every block's frames are streamed to the host on a copy stream while the next block
         computes, and the caller's stream waits for the last copy before the call returns control of ``out_host``.
         A ``torch.uint8`` ``out_host`` receives pixel-space frames (``to_pixels(uint8=True)``, converted on the device block
-        by block): a quarter of the D2H bytes of the fp32 model-space frames."""
+        by block): a quarter of the D2H bytes of the fp32 model-space frames.
+
+        ``gather_group`` (a ``torch.distributed`` process group, or ``True`` for the default group; every rank holds the
+        same number of clips): the frames of all ranks are all-gathered BLOCK BY BLOCK with asynchronous NCCL collectives,
+        so the exchange of block i overlaps the kernels of block i+1; the call returns the global batch
+        (world * N, num_future, C, H, W), rank-major like ``distributed.gather_frames``."""
         dev = next(self.parameters()).device
         if not past_frames.is_cuda:
             past_frames = past_frames.to(dev, non_blocking=True)
@@ -152,6 +157,11 @@ class NPVPInference(nn.Module):
             copy_stream = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=dev))
         as_u8 = out_host is not None and out_host.dtype == torch.uint8
         out_u8 = None
+        pending = []                                         # (async all-gather handle, gathered block, first frame, frames)
+        if gather_group is not None:
+            import torch.distributed as dist
+            group = None if gather_group is True else gather_group
+            world = dist.get_world_size(group)
         out, ctx, done, blk = None, past_frames, 0, 0
         while done < num_future:
             eps = None if eps_list is None else eps_list[blk]
@@ -177,6 +187,11 @@ class NPVPInference(nn.Module):
                         out_host[i, done:done + take].copy_(src[i, s0:s0 + take], non_blocking=True)
                     if as_u8:
                         out_u8.record_stream(copy_stream)
+            if gather_group is not None and world > 1:
+                # a private contiguous copy: `pred` may be a graph-owned buffer that the next block overwrites
+                mine = out[:, done:done + take].contiguous()
+                allb = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+                pending.append((dist.all_gather_into_tensor(allb, mine, group=group, async_op=True), allb, mine, done, take))
             done += take
             blk += 1
             if Tp >= To:
@@ -186,6 +201,13 @@ class NPVPInference(nn.Module):
         if copy_stream is not None:
             torch.cuda.current_stream().wait_stream(copy_stream)
             out.record_stream(copy_stream)
+        if pending:
+            n = out.shape[0]
+            full = torch.empty((world * n, num_future) + tuple(out.shape[2:]), dtype=out.dtype, device=out.device)
+            for work, allb, _mine, d0, tk in pending:
+                work.wait()                                  # current stream waits for the collective
+                full.view(world, n, num_future, *out.shape[2:])[:, :, d0:d0 + tk].copy_(allb)
+            return full
         return out
 
     # -- pixel space (utils/dataset.py:860-886, utils/train_summary.py:244-245) ----------------------

@@ -36,6 +36,16 @@ def _worker(rank, world, port, ret):
             single = model.predict(x, eps)
             ret["equal"] = bool(torch.equal(full, single))
             ret["shape"] = tuple(full.shape)
+        # block-autoregressive rollout with the per-block overlapped all-gather == rollout + one gather at the end
+        x4 = (torch.rand((4, 4, 3, 128, 128), generator=g) * 2 - 1).to(rank)
+        eps4 = [torch.randn((4, 512, 8, 8), generator=g).to(rank) for _ in range(2)]
+        l4, h4 = shard_bounds(4, rank, world)
+        el = [e[l4:h4] for e in eps4]
+        a = model.rollout(x4[l4:h4], 7, eps_list=el, gather_group=True)
+        b = gather_frames(model.rollout(x4[l4:h4], 7, eps_list=el), 4)
+        torch.cuda.synchronize()
+        if rank == 0:
+            ret["rollout_equal"] = bool(torch.equal(a, b)) and tuple(a.shape) == (4, 7, 3, 128, 128)
     finally:
         dist.destroy_process_group()
 
@@ -46,3 +56,4 @@ def test_sharded_prediction_bitwise_equal_to_single_gpu():
     mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     assert ret["shape"] == (5, 5, 3, 128, 128)
     assert ret["equal"], "gathered multi-GPU frames differ from the single-GPU batch"
+    assert ret["rollout_equal"], "per-block overlapped all-gather differs from rollout + gather_frames"
