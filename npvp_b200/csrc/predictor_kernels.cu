@@ -13,7 +13,7 @@ constexpr float kEps = 1e-5f;
 // 512-thread block (64 values per thread, 110-128 registers): one block per SM, so the load -> reduce -> compute -> store
 // chain of a frame never overlapped with anything (24% warps active, 3.5 TB/s, r01 ncu).  A frame is now owned by a
 // CLUSTER of kFrameCL blocks of 256 threads: block `rank` holds tokens 16 rank .. 16 rank + 15 (32 values per thread), the
-// whole-frame mean / variance is merged across the cluster through distributed shared memory, and four such blocks of
+// whole-frame mean / variance is merged across the cluster through distributed shared memory (st.async + mbarrier), and four such blocks of
 // different frames share an SM.
 // Thread layout: warp w of block `rank` owns tokens tok0 = 16 rank + 2 w and tok0 + 1; lane l owns channels
 // {128 j + 4 l + i}: one float4 per j => fully coalesced 512-byte warp accesses.
@@ -23,15 +23,71 @@ constexpr int kFrameThreads = kTok / kFrameCL / kTPW * 32;    // 256
 struct FrameRegs { float v[kTPW][16]; };
 
 __device__ __forceinline__ uint32_t frame_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void frame_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void frame_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ float2 ld_cluster_f2(const float2* local, uint32_t rank) {
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(local);
-  uint32_t ra;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-  float2 v;
-  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
-  return v;
+__device__ __forceinline__ void frame_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t frame_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t frame_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+
+// Cluster exchange of the per-block partial statistics.  Each block owns, per exchange e, a table slots[e][kFrameCL] and an
+// mbarrier bars[e].  Thread 0 posts its (mean, M2) into slot [e][own rank] of every PEER with st.async (a remote
+// shared-memory store that completes transaction bytes on the peer's mbarrier), writes its own entry locally and arrives
+// with expect_tx; every thread then waits on the LOCAL mbarrier and reads the LOCAL table.  Unlike barrier.cluster with
+// release / acquire semantics this does not make every thread drain its outstanding global stores first (r01 ncu: the
+// second exchange of the TAIL kernel sat behind the y / out_ln stores: stall_membar 1.8-3.8 and stall_barrier 1.6-3.5
+// issue slots per instruction).  The only cluster barrier left is the one that publishes the mbarrier initialisation at
+// kernel entry, when nothing is in flight.  No block can exit while a peer still writes into it: it has waited for all of
+// them.
+struct FrameXchg {
+  float2 slots[2][kFrameCL];
+  unsigned long long bars[2];
+};
+
+__device__ __forceinline__ void frame_xchg_init(FrameXchg& x) {
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(frame_smem_u32(&x.bars[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(frame_smem_u32(&x.bars[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  frame_cluster_sync();
+}
+
+// thread 0 of every block calls post(); all threads call wait() and then read x.slots[e][0..kFrameCL)
+__device__ __forceinline__ void frame_xchg_post(FrameXchg& x, int e, float2 v) {
+  const uint32_t me = frame_cluster_rank();
+  const uint32_t bar = frame_smem_u32(&x.bars[e]), slot = frame_smem_u32(&x.slots[e][me]);
+  x.slots[e][me] = v;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)((kFrameCL - 1) * sizeof(float2))) : "memory");
+#pragma unroll
+  for (uint32_t r = 0; r < (uint32_t)kFrameCL; ++r) {
+    if (r == me) continue;
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(frame_mapa(slot, r)), "f"(v.x),
+                 "f"(v.y), "r"(frame_mapa(bar, r))
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void frame_xchg_wait(FrameXchg& x, int e) {
+  const uint32_t bar = frame_smem_u32(&x.bars[e]);
+  uint32_t ok = 0, spins = 0;
+  long long t0 = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar)
+        : "memory");
+    if (!ok && (++spins & 0x3FFu) == 0) {                      // bounded: a lost arrival traps instead of hanging the GPU
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
 }
 
 // x: first token of this warp (row pointer arithmetic is done by the callers through tok0)
@@ -90,11 +146,9 @@ __device__ __forceinline__ void token_layernorm(float (&v)[16], const float4 (&w
 }
 
 // Mean / rstd over the whole frame.  Each block reduces its quarter with a two-pass (mean, centred sum of squares),
-// publishes (mean_k, M2_k) in `slot` of its own shared memory, and after one cluster barrier every thread merges the four
-// quarters (equal counts: M2 = sum M2_k + n_k sum (mean_k - mean)^2).  A slot is written once per kernel, so the only
-// other cluster-wide ordering needed is "nobody exits while its slot may still be read": callers arrive after their last
-// frame_stats and wait before returning (frame_cluster_arrive / frame_cluster_wait).
-__device__ __forceinline__ void frame_stats(const FrameRegs& r, float* red, float2* slot, float& mean, float& rstd) {
+// exchanges (mean_k, M2_k) with its three peers (frame_xchg_*), and every thread merges the four quarters
+// (equal counts: M2 = sum M2_k + n_k sum (mean_k - mean)^2).
+__device__ __forceinline__ void frame_stats(const FrameRegs& r, float* red, FrameXchg& xc, int e, float& mean, float& rstd) {
   constexpr float inv_nk = 1.0f / (kTok / kFrameCL * kC);
   float s = 0.f, dummy = 0.f;
 #pragma unroll
@@ -110,12 +164,11 @@ __device__ __forceinline__ void frame_stats(const FrameRegs& r, float* red, floa
 #pragma unroll
     for (int i = 0; i < 16; ++i) { const float d = r.v[t][i] - mk; q = fmaf(d, d, q); }
   block_sum2(q, dummy, red);
-  if (threadIdx.x == 0) *slot = make_float2(mk, q);
-  frame_cluster_arrive();
-  frame_cluster_wait();
+  if (threadIdx.x == 0) frame_xchg_post(xc, e, make_float2(mk, q));
+  frame_xchg_wait(xc, e);
   float2 part[kFrameCL];
 #pragma unroll
-  for (int k = 0; k < kFrameCL; ++k) part[k] = ld_cluster_f2(slot, k);
+  for (int k = 0; k < kFrameCL; ++k) part[k] = xc.slots[e][k];
   float m = 0.f;
 #pragma unroll
   for (int k = 0; k < kFrameCL; ++k) m += part[k].x;
@@ -130,7 +183,7 @@ __device__ __forceinline__ void frame_stats(const FrameRegs& r, float* red, floa
 // a = LN(x); u = a + qe; fused = GN1(u) * (1 + gamma) + beta
 // ---------------------------------------------------------------------------------------------
 // r holds this block's quarter of the frame in fp32; applies the optional token LayerNorm, writes `a`, then the positional fuse.
-__device__ __forceinline__ void posfuse_from_regs(FrameRegs& r, float* red, float2* slot, int f, int T, const float* __restrict__ ln_w,
+__device__ __forceinline__ void posfuse_from_regs(FrameRegs& r, float* red, FrameXchg& xc, int f, int T, const float* __restrict__ ln_w,
                                                   const float* __restrict__ ln_b, const float* __restrict__ qe,
                                                   const float* __restrict__ beta, const float* __restrict__ gamma,
                                                   bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int tok0, int lane) {
@@ -159,7 +212,7 @@ __device__ __forceinline__ void posfuse_from_regs(FrameRegs& r, float* red, floa
     }
   }
   float mean, rstd;
-  frame_stats(r, red, slot, mean, rstd);
+  frame_stats(r, red, xc, 1, mean, rstd);
 #pragma unroll
   for (int t = 0; t < kTPW; ++t) {
     const size_t off = ((size_t)t_idx * kTok + tok0 + t) * kC;
@@ -200,15 +253,14 @@ ln_posfuse_kernel(float* __restrict__ x, const bf16* __restrict__ delta, const f
                   const float* __restrict__ qe, const float* __restrict__ beta, const float* __restrict__ gamma,
                   bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int T) {
   __shared__ float red[64];
-  __shared__ float2 slots[2];
+  __shared__ __align__(8) FrameXchg xc;
+  frame_xchg_init(xc);
   const int f = blockIdx.x / kFrameCL, lane = threadIdx.x & 31;
   const int tok0 = (int)frame_cluster_rank() * (kTok / kFrameCL) + (threadIdx.x >> 5) * kTPW;
   FrameRegs r;
   frame_load(x + (size_t)f * kTok * kC, r, tok0, lane);
   if (delta) frame_add_delta(x + (size_t)f * kTok * kC, delta + (size_t)f * kTok * kC, r, tok0, lane);
-  posfuse_from_regs(r, red, &slots[1], f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, tok0, lane);
-  frame_cluster_arrive();                                     // keep `slots` alive until every block of the frame has read them
-  frame_cluster_wait();
+  posfuse_from_regs(r, red, xc, f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, tok0, lane);
 }
 
 extern "C" int npvp_ln_posfuse(const float* x, const float* ln_w, const float* ln_b, const float* qe, const float* beta,
@@ -301,14 +353,15 @@ frame_ln_gelu_residual_kernel(const void* __restrict__ h, int h_is_bf16, const f
                               const float* __restrict__ qe, const float* __restrict__ beta, const float* __restrict__ gamma,
                               bf16* __restrict__ out_ln, bf16* __restrict__ out_fused) {
   __shared__ float red[64];
-  __shared__ float2 slots[2];
+  __shared__ __align__(8) FrameXchg xc;
+  frame_xchg_init(xc);
   const int f = blockIdx.x / kFrameCL, lane = threadIdx.x & 31;
   const int tok0 = (int)frame_cluster_rank() * (kTok / kFrameCL) + (threadIdx.x >> 5) * kTPW;
   FrameRegs r;
   if (h_is_bf16) frame_load_bf16((const bf16*)h + (size_t)f * kTok * kC, r, tok0, lane);
   else frame_load((const float*)h + (size_t)f * kTok * kC, r, tok0, lane);
   float mean, rstd;
-  frame_stats(r, red, &slots[0], mean, rstd);
+  frame_stats(r, red, xc, 0, mean, rstd);
 #pragma unroll
   for (int t = 0; t < kTPW; ++t) {
     const size_t tok = tok0 + t;
@@ -328,9 +381,7 @@ frame_ln_gelu_residual_kernel(const void* __restrict__ h, int h_is_bf16, const f
     }
   }
   // fused consumer: the next op of every block is LayerNorm + positional fuse of the stream just updated
-  if (TAIL) posfuse_from_regs(r, red, &slots[1], f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, tok0, lane);
-  frame_cluster_arrive();                                     // keep `slots` alive until every block of the frame has read them
-  frame_cluster_wait();
+  if (TAIL) posfuse_from_regs(r, red, xc, f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, tok0, lane);
 }
 
 extern "C" int npvp_frame_ln_gelu_residual(const void* h, int h_is_bf16, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,
