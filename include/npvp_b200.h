@@ -155,6 +155,18 @@ int npvp_ffn_dwconv(const void* h_bf16, const float* stats1, const float* n1w, c
 /* step 3: out = GELU(LN2(y)) bf16, statistics from the partials of step 2. */
 int npvp_ffn_norm2(const void* y_bf16, const float* partial2, const float* n2w, const float* n2b, void* out_bf16,
                    int64_t frames, int64_t Ch, void* stream);
+/* steps 2 + 3 in one pass (Ch = 2048 only): out = GELU(LN2(dw3x3(GELU(LN1(h1))) + b)), bf16 [frames,64,Ch], out != h1.
+ * The 16 channel chunks of a frame are 16 blocks that exchange their LN2 partial statistics
+ *   xch != NULL: through L2 - xch is a 128-byte aligned fp32 scratch [frames,16,2] (the call resets it); all SMs work;
+ *                needs npvp_ffn_mid_lanes() > 0 (16-block frame lanes resident at once);
+ *   xch == NULL: through distributed shared memory, as one 16-block cluster (non-portable size; npvp_ffn_mid_clusters()
+ *                = clusters the device holds at once - 7 on a B200, i.e. 112 of 148 SMs).
+ * Same values as npvp_ffn_dwconv + npvp_ffn_norm2 up to fp32 summation order. */
+int npvp_ffn_mid(const void* h_bf16, const float* stats1, const float* n1w, const float* n1b, const float* dw_w,
+                 const float* dw_b, const float* n2w, const float* n2b, void* out_bf16, float* xch, int64_t frames,
+                 int64_t Ch, void* stream);
+int npvp_ffn_mid_clusters(void);
+int npvp_ffn_mid_lanes(void);
 
 /* ---- predictor: attention cores (8 heads x 64) ---------------------------------------------
  * softmax(Q K^T / 8 [+mask]) V for the short sequences of the factorised attention

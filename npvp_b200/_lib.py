@@ -53,6 +53,9 @@ SIGNATURES = {
     "npvp_ssim": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp],
     "npvp_ffn_dwconv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_ffn_norm2": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "npvp_ffn_mid": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "npvp_ffn_mid_clusters": [],
+    "npvp_ffn_mid_lanes": [],
     "npvp_attention": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i64, _i32, _i32, _i32, _vp],
     "npvp_dwconv3x3_tokens": [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp],
     "npvp_latent_reparam": [_vp, _i64, _vp, _vp, _i64, _i64, _vp],
@@ -346,6 +349,28 @@ class Ops:
         frames, Ch = partial2.shape[0], y.shape[-1]
         self._call("npvp_ffn_norm2", y.data_ptr(), partial2.data_ptr(), n2w.data_ptr(), n2b.data_ptr(), out.data_ptr(), frames,
                    Ch, self._stream())
+
+    def ffn_mid_clusters(self):
+        """16-block clusters of the fused conv-FFN middle the device holds at once (DSMEM exchange; 0: not schedulable)."""
+        return int(self.lib.npvp_ffn_mid_clusters())
+
+    def ffn_mid_lanes(self):
+        """16-block frame lanes of the fused conv-FFN middle resident at once (L2 exchange; 0: use ffn_dwconv + ffn_norm2)."""
+        return int(self.lib.npvp_ffn_mid_lanes())
+
+    def ffn_mid(self, h, stats1, n1w, n1b, dw_w, dw_b, n2w, n2b, out, xch=None):
+        """``xch``: fp32 scratch [frames,16,2] -> statistics exchange through L2 (all SMs); None -> 16-block clusters / DSMEM."""
+        _chk(h, torch.bfloat16, "h"); _chk(out, torch.bfloat16, "out")
+        for t, n in ((stats1, "stats1"), (n1w, "n1w"), (n1b, "n1b"), (dw_w, "dw_w"), (dw_b, "dw_b"), (n2w, "n2w"), (n2b, "n2b")):
+            _chk(t, torch.float32, n)
+        frames, Ch = stats1.shape[0], h.shape[-1]
+        assert dw_w.shape == (9, Ch) and n1w.shape == (64, Ch) and n2w.shape == (64, Ch) and out.data_ptr() != h.data_ptr()
+        if xch is not None:
+            _chk(xch, torch.float32, "xch")
+            assert xch.shape == (frames, Ch // FFN_CHUNK, 2)
+        self._call("npvp_ffn_mid", h.data_ptr(), stats1.data_ptr(), n1w.data_ptr(), n1b.data_ptr(), dw_w.data_ptr(), dw_b.data_ptr(),
+                   n2w.data_ptr(), n2b.data_ptr(), out.data_ptr(), xch.data_ptr() if xch is not None else None, frames, Ch,
+                   self._stream())
 
     def attention(self, q, k, v, out, mode, n_clips, Tq, Tk, mask_last=False):
         for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):

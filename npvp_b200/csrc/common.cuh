@@ -85,6 +85,44 @@ __device__ __forceinline__ void gelu_erf_x8(float (&x)[8]) {
   }
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: one instruction, two IEEE-rn fp32 results).  Measured on B200
+// (tools/ubench/ffma2.cu): the FMA pipe retires the same 128 FMA / clk / SM either way, so packing does not add arithmetic
+// throughput - it halves the ISSUE slots the arithmetic takes, which is what bounds the elementwise-heavy kernels here
+// (LayerNorm affine + GELU + depthwise taps: ~19 of ~27 issued instructions per element are FMA-pipe).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t u) { return pk2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(f32x2 v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// gelu_erf on a packed pair, bit-identical to the scalar form: the Horner chain runs in nu = -min(|x|, 5.5) with the odd
+// coefficients negated (round-to-nearest is sign symmetric), so the final step is fma(nu, Q, max(x, 0)) with no negation.
+// Per pair: 2 FMNMX + 6 FFMA2 + 2 MUFU + 2 FMNMX + 1 FFMA2 = 13 issue slots (20 scalar).
+__device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
+  float x0, x1;
+  upk2(x, x0, x1);
+  const f32x2 nu = pk2(fmaxf(-fabsf(x0), -5.5f), fmaxf(-fabsf(x1), -5.5f));
+  f32x2 p = fma2(pk2(3.309290792e-05f, 3.309290792e-05f), nu, pk2(7.692205073e-04f, 7.692205073e-04f));
+  p = fma2(p, nu, pk2(8.080719144e-03f, 8.080719144e-03f));
+  p = fma2(p, nu, pk2(5.341210813e-02f, 5.341210813e-02f));
+  p = fma2(p, nu, pk2(-4.587709705e-01f, -4.587709705e-01f));
+  p = fma2(p, nu, pk2(1.151201703e+00f, 1.151201703e+00f));
+  p = fma2(p, nu, pk2(-9.999930609e-01f, -9.999930609e-01f));
+  float p0, p1, r0, r1;
+  upk2(p, p0, p1);
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r0) : "f"(x0));
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r1) : "f"(x1));
+  return fma2(nu, pk2(ex2_approx(p0), ex2_approx(p1)), pk2(r0, r1));
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == NPVP_ACT_RELU) return fmaxf(v, 0.0f);
   if (act == NPVP_ACT_GELU) return gelu_erf(v);

@@ -128,6 +128,12 @@ class PredictorEngine:
         self.device = dev
         self.ws = Workspace(dev)
         self.stochastic = bool(mod.stochastic)
+        # conv-FFN middle: "split" = ffn_dwconv + ffn_norm2 (default, fastest: DESIGN.md section 4); experimental single-pass
+        # kernels: "cluster" = 16-block clusters exchanging the LN2 statistics through DSMEM, "fused" = the same through L2
+        mid = os.environ.get("NPVP_B200_FFN_MID", "split")
+        if mid == "fused" and _lib.ops().ffn_mid_lanes() <= 0 or mid == "cluster" and _lib.ops().ffn_mid_clusters() <= 0:
+            mid = "split"
+        self._ffn_mid = mid
         self.enc_layers = [_EncLayer(b) for b in mod.EVT_Former.layers]
         self.dec_layers = [_DecLayer(b) for b in mod.transformer.layers]
         self.norm_enc = _LN(mod.EVT_Former.norm)
@@ -237,9 +243,14 @@ class PredictorEngine:
         pt1 = ws.f32(f"pt1_{tag}", frames, 4 * w.hid // 256, 2)
         op.gemm(a_bf, w.w1, bias=w.b1, out_bf16=h1, frame_stats=pt1)     # LayerNorm((hid,8,8)) statistics from the fc1 epilogue
         op.ffn_stats_finalize(pt1, st1, 64 * w.hid)
-        op.ffn_dwconv(h1, st1, w.n1w, w.n1b, w.dw_w, w.dw_b, y2, pt2)
-        op.ffn_norm2(y2, pt2, w.n2w, w.n2b, h1)                 # h1 is dead: reuse it for GELU(LN2(.))
-        op.gemm(h1, w.w2, bias=w.b2, out_bf16=h3)
+        if self._ffn_mid != "split" and w.hid == 2048:          # one pass over the frame: h1 read once, GELU(LN2(.)) written once
+            op.ffn_mid(h1, st1, w.n1w, w.n1b, w.dw_w, w.dw_b, w.n2w, w.n2b, y2, xch=pt2 if self._ffn_mid == "fused" else None)
+            h2 = y2
+        else:
+            op.ffn_dwconv(h1, st1, w.n1w, w.n1b, w.dw_w, w.dw_b, y2, pt2)
+            op.ffn_norm2(y2, pt2, w.n2w, w.n2b, h1)             # h1 is dead: reuse it for GELU(LN2(.))
+            h2 = h1
+        op.gemm(h2, w.w2, bias=w.b2, out_bf16=h3)
         if tail is None:
             op.frame_ln_gelu_residual(h3, w.n3w, w.n3b, x)
         else:
@@ -255,50 +266,55 @@ class PredictorEngine:
     # ------------------------------------------------------------------------------------------
     # EVT_Former (VidHRFormer.py:25-52, 79-116)
     # ------------------------------------------------------------------------------------------
-    def encode(self, x_tokens, beta, gamma, n, T):
-        """x_tokens fp32 [n*T*64, 512] (consumed in place) -> (memory fp32, memory bf16) [n*T*64,512]."""
+    def encode(self, x_tokens, beta, gamma, n, T, tag="enc"):
+        """x_tokens fp32 [n*T*64, 512] (consumed in place) -> (memory fp32, memory bf16) [n*T*64,512].
+        ``tag`` names the scratch buffers: the posterior pass over the ground-truth future ("encp") keeps its own set, so
+        the context memory survives it and neither pass re-allocates when To != Tp."""
         op, ws = _lib.ops(), self.ws
         M = n * T * TOK
         x = x_tokens
-        a = ws.bf16("a_enc", M, C)
-        f = ws.bf16("f_enc", M, C)
+        a = ws.bf16(f"a_{tag}", M, C)
+        f = ws.bf16(f"f_{tag}", M, C)
         d = None                                                 # pending (deferred) residual of the previous branch
         for L in self.enc_layers:
             self._ln_fuse(x, d, L.n1, None, beta, gamma, a, f, n, T)
-            d = self._self_attention(x, a, f, L.attn_s, ATTN_SPATIAL, n, T, False, "enc")
+            d = self._self_attention(x, a, f, L.attn_s, ATTN_SPATIAL, n, T, False, tag)
             self._ln_rows(x, d, L.n2, out_bf16=a)
-            self._conv_ffn(x, a, L.ffn_s, n * T, "enc", tail=(L.n3, None, beta, gamma, a, f, n, T))   # + LN3 / fuse
-            d = self._self_attention(x, a, f, L.attn_t, ATTN_TEMPORAL, n, T, True, "enc")    # mask quirk :100-102
+            self._conv_ffn(x, a, L.ffn_s, n * T, tag, tail=(L.n3, None, beta, gamma, a, f, n, T))   # + LN3 / fuse
+            d = self._self_attention(x, a, f, L.attn_t, ATTN_TEMPORAL, n, T, True, tag)      # mask quirk :100-102
             self._ln_rows(x, d, L.n4, out_bf16=a)
-            d = self._mlp_ffn(x, a, L, "enc")
-        mem = ws.f32("mem_f32", M, C)
-        mem_bf = ws.bf16("mem_bf16", M, C)
+            d = self._mlp_ffn(x, a, L, tag)
+        sfx = "" if tag == "enc" else "_" + tag
+        mem = ws.f32("mem_f32" + sfx, M, C)
+        mem_bf = ws.bf16("mem_bf16" + sfx, M, C)
         self._ln_rows(x, d, self.norm_enc, out_f32=mem, out_bf16=mem_bf)
         return mem, mem_bf
 
     # ------------------------------------------------------------------------------------------
     # latent event code (submodules.py:388-410)
     # ------------------------------------------------------------------------------------------
-    def latent(self, evt, n, eps, n_samples=1):
+    def latent(self, evt, n, eps, n_samples=1, E=None, sfx=""):
         """evt fp32 [n*64,512] token-major -> z fp32 [n*K*64,512]; keeps (mu|logvar) of the n clips in the workspace.
-        K > 1: the prior (mu, logvar) is computed once per clip and re-parameterised with K noise tensors."""
-        op, ws, E = _lib.ops(), self.ws, self.evt
+        K > 1: the prior (mu, logvar) is computed once per clip and re-parameterised with K noise tensors.
+        ``E`` / ``sfx``: another packed EventEncoder (the posterior) with its own scratch buffers."""
+        op, ws = _lib.ops(), self.ws
+        E = self.evt if E is None else E
         M = n * TOK
-        e1 = ws.bf16("evt_e1", M, C)
+        e1 = ws.bf16("evt_e1" + sfx, M, C)
         op.dwconv3x3_tokens(evt, E.dw_w, E.dw_shift, e1, relu=True)
-        e2 = ws.bf16("evt_e2", M, E.hidden)
+        e2 = ws.bf16("evt_e2" + sfx, M, E.hidden)
         op.conv_gemm(e1, E.w2, n, 8, 8, C, 3, 3, 1, 1, PAD_ZERO, 8, 8, bias=E.b2, act=ACT_RELU, out_bf16=e2)
-        e3 = ws.bf16("evt_e3", M, E.hidden)
+        e3 = ws.bf16("evt_e3" + sfx, M, E.hidden)
         op.gemm(e2, E.w3, bias=E.b3, act=ACT_RELU, out_bf16=e3)
-        mulv = ws.f32("evt_mulv", M, E.w_head.shape[0])
+        mulv = ws.f32("evt_mulv" + sfx, M, E.w_head.shape[0])
         op.gemm(e3, E.w_head, bias=E.b_head, out_f32=mulv)
         K = int(n_samples)
         src = mulv
         if K > 1:
             W2 = mulv.shape[1]
-            src = ws.f32("evt_mulv_rep", M * K, W2)
+            src = ws.f32("evt_mulv_rep" + sfx, M * K, W2)
             src.view(n, K, TOK, W2).copy_(mulv.view(n, 1, TOK, W2).expand(n, K, TOK, W2))
-        z = ws.f32("evt_z", M * K, C)
+        z = ws.f32("evt_z" + sfx, M * K, C)
         op.latent_reparam(src, eps if E.stochastic else None, z, n * K, C)
         return z, mulv
 
@@ -369,9 +385,35 @@ class PredictorEngine:
         op.tokens_to_nchw(tok.view(n * T, TOK, C), out.view(n * T, C, TOK))
         return out
 
-    def run(self, observed, channels_last=False, out16=None, n_samples=1):
+    @staticmethod
+    def _mu_logvar_nchw(mulv, n):
+        """(mu | logvar) token-major fp32 [n*64, 1024] -> two (n, 512, 8, 8) tensors in the reference layout."""
+        t = mulv.view(n, 8, 8, 2, C).permute(3, 0, 4, 1, 2).contiguous()
+        return t[0], t[1]
+
+    def posterior(self, gt, n, channels_last, beta_p, gamma_p, sample_noise):
+        """NPVP-S posterior on the ground-truth future features (Predictor.py:311-313): EVT_Former over the Tp target frames with
+        the target positional code, temporal mean, ``evt_posterior`` heads -> (mu_p, logvar_p).  z_p itself is only used in
+        training mode (:316-318), so no re-parameterisation kernel runs; with ``sample_noise`` one noise tensor is still drawn
+        and dropped so that the global generator advances exactly like the reference's second ``torch.randn`` (submodules.py:409)."""
+        post = self.__dict__.get("_evt_post")
+        if post is None:
+            post = self._evt_post = _EventEnc(self.mod.evt_posterior, True)
+        tok, n2, Tp = self._to_tokens(gt, channels_last, "x_encp")
+        assert n2 == n and Tp * TOK == beta_p.shape[0], "predict_features_gt must hold one frame per target timestamp"
+        mem_p, _ = self.encode(tok, beta_p, gamma_p, n, Tp, tag="encp")
+        evt_p = self.ws.f32("evt_p", n * TOK, C)
+        _lib.ops().temporal_mean(mem_p, evt_p, n, Tp)
+        if sample_noise:
+            torch.randn((n, C, 8, 8), device=self.device)
+        _, mulv_p = self.latent(evt_p, n, None, E=post, sfx="_p")
+        return self._mu_logvar_nchw(mulv_p, n)
+
+    def run(self, observed, channels_last=False, out16=None, n_samples=1, predict_gt=None):
         """``n_samples`` = K > 1 (NPVP-S): K stochastic futures per clip from ONE pass of the EVT_Former and the prior (only the
-        latent and the NAR decoder run per sample); the batch dimension of the result is clip-major (clip 0 sample 0..K-1, ...)."""
+        latent and the NAR decoder run per sample); the batch dimension of the result is clip-major (clip 0 sample 0..K-1, ...).
+        ``predict_gt`` (NPVP-S, eval): ground-truth future features -> (out, mu_o, logvar_o, mu_p, logvar_p) like the reference
+        (Predictor.py:324-327); the decoder is still queried with the prior sample.  The deterministic model ignores it (:328-335)."""
         mod = self.mod
         K = int(n_samples)
         assert K >= 1 and (K == 1 or self.stochastic), "several samples per clip only make sense for the stochastic model (NPVP-S)"
@@ -402,7 +444,13 @@ class PredictorEngine:
         if out16 is not None:   # engine-internal hand-off to the frame decoder (a view of the workspace, consumed at once)
             assert channels_last
             return out_bf.view(n * K, Tp, 8, 8, C)
-        return self._from_tokens(out, n * K, Tp, channels_last)
+        res = self._from_tokens(out, n * K, Tp, channels_last)
+        if predict_gt is not None and self.stochastic:
+            assert K == 1, "predict_features_gt and n_samples > 1 cannot be combined"
+            mu_o, logvar_o = self._mu_logvar_nchw(mulv, n)
+            mu_p, logvar_p = self.posterior(predict_gt, n, channels_last, beta_p, gamma_p, sample_noise=mod.injected_eps is None)
+            return res, mu_o, logvar_o, mu_p, logvar_p
+        return res
 
     def evt_coding(self, x, pos_beta, pos_gamma):
         """Predictor.evt_coding_forward (Predictor.py:337-350): returns (memory (N,T,C,H,W), evt_coding (N,C,H,W))."""

@@ -61,7 +61,34 @@ class NPVPInference(nn.Module):
                                    evt_former_num_layers=P.evt_former_num_layers, rand_context=P.rand_context)
         if P.rand_context:
             self.predictor.reset_pos_coor(self.to_list, self.tp_list)
+        # batch -> (context clip, target clip), selected like LitPredictor.__init__ (Predictor.py:62-70)
+        if P.rand_context:
+            self.batch_process_fn = self.rand_context_batch_process
+        elif P.get("VFI", False):
+            self.batch_process_fn = self.VFI_batch_process
+        else:
+            self.batch_process_fn = self.normal_batch_process
         self.eval()
+
+    # -- batch pre-processing (Predictor.py:241-262) ----------------------------------------------------
+    def rand_context_batch_process(self, batch):
+        """(clip_o, clip_p, idx_o, idx_p) from the random-context dataloader: re-targets the predictor at the batch's context /
+        target frame indices by slicing ``all_coor`` (Predictor.py:241-251) and returns (clip_o, clip_p)."""
+        clip_batch_o, clip_batch_p, idx_o, idx_p = batch
+        coor = self.predictor.all_coor
+        self.predictor.observed_coor = coor[idx_o, ...].flatten(0, 2)
+        self.predictor.predict_coor = coor[idx_p, ...].flatten(0, 2)
+        self.predictor.TP = idx_p.shape[0]
+        return (clip_batch_o, clip_batch_p)
+
+    def VFI_batch_process(self, batch):
+        """(past, future) -> (context frames, frames to interpolate) by the YAML's index lists (Predictor.py:253-259)."""
+        past_frames, future_frames = batch
+        clip = torch.cat([past_frames, future_frames], dim=1)
+        return (clip[:, self.to_list, ...], clip[:, self.tp_list, ...])
+
+    def normal_batch_process(self, batch):
+        return batch
 
     # -- checkpoints --------------------------------------------------------------------------------
     def load_lightning_ckpt(self, path: str, strict: bool = True):

@@ -107,12 +107,16 @@ class Predictor(_EngineModule):
             self.predict_coor = self.predict_coor.to(dev, torch.float32)
 
     def forward(self, observed_features, predict_features_gt=None):
-        """observed_features: (N, To, C, H, W) fp32 CUDA -> predicted features (N, Tp, C, H, W)."""
+        """observed_features: (N, To, C, H, W) fp32 CUDA -> predicted features (N, Tp, C, H, W).
+        NPVP-S with ``predict_features_gt`` (N, Tp, C, H, W): also runs the posterior on the ground-truth future and returns
+        ``(out, mu_o, logvar_o, mu_p, logvar_p)`` like the reference in eval mode (Predictor.py:311-313, 320-327) - the
+        inputs of the KL term (criterion.py:341-354).  NPVP-D ignores it (:328-335).  Training mode (decoder queried
+        with the posterior sample, :316-318) is not supported: ``_guard`` rejects ``training=True``."""
         self._guard(observed_features)
         self._coords_ready()
-        if predict_features_gt is not None:
-            raise NotImplementedError("the posterior branch on ground-truth future features (training / KL evaluation, "
-                                      "Predictor.py:311-327) is not on the inference hot path")
+        if predict_features_gt is not None and self.stochastic:
+            self._guard(predict_features_gt)
+            return self._engine().run(observed_features, predict_gt=predict_features_gt)
         return self._engine().run(observed_features)
 
     def forward_tokens(self, observed_tokens, out16=None, n_samples=1):

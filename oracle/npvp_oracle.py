@@ -252,9 +252,11 @@ def event_encoder(sd: SD, p: str, x: Tensor, stochastic: bool, eps: Optional[Ten
 def predictor_forward(sd: SD, observed_features: Tensor, observed_coor: Tensor, predict_coor: Tensor,
                       stochastic: bool, eps: Optional[Tensor] = None, fuse_method: str = "Add",
                       evt_layers: int = 4, dec_layers: int = 8, prefix: str = "",
-                      return_latent: bool = False):
-    """Predictor.forward in eval mode without ground-truth features, models/Predictor.py:301-350.
-    observed_features (N,To,C,H,W) -> (N,Tp,C,H,W)."""
+                      return_latent: bool = False, predict_features_gt: Optional[Tensor] = None):
+    """Predictor.forward in eval mode, models/Predictor.py:301-350.  observed_features (N,To,C,H,W) -> (N,Tp,C,H,W).
+    With ``predict_features_gt`` (N,Tp,C,H,W) the stochastic model also runs the posterior on the ground-truth future
+    (Predictor.py:311-313) and returns (out, mu_o, logvar_o, mu_p, logvar_p) (:324-327) - the KL / ELBO evaluation path;
+    in eval mode the decoder is still queried with the PRIOR sample z_o (:320-322).  The deterministic model ignores it (:328-335)."""
     p = prefix
     Tp = predict_coor.shape[0] // (observed_features.shape[-1] * observed_features.shape[-2])
     op = nrmlp(sd, p + "nrmlp.", observed_coor, fuse_method)
@@ -270,6 +272,10 @@ def predictor_forward(sd: SD, observed_features: Tensor, observed_coor: Tensor, 
     out = decoder_nar(sd, p + "transformer.", query_evt, memory, op, pp, dec_layers)
     if return_latent:
         return out, memory, evt, z, mu, logvar
+    if stochastic and predict_features_gt is not None:
+        memory_p = evt_former(sd, p + "EVT_Former.", predict_features_gt, pp[0], pp[1], evt_layers)     # Predictor.py:312
+        _, mu_p, logvar_p = event_encoder(sd, p + "evt_posterior.", memory_p.mean(dim=1), True, eps)   # :313 (z_p unused in eval)
+        return out, mu, logvar, mu_p, logvar_p
     return out
 
 

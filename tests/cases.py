@@ -12,6 +12,8 @@ from util_init import fingerprint, reset_shared_norm, seeded_rand, seeded_randn,
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PRED_CASES = ["pred_S_stress_realT", "pred_D_default", "pred_D_stress_vfi"]
+PRED_GT_CASES = ["pred_S_stress_gt"]          # NPVP-S with ground-truth future features (posterior branch, Predictor.py:311-327)
+LATENT_KEYS = ("mu_o", "logvar_o", "mu_p", "logvar_p")
 AE_CASES = ["ae_famB_stress", "ae_famA_default", "ae_famA_rgb_stress"]
 
 
@@ -48,6 +50,23 @@ def build_predictor_case(name):
     x = torch.relu(seeded_randn((int(m["N"]), len(to), 512, 8, 8), seed + 100))
     eps = seeded_randn((int(m["N"]), 512, 8, 8), seed + 200)
     return mod, x, eps, stoch, z
+
+
+def build_predictor_gt_case(name):
+    """As build_predictor_case plus the ground-truth future features the fixture was generated with."""
+    mod, x, eps, stoch, z = build_predictor_case(name)
+    _, m = load_golden(name)
+    gt = torch.relu(seeded_randn((int(m["N"]), len(m["tp"]), 512, 8, 8), int(m["seed"]) + 300))
+    return mod, x, gt, eps, z
+
+
+def golden_latents(outs, z):
+    """[(name, strided sample of ours, golden sample)] for the four latent tensors of a posterior-branch fixture."""
+    res = []
+    for key, t in zip(LATENT_KEYS, outs[1:]):
+        ours = t.detach().float().cpu().reshape(-1)[:: int(z[key + "_stride"])].numpy()
+        res.append((key, ours, z[key]))
+    return res
 
 
 def build_ae_case(name):

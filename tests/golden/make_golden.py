@@ -111,7 +111,7 @@ def main():
         ("pred_D_stress_vfi", False, 10, [0, 1, 8, 9], [3, 5.5], 2, True, 13),
     ]
     hl = torch.linspace(0, 7, 8)
-    for name, stoch, max_T, to, tp, N, stress, seed in pred_cases:
+    for name, stoch, max_T, to, tp, N, stress, seed in ([] if "--gt-only" in sys.argv else pred_cases):
         to_t, tp_t = torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32)
         args = (8, 8, max_T, hl, hl, to_t, tp_t, 512, 'Add', 'layer', 256, 1, stoch, 8)
         kw = dict(evt_former=True, learn_evt_token=False, evt_former_num_layers=4, rand_context=False)
@@ -142,6 +142,51 @@ def main():
         fp = fingerprint(ref.state_dict())
         save(name, out_ref, dict(seed=seed, stochastic=stoch, max_T=max_T, to=to, tp=tp, N=N, stress=stress,
                                  fp_sum=fp["sum"], fp_abs=fp["abs_sum"], fp_numel=fp["numel"], fp_keys=fp["keys"]))
+
+    # ---------------------------------------------------------------- NPVP-S with ground-truth future features (posterior branch)
+    # Predictor.forward(observed, predict_features_gt) in eval mode -> (out, mu_o, logvar_o, mu_p, logvar_p), Predictor.py:311-327
+    for name, max_T, to, tp, N, seed in [("pred_S_stress_gt", 9, [0, 1.5, 3], [2, 4, 5.25, 8], 2, 14)]:
+        to_t, tp_t = torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32)
+        args = (8, 8, max_T, hl, hl, to_t, tp_t, 512, 'Add', 'layer', 256, 1, True, 8)
+        kw = dict(evt_former=True, learn_evt_token=False, evt_former_num_layers=4, rand_context=False)
+        reset_shared_norm(RefPredictor)
+        reset_shared_norm(npvp_b200.Predictor)
+        torch.manual_seed(seed)
+        ref = RefPredictor(*args, **kw).eval()
+        torch.manual_seed(seed)
+        mine = npvp_b200.Predictor(*args, **kw).eval()
+        stress_init_(ref, seed)
+        stress_init_(mine, seed)
+        check_same_weights(ref, mine, name)
+        x = torch.relu(seeded_randn((N, len(to), 512, 8, 8), seed + 100))
+        gt = torch.relu(seeded_randn((N, len(tp), 512, 8, 8), seed + 300))
+        eps = seeded_randn((N, 512, 8, 8), seed + 200)
+        real = ref_sub.torch.randn
+        try:
+            ref_sub.torch.randn = lambda *a, **k: eps.clone()
+            outs_ref = ref(x, gt)
+        finally:
+            ref_sub.torch.randn = real
+        sd = {k: v.clone() for k, v in mine.state_dict().items()}
+        outs_or = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps, predict_features_gt=gt)
+        assert len(outs_ref) == 5 and len(outs_or) == 5
+        errs = [float((a - b).abs().max()) for a, b in zip(outs_ref, outs_or)]
+        report.append((name, tuple(outs_ref[0].shape), max(errs)))
+        assert max(errs) < 5e-5, (name, errs)
+        fp = fingerprint(ref.state_dict())
+        extra = {}
+        for key, t in zip(("mu_o", "logvar_o", "mu_p", "logvar_p"), outs_ref[1:]):
+            vals, stride = sample(t, 8000)
+            extra[key] = vals
+            extra[key + "_stride"] = np.int64(stride)
+        save(name, outs_ref[0], dict(seed=seed, stochastic=True, max_T=max_T, to=to, tp=tp, N=N, stress=True,
+                                     fp_sum=fp["sum"], fp_abs=fp["abs_sum"], fp_numel=fp["numel"], fp_keys=fp["keys"]), extra)
+    if "--gt-only" in sys.argv:
+        print(report)
+        with open(os.path.join(HERE, "REPORT.txt"), "a") as f:
+            for r in report[-1:]:
+                f.write(f"{r[0]}, {r[1]}, {r[2]:.3e}\n")
+        return
 
     # ---------------------------------------------------------------- autoencoder cases
     ae_cases = [

@@ -191,6 +191,21 @@ class SpecOps:
         v = (yy - mean.float().reshape(-1, 1, 1)) * rstd.float().reshape(-1, 1, 1) * n2w + n2b
         out.copy_(_act(v, ACT_GELU).reshape(out.shape).to(torch.bfloat16))
 
+    def ffn_mid_clusters(self):
+        return 7
+
+    def ffn_mid_lanes(self):
+        return 9
+
+    def ffn_mid(self, h, stats1, n1w, n1b, dw_w, dw_b, n2w, n2b, out, xch=None):
+        """Fused ffn_dwconv + ffn_norm2: same values (conv output rounded to bf16 before LN2, statistics from the fp32 values)."""
+        frames, Ch = stats1.shape[0], h.shape[-1]
+        y = torch.empty_like(h)
+        pt = torch.empty(frames, Ch // FFN_CHUNK, 2, dtype=torch.float32, device=h.device)
+        self.ffn_dwconv(h, stats1, n1w, n1b, dw_w, dw_b, y, pt)
+        self.ffn_norm2(y, pt, n2w, n2b, out)
+        self.launches -= 1
+
     def attention(self, q, k, v, out, mode, n_clips, Tq, Tk, mask_last=False):
         self.launches += 1
         H, D = 8, 64

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import npvp_b200._lib as _lib
-from cases import AE_CASES, PRED_CASES, build_ae_case, build_predictor_case
+from cases import AE_CASES, PRED_CASES, PRED_GT_CASES, build_ae_case, build_predictor_case, build_predictor_gt_case
 from kernel_specs import SpecOps
 from oracle import npvp_oracle as O
 
@@ -37,6 +37,22 @@ def test_predictor_engine_vs_oracle(name):
     assert _rel(out, ref) < 3e-2, _rel(out, ref)
     out_cl = PredictorEngine(mod).run(x.permute(0, 1, 3, 4, 2).contiguous(), channels_last=True)
     assert torch.equal(out_cl.permute(0, 1, 4, 2, 3), out)
+
+
+@pytest.mark.parametrize("name", PRED_GT_CASES)
+def test_predictor_engine_posterior_branch(name):
+    from npvp_b200.engine_predictor import PredictorEngine
+    mod, x, gt, eps, _ = build_predictor_gt_case(name)
+    sd = mod.state_dict()
+    ref = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps, predict_features_gt=gt)
+    mod.injected_eps = eps
+    eng = PredictorEngine(mod)
+    outs = eng.run(x, predict_gt=gt)
+    assert len(outs) == 5
+    for a, b in zip(outs, ref):
+        assert a.shape == b.shape
+        assert _rel(a, b) < 3e-2, _rel(a, b)
+    assert torch.equal(eng.run(x), outs[0])         # same prediction with and without the ground truth
 
 
 @pytest.mark.parametrize("name", AE_CASES)

@@ -196,6 +196,34 @@ def test_conv_ffn_middle(op, spec):
     close(res[0][3], res[1][3], 2e-2, "ffn norm2")
 
 
+@pytest.mark.parametrize("xchg", ["l2", "dsmem"])
+@pytest.mark.parametrize("frames", [1, 3, 37, 130])
+def test_conv_ffn_middle_fused(op, spec, frames, xchg):
+    """npvp_ffn_mid (one pass; statistics exchange through L2 or through a 16-block cluster's shared memory) against
+    npvp_ffn_dwconv + npvp_ffn_norm2 and the specification."""
+    Ch = 2048
+    assert op.ffn_mid_lanes() > 0 and op.ffn_mid_clusters() > 0
+    h = (rn(frames * 64, Ch, seed=1, scale=1.5) + 0.2).to(torch.bfloat16)
+    n1w, n1b = rn(64, Ch, seed=2) * 0.3 + 1, rn(64, Ch, seed=3) * 0.3
+    n2w, n2b = rn(64, Ch, seed=4) * 0.3 + 1, rn(64, Ch, seed=5) * 0.3
+    dw_w, dw_b = rn(9, Ch, seed=6, scale=0.4), rn(Ch, seed=7, scale=0.2)
+    st = torch.empty(frames, 2, device=DEV)
+    op.ffn_frame_stats(h, st)
+    fused, ref = torch.empty_like(h), torch.empty_like(h)
+    xch = torch.empty(frames, Ch // FFN_CHUNK, 2, device=DEV) if xchg == "l2" else None
+    for _ in range(2):                                             # twice: the exchange table must be reusable
+        fused.fill_(float("nan"))
+        op.ffn_mid(h, st, n1w, n1b, dw_w, dw_b, n2w, n2b, fused, xch=xch)
+    spec.ffn_mid(h, st, n1w, n1b, dw_w, dw_b, n2w, n2b, ref)
+    close(fused, ref, 2e-2, "ffn_mid vs spec")
+    y, pt, split = torch.empty_like(h), torch.empty(frames, Ch // FFN_CHUNK, 2, device=DEV), torch.empty_like(h)
+    op.ffn_dwconv(h, st, n1w, n1b, dw_w, dw_b, y, pt)
+    op.ffn_norm2(y, pt, n2w, n2b, split)
+    d = (fused.float() - split.float()).abs()
+    print(f"fused vs split: max abs {float(d.max()):.3e}, mismatching elements {int((d > 0).sum())} / {d.numel()}")
+    close(fused, split, 1e-2, "ffn_mid vs two-kernel path")
+
+
 @pytest.mark.parametrize("mode,n,Tq,Tk,mask", [(0, 2, 3, 3, False), (1, 2, 5, 5, True), (1, 2, 5, 5, False), (1, 1, 7, 3, False),
                                                (1, 1, 2, 2, True), (1, 1, 28, 2, False), (1, 1, 23, 10, False), (1, 1, 1, 1, True)])
 def test_attention(op, spec, mode, n, Tq, Tk, mask):

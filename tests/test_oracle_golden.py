@@ -3,7 +3,8 @@ import numpy as np
 import pytest
 import torch
 
-from cases import AE_CASES, PRED_CASES, build_ae_case, build_predictor_case, golden_sample
+from cases import (AE_CASES, PRED_CASES, PRED_GT_CASES, build_ae_case, build_predictor_case, build_predictor_gt_case,
+                   golden_latents, golden_sample)
 from oracle import npvp_oracle as O
 
 torch.set_grad_enabled(False)
@@ -17,6 +18,21 @@ def test_predictor_oracle_matches_reference(name):
     assert list(out.shape) == list(z["shape"])
     np.testing.assert_allclose(golden_sample(out, z), z["sample"], atol=5e-5, rtol=0)
     assert abs(float(out.double().mean()) - float(z["mean"])) < 1e-5
+
+
+@pytest.mark.parametrize("name", PRED_GT_CASES)
+def test_predictor_posterior_oracle_matches_reference(name):
+    """Predictor.forward(observed, predict_features_gt) in eval mode: (out, mu_o, logvar_o, mu_p, logvar_p)."""
+    mod, x, gt, eps, z = build_predictor_gt_case(name)
+    sd = mod.state_dict()
+    outs = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps, predict_features_gt=gt)
+    assert len(outs) == 5 and list(outs[0].shape) == list(z["shape"])
+    np.testing.assert_allclose(golden_sample(outs[0], z), z["sample"], atol=5e-5, rtol=0)
+    for key, ours, gold in golden_latents(outs, z):
+        np.testing.assert_allclose(ours, gold, atol=5e-5, rtol=0, err_msg=key)
+    # the decoder is queried with the PRIOR sample: the prediction does not depend on the ground truth
+    plain = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps)
+    assert torch.equal(plain, outs[0])
 
 
 @pytest.mark.parametrize("name", AE_CASES)

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from cases import AE_CASES, PRED_CASES, build_ae_case, build_predictor_case, golden_sample
+from cases import (AE_CASES, PRED_CASES, PRED_GT_CASES, build_ae_case, build_predictor_case, build_predictor_gt_case,
+                   golden_latents, golden_sample)
 from oracle import npvp_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -39,6 +40,35 @@ def test_predictor_matches_oracle_and_golden(name):
     assert r < 3e-2
     g = torch.from_numpy(z["sample"])
     assert float((torch.from_numpy(golden_sample(out, z)) - g).abs().max()) < 3e-2 * float(z["absmax"])
+
+
+@pytest.mark.parametrize("name", PRED_GT_CASES)
+def test_predictor_posterior_branch(name):
+    """NPVP-S forward(observed, predict_features_gt) -> (out, mu_o, logvar_o, mu_p, logvar_p) against the oracle and the
+    reference-generated fixture (Predictor.py:311-327): the inputs of the KL term."""
+    mod, x, gt, eps, z = build_predictor_gt_case(name)
+    sd = mod.state_dict()
+    ref = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps, predict_features_gt=gt)
+    mod = mod.cuda()
+    mod.injected_eps = eps.cuda()
+    outs = mod(x.cuda(), gt.cuda())
+    assert isinstance(outs, tuple) and len(outs) == 5
+    outs = [o.cpu() for o in outs]
+    for key, a, b in zip(("out", "mu_o", "logvar_o", "mu_p", "logvar_p"), outs, ref):
+        assert a.shape == b.shape, key
+        r = _rel(a, b)
+        print(f"{name}.{key}: rel err vs oracle {r:.3e}")
+        assert r < 3e-2, (key, r)
+    for key, ours, gold in golden_latents(outs, z):
+        assert float(np.abs(ours - gold).max()) < 3e-2 * float(np.abs(gold).max()), key
+    assert torch.equal(mod(x.cuda()).cpu(), outs[0])
+    mod.injected_eps = None                          # sampled noise: shapes only, and the RNG advances by two draws like the reference
+    torch.manual_seed(5)
+    mod(x.cuda(), gt.cuda())
+    a = torch.randn(1, device="cuda")
+    torch.manual_seed(5)
+    torch.randn((x.shape[0], 512, 8, 8), device="cuda"); torch.randn((x.shape[0], 512, 8, 8), device="cuda")
+    assert torch.equal(a, torch.randn(1, device="cuda"))
 
 
 @pytest.mark.parametrize("name", AE_CASES)
