@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--clips B]
 
 Workload (BASELINE.json metric "predicted frames/sec ... Cityscapes 128^2 NPVP-S"): config_Cityscapes_VFP_NPVP-S,
-128x128 RGB, 2 context frames -> 28 predicted frames per clip by block-autoregressive rollout (2->10, 2->10, 2->8;
-max_T = 12 forbids a one-shot 2->28), random-init weights, synthetic clips.  A step = one rollout of B clips per GPU
+128x128 RGB, 2 context frames -> 28 predicted frames per clip by block-autoregressive rollout (2->10, 2->10, 2->8: the third block
+queries the 8 timestamps that are still needed; max_T = 12 forbids a one-shot 2->28), random-init weights, synthetic clips.  A step = one rollout of B clips per GPU
 (weak scaling: B fixed per GPU); for N > 1 the step ends with the NCCL all-gather of the predicted frames.
 
 One JSON line on rank 0:  value = device-resident throughput, e2e = through model.rollout with pinned host buffers
@@ -30,7 +30,9 @@ import torch  # noqa: E402
 
 PRESET = "Cityscapes_VFP_NPVP-S"
 N_FUTURE = 28
-WORKLOAD = "Cityscapes 128x128 RGB NPVP-S VFP 2->28 (block-autoregressive 2->10,2->10,2->8; config_Cityscapes_VFP_NPVP-S.yaml)"
+WORKLOAD = ("Cityscapes 128x128 RGB NPVP-S VFP 2->28 (block-autoregressive 2->10,2->10,2->8: the third block queries only "
+            "its 8 target timestamps; config_Cityscapes_VFP_NPVP-S.yaml)")
+LAST_BLOCK = "query"      # NPVPInference.rollout(last_block=...): "truncate" would predict 10 frames in the third block and drop 2
 METRIC = "predicted frames/sec"
 
 
@@ -98,12 +100,16 @@ def oracle_rollout_fn(clips: int):
     g = torch.Generator().manual_seed(1234)
     x = torch.rand((clips, 2, 3, 128, 128), generator=g) * 2 - 1
 
+    hl = torch.linspace(0, 7, 8)
+    short = O.coor_generator(model.tp_list[:N_FUTURE % 10], hl, hl, cfg.Predictor.max_T, 8, 8)   # last block: 8 target timestamps
+
     def fn():
         ctx, done, outs = x, 0, []
         while done < N_FUTURE:
             eps = torch.randn((clips, 512, 8, 8), generator=g)
-            pred = O.npvp_predict_frames(esd, psd, dsd, ctx, ocfg, psd["observed_coor"], psd["predict_coor"], eps)
             take = min(10, N_FUTURE - done)
+            # like rollout(last_block="query"): the last block asks only for the timestamps that are still needed
+            pred = O.npvp_predict_frames(esd, psd, dsd, ctx, ocfg, psd["observed_coor"], psd["predict_coor"] if take == 10 else short, eps)
             outs.append(pred[:, :take])
             done += take
             ctx = pred[:, 8:10]
@@ -202,17 +208,17 @@ def run_ours(args):
 
     def step_device():
         # N > 1: the all-gather of each AR block's frames is issued asynchronously and overlaps the next block's kernels
-        return model.rollout(x_dev, N_FUTURE, gather_group=True if world > 1 else None)
+        return model.rollout(x_dev, N_FUTURE, gather_group=True if world > 1 else None, last_block=LAST_BLOCK)
 
     def step_e2e():
         # public API on host buffers: async H2D of the context frames, per-block D2H of the frames on a copy stream
-        model.rollout(host_in, N_FUTURE, out_host=host_out, gather_group=True if world > 1 else None)
+        model.rollout(host_in, N_FUTURE, out_host=host_out, gather_group=True if world > 1 else None, last_block=LAST_BLOCK)
 
     host_out_u8 = torch.empty(host_out.shape, dtype=torch.uint8).pin_memory()
 
     def step_e2e_u8():
         # same call with a uint8 host buffer: pixel-space frames (VidReNormalize + clamp + uint8 on the device), D2H / 4
-        model.rollout(host_in, N_FUTURE, out_host=host_out_u8)
+        model.rollout(host_in, N_FUTURE, out_host=host_out_u8, last_block=LAST_BLOCK)
 
     def timed(step_fn, steps, warmup):
         for _ in range(warmup):
@@ -238,10 +244,10 @@ def run_ours(args):
         return float(ms.item())
 
     if args.profile:          # one warm rollout + one profiled rollout, nothing else (for `ncu -k ...` / launch lists)
-        model.rollout(x_dev, N_FUTURE)
+        model.rollout(x_dev, N_FUTURE, last_block=LAST_BLOCK)
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
-        model.rollout(x_dev, N_FUTURE)
+        model.rollout(x_dev, N_FUTURE, last_block=LAST_BLOCK)
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         return
@@ -265,7 +271,7 @@ def run_ours(args):
     if rank == 0:
         model.use_cuda_graphs(False)                           # per-launch events need eager launches
         with GemmTimer(ops) as gt:
-            model.rollout(x_dev, N_FUTURE)
+            model.rollout(x_dev, N_FUTURE, last_block=LAST_BLOCK)
         s = gt.summary()
         hbm, tf, which = load_peaks()
         ach = s["flops"] / s["seconds"] / 1e12 if s["seconds"] > 0 else 0.0

@@ -157,10 +157,27 @@ class NPVPInference(nn.Module):
             g = graphs[key] = _GraphedPredict(self, past_frames)
         return g(past_frames, eps)
 
+    def _short_block_coor(self, take: int):
+        """Target coordinates of the first ``take`` timestamps of ``tp_list``, cached on the device: the same tensor object is
+        handed to the predictor every time, so a captured CUDA graph of the short block is found again."""
+        cache = self.__dict__.setdefault("_short_coor", {})
+        dev = next(self.parameters()).device
+        key = (int(take), str(dev))
+        if key not in cache:
+            p = self.predictor
+            cache[key] = p.coor_generator(self.tp_list[:take], p.h_list, p.w_list).to(dev, torch.float32)
+        return cache[key]
+
     def rollout(self, past_frames, num_future: int, eps_list: Optional[Sequence[torch.Tensor]] = None,
-                out_host: Optional[torch.Tensor] = None, gather_group=None):
+                out_host: Optional[torch.Tensor] = None, gather_group=None, last_block: str = "truncate"):
         """Block-autoregressive VFP: predict len(tp_list) frames, feed the last To predictions back as context
-        (image space), repeat until ``num_future`` frames exist; the last block is truncated.
+        (image space), repeat until ``num_future`` frames exist.
+
+        ``last_block`` - when fewer than len(tp_list) frames remain (2 -> 28 = 10 + 10 + 8 with the shipped YAMLs):
+        "truncate" predicts the full block and drops the surplus frames; "query" asks the continuous-time decoder only for the
+        timestamps that are needed (the first ``take`` of ``tp_list`` - SURVEY.md section 8d, "third block's tp cut to 8"), which
+        skips the surplus frames' decoder and frame-decoder work.  The two differ in value (the target frames attend to each
+        other over time), both are block-autoregressive uses of the reference model.
 
         ``past_frames`` may be a (pinned) host tensor: it is uploaded asynchronously.  With ``out_host`` (a pinned host
         tensor (N, num_future, C, H, W)) every block's frames are streamed to the host on a copy stream while the next block
@@ -190,12 +207,22 @@ class NPVPInference(nn.Module):
             group = None if gather_group is True else gather_group
             world = dist.get_world_size(group)
         out, ctx, done, blk = None, past_frames, 0, 0
+        assert last_block in ("truncate", "query")
         while done < num_future:
             eps = None if eps_list is None else eps_list[blk]
-            pred = self.predict(ctx, eps)                    # may be a graph-owned buffer: copy out before the next block
+            take = min(Tp, num_future - done)
+            if take < Tp and last_block == "query":          # re-target the predictor at the timestamps still needed
+                p = self.predictor
+                saved = (p.predict_coor, p.TP)
+                p.predict_coor, p.TP = self._short_block_coor(take), take
+                try:
+                    pred = self.predict(ctx, eps)
+                finally:
+                    p.predict_coor, p.TP = saved
+            else:
+                pred = self.predict(ctx, eps)                # may be a graph-owned buffer: copy out before the next block
             if out is None:
                 out = torch.empty((pred.shape[0], num_future) + tuple(pred.shape[2:]), dtype=pred.dtype, device=pred.device)
-            take = min(Tp, num_future - done)
             out[:, done:done + take].copy_(pred[:, :take])
             src, s0 = out, done
             if as_u8:                                        # one kernel per block on the whole (N, Tp, C, H, W) prediction
@@ -221,6 +248,8 @@ class NPVPInference(nn.Module):
                 pending.append((dist.all_gather_into_tensor(allb, mine, group=group, async_op=True), allb, mine, done, take))
             done += take
             blk += 1
+            if done >= num_future:
+                break
             if Tp >= To:
                 ctx = out[:, done - To:done] if take == Tp else pred[:, Tp - To:Tp]
             else:

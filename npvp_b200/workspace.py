@@ -19,12 +19,16 @@ class Workspace:
         key = (name, tuple(int(s) for s in shape), dtype)
         buf = self._bufs.get(key)
         if buf is None:
-            # drop stale shapes of the same name so long-running processes do not accumulate dead buffers
-            for k in [k for k in self._bufs if k[0] == name]:
-                del self._bufs[k]
+            # Buffers of other shapes under the same name stay alive: a captured CUDA graph replays with the raw pointers of
+            # the shapes it was captured with (a rollout alternates between full and short blocks), so freeing them here
+            # would hand their memory to someone else under a live graph.  ``trim()`` releases everything explicitly.
             buf = torch.empty(key[1], dtype=dtype, device=self.device)
             self._bufs[key] = buf
         return buf
+
+    def trim(self):
+        """Release every cached buffer (only when no captured graph that used them will be replayed again)."""
+        self._bufs.clear()
 
     def bf16(self, name, *shape):
         return self.get(name, shape, torch.bfloat16)

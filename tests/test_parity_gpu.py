@@ -149,6 +149,39 @@ def test_rollout_block_autoregressive():
     assert torch.equal(out3, out) and torch.equal(host_out, out.cpu())
 
 
+def test_rollout_last_block_query_matches_oracle():
+    """rollout(last_block="query"): the short last block asks the decoder for the remaining timestamps only.  Checked against
+    the oracle driven the same way (pixel tolerance of the end-to-end path), and the predictor's coordinates are restored."""
+    from npvp_b200.pipeline import build_from_config
+    from util_init import seeded_rand, stress_init_
+    model = build_from_config("BAIR_VFP_NPVP-S", device="cpu", seed=0)
+    for i, m in enumerate((model.VPTR_Enc, model.VPTR_Dec, model.predictor)):
+        stress_init_(m, 40 + i)
+    x = seeded_rand((2, 2, 3, 64, 64), 6) * 2 - 1
+    eps = [torch.randn(2, 512, 8, 8, generator=torch.Generator().manual_seed(10 + i)) for i in range(2)]
+    cfg = model.cfg
+    ocfg = dict(n_downsampling=cfg.AE.n_downsampling, num_res_blocks=cfg.AE.num_res_blocks, out_layer=cfg.AE.out_layer, stochastic=True)
+    esd, psd, dsd = model.VPTR_Enc.state_dict(), model.predictor.state_dict(), model.VPTR_Dec.state_dict()
+    hl = torch.linspace(0, 7, 8)
+    short = O.coor_generator(model.tp_list[:3], hl, hl, cfg.Predictor.max_T, 8, 8)
+    b1 = O.npvp_predict_frames(esd, psd, dsd, x, ocfg, psd["observed_coor"], psd["predict_coor"], eps[0])
+    b2 = O.npvp_predict_frames(esd, psd, dsd, b1[:, 8:10], ocfg, psd["observed_coor"], short, eps[1])
+    ref = torch.cat([b1, b2], 1)
+    model = model.cuda()
+    coor_before = model.predictor.predict_coor
+    for graphs in (False, True):
+        model.use_cuda_graphs(graphs)
+        for _ in range(2):
+            out = model.rollout(x.cuda(), 13, [e.cuda() for e in eps], last_block="query")
+        assert out.shape == (2, 13, 3, 64, 64)
+        err = float((model.to_pixels(out).cpu() - _ref_pixels(model, ref)).abs().max())
+        print(f"rollout 10 + 3 (query), graphs={graphs}: max pixel err {err:.3e}")
+        assert err <= 1e-2
+        assert model.predictor.predict_coor is coor_before and model.predictor.TP == 10
+    trunc = model.rollout(x.cuda(), 13, [e.cuda() for e in eps])                 # default: full block, surplus dropped
+    assert torch.equal(trunc[:, :10], out[:, :10]) and not torch.equal(trunc[:, 10:], out[:, 10:])
+
+
 def test_batch_invariance_and_determinism():
     """Per-clip math never mixes clips: clip 0 alone == clip 0 inside a batch, bit for bit (basis of the multi-GPU check)."""
     from npvp_b200.pipeline import build_from_config
