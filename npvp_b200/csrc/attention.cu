@@ -18,6 +18,13 @@ constexpr int kMaxL = 32;
 constexpr int kWarpsPerBlock = 4;
 constexpr int kVStride = kHd + 8;   // halves per staged V row: 144 B keeps the 8 ldmatrix row addresses on distinct banks
 
+// Read-only 16-byte load.
+__device__ __forceinline__ uint4 ldg128_batched(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
 template <int MODE>
 __device__ __forceinline__ int64_t seq_row(int64_t s, int i, int T) {
   if (MODE == NPVP_ATTN_SPATIAL_WINDOW) {
@@ -55,11 +62,12 @@ __device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t u) {
   return pack_f16x2(f.x, f.y);
 }
 
-template <int MODE>
+// KT = key tiles of 8 held in registers: 2 for Lk <= 16 (every shipped configuration: windows of 16, T <= 12), 4 up to kMaxL.
+template <int MODE, int KT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 attention_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k, int64_t ldk, const bf16* __restrict__ v,
                  int64_t ldv, bf16* __restrict__ out, int64_t ldo, int Tq, int Tk, int mask_last) {
-  __shared__ __align__(16) __half sV[kWarpsPerBlock][kMaxL][kVStride];
+  __shared__ __align__(16) __half sV[kWarpsPerBlock][KT * 8][kVStride];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int64_t s = blockIdx.x;
@@ -70,53 +78,85 @@ attention_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict
   const int n_kt = (Lk + 7) >> 3;        // key tiles of 8 (S columns)
   const int n_kk = (Lk + 15) >> 4;       // key tiles of 16 (P V reduction steps)
 
-  // ---- stage V (rows = keys) as fp16, zero-padded to a multiple of 16 keys ----
-  for (int j = 0; j < n_kk * 16; ++j) {
-    uint32_t u = 0u;
-    if (j < Lk) u = bf16x2_to_f16x2(__ldg(reinterpret_cast<const uint32_t*>(v + seq_row<MODE>(s, j, Tk) * ldv + col) + lane));
-    reinterpret_cast<uint32_t*>(&sV[w][j][0])[lane] = u;
-  }
-  __syncwarp();
-
-  // ---- K as B fragments: key tile t (8 keys), d-step kk (16 dims): b0 = K[8t+gid][16kk+2tig..], b1 = ... +8 ----
-  uint32_t kb[4][4][2];
+  // A warp lives for one (sequence, head): ~5 KB of traffic, so its run time is the number of dependent global round trips
+  // and of memory instructions (the first version issued 48 4-byte loads and 16 4-byte stores per thread, half of every
+  // store sector unused, and ptxas sank the loads next to the mma that consumes them: 3 TB/s).  Every access is now 16 bytes:
+  //  * the contraction over the 64 head dims is a sum, so Q and K may enumerate the dims in any common order: thread `tig`
+  //    takes the 32 contiguous bytes [16 tig, 16 tig + 16) of a row and feeds dims 16 tig + 4 kk + {0,1} / + {2,3} to the
+  //    k-slots (2 tig, 2 tig + 1) / (2 tig + 8, 2 tig + 9) of step kk: 2 x LDG.128 per row instead of 8 x LDG.32;
+  //  * V is staged with its columns permuted (physical dim 16 t + 2 d + e -> column 8 d + 2 t + e), so the PV accumulators of
+  //    thread `tig` are the physical dims [16 tig, 16 tig + 16) of its two rows: 2 x STG.128 per row, full sectors.
+  // ---- V rows (keys): lane = (row 4 i + (lane >> 3), 16-byte chunk lane & 7) ----
+  const int vc = lane & 7, vr = lane >> 3;
+  uint4 vraw[KT * 2];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int i = 0; i < KT * 2; ++i) {
+    const int j = 4 * i + vr;
+    vraw[i] = (j < Lk) ? ldg128_batched(reinterpret_cast<const uint4*>(v + seq_row<MODE>(s, j, Tk) * ldv + col) + vc) : make_uint4(0u, 0u, 0u, 0u);
+  }
+
+  // ---- K as B fragments: key tile t (8 keys = n), step kk: b0 = kr[2 kk], b1 = kr[2 kk + 1] of the thread's 32 bytes ----
+  uint32_t kb[KT][4][2];
+#pragma unroll
+  for (int t = 0; t < KT; ++t) {
     const int j = 8 * t + gid;
     const bool ok = (t < n_kt) && (j < Lk);
-    const uint32_t* krow = reinterpret_cast<const uint32_t*>(k + (ok ? seq_row<MODE>(s, j, Tk) : 0) * ldk + col);
+    const uint4* krow = reinterpret_cast<const uint4*>(k + (ok ? seq_row<MODE>(s, j, Tk) : 0) * ldk + col) + 2 * tig;
+    const uint4 lo = ok ? ldg128_batched(krow) : make_uint4(0u, 0u, 0u, 0u), hi = ok ? ldg128_batched(krow + 1) : make_uint4(0u, 0u, 0u, 0u);
+    kb[t][0][0] = lo.x; kb[t][0][1] = lo.y; kb[t][1][0] = lo.z; kb[t][1][1] = lo.w;
+    kb[t][2][0] = hi.x; kb[t][2][1] = hi.y; kb[t][3][0] = hi.z; kb[t][3][1] = hi.w;
+  }
+
+  // ---- query block: a0 / a2 of step kk = the same two registers of row gid, a1 / a3 of row gid + 8 ----
+  uint32_t qa[4][4];
+  auto load_q = [&](int m0) {
+    const int r0 = m0 + gid, r1 = m0 + gid + 8;
+    const bool ok0 = r0 < Lq, ok1 = r1 < Lq;
+    const uint4* q0 = reinterpret_cast<const uint4*>(q + seq_row<MODE>(s, ok0 ? r0 : 0, Tq) * ldq + col) + 2 * tig;
+    const uint4* q1 = reinterpret_cast<const uint4*>(q + seq_row<MODE>(s, ok1 ? r1 : 0, Tq) * ldq + col) + 2 * tig;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 a_lo = ok0 ? ldg128_batched(q0) : z, a_hi = ok0 ? ldg128_batched(q0 + 1) : z;
+    const uint4 b_lo = ok1 ? ldg128_batched(q1) : z, b_hi = ok1 ? ldg128_batched(q1 + 1) : z;
+    qa[0][0] = a_lo.x; qa[0][2] = a_lo.y; qa[1][0] = a_lo.z; qa[1][2] = a_lo.w;
+    qa[2][0] = a_hi.x; qa[2][2] = a_hi.y; qa[3][0] = a_hi.z; qa[3][2] = a_hi.w;
+    qa[0][1] = b_lo.x; qa[0][3] = b_lo.y; qa[1][1] = b_lo.z; qa[1][3] = b_lo.w;
+    qa[2][1] = b_hi.x; qa[2][3] = b_hi.y; qa[3][1] = b_hi.z; qa[3][3] = b_hi.w;
+  };
+  load_q(0);
+
+  // ---- stage V as fp16 (exact copies of the bf16 values) with permuted columns; rows >= Lk are zero ----
+  {
+    const int cbase = 8 * ((vc & 1) * 4) + 2 * (vc >> 1);      // register i2 of the chunk -> columns cbase + 8 i2, + 1
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      kb[t][kk][0] = ok ? __ldg(krow + 8 * kk + tig) : 0u;
-      kb[t][kk][1] = ok ? __ldg(krow + 8 * kk + 4 + tig) : 0u;
+    for (int i = 0; i < KT * 2; ++i) {
+      __half* row = &sV[w][4 * i + vr][cbase];
+      *reinterpret_cast<uint32_t*>(row) = bf16x2_to_f16x2(vraw[i].x);
+      *reinterpret_cast<uint32_t*>(row + 8) = bf16x2_to_f16x2(vraw[i].y);
+      *reinterpret_cast<uint32_t*>(row + 16) = bf16x2_to_f16x2(vraw[i].z);
+      *reinterpret_cast<uint32_t*>(row + 24) = bf16x2_to_f16x2(vraw[i].w);
     }
   }
+  __syncwarp();
 
   for (int m0 = 0; m0 < Lq; m0 += 16) {
     const int r0 = m0 + gid, r1 = m0 + gid + 8;             // the two query rows this thread holds
     const bool ok0 = r0 < Lq, ok1 = r1 < Lq;
     const int64_t row0 = seq_row<MODE>(s, ok0 ? r0 : 0, Tq), row1 = seq_row<MODE>(s, ok1 ? r1 : 0, Tq);
-    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(q + row0 * ldq + col);
-    const uint32_t* q1 = reinterpret_cast<const uint32_t*>(q + row1 * ldq + col);
     // ---- S = Q K^T ----
-    float sc[4][4];
+    float sc[KT][4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.f; }
+    for (int t = 0; t < KT; ++t) { sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.f; }
+    if (m0 > 0) load_q(m0);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      uint32_t a[4];
-      a[0] = ok0 ? __ldg(q0 + 8 * kk + tig) : 0u;
-      a[1] = ok1 ? __ldg(q1 + 8 * kk + tig) : 0u;
-      a[2] = ok0 ? __ldg(q0 + 8 * kk + 4 + tig) : 0u;
-      a[3] = ok1 ? __ldg(q1 + 8 * kk + 4 + tig) : 0u;
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (t < n_kt) mma_bf16_16816(sc[t], a, kb[t][kk][0], kb[t][kk][1]);
+      for (int t = 0; t < KT; ++t)
+        if (t < n_kt) mma_bf16_16816(sc[t], qa[kk], kb[t][kk][0], kb[t][kk][1]);
     }
     // ---- softmax over keys (thread holds cols 8t+2tig, +1 of rows r0 (c0,c1) and r1 (c2,c3)) ----
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
+    for (int t = 0; t < KT; ++t)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = 8 * t + 2 * tig + e;
@@ -134,7 +174,7 @@ attention_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
+    for (int t = 0; t < KT; ++t)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const float p0 = (sc[t][e] == -INFINITY) ? 0.f : expf(sc[t][e] - mx0);
@@ -154,7 +194,7 @@ attention_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict
 #pragma unroll
     for (int d = 0; d < 8; ++d) { o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f; }
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
+    for (int kk = 0; kk < KT / 2; ++kk) {
       if (kk < n_kk) {
         uint32_t a[4];
         a[0] = pack_f16x2(sc[2 * kk][0] * inv0, sc[2 * kk][1] * inv0);
@@ -169,11 +209,16 @@ attention_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict
         }
       }
     }
-    // ---- store: thread holds dims 8d+2tig, +1 of rows r0 / r1 ----
-#pragma unroll
-    for (int d = 0; d < 8; ++d) {
-      if (ok0) reinterpret_cast<uint32_t*>(out + row0 * ldo + col)[4 * d + tig] = pack_bf16x2(o[d][0], o[d][1]);
-      if (ok1) reinterpret_cast<uint32_t*>(out + row1 * ldo + col)[4 * d + tig] = pack_bf16x2(o[d][2], o[d][3]);
+    // ---- store: the thread's 16 accumulator columns of a row are the physical dims 16 tig + 2 d + {0,1}: 32 contiguous bytes ----
+    if (ok0) {
+      uint4* dst = reinterpret_cast<uint4*>(out + row0 * ldo + col) + 2 * tig;
+      dst[0] = make_uint4(pack_bf16x2(o[0][0], o[0][1]), pack_bf16x2(o[1][0], o[1][1]), pack_bf16x2(o[2][0], o[2][1]), pack_bf16x2(o[3][0], o[3][1]));
+      dst[1] = make_uint4(pack_bf16x2(o[4][0], o[4][1]), pack_bf16x2(o[5][0], o[5][1]), pack_bf16x2(o[6][0], o[6][1]), pack_bf16x2(o[7][0], o[7][1]));
+    }
+    if (ok1) {
+      uint4* dst = reinterpret_cast<uint4*>(out + row1 * ldo + col) + 2 * tig;
+      dst[0] = make_uint4(pack_bf16x2(o[0][2], o[0][3]), pack_bf16x2(o[1][2], o[1][3]), pack_bf16x2(o[2][2], o[2][3]), pack_bf16x2(o[3][2], o[3][3]));
+      dst[1] = make_uint4(pack_bf16x2(o[4][2], o[4][3]), pack_bf16x2(o[5][2], o[5][3]), pack_bf16x2(o[6][2], o[6][3]), pack_bf16x2(o[7][2], o[7][3]));
     }
   }
 }
@@ -189,13 +234,17 @@ extern "C" int npvp_attention(const void* q, int64_t ldq, const void* k, int64_t
   if (mode == NPVP_ATTN_SPATIAL_WINDOW) {
     NPVP_REQUIRE(Tq == Tk, "npvp_attention: spatial window attention needs Tq == Tk");
     const int64_t nseq = n_clips * Tq * 4;
-    attention_kernel<NPVP_ATTN_SPATIAL_WINDOW><<<dim3((unsigned)nseq, kHeads / kWarpsPerBlock), block, 0, st>>>(
+    attention_kernel<NPVP_ATTN_SPATIAL_WINDOW, 2><<<dim3((unsigned)nseq, kHeads / kWarpsPerBlock), block, 0, st>>>(
         (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)out, ldo, Tq, Tk, 0);
   } else if (mode == NPVP_ATTN_TEMPORAL) {
     NPVP_REQUIRE(Tq <= kMaxL && Tk <= kMaxL, "npvp_attention: temporal length above %d not supported (Tq=%d Tk=%d)", kMaxL, Tq, Tk);
     const int64_t nseq = n_clips * 64;
-    attention_kernel<NPVP_ATTN_TEMPORAL><<<dim3((unsigned)nseq, kHeads / kWarpsPerBlock), block, 0, st>>>(
-        (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)out, ldo, Tq, Tk, mask_last);
+    if (Tk <= 16)
+      attention_kernel<NPVP_ATTN_TEMPORAL, 2><<<dim3((unsigned)nseq, kHeads / kWarpsPerBlock), block, 0, st>>>(
+          (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)out, ldo, Tq, Tk, mask_last);
+    else
+      attention_kernel<NPVP_ATTN_TEMPORAL, 4><<<dim3((unsigned)nseq, kHeads / kWarpsPerBlock), block, 0, st>>>(
+          (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)out, ldo, Tq, Tk, mask_last);
   } else {
     NPVP_REQUIRE(false, "npvp_attention: unknown mode %d", mode);
   }
