@@ -112,11 +112,14 @@ int npvp_fourier_features(const float* coor, const float* B, float* out, int64_t
 /* Fused  a = LayerNorm_C(x) ; u = a + qe ; fused = GroupNorm1(u over the frame) * (1+gamma) + beta
  * (VidHRFormer.py:87-88,95-96,210-212,218-219,229,236 + PosFeatFuser submodules.py:432-454).
  * x fp32 [n_clips*T, 64, 512]; ln_w/ln_b fp32 [512] or NULL (no LayerNorm: a = x);
- * qe fp32 [n_clips, 64, 512] or NULL; beta fp32 [T,64,512]; gamma fp32 [T,64,512] or NULL;
+ * qe fp32 [n_clips, 64, 512] or NULL; beta fp32 [pos_frames,64,512]; gamma fp32 [pos_frames,64,512] or NULL;
+ * pos_frames = T (or 0): one set of timestamps shared by the batch, like the reference's per-module coordinates
+ * (Predictor.py:352-359); pos_frames = n_clips * T: every clip has its own timestamps (a batch mixing prediction,
+ * interpolation and arbitrary continuous-time queries);
  * out_ln (bf16, optional) receives a; out_fused (bf16, optional) receives fused. */
 int npvp_ln_posfuse(const float* x, const float* ln_w, const float* ln_b, const float* qe, const float* beta,
                     const float* gamma, void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T,
-                    void* stream);
+                    int64_t pos_frames, void* stream);
 /* LayerNorm over C=512 per token (VidHRFormer.py:91,110,214,224,243; final norm :48,:151 with relu=1 for :159).
  * Outputs optional fp32 and/or bf16. */
 int npvp_layernorm_rows(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16,
@@ -127,7 +130,8 @@ int npvp_layernorm_rows(const float* x, const float* w, const float* b, float* o
 int npvp_add_layernorm_rows(float* x, const void* delta_bf16, const float* w, const float* b, float* out_f32, void* out_bf16,
                             int64_t rows, int relu, int fp16, void* stream);
 int npvp_add_ln_posfuse(float* x, const void* delta_bf16, const float* ln_w, const float* ln_b, const float* qe, const float* beta,
-                        const float* gamma, void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T, void* stream);
+                        const float* gamma, void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T, int64_t pos_frames,
+                        void* stream);
 /* y += GELU(LayerNorm_(C,8,8)(h))  - MlpDWBN norm3 + act3 + the block's residual add
  * (VidHRFormer.py:388-389 with :91/:214/:243).  h [frames,64,512] fp32 (h_is_bf16 = 0) or bf16 (1: the fc2 GEMM's 16-bit
  * output; h is normalised right here, so its rounding is harmless); w,b fp32 [64,512] (hw-major). */
@@ -137,7 +141,8 @@ int npvp_frame_ln_gelu_residual(const void* h, int h_is_bf16, const float* w_hwc
  * npvp_ln_posfuse on the new y (VidHRFormer.py:91 -> :95-96, :214 -> :218-219, :243 -> next layer's :210-212). */
 int npvp_frame_ln_gelu_residual_posfuse(const void* h, int h_is_bf16, const float* w_hwc, const float* b_hwc, float* y, const float* ln_w,
                                         const float* ln_b, const float* qe, const float* beta, const float* gamma,
-                                        void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T, void* stream);
+                                        void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T, int64_t pos_frames,
+                                        void* stream);
 /* mean over time of the memory (Predictor.py:346): mem fp32 [n,T,64*512] -> evt fp32 [n,64*512]. */
 int npvp_temporal_mean(const float* mem, float* evt, int64_t n_clips, int64_t T, int64_t frame_elems, void* stream);
 

@@ -38,12 +38,12 @@ SIGNATURES = {
                             C.POINTER(Epilogue), _vp],
     "npvp_gemm_f32": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i32, _vp, _i64, _vp],
     "npvp_fourier_features": [_vp, _vp, _vp, _i64, _i32, _vp],
-    "npvp_ln_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "npvp_ln_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     "npvp_add_layernorm_rows": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
-    "npvp_add_ln_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "npvp_add_ln_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     "npvp_layernorm_rows": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "npvp_frame_ln_gelu_residual": [_vp, _i32, _vp, _vp, _vp, _i64, _vp],
-    "npvp_frame_ln_gelu_residual_posfuse": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "npvp_frame_ln_gelu_residual_posfuse": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     "npvp_temporal_mean": [_vp, _vp, _i64, _i64, _i64, _vp],
     "npvp_ffn_frame_stats": [_vp, _vp, _i64, _i64, _vp],
     "npvp_ffn_stats_finalize": [_vp, _i64, _vp, _i64, _i64, _vp],
@@ -230,9 +230,8 @@ class Ops:
         _chk(out_ln, torch.bfloat16, "out_ln"); _chk(out_fused, torch.bfloat16, "out_fused")
         assert x.numel() == n_clips * T * 64 * 512
         assert qe is None or qe.numel() == n_clips * 64 * 512
-        assert beta is None or beta.numel() == T * 64 * 512
         self._call("npvp_ln_posfuse", x.data_ptr(), _ptr(ln_w), _ptr(ln_b), _ptr(qe), _ptr(beta), _ptr(gamma), _ptr(out_ln),
-                   _ptr(out_fused), n_clips, T, self._stream())
+                   _ptr(out_fused), n_clips, T, _pos_frames(beta, gamma, n_clips, T), self._stream())
 
     def add_layernorm_rows(self, x, delta, w, b, out_f32=None, out_bf16=None, relu=False):
         """x += delta (deferred residual, written back), then LayerNorm(512) of the updated rows."""
@@ -249,7 +248,7 @@ class Ops:
         _chk(out_ln, torch.bfloat16, "out_ln"); _chk(out_fused, torch.bfloat16, "out_fused")
         assert x.numel() == n_clips * T * 64 * 512 and delta.numel() == x.numel()
         self._call("npvp_add_ln_posfuse", x.data_ptr(), delta.data_ptr(), _ptr(ln_w), _ptr(ln_b), _ptr(qe), _ptr(beta), _ptr(gamma),
-                   _ptr(out_ln), _ptr(out_fused), n_clips, T, self._stream())
+                   _ptr(out_ln), _ptr(out_fused), n_clips, T, _pos_frames(beta, gamma, n_clips, T), self._stream())
 
     def layernorm_rows(self, x, w, b, out_f32=None, out_bf16=None, relu=False):
         _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(b, torch.float32, "b")
@@ -276,7 +275,8 @@ class Ops:
         assert h.numel() == n_clips * T * 64 * 512 and y.numel() == h.numel()
         self._call("npvp_frame_ln_gelu_residual_posfuse", h.data_ptr(), int(h.dtype == torch.bfloat16), w_hwc.data_ptr(), b_hwc.data_ptr(),
                    y.data_ptr(), _ptr(ln_w),
-                   _ptr(ln_b), _ptr(qe), _ptr(beta), _ptr(gamma), _ptr(out_ln), _ptr(out_fused), n_clips, T, self._stream())
+                   _ptr(ln_b), _ptr(qe), _ptr(beta), _ptr(gamma), _ptr(out_ln), _ptr(out_fused), n_clips, T,
+                   _pos_frames(beta, gamma, n_clips, T), self._stream())
 
     def temporal_mean(self, mem, evt, n_clips, T):
         _chk(mem, torch.float32, "mem"); _chk(evt, torch.float32, "evt")
@@ -487,6 +487,17 @@ def unpack_head_weights(p: torch.Tensor, Cout: int) -> torch.Tensor:
     b5[:, :, _head_frag_index(p.device), :, :] = frag
     full = b5.reshape(P, 7, 2, 16, NT * 8).permute(1, 0, 2, 3, 4).reshape(7, P * 32, NT * 8)[:, :, :7 * Cout]
     return full.reshape(7, P * 32, 7, Cout).permute(0, 2, 1, 3).reshape(49 * P * 32, Cout).contiguous()
+
+
+def _pos_frames(beta, gamma, n_clips, T):
+    """Frames covered by the positional code: T (timestamps shared by the batch) or n_clips * T (per-clip timestamps)."""
+    if beta is None:
+        return 0
+    frames = beta.numel() // (64 * 512)
+    assert beta.numel() == frames * 64 * 512 and frames in (T, n_clips * T), \
+        f"positional code covers {frames} frames; expected T = {T} or n_clips * T = {n_clips * T}"
+    assert gamma is None or gamma.numel() == beta.numel()
+    return frames
 
 
 FFN_CHUNK = 128        # channels per partial-statistics chunk of the conv-FFN middle (kFfnChunk in predictor_kernels.cu)

@@ -183,11 +183,11 @@ __device__ __forceinline__ void frame_stats(const FrameRegs& r, float* red, Fram
 // a = LN(x); u = a + qe; fused = GN1(u) * (1 + gamma) + beta
 // ---------------------------------------------------------------------------------------------
 // r holds this block's quarter of the frame in fp32; applies the optional token LayerNorm, writes `a`, then the positional fuse.
-__device__ __forceinline__ void posfuse_from_regs(FrameRegs& r, float* red, FrameXchg& xc, int f, int T, const float* __restrict__ ln_w,
+__device__ __forceinline__ void posfuse_from_regs(FrameRegs& r, float* red, FrameXchg& xc, int f, int T, int Tpos, const float* __restrict__ ln_w,
                                                   const float* __restrict__ ln_b, const float* __restrict__ qe,
                                                   const float* __restrict__ beta, const float* __restrict__ gamma,
                                                   bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int tok0, int lane) {
-  const int n = f / T, t_idx = f % T;
+  const int n = f / T, t_idx = f % Tpos;      // Tpos = T: one timestamp set for the batch; n_clips * T: per-clip timestamps
   if (ln_w) {
     float4 w[4], b[4];
 #pragma unroll
@@ -251,7 +251,7 @@ __device__ __forceinline__ void frame_add_delta(float* __restrict__ x, const bf1
 __global__ void __cluster_dims__(kFrameCL, 1, 1) __launch_bounds__(kFrameThreads, 4)
 ln_posfuse_kernel(float* __restrict__ x, const bf16* __restrict__ delta, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                   const float* __restrict__ qe, const float* __restrict__ beta, const float* __restrict__ gamma,
-                  bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int T) {
+                  bf16* __restrict__ out_ln, bf16* __restrict__ out_fused, int T, int Tpos) {
   __shared__ float red[64];
   __shared__ __align__(8) FrameXchg xc;
   frame_xchg_init(xc);
@@ -260,31 +260,33 @@ ln_posfuse_kernel(float* __restrict__ x, const bf16* __restrict__ delta, const f
   FrameRegs r;
   frame_load(x + (size_t)f * kTok * kC, r, tok0, lane);
   if (delta) frame_add_delta(x + (size_t)f * kTok * kC, delta + (size_t)f * kTok * kC, r, tok0, lane);
-  posfuse_from_regs(r, red, xc, f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, tok0, lane);
+  posfuse_from_regs(r, red, xc, f, T, Tpos, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, tok0, lane);
 }
 
 extern "C" int npvp_ln_posfuse(const float* x, const float* ln_w, const float* ln_b, const float* qe, const float* beta,
                                const float* gamma, void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T,
-                               void* stream) {
+                               int64_t pos_frames, void* stream) {
   NPVP_REQUIRE(x && (out_ln_bf16 || out_fused_bf16), "npvp_ln_posfuse: null pointer");
   NPVP_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "npvp_ln_posfuse: ln_w/ln_b must both be set or both NULL");
   NPVP_REQUIRE(!out_fused_bf16 || beta, "npvp_ln_posfuse: beta required for the fused output");
   NPVP_REQUIRE(n_clips > 0 && T > 0, "npvp_ln_posfuse: empty input");
+  NPVP_REQUIRE(pos_frames == 0 || pos_frames == T || pos_frames == n_clips * T, "npvp_ln_posfuse: pos_frames must be 0, T or n_clips * T");
   ln_posfuse_kernel<<<(unsigned)(n_clips * T * kFrameCL), kFrameThreads, 0, (cudaStream_t)stream>>>(const_cast<float*>(x), nullptr, ln_w, ln_b, qe, beta, gamma,
-                                                                              (bf16*)out_ln_bf16, (bf16*)out_fused_bf16, (int)T);
+                                                                              (bf16*)out_ln_bf16, (bf16*)out_fused_bf16, (int)T, (int)(pos_frames ? pos_frames : T));
   NPVP_LAUNCH_CHECK("ln_posfuse_kernel");
   return NPVP_OK;
 }
 
 extern "C" int npvp_add_ln_posfuse(float* x, const void* delta_bf16, const float* ln_w, const float* ln_b, const float* qe,
                                    const float* beta, const float* gamma, void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips,
-                                   int64_t T, void* stream) {
+                                   int64_t T, int64_t pos_frames, void* stream) {
   NPVP_REQUIRE(x && delta_bf16 && (out_ln_bf16 || out_fused_bf16), "npvp_add_ln_posfuse: null pointer");
   NPVP_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "npvp_add_ln_posfuse: ln_w/ln_b must both be set or both NULL");
   NPVP_REQUIRE(!out_fused_bf16 || beta, "npvp_add_ln_posfuse: beta required for the fused output");
   NPVP_REQUIRE(n_clips > 0 && T > 0, "npvp_add_ln_posfuse: empty input");
+  NPVP_REQUIRE(pos_frames == 0 || pos_frames == T || pos_frames == n_clips * T, "npvp_add_ln_posfuse: pos_frames must be 0, T or n_clips * T");
   ln_posfuse_kernel<<<(unsigned)(n_clips * T * kFrameCL), kFrameThreads, 0, (cudaStream_t)stream>>>(x, (const bf16*)delta_bf16, ln_w, ln_b, qe, beta, gamma,
-                                                                              (bf16*)out_ln_bf16, (bf16*)out_fused_bf16, (int)T);
+                                                                              (bf16*)out_ln_bf16, (bf16*)out_fused_bf16, (int)T, (int)(pos_frames ? pos_frames : T));
   NPVP_LAUNCH_CHECK("ln_posfuse_kernel<add>");
   return NPVP_OK;
 }
@@ -349,7 +351,7 @@ extern "C" int npvp_add_layernorm_rows(float* x, const void* delta_bf16, const f
 template <bool TAIL>
 __global__ void __cluster_dims__(kFrameCL, 1, 1) __launch_bounds__(kFrameThreads, 4)
 frame_ln_gelu_residual_kernel(const void* __restrict__ h, int h_is_bf16, const float* __restrict__ w_hwc, const float* __restrict__ b_hwc,
-                              float* __restrict__ y, int T, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                              float* __restrict__ y, int T, int Tpos, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                               const float* __restrict__ qe, const float* __restrict__ beta, const float* __restrict__ gamma,
                               bf16* __restrict__ out_ln, bf16* __restrict__ out_fused) {
   __shared__ float red[64];
@@ -381,13 +383,13 @@ frame_ln_gelu_residual_kernel(const void* __restrict__ h, int h_is_bf16, const f
     }
   }
   // fused consumer: the next op of every block is LayerNorm + positional fuse of the stream just updated
-  if (TAIL) posfuse_from_regs(r, red, xc, f, T, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, tok0, lane);
+  if (TAIL) posfuse_from_regs(r, red, xc, f, T, Tpos, ln_w, ln_b, qe, beta, gamma, out_ln, out_fused, tok0, lane);
 }
 
 extern "C" int npvp_frame_ln_gelu_residual(const void* h, int h_is_bf16, const float* w_hwc, const float* b_hwc, float* y, int64_t frames,
                                            void* stream) {
   NPVP_REQUIRE(h && w_hwc && b_hwc && y && frames > 0, "npvp_frame_ln_gelu_residual: bad arguments");
-  frame_ln_gelu_residual_kernel<false><<<(unsigned)(frames * kFrameCL), kFrameThreads, 0, (cudaStream_t)stream>>>(h, h_is_bf16, w_hwc, b_hwc, y, 1, nullptr, nullptr, nullptr,
+  frame_ln_gelu_residual_kernel<false><<<(unsigned)(frames * kFrameCL), kFrameThreads, 0, (cudaStream_t)stream>>>(h, h_is_bf16, w_hwc, b_hwc, y, 1, 1, nullptr, nullptr, nullptr,
                                                                                           nullptr, nullptr, nullptr, nullptr);
   NPVP_LAUNCH_CHECK("frame_ln_gelu_residual_kernel");
   return NPVP_OK;
@@ -395,12 +397,16 @@ extern "C" int npvp_frame_ln_gelu_residual(const void* h, int h_is_bf16, const f
 
 extern "C" int npvp_frame_ln_gelu_residual_posfuse(const void* h, int h_is_bf16, const float* w_hwc, const float* b_hwc, float* y, const float* ln_w,
                                                    const float* ln_b, const float* qe, const float* beta, const float* gamma,
-                                                   void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T, void* stream) {
+                                                   void* out_ln_bf16, void* out_fused_bf16, int64_t n_clips, int64_t T, int64_t pos_frames,
+                                                   void* stream) {
   NPVP_REQUIRE(h && w_hwc && b_hwc && y && n_clips > 0 && T > 0, "npvp_frame_ln_gelu_residual_posfuse: bad arguments");
   NPVP_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "npvp_frame_ln_gelu_residual_posfuse: ln_w/ln_b must both be set or both NULL");
   NPVP_REQUIRE((out_ln_bf16 || out_fused_bf16) && (!out_fused_bf16 || beta), "npvp_frame_ln_gelu_residual_posfuse: outputs / beta missing");
+  NPVP_REQUIRE(pos_frames == 0 || pos_frames == T || pos_frames == n_clips * T,
+               "npvp_frame_ln_gelu_residual_posfuse: pos_frames must be 0, T or n_clips * T");
   frame_ln_gelu_residual_kernel<true><<<(unsigned)(n_clips * T * kFrameCL), kFrameThreads, 0, (cudaStream_t)stream>>>(
-      h, h_is_bf16, w_hwc, b_hwc, y, (int)T, ln_w, ln_b, qe, beta, gamma, (bf16*)out_ln_bf16, (bf16*)out_fused_bf16);
+      h, h_is_bf16, w_hwc, b_hwc, y, (int)T, (int)(pos_frames ? pos_frames : T), ln_w, ln_b, qe, beta, gamma, (bf16*)out_ln_bf16,
+      (bf16*)out_fused_bf16);
   NPVP_LAUNCH_CHECK("frame_ln_gelu_residual_kernel<posfuse>");
   return NPVP_OK;
 }

@@ -400,7 +400,7 @@ class PredictorEngine:
         if post is None:
             post = self._evt_post = _EventEnc(self.mod.evt_posterior, True)
         tok, n2, Tp = self._to_tokens(gt, channels_last, "x_encp")
-        assert n2 == n and Tp * TOK == beta_p.shape[0], "predict_features_gt must hold one frame per target timestamp"
+        assert n2 == n and beta_p.shape[0] in (Tp * TOK, n * Tp * TOK), "predict_features_gt must hold one frame per target timestamp"
         mem_p, _ = self.encode(tok, beta_p, gamma_p, n, Tp, tag="encp")
         evt_p = self.ws.f32("evt_p", n * TOK, C)
         _lib.ops().temporal_mean(mem_p, evt_p, n, Tp)
@@ -419,8 +419,13 @@ class PredictorEngine:
         assert K >= 1 and (K == 1 or self.stochastic), "several samples per clip only make sense for the stochastic model (NPVP-S)"
         x, n, To = self._to_tokens(observed, channels_last, "x_enc")
         oc, pc = mod.observed_coor, mod.predict_coor
-        assert oc.shape[0] == To * TOK, f"observed_coor has {oc.shape[0] // TOK} timestamps but the input has {To} frames"
-        Tp = pc.shape[0] // TOK
+        per_clip = int(getattr(mod, "_coor_clips", 0))      # > 0: every clip has its own timestamps (reset_pos_coor_per_clip)
+        if per_clip:
+            assert per_clip == n, f"per-clip timestamps were set for {per_clip} clips but the batch has {n}"
+            assert K == 1, "several samples per clip with per-clip timestamps are not supported"
+        assert oc.shape[0] == (per_clip or 1) * To * TOK, \
+            f"observed_coor has {oc.shape[0] // TOK // (per_clip or 1)} timestamps but the input has {To} frames"
+        Tp = pc.shape[0] // TOK // (per_clip or 1)
         assert Tp <= 32 and To <= 32, "temporal attention kernels hold at most 32 timestamps per sequence"
         (beta_o, gamma_o), (beta_p, gamma_p) = self._positional_pair(oc, pc)
         mem, mem_bf = self.encode(x, beta_o, gamma_o, n, To)

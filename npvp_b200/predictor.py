@@ -67,6 +67,7 @@ class Predictor(_EngineModule):
         # stochastic path reproducible; ``None`` samples torch.randn on the input's device like the reference.
         self.injected_eps = None
         self.last_latent = None
+        self._coor_clips = 0          # > 0 after reset_pos_coor_per_clip: number of clips the coordinate buffers describe
 
     # -- reference API ------------------------------------------------------------------------------
     def reset_pos_coor(self, to_list, tp_list):
@@ -78,6 +79,26 @@ class Predictor(_EngineModule):
         self.predict_coor = self.coor_generator(tp_list, self.h_list, self.w_list).to(device)
         self.observed_coor = self.coor_generator(to_list, self.h_list, self.w_list).to(device)
         self.TP = tp_list.shape[0]
+        self._coor_clips = 0
+
+    def reset_pos_coor_per_clip(self, to_lists, tp_lists):
+        """Extension of ``reset_pos_coor`` (the reference shares one timestamp set per module, Predictor.py:352-359, so a
+        "mixed" batch is a sequence of calls there): ``to_lists`` (N, To) and ``tp_lists`` (N, Tp) give every clip of the next
+        batches its own context / target timestamps - prediction, interpolation and arbitrary continuous-time queries in one
+        batch.  Clip i computes exactly what ``reset_pos_coor(to_lists[i], tp_lists[i])`` followed by a forward of clip i alone
+        computes (per-clip arithmetic is batch invariant).  ``reset_pos_coor`` switches back to shared timestamps."""
+        to_lists, tp_lists = torch.as_tensor(to_lists, dtype=torch.float32), torch.as_tensor(tp_lists, dtype=torch.float32)
+        assert to_lists.dim() == 2 and tp_lists.dim() == 2 and to_lists.shape[0] == tp_lists.shape[0], \
+            "expected (N, To) and (N, Tp) timestamp tables"
+        try:
+            device = self.observed_coor.device
+        except AttributeError:
+            device = self.all_coor.device
+        gen = lambda tl: torch.cat([self.coor_generator(t, self.h_list, self.w_list) for t in tl], 0).to(device)
+        self.predict_coor = gen(tp_lists)
+        self.observed_coor = gen(to_lists)
+        self.TP = tp_lists.shape[1]
+        self._coor_clips = int(to_lists.shape[0])
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
         # observed_coor / predict_coor follow the *current* (to, tp): a checkpoint saved after reset_pos_coor

@@ -111,8 +111,10 @@ class SpecOps:
         mu = flat.mean(-1, keepdim=True)
         var = ((flat - mu) ** 2).mean(-1, keepdim=True)
         nrm = ((flat - mu) * torch.rsqrt(var + EPS)).reshape(n_clips, T, 64, 512)
-        g = 0.0 if gamma is None else gamma.reshape(1, T, 64, 512)
-        out_fused.copy_((nrm * (1.0 + g) + beta.reshape(1, T, 64, 512)).reshape(out_fused.shape).to(torch.bfloat16))
+        nb = beta.numel() // (T * 64 * 512)          # 1: timestamps shared by the batch; n_clips: per-clip timestamps
+        assert nb in (1, n_clips)
+        g = 0.0 if gamma is None else gamma.reshape(nb, T, 64, 512)
+        out_fused.copy_((nrm * (1.0 + g) + beta.reshape(nb, T, 64, 512)).reshape(out_fused.shape).to(torch.bfloat16))
 
     def add_layernorm_rows(self, x, delta, w, b, out_f32=None, out_bf16=None, relu=False):
         x.add_(delta.float().reshape(x.shape))

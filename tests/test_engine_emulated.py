@@ -55,6 +55,32 @@ def test_predictor_engine_posterior_branch(name):
     assert torch.equal(eng.run(x), outs[0])         # same prediction with and without the ground truth
 
 
+def test_predictor_engine_per_clip_timestamps():
+    """reset_pos_coor_per_clip: clip i of a mixed batch == the oracle run on clip i with its own timestamps."""
+    from npvp_b200.engine_predictor import PredictorEngine
+    mod, x, eps, _, _ = build_predictor_case("pred_S_stress_realT")
+    x = torch.cat([x, x.flip(1) * 0.5 + 0.1], 0)                      # two clips, 3 context frames each
+    eps = torch.cat([eps, eps.flip(1)], 0)
+    to = torch.tensor([[0., 1., 4.], [0., 7., 8.]])                   # clip 0: prediction-like, clip 1: interpolation-like
+    tp = torch.tensor([[2., 2.5, 3., 5.], [1., 3.25, 4., 6.5]])
+    sd = mod.state_dict()
+    hl = torch.linspace(0, 7, 8)
+    refs = []
+    for i in range(2):
+        oc = O.coor_generator(to[i], hl, hl, mod.max_T, 8, 8)
+        pc = O.coor_generator(tp[i], hl, hl, mod.max_T, 8, 8)
+        refs.append(O.predictor_forward(sd, x[i:i + 1], oc, pc, True, eps[i:i + 1]))
+    ref = torch.cat(refs, 0)
+    mod.reset_pos_coor_per_clip(to, tp)
+    mod.injected_eps = eps
+    out = PredictorEngine(mod).run(x)
+    assert out.shape == ref.shape == (2, 4, 512, 8, 8)
+    assert _rel(out, ref) < 3e-2, _rel(out, ref)
+    mod.reset_pos_coor(to[0], tp[0])                                  # back to shared timestamps
+    mod.injected_eps = eps[:1]
+    assert _rel(PredictorEngine(mod).run(x[:1]), refs[0]) < 3e-2
+
+
 @pytest.mark.parametrize("name", AE_CASES)
 def test_autoencoder_engine_vs_oracle(name):
     from npvp_b200.engine_autoencoder import DecoderEngine, EncoderEngine

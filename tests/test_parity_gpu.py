@@ -182,6 +182,34 @@ def test_rollout_last_block_query_matches_oracle():
     assert torch.equal(trunc[:, :10], out[:, :10]) and not torch.equal(trunc[:, 10:], out[:, 10:])
 
 
+def test_per_clip_timestamps_mixed_batch():
+    """A batch mixing tasks (per-clip context / target timestamps, BASELINE config 2 "mixed ... continuous-time queries"):
+    clip i == the oracle on clip i with its own timestamps, and == the module re-targeted at clip i's timestamps, bit for bit."""
+    mod, x, eps, _, _ = build_predictor_case("pred_S_stress_realT")
+    x = torch.cat([x, x.flip(1) * 0.5 + 0.1, x * 0.8], 0)
+    eps = torch.cat([eps, eps.flip(1), -eps], 0)
+    to = torch.tensor([[0., 1., 4.], [0., 7., 8.], [2., 2.5, 3.]])
+    tp = torch.tensor([[2., 2.5, 3., 5.], [1., 3.25, 4., 6.5], [0., 1., 3.5, 9.]])
+    sd = mod.state_dict()
+    hl = torch.linspace(0, 7, 8)
+    refs = [O.predictor_forward(sd, x[i:i + 1], O.coor_generator(to[i], hl, hl, mod.max_T, 8, 8),
+                                O.coor_generator(tp[i], hl, hl, mod.max_T, 8, 8), True, eps[i:i + 1]) for i in range(3)]
+    mod = mod.cuda()
+    mod.reset_pos_coor_per_clip(to, tp)
+    mod.injected_eps = eps.cuda()
+    out = mod(x.cuda())
+    assert out.shape == (3, 4, 512, 8, 8)
+    for i in range(3):
+        r = _rel(out[i:i + 1].cpu(), refs[i])
+        print(f"mixed batch clip {i}: rel err vs oracle {r:.3e}")
+        assert r < 3e-2
+        mod.reset_pos_coor(to[i], tp[i])
+        mod.injected_eps = eps[i:i + 1].cuda()
+        assert torch.equal(mod(x[i:i + 1].cuda()), out[i:i + 1])
+        mod.reset_pos_coor_per_clip(to, tp)
+        mod.injected_eps = eps.cuda()
+
+
 def test_batch_invariance_and_determinism():
     """Per-clip math never mixes clips: clip 0 alone == clip 0 inside a batch, bit for bit (basis of the multi-GPU check)."""
     from npvp_b200.pipeline import build_from_config

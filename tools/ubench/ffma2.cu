@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(512) k(float* out, float a, float b, int iters
 #pragma unroll
       for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(a), "f"(b));
     }
-  } else {
+  } else if (MODE == 1) {
     unsigned long long p[8], aa, bb;
     asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
     asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
@@ -22,6 +22,29 @@ __global__ void __launch_bounds__(512) k(float* out, float a, float b, int iters
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(aa), "l"(bb));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm("mov.b64 {%0, %1}, %2;" : "=f"(x[2 * i]), "=f"(x[2 * i + 1]) : "l"(p[i]));
+  }
+  if (MODE == 2) {            // scalar, three distinct register operands per FMA (no operand reuse between neighbours)
+    float y[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = a + i * 1e-6f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(y[i]), "f"(y[(i + 5) & 15]));
+    }
+  }
+  if (MODE == 3) {            // packed, three distinct 64-bit register operands per FFMA2
+    unsigned long long p[8], y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      asm("mov.b64 %0, {%1, %2};" : "=l"(p[i]) : "f"(x[2 * i]), "f"(x[2 * i + 1]));
+      asm("mov.b64 %0, {%1, %2};" : "=l"(y[i]) : "f"(a + i * 1e-6f), "f"(a - i * 1e-6f));
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(y[i]), "l"(y[(i + 3) & 7]));
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) asm("mov.b64 {%0, %1}, %2;" : "=f"(x[2 * i]), "=f"(x[2 * i + 1]) : "l"(p[i]));
@@ -56,7 +79,9 @@ void run(const char* name, int iters) {
 int main() {
   run<0>("FFMA  (scalar, 16 chains/thread)", 1 << 14);
   run<1>("FFMA2 (packed,  8 chains/thread)", 1 << 14);
-  run<0>("FFMA  (scalar, 16 chains/thread)", 1 << 14);
-  run<1>("FFMA2 (packed,  8 chains/thread)", 1 << 14);
+  run<2>("FFMA  (scalar, distinct operands)", 1 << 14);
+  run<3>("FFMA2 (packed, distinct operands)", 1 << 14);
+  run<2>("FFMA  (scalar, distinct operands)", 1 << 14);
+  run<3>("FFMA2 (packed, distinct operands)", 1 << 14);
   return 0;
 }
