@@ -180,6 +180,14 @@ class GemmTimer:
         rows = [(e0.elapsed_time(e1) * 1e-3, fl, shp) for e0, e1, fl, shp in self.records]
         big = [r for r in rows if r[2][2] >= 64]      # launches on the tcgen05 path (K >= 64; everything else is the SIMT kernel)
         t, f = sum(r[0] for r in big), sum(r[1] for r in big)
+        if os.environ.get("NPVP_BENCH_GEMM_TABLE"):    # per-shape table on stderr (profiles/*_gemm_shapes.md)
+            agg = {}
+            for sec, fl, shp in rows:
+                a = agg.setdefault(shp, [0, 0.0, 0.0])
+                a[0] += 1; a[1] += sec; a[2] += fl
+            print("| M | N | K | launches | total ms | avg us | TFLOP/s |\n|---:|---:|---:|---:|---:|---:|---:|", file=sys.stderr)
+            for shp, (n, sec, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                print(f"| {shp[0]} | {shp[1]} | {shp[2]} | {n} | {sec * 1e3:.3f} | {sec / n * 1e6:.1f} | {fl / sec * 1e-12:.0f} |", file=sys.stderr)
         return {"launches": len(big), "seconds": t, "flops": f, "all_gemm_seconds": sum(r[0] for r in rows)}
 
 

@@ -167,9 +167,10 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 // The autoencoder runs in half (its errors go straight to pixels), the predictor in bfloat16 (range safety).
 typedef uint16_t h16;
 __device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi, int fp16) {
-  if (fp16) {
-    __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
-    return *reinterpret_cast<uint32_t*>(&v);
+  if (fp16) {                                  // one F2FP.SATFINITE: round to nearest, |x| > 65504 -> +-65504 (was 4 FMNMX + F2FP)
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
   }
   return pack_bf16x2(lo, hi);
 }
