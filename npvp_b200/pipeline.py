@@ -169,7 +169,8 @@ class NPVPInference(nn.Module):
         return cache[key]
 
     def rollout(self, past_frames, num_future: int, eps_list: Optional[Sequence[torch.Tensor]] = None,
-                out_host: Optional[torch.Tensor] = None, gather_group=None, last_block: str = "truncate"):
+                out_host: Optional[torch.Tensor] = None, gather_group=None, last_block: str = "truncate",
+                wait_output: bool = True):
         """Block-autoregressive VFP: predict len(tp_list) frames, feed the last To predictions back as context
         (image space), repeat until ``num_future`` frames exist.
 
@@ -184,6 +185,10 @@ class NPVPInference(nn.Module):
         computes, and the caller's stream waits for the last copy before the call returns control of ``out_host``.
         A ``torch.uint8`` ``out_host`` receives pixel-space frames (``to_pixels(uint8=True)``, converted on the device block
         by block): a quarter of the D2H bytes of the fp32 model-space frames.
+
+        ``wait_output=False`` (with ``out_host``): the caller's stream does not wait for the last block's device-to-host copy;
+        ``self.output_ready`` (a CUDA event recorded on the copy stream) says when ``out_host`` is complete.  A serving loop
+        that calls ``rollout`` back to back then overlaps the tail copy of one call with the first block of the next.
 
         ``gather_group`` (a ``torch.distributed`` process group, or ``True`` for the default group; every rank holds the
         same number of clips): the frames of all ranks are all-gathered BLOCK BY BLOCK with asynchronous NCCL collectives,
@@ -255,7 +260,10 @@ class NPVPInference(nn.Module):
             else:
                 ctx = torch.cat([ctx[:, Tp:], pred], dim=1)
         if copy_stream is not None:
-            torch.cuda.current_stream().wait_stream(copy_stream)
+            self.output_ready = torch.cuda.Event()
+            self.output_ready.record(copy_stream)
+            if wait_output:
+                torch.cuda.current_stream().wait_stream(copy_stream)
             out.record_stream(copy_stream)
         if pending:
             n = out.shape[0]
