@@ -12,7 +12,7 @@ from npvp_b200.pipeline import build_from_config  # noqa: E402
 
 
 def gpu_fps(model, x, n_future, iters=5, rollout=False):
-    fn = (lambda: model.rollout(x, n_future)) if rollout else (lambda: model.predict(x))
+    fn = (lambda: model.rollout(x, n_future, last_block="query")) if rollout else (lambda: model.predict(x))
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -53,6 +53,21 @@ def main():
         print(f"| {preset} ({c.Dataset.num_past_frames}->{nf}{' block-AR' if roll else ''}) | {n} | {fps:,.0f} | {cpu} |", flush=True)
         del model
         torch.cuda.empty_cache()
+    # BASELINE config 3: 8 stochastic samples per clip (frame encoder, EVT_Former and prior run once per clip)
+    model = build_from_config("BAIR_VFP_NPVP-S", device="cuda", seed=0)
+    x = torch.rand(16, 2, 3, 64, 64, device="cuda") * 2 - 1
+    for _ in range(2):
+        model.predict_samples(x, 8)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        model.predict_samples(x, 8)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"| BAIR_VFP_NPVP-S (2->10, 8 samples per clip, predict_samples, eager) | 16 x 8 | {16 * 8 * 10 * 5 / (e0.elapsed_time(e1) * 1e-3):,.0f} | |", flush=True)
+    del model
+    torch.cuda.empty_cache()
     print("\nKITTI VFP NPVP-S 4->5, 128x128 RGB, batch sweep (one B200):\n\n| clips | frames/s | ms / forward |\n|---:|---:|---:|")
     model = build_from_config("KITTI_VFP_NPVP-S", device="cuda", seed=0).use_cuda_graphs(True)
     for n in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512):
