@@ -206,7 +206,7 @@ class NPVPInference(nn.Module):
             copy_stream = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=dev))
         as_u8 = out_host is not None and out_host.dtype == torch.uint8
         out_u8 = None
-        pending = []                                         # (async all-gather handle, gathered block, first frame, frames)
+        pending, full, asm_stream = [], None, None          # async all-gathers in flight (handles keep their buffers alive)
         if gather_group is not None:
             import torch.distributed as dist
             group = None if gather_group is True else gather_group
@@ -250,7 +250,20 @@ class NPVPInference(nn.Module):
                 # a private contiguous copy: `pred` may be a graph-owned buffer that the next block overwrites
                 mine = out[:, done:done + take].contiguous()
                 allb = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
-                pending.append((dist.all_gather_into_tensor(allb, mine, group=group, async_op=True), allb, mine, done, take))
+                work = dist.all_gather_into_tensor(allb, mine, group=group, async_op=True)
+                # the gathered block is moved into the rank-major result on a side stream as soon as the collective is done,
+                # i.e. under the next block's kernels; only the last block's exchange and copy stay exposed
+                if full is None:
+                    n = out.shape[0]
+                    full = torch.empty((world * n, num_future) + tuple(out.shape[2:]), dtype=out.dtype, device=out.device)
+                    asm_stream = self.__dict__.setdefault("_asm_stream", torch.cuda.Stream(device=dev))
+                    asm_stream.wait_stream(torch.cuda.current_stream())      # `full` may reuse memory of earlier work on this stream
+                    full.record_stream(asm_stream)
+                with torch.cuda.stream(asm_stream):
+                    work.wait()                              # the side stream waits for the collective
+                    full.view(world, out.shape[0], num_future, *out.shape[2:])[:, :, done:done + take].copy_(allb)
+                allb.record_stream(asm_stream)
+                pending.append((work, allb, mine))
             done += take
             blk += 1
             if done >= num_future:
@@ -266,11 +279,7 @@ class NPVPInference(nn.Module):
                 torch.cuda.current_stream().wait_stream(copy_stream)
             out.record_stream(copy_stream)
         if pending:
-            n = out.shape[0]
-            full = torch.empty((world * n, num_future) + tuple(out.shape[2:]), dtype=out.dtype, device=out.device)
-            for work, allb, _mine, d0, tk in pending:
-                work.wait()                                  # current stream waits for the collective
-                full.view(world, n, num_future, *out.shape[2:])[:, :, d0:d0 + tk].copy_(allb)
+            torch.cuda.current_stream().wait_stream(asm_stream)
             return full
         return out
 
