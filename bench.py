@@ -191,6 +191,64 @@ class GemmTimer:
         return {"launches": len(big), "seconds": t, "flops": f, "all_gemm_seconds": sum(r[0] for r in rows)}
 
 
+class MemTimer:
+    """Same instrumented pass for the memory-bound kernels: CUDA events per launch and ALGORITHMIC bytes per launch (every
+    operand counted once in, every result once out, parameters not counted - DESIGN.md section 4), for `roofline_memory`."""
+
+    @staticmethod
+    def _b(t):
+        return 0 if t is None else t.numel() * t.element_size()
+
+    def __init__(self, ops):
+        B = self._b
+        rows512 = lambda t: t.shape[0] * 512 * t.element_size()          # strided [rows, 512] views of wider matrices
+        self.ops, self.records, self._saved = ops, [], {}
+        self.formulas = {
+            "ffn_dwconv": lambda a, k: B(a[0]) + B(a[6]),
+            "ffn_norm2": lambda a, k: B(a[0]) + B(a[4]),
+            "attention": lambda a, k: rows512(a[0]) + rows512(a[1]) + rows512(a[2]) + rows512(a[3]),
+            "frame_ln_gelu_residual_posfuse": lambda a, k: B(a[0]) + 2 * B(a[3]) + B(a[9]) + B(a[10]),
+            "ln_posfuse": lambda a, k: B(a[0]) + B(a[6]) + B(a[7]),
+            "add_ln_posfuse": lambda a, k: 2 * B(a[0]) + B(a[1]) + B(a[7]) + B(a[8]),
+            "layernorm_rows": lambda a, k: B(a[0]) + B(k.get("out_f32")) + B(k.get("out_bf16")),
+            "add_layernorm_rows": lambda a, k: 2 * B(a[0]) + B(a[1]) + B(k.get("out_f32")) + B(k.get("out_bf16")),
+        }
+
+    def __enter__(self):
+        for name, formula in self.formulas.items():
+            orig = getattr(self.ops, name)
+            self._saved[name] = orig
+
+            def timed(*a, _orig=orig, _name=name, _formula=formula, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _orig(*a, **k)
+                e1.record()
+                self.records.append((_name, e0, e1, float(_formula(a, k))))
+            setattr(self.ops, name, timed)
+        return self
+
+    def __exit__(self, *exc):
+        for name in self._saved:
+            try:
+                delattr(self.ops, name)            # drop the instance attribute: the class method is visible again
+            except AttributeError:
+                pass
+
+    def summary(self, hbm_gbs):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, byts in self.records:
+            a = agg.setdefault(name, [0, 0.0, 0.0])
+            a[0] += 1; a[1] += e0.elapsed_time(e1) * 1e-3; a[2] += byts
+        out = []
+        for name, (n, sec, byts) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            gbs = byts / sec * 1e-9 if sec > 0 else 0.0
+            out.append({"kernel": name, "bound": "hbm", "launches_per_step": n, "ms_per_step": 1e3 * sec, "bytes_per_step": byts,
+                        "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs})
+        return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from npvp_b200 import _lib
@@ -290,13 +348,19 @@ def run_ours(args):
     e2e_steps = max(2, min(args.steps, 10))
     e2e_u8_ms = timed(step_e2e_u8, e2e_steps, 1, whole=True) if world == 1 else None
 
-    roof = None
+    roof, roof_mem = None, None
     if rank == 0:
         model.use_cuda_graphs(False)                           # per-launch events need eager launches
         with GemmTimer(ops) as gt:
             model.rollout(x_dev, N_FUTURE, last_block=LAST_BLOCK)
         s = gt.summary()
         hbm, tf, which = load_peaks()
+        try:                                                   # memory-bound kernels: achieved algorithmic GB/s per kernel family
+            with MemTimer(ops) as mt:
+                model.rollout(x_dev, N_FUTURE, last_block=LAST_BLOCK)
+            roof_mem = mt.summary(hbm)
+        except Exception as exc:                               # never lose the bench line over the extra table
+            roof_mem = [{"error": repr(exc)}]
         ach = s["flops"] / s["seconds"] / 1e12 if s["seconds"] > 0 else 0.0
         traffic, traffic_note = None, None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -339,6 +403,7 @@ def run_ours(args):
                         "value": frames_step * e2e_steps / (e2e_u8_ms * 1e-3), "d2h_bytes_per_step": host_out_u8.numel(),
                         "note": "same call with a uint8 out_host: frames leave the device as pixel-space bytes"}},
             "roofline": roof,
+            "roofline_memory": roof_mem,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
