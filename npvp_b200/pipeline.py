@@ -158,15 +158,14 @@ class NPVPInference(nn.Module):
         return g(past_frames, eps)
 
     def _short_block_coor(self, take: int):
-        """Target coordinates of the first ``take`` timestamps of ``tp_list``, cached on the device: the same tensor object is
-        handed to the predictor every time, so a captured CUDA graph of the short block is found again."""
-        cache = self.__dict__.setdefault("_short_coor", {})
-        dev = next(self.parameters()).device
-        key = (int(take), str(dev))
-        if key not in cache:
-            p = self.predictor
-            cache[key] = p.coor_generator(self.tp_list[:take], p.h_list, p.w_list).to(dev, torch.float32)
-        return cache[key]
+        """Target coordinates of the first ``take`` timestamps the predictor is currently aimed at: the leading rows of its
+        ``predict_coor`` (rows are timestamp-major), so the short block follows ``reset_pos_coor`` like the full blocks do.
+        The slice shares the buffer's storage, so a captured CUDA graph of the short block (keyed by pointer and shape) is
+        found again on the next rollout."""
+        p = self.predictor
+        assert getattr(p, "_coor_clips", 0) == 0, "rollout(last_block='query') needs timestamps shared by the batch"
+        rows = p.predict_coor.shape[0] // int(p.TP)
+        return p.predict_coor[:take * rows]
 
     def rollout(self, past_frames, num_future: int, eps_list: Optional[Sequence[torch.Tensor]] = None,
                 out_host: Optional[torch.Tensor] = None, gather_group=None, last_block: str = "truncate",
