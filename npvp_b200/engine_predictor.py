@@ -136,6 +136,13 @@ class PredictorEngine:
         self._ffn_mid = mid
         self.enc_layers = [_EncLayer(b) for b in mod.EVT_Former.layers]
         self.dec_layers = [_DecLayer(b) for b in mod.transformer.layers]
+        # encoder-decoder attention: the K / V projections of the (layer-invariant) memory do not depend on the decoder state, so
+        # the 8 layers' weights are stacked and each projection is ONE GEMM with N = 8 x 512 per forward instead of 8 GEMMs on
+        # only 128 tiles each (M = clips x To x 64 is small); layer l reads columns [512 l, 512 l + 512) of the result
+        self.wk_all = torch.cat([L.attn_x.wk for L in self.dec_layers], 0).contiguous()
+        self.bk_all = torch.cat([L.attn_x.bk for L in self.dec_layers], 0).contiguous()
+        self.wv_all = torch.cat([L.attn_x.wv for L in self.dec_layers], 0).contiguous()
+        self.bv_all = torch.cat([L.attn_x.bv for L in self.dec_layers], 0).contiguous()
         self.norm_enc = _LN(mod.EVT_Former.norm)
         self.norm_dec = _LN(mod.transformer.norm)
         latent = mod.evt_prior if self.stochastic else mod.evt_posterior      # Predictor.py:310 / :330
@@ -330,8 +337,11 @@ class PredictorEngine:
         f = ws.bf16("f_dec", M, C)
         keyf = ws.bf16("keyf", Mo, C)
         op.ln_posfuse(mem, None, None, None, beta_o, gamma_o, None, keyf, n, To)   # fuse(memory): layer invariant
-        kx = ws.bf16("kx", Mo, C)
-        vx = ws.bf16("vx", Mo, C)
+        nl = len(self.dec_layers)
+        kx_all = ws.bf16("kx_all", Mo, nl * C)
+        vx_all = ws.bf16("vx_all", Mo, nl * C)
+        op.gemm(keyf, self.wk_all, bias=self.bk_all, out_bf16=kx_all)
+        op.gemm(mem_bf, self.wv_all, bias=self.bv_all, out_bf16=vx_all)
         qx = ws.bf16("qx", M, C)
         ox = ws.bf16("o_dec", M, C)
         for li, L in enumerate(self.dec_layers):
@@ -347,9 +357,7 @@ class PredictorEngine:
             self._ln_fuse(y, d, L.n5, z, beta_p, gamma_p, None, f, n, Tp)
             X = L.attn_x
             op.gemm(f, X.wq, bias=X.bq, out_bf16=qx)
-            op.gemm(keyf, X.wk, bias=X.bk, out_bf16=kx)
-            op.gemm(mem_bf, X.wv, bias=X.bv, out_bf16=vx)
-            op.attention(qx, kx, vx, ox, ATTN_TEMPORAL, n, Tp, To, False)
+            op.attention(qx, kx_all[:, li * C:(li + 1) * C], vx_all[:, li * C:(li + 1) * C], ox, ATTN_TEMPORAL, n, Tp, To, False)
             d = self._residual_gemm(y, ox, X.wo, X.bo, "dec")
             self._ln_rows(y, d, L.n6, out_bf16=a)
             nxt = self.dec_layers[li + 1] if li + 1 < len(self.dec_layers) else None
