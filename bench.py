@@ -405,6 +405,18 @@ def run_ours(args):
             "roofline": roof,
             "roofline_memory": roof_mem,
         }
+        try:   # SURVEY 8d end-to-end figure: t_roof = sum_k max(F_k / P_bf16, B_k / BW) over the kernels measured above
+            t_gemm = roof["flops_per_step"] / (roof["peak"] * 1e12)
+            t_mem = sum(r["bytes_per_step"] for r in roof_mem if "bytes_per_step" in r) / (hbm * 1e9)
+            t_roof = t_gemm + t_mem
+            line["roofline_e2e"] = {
+                "t_roof_ms": 1e3 * t_roof, "gemm_ms": 1e3 * t_gemm, "memory_ms": 1e3 * t_mem,
+                "roofline_fps": B * N_FUTURE / t_roof, "achieved_frac": (value / world) / (B * N_FUTURE / t_roof),
+                "note": "per GPU; contractions at the measured sustained bf16 peak plus the algorithmic bytes of the memory-bound kernel "
+                        "families at the measured HBM bandwidth; the autoencoder's stem / head / non-local attention kernels and the "
+                        "small latent / layout kernels are not counted, which makes the bound optimistic"}
+        except Exception as exc:
+            line["roofline_e2e"] = {"error": repr(exc)}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

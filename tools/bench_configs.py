@@ -39,7 +39,32 @@ def cpu_fps(preset, n, to, tp_n, rollout_frames=None):
     return n * tp_n / (time.perf_counter() - t0)
 
 
+def faithful():
+    """the LitPredictor.forward-faithful call (also decodes the context reconstructions, Predictor.py:72-86) next to
+    the throughput path, one 2 -> 10 block of the headline config, eager launches for both."""
+    model = build_from_config("Cityscapes_VFP_NPVP-S", device="cuda", seed=0)
+    x = torch.rand(64, 2, 3, 128, 128, device="cuda") * 2 - 1
+
+    def run(fn, iters=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    t_pred, t_fwd = run(lambda: model.predict(x)), run(lambda: model(x))
+    print("| call (Cityscapes NPVP-S, 64 clips, 2 -> 10, eager) | ms | predicted frames/s |\n|---|---:|---:|")
+    print(f"| `model.predict(past)` (Enc(context) -> Predictor -> Dec(predictions), channels-last hand-offs) | {t_pred:.2f} | {640 / t_pred * 1e3:,.0f} |")
+    print(f"| `model(past)` = LitPredictor.forward triple (+ Dec(context) reconstructions, NCHW fp32 between the modules) | {t_fwd:.2f} | {640 / t_fwd * 1e3:,.0f} |")
+
+
 def main():
+    if "--faithful" in sys.argv:
+        return faithful()
     do_cpu = "--cpu" in sys.argv
     print("| config | clips | frames/s (B200, CUDA graphs) | CPU oracle frames/s |\n|---|---:|---:|---:|")
     rows = [("SMMNIST_VFP_NPVP-D", 8, 10, False), ("SMMNIST_VFP_NPVP-D", 64, 10, False), ("KTH_Unified_NPVP-S", 8, 10, False), ("KTH_Unified_NPVP-S", 64, 10, False),
