@@ -117,6 +117,24 @@ def oracle_rollout_fn(clips: int):
     return fn, clips * N_FUTURE
 
 
+def cpu_baseline_forward(preset: str, n: int, to: int, tp_n: int) -> float:
+    """cpu_baseline leg for the other BASELINE configurations (tools/bench_configs.py --cpu): frames/s of ONE oracle forward
+    (Enc -> Predictor -> Dec) of `n` clips of config `preset` on all host threads, after one warm-up."""
+    from npvp_b200.pipeline import build_from_config
+    from oracle import npvp_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    m = build_from_config(preset, device="cpu", seed=0)
+    c = m.cfg
+    oc = dict(n_downsampling=c.AE.n_downsampling, num_res_blocks=c.AE.num_res_blocks, out_layer=c.AE.out_layer, stochastic=c.Predictor.stochastic)
+    esd, psd, dsd = m.VPTR_Enc.state_dict(), m.predictor.state_dict(), m.VPTR_Dec.state_dict()
+    x = torch.rand(n, to, c.Dataset.img_channels, c.Dataset.img_size, c.Dataset.img_size)
+    f = lambda: O.npvp_predict_frames(esd, psd, dsd, x, oc, m.predictor.observed_coor, m.predictor.predict_coor)
+    f()
+    t0 = time.perf_counter()
+    f()
+    return n * tp_n / (time.perf_counter() - t0)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:

@@ -1,4 +1,5 @@
-"""Stage-wise error attribution of the CUDA path against the CPU oracle (run on the GPU box)."""
+"""Stage-wise error attribution of the CUDA path against the CPU oracle (run on the GPU box: python tests/diag_parity.py).
+Test infrastructure: lives under tests/ because it imports oracle/."""
 import os
 import sys
 

@@ -2,7 +2,6 @@
 usage: python tools/bench_configs.py [--cpu]   ->  markdown tables on stdout"""
 import os
 import sys
-import time
 
 import torch
 
@@ -25,18 +24,10 @@ def gpu_fps(model, x, n_future, iters=5, rollout=False):
     return x.shape[0] * n_future * iters / (e0.elapsed_time(e1) * 1e-3)
 
 
-def cpu_fps(preset, n, to, tp_n, rollout_frames=None):
-    from oracle import npvp_oracle as O
-    m = build_from_config(preset, device="cpu", seed=0)
-    c = m.cfg
-    oc = dict(n_downsampling=c.AE.n_downsampling, num_res_blocks=c.AE.num_res_blocks, out_layer=c.AE.out_layer, stochastic=c.Predictor.stochastic)
-    esd, psd, dsd = m.VPTR_Enc.state_dict(), m.predictor.state_dict(), m.VPTR_Dec.state_dict()
-    x = torch.rand(n, to, c.Dataset.img_channels, c.Dataset.img_size, c.Dataset.img_size)
-    f = lambda: O.npvp_predict_frames(esd, psd, dsd, x, oc, m.predictor.observed_coor, m.predictor.predict_coor)
-    f()
-    t0 = time.perf_counter()
-    f()
-    return n * tp_n / (time.perf_counter() - t0)
+def cpu_fps(preset, n, to, tp_n):
+    """CPU baseline of one forward of a config: bench.py's cpu_baseline leg (the only code outside tests/ that runs oracle/)."""
+    import bench
+    return bench.cpu_baseline_forward(preset, n, to, tp_n)
 
 
 def faithful():
