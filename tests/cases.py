@@ -12,6 +12,7 @@ from util_init import fingerprint, reset_shared_norm, seeded_rand, seeded_randn,
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PRED_CASES = ["pred_S_stress_realT", "pred_D_default", "pred_D_stress_vfi"]
+PRED_SPADE_CASES = ["pred_S_stress_spade"]    # fuse_method='SPADE' (the constructor default; every shipped YAML uses 'Add')
 PRED_GT_CASES = ["pred_S_stress_gt"]          # NPVP-S with ground-truth future features (posterior branch, Predictor.py:311-327)
 LATENT_KEYS = ("mu_o", "logvar_o", "mu_p", "logvar_p")
 AE_CASES = ["ae_famB_stress", "ae_famA_default", "ae_famA_rgb_stress"]
@@ -42,10 +43,13 @@ def build_predictor_case(name):
     hl = torch.linspace(0, 7, 8)
     reset_shared_norm(npvp_b200.Predictor)
     torch.manual_seed(seed)
-    mod = npvp_b200.Predictor(8, 8, int(m["max_T"]), hl, hl, to, tp, 512, 'Add', 'layer', 256, 1, stoch, 8,
+    fuse = str(m["fuse_method"]) if "fuse_method" in m else 'Add'
+    mod = npvp_b200.Predictor(8, 8, int(m["max_T"]), hl, hl, to, tp, 512, fuse, 'layer', 256, 1, stoch, 8,
                               evt_former=True, learn_evt_token=False, evt_former_num_layers=4, rand_context=False).eval()
     if bool(m["stress"]):
         stress_init_(mod, seed)
+    if "gamma_scale" in m:                                  # SPADE fixtures: enlarge gamma so that the (1 + gamma) factor matters
+        mod.nrmlp.mlp_gamma.weight.data.mul_(float(m["gamma_scale"]))
     check_fingerprint(mod, m)
     x = torch.relu(seeded_randn((int(m["N"]), len(to), 512, 8, 8), seed + 100))
     eps = seeded_randn((int(m["N"]), 512, 8, 8), seed + 200)

@@ -111,7 +111,8 @@ def main():
         ("pred_D_stress_vfi", False, 10, [0, 1, 8, 9], [3, 5.5], 2, True, 13),
     ]
     hl = torch.linspace(0, 7, 8)
-    for name, stoch, max_T, to, tp, N, stress, seed in ([] if "--gt-only" in sys.argv else pred_cases):
+    only_new = "--gt-only" in sys.argv or "--spade-only" in sys.argv
+    for name, stoch, max_T, to, tp, N, stress, seed in ([] if only_new else pred_cases):
         to_t, tp_t = torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32)
         args = (8, 8, max_T, hl, hl, to_t, tp_t, 512, 'Add', 'layer', 256, 1, stoch, 8)
         kw = dict(evt_former=True, learn_evt_token=False, evt_former_num_layers=4, rand_context=False)
@@ -145,7 +146,7 @@ def main():
 
     # ---------------------------------------------------------------- NPVP-S with ground-truth future features (posterior branch)
     # Predictor.forward(observed, predict_features_gt) in eval mode -> (out, mu_o, logvar_o, mu_p, logvar_p), Predictor.py:311-327
-    for name, max_T, to, tp, N, seed in [("pred_S_stress_gt", 9, [0, 1.5, 3], [2, 4, 5.25, 8], 2, 14)]:
+    for name, max_T, to, tp, N, seed in ([] if "--spade-only" in sys.argv else [("pred_S_stress_gt", 9, [0, 1.5, 3], [2, 4, 5.25, 8], 2, 14)]):
         to_t, tp_t = torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32)
         args = (8, 8, max_T, hl, hl, to_t, tp_t, 512, 'Add', 'layer', 256, 1, True, 8)
         kw = dict(evt_former=True, learn_evt_token=False, evt_former_num_layers=4, rand_context=False)
@@ -181,6 +182,46 @@ def main():
             extra[key + "_stride"] = np.int64(stride)
         save(name, outs_ref[0], dict(seed=seed, stochastic=True, max_T=max_T, to=to, tp=tp, N=N, stress=True,
                                      fp_sum=fp["sum"], fp_abs=fp["abs_sum"], fp_numel=fp["numel"], fp_keys=fp["keys"]), extra)
+    # ---------------------------------------------------------------- fuse_method='SPADE' (the constructor default, Predictor.py:268;
+    # every shipped YAML uses 'Add'): the NRMLP also emits gamma and the fuser scales by (1 + gamma) (submodules.py:296-297, 441-447)
+    for name, max_T, to, tp, N, seed in [("pred_S_stress_spade", 10, [0, 2, 3.5], [1, 4, 6, 9.5], 2, 15)]:
+        to_t, tp_t = torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32)
+        args = (8, 8, max_T, hl, hl, to_t, tp_t, 512, 'SPADE', 'layer', 256, 1, True, 8)
+        kw = dict(evt_former=True, learn_evt_token=False, evt_former_num_layers=4, rand_context=False)
+        reset_shared_norm(RefPredictor)
+        reset_shared_norm(npvp_b200.Predictor)
+        torch.manual_seed(seed)
+        ref = RefPredictor(*args, **kw).eval()
+        torch.manual_seed(seed)
+        mine = npvp_b200.Predictor(*args, **kw).eval()
+        stress_init_(ref, seed)
+        stress_init_(mine, seed)
+        for m in (ref, mine):                      # make gamma matter: the default init leaves |gamma| ~ 0.05
+            m.nrmlp.mlp_gamma.weight.data.mul_(6.0)
+        check_same_weights(ref, mine, name)
+        x = torch.relu(seeded_randn((N, len(to), 512, 8, 8), seed + 100))
+        eps = seeded_randn((N, 512, 8, 8), seed + 200)
+        real = ref_sub.torch.randn
+        try:
+            ref_sub.torch.randn = lambda *a, **k: eps.clone()
+            out_ref = ref(x)
+        finally:
+            ref_sub.torch.randn = real
+        sd = {k: v.clone() for k, v in mine.state_dict().items()}
+        out_or = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps, fuse_method="SPADE")
+        gam = O.nrmlp(sd, "nrmlp.", sd["predict_coor"], "SPADE")[1]
+        err = float((out_ref - out_or).abs().max())
+        report.append((name, tuple(out_ref.shape), err))
+        assert err < 5e-5 and float(gam.abs().max()) > 0.2, (name, err, float(gam.abs().max()))
+        fp = fingerprint(ref.state_dict())
+        save(name, out_ref, dict(seed=seed, stochastic=True, max_T=max_T, to=to, tp=tp, N=N, stress=True, fuse_method="SPADE",
+                                 gamma_scale=6.0, fp_sum=fp["sum"], fp_abs=fp["abs_sum"], fp_numel=fp["numel"], fp_keys=fp["keys"]))
+    if "--spade-only" in sys.argv:
+        print(report)
+        with open(os.path.join(HERE, "REPORT.txt"), "a") as f:
+            for r in report[-1:]:
+                f.write(f"{r[0]}, {r[1]}, {r[2]:.3e}\n")
+        return
     if "--gt-only" in sys.argv:
         print(report)
         with open(os.path.join(HERE, "REPORT.txt"), "a") as f:

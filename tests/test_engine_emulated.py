@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import npvp_b200._lib as _lib
-from cases import AE_CASES, PRED_CASES, PRED_GT_CASES, build_ae_case, build_predictor_case, build_predictor_gt_case
+from cases import AE_CASES, PRED_CASES, PRED_GT_CASES, PRED_SPADE_CASES, build_ae_case, build_predictor_case, build_predictor_gt_case
 from kernel_specs import SpecOps
 from oracle import npvp_oracle as O
 
@@ -37,6 +37,17 @@ def test_predictor_engine_vs_oracle(name):
     assert _rel(out, ref) < 3e-2, _rel(out, ref)
     out_cl = PredictorEngine(mod).run(x.permute(0, 1, 3, 4, 2).contiguous(), channels_last=True)
     assert torch.equal(out_cl.permute(0, 1, 4, 2, 3), out)
+
+
+@pytest.mark.parametrize("name", PRED_SPADE_CASES)
+def test_predictor_engine_spade(name):
+    from npvp_b200.engine_predictor import PredictorEngine
+    mod, x, eps, stoch, _ = build_predictor_case(name)
+    sd = mod.state_dict()
+    ref = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], stoch, eps, fuse_method="SPADE")
+    mod.injected_eps = eps
+    out = PredictorEngine(mod).run(x)
+    assert _rel(out, ref) < 3e-2, _rel(out, ref)
 
 
 @pytest.mark.parametrize("name", PRED_GT_CASES)

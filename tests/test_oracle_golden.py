@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from cases import (AE_CASES, PRED_CASES, PRED_GT_CASES, build_ae_case, build_predictor_case, build_predictor_gt_case,
+from cases import (AE_CASES, PRED_CASES, PRED_GT_CASES, PRED_SPADE_CASES, build_ae_case, build_predictor_case, build_predictor_gt_case,
                    golden_latents, golden_sample)
 from oracle import npvp_oracle as O
 
@@ -18,6 +18,18 @@ def test_predictor_oracle_matches_reference(name):
     assert list(out.shape) == list(z["shape"])
     np.testing.assert_allclose(golden_sample(out, z), z["sample"], atol=5e-5, rtol=0)
     assert abs(float(out.double().mean()) - float(z["mean"])) < 1e-5
+
+
+@pytest.mark.parametrize("name", PRED_SPADE_CASES)
+def test_predictor_spade_oracle_matches_reference(name):
+    """fuse_method='SPADE': NRMLP emits gamma as well and the fuser multiplies by (1 + gamma) (submodules.py:296-297, 441-447)."""
+    mod, x, eps, stoch, z = build_predictor_case(name)
+    sd = mod.state_dict()
+    assert "nrmlp.mlp_gamma.weight" in sd
+    out = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], stoch, eps, fuse_method="SPADE")
+    np.testing.assert_allclose(golden_sample(out, z), z["sample"], atol=5e-5, rtol=0)
+    plain = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], stoch, eps, fuse_method="Add")
+    assert float((plain - out).abs().max()) > 1e-2           # gamma really changes the result in this fixture
 
 
 @pytest.mark.parametrize("name", PRED_GT_CASES)

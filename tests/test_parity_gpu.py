@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from cases import (AE_CASES, PRED_CASES, PRED_GT_CASES, build_ae_case, build_predictor_case, build_predictor_gt_case,
+from cases import (AE_CASES, PRED_CASES, PRED_GT_CASES, PRED_SPADE_CASES, build_ae_case, build_predictor_case, build_predictor_gt_case,
                    golden_latents, golden_sample)
 from oracle import npvp_oracle as O
 
@@ -40,6 +40,21 @@ def test_predictor_matches_oracle_and_golden(name):
     assert r < 3e-2
     g = torch.from_numpy(z["sample"])
     assert float((torch.from_numpy(golden_sample(out, z)) - g).abs().max()) < 3e-2 * float(z["absmax"])
+
+
+@pytest.mark.parametrize("name", PRED_SPADE_CASES)
+def test_predictor_spade_matches_oracle_and_golden(name):
+    """fuse_method='SPADE' (the constructor default): gamma from the NRMLP kernels, (1 + gamma) in the fuse kernels."""
+    mod, x, eps, stoch, z = build_predictor_case(name)
+    sd = mod.state_dict()
+    ref = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], stoch, eps, fuse_method="SPADE")
+    mod = mod.cuda()
+    mod.injected_eps = eps.cuda()
+    out = mod(x.cuda()).cpu()
+    r = _rel(out, ref)
+    print(f"{name}: rel err vs oracle {r:.3e}")
+    assert r < 3e-2
+    assert float((torch.from_numpy(golden_sample(out, z)) - torch.from_numpy(z["sample"])).abs().max()) < 3e-2 * float(z["absmax"])
 
 
 @pytest.mark.parametrize("name", PRED_GT_CASES)
