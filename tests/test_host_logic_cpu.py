@@ -64,3 +64,33 @@ def test_per_clip_coordinates_layout():
         m.reset_pos_coor_per_clip(torch.tensor([[0., 11.]]), tp[:1])              # outside max_T (submodules.py:351)
     m.reset_pos_coor(to[0], tp[0])
     assert m._coor_clips == 0 and m.predict_coor.shape == (3 * 64, 3)
+
+
+def test_error_conventions_of_the_reference_api():
+    """same exception types as the reference for bad arguments; unsupported reference options raise instead of
+    silently computing something else."""
+    import npvp_b200
+    hl = torch.linspace(0, 7, 8)
+    to, tp = torch.tensor([0., 1.]), torch.tensor([2., 3.])
+    base = (8, 8, 4, hl, hl, to, tp, 512, 'Add')
+    with pytest.raises(NotImplementedError):                    # ResNetAutoEncoder.py:239
+        npvp_b200.ResnetEncoder(3, padding_type="circular", learn_3d=False)
+    with pytest.raises(ValueError):                             # submodules.py:429
+        npvp_b200.Predictor(*base, 'bogus', 256, 1, False, 1, evt_former_num_layers=1)
+    with pytest.raises(NotImplementedError):
+        npvp_b200.Predictor(*base, 'layer', 256, 1, False, 1, evt_former=False)
+    with pytest.raises(NotImplementedError):
+        npvp_b200.Predictor(*base, 'layer', 256, 1, False, 1, evt_former_num_layers=1, learn_evt_token=True)
+    with pytest.raises(NotImplementedError):
+        npvp_b200.Predictor(*base, 'layer', 256, 1, False, 1, evt_former_num_layers=1, return_intermediate=True)
+    with pytest.raises(NotImplementedError):
+        npvp_b200.Predictor(8, 8, 4, hl, hl, to, tp, 256, 'Add', 'layer', 256, 1, False, 1, evt_former_num_layers=1)   # embed_dim != 512
+    rc = npvp_b200.Predictor(*base, 'layer', 256, 1, True, 1, evt_former_num_layers=1, rand_context=True).eval()
+    assert rc.observed_coor is None and rc.predict_coor is None and tuple(rc.all_coor.shape) == (4, 8, 8, 3)   # Predictor.py:282-284
+    with pytest.raises(RuntimeError, match="reset_pos_coor"):   # the reference would crash inside nrmlp(None)
+        rc._coords_ready()
+    rc.reset_pos_coor(to, tp)
+    assert rc.observed_coor.shape == (2 * 64, 3) and rc.TP == 2
+    rc.train()
+    with pytest.raises(NotImplementedError, match="inference"):  # training-mode posterior sampling (Predictor.py:316-318) is rejected
+        rc(torch.zeros(1, 2, 512, 8, 8), torch.zeros(1, 2, 512, 8, 8))
