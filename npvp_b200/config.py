@@ -81,6 +81,8 @@ def _preset(name, ch, hw, past, future, ngf, nd, nr, out_layer, max_T, stochasti
 # Values transcribed from the reference YAMLs named in BASELINE.json (configs/config_<...>.yaml).
 PRESETS: Dict[str, AttrDict] = {
     "SMMNIST_VFP_NPVP-D": _preset("SMMNIST", 1, 64, 5, 10, 64, 3, 2, "Sigmoid", 15, False),
+    # BASELINE.json's text for config 1 says "10 context -> 10 future"; the YAML above is 5 -> 10.  Labelled variant:
+    "SMMNIST_VFP_NPVP-D_10to10": _preset("SMMNIST", 1, 64, 10, 10, 64, 3, 2, "Sigmoid", 20, False),
     "KTH_Unified_NPVP-S": _preset("KTH", 1, 64, 10, 10, 64, 3, 2, "Tanh", 20, True, rand_context=True),
     "BAIR_VFP_NPVP-S": _preset("BAIR", 3, 64, 2, 10, 64, 3, 2, "Tanh", 12, True, test_future=28),
     "Cityscapes_VFP_NPVP-D": _preset("CityScapes", 3, 128, 2, 10, 32, 4, 3, "Tanh", 12, False, test_future=28),

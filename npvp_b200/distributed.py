@@ -47,5 +47,6 @@ def predict_sharded(fn, past_frames_global: torch.Tensor, group=None, **kw) -> t
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n = past_frames_global.shape[0]
     lo, hi = shard_bounds(n, rank, world)
+    assert n >= world, f"predict_sharded: {n} clips cannot be spread over {world} ranks (every rank needs at least one clip)"
     local = fn(past_frames_global[lo:hi], **kw)
     return gather_frames(local, n, group)

@@ -36,7 +36,7 @@ def _worker(rank, world, port, n_clips, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_clips", [4, 5, 1])
+@pytest.mark.parametrize("n_clips", [4, 5, 2])
 def test_sharded_predict_matches_single_process(n_clips):
     world, port = 2, _free_port()
     ret = mp.Manager().dict()

@@ -58,7 +58,7 @@ def main():
         return faithful()
     do_cpu = "--cpu" in sys.argv
     print("| config | clips | frames/s (B200, CUDA graphs) | CPU oracle frames/s |\n|---|---:|---:|---:|")
-    rows = [("SMMNIST_VFP_NPVP-D", 8, 10, False), ("SMMNIST_VFP_NPVP-D", 64, 10, False), ("KTH_Unified_NPVP-S", 8, 10, False), ("KTH_Unified_NPVP-S", 64, 10, False),
+    rows = [("SMMNIST_VFP_NPVP-D", 8, 10, False), ("SMMNIST_VFP_NPVP-D", 64, 10, False), ("SMMNIST_VFP_NPVP-D_10to10", 8, 10, False), ("KTH_Unified_NPVP-S", 8, 10, False), ("KTH_Unified_NPVP-S", 64, 10, False),
             ("BAIR_VFP_NPVP-S", 64, 28, True), ("Cityscapes_VFP_NPVP-D", 64, 28, True), ("Cityscapes_VFP_NPVP-S", 64, 28, True)]
     for preset, n, nf, roll in rows:
         model = build_from_config(preset, device="cuda", seed=0).use_cuda_graphs(True)
