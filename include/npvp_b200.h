@@ -62,8 +62,8 @@ typedef struct npvp_epilogue {
   int32_t res1_bf16; /* 1: res1 is bf16, 0: fp32 */
   int32_t res2_bf16;
   int32_t post_relu;
-  int32_t fp16;      /* 16-bit type of A, W, out_bf16 and 16-bit residuals: 0 = bfloat16, 1 = IEEE half */
-  int32_t reserved;
+  int32_t fp16;      /* 16-bit type of the operands A, W: 0 = bfloat16, 1 = IEEE half */
+  int32_t out16;     /* 16-bit type of out_bf16 and of 16-bit residuals: 0 = same as the operands, 1 = IEEE half, 2 = bfloat16 */
   int64_t ld_out;
   int64_t ld_res;
   /* optional (NULL = off): per-frame partial statistics of the stored values, a frame being 64 consecutive rows.
@@ -160,18 +160,21 @@ int npvp_ffn_dwconv(const void* h_bf16, const float* stats1, const float* n1w, c
 /* step 3: out = GELU(LN2(y)) bf16, statistics from the partials of step 2. */
 int npvp_ffn_norm2(const void* y_bf16, const float* partial2, const float* n2w, const float* n2b, void* out_bf16,
                    int64_t frames, int64_t Ch, void* stream);
-/* steps 2 + 3 in one pass (Ch = 2048 only): out = GELU(LN2(dw3x3(GELU(LN1(h1))) + b)), bf16 [frames,64,Ch], out != h1.
- * The 16 channel chunks of a frame are 16 blocks that exchange their LN2 partial statistics
- *   xch != NULL: through L2 - xch is a 128-byte aligned fp32 scratch [frames,16,2] (the call resets it); all SMs work;
- *                needs npvp_ffn_mid_lanes() > 0 (16-block frame lanes resident at once);
- *   xch == NULL: through distributed shared memory, as one 16-block cluster (non-portable size; npvp_ffn_mid_clusters()
- *                = clusters the device holds at once - 7 on a B200, i.e. 112 of 148 SMs).
- * Same values as npvp_ffn_dwconv + npvp_ffn_norm2 up to fp32 summation order. */
-int npvp_ffn_mid(const void* h_bf16, const float* stats1, const float* n1w, const float* n1b, const float* dw_w,
-                 const float* dw_b, const float* n2w, const float* n2b, void* out_bf16, float* xch, int64_t frames,
-                 int64_t Ch, void* stream);
-int npvp_ffn_mid_clusters(void);
-int npvp_ffn_mid_lanes(void);
+/* steps 1b + 2 + 3 in ONE pass and in packed half arithmetic (Ch = 2048 only; replaces VidHRFormer.py:377-381, i.e.
+ * norm1 -> act1 -> dw3x3 -> norm2 -> act2 of MlpDWBN.forward):  out = GELU(LN2(dw3x3(GELU(LN1(h1))) + b)).
+ *   h1_f16    IEEE half [frames,64,Ch]: fc1 output (npvp_gemm_bf16 with out16 = 1)
+ *   part1     fp32 [frames,32,2]: the fc1 epilogue's partial (sum, sumsq) (npvp_epilogue_t.frame_stats); reduced here
+ *   ln_wb_f16 half [2 norms][64 px][Ch/2 pairs][(w_c, w_c+1), (b_c, b_c+1)]: both LayerNorm affines, pair-interleaved
+ *   dw_w_f16  half [9,Ch], dw_b_f16 half [Ch]
+ *   out_f16   half [frames,64,Ch] (!= h1): feeds fc2 (npvp_gemm_bf16 with fp16 = 1)
+ *   xch       fp32 [>= frames,32,2], 256-byte aligned, and cnt uint32 [>= frames]: statistics exchange between the 32 warps
+ *             (on 32 SMs) that share a frame.  PERSISTENT scratch owned by the caller: xch must hold the all-ones bit
+ *             pattern and cnt zeros before the first call; every call leaves them in that state again (no memset per call).
+ * All blocks of the launch are co-resident (npvp_ffn_mid16_lanes() x 32 blocks; 0 = the kernel does not fit the device).
+ * Statistics are fp32 / fp64; element-wise math is half2 (max |GELU error| 1.0e-3 = half an ulp at |x| ~ 3). */
+int npvp_ffn_mid16(const void* h1_f16, const float* part1, const void* ln_wb_f16, const void* dw_w_f16, const void* dw_b_f16,
+                   void* out_f16, float* xch, unsigned int* cnt, int64_t frames, int64_t Ch, void* stream);
+int npvp_ffn_mid16_lanes(void);
 
 /* ---- predictor: attention cores (8 heads x 64) ---------------------------------------------
  * softmax(Q K^T / 8 [+mask]) V for the short sequences of the factorised attention

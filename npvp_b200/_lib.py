@@ -27,7 +27,7 @@ _i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
 class Epilogue(C.Structure):
     _fields_ = [("bias", _vp), ("res1", _vp), ("res2", _vp), ("out_f32", _vp), ("out_bf16", _vp),
                 ("alpha", _f32), ("act", C.c_int32), ("res1_bf16", C.c_int32), ("res2_bf16", C.c_int32),
-                ("post_relu", C.c_int32), ("fp16", C.c_int32), ("reserved", C.c_int32), ("ld_out", _i64), ("ld_res", _i64),
+                ("post_relu", C.c_int32), ("fp16", C.c_int32), ("out16", C.c_int32), ("ld_out", _i64), ("ld_res", _i64),
                 ("frame_stats", _vp)]
 
 
@@ -53,9 +53,8 @@ SIGNATURES = {
     "npvp_ssim": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp],
     "npvp_ffn_dwconv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_ffn_norm2": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
-    "npvp_ffn_mid": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
-    "npvp_ffn_mid_clusters": [],
-    "npvp_ffn_mid_lanes": [],
+    "npvp_ffn_mid16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "npvp_ffn_mid16_lanes": [],
     "npvp_attention": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i64, _i32, _i32, _i32, _vp],
     "npvp_dwconv3x3_tokens": [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp],
     "npvp_latent_reparam": [_vp, _i64, _vp, _vp, _i64, _i64, _vp],
@@ -156,10 +155,12 @@ class Ops:
     # -- contractions ---------------------------------------------------------------------------
     def gemm(self, a, w, *, bias=None, act=ACT_NONE, alpha=1.0, res1=None, res2=None, out_f32=None, out_bf16=None,
              post_relu=False, backend=None, frame_stats=None):
-        """``frame_stats``: fp32 [M/64, 4*N/256, 2] receiving partial (sum, sumsq) of the outputs per 64-row frame."""
+        """``frame_stats``: fp32 [M/64, 4*N/256, 2] receiving partial (sum, sumsq) of the outputs per 64-row frame.
+        ``out_bf16`` (and 16-bit residuals) may be of the other 16-bit type than the operands (npvp_epilogue_t.out16)."""
         _chk16(a, "a", False); _chk16(w, "w", False, like=a)
         _chk(bias, torch.float32, "bias"); _chk(out_f32, torch.float32, "out_f32", False)
-        _chk16(out_bf16, "out_bf16", False, like=a)
+        _chk16(out_bf16, "out_bf16", False)
+        o16 = out_bf16.dtype if out_bf16 is not None else a.dtype
         lda, ldw = _rowmajor(a, "a"), _rowmajor(w, "w")
         M, K = a.shape
         N = w.shape[0]
@@ -171,13 +172,14 @@ class Ops:
         ld_res = 0
         for r in (res1, res2):
             if r is not None:
-                assert r.is_cuda and r.shape == (M, N) and r.dtype in (torch.float32, a.dtype)
+                assert r.is_cuda and r.shape == (M, N) and r.dtype in (torch.float32, o16)
                 ld = _rowmajor(r, "res")
                 assert ld_res in (0, ld), "gemm: residuals must share a row stride"
                 ld_res = ld
         ep = Epilogue(_ptr(bias), _ptr(res1), _ptr(res2), _ptr(out_f32), _ptr(out_bf16), float(alpha), int(act),
                       int(res1 is not None and res1.dtype in H16),
-                      int(res2 is not None and res2.dtype in H16), int(post_relu), _is_fp16(a), 0, ld_out, ld_res, _ptr(frame_stats))
+                      int(res2 is not None and res2.dtype in H16), int(post_relu), _is_fp16(a),
+                      0 if o16 == a.dtype else (1 if o16 == torch.float16 else 2), ld_out, ld_res, _ptr(frame_stats))
         if frame_stats is not None:
             _chk(frame_stats, torch.float32, "frame_stats")
             assert M % 64 == 0 and N % 256 == 0 and tuple(frame_stats.shape) == (M // 64, 4 * N // 256, 2)
@@ -350,27 +352,22 @@ class Ops:
         self._call("npvp_ffn_norm2", y.data_ptr(), partial2.data_ptr(), n2w.data_ptr(), n2b.data_ptr(), out.data_ptr(), frames,
                    Ch, self._stream())
 
-    def ffn_mid_clusters(self):
-        """16-block clusters of the fused conv-FFN middle the device holds at once (DSMEM exchange; 0: not schedulable)."""
-        return int(self.lib.npvp_ffn_mid_clusters())
+    def ffn_mid16_lanes(self):
+        """Frame lanes (32 blocks each) of the single-pass conv-FFN middle resident at once (0: the kernel does not fit)."""
+        return int(self.lib.npvp_ffn_mid16_lanes())
 
-    def ffn_mid_lanes(self):
-        """16-block frame lanes of the fused conv-FFN middle resident at once (L2 exchange; 0: use ffn_dwconv + ffn_norm2)."""
-        return int(self.lib.npvp_ffn_mid_lanes())
-
-    def ffn_mid(self, h, stats1, n1w, n1b, dw_w, dw_b, n2w, n2b, out, xch=None):
-        """``xch``: fp32 scratch [frames,16,2] -> statistics exchange through L2 (all SMs); None -> 16-block clusters / DSMEM."""
-        _chk(h, torch.bfloat16, "h"); _chk(out, torch.bfloat16, "out")
-        for t, n in ((stats1, "stats1"), (n1w, "n1w"), (n1b, "n1b"), (dw_w, "dw_w"), (dw_b, "dw_b"), (n2w, "n2w"), (n2b, "n2b")):
-            _chk(t, torch.float32, n)
-        frames, Ch = stats1.shape[0], h.shape[-1]
-        assert dw_w.shape == (9, Ch) and n1w.shape == (64, Ch) and n2w.shape == (64, Ch) and out.data_ptr() != h.data_ptr()
-        if xch is not None:
-            _chk(xch, torch.float32, "xch")
-            assert xch.shape == (frames, Ch // FFN_CHUNK, 2)
-        self._call("npvp_ffn_mid", h.data_ptr(), stats1.data_ptr(), n1w.data_ptr(), n1b.data_ptr(), dw_w.data_ptr(), dw_b.data_ptr(),
-                   n2w.data_ptr(), n2b.data_ptr(), out.data_ptr(), xch.data_ptr() if xch is not None else None, frames, Ch,
-                   self._stream())
+    def ffn_mid16(self, h1, part1, ln_wb, dw_w, dw_b, out, xch, cnt):
+        """out = GELU(LN2(dw3x3(GELU(LN1(h1))) + b)), half in / half out, one pass (see include/npvp_b200.h).
+        ``xch`` / ``cnt``: persistent exchange scratch from :func:`ffn_mid16_scratch`."""
+        _chk(h1, torch.float16, "h1"); _chk(out, torch.float16, "out"); _chk(part1, torch.float32, "part1")
+        _chk(ln_wb, torch.float16, "ln_wb"); _chk(dw_w, torch.float16, "dw_w"); _chk(dw_b, torch.float16, "dw_b")
+        _chk(xch, torch.float32, "xch"); _chk(cnt, torch.int32, "cnt")
+        frames, Ch = part1.shape[0], h1.shape[-1]
+        assert h1.numel() == frames * 64 * Ch and out.numel() == h1.numel() and tuple(part1.shape) == (frames, 32, 2)
+        assert tuple(ln_wb.shape) == (2, 64, Ch // 2, 2, 2) and tuple(dw_w.shape) == (9, Ch) and dw_b.numel() == Ch
+        assert xch.numel() >= frames * 64 and cnt.numel() >= frames and out.data_ptr() != h1.data_ptr()
+        self._call("npvp_ffn_mid16", h1.data_ptr(), part1.data_ptr(), ln_wb.data_ptr(), dw_w.data_ptr(), dw_b.data_ptr(), out.data_ptr(),
+                   xch.data_ptr(), cnt.data_ptr(), frames, Ch, self._stream())
 
     def attention(self, q, k, v, out, mode, n_clips, Tq, Tk, mask_last=False):
         for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
@@ -501,6 +498,14 @@ def _pos_frames(beta, gamma, n_clips, T):
 
 
 FFN_CHUNK = 128        # channels per partial-statistics chunk of the conv-FFN middle (kFfnChunk in predictor_kernels.cu)
+
+
+def ffn_mid16_scratch(frames: int, device) -> tuple:
+    """Persistent exchange scratch of :meth:`Ops.ffn_mid16` at rest: (xch fp32 [frames,32,2] of all-ones bit patterns, cnt int32
+    [frames] zeros).  Every call returns it to this state, so one pair serves all launches of a stream (the launches are
+    stream-ordered; concurrent streams need separate pairs)."""
+    xch = torch.full((frames, 32, 2), -1, dtype=torch.int32, device=device).view(torch.float32)
+    return xch, torch.zeros(frames, dtype=torch.int32, device=device)
 
 _OPS: Optional[Ops] = None
 

@@ -199,6 +199,7 @@ struct EpiParams {
   h16* out_bf16;      // 16-bit output (bf16 or half, see fp16)
   float alpha;
   int act, res1_bf16, res2_bf16, post_relu, fp16;
+  int out_fp16;        // 16-bit type of out_bf16 and of 16-bit residuals (npvp_epilogue_t.out16: defaults to the operands' type)
   int64_t ld_out, ld_res;
   float* frame_stats;  // see npvp_epilogue_t
 };
@@ -208,8 +209,8 @@ __device__ __forceinline__ float epi_value(const EpiParams& e, float acc, int64_
   if (e.bias) v += __ldg(e.bias + n);
   v = apply_act(v, e.act);
   v *= e.alpha;
-  if (e.res1) v += e.res1_bf16 ? h16_to_float(((const h16*)e.res1)[m * e.ld_res + n], e.fp16) : ((const float*)e.res1)[m * e.ld_res + n];
-  if (e.res2) v += e.res2_bf16 ? h16_to_float(((const h16*)e.res2)[m * e.ld_res + n], e.fp16) : ((const float*)e.res2)[m * e.ld_res + n];
+  if (e.res1) v += e.res1_bf16 ? h16_to_float(((const h16*)e.res1)[m * e.ld_res + n], e.out_fp16) : ((const float*)e.res1)[m * e.ld_res + n];
+  if (e.res2) v += e.res2_bf16 ? h16_to_float(((const h16*)e.res2)[m * e.ld_res + n], e.out_fp16) : ((const float*)e.res2)[m * e.ld_res + n];
   if (e.post_relu) v = fmaxf(v, 0.0f);
   return v;
 }
@@ -222,6 +223,7 @@ static inline EpiParams make_epi(const npvp_epilogue_t* ep) {
   e.out_f32 = (float*)ep->out_f32;
   e.out_bf16 = (h16*)ep->out_bf16;
   e.fp16 = ep->fp16;
+  e.out_fp16 = ep->out16 == 0 ? ep->fp16 : (ep->out16 == 1 ? 1 : 0);
   e.alpha = ep->alpha;
   e.act = ep->act;
   e.res1_bf16 = ep->res1_bf16;

@@ -261,14 +261,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * ep.ld_out + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_h16x2(v[8 * j], v[8 * j + 1], ep.fp16), pack_h16x2(v[8 * j + 2], v[8 * j + 3], ep.fp16),
-                                  pack_h16x2(v[8 * j + 4], v[8 * j + 5], ep.fp16), pack_h16x2(v[8 * j + 6], v[8 * j + 7], ep.fp16));
+              dst[j] = make_uint4(pack_h16x2(v[8 * j], v[8 * j + 1], ep.out_fp16), pack_h16x2(v[8 * j + 2], v[8 * j + 3], ep.out_fp16),
+                                  pack_h16x2(v[8 * j + 4], v[8 * j + 5], ep.out_fp16), pack_h16x2(v[8 * j + 6], v[8 * j + 7], ep.out_fp16));
           }
         } else {
           for (int j = 0; j < 32 && n0 + j < N; ++j) {
             const float v = epi_value(ep, __uint_as_float(r[j]), m, n0 + j);
             if (ep.out_f32) ep.out_f32[m * ep.ld_out + n0 + j] = v;
-            if (ep.out_bf16) ep.out_bf16[m * ep.ld_out + n0 + j] = float_to_h16(v, ep.fp16);
+            if (ep.out_bf16) ep.out_bf16[m * ep.ld_out + n0 + j] = float_to_h16(v, ep.out_fp16);
           }
         }
       }
@@ -655,7 +655,7 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     uint32_t acc_phase = 0;
     const int sub_row = lane >> 3, chunk = lane & 7;                // coalesced layout: 4 rows x 8 float4 per instruction
     const bool has_bias = ep.bias != nullptr;
-    const int fp16 = ep.fp16;
+    const int fp16 = ep.out_fp16;                                  // 16-bit type of the OUTPUT (and of 16-bit residuals)
     const float alpha = ep.alpha;
     const float relu_floor = ep.post_relu ? 0.f : -INFINITY;
     constexpr int kColsPerWarp = BN / 2;
@@ -905,7 +905,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint32_t acc_phase = 0;
     const int sub_row = lane >> 3, chunk = lane & 7;
     const bool has_bias = ep.bias != nullptr;
-    const int fp16 = ep.fp16;
+    const int fp16 = ep.out_fp16;                                  // 16-bit type of the OUTPUT (and of 16-bit residuals)
     const float alpha = ep.alpha;
     const float relu_floor = ep.post_relu ? 0.f : -INFINITY;
     constexpr int kColsPerWarp = BN / 2;
@@ -1002,7 +1002,7 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t lda, const TA* __restrict__ W
       if (n >= N) continue;
       const float v = epi_value(ep, acc[i][j], m, n);
       if (ep.out_f32) ep.out_f32[m * ep.ld_out + n] = v;
-      if (ep.out_bf16) ep.out_bf16[m * ep.ld_out + n] = float_to_h16(v, ep.fp16);
+      if (ep.out_bf16) ep.out_bf16[m * ep.ld_out + n] = float_to_h16(v, ep.out_fp16);
     }
   }
 }

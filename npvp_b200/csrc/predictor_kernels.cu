@@ -844,290 +844,6 @@ extern "C" int npvp_ffn_norm2(const void* y_bf16, const float* partial2, const f
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused conv-FFN middle: out = GELU(LN2(dw3x3(GELU(LN1(h1))) + b)) in ONE pass over the frame (h1 read once, out written
-// once: 4 B per element instead of the 8 B of ffn_dwconv + ffn_norm2, which wrote and re-read the bf16 conv output).
-// LN2 needs the statistics of the whole (2048, 8, 8) frame while a block can only afford the parameters of 128 channels
-// in shared memory (2 LayerNorms x 64 px x 128 ch x (w, b) fp32 = 128 KB), so the 16 channel chunks of a frame run as one
-// CLUSTER of 16 blocks (non-portable size; one cluster per GPC) and trade their (sum, sumsq) partials through distributed
-// shared memory: st.async into every peer's slot table, completing transaction bytes on the peer's mbarrier - every thread
-// waits on a LOCAL mbarrier and reads a LOCAL table, no cluster barrier after kernel entry.  A block runs kMidGroups
-// independent 128-thread groups, each on its own frame with its own double-buffered slot table / mbarrier pair.
-// Thread layout inside a group: lane & 15 = channel PAIR (all arithmetic is packed f32x2: FFMA2), lane >> 4 = image half.
-// The lower half stores its rows mirrored (local row r = image row 7 - r) and loads its vertical taps mirrored, so for both
-// halves local row 0 touches the zero padding and local row 3 touches the other half's row 3, fetched with one
-// __shfl_xor(.., 16) per value: no divergence, no selects.  The conv output is rounded to bf16 before LN2 (the statistics
-// use the fp32 values), exactly like the two-kernel path, so both paths share one specification.
-constexpr int kMidGroups = 4;
-constexpr int kMidCL = 16;                                        // blocks per cluster = 2048 / kFfnChunk
-constexpr int kMidPairs = kFfnChunk / 2;                          // 64 channel pairs per block
-struct MidXchg {
-  float2 slots[kMidGroups][2][kMidCL];
-  unsigned long long bars[kMidGroups][2];
-};
-
-__device__ __forceinline__ void mid_xchg_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0, spins = 0;
-  long long t0 = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!ok && (++spins & 0x3FFu) == 0) {                        // bounded: a lost arrival traps instead of hanging the GPU
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000LL) __trap();
-    }
-  }
-}
-
-// XCHG = 0: the 16 blocks of a frame lane are one cluster and exchange through distributed shared memory (above).
-// XCHG = 1: no cluster (a 16-block cluster fits only 7 of the 8 GPCs: 112 of 148 SMs).  The 16 chunk blocks of a frame lane
-//           are ordinary blocks (grid <= one block per SM, so all are resident) and exchange through L2: each group
-//           publishes its (sum, sumsq) with ONE 8-byte store into xch[frame][chunk] - the value is its own flag, the table
-//           is pre-set to an all-ones bit pattern that no arithmetic produces - and lanes 0..15 of every warp poll the
-//           128-byte line of the frame until all 16 entries are there.
-template <int XCHG>
-__global__ void __launch_bounds__(kFfnChunk * kMidGroups, 1)
-ffn_mid_kernel(const bf16* __restrict__ h, const float* __restrict__ stats1, const float* __restrict__ n1w, const float* __restrict__ n1b,
-               const float* __restrict__ dw_w, const float* __restrict__ dw_b, const float* __restrict__ n2w,
-               const float* __restrict__ n2b, bf16* __restrict__ out, float2* __restrict__ xch, int frames) {
-  constexpr int Ch = kMidCL * kFfnChunk;
-  extern __shared__ float4 mid_wb[];                             // [2 LayerNorms][64 px][64 pairs] (w_c, w_c+1, b_c, b_c+1)
-  __shared__ float red[kMidGroups][2][8];
-  __shared__ __align__(16) MidXchg xc;
-  const uint32_t rank = XCHG == 0 ? frame_cluster_rank() : blockIdx.x % kMidCL;   // = channel chunk
-  const int grp = threadIdx.x / kFfnChunk, tc = threadIdx.x % kFfnChunk, gw = tc >> 5, lane = threadIdx.x & 31;
-  const int pair = gw * 16 + (lane & 15), half = lane >> 4;
-  const int c0 = (int)rank * kFfnChunk + 2 * pair;
-  const int pbase = half ? 56 : 0, pstep = half ? -8 : 8;          // local row r = image row (half ? 7 - r : r)
-  if (XCHG == 0 && threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < kMidGroups * 2; ++i)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(frame_smem_u32(&xc.bars[i >> 1][i & 1])) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = threadIdx.x; i < 2 * kTok * kMidPairs; i += kFfnChunk * kMidGroups) {
-    const int ln = i / (kTok * kMidPairs), p = (i / kMidPairs) % kTok, pr = i % kMidPairs;
-    const size_t off = (size_t)p * Ch + rank * kFfnChunk + 2 * pr;
-    const float2 w = __ldg(reinterpret_cast<const float2*>((ln ? n2w : n1w) + off));
-    const float2 b = __ldg(reinterpret_cast<const float2*>((ln ? n2b : n1b) + off));
-    mid_wb[i] = make_float4(w.x, w.y, b.x, b.y);
-  }
-  f32x2 w[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const int kk = (half ? 2 - k / 3 : k / 3) * 3 + k % 3;          // lower half: vertical taps mirrored
-    const float2 t = __ldg(reinterpret_cast<const float2*>(dw_w + (size_t)kk * Ch + c0));
-    w[k] = pk2(t.x, t.y);
-  }
-  const float2 bias_f = __ldg(reinterpret_cast<const float2*>(dw_b + c0));
-  const f32x2 bias = pk2(bias_f.x, bias_f.y);
-  if (XCHG == 0) frame_cluster_sync();                           // parameters staged, every peer's mbarriers initialised
-  else __syncthreads();
-  const int cluster_id = blockIdx.x / kMidCL, n_clusters = gridDim.x / kMidCL;
-  int it = 0;
-  for (int f = cluster_id * kMidGroups + grp; f < frames; f += n_clusters * kMidGroups, ++it) {
-    const int buf = it & 1;
-    const float rstd1 = __ldg(stats1 + 2 * f + 1), nmr1 = -__ldg(stats1 + 2 * f) * rstd1;
-    const f32x2 rs1 = pk2(rstd1, rstd1), nm1 = pk2(nmr1, nmr1);
-    const bf16* src = h + (size_t)f * kTok * Ch + c0;
-    uint32_t raw[32];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        const int p = pbase + r * pstep + x;
-        raw[r * 8 + x] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)p * Ch));
-      }
-    f32x2 a[5][8];                                               // local rows 0..3 + the other half's row 3
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        const int p = pbase + r * pstep + x;
-        const float4 wb = mid_wb[p * kMidPairs + pair];
-        a[r][x] = gelu_erf2(fma2(fma2(bf16x2_to_f32x2(raw[r * 8 + x]), rs1, nm1), pk2(wb.x, wb.y), pk2(wb.z, wb.w)));
-      }
-#pragma unroll
-    for (int x = 0; x < 8; ++x) {
-      float lo, hi;
-      upk2(a[3][x], lo, hi);
-      a[4][x] = pk2(__shfl_xor_sync(0xffffffffu, lo, 16), __shfl_xor_sync(0xffffffffu, hi, 16));
-    }
-    uint32_t o[32];                                              // conv output, bf16x2 (what LN2 sees, as in the two-kernel path)
-    f32x2 s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        f32x2 acc = bias;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int lr = r + ky - 1;
-          if (lr < 0) continue;
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int ix = x + kx - 1;
-            if (ix >= 0 && ix <= 7) acc = fma2(a[lr][ix], w[ky * 3 + kx], acc);
-          }
-        }
-        s2 = add2(s2, acc);
-        q2 = fma2(acc, acc, q2);
-        o[r * 8 + x] = f32x2_to_bf16x2(acc);
-      }
-    float s_lo, s_hi, q_lo, q_hi;
-    upk2(s2, s_lo, s_hi);
-    upk2(q2, q_lo, q_hi);
-    const float s = warp_sum(s_lo + s_hi), q = warp_sum(q_lo + q_hi);
-    if (lane == 0) { red[grp][buf][gw] = s; red[grp][buf][4 + gw] = q; }
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kFfnChunk) : "memory");
-    const uint32_t bar = frame_smem_u32(&xc.bars[grp][buf]);
-    double sd = 0.0, qd = 0.0;
-    if (XCHG == 1) {
-      float2* line = xch + (size_t)f * kMidCL;
-      if (tc == 0) {
-        const float* rr = red[grp][buf];
-        const float vx = (rr[0] + rr[1]) + (rr[2] + rr[3]), vy = (rr[4] + rr[5]) + (rr[6] + rr[7]);
-        asm volatile("st.relaxed.gpu.global.v2.f32 [%0], {%1, %2};" ::"l"(line + rank), "f"(vx), "f"(vy) : "memory");
-      }
-      float vx = 0.f, vy = 0.f;
-      uint32_t spins = 0;
-      long long t0 = 0;
-      for (;;) {
-        uint32_t bx = 0;
-        if (lane < kMidCL) {
-          asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(vx), "=f"(vy) : "l"(line + lane) : "memory");
-          bx = __float_as_uint(vx);
-        }
-        if (__all_sync(0xffffffffu, bx != 0xffffffffu)) break;
-        __nanosleep(100);                                            // back off: a spinning warp takes issue slots from its SM
-        if ((++spins & 0xFFu) == 0) {                                // bounded: a missing peer traps instead of hanging the GPU
-          const long long now = clock64();
-          if (t0 == 0) t0 = now;
-          else if (now - t0 > 4000000000LL) __trap();
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < kMidCL; ++k) {
-        sd += (double)__shfl_sync(0xffffffffu, vx, k);
-        qd += (double)__shfl_sync(0xffffffffu, vy, k);
-      }
-    } else {
-    if (tc == 0) {
-      const float* rr = red[grp][buf];
-      const float2 v = make_float2((rr[0] + rr[1]) + (rr[2] + rr[3]), (rr[4] + rr[5]) + (rr[6] + rr[7]));
-      const uint32_t slot = frame_smem_u32(&xc.slots[grp][buf][rank]);
-      xc.slots[grp][buf][rank] = v;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)((kMidCL - 1) * sizeof(float2))) : "memory");
-#pragma unroll
-      for (uint32_t r = 0; r < (uint32_t)kMidCL; ++r) {
-        if (r == rank) continue;
-        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(frame_mapa(slot, r)),
-                     "f"(v.x), "f"(v.y), "r"(frame_mapa(bar, r))
-                     : "memory");
-      }
-    }
-    mid_xchg_wait(bar, (uint32_t)((it >> 1) & 1));
-#pragma unroll
-    for (int k = 0; k < kMidCL; ++k) {
-      const float2 v = xc.slots[grp][buf][k];
-      sd += (double)v.x;
-      qd += (double)v.y;
-    }
-    }
-    constexpr double inv_n = 1.0 / ((double)kTok * (double)Ch);
-    const double mean_d = sd * inv_n;
-    const float rstd2 = (float)(1.0 / sqrt(fmax(qd * inv_n - mean_d * mean_d, 0.0) + (double)kEps));
-    const float nmr2 = -(float)mean_d * rstd2;
-    const f32x2 rs2 = pk2(rstd2, rstd2), nm2 = pk2(nmr2, nmr2);
-    bf16* dst = out + (size_t)f * kTok * Ch + c0;
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        const int p = pbase + r * pstep + x;
-        const float4 wb = mid_wb[(kTok + p) * kMidPairs + pair];
-        const f32x2 v = gelu_erf2(fma2(fma2(bf16x2_to_f32x2(o[r * 8 + x]), rs2, nm2), pk2(wb.x, wb.y), pk2(wb.z, wb.w)));
-        *reinterpret_cast<uint32_t*>(dst + (size_t)p * Ch) = f32x2_to_bf16x2(v);
-      }
-  }
-}
-
-static int g_mid_clusters = -1;                                   // max co-resident 16-block clusters (0: not schedulable)
-static int g_mid_lanes = -1;                                      // XCHG = 1: frame lanes (16 blocks each) that are resident at once
-constexpr int kMidSmem = 2 * kTok * kMidPairs * (int)sizeof(float4);
-static void ffn_mid_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, unsigned blocks, cudaStream_t st) {
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kMidCL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.gridDim = dim3(blocks);
-  cfg.blockDim = dim3(kFfnChunk * kMidGroups);
-  cfg.dynamicSmemBytes = kMidSmem;
-  cfg.stream = st;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-}
-static void ffn_mid_setup() {
-  if (g_mid_clusters >= 0) return;
-  g_mid_clusters = g_mid_lanes = 0;
-  int dev = 0, sms = 0, per_sm = 0;
-  if (cudaFuncSetAttribute(ffn_mid_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMidSmem) == cudaSuccess &&
-      cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffn_mid_kernel<1>, kFfnChunk * kMidGroups, kMidSmem) == cudaSuccess)
-    g_mid_lanes = sms * per_sm / kMidCL;
-  if (cudaFuncSetAttribute(ffn_mid_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMidSmem) == cudaSuccess &&
-      cudaFuncSetAttribute(ffn_mid_kernel<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
-    ffn_mid_cluster_cfg(cfg, attr, kMidCL * 8, nullptr);
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, ffn_mid_kernel<0>, &cfg) == cudaSuccess) g_mid_clusters = n;
-  }
-  cudaGetLastError();
-}
-
-extern "C" int npvp_ffn_mid_clusters(void) { ffn_mid_setup(); return g_mid_clusters; }
-extern "C" int npvp_ffn_mid_lanes(void) { ffn_mid_setup(); return g_mid_lanes; }
-
-extern "C" int npvp_ffn_mid(const void* h_bf16, const float* stats1, const float* n1w, const float* n1b, const float* dw_w,
-                            const float* dw_b, const float* n2w, const float* n2b, void* out_bf16, float* xch, int64_t frames,
-                            int64_t Ch, void* stream) {
-  NPVP_REQUIRE(h_bf16 && stats1 && n1w && n1b && dw_w && dw_b && n2w && n2b && out_bf16, "npvp_ffn_mid: null pointer");
-  NPVP_REQUIRE(frames > 0 && frames < (1ll << 31), "npvp_ffn_mid: frames > 0");
-  NPVP_REQUIRE(Ch == kMidCL * kFfnChunk, "npvp_ffn_mid: Ch must be %d (use npvp_ffn_dwconv + npvp_ffn_norm2 otherwise)", kMidCL * kFfnChunk);
-  NPVP_REQUIRE(h_bf16 != out_bf16, "npvp_ffn_mid: in-place operation is not supported (a frame's chunks finish at different times)");
-  ffn_mid_setup();
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t want = (frames + kMidGroups - 1) / kMidGroups;
-  cudaError_t err;
-  if (xch != nullptr) {                                           // exchange through L2: every SM works
-    NPVP_REQUIRE(g_mid_lanes > 0, "npvp_ffn_mid: the kernel does not fit on this device");
-    NPVP_REQUIRE(((uintptr_t)xch & 127) == 0, "npvp_ffn_mid: xch must be 128-byte aligned");
-    const int64_t lanes = want > g_mid_lanes ? g_mid_lanes : want;
-    err = cudaMemsetAsync(xch, 0xFF, (size_t)frames * kMidCL * sizeof(float2), st);
-    if (err != cudaSuccess) { npvp_set_error("ffn_mid: cudaMemsetAsync: %s", cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
-    ffn_mid_kernel<1><<<(unsigned)(kMidCL * lanes), kFfnChunk * kMidGroups, kMidSmem, st>>>(
-        (const bf16*)h_bf16, stats1, n1w, n1b, dw_w, dw_b, n2w, n2b, (bf16*)out_bf16, (float2*)xch, (int)frames);
-  } else {                                                        // exchange through distributed shared memory: 16-block clusters
-    NPVP_REQUIRE(g_mid_clusters > 0, "npvp_ffn_mid: a cluster of %d blocks cannot be scheduled on this device", kMidCL);
-    const int64_t ncl = want > g_mid_clusters ? g_mid_clusters : want;
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
-    ffn_mid_cluster_cfg(cfg, attr, (unsigned)(kMidCL * ncl), st);
-    err = cudaLaunchKernelEx(&cfg, ffn_mid_kernel<0>, (const bf16*)h_bf16, stats1, n1w, n1b, dw_w, dw_b, n2w, n2b, (bf16*)out_bf16,
-                             (float2*)nullptr, (int)frames);
-    if (err != cudaSuccess) { npvp_set_error("ffn_mid_kernel: launch failed: %s", cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
-  }
-  NPVP_LAUNCH_CHECK("ffn_mid_kernel");
-  return NPVP_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
 // Fourier features
 // ---------------------------------------------------------------------------------------------
 __global__ void fourier_features_kernel(const float* __restrict__ coor, const float* __restrict__ B, float* __restrict__ out,

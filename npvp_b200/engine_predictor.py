@@ -65,15 +65,29 @@ class _MHA:
 
 
 class _ConvFFN:
-    def __init__(self, m):
+    """MlpDWBN weights.  ``half_mid`` (hidden width 2048, the only one NPVP uses): the middle runs as ONE half-precision
+    kernel (npvp_ffn_mid16) - both LayerNorm((hid,8,8)) affines pair-interleaved in IEEE half [2, 64, hid/2, (w|b), 2], half
+    depthwise taps, and fc2 as a half GEMM.  Other widths keep the fp32 two-kernel path."""
+
+    def __init__(self, m, half_mid):
         hid = m.fc1.weight.shape[0]
         self.hid = hid
+        self.half_mid = bool(half_mid) and hid == 2048
         self.w1, self.b1 = _bf(m.fc1.weight.reshape(hid, C)), _f(m.fc1.bias)
-        self.n1w, self.n1b = _chw_affine(m.norm1)
-        self.dw_w = _f(m.dw3x3.weight.reshape(hid, 9).t())
-        self.dw_b = _f(m.dw3x3.bias)
-        self.n2w, self.n2b = _chw_affine(m.norm2)
-        self.w2, self.b2 = _bf(m.fc2.weight.reshape(-1, hid)), _f(m.fc2.bias)
+        n1w, n1b = _chw_affine(m.norm1)
+        n2w, n2b = _chw_affine(m.norm2)
+        dw_w = _f(m.dw3x3.weight.reshape(hid, 9).t())
+        if self.half_mid:
+            pair = lambda w, b: torch.stack([w.view(TOK, hid // 2, 2), b.view(TOK, hid // 2, 2)], dim=2)
+            self.ln_wb = torch.stack([pair(n1w, n1b), pair(n2w, n2b)], dim=0).to(torch.float16).contiguous()
+            self.dw_w16 = dw_w.to(torch.float16).contiguous()
+            self.dw_b16 = m.dw3x3.bias.detach().to(torch.float16).contiguous()
+            self.w2 = m.fc2.weight.detach().reshape(-1, hid).to(torch.float16).contiguous()
+        else:
+            self.n1w, self.n1b, self.n2w, self.n2b = n1w, n1b, n2w, n2b
+            self.dw_w, self.dw_b = dw_w, _f(m.dw3x3.bias)
+            self.w2 = _bf(m.fc2.weight.reshape(-1, hid))
+        self.b2 = _f(m.fc2.bias)
         self.n3w, self.n3b = _chw_affine(m.norm3)
 
 
@@ -83,9 +97,9 @@ class _LN:
 
 
 class _EncLayer:
-    def __init__(self, blk):
+    def __init__(self, blk, half_mid=True):
         self.attn_s = _MHA(blk.SLMHSA.attn)
-        self.ffn_s = _ConvFFN(blk.SpatialFFN)
+        self.ffn_s = _ConvFFN(blk.SpatialFFN, half_mid)
         self.attn_t = _MHA(blk.temporal_MHSA)
         self.n1, self.n2, self.n3, self.n4 = _LN(blk.norm1), _LN(blk.norm2), _LN(blk.norm3), _LN(blk.norm4)
         self.l1w, self.l1b = _bf(blk.linear1.weight), _f(blk.linear1.bias)
@@ -93,10 +107,10 @@ class _EncLayer:
 
 
 class _DecLayer(_EncLayer):
-    def __init__(self, blk):
-        super().__init__(blk)
+    def __init__(self, blk, half_mid=True):
+        super().__init__(blk, half_mid)
         self.attn_x = _MHA(blk.EncDecAttn, split_q=True)
-        self.ffn_x = _ConvFFN(blk.SpatialFFN1)
+        self.ffn_x = _ConvFFN(blk.SpatialFFN1, half_mid)
         self.n5, self.n6 = _LN(blk.norm5), _LN(blk.norm6)
 
 
@@ -128,14 +142,13 @@ class PredictorEngine:
         self.device = dev
         self.ws = Workspace(dev)
         self.stochastic = bool(mod.stochastic)
-        # conv-FFN middle: "split" = ffn_dwconv + ffn_norm2 (default, fastest: DESIGN.md section 4); experimental single-pass
-        # kernels: "cluster" = 16-block clusters exchanging the LN2 statistics through DSMEM, "fused" = the same through L2
-        mid = os.environ.get("NPVP_B200_FFN_MID", "split")
-        if mid == "fused" and _lib.ops().ffn_mid_lanes() <= 0 or mid == "cluster" and _lib.ops().ffn_mid_clusters() <= 0:
-            mid = "split"
-        self._ffn_mid = mid
-        self.enc_layers = [_EncLayer(b) for b in mod.EVT_Former.layers]
-        self.dec_layers = [_DecLayer(b) for b in mod.transformer.layers]
+        # conv-FFN middle: "half" (default) = one single-pass half-precision kernel (npvp_ffn_mid16);
+        # "split" = the fp32 two-kernel path ffn_dwconv + ffn_norm2 (r01; kept for A/B runs and for hidden widths != 2048)
+        mid = os.environ.get("NPVP_B200_FFN_MID", "half")
+        half_mid = mid == "half" and _lib.ops().ffn_mid16_lanes() > 0
+        self._mid16 = {}                                         # frames -> persistent (xch, cnt) exchange scratch
+        self.enc_layers = [_EncLayer(b, half_mid) for b in mod.EVT_Former.layers]
+        self.dec_layers = [_DecLayer(b, half_mid) for b in mod.transformer.layers]
         # encoder-decoder attention: the K / V projections of the (layer-invariant) memory do not depend on the decoder state, so
         # the 8 layers' weights are stacked and each projection is ONE GEMM with N = 8 x 512 per forward instead of 8 GEMMs on
         # only 128 tiles each (M = clips x To x 64 is small); layer l reads columns [512 l, 512 l + 512) of the result
@@ -242,18 +255,23 @@ class PredictorEngine:
         LayerNorm + positional fuse that consumes the updated stream next, fused into the last kernel."""
         op, ws = _lib.ops(), self.ws
         M = x.shape[0]
-        h1 = ws.bf16(f"h1_{tag}", M, w.hid)
-        y2 = ws.bf16(f"y2_{tag}", M, w.hid)
         h3 = ws.bf16(f"h3_{tag}", M, C)       # 16-bit is enough: h3 is re-normalised by LayerNorm((C,8,8)) immediately
-        st1 = ws.f32(f"st1_{tag}", frames, 2)
-        pt2 = ws.f32(f"pt2_{tag}", frames, w.hid // _lib.FFN_CHUNK, 2)
         pt1 = ws.f32(f"pt1_{tag}", frames, 4 * w.hid // 256, 2)
-        op.gemm(a_bf, w.w1, bias=w.b1, out_bf16=h1, frame_stats=pt1)     # LayerNorm((hid,8,8)) statistics from the fc1 epilogue
-        op.ffn_stats_finalize(pt1, st1, 64 * w.hid)
-        if self._ffn_mid != "split" and w.hid == 2048:          # one pass over the frame: h1 read once, GELU(LN2(.)) written once
-            op.ffn_mid(h1, st1, w.n1w, w.n1b, w.dw_w, w.dw_b, w.n2w, w.n2b, y2, xch=pt2 if self._ffn_mid == "fused" else None)
-            h2 = y2
+        if w.half_mid:                        # fc1 (bf16 operands -> half h1 + LN1 partial statistics) -> one-pass middle -> fc2 (half)
+            h1 = ws.h16(f"h1_{tag}", torch.float16, M, w.hid)
+            h2 = ws.h16(f"h2_{tag}", torch.float16, M, w.hid)
+            op.gemm(a_bf, w.w1, bias=w.b1, out_bf16=h1, frame_stats=pt1)
+            scratch = self._mid16.get(frames)
+            if scratch is None:
+                scratch = self._mid16[frames] = _lib.ffn_mid16_scratch(frames, self.device)
+            op.ffn_mid16(h1, pt1, w.ln_wb, w.dw_w16, w.dw_b16, h2, *scratch)
         else:
+            h1 = ws.bf16(f"h1_{tag}", M, w.hid)
+            y2 = ws.bf16(f"y2_{tag}", M, w.hid)
+            st1 = ws.f32(f"st1_{tag}", frames, 2)
+            pt2 = ws.f32(f"pt2_{tag}", frames, w.hid // _lib.FFN_CHUNK, 2)
+            op.gemm(a_bf, w.w1, bias=w.b1, out_bf16=h1, frame_stats=pt1)     # LayerNorm((hid,8,8)) statistics from the fc1 epilogue
+            op.ffn_stats_finalize(pt1, st1, 64 * w.hid)
             op.ffn_dwconv(h1, st1, w.n1w, w.n1b, w.dw_w, w.dw_b, y2, pt2)
             op.ffn_norm2(y2, pt2, w.n2w, w.n2b, h1)             # h1 is dead: reuse it for GELU(LN2(.))
             h2 = h1

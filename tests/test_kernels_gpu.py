@@ -196,32 +196,46 @@ def test_conv_ffn_middle(op, spec):
     close(res[0][3], res[1][3], 2e-2, "ffn norm2")
 
 
-@pytest.mark.parametrize("xchg", ["l2", "dsmem"])
-@pytest.mark.parametrize("frames", [1, 3, 37, 130])
-def test_conv_ffn_middle_fused(op, spec, frames, xchg):
-    """npvp_ffn_mid (one pass; statistics exchange through L2 or through a 16-block cluster's shared memory) against
-    npvp_ffn_dwconv + npvp_ffn_norm2 and the specification."""
+@pytest.mark.parametrize("frames", [1, 3, 37, 130, 640])
+def test_conv_ffn_middle_half(op, spec, frames):
+    """npvp_ffn_mid16 (one pass, half2 arithmetic, statistics exchange through L2) fed by the fc1 GEMM (half output + LN1
+    partial statistics from its epilogue) against the fp32 specification; run twice on one persistent exchange scratch (the
+    kernel must leave it at rest), and the scratch is checked to be back at rest."""
+    from npvp_b200._lib import ffn_mid16_scratch
     Ch = 2048
-    assert op.ffn_mid_lanes() > 0 and op.ffn_mid_clusters() > 0
-    h = (rn(frames * 64, Ch, seed=1, scale=1.5) + 0.2).to(torch.bfloat16)
+    assert op.ffn_mid16_lanes() > 0
+    a = rn(frames * 64, 512, seed=11, dtype=torch.bfloat16)
+    w1, b1 = rn(Ch, 512, seed=12, scale=0.06, dtype=torch.bfloat16), rn(Ch, seed=13, scale=0.3)
+    h1, part1 = torch.empty(frames * 64, Ch, dtype=torch.float16, device=DEV), torch.empty(frames, 32, 2, device=DEV)
+    op.gemm(a, w1, bias=b1, out_bf16=h1, frame_stats=part1)                       # bf16 operands -> half output (out16 = 1)
+    h1_ref, part1_ref = torch.empty_like(h1), torch.empty_like(part1)
+    spec.gemm(a, w1, bias=b1, out_bf16=h1_ref, frame_stats=part1_ref)
+    close(h1, h1_ref, 2e-3, "fc1 half output")
+    close(part1, part1_ref, 1e-3, "fc1 frame statistics")
     n1w, n1b = rn(64, Ch, seed=2) * 0.3 + 1, rn(64, Ch, seed=3) * 0.3
     n2w, n2b = rn(64, Ch, seed=4) * 0.3 + 1, rn(64, Ch, seed=5) * 0.3
-    dw_w, dw_b = rn(9, Ch, seed=6, scale=0.4), rn(Ch, seed=7, scale=0.2)
-    st = torch.empty(frames, 2, device=DEV)
-    op.ffn_frame_stats(h, st)
-    fused, ref = torch.empty_like(h), torch.empty_like(h)
-    xch = torch.empty(frames, Ch // FFN_CHUNK, 2, device=DEV) if xchg == "l2" else None
-    for _ in range(2):                                             # twice: the exchange table must be reusable
-        fused.fill_(float("nan"))
-        op.ffn_mid(h, st, n1w, n1b, dw_w, dw_b, n2w, n2b, fused, xch=xch)
-    spec.ffn_mid(h, st, n1w, n1b, dw_w, dw_b, n2w, n2b, ref)
-    close(fused, ref, 2e-2, "ffn_mid vs spec")
-    y, pt, split = torch.empty_like(h), torch.empty(frames, Ch // FFN_CHUNK, 2, device=DEV), torch.empty_like(h)
-    op.ffn_dwconv(h, st, n1w, n1b, dw_w, dw_b, y, pt)
-    op.ffn_norm2(y, pt, n2w, n2b, split)
-    d = (fused.float() - split.float()).abs()
-    print(f"fused vs split: max abs {float(d.max()):.3e}, mismatching elements {int((d > 0).sum())} / {d.numel()}")
-    close(fused, split, 1e-2, "ffn_mid vs two-kernel path")
+    pair = lambda w, b: torch.stack([w.view(64, Ch // 2, 2), b.view(64, Ch // 2, 2)], dim=2)
+    ln_wb = torch.stack([pair(n1w, n1b), pair(n2w, n2b)], 0).to(torch.float16).contiguous()
+    dw_w, dw_b = rn(9, Ch, seed=6, scale=0.4).to(torch.float16), rn(Ch, seed=7, scale=0.2).to(torch.float16)
+    xch, cnt = ffn_mid16_scratch(frames, DEV)
+    out, ref = torch.empty_like(h1), torch.empty_like(h1)
+    for _ in range(2):
+        out.fill_(float("nan"))
+        op.ffn_mid16(h1, part1, ln_wb, dw_w, dw_b, out, xch, cnt)
+    torch.cuda.synchronize()
+    assert bool((xch.view(torch.int32) == -1).all()) and bool((cnt == 0).all()), "exchange scratch not back at rest"
+    spec.ffn_mid16(h1, part1, ln_wb, dw_w, dw_b, ref, None, None)
+    d = (out.float() - ref.float()).abs()
+    print(f"ffn_mid16 frames={frames}: max abs {float(d.max()):.3e} (max |ref| {float(ref.float().abs().max()):.2f}), mean abs {float(d.mean()):.3e}")
+    assert bool(torch.isfinite(out.float()).all())
+    close(out, ref, 1e-2, "ffn_mid16 vs spec")
+    assert float(d.mean()) < 1.5e-3
+    # fc2 on the half activations with half weights, bf16 output (out16 = 2)
+    w2, b2 = rn(512, Ch, seed=14, scale=0.03).to(torch.float16), rn(512, seed=15, scale=0.3)
+    h3, h3_ref = torch.empty(frames * 64, 512, dtype=torch.bfloat16, device=DEV), torch.empty(frames * 64, 512, dtype=torch.bfloat16, device=DEV)
+    op.gemm(out, w2, bias=b2, out_bf16=h3)
+    spec.gemm(out, w2, bias=b2, out_bf16=h3_ref)
+    close(h3, h3_ref, 1e-2, "fc2 half operands -> bf16 output")
 
 
 @pytest.mark.parametrize("mode,n,Tq,Tk,mask", [(0, 2, 3, 3, False), (1, 2, 5, 5, True), (1, 2, 5, 5, False), (1, 1, 7, 3, False),
