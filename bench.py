@@ -88,25 +88,26 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on host cores
 # ----------------------------------------------------------------------------------------------------------------
-def oracle_rollout_fn(clips: int):
-    """Returns (fn, frames_per_call): fn() runs the CPU oracle's block-AR 2->28 rollout for `clips` clips."""
+def oracle_rollout_fn(clips: int, device="cpu"):
+    """Returns (fn, frames_per_call): fn() runs the oracle's block-AR 2->28 rollout for `clips` clips on `device` (CPU: the
+    reference arm / cpu_baseline; a CUDA device: the reference's eager PyTorch path on the GPU, `gpu_eager_baseline`)."""
     from npvp_b200.pipeline import build_from_config
     from oracle import npvp_oracle as O
     torch.set_num_threads(os.cpu_count())
     model = build_from_config(PRESET, device="cpu", seed=0)
     cfg = model.cfg
     ocfg = dict(n_downsampling=cfg.AE.n_downsampling, num_res_blocks=cfg.AE.num_res_blocks, out_layer=cfg.AE.out_layer, stochastic=True)
-    esd, psd, dsd = model.VPTR_Enc.state_dict(), model.predictor.state_dict(), model.VPTR_Dec.state_dict()
+    esd, psd, dsd = ({k: v.to(device) for k, v in m.state_dict().items()} for m in (model.VPTR_Enc, model.predictor, model.VPTR_Dec))
     g = torch.Generator().manual_seed(1234)
-    x = torch.rand((clips, 2, 3, 128, 128), generator=g) * 2 - 1
+    x = (torch.rand((clips, 2, 3, 128, 128), generator=g) * 2 - 1).to(device)
 
     hl = torch.linspace(0, 7, 8)
-    short = O.coor_generator(model.tp_list[:N_FUTURE % 10], hl, hl, cfg.Predictor.max_T, 8, 8)   # last block: 8 target timestamps
+    short = O.coor_generator(model.tp_list[:N_FUTURE % 10], hl, hl, cfg.Predictor.max_T, 8, 8).to(device)   # last block: 8 target timestamps
 
     def fn():
         ctx, done, outs = x, 0, []
         while done < N_FUTURE:
-            eps = torch.randn((clips, 512, 8, 8), generator=g)
+            eps = torch.randn((clips, 512, 8, 8), generator=g).to(device)
             take = min(10, N_FUTURE - done)
             # like rollout(last_block="query"): the last block asks only for the timestamps that are still needed
             pred = O.npvp_predict_frames(esd, psd, dsd, ctx, ocfg, psd["observed_coor"], psd["predict_coor"] if take == 10 else short, eps)
@@ -135,6 +136,55 @@ def cpu_baseline_forward(preset: str, n: int, to: int, tp_n: int) -> float:
     return n * tp_n / (time.perf_counter() - t0)
 
 
+def gpu_eager_baseline(dev, clips_list=(8, 64)):
+    """See _gpu_eager_baseline: the YAML batch size (8 clips) and the GPU arm's own batch (64 clips)."""
+    return {f"clips_{c}": _gpu_eager_baseline(dev, c) for c in clips_list}
+
+
+def _gpu_eager_baseline(dev, clips: int = 8):
+    """The reference's eager PyTorch path on THIS GPU ("the bar is the reference's eager PyTorch path"; BASELINE.md
+    section 3): the oracle - the same torch ops the reference modules dispatch to (cuDNN / cuBLAS / ATen) - run on the CUDA device
+    on the bench workload, CUDA-event timed, in the three modes a maintainer of Inference.ipynb would try: fp32 with TF32 off (the
+    parity reference), TF32 on, and torch.autocast(bfloat16).  Kernel launches of one rollout counted with torch.profiler."""
+    fn, frames = oracle_rollout_fn(clips, device=dev)
+    res = {"clips": clips, "frames_per_rollout": frames, "unit": "frames/s",
+           "what": "oracle port of the reference path as eager PyTorch on this GPU (torch %s), %d clips, block-AR 2->28" % (torch.__version__, clips)}
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+
+    def timeit(run):
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        return 2 * frames / (e0.elapsed_time(e1) * 1e-3)
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+        res["fp32"] = timeit(fn)
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                fn()
+                torch.cuda.synchronize()
+            res["kernel_launches_per_rollout"] = int(sum(e.count for e in prof.key_averages() if e.device_type is not None and "cuda" in str(e.device_type).lower()))
+        except Exception as exc:                                # the count is a diagnostic: never lose the timings over it
+            res["kernel_launches_per_rollout"] = None
+            res["profiler_error"] = repr(exc)[:200]
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+        res["tf32"] = timeit(fn)
+
+        def autocast():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                fn()
+        res["bf16_autocast"] = timeit(autocast)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -155,7 +205,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_step": clips, "device": "host CPU"},
+        "config": {"workload": WORKLOAD, "clips_per_step": clips, "device": "host CPU", "same_config_as_gpu_arm": False,
+                   "note": "bounded sample: 2 clips per step against 64 per GPU on the GPU arm (CPU throughput is flat in the batch size, "
+                           "BASELINE.md section 2); the oracle port runs the same torch CPU ops as the reference modules (max |diff| 4e-5, tests/golden/REPORT.txt)"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -185,7 +237,13 @@ class GemmTimer:
             self._orig_conv(x, w, frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo, *a, **kw)
             e1.record()
             M, K = frames * Ho * Wo, KH * KW * Cc
-            self.records.append((e0, e1, 2.0 * M * K * w.shape[0], (M, w.shape[0], K)))
+            flops = 2.0 * M * K * w.shape[0]
+            if KH == 2 and KW == 2 and stride == 1 and pad == 0 and w.shape[0] % 4 == 0:
+                # ConvTranspose2d(3, s2, p1, op1) run as a GEMM over the 2x2 input neighbourhood with N = 4 Cout (engine_autoencoder):
+                # 9 of its 16 (phase, tap) weight blocks are live.  ALGORITHMIC work = 9 Cin Cout MACs per input pixel
+                # (SURVEY Appendix A.12), whatever the kernel multiplies.
+                flops *= 9.0 / 16.0
+            self.records.append((e0, e1, flops, (M, w.shape[0], K)))
         self._orig_conv = self.ops.conv_gemm
         self.ops.gemm, self.ops.conv_gemm = timed, timed_conv
         return self
@@ -222,8 +280,11 @@ class MemTimer:
         rows512 = lambda t: t.shape[0] * 512 * t.element_size()          # strided [rows, 512] views of wider matrices
         self.ops, self.records, self._saved = ops, [], {}
         self.formulas = {
-            "ffn_dwconv": lambda a, k: B(a[0]) + B(a[6]),
-            "ffn_norm2": lambda a, k: B(a[0]) + B(a[4]),
+            # conv-FFN middle: ONE 16-bit frame in + ONE out per frame-FFN (0.524 MB), for whichever kernels implement it
+            "ffn_mid16": lambda a, k: B(a[0]) + B(a[5]),
+            "ffn_dwconv": lambda a, k: B(a[0]),
+            "ffn_norm2": lambda a, k: B(a[4]),
+            "ffn_stats_finalize": lambda a, k: 0.0,
             "attention": lambda a, k: rows512(a[0]) + rows512(a[1]) + rows512(a[2]) + rows512(a[3]),
             "frame_ln_gelu_residual_posfuse": lambda a, k: B(a[0]) + 2 * B(a[3]) + B(a[9]) + B(a[10]),
             "ln_posfuse": lambda a, k: B(a[0]) + B(a[6]) + B(a[7]),
@@ -255,15 +316,17 @@ class MemTimer:
 
     def summary(self, hbm_gbs):
         torch.cuda.synchronize()
+        family = {"ffn_mid16": "conv_ffn_middle", "ffn_dwconv": "conv_ffn_middle", "ffn_norm2": "conv_ffn_middle",
+                  "ffn_stats_finalize": "conv_ffn_middle"}     # one family: 0.524 MB algorithmic per frame-FFN however many kernels run
         agg = {}
         for name, e0, e1, byts in self.records:
-            a = agg.setdefault(name, [0, 0.0, 0.0])
-            a[0] += 1; a[1] += e0.elapsed_time(e1) * 1e-3; a[2] += byts
+            a = agg.setdefault(family.get(name, name), [0, 0.0, 0.0, set()])
+            a[0] += 1; a[1] += e0.elapsed_time(e1) * 1e-3; a[2] += byts; a[3].add(name)
         out = []
-        for name, (n, sec, byts) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        for name, (n, sec, byts, members) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             gbs = byts / sec * 1e-9 if sec > 0 else 0.0
-            out.append({"kernel": name, "bound": "hbm", "launches_per_step": n, "ms_per_step": 1e3 * sec, "bytes_per_step": byts,
-                        "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs})
+            out.append({"kernel": name, "members": sorted(members), "bound": "hbm", "launches_per_step": n, "ms_per_step": 1e3 * sec,
+                        "bytes_per_step": byts, "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs})
         return out
 
 
@@ -291,15 +354,18 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > 126 MB L2
 
     def step_device():
-        # N > 1: the all-gather of each AR block's frames is issued asynchronously and overlaps the next block's kernels
-        return model.rollout(x_dev, N_FUTURE, gather_group=True if world > 1 else None, last_block=LAST_BLOCK)
+        # N > 1: the one exchange of the path - the frames of every AR block are gathered on rank 0 as uint8 pixel frames
+        # (what a video consumer takes: VidReNormalize + clamp + uint8, utils/dataset.py:860-886), asynchronously, overlapping the
+        # next block's kernels (npvp_b200.distributed.BlockGather)
+        return model.rollout(x_dev, N_FUTURE, gather_group=True if world > 1 else None, gather_dst=0, gather_dtype=torch.uint8,
+                             last_block=LAST_BLOCK)
 
     def step_e2e():
         # public API on host buffers: async H2D of the context frames, per-block D2H of the frames on a copy stream
         # wait_output=False: the tail copy of one call overlaps the first block of the next; timed() synchronises the device
-        # before it stops the clock, so every copy is inside the timed region
-        model.rollout(host_in, N_FUTURE, out_host=host_out, gather_group=True if world > 1 else None, last_block=LAST_BLOCK,
-                      wait_output=False)
+        # before it stops the clock, so every copy is inside the timed region.  N > 1: every rank delivers its own shard to its
+        # own pinned host buffer (the batch is gathered in host memory: no device-side exchange is needed on this path)
+        model.rollout(host_in, N_FUTURE, out_host=host_out, last_block=LAST_BLOCK, wait_output=False)
 
     host_out_u8 = torch.empty(host_out.shape, dtype=torch.uint8).pin_memory()
 
@@ -366,6 +432,21 @@ def run_ours(args):
     e2e_steps = max(2, min(args.steps, 10))
     e2e_u8_ms = timed(step_e2e_u8, e2e_steps, 1, whole=True) if world == 1 else None
 
+    gather_equal = None
+    if world > 1:
+        # what tests/test_multigpu_gpu.py claims, proven inside the driver's scaling run: with seeded inputs and injected latent
+        # noise, rank 0 recomputes the first clip of rank 1 locally and compares it BITWISE with what arrived through NCCL
+        def seeded(r):
+            gg = torch.Generator(device="cpu").manual_seed(99 + r)
+            xs = (torch.rand((B, 2, 3, 128, 128), generator=gg) * 2 - 1).to(dev)
+            return xs, [torch.randn((B, 512, 8, 8), generator=gg).to(dev) for _ in range(3)]
+        xs, es = seeded(rank)
+        got = model.rollout(xs, N_FUTURE, es, gather_group=True, gather_dst=0, gather_dtype=torch.uint8, last_block=LAST_BLOCK)
+        if rank == 0:
+            x1, e1 = seeded(1)
+            mine = model.to_pixels(model.rollout(x1[:1], N_FUTURE, [e[:1] for e in e1], last_block=LAST_BLOCK), uint8=True)
+            gather_equal = bool(torch.equal(got[B:B + 1], mine)) and tuple(got.shape) == (B * world, N_FUTURE, 3, 128, 128)
+
     roof, roof_mem = None, None
     if rank == 0:
         model.use_cuda_graphs(False)                           # per-launch events need eager launches
@@ -405,12 +486,20 @@ def run_ours(args):
             dt = time.perf_counter() - t0
             cpu = {"value": frames / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"4 clips x 28 frames, one rollout after one warm-up (oracle port, fp32, {os.cpu_count()} torch threads)"}
+        eager = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                eager = gpu_eager_baseline(dev)
+            except Exception as exc:                           # never lose the bench line over the extra baseline
+                eager = {"error": repr(exc)[:300]}
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_gpu": B, "global_clips": B * world, "frames_per_clip": N_FUTURE,
-                       "parallelism": f"dp{world} batch-sharded, all_gather of frames" if world > 1 else "single GPU",
+                       "parallelism": (f"dp{world} batch-sharded, weights replicated; one exchange: per-block async gather of the uint8 "
+                                       "pixel frames on rank 0 (NCCL grouped send/recv)") if world > 1 else "single GPU",
+                       "gather_equal": gather_equal,
                        "l2": "256 MiB buffer written between timed steps; per-step activations also exceed the 126 MB L2",
                        "arith": "predictor bf16 / autoencoder fp16 operands, fp32 accumulate / residual / statistics",
                        "cuda_graphs": bool(args.graphs)},
@@ -437,6 +526,8 @@ def run_ours(args):
             line["roofline_e2e"] = {"error": repr(exc)}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if eager is not None:
+            line["gpu_eager_baseline"] = eager
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -22,8 +22,32 @@ class _EngineModule(nn.Module):
         if not x.is_cuda:
             raise NotImplementedError(f"{type(self).__name__}: input must be a CUDA tensor (there is no CPU fallback)")
 
+    _NOT_WEIGHTS = ("observed_coor", "predict_coor", "all_coor")      # derived coordinate buffers: not packed into the engine
+
     def _weights_version(self):
-        return tuple(int(t._version) for t in list(self.parameters()) + list(self.buffers())), next(self.parameters()).device
+        """Cheap fingerprint of the weights the engine packed: (sum of the tensors' in-place modification counters, tensor
+        count, device).  The counters only grow, so the sum changes whenever any weight is written (load_state_dict, optimiser
+        step, manual edits).  The tensor list is cached - walking the module tree (~800 tensors) on every call cost 0.3 ms per
+        module and forward, visible at batch 1 - and dropped whenever ``.to()`` / ``.cuda()`` / ``.half()`` may have replaced
+        tensors (``_apply``)."""
+        ts = self.__dict__.get("_ver_tensors")
+        if ts is None:
+            ts = [t for _, t in self.named_parameters()] + [t for n, t in self.named_buffers() if n.rsplit(".", 1)[-1] not in self._NOT_WEIGHTS]
+            self.__dict__["_ver_tensors"] = ts
+        v = 0
+        for t in ts:
+            v += t._version
+        return v, len(ts), ts[0].device
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_ver_tensors", None)
+        self.__dict__.pop("_eng", None)
+        return super()._apply(fn, *args, **kwargs)
+
+    def _on_device(self, x: torch.Tensor):
+        """Context that makes the input's GPU the current device: the C-ABI launches on ``torch.cuda.current_stream()``, i.e. in
+        the CURRENT device's context - a model built on cuda:1 while cuda:0 is current would otherwise launch on the wrong GPU."""
+        return torch.cuda.device(x.device)
 
     def _engine(self):
         key = self._weights_version()
@@ -68,12 +92,14 @@ class ResnetEncoder(_EngineModule):
     def forward(self, x):
         """x: (N, T, C, H, W) fp32 CUDA -> (N, T, ngf*2^n, H/2^n, W/2^n) fp32."""
         self._guard(x)
-        return self._engine().run(x)
+        with self._on_device(x):
+            return self._engine().run(x)
 
     def forward_tokens(self, x):
         """Engine-internal variant: returns channels-last features (N, T, h, w, C) without the NCHW copy."""
         self._guard(x)
-        return self._engine().run(x, channels_last=True)
+        with self._on_device(x):
+            return self._engine().run(x, channels_last=True)
 
 
 class ResnetDecoder(_EngineModule):
@@ -101,9 +127,11 @@ class ResnetDecoder(_EngineModule):
     def forward(self, x):
         """x: (N, T, C, h, w) fp32 CUDA -> (N, T, output_nc, H, W) fp32."""
         self._guard(x)
-        return self._engine().run(x)
+        with self._on_device(x):
+            return self._engine().run(x)
 
     def forward_tokens(self, x_cl):
         """Engine-internal variant: takes channels-last features (N, T, h, w, C)."""
         self._guard(x_cl)
-        return self._engine().run(x_cl, channels_last=True)
+        with self._on_device(x_cl):
+            return self._engine().run(x_cl, channels_last=True)

@@ -83,11 +83,16 @@ PRESETS: Dict[str, AttrDict] = {
     "SMMNIST_VFP_NPVP-D": _preset("SMMNIST", 1, 64, 5, 10, 64, 3, 2, "Sigmoid", 15, False),
     # BASELINE.json's text for config 1 says "10 context -> 10 future"; the YAML above is 5 -> 10.  Labelled variant:
     "SMMNIST_VFP_NPVP-D_10to10": _preset("SMMNIST", 1, 64, 10, 10, 64, 3, 2, "Sigmoid", 20, False),
-    "KTH_Unified_NPVP-S": _preset("KTH", 1, 64, 10, 10, 64, 3, 2, "Tanh", 20, True, rand_context=True),
+    "KTH_Unified_NPVP-S": _preset("KTH", 1, 64, 10, 10, 64, 3, 2, "Tanh", 20, True, rand_context=True, test_future=20),
     "BAIR_VFP_NPVP-S": _preset("BAIR", 3, 64, 2, 10, 64, 3, 2, "Tanh", 12, True, test_future=28),
     "Cityscapes_VFP_NPVP-D": _preset("CityScapes", 3, 128, 2, 10, 32, 4, 3, "Tanh", 12, False, test_future=28),
     "Cityscapes_VFP_NPVP-S": _preset("CityScapes", 3, 128, 2, 10, 32, 4, 3, "Tanh", 12, True, test_future=28),
     "KITTI_VFP_NPVP-S": _preset("KITTI", 3, 128, 4, 5, 32, 4, 3, "Tanh", 9, True, batch=16),
+    # NOT shipped YAMLs: the one-shot 2 -> 28 variants of BASELINE configs 3 / 4 (the YAMLs' max_T = 12 forbids
+    # 28 target timestamps in one call; max_T = 30 is the smallest change that allows it - Predictor.py:41, submodules.py:351)
+    "BAIR_VFP_NPVP-S_oneshot28": _preset("BAIR", 3, 64, 2, 28, 64, 3, 2, "Tanh", 30, True),
+    "Cityscapes_VFP_NPVP-D_oneshot28": _preset("CityScapes", 3, 128, 2, 28, 32, 4, 3, "Tanh", 30, False),
+    "Cityscapes_VFP_NPVP-S_oneshot28": _preset("CityScapes", 3, 128, 2, 28, 32, 4, 3, "Tanh", 30, True),
 }
 
 

@@ -147,6 +147,7 @@ class PredictorEngine:
         mid = os.environ.get("NPVP_B200_FFN_MID", "half")
         half_mid = mid == "half" and _lib.ops().ffn_mid16_lanes() > 0
         self._mid16 = {}                                         # frames -> persistent (xch, cnt) exchange scratch
+        self._pos_lru = {}                                       # coordinate tensor key -> (tensor, (beta, gamma), buffers)
         self.enc_layers = [_EncLayer(b, half_mid) for b in mod.EVT_Former.layers]
         self.dec_layers = [_DecLayer(b, half_mid) for b in mod.transformer.layers]
         # encoder-decoder attention: the K / V projections of the (layer-invariant) memory do not depend on the decoder state, so
@@ -169,48 +170,69 @@ class PredictorEngine:
     # ------------------------------------------------------------------------------------------
     # positional code
     # ------------------------------------------------------------------------------------------
-    def positional(self, coor, tag):
-        """NRMLP (submodules.py:299-327): coor fp32 [R,3] -> (beta [R,512], gamma [R,512] | None)."""
-        op, ws = _lib.ops(), self.ws
+    def positional(self, coor, bufs):
+        """NRMLP (submodules.py:299-327): coor fp32 [R,3] -> (beta [R,512], gamma [R,512] | None), written into ``bufs`` (a dict
+        of scratch / result buffers owned by one table slot, allocated on first use)."""
+        op = _lib.ops()
         coor = coor.detach().to(self.device, torch.float32).contiguous()
         R = coor.shape[0]
         half = self.nr_B.shape[0]
-        cur = ws.f32(f"nr_ff_{tag}", R, 2 * half)
+
+        def buf(name, cols):
+            t = bufs.get(name)
+            if t is None or t.shape != (R, cols):
+                t = bufs[name] = torch.empty(R, cols, dtype=torch.float32, device=self.device)
+            return t
+        cur = buf("ff", 2 * half)
         op.fourier_features(coor, self.nr_B, cur)
         for i, (w, b) in enumerate(self.nr_mlp):
-            nxt = ws.f32(f"nr_h{i}_{tag}", R, w.shape[0])
+            nxt = buf(f"h{i}", w.shape[0])
             op.gemm_f32(cur, w, b, ACT_RELU, nxt)
             cur = nxt
-        beta = ws.f32(f"nr_beta_{tag}", R, C)
+        beta = buf("beta", C)
         op.gemm_f32(cur, self.nr_beta[0], self.nr_beta[1], ACT_NONE, beta)
         gamma = None
         if self.nr_gamma is not None:
-            gamma = ws.f32(f"nr_gamma_{tag}", R, C)
+            gamma = buf("gamma", C)
             op.gemm_f32(cur, self.nr_gamma[0], self.nr_gamma[1], ACT_NONE, gamma)
         return beta, gamma
 
-    def positional_async(self, oc, pc):
-        """Fork: compute both positional codes on a side stream (ordered after everything already queued on the current
-        stream, so the previous forward has finished with the buffers).  ``run`` joins.  Works under CUDA-graph capture,
-        where it becomes a parallel branch of the graph."""
-        cur = torch.cuda.current_stream(self.device)
-        side = self.__dict__.get("_pos_stream")
-        if side is None:
-            side = self._pos_stream = torch.cuda.Stream(device=self.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            bo = self.positional(oc, "o")
-            bp = self.positional(pc, "p")
-        self._pos_pending = (oc, pc, bo, bp, side)
+    @staticmethod
+    def _coor_key(coor):
+        """Identity of a coordinate tensor's CONTENT as far as it can be told without reading it: storage address, shape and
+        the tensor's in-place modification counter.  The table slot keeps a reference to the tensor, so the address cannot be
+        recycled for other coordinates while the entry lives."""
+        return (coor.data_ptr(), tuple(coor.shape), int(coor._version), coor.device)
+
+    def positional_table(self, coor, slot=None):
+        """Cached NRMLP code of ``coor``.  The code depends only on the coordinates and the NRMLP weights (0.6-1.5
+        GFLOP of fp32 work per forward when recomputed, 24 launches), so it is computed once per coordinate tensor and kept in
+        a small LRU table (the engine itself is rebuilt when any weight changes).  ``slot``: a dict owned by the caller
+        (a captured CUDA graph) that pins the result buffers: the table is then recomputed IN PLACE when the coordinates
+        change, so that pointers baked into the graph stay valid."""
+        key = self._coor_key(coor)
+        if slot is not None:
+            if slot.get("key") != key:
+                slot["key"], slot["coor"] = None, coor
+                slot["val"] = self.positional(coor, slot.setdefault("bufs", {}))
+                slot["key"] = key
+            return slot["val"]
+        lru = self._pos_lru
+        hit = lru.pop(key, None)
+        if hit is None:
+            bufs = {}
+            if len(lru) >= 8:                                   # recycle the buffers of the least recently used entry
+                old_key = next(iter(lru))
+                bufs = lru.pop(old_key)[2]
+            hit = (coor, self.positional(coor, bufs), bufs)
+        lru[key] = hit                                          # (re-)insert as most recently used
+        return hit[1]
 
     def _positional_pair(self, oc, pc):
-        pend = self.__dict__.pop("_pos_pending", None)
-        if pend is not None and pend[0] is oc and pend[1] is pc:
-            torch.cuda.current_stream(self.device).wait_stream(pend[4])      # join
-            return pend[2], pend[3]
-        if pend is not None:                                                  # stale prefetch (coordinates replaced): still join
-            torch.cuda.current_stream(self.device).wait_stream(pend[4])
-        return self.positional(oc, "o"), self.positional(pc, "p")
+        slots = self.__dict__.get("_graph_slots")               # set by a captured forward (pipeline._GraphedPredict)
+        if slots is not None:
+            return self.positional_table(oc, slots[0]), self.positional_table(pc, slots[1])
+        return self.positional_table(oc), self.positional_table(pc)
 
     # ------------------------------------------------------------------------------------------
     # building blocks (x: fp32 residual stream [M,512], updated in place)

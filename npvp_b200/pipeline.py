@@ -38,6 +38,20 @@ def timestamp_lists(cfg):
     return to, tp
 
 
+def _on_model_device(fn):
+    """Run a method with the model's GPU as the current CUDA device (the C-ABI launches on the current device's stream)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapped
+
+
 class NPVPInference(nn.Module):
     def __init__(self, cfg):
         super().__init__()
@@ -91,14 +105,29 @@ class NPVPInference(nn.Module):
         return batch
 
     # -- checkpoints --------------------------------------------------------------------------------
-    def load_lightning_ckpt(self, path: str, strict: bool = True):
-        """Load a reference Lightning ``.ckpt`` (keys VPTR_Enc.*, VPTR_Dec.*, predictor.*; Predictor.py:18-19,43)."""
-        blob = torch.load(path, map_location="cpu")
-        sd = blob.get("state_dict", blob)
+    def load_lightning_ckpt(self, path: str, strict: bool = True, trust_pickle: bool = False):
+        """Load a reference Lightning ``.ckpt`` (keys VPTR_Enc.*, VPTR_Dec.*, predictor.*; Predictor.py:18-19,43).
+
+        Only the ``state_dict`` entry is used; keys of other top-level modules of the LightningModule (losses, discriminator)
+        are dropped.  The file is first read with ``weights_only=True`` (tensors and plain containers only).  Lightning
+        checkpoints that pickle arbitrary objects next to the weights (hyper-parameter objects, callback state) need the
+        unsafe unpickler like the reference's own ``load_from_checkpoint``: pass ``trust_pickle=True`` for files you trust."""
+        import pickle
+        try:
+            blob = torch.load(path, map_location="cpu", weights_only=True)
+        except (pickle.UnpicklingError, RuntimeError) as exc:
+            if not trust_pickle:
+                raise RuntimeError(f"{path}: not loadable with weights_only=True ({exc}); pass trust_pickle=True if the file is "
+                                   "trusted (it is then unpickled like the reference does)") from exc
+            blob = torch.load(path, map_location="cpu", weights_only=False)
+        sd = blob.get("state_dict", blob) if isinstance(blob, dict) else blob
         keep = {k: v for k, v in sd.items() if k.split(".")[0] in ("VPTR_Enc", "VPTR_Dec", "predictor")}
+        if not keep:
+            raise KeyError(f"{path}: no VPTR_Enc.* / VPTR_Dec.* / predictor.* entries in the checkpoint's state_dict")
         return self.load_state_dict(keep, strict=strict)
 
     # -- reference-faithful forward -----------------------------------------------------------------
+    @_on_model_device
     def forward(self, past_frames, future_frames=None):
         past_feats = self.VPTR_Enc(past_frames)
         rec_past = self.VPTR_Dec(past_feats)
@@ -119,6 +148,7 @@ class NPVPInference(nn.Module):
         finally:
             self.predictor.injected_eps = None
 
+    @_on_model_device
     def predict_samples(self, past_frames, n_samples: int, eps: Optional[torch.Tensor] = None):
         """NPVP-S: ``n_samples`` futures per clip -> (N, n_samples, Tp, Cimg, H, W).  The frame encoder, the EVT_Former and
         the prior run once per clip; latent sampling, the NAR decoder and the frame decoder run per sample (BASELINE
@@ -133,43 +163,56 @@ class NPVPInference(nn.Module):
         finally:
             self.predictor.injected_eps = None
 
+    MAX_GRAPHS = 8          # captured forwards kept per model (least recently used first out; each owns a private memory pool)
+
     def use_cuda_graphs(self, enabled: bool = True):
-        """Replay ``predict`` as one CUDA graph per (batch shape, timestamps, weights version): the ~430 kernel launches
-        of a forward are launch-bound at small batch.  The returned tensor is then a graph-owned buffer that the next
-        ``predict`` call with the same shapes overwrites."""
+        """Replay ``predict`` as one CUDA graph per (batch shape, number of context / target timestamps, per-clip or shared
+        timestamps, weights version): the ~400 kernel launches of a forward are launch-bound at small batch.  The returned
+        tensor is then a graph-owned buffer that the next ``predict`` call with the same shapes overwrites.
+
+        The timestamps themselves are NOT part of the key: the positional codes live in buffers owned by the captured forward
+        and are recomputed in place, outside the graph, whenever ``reset_pos_coor`` / ``rand_context_batch_process`` installs
+        new coordinates - a serving loop with random contexts (KTH unified) replays one graph.  At most ``MAX_GRAPHS`` captured
+        forwards are kept; the least recently used one is dropped together with its memory pool."""
         self._graphs = {} if enabled else None
         return self
 
     def _graph_key(self, x):
         p = self.predictor
-        return (tuple(x.shape), x.device, p.observed_coor.data_ptr(), p.predict_coor.data_ptr(), tuple(p.observed_coor.shape),
-                tuple(p.predict_coor.shape), self.VPTR_Enc._weights_version(), self.VPTR_Dec._weights_version(), p._weights_version())
+        return (tuple(x.shape), x.device, tuple(p.observed_coor.shape), tuple(p.predict_coor.shape), int(getattr(p, "_coor_clips", 0)),
+                self.VPTR_Enc._weights_version(), self.VPTR_Dec._weights_version(), p._weights_version())
 
+    @_on_model_device
     def predict(self, past_frames, eps: Optional[torch.Tensor] = None):
         """past_frames (N,To,Cimg,H,W) fp32 CUDA -> predicted frames (N,Tp,Cimg,H,W) fp32.
         ``eps``: optional injected latent noise (N,512,8,8) for NPVP-S (default: torch.randn like the reference)."""
         graphs = getattr(self, "_graphs", None)
         if graphs is None:
             return self._predict_eager(past_frames, eps)
+        self.predictor._coords_ready()
         key = self._graph_key(past_frames)
-        g = graphs.get(key)
+        g = graphs.pop(key, None)
         if g is None:
-            g = graphs[key] = _GraphedPredict(self, past_frames)
+            while len(graphs) >= self.MAX_GRAPHS:            # evict the least recently used captured forward (and its pool)
+                graphs.pop(next(iter(graphs)))
+            g = _GraphedPredict(self, past_frames)
+        graphs[key] = g                                       # (re-)insert as most recently used
         return g(past_frames, eps)
 
     def _short_block_coor(self, take: int):
         """Target coordinates of the first ``take`` timestamps the predictor is currently aimed at: the leading rows of its
         ``predict_coor`` (rows are timestamp-major), so the short block follows ``reset_pos_coor`` like the full blocks do.
-        The slice shares the buffer's storage, so a captured CUDA graph of the short block (keyed by pointer and shape) is
-        found again on the next rollout."""
+        The slice shares the buffer's storage and modification counter, so its cached positional code is found again on the
+        next rollout (engine_predictor.PredictorEngine.positional_table)."""
         p = self.predictor
         assert getattr(p, "_coor_clips", 0) == 0, "rollout(last_block='query') needs timestamps shared by the batch"
         rows = p.predict_coor.shape[0] // int(p.TP)
         return p.predict_coor[:take * rows]
 
+    @_on_model_device
     def rollout(self, past_frames, num_future: int, eps_list: Optional[Sequence[torch.Tensor]] = None,
                 out_host: Optional[torch.Tensor] = None, gather_group=None, last_block: str = "truncate",
-                wait_output: bool = True):
+                wait_output: bool = True, gather_dst: Optional[int] = 0, gather_dtype: torch.dtype = torch.float32):
         """Block-autoregressive VFP: predict len(tp_list) frames, feed the last To predictions back as context
         (image space), repeat until ``num_future`` frames exist.
 
@@ -190,14 +233,27 @@ class NPVPInference(nn.Module):
         that calls ``rollout`` back to back then overlaps the tail copy of one call with the first block of the next.
 
         ``gather_group`` (a ``torch.distributed`` process group, or ``True`` for the default group; every rank holds the
-        same number of clips): the frames of all ranks are all-gathered BLOCK BY BLOCK with asynchronous NCCL collectives,
-        so the exchange of block i overlaps the kernels of block i+1; the call returns the global batch
-        (world * N, num_future, C, H, W), rank-major like ``distributed.gather_frames``."""
+        same number of clips): the frames of all ranks are gathered BLOCK BY BLOCK with asynchronous collectives, so the
+        exchange of block i overlaps the kernels of block i+1 (``distributed.BlockGather``).  ``gather_dst``: the group rank
+        that receives the global batch (world * N, num_future, C, H, W), rank-major (default 0; the other ranks get their own
+        shard back), or ``None``: every rank receives it (all-gather).  ``gather_dtype``: what travels - ``torch.float32``
+        (model-space frames, bit-identical to the single-GPU result), ``torch.float16`` (model space, rounded) or
+        ``torch.uint8`` (pixel-space frames like ``to_pixels(uint8=True)``: a quarter of the bytes)."""
         dev = next(self.parameters()).device
         if not past_frames.is_cuda:
             past_frames = past_frames.to(dev, non_blocking=True)
-        To, Tp = past_frames.shape[1], int(self.tp_list.shape[0])
-        assert To == int(self.to_list.shape[0])
+        p = self.predictor
+        p._coords_ready()
+        if int(getattr(p, "_coor_clips", 0)):
+            raise ValueError("rollout: block-autoregressive feedback needs timestamps shared by the batch (reset_pos_coor), not per-clip ones")
+        To, Tp = int(p.observed_coor.shape[0]) // 64, int(p.TP)          # the predictor's CURRENT targeting (reset_pos_coor / batch fns)
+        if past_frames.shape[1] != To:
+            raise ValueError(f"rollout: the predictor is aimed at {To} context frames but the input has {past_frames.shape[1]}")
+        t_o, t_p = p.observed_coor[::64, 0], p.predict_coor[::64, 0]
+        if not (bool((t_o[1:] > t_o[:-1]).all()) and bool((t_p[1:] > t_p[:-1]).all()) and bool(t_p[0] > t_o[-1])):
+            raise ValueError("rollout: feeding predictions back as context only makes sense for future prediction (increasing context "
+                             "timestamps followed by increasing target timestamps); the predictor is aimed at an interpolation / "
+                             "random-context task")
         copy_stream = None
         if out_host is not None:
             assert not out_host.is_cuda and out_host.shape[1] == num_future
@@ -205,11 +261,14 @@ class NPVPInference(nn.Module):
             copy_stream = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=dev))
         as_u8 = out_host is not None and out_host.dtype == torch.uint8
         out_u8 = None
-        pending, full, asm_stream = [], None, None          # async all-gathers in flight (handles keep their buffers alive)
+        gatherer = None
         if gather_group is not None:
             import torch.distributed as dist
+            from .distributed import BlockGather
             group = None if gather_group is True else gather_group
-            world = dist.get_world_size(group)
+            assert gather_dtype in (torch.float32, torch.float16, torch.uint8), "gather_dtype: float32, float16 or uint8"
+            if dist.get_world_size(group) > 1:
+                gatherer = BlockGather(group, gather_dst, num_future)
         out, ctx, done, blk = None, past_frames, 0, 0
         assert last_block in ("truncate", "query")
         while done < num_future:
@@ -229,10 +288,11 @@ class NPVPInference(nn.Module):
                 out = torch.empty((pred.shape[0], num_future) + tuple(pred.shape[2:]), dtype=pred.dtype, device=pred.device)
             out[:, done:done + take].copy_(pred[:, :take])
             src, s0 = out, done
-            if as_u8:                                        # one kernel per block on the whole (N, Tp, C, H, W) prediction
-                mean, std = self._renorm_constants()
+            if as_u8 or (gatherer is not None and gather_dtype == torch.uint8):
+                mean, std = self._renorm_constants()        # one kernel per block on the whole (N, Tp, C, H, W) prediction
                 out_u8 = torch.empty(pred.shape, dtype=torch.uint8, device=pred.device)
                 _lib.ops().frames_to_pixels(pred.contiguous(), mean, std, out_u8=out_u8)
+            if as_u8:
                 src, s0 = out_u8, 0
             if copy_stream is not None:                      # D2H of this block overlaps the next block's kernels
                 ready = torch.cuda.Event()
@@ -245,24 +305,13 @@ class NPVPInference(nn.Module):
                         out_host[i, done:done + take].copy_(src[i, s0:s0 + take], non_blocking=True)
                     if as_u8:
                         out_u8.record_stream(copy_stream)
-            if gather_group is not None and world > 1:
-                # a private contiguous copy: `pred` may be a graph-owned buffer that the next block overwrites
-                mine = out[:, done:done + take].contiguous()
-                allb = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
-                work = dist.all_gather_into_tensor(allb, mine, group=group, async_op=True)
-                # the gathered block is moved into the rank-major result on a side stream as soon as the collective is done,
-                # i.e. under the next block's kernels; only the last block's exchange and copy stay exposed
-                if full is None:
-                    n = out.shape[0]
-                    full = torch.empty((world * n, num_future) + tuple(out.shape[2:]), dtype=out.dtype, device=out.device)
-                    asm_stream = self.__dict__.setdefault("_asm_stream", torch.cuda.Stream(device=dev))
-                    asm_stream.wait_stream(torch.cuda.current_stream())      # `full` may reuse memory of earlier work on this stream
-                    full.record_stream(asm_stream)
-                with torch.cuda.stream(asm_stream):
-                    work.wait()                              # the side stream waits for the collective
-                    full.view(world, out.shape[0], num_future, *out.shape[2:])[:, :, done:done + take].copy_(allb)
-                allb.record_stream(asm_stream)
-                pending.append((work, allb, mine))
+            if gatherer is not None:
+                # a private contiguous payload: `pred` may be a graph-owned buffer that the next block overwrites
+                if gather_dtype == torch.uint8:
+                    mine = out_u8[:, :take].contiguous() if take < out_u8.shape[1] else out_u8
+                else:
+                    mine = out[:, done:done + take].to(gather_dtype).contiguous() if gather_dtype != out.dtype else out[:, done:done + take].contiguous()
+                gatherer.submit(mine, done)
             done += take
             blk += 1
             if done >= num_future:
@@ -277,9 +326,10 @@ class NPVPInference(nn.Module):
             if wait_output:
                 torch.cuda.current_stream().wait_stream(copy_stream)
             out.record_stream(copy_stream)
-        if pending:
-            torch.cuda.current_stream().wait_stream(asm_stream)
-            return full
+        if gatherer is not None:
+            full = gatherer.result()
+            if full is not None:
+                return full
         return out
 
     # -- pixel space (utils/dataset.py:860-886, utils/train_summary.py:244-245) ----------------------
@@ -289,6 +339,7 @@ class NPVPInference(nn.Module):
             return (0.0,) * c, (1.0,) * c
         return RENORM[self.cfg.Dataset.name]
 
+    @_on_model_device
     def to_pixels(self, frames, uint8: bool = False):
         """Model output (..., C, H, W) -> [0,1] pixel space: VidReNormalize + clamp (utils/dataset.py:860-886,
         utils/train_summary.py:243-245; Sigmoid models: clamp only); ``uint8=True`` returns what the reference writes to
@@ -301,6 +352,7 @@ class NPVPInference(nn.Module):
         _lib.ops().frames_to_pixels(x, mean, std, out_u8=out if uint8 else None, out_f32=None if uint8 else out)
         return out
 
+    @_on_model_device
     def from_pixels(self, frames_u8):
         """uint8 frames (..., C, H, W) -> model-space fp32 input: VidToTensor + VidNormalize (utils/dataset.py:835-858)."""
         if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8:
@@ -316,24 +368,36 @@ class NPVPInference(nn.Module):
 
 
 class _GraphedPredict:
-    """One captured forward: static input / noise buffers, graph-owned output."""
+    """One captured forward: static input / noise buffers, graph-owned output, and graph-owned positional codes
+    (``slots``): the NRMLP tables the captured kernels read are recomputed in place - eagerly, before the replay - when the
+    predictor's coordinates have changed since the last call, so the graph does not depend on the timestamps."""
 
     def __init__(self, model: NPVPInference, example: torch.Tensor):
+        self.model = model
         self.stochastic = bool(model.predictor.stochastic)
         self.x = torch.empty_like(example, dtype=torch.float32).contiguous()
         self.x.copy_(example)
         n = example.shape[0]
         self.eps = torch.zeros((n, 512, 8, 8), device=example.device) if self.stochastic else None
+        self.slots = ({}, {})
+        self.eng = model.predictor._engine()
         side = torch.cuda.Stream(device=example.device)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                       # warm-up: builds engines, workspaces, kernel attributes
+        with torch.cuda.stream(side):                       # warm-up: builds engines, workspaces, kernel attributes, positional codes
             for _ in range(2):
-                model._predict_eager(self.x, self.eps)
+                self._run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = model._predict_eager(self.x, self.eps)
+            self.out = self._run()
+
+    def _run(self):
+        self.eng._graph_slots = self.slots
+        try:
+            return self.model._predict_eager(self.x, self.eps)
+        finally:
+            self.eng._graph_slots = None
 
     def __call__(self, x, eps):
         self.x.copy_(x)
@@ -342,6 +406,12 @@ class _GraphedPredict:
                 self.eps.normal_()                          # sampled outside the graph, like torch.randn in the reference
             else:
                 self.eps.copy_(eps)
+        p = self.model.predictor
+        self.eng._graph_slots = self.slots
+        try:                                                # no-op unless the coordinates changed: then 24 small eager launches
+            self.eng._positional_pair(p.observed_coor, p.predict_coor)
+        finally:
+            self.eng._graph_slots = None
         self.graph.replay()
         return self.out
 

@@ -135,17 +135,19 @@ class Predictor(_EngineModule):
         with the posterior sample, :316-318) is not supported: ``_guard`` rejects ``training=True``."""
         self._guard(observed_features)
         self._coords_ready()
-        if predict_features_gt is not None and self.stochastic:
-            self._guard(predict_features_gt)
-            return self._engine().run(observed_features, predict_gt=predict_features_gt)
-        return self._engine().run(observed_features)
+        with self._on_device(observed_features):
+            if predict_features_gt is not None and self.stochastic:
+                self._guard(predict_features_gt)
+                return self._engine().run(observed_features, predict_gt=predict_features_gt)
+            return self._engine().run(observed_features)
 
     def forward_tokens(self, observed_tokens, out16=None, n_samples=1):
         """Engine-internal: channels-last (N,To,H,W,C) in -> channels-last (N*n_samples,Tp,H,W,C) out (fp32, or the 16-bit
         workspace view of dtype ``out16`` that the frame decoder consumes directly)."""
         self._guard(observed_tokens)
         self._coords_ready()
-        return self._engine().run(observed_tokens, channels_last=True, out16=out16, n_samples=n_samples)
+        with self._on_device(observed_tokens):
+            return self._engine().run(observed_tokens, channels_last=True, out16=out16, n_samples=n_samples)
 
     def forward_samples(self, observed_features, n_samples: int):
         """NPVP-S: ``n_samples`` stochastic futures per clip, (N, To, C, H, W) -> (N, n_samples, Tp, C, H, W).  Equivalent to
@@ -153,16 +155,19 @@ class Predictor(_EngineModule):
         clip-major), but the EVT_Former and the prior run once."""
         self._guard(observed_features)
         self._coords_ready()
-        out = self._engine().run(observed_features, n_samples=n_samples)
+        with self._on_device(observed_features):
+            out = self._engine().run(observed_features, n_samples=n_samples)
         return out.view(observed_features.shape[0], n_samples, *out.shape[1:])
 
     def prefetch_positional(self):
-        """Start the NRMLP positional code (input independent: 8 small fp32 GEMMs on a handful of SMs) on a side stream.
-        Callers that run other work first - the pipeline runs the frame encoder - overlap it; the next forward joins."""
+        """Make sure the NRMLP positional codes of the current coordinates exist (they are cached per coordinate tensor and
+        recomputed only when ``reset_pos_coor`` / a batch-process function installs new coordinates)."""
         self._coords_ready()
-        self._engine().positional_async(self.observed_coor, self.predict_coor)
+        with self._on_device(self.nrmlp.B):
+            self._engine()._positional_pair(self.observed_coor, self.predict_coor)
 
     def evt_coding_forward(self, x, pos_beta, pos_gamma):
         """EVT_Former + temporal mean (Predictor.py:337-350).  x (N,T,C,H,W); pos_beta/gamma (T*H*W, C)."""
         self._guard(x)
-        return self._engine().evt_coding(x, pos_beta, pos_gamma)
+        with self._on_device(x):
+            return self._engine().evt_coding(x, pos_beta, pos_gamma)

@@ -15,6 +15,11 @@ under ``tests/golden/*.npz``.  ``tests/test_oracle_golden.py`` replays them.
 Every function works on a flat ``state_dict``-style mapping ``sd`` (name -> tensor)
 using the reference's own key names, so it can consume either the reference's
 checkpoints or ``npvp_b200`` module state_dicts.  Citations are into /root/reference.
+
+The functions are device agnostic (plain torch ops on whatever device the state_dict and the
+inputs live on): on CPU they are the parity oracle, and ``bench.py``'s ``gpu_eager_baseline``
+leg runs the same code on ``cuda`` to time what the reference's eager PyTorch path costs on a B200
+(the same ATen / cuDNN / cuBLAS kernels the reference modules dispatch to).
 """
 from __future__ import annotations
 
@@ -184,7 +189,7 @@ def enc_block(sd: SD, p: str, x: Tensor, beta: Tensor, gamma: Tensor) -> Tensor:
     x1 = _layer_norm_c(x, sd[p + "norm3.weight"], sd[p + "norm3.bias"])
     temp = pos_fuse(x1, beta, gamma)
     # mask quirk (VidHRFormer.py:100-102): frames 0..T-2 may not attend to the last frame
-    mask = torch.zeros(T, T, dtype=torch.bool)
+    mask = torch.zeros(T, T, dtype=torch.bool, device=x.device)
     mask[0:-1, -1] = True
     x = x + _from_seq(mha(sd, p + "temporal_MHSA.", _to_seq(temp), _to_seq(temp), _to_seq(x1), mask), N, H, W)
     x1 = _layer_norm_c(x, sd[p + "norm4.weight"], sd[p + "norm4.bias"])
@@ -245,7 +250,7 @@ def event_encoder(sd: SD, p: str, x: Tensor, stochastic: bool, eps: Optional[Ten
         return mu
     logvar = F.conv2d(y, sd[p + "logvar_net.weight"], sd[p + "logvar_net.bias"])
     if eps is None:
-        eps = torch.randn(mu.shape)
+        eps = torch.randn(mu.shape, device=mu.device)                     # submodules.py:409
     return mu + torch.exp(0.5 * logvar) * eps, mu, logvar
 
 

@@ -44,6 +44,40 @@ def test_sharded_predict_matches_single_process(n_clips):
     assert all(ret[r] for r in range(world)), dict(ret)
 
 
+def _block_worker(rank, world, port, dst, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from npvp_b200.distributed import BlockGather
+        g = torch.Generator().manual_seed(1)
+        n, nf = 3, 7                                            # clips per rank, frames per clip: blocks of 3 + 3 + 1
+        full = torch.rand((world * n, nf, 2, 4, 4), generator=g)
+        ok = True
+        for dtype in (torch.float32, torch.uint8):
+            ref = (full * 255).to(torch.uint8) if dtype == torch.uint8 else full
+            bg = BlockGather(None, dst, nf)
+            for done in (0, 3, 6):
+                take = min(3, nf - done)
+                bg.submit(ref[rank * n:(rank + 1) * n, done:done + take].contiguous(), done)
+            res = bg.result()
+            if dst is None or rank == dst:
+                ok = ok and res is not None and res.dtype == dtype and torch.equal(res, ref)
+            else:
+                ok = ok and res is None
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dst", [0, 1, None])
+def test_block_gather_assembles_rank_major_batch(dst):
+    """distributed.BlockGather (the per-block exchange of NPVPInference.rollout): gather to one rank or to all, any payload type."""
+    world, port = 2, _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_block_worker, args=(world, port, dst, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world)), dict(ret)
+
+
 def test_shard_bounds_cover_batch():
     for n in (1, 7, 8, 64, 513):
         for w in (1, 2, 4, 8):

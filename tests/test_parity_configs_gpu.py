@@ -1,0 +1,138 @@
+"""GPU: end-to-end parity of every BASELINE.json configuration that bench.py / tools/bench_configs.py publish numbers for,
+against the CPU oracle, under STRESS init (default init hides wrong-layer / wrong-coordinate bugs).
+
+  * the headline workload itself: Cityscapes NPVP-S, N = 8 clips, the full 28-frame 3-block rollout(last_block="query") with the
+    GPU's own predictions fed back as context twice - pixel tolerance on all 28 frames, error growth per block reported;
+  * Cityscapes NPVP-D (config 4), SMMNIST 10 -> 10 (config 1 as worded in BASELINE.json), the one-shot 2 -> 28 variant
+    (max_T = 30, not a shipped YAML).
+Tolerances (BASELINE.json north_star): max |pixel error| <= 1e-2 on [0,1] frames, |delta PSNR| <= 0.1 dB.
+"""
+import pytest
+import torch
+
+from oracle import npvp_oracle as O
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+def _ref_pixels(model, frames_cpu):
+    from oracle import post_oracle as P
+    mean, std = model._renorm_constants()
+    return P.renormalize_clamp(frames_cpu, mean, std)
+
+
+def _build(preset_name, seed_base=1):
+    from npvp_b200.pipeline import build_from_config
+    from util_init import reset_shared_norm, stress_init_
+    import npvp_b200
+    reset_shared_norm(npvp_b200.Predictor)
+    model = build_from_config(preset_name, device="cpu", seed=0)
+    for i, m in enumerate((model.VPTR_Enc, model.VPTR_Dec, model.predictor)):
+        stress_init_(m, seed_base + i)
+    # Random transposed-conv weights shrink the signal by ~sqrt(6) per layer while the stress-init BatchNorm shifts add an input
+    # independent pattern: left alone, the decoded frames barely depend on the predictor's output (measured: mean |change| 2e-4
+    # for another context, 4e-4 for other latent noise, against a frame std of 0.29), and an end-to-end pixel test would compare
+    # mostly that pattern.  A gain of 2 on the decoder's ConvTranspose weights raises the sensitivity ~20x (printed by the
+    # headline test) without saturating the Tanh head.
+    for k, v in model.VPTR_Dec.state_dict().items():
+        if v.dim() == 4 and v.shape[-1] == 3:
+            v.mul_(2.0)
+    cfg = model.cfg
+    ocfg = dict(n_downsampling=cfg.AE.n_downsampling, num_res_blocks=cfg.AE.num_res_blocks, out_layer=cfg.AE.out_layer,
+                stochastic=cfg.Predictor.stochastic)
+    return model, cfg, ocfg
+
+
+def _check(model, out, ref, what):
+    """Pixel-space tolerance of the north_star, plus two guards that keep the comparison informative: the UNCLAMPED pixel error
+    (model-space error x the dataset std of VidReNormalize: what the clamp to [0,1] could hide) obeys the same bound, and the
+    reference frames are not mostly saturated (a stress init whose Tanh head drives every pixel to 0 or 1 compares nothing)."""
+    from util_init import seeded_rand
+    px, px_ref = model.to_pixels(out).cpu(), _ref_pixels(model, ref)
+    err = float((px - px_ref).abs().max())
+    gt = seeded_rand(tuple(px_ref.shape), 99)
+    dpsnr = abs(float(O.psnr(px, gt)) - float(O.psnr(px_ref, gt)))
+    _, std = model._renorm_constants()
+    raw = float((out.cpu() - ref).abs().max()) * max(std)
+    sat = float(((px_ref == 0) | (px_ref == 1)).float().mean())
+    print(f"{what}: max pixel err {err:.3e} (unclamped {raw:.3e})  dPSNR {dpsnr:.4f} dB  saturated reference pixels {100 * sat:.0f}%  pixel std {float(px_ref.std()):.3f}")
+    assert sat < 0.9, (what, "degenerate fixture: reference frames saturated", sat)
+    assert err <= 1e-2 and raw <= 1e-2 and dpsnr <= 0.1, (what, err, raw, dpsnr)
+    return px, px_ref
+
+
+def test_headline_workload_full_rollout_stress_init():
+    """bench.py's workload: Cityscapes 128x128 NPVP-S, 2 -> 28 by rollout(last_block='query'), 8 clips, stress init, injected noise."""
+    from util_init import seeded_rand, seeded_randn
+    N, NF = 8, 28
+    model, cfg, ocfg = _build("Cityscapes_VFP_NPVP-S", 1)
+    x = seeded_rand((N, 2, 3, 128, 128), 1234) * 2 - 1
+    eps = [seeded_randn((N, 512, 8, 8), 4321 + i) for i in range(3)]
+    esd, psd, dsd = model.VPTR_Enc.state_dict(), model.predictor.state_dict(), model.VPTR_Dec.state_dict()
+    hl = torch.linspace(0, 7, 8)
+    short = O.coor_generator(model.tp_list[:8], hl, hl, cfg.Predictor.max_T, 8, 8)
+    ctx, outs = x, []
+    for b in range(3):                                             # the oracle driven exactly like rollout(last_block="query")
+        take = min(10, NF - 10 * b)
+        pred = O.npvp_predict_frames(esd, psd, dsd, ctx, ocfg, psd["observed_coor"], psd["predict_coor"] if take == 10 else short, eps[b])
+        outs.append(pred[:, :take])
+        ctx = pred[:, 8:10]
+    ref = torch.cat(outs, 1)
+    # how informative the fixture is: change of the reference frames under other latent noise / another context (first block, 2 clips)
+    alt_eps = O.npvp_predict_frames(esd, psd, dsd, x[:2], ocfg, psd["observed_coor"], psd["predict_coor"], seeded_randn((2, 512, 8, 8), 5))
+    alt_ctx = O.npvp_predict_frames(esd, psd, dsd, x[2:4], ocfg, psd["observed_coor"], psd["predict_coor"], eps[0][:2])
+    sens_eps, sens_ctx = float((alt_eps - ref[:2, :10]).abs().mean()), float((alt_ctx - ref[:2, :10]).abs().mean())
+    print(f"fixture sensitivity (model space, mean |change|): other noise {sens_eps:.3e}, other context {sens_ctx:.3e}, frame std {float(ref.std()):.3f}")
+    model = model.cuda()
+    for graphs in (False, True):
+        model.use_cuda_graphs(graphs)
+        out = model.rollout(x.cuda(), NF, [e.cuda() for e in eps], last_block="query")
+        assert out.shape == (N, NF, 3, 128, 128)
+        px, px_ref = _check(model, out, ref, f"Cityscapes NPVP-S rollout 2->28, N={N}, graphs={graphs}")
+        growth = [float((out[:, a:b].cpu() - ref[:, a:b]).abs().max()) for a, b in ((0, 10), (10, 20), (20, 28))]
+        print("  max model-space err per autoregressive block (error growth under feedback): " + ", ".join(f"{g:.3e}" for g in growth))
+        mean_err = float((out.cpu() - ref).abs().mean())
+        print(f"  mean model-space err {mean_err:.3e} = {100 * mean_err / sens_eps:.1f}% of the change caused by other latent noise")
+        assert mean_err < 0.1 * min(sens_eps, sens_ctx), "the numerical error must be small against what the inputs change"
+    # batch invariance at the bench's scale: clip 3 alone == clip 3 inside the batch, bit for bit
+    solo = model.rollout(x[3:4].cuda(), NF, [e[3:4].cuda() for e in eps], last_block="query")
+    assert torch.equal(solo, out[3:4])
+
+
+@pytest.mark.parametrize("preset_name,N", [("Cityscapes_VFP_NPVP-D", 8), ("SMMNIST_VFP_NPVP-D_10to10", 8),
+                                           ("Cityscapes_VFP_NPVP-S_oneshot28", 2), ("BAIR_VFP_NPVP-S_oneshot28", 2)])
+def test_config_forward_stress_init(preset_name, N):
+    from util_init import seeded_rand, seeded_randn
+    model, cfg, ocfg = _build(preset_name, 1)
+    To, Tp = cfg.Dataset.num_past_frames, cfg.Dataset.num_future_frames
+    hw, ch = cfg.Dataset.img_size, cfg.Dataset.img_channels
+    x = seeded_rand((N, To, ch, hw, hw), 77)
+    if cfg.AE.out_layer == "Tanh":
+        x = x * 2 - 1
+    stoch = bool(cfg.Predictor.stochastic)
+    eps = seeded_randn((N, 512, 8, 8), 78) if stoch else None
+    psd = model.predictor.state_dict()
+    ref = O.npvp_predict_frames(model.VPTR_Enc.state_dict(), psd, model.VPTR_Dec.state_dict(), x, ocfg,
+                                psd["observed_coor"], psd["predict_coor"], eps)
+    model = model.cuda()
+    out = model.predict(x.cuda(), eps.cuda() if stoch else None)
+    assert out.shape == (N, Tp, ch, hw, hw)
+    _check(model, out, ref, f"{preset_name} {To}->{Tp}, N={N}")
+
+
+def test_cityscapes_deterministic_rollout():
+    """BASELINE config 4 as benchmarked: NPVP-D, 2 -> 28 block-autoregressive (truncate mode), 2 clips vs the oracle."""
+    from util_init import seeded_rand
+    model, cfg, ocfg = _build("Cityscapes_VFP_NPVP-D", 1)
+    x = seeded_rand((2, 2, 3, 128, 128), 5) * 2 - 1
+    esd, psd, dsd = model.VPTR_Enc.state_dict(), model.predictor.state_dict(), model.VPTR_Dec.state_dict()
+    ctx, outs = x, []
+    for b in range(3):
+        pred = O.npvp_predict_frames(esd, psd, dsd, ctx, ocfg, psd["observed_coor"], psd["predict_coor"], None)
+        outs.append(pred)
+        ctx = pred[:, 8:10]
+    ref = torch.cat(outs, 1)[:, :28]
+    model = model.cuda()
+    out = model.rollout(x.cuda(), 28)
+    _check(model, out, ref, "Cityscapes NPVP-D rollout 2->28 (truncate)")

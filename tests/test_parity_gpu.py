@@ -1,7 +1,8 @@
 """GPU: the shipped modules (CUDA path through the C-ABI) against the CPU oracle and the reference goldens.
 
 Tolerances (BASELINE.json north_star): max |pixel error| <= 1e-2 on [0,1] frames and |delta PSNR| <= 0.1 dB for the
-end-to-end path; feature-space blocks are held to 3e-2 of the tensor's max (bf16 operands, fp32 accumulate)."""
+end-to-end path; feature-space blocks are held to 2e-2 of the tensor's max (the bound for the 16-bit-operand
+mode; bf16 / half operands, fp32 accumulate)."""
 import numpy as np
 import pytest
 import torch
@@ -12,6 +13,7 @@ from oracle import npvp_oracle as O
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
+FEAT_TOL = 2e-2
 
 
 
@@ -37,9 +39,9 @@ def test_predictor_matches_oracle_and_golden(name):
     assert out.shape == ref.shape
     r = _rel(out, ref)
     print(f"{name}: rel err vs oracle {r:.3e}, abs {float((out - ref).abs().max()):.3e}")
-    assert r < 3e-2
+    assert r < FEAT_TOL
     g = torch.from_numpy(z["sample"])
-    assert float((torch.from_numpy(golden_sample(out, z)) - g).abs().max()) < 3e-2 * float(z["absmax"])
+    assert float((torch.from_numpy(golden_sample(out, z)) - g).abs().max()) < FEAT_TOL * float(z["absmax"])
 
 
 @pytest.mark.parametrize("name", PRED_SPADE_CASES)
@@ -53,8 +55,8 @@ def test_predictor_spade_matches_oracle_and_golden(name):
     out = mod(x.cuda()).cpu()
     r = _rel(out, ref)
     print(f"{name}: rel err vs oracle {r:.3e}")
-    assert r < 3e-2
-    assert float((torch.from_numpy(golden_sample(out, z)) - torch.from_numpy(z["sample"])).abs().max()) < 3e-2 * float(z["absmax"])
+    assert r < FEAT_TOL
+    assert float((torch.from_numpy(golden_sample(out, z)) - torch.from_numpy(z["sample"])).abs().max()) < FEAT_TOL * float(z["absmax"])
 
 
 @pytest.mark.parametrize("name", PRED_GT_CASES)
@@ -73,9 +75,9 @@ def test_predictor_posterior_branch(name):
         assert a.shape == b.shape, key
         r = _rel(a, b)
         print(f"{name}.{key}: rel err vs oracle {r:.3e}")
-        assert r < 3e-2, (key, r)
+        assert r < FEAT_TOL, (key, r)
     for key, ours, gold in golden_latents(outs, z):
-        assert float(np.abs(ours - gold).max()) < 3e-2 * float(np.abs(gold).max()), key
+        assert float(np.abs(ours - gold).max()) < FEAT_TOL * float(np.abs(gold).max()), key
     assert torch.equal(mod(x.cuda()).cpu(), outs[0])
     mod.injected_eps = None                          # sampled noise: shapes only, and the RNG advances by two draws like the reference
     torch.manual_seed(5)
@@ -94,7 +96,7 @@ def test_autoencoder_matches_oracle_and_golden(name):
     feats = enc.cuda()(x.cuda()).cpu()
     frames = dec.cuda()(f_in.cuda()).cpu()
     print(f"{name}: enc rel {_rel(feats, feats_ref):.3e}  dec abs {float((frames - frames_ref).abs().max()):.3e}")
-    assert _rel(feats, feats_ref) < 3e-2
+    assert _rel(feats, feats_ref) < FEAT_TOL
     assert float((frames - frames_ref).abs().max()) < 1e-2
     assert float(np.abs(golden_sample(frames, zd) - zd["sample"]).max()) < 1e-2
 
@@ -217,7 +219,7 @@ def test_per_clip_timestamps_mixed_batch():
     for i in range(3):
         r = _rel(out[i:i + 1].cpu(), refs[i])
         print(f"mixed batch clip {i}: rel err vs oracle {r:.3e}")
-        assert r < 3e-2
+        assert r < FEAT_TOL
         mod.reset_pos_coor(to[i], tp[i])
         mod.injected_eps = eps[i:i + 1].cuda()
         assert torch.equal(mod(x[i:i + 1].cuda()), out[i:i + 1])
@@ -313,3 +315,57 @@ def test_bair_multiple_stochastic_samples():
     rep = model.predict(x2.repeat_interleave(4, dim=0), e2)
     assert torch.equal(smp2.reshape(rep.shape), rep)
     assert torch.equal(smp2[0], smp[0, :4])
+
+
+def test_cuda_graph_cache_follows_coordinates_and_is_bounded():
+    """use_cuda_graphs: the captured forward does not depend on the timestamps (positional codes live in graph-owned buffers
+    that are recomputed in place when reset_pos_coor / rand_context_batch_process install new coordinates), and the cache
+    holds at most MAX_GRAPHS captured forwards (it used to be keyed by coordinate pointers and never evicted)."""
+    from npvp_b200.pipeline import build_from_config
+    from util_init import seeded_rand, stress_init_
+    model = build_from_config("KTH_Unified_NPVP-S", device="cpu", seed=0)
+    stress_init_(model.predictor, 3)
+    model = model.cuda()
+    N = 2
+    clip = (seeded_rand((N, 20, 1, 64, 64), 77) * 2 - 1).cuda()
+    eps = torch.randn(N, 512, 8, 8, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    tasks = [KTH_TASKS["VFP"], KTH_TASKS["VPE"], KTH_TASKS["VRC"]]
+    eager = []
+    for to, tp in tasks:
+        model.predictor.reset_pos_coor(torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32))
+        eager.append(model.predict(clip[:, to], eps).clone())
+    model.use_cuda_graphs(True)
+    for rep in range(2):
+        for (to, tp), ref in zip(tasks, eager):
+            model.predictor.reset_pos_coor(torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32))
+            assert torch.equal(model.predict(clip[:, to], eps), ref)
+    assert len(model._graphs) == 1, "three 10 -> 10 tasks must share one captured forward"
+    # the reference's random-context batch function (Predictor.py:241-251) re-targets the same graph
+    idx_o, idx_p = torch.tensor(tasks[2][0]), torch.tensor(tasks[2][1])
+    o, _ = model.batch_process_fn((clip[:, idx_o], clip[:, idx_p], idx_o, idx_p))
+    assert torch.equal(model.predict(o, eps), eager[2]) and len(model._graphs) == 1
+    for n in range(1, model.MAX_GRAPHS + 3):                          # more batch shapes than the cache holds
+        model.predict(clip[:1, idx_o].expand(n, -1, -1, -1, -1).contiguous(), eps[:1].expand(n, -1, -1, -1).contiguous())
+    assert len(model._graphs) == model.MAX_GRAPHS
+    assert torch.equal(model.predict(o, eps), eager[2])               # evicted and captured again: same result
+
+
+def test_rollout_follows_current_targeting_and_rejects_interpolation():
+    """rollout takes the number of context / target frames from the predictor's CURRENT coordinates, and refuses
+    tasks where feeding predictions back has no meaning."""
+    from npvp_b200.pipeline import build_from_config
+    from util_init import seeded_rand
+    model = build_from_config("KTH_Unified_NPVP-S", device="cuda", seed=0)
+    clip = (seeded_rand((1, 20, 1, 64, 64), 7) * 2 - 1).cuda()
+    eps = [torch.zeros(1, 512, 8, 8, device="cuda")] * 3
+    model.predictor.reset_pos_coor(torch.arange(0., 4.), torch.arange(4., 10.))              # 4 -> 6 on a model built for 10 -> 10
+    out = model.rollout(clip[:, :4], 14, eps)
+    assert out.shape == (1, 14, 1, 64, 64)
+    assert torch.equal(out[:, :6], model.predict(clip[:, :4], eps[0]))
+    assert torch.equal(out[:, 6:12], model.predict(out[:, 2:6], eps[1]))
+    with pytest.raises(ValueError, match="context frames"):
+        model.rollout(clip[:, :10], 14, eps)
+    to, tp = KTH_TASKS["VFI"]
+    model.predictor.reset_pos_coor(torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32))
+    with pytest.raises(ValueError, match="future prediction"):
+        model.rollout(clip[:, to], 14, eps)

@@ -39,3 +39,57 @@ def test_vfi_and_normal_batch_process():
     cfg.Predictor.VFI = False
     m2 = NPVPInference(cfg)
     assert m2.batch_process_fn((past, fut)) == (past, fut)
+
+
+class _Opaque:
+    """Stands in for the arbitrary objects (hyper-parameter namespaces, callback state) Lightning pickles into a .ckpt."""
+
+    def __init__(self, v):
+        self.v = v
+
+
+def test_load_lightning_ckpt_round_trip(tmp_path):
+    """A synthetic Lightning checkpoint {'state_dict': {VPTR_Enc.*, VPTR_Dec.*, predictor.*, <other modules>}, 'callbacks': ...,
+    'optimizer_states': ...} (Predictor.py:18-19,43) loads with strict=True: extra top-level modules are dropped, the
+    shared norm's two keys land in one tensor, the coordinate buffers of a checkpoint saved after reset_pos_coor (other
+    shapes) are ignored, and a file that pickles arbitrary objects needs trust_pickle=True."""
+    import pytest
+    from util_init import stress_init_
+    src = NPVPInference(preset("KITTI_VFP_NPVP-S"))
+    for i, mod in enumerate((src.VPTR_Enc, src.VPTR_Dec, src.predictor)):
+        stress_init_(mod, 50 + i)
+    src.predictor.reset_pos_coor(torch.tensor([0., 1.]), torch.tensor([2., 3., 4.5]))       # buffers saved with other shapes
+    sd = {k: v.clone() for k, v in src.state_dict().items()}
+    assert any(k.startswith("VPTR_Enc.") for k in sd) and "predictor.EVT_Former.norm.weight" in sd and "predictor.transformer.norm.weight" in sd
+    sd["loss_fn.weight"] = torch.ones(3)                                                   # another module of the LightningModule
+    sd["discriminator.model.0.weight"] = torch.zeros(4, 3, 4, 4)
+    plain = {"epoch": 7, "global_step": 1234, "state_dict": sd, "optimizer_states": [{"state": {}, "param_groups": [{"lr": 1e-4}]}],
+             "lr_schedulers": [], "callbacks": {"ModelCheckpoint": {"best_model_score": torch.tensor(0.5)}}}
+    path = tmp_path / "plain.ckpt"
+    torch.save(plain, path)
+    dst = NPVPInference(preset("KITTI_VFP_NPVP-S"))
+    shape_before = tuple(dst.predictor.predict_coor.shape)
+    res = dst.load_lightning_ckpt(str(path))
+    assert not res.missing_keys and not res.unexpected_keys
+    ref = src.state_dict()
+    for k, v in dst.state_dict().items():
+        if k.endswith(("observed_coor", "predict_coor")):
+            continue
+        assert torch.equal(v, ref[k]), k
+    assert tuple(dst.predictor.predict_coor.shape) == shape_before                           # derived buffers follow the module, not the file
+    assert dst.predictor.EVT_Former.norm.weight.data_ptr() == dst.predictor.transformer.norm.weight.data_ptr()
+    # a checkpoint with arbitrary pickled objects: refused by default, loaded with trust_pickle=True
+    pickled = dict(plain, hyper_parameters=_Opaque(3))
+    path2 = tmp_path / "pickled.ckpt"
+    torch.save(pickled, path2)
+    dst2 = NPVPInference(preset("KITTI_VFP_NPVP-S"))
+    with pytest.raises(RuntimeError, match="trust_pickle"):
+        dst2.load_lightning_ckpt(str(path2))
+    dst2.load_lightning_ckpt(str(path2), trust_pickle=True)
+    assert torch.equal(dst2.VPTR_Dec.state_dict()["model.0.weight"], ref["VPTR_Dec.model.0.weight"])
+    # a bare module state_dict (no 'state_dict' wrapper) also loads; a file without the three prefixes is an error
+    torch.save(src.state_dict(), tmp_path / "bare.ckpt")
+    NPVPInference(preset("KITTI_VFP_NPVP-S")).load_lightning_ckpt(str(tmp_path / "bare.ckpt"))
+    torch.save({"state_dict": {"foo.bar": torch.zeros(1)}}, tmp_path / "empty.ckpt")
+    with pytest.raises(KeyError):
+        NPVPInference(preset("KITTI_VFP_NPVP-S")).load_lightning_ckpt(str(tmp_path / "empty.ckpt"))
