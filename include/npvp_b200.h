@@ -246,6 +246,15 @@ int npvp_psnr(const float* x, const float* y, float* out, int64_t n_images, int6
  * (C,H,W).  window11: HOST array, the normalised 1-D Gaussian (the reference's 2-D window is its outer product). */
 int npvp_ssim(const float* x, const float* y, const float* window11, float* out, int64_t n_images, int C, int H, int W,
               void* stream);
+/* Best-of-K evaluation of stochastic samples (NPVP-S; utils/metrics.py:12-109 applied per sample): per-frame PSNR
+ * (window11 == NULL) or SSIM (window11 = host pointer to the 11 normalised Gaussian taps) of samples fp32
+ * [n_clips][K][T][C,H,W] against gt fp32 [n_clips][T][C,H,W] (read in place, not replicated) -> scores fp32 [n_clips][K][T]. */
+int npvp_sample_scores(const float* samples, const float* gt, const float* window11, float* scores, int64_t n_clips, int K, int T,
+                       int C, int H, int W, float data_range, void* stream);
+/* mean_scores[n][k] = mean_t scores[n][k][t]; best_idx[n] = argmax_k (ties: lowest k); best (optional, NULL to skip)
+ * receives the winner's frames: clip_elems = T*C*H*W fp32 values per sample (multiple of 4, 16-byte aligned buffers). */
+int npvp_best_of_k(const float* scores, const float* samples, int64_t n_clips, int K, int T, int64_t clip_elems, int32_t* best_idx,
+                   float* mean_scores, float* best, void* stream);
 
 #ifdef __cplusplus
 }

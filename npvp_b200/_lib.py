@@ -51,6 +51,8 @@ SIGNATURES = {
     "npvp_pixels_to_frames": [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _vp],
     "npvp_psnr": [_vp, _vp, _vp, _i64, _i64, _f32, _vp],
     "npvp_ssim": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp],
+    "npvp_sample_scores": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
+    "npvp_best_of_k": [_vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp, _vp, _vp],
     "npvp_ffn_dwconv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_ffn_norm2": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "npvp_ffn_mid16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
@@ -328,6 +330,25 @@ class Ops:
         n, Cc, H, W = x.shape
         assert x.shape == y.shape and out.shape == (n,) and len(window11) == 11
         self._call("npvp_ssim", x.data_ptr(), y.data_ptr(), self._host_f32(window11), out.data_ptr(), n, Cc, H, W, self._stream())
+
+    def sample_scores(self, samples, gt, scores, window11=None, data_range=1.0):
+        """samples fp32 (N, K, T, C, H, W) vs gt fp32 (N, T, C, H, W) -> scores (N, K, T): PSNR, or SSIM when ``window11`` is given."""
+        _chk(samples, torch.float32, "samples"); _chk(gt, torch.float32, "gt"); _chk(scores, torch.float32, "scores")
+        n, K, T, Cc, H, W = samples.shape
+        assert tuple(gt.shape) == (n, T, Cc, H, W) and tuple(scores.shape) == (n, K, T) and (window11 is None or len(window11) == 11)
+        self._call("npvp_sample_scores", samples.data_ptr(), gt.data_ptr(), None if window11 is None else self._host_f32(window11),
+                   scores.data_ptr(), n, K, T, Cc, H, W, float(data_range), self._stream())
+
+    def best_of_k(self, scores, samples, best_idx, mean_scores, best=None):
+        """scores (N, K, T) -> mean_scores (N, K), best_idx int32 (N,), and (optional) the winner's frames of samples (N, K, ...)."""
+        _chk(scores, torch.float32, "scores"); _chk(mean_scores, torch.float32, "mean_scores"); _chk(best_idx, torch.int32, "best_idx")
+        _chk(samples, torch.float32, "samples"); _chk(best, torch.float32, "best")
+        n, K, T = scores.shape
+        clip_elems = 0 if samples is None else samples.numel() // (n * K)
+        assert tuple(mean_scores.shape) == (n, K) and tuple(best_idx.shape) == (n,)
+        assert best is None or (samples is not None and best.numel() == n * clip_elems)
+        self._call("npvp_best_of_k", scores.data_ptr(), _ptr(samples), n, K, T, clip_elems, best_idx.data_ptr(), mean_scores.data_ptr(),
+                   _ptr(best), self._stream())
 
     def ffn_stats_finalize(self, partial, stats, elems_per_frame):
         _chk(partial, torch.float32, "partial"); _chk(stats, torch.float32, "stats")

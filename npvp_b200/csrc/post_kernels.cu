@@ -87,10 +87,12 @@ extern "C" int npvp_pixels_to_frames(const void* in_u8, const float* mean, const
 // PSNR per image: -10 log10(mean((x/r - y/r)^2) + 1e-8); one block per image, fp32 per-thread partials, fp64 combine
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-psnr_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, int64_t elems, float data_range) {
+psnr_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, int64_t elems, float data_range, int K, int T) {
   __shared__ double red[8];
+  // K > 0: x holds K samples per clip, [clip][sample][t], scored against ONE ground truth [clip][t] (best-of-K evaluation)
+  const size_t yimg = K > 0 ? (size_t)(blockIdx.x / (unsigned)(K * T)) * T + blockIdx.x % (unsigned)T : (size_t)blockIdx.x;
   const float* xi = x + (size_t)blockIdx.x * elems;
-  const float* yi = y + (size_t)blockIdx.x * elems;
+  const float* yi = y + yimg * elems;
   double acc = 0.0;
   for (int64_t i0 = 0; i0 < elems; i0 += 256 * 64) {           // fp32 within a 64-element run per thread, fp64 across runs
     float s = 0.f;
@@ -115,7 +117,7 @@ psnr_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __r
 extern "C" int npvp_psnr(const float* x, const float* y, float* out, int64_t n_images, int64_t elems, float data_range, void* stream) {
   NPVP_REQUIRE(x && y && out && n_images > 0 && elems > 0 && data_range > 0.f, "npvp_psnr: bad arguments");
   NPVP_REQUIRE(n_images < (1ll << 31), "npvp_psnr: too many images");
-  psnr_kernel<<<(unsigned)n_images, 256, 0, (cudaStream_t)stream>>>(x, y, out, elems, data_range);
+  psnr_kernel<<<(unsigned)n_images, 256, 0, (cudaStream_t)stream>>>(x, y, out, elems, data_range, 0, 1);
   NPVP_LAUNCH_CHECK("psnr_kernel");
   return NPVP_OK;
 }
@@ -131,16 +133,17 @@ constexpr int kSsimW = 11, kSsimR = 5, kSsimT = 32, kSsimP = kSsimT + 2 * kSsimR
 struct SsimWin { float g[kSsimW]; };
 
 __global__ void __launch_bounds__(256)
-ssim_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, SsimWin win, int C, int H, int W) {
+ssim_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, SsimWin win, int C, int H, int W, int K, int T) {
   __shared__ float px[kSsimP][kSsimP + 1], py[kSsimP][kSsimP + 1];
   __shared__ float hb[5][kSsimP][kSsimT + 1];
   __shared__ double red[8];
   const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
   const size_t img = (size_t)blockIdx.x * C * H * W;
+  const size_t yimg = (K > 0 ? (size_t)(blockIdx.x / (unsigned)(K * T)) * T + blockIdx.x % (unsigned)T : (size_t)blockIdx.x) * C * H * W;
   double acc = 0.0;
   for (int c = 0; c < C; ++c) {
     const float* xc = x + img + (size_t)c * H * W;
-    const float* yc = y + img + (size_t)c * H * W;
+    const float* yc = y + yimg + (size_t)c * H * W;
     for (int ty = 0; ty < H; ty += kSsimT)
       for (int tx = 0; tx < W; tx += kSsimT) {
         __syncthreads();                                          // previous tile fully consumed
@@ -199,7 +202,66 @@ extern "C" int npvp_ssim(const float* x, const float* y, const float* window11, 
   NPVP_REQUIRE(n_images < (1ll << 31), "npvp_ssim: too many images");
   SsimWin w;
   for (int k = 0; k < kSsimW; ++k) w.g[k] = window11[k];        // host pointer: the normalised 1-D Gaussian
-  ssim_kernel<<<(unsigned)n_images, 256, 0, (cudaStream_t)stream>>>(x, y, out, w, C, H, W);
+  ssim_kernel<<<(unsigned)n_images, 256, 0, (cudaStream_t)stream>>>(x, y, out, w, C, H, W, 0, 1);
   NPVP_LAUNCH_CHECK("ssim_kernel");
+  return NPVP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Best-of-K evaluation of stochastic samples (NPVP-S, BASELINE config 3: 8 samples per clip): per-frame PSNR or SSIM of
+// every sample [clip][sample][t] against the clip's ground truth [clip][t] (read in place, never replicated), then per
+// clip the sample with the best mean score over time is selected and its frames are copied out.
+// ---------------------------------------------------------------------------------------------
+extern "C" int npvp_sample_scores(const float* samples, const float* gt, const float* window11, float* scores, int64_t n_clips, int K, int T,
+                                  int C, int H, int W, float data_range, void* stream) {
+  NPVP_REQUIRE(samples && gt && scores && n_clips > 0 && K > 0 && T > 0 && C > 0 && H > 0 && W > 0 && data_range > 0.f, "npvp_sample_scores: bad arguments");
+  const int64_t n_images = n_clips * K * T;
+  NPVP_REQUIRE(n_images < (1ll << 31), "npvp_sample_scores: too many images");
+  if (window11) {                                                  // SSIM (host pointer to the normalised 1-D Gaussian)
+    SsimWin w;
+    for (int k = 0; k < kSsimW; ++k) w.g[k] = window11[k];
+    ssim_kernel<<<(unsigned)n_images, 256, 0, (cudaStream_t)stream>>>(samples, gt, scores, w, C, H, W, K, T);
+    NPVP_LAUNCH_CHECK("ssim_kernel<samples>");
+  } else {
+    psnr_kernel<<<(unsigned)n_images, 256, 0, (cudaStream_t)stream>>>(samples, gt, scores, (int64_t)C * H * W, data_range, K, T);
+    NPVP_LAUNCH_CHECK("psnr_kernel<samples>");
+  }
+  return NPVP_OK;
+}
+
+// one block per clip: mean score over time per sample (fp64), argmax (ties: lowest index), copy of the winner's frames
+__global__ void __launch_bounds__(256)
+best_of_k_kernel(const float* __restrict__ scores, const float* __restrict__ samples, int K, int T, int64_t clip_elems, int32_t* __restrict__ best_idx,
+                 float* __restrict__ mean_scores, float* __restrict__ best) {
+  __shared__ int s_best;
+  const int n = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int arg = 0;
+    double top = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double m = 0.0;
+      for (int t = 0; t < T; ++t) m += (double)scores[((size_t)n * K + k) * T + t];
+      m /= (double)T;
+      mean_scores[(size_t)n * K + k] = (float)m;
+      if (k == 0 || m > top) { top = m; arg = k; }
+    }
+    best_idx[n] = arg;
+    s_best = arg;
+  }
+  __syncthreads();
+  if (!best) return;
+  const float4* src = reinterpret_cast<const float4*>(samples + ((size_t)n * K + s_best) * clip_elems);
+  float4* dst = reinterpret_cast<float4*>(best + (size_t)n * clip_elems);
+  for (int64_t i = threadIdx.x; i < clip_elems / 4; i += 256) dst[i] = __ldg(src + i);
+}
+
+extern "C" int npvp_best_of_k(const float* scores, const float* samples, int64_t n_clips, int K, int T, int64_t clip_elems, int32_t* best_idx,
+                              float* mean_scores, float* best, void* stream) {
+  NPVP_REQUIRE(scores && best_idx && mean_scores && n_clips > 0 && K > 0 && T > 0, "npvp_best_of_k: bad arguments");
+  NPVP_REQUIRE(!best || (samples && clip_elems > 0 && clip_elems % 4 == 0 && ((uintptr_t)samples % 16) == 0 && ((uintptr_t)best % 16) == 0),
+               "npvp_best_of_k: samples / best must be 16-byte aligned with clip_elems %% 4 == 0");
+  NPVP_REQUIRE(n_clips < (1ll << 31), "npvp_best_of_k: too many clips");
+  best_of_k_kernel<<<(unsigned)n_clips, 256, 0, (cudaStream_t)stream>>>(scores, samples, K, T, clip_elems, best_idx, mean_scores, best);
+  NPVP_LAUNCH_CHECK("best_of_k_kernel");
   return NPVP_OK;
 }

@@ -439,7 +439,7 @@ class PredictorEngine:
         t = mulv.view(n, 8, 8, 2, C).permute(3, 0, 4, 1, 2).contiguous()
         return t[0], t[1]
 
-    def posterior(self, gt, n, channels_last, beta_p, gamma_p, sample_noise):
+    def posterior(self, gt, n, channels_last, beta_p, gamma_p, sample_noise, eps_p=None, want_z=False):
         """NPVP-S posterior on the ground-truth future features (Predictor.py:311-313): EVT_Former over the Tp target frames with
         the target positional code, temporal mean, ``evt_posterior`` heads -> (mu_p, logvar_p).  z_p itself is only used in
         training mode (:316-318), so no re-parameterisation kernel runs; with ``sample_noise`` one noise tensor is still drawn
@@ -452,12 +452,19 @@ class PredictorEngine:
         mem_p, _ = self.encode(tok, beta_p, gamma_p, n, Tp, tag="encp")
         evt_p = self.ws.f32("evt_p", n * TOK, C)
         _lib.ops().temporal_mean(mem_p, evt_p, n, Tp)
+        if want_z:            # z_p = mu_p + exp(logvar_p / 2) eps_p drives the decoder (Predictor.py:315-318)
+            if eps_p is None:
+                eps_p = torch.randn((n, C, 8, 8), device=self.device)                     # the reference's second draw (submodules.py:409)
+            eps_p = eps_p.detach().to(self.device, torch.float32).contiguous()
+            assert tuple(eps_p.shape) == (n, C, 8, 8), f"posterior noise must be {(n, C, 8, 8)}, got {tuple(eps_p.shape)}"
+            z_p, mulv_p = self.latent(evt_p, n, eps_p, E=post, sfx="_p")
+            return self._mu_logvar_nchw(mulv_p, n) + (z_p,)
         if sample_noise:
             torch.randn((n, C, 8, 8), device=self.device)
         _, mulv_p = self.latent(evt_p, n, None, E=post, sfx="_p")
         return self._mu_logvar_nchw(mulv_p, n)
 
-    def run(self, observed, channels_last=False, out16=None, n_samples=1, predict_gt=None):
+    def run(self, observed, channels_last=False, out16=None, n_samples=1, predict_gt=None, decode_posterior=False):
         """``n_samples`` = K > 1 (NPVP-S): K stochastic futures per clip from ONE pass of the EVT_Former and the prior (only the
         latent and the NAR decoder run per sample); the batch dimension of the result is clip-major (clip 0 sample 0..K-1, ...).
         ``predict_gt`` (NPVP-S, eval): ground-truth future features -> (out, mu_o, logvar_o, mu_p, logvar_p) like the reference
@@ -488,6 +495,14 @@ class PredictorEngine:
             assert tuple(eps.shape) == (n * K, C, 8, 8), f"latent noise must be {(n * K, C, 8, 8)}, got {tuple(eps.shape)}"
         z, mulv = self.latent(evt, n, eps, K)
         mod.last_latent = (z, mulv)
+        post = None
+        if decode_posterior:                  # Predictor.py:315-318 (the reference's training-mode branch, forward only)
+            assert self.stochastic and predict_gt is not None and K == 1, \
+                "please input groundtruth predict features for storchastic model training/val"
+            (_, _), (bp_, gp_) = self._positional_pair(oc, pc)
+            mu_p, logvar_p, z = self.posterior(predict_gt, n, channels_last, bp_, gp_, False,
+                                               eps_p=getattr(mod, "injected_eps_p", None), want_z=True)
+            post = (mu_p, logvar_p)
         if K > 1:            # the decoder sees n*K clips: replicate the (small) encoder memory, clip-major
             rep = lambda t, name, dt: self.ws.get(name, (n * K * To * TOK, C), dt).view(n, K, To * TOK, C).copy_(
                 t.view(n, 1, To * TOK, C).expand(n, K, To * TOK, C)).view(n * K * To * TOK, C)
@@ -501,8 +516,9 @@ class PredictorEngine:
         if predict_gt is not None and self.stochastic:
             assert K == 1, "predict_features_gt and n_samples > 1 cannot be combined"
             mu_o, logvar_o = self._mu_logvar_nchw(mulv, n)
-            mu_p, logvar_p = self.posterior(predict_gt, n, channels_last, beta_p, gamma_p, sample_noise=mod.injected_eps is None)
-            return res, mu_o, logvar_o, mu_p, logvar_p
+            if post is None:
+                post = self.posterior(predict_gt, n, channels_last, beta_p, gamma_p, sample_noise=mod.injected_eps is None)
+            return res, mu_o, logvar_o, post[0], post[1]
         return res
 
     def evt_coding(self, x, pos_beta, pos_gamma):

@@ -51,3 +51,26 @@ class SSIM(torch.nn.Module):
         _lib.ops().ssim(x, y, self.window, out)
         # the reference's mean_flag=True is the mean over every element of the SSIM map = mean of the per-image means
         return out.mean() if mean_flag else out
+
+
+def best_of_k(samples, gt, metric: str = "psnr", data_range=1.0):
+    """Best-of-K selection for stochastic prediction (NPVP-S, BASELINE config 3): ``samples`` (N, K, T, C, H, W) and ``gt``
+    (N, T, C, H, W) are pixel-space fp32 CUDA tensors.  Every sample's frames are scored against the clip's ground truth with
+    the reference's PSNR or SSIM (utils/metrics.py:12-109, per frame like ``pred_ave_metrics`` :111-140), averaged over time,
+    and the best sample of every clip is returned:  (best (N, T, C, H, W), best_idx int32 (N,), mean_scores (N, K),
+    scores (N, K, T)).  Two kernels (score, select); the ground truth is never replicated K times."""
+    if not (isinstance(samples, torch.Tensor) and isinstance(gt, torch.Tensor) and samples.is_cuda and gt.is_cuda):
+        raise NotImplementedError("npvp_b200.metrics.best_of_k: inputs must be CUDA tensors (there is no CPU fallback)")
+    if samples.dim() != 6 or gt.dim() != 5 or tuple(samples.shape[:1] + samples.shape[2:]) != tuple(gt.shape):
+        raise ValueError(f"best_of_k: expected samples (N, K, T, C, H, W) and gt (N, T, C, H, W), got {tuple(samples.shape)} and {tuple(gt.shape)}")
+    if metric not in ("psnr", "ssim"):
+        raise ValueError("best_of_k: metric must be 'psnr' or 'ssim'")
+    x, y = samples.detach().to(torch.float32).contiguous(), gt.detach().to(torch.float32).contiguous()
+    n, K, T = x.shape[:3]
+    scores = torch.empty((n, K, T), dtype=torch.float32, device=x.device)
+    _lib.ops().sample_scores(x, y, scores, gaussian_window_1d(11, 1.5) if metric == "ssim" else None, data_range)
+    best = torch.empty_like(y)
+    idx = torch.empty(n, dtype=torch.int32, device=x.device)
+    mean_scores = torch.empty((n, K), dtype=torch.float32, device=x.device)
+    _lib.ops().best_of_k(scores, x, idx, mean_scores, best)
+    return best, idx, mean_scores, scores

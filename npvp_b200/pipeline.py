@@ -165,6 +165,20 @@ class NPVPInference(nn.Module):
 
     MAX_GRAPHS = 8          # captured forwards kept per model (least recently used first out; each owns a private memory pool)
 
+    @_on_model_device
+    def predict_best_of_k(self, past_frames, future_frames, n_samples: int, metric: str = "psnr", eps: Optional[torch.Tensor] = None):
+        """NPVP-S evaluation protocol for stochastic models (BASELINE config 3): draw ``n_samples`` futures per clip
+        (``predict_samples``: frame encoder, EVT_Former and prior once per clip), score every sample against the ground-truth
+        future frames in pixel space ([0,1], ``to_pixels``) with the reference's PSNR / SSIM (utils/metrics.py:12-109) and keep
+        the best sample of every clip.  Returns (best frames in MODEL space (N, Tp, C, H, W), best_idx (N,), mean_scores (N, K))."""
+        from .metrics import best_of_k
+        smp = self.predict_samples(past_frames, n_samples, eps)
+        if tuple(future_frames.shape) != tuple(smp.shape[:1] + smp.shape[2:]):
+            raise ValueError(f"predict_best_of_k: future_frames must be {tuple(smp.shape[:1] + smp.shape[2:])}, got {tuple(future_frames.shape)}")
+        _, idx, mean_scores, _ = best_of_k(self.to_pixels(smp), self.to_pixels(future_frames.to(smp.device)), metric)
+        best = smp[torch.arange(smp.shape[0], device=smp.device), idx.long()]
+        return best, idx, mean_scores
+
     def use_cuda_graphs(self, enabled: bool = True):
         """Replay ``predict`` as one CUDA graph per (batch shape, number of context / target timestamps, per-clip or shared
         timestamps, weights version): the ~400 kernel launches of a forward are launch-bound at small batch.  The returned

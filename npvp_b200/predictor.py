@@ -67,6 +67,11 @@ class Predictor(_EngineModule):
         # stochastic path reproducible; ``None`` samples torch.randn on the input's device like the reference.
         self.injected_eps = None
         self.last_latent = None
+        # Forward-only form of the reference's training-mode branch (Predictor.py:315-318): with ``posterior_decode = True``
+        # and ground-truth future features, the decoder is queried with the POSTERIOR sample z_p (reconstruction term of the
+        # ELBO) instead of the prior sample.  ``injected_eps_p``: the posterior's noise (the reference's second torch.randn).
+        self.posterior_decode = False
+        self.injected_eps_p = None
         self._coor_clips = 0          # > 0 after reset_pos_coor_per_clip: number of clips the coordinate buffers describe
 
     # -- reference API ------------------------------------------------------------------------------
@@ -131,14 +136,17 @@ class Predictor(_EngineModule):
         """observed_features: (N, To, C, H, W) fp32 CUDA -> predicted features (N, Tp, C, H, W).
         NPVP-S with ``predict_features_gt`` (N, Tp, C, H, W): also runs the posterior on the ground-truth future and returns
         ``(out, mu_o, logvar_o, mu_p, logvar_p)`` like the reference in eval mode (Predictor.py:311-313, 320-327) - the
-        inputs of the KL term (criterion.py:341-354).  NPVP-D ignores it (:328-335).  Training mode (decoder queried
-        with the posterior sample, :316-318) is not supported: ``_guard`` rejects ``training=True``."""
+        inputs of the KL term (criterion.py:341-354).  NPVP-D ignores it (:328-335).  ``training=True`` is rejected by ``_guard``
+        (no backward pass exists here); the forward of the training-mode branch - decoder queried with the posterior sample,
+        :315-318 - is available through the explicit flag ``posterior_decode``."""
         self._guard(observed_features)
         self._coords_ready()
         with self._on_device(observed_features):
+            if self.posterior_decode and self.stochastic:
+                assert predict_features_gt is not None, "please input groundtruth predict features for storchastic model training/val"   # :316
             if predict_features_gt is not None and self.stochastic:
                 self._guard(predict_features_gt)
-                return self._engine().run(observed_features, predict_gt=predict_features_gt)
+                return self._engine().run(observed_features, predict_gt=predict_features_gt, decode_posterior=bool(self.posterior_decode))
             return self._engine().run(observed_features)
 
     def forward_tokens(self, observed_tokens, out16=None, n_samples=1):

@@ -257,11 +257,15 @@ def event_encoder(sd: SD, p: str, x: Tensor, stochastic: bool, eps: Optional[Ten
 def predictor_forward(sd: SD, observed_features: Tensor, observed_coor: Tensor, predict_coor: Tensor,
                       stochastic: bool, eps: Optional[Tensor] = None, fuse_method: str = "Add",
                       evt_layers: int = 4, dec_layers: int = 8, prefix: str = "",
-                      return_latent: bool = False, predict_features_gt: Optional[Tensor] = None):
+                      return_latent: bool = False, predict_features_gt: Optional[Tensor] = None,
+                      decode_with_posterior: bool = False, eps_p: Optional[Tensor] = None):
     """Predictor.forward in eval mode, models/Predictor.py:301-350.  observed_features (N,To,C,H,W) -> (N,Tp,C,H,W).
     With ``predict_features_gt`` (N,Tp,C,H,W) the stochastic model also runs the posterior on the ground-truth future
     (Predictor.py:311-313) and returns (out, mu_o, logvar_o, mu_p, logvar_p) (:324-327) - the KL / ELBO evaluation path;
-    in eval mode the decoder is still queried with the PRIOR sample z_o (:320-322).  The deterministic model ignores it (:328-335)."""
+    in eval mode the decoder is still queried with the PRIOR sample z_o (:320-322).  The deterministic model ignores it (:328-335).
+    ``decode_with_posterior``: the branch the reference takes when ``self.training`` is set (:315-318, forward only here): the
+    decoder is queried with the POSTERIOR sample z_p = mu_p + exp(logvar_p / 2) eps_p - the reconstruction term of the ELBO.
+    ``eps_p``: the posterior's noise (the reference's second ``torch.randn`` draw; defaults to ``eps``)."""
     p = prefix
     Tp = predict_coor.shape[0] // (observed_features.shape[-1] * observed_features.shape[-2])
     op = nrmlp(sd, p + "nrmlp.", observed_coor, fuse_method)
@@ -273,13 +277,19 @@ def predictor_forward(sd: SD, observed_features: Tensor, observed_coor: Tensor, 
     else:
         z = event_encoder(sd, p + "evt_posterior.", evt, False)                     # Predictor.py:330
         mu, logvar = z, None
+    if stochastic and predict_features_gt is not None:
+        memory_p = evt_former(sd, p + "EVT_Former.", predict_features_gt, pp[0], pp[1], evt_layers)     # Predictor.py:312
+        z_p, mu_p, logvar_p = event_encoder(sd, p + "evt_posterior.", memory_p.mean(dim=1), True,
+                                            eps if eps_p is None else eps_p)                            # :313
+        if decode_with_posterior:                                                                       # :315-318
+            z = z_p
+    else:
+        assert not decode_with_posterior, "please input groundtruth predict features for storchastic model training/val"   # :316
     query_evt = z.unsqueeze(1).repeat(1, Tp, 1, 1, 1)
     out = decoder_nar(sd, p + "transformer.", query_evt, memory, op, pp, dec_layers)
     if return_latent:
         return out, memory, evt, z, mu, logvar
     if stochastic and predict_features_gt is not None:
-        memory_p = evt_former(sd, p + "EVT_Former.", predict_features_gt, pp[0], pp[1], evt_layers)     # Predictor.py:312
-        _, mu_p, logvar_p = event_encoder(sd, p + "evt_posterior.", memory_p.mean(dim=1), True, eps)   # :313 (z_p unused in eval)
         return out, mu, logvar, mu_p, logvar_p
     return out
 

@@ -74,3 +74,17 @@ def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11) -> torch
     C1, C2 = 0.01 ** 2, 0.03 ** 2
     m = ((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))
     return torch.mean(m, dim=(1, 2, 3))
+
+
+def best_of_k(samples: torch.Tensor, gt: torch.Tensor, metric: str = "psnr"):
+    """Best-of-K selection: samples (N, K, T, C, H, W), gt (N, T, C, H, W), pixel space.  Per-frame metric with the functions
+    above (the reference applies its metrics frame by frame, utils/metrics.py:127-135), mean over time per sample, argmax over
+    the K samples of a clip.  Returns (best (N, T, C, H, W), best_idx (N,), mean_scores (N, K))."""
+    N, K, T = samples.shape[:3]
+    fn = psnr if metric == "psnr" else ssim
+    flat = samples.reshape(N * K * T, *samples.shape[3:])
+    ref = gt.unsqueeze(1).expand(N, K, *gt.shape[1:]).reshape(N * K * T, *gt.shape[2:])
+    scores = fn(flat, ref).reshape(N, K, T)
+    mean_scores = scores.double().mean(-1).float()
+    idx = mean_scores.argmax(dim=1)
+    return samples[torch.arange(N), idx], idx, mean_scores

@@ -14,6 +14,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PRED_CASES = ["pred_S_stress_realT", "pred_D_default", "pred_D_stress_vfi"]
 PRED_SPADE_CASES = ["pred_S_stress_spade"]    # fuse_method='SPADE' (the constructor default; every shipped YAML uses 'Add')
 PRED_GT_CASES = ["pred_S_stress_gt"]          # NPVP-S with ground-truth future features (posterior branch, Predictor.py:311-327)
+PRED_ZP_CASES = ["pred_S_stress_zp"]          # decoder driven by the posterior sample z_p (Predictor.py:315-318), two noise tensors
 LATENT_KEYS = ("mu_o", "logvar_o", "mu_p", "logvar_p")
 AE_CASES = ["ae_famB_stress", "ae_famA_default", "ae_famA_rgb_stress"]
 
@@ -62,6 +63,14 @@ def build_predictor_gt_case(name):
     _, m = load_golden(name)
     gt = torch.relu(seeded_randn((int(m["N"]), len(m["tp"]), 512, 8, 8), int(m["seed"]) + 300))
     return mod, x, gt, eps, z
+
+
+def build_predictor_zp_case(name):
+    """As build_predictor_gt_case plus the posterior's own noise tensor (the reference's second torch.randn draw)."""
+    mod, x, gt, eps, z = build_predictor_gt_case(name)
+    _, m = load_golden(name)
+    eps_p = seeded_randn((int(m["N"]), 512, 8, 8), int(m["seed"]) + 400)
+    return mod, x, gt, eps, eps_p, z
 
 
 def golden_latents(outs, z):

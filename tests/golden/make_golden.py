@@ -111,7 +111,7 @@ def main():
         ("pred_D_stress_vfi", False, 10, [0, 1, 8, 9], [3, 5.5], 2, True, 13),
     ]
     hl = torch.linspace(0, 7, 8)
-    only_new = "--gt-only" in sys.argv or "--spade-only" in sys.argv
+    only_new = "--gt-only" in sys.argv or "--spade-only" in sys.argv or "--zp-only" in sys.argv
     for name, stoch, max_T, to, tp, N, stress, seed in ([] if only_new else pred_cases):
         to_t, tp_t = torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32)
         args = (8, 8, max_T, hl, hl, to_t, tp_t, 512, 'Add', 'layer', 256, 1, stoch, 8)
@@ -146,7 +146,7 @@ def main():
 
     # ---------------------------------------------------------------- NPVP-S with ground-truth future features (posterior branch)
     # Predictor.forward(observed, predict_features_gt) in eval mode -> (out, mu_o, logvar_o, mu_p, logvar_p), Predictor.py:311-327
-    for name, max_T, to, tp, N, seed in ([] if "--spade-only" in sys.argv else [("pred_S_stress_gt", 9, [0, 1.5, 3], [2, 4, 5.25, 8], 2, 14)]):
+    for name, max_T, to, tp, N, seed in ([] if ("--spade-only" in sys.argv or "--zp-only" in sys.argv) else [("pred_S_stress_gt", 9, [0, 1.5, 3], [2, 4, 5.25, 8], 2, 14)]):
         to_t, tp_t = torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32)
         args = (8, 8, max_T, hl, hl, to_t, tp_t, 512, 'Add', 'layer', 256, 1, True, 8)
         kw = dict(evt_former=True, learn_evt_token=False, evt_former_num_layers=4, rand_context=False)
@@ -182,9 +182,56 @@ def main():
             extra[key + "_stride"] = np.int64(stride)
         save(name, outs_ref[0], dict(seed=seed, stochastic=True, max_T=max_T, to=to, tp=tp, N=N, stress=True,
                                      fp_sum=fp["sum"], fp_abs=fp["abs_sum"], fp_numel=fp["numel"], fp_keys=fp["keys"]), extra)
+    # ---------------------------------------------------------------- NPVP-S decoder driven by the POSTERIOR sample z_p (Predictor.py:315-318):
+    # the branch the reference takes when self.training is set.  Only the top-level flag is raised (ref.training = True, no
+    # recursion), so dropout / drop-path stay in eval mode and the forward is deterministic; two different noise tensors are
+    # injected for the prior's and the posterior's torch.randn draws, in the reference's order.
+    for name, max_T, to, tp, N, seed in ([] if ("--spade-only" in sys.argv or "--gt-only" in sys.argv) else [("pred_S_stress_zp", 9, [0, 2, 3.5], [1, 4.5, 6, 8], 2, 16)]):
+        to_t, tp_t = torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32)
+        args = (8, 8, max_T, hl, hl, to_t, tp_t, 512, 'Add', 'layer', 256, 1, True, 8)
+        kw = dict(evt_former=True, learn_evt_token=False, evt_former_num_layers=4, rand_context=False)
+        reset_shared_norm(RefPredictor)
+        reset_shared_norm(npvp_b200.Predictor)
+        torch.manual_seed(seed)
+        ref = RefPredictor(*args, **kw).eval()
+        torch.manual_seed(seed)
+        mine = npvp_b200.Predictor(*args, **kw).eval()
+        stress_init_(ref, seed)
+        stress_init_(mine, seed)
+        check_same_weights(ref, mine, name)
+        x = torch.relu(seeded_randn((N, len(to), 512, 8, 8), seed + 100))
+        gt = torch.relu(seeded_randn((N, len(tp), 512, 8, 8), seed + 300))
+        eps = seeded_randn((N, 512, 8, 8), seed + 200)
+        eps_p = seeded_randn((N, 512, 8, 8), seed + 400)
+        draws = [eps, eps_p]
+        real = ref_sub.torch.randn
+        try:
+            ref_sub.torch.randn = lambda *a, **k: draws.pop(0).clone()
+            ref.training = True                       # top-level flag only: children stay in eval mode
+            outs_ref = ref(x, gt)
+        finally:
+            ref_sub.torch.randn = real
+            ref.training = False
+        assert not draws
+        sd = {k: v.clone() for k, v in mine.state_dict().items()}
+        outs_or = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps, predict_features_gt=gt,
+                                      decode_with_posterior=True, eps_p=eps_p)
+        errs = [float((a - b).abs().max()) for a, b in zip(outs_ref, outs_or)]
+        prior_out = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps)
+        assert float((prior_out - outs_ref[0]).abs().max()) > 1e-2, "the posterior-driven output must differ from the prior-driven one"
+        report.append((name, tuple(outs_ref[0].shape), max(errs)))
+        assert max(errs) < 5e-5, (name, errs)
+        fp = fingerprint(ref.state_dict())
+        extra = {}
+        for key, t in zip(("mu_o", "logvar_o", "mu_p", "logvar_p"), outs_ref[1:]):
+            vals, stride = sample(t, 8000)
+            extra[key] = vals
+            extra[key + "_stride"] = np.int64(stride)
+        save(name, outs_ref[0], dict(seed=seed, stochastic=True, max_T=max_T, to=to, tp=tp, N=N, stress=True,
+                                     fp_sum=fp["sum"], fp_abs=fp["abs_sum"], fp_numel=fp["numel"], fp_keys=fp["keys"]), extra)
     # ---------------------------------------------------------------- fuse_method='SPADE' (the constructor default, Predictor.py:268;
     # every shipped YAML uses 'Add'): the NRMLP also emits gamma and the fuser scales by (1 + gamma) (submodules.py:296-297, 441-447)
-    for name, max_T, to, tp, N, seed in [("pred_S_stress_spade", 10, [0, 2, 3.5], [1, 4, 6, 9.5], 2, 15)]:
+    for name, max_T, to, tp, N, seed in ([] if "--zp-only" in sys.argv else [("pred_S_stress_spade", 10, [0, 2, 3.5], [1, 4, 6, 9.5], 2, 15)]):
         to_t, tp_t = torch.tensor(to, dtype=torch.float32), torch.tensor(tp, dtype=torch.float32)
         args = (8, 8, max_T, hl, hl, to_t, tp_t, 512, 'SPADE', 'layer', 256, 1, True, 8)
         kw = dict(evt_former=True, learn_evt_token=False, evt_former_num_layers=4, rand_context=False)
@@ -216,7 +263,7 @@ def main():
         fp = fingerprint(ref.state_dict())
         save(name, out_ref, dict(seed=seed, stochastic=True, max_T=max_T, to=to, tp=tp, N=N, stress=True, fuse_method="SPADE",
                                  gamma_scale=6.0, fp_sum=fp["sum"], fp_abs=fp["abs_sum"], fp_numel=fp["numel"], fp_keys=fp["keys"]))
-    if "--spade-only" in sys.argv:
+    if "--spade-only" in sys.argv or "--zp-only" in sys.argv:
         print(report)
         with open(os.path.join(HERE, "REPORT.txt"), "a") as f:
             for r in report[-1:]:

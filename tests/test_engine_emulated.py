@@ -6,7 +6,8 @@ import pytest
 import torch
 
 import npvp_b200._lib as _lib
-from cases import AE_CASES, PRED_CASES, PRED_GT_CASES, PRED_SPADE_CASES, build_ae_case, build_predictor_case, build_predictor_gt_case
+from cases import (AE_CASES, PRED_CASES, PRED_GT_CASES, PRED_SPADE_CASES, PRED_ZP_CASES, build_ae_case, build_predictor_case,
+                   build_predictor_gt_case, build_predictor_zp_case)
 from kernel_specs import SpecOps
 from oracle import npvp_oracle as O
 
@@ -64,6 +65,28 @@ def test_predictor_engine_posterior_branch(name):
         assert a.shape == b.shape
         assert _rel(a, b) < 3e-2, _rel(a, b)
     assert torch.equal(eng.run(x), outs[0])         # same prediction with and without the ground truth
+
+
+@pytest.mark.parametrize("name", PRED_ZP_CASES)
+def test_predictor_engine_posterior_decode(name):
+    """Decoder driven by z_p (Predictor.py:315-318): engine vs oracle; the result differs from the prior-driven forward."""
+    from npvp_b200.engine_predictor import PredictorEngine
+    mod, x, gt, eps, eps_p, _ = build_predictor_zp_case(name)
+    sd = mod.state_dict()
+    ref = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps, predict_features_gt=gt,
+                              decode_with_posterior=True, eps_p=eps_p)
+    mod.injected_eps, mod.injected_eps_p = eps, eps_p
+    eng = PredictorEngine(mod)
+    outs = eng.run(x, predict_gt=gt, decode_posterior=True)
+    assert len(outs) == 5
+    for a, b in zip(outs, ref):
+        assert a.shape == b.shape
+        assert _rel(a, b) < 3e-2, _rel(a, b)
+    # the fixture tells the two latent samples apart: the prior-driven forward is 4x further from the reference than our error
+    prior_ref = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps)
+    gap = float((prior_ref - ref[0]).abs().mean())
+    assert float((outs[0] - ref[0]).abs().mean()) < 0.25 * gap
+    assert float((eng.run(x) - ref[0]).abs().mean()) > 0.75 * gap
 
 
 def test_predictor_engine_per_clip_timestamps():

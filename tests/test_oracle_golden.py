@@ -3,8 +3,8 @@ import numpy as np
 import pytest
 import torch
 
-from cases import (AE_CASES, PRED_CASES, PRED_GT_CASES, PRED_SPADE_CASES, build_ae_case, build_predictor_case, build_predictor_gt_case,
-                   golden_latents, golden_sample)
+from cases import (AE_CASES, PRED_CASES, PRED_GT_CASES, PRED_SPADE_CASES, PRED_ZP_CASES, build_ae_case, build_predictor_case,
+                   build_predictor_gt_case, build_predictor_zp_case, golden_latents, golden_sample)
 from oracle import npvp_oracle as O
 
 torch.set_grad_enabled(False)
@@ -45,6 +45,22 @@ def test_predictor_posterior_oracle_matches_reference(name):
     # the decoder is queried with the PRIOR sample: the prediction does not depend on the ground truth
     plain = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps)
     assert torch.equal(plain, outs[0])
+
+
+@pytest.mark.parametrize("name", PRED_ZP_CASES)
+def test_predictor_posterior_decode_oracle_matches_reference(name):
+    """decode_with_posterior: the reference's training-mode branch (Predictor.py:315-318), fixture generated from the reference with
+    its top-level training flag raised and two injected noise tensors."""
+    mod, x, gt, eps, eps_p, z = build_predictor_zp_case(name)
+    sd = mod.state_dict()
+    outs = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps, predict_features_gt=gt,
+                               decode_with_posterior=True, eps_p=eps_p)
+    assert len(outs) == 5 and list(outs[0].shape) == list(z["shape"])
+    np.testing.assert_allclose(golden_sample(outs[0], z), z["sample"], atol=5e-5, rtol=0)
+    for key, ours, gold in golden_latents(outs, z):
+        np.testing.assert_allclose(ours, gold, atol=5e-5, rtol=0, err_msg=key)
+    with pytest.raises(AssertionError):                                # Predictor.py:316
+        O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps, decode_with_posterior=True)
 
 
 @pytest.mark.parametrize("name", AE_CASES)

@@ -7,8 +7,8 @@ import numpy as np
 import pytest
 import torch
 
-from cases import (AE_CASES, PRED_CASES, PRED_GT_CASES, PRED_SPADE_CASES, build_ae_case, build_predictor_case, build_predictor_gt_case,
-                   golden_latents, golden_sample)
+from cases import (AE_CASES, PRED_CASES, PRED_GT_CASES, PRED_SPADE_CASES, PRED_ZP_CASES, build_ae_case, build_predictor_case,
+                   build_predictor_gt_case, build_predictor_zp_case, golden_latents, golden_sample)
 from oracle import npvp_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -84,6 +84,47 @@ def test_predictor_posterior_branch(name):
     mod(x.cuda(), gt.cuda())
     a = torch.randn(1, device="cuda")
     torch.manual_seed(5)
+    torch.randn((x.shape[0], 512, 8, 8), device="cuda"); torch.randn((x.shape[0], 512, 8, 8), device="cuda")
+    assert torch.equal(a, torch.randn(1, device="cuda"))
+
+
+@pytest.mark.parametrize("name", PRED_ZP_CASES)
+def test_predictor_posterior_decode(name):
+    """``posterior_decode``: the forward of the reference's training-mode branch (Predictor.py:315-318) - the NAR decoder is
+    queried with the posterior sample z_p = mu_p + exp(logvar_p / 2) eps_p of the ground-truth future - against the oracle and a
+    fixture generated from the reference itself (top-level training flag raised, dropout layers in eval mode)."""
+    mod, x, gt, eps, eps_p, z = build_predictor_zp_case(name)
+    sd = mod.state_dict()
+    ref = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps, predict_features_gt=gt,
+                              decode_with_posterior=True, eps_p=eps_p)
+    mod = mod.cuda()
+    mod.injected_eps, mod.injected_eps_p, mod.posterior_decode = eps.cuda(), eps_p.cuda(), True
+    outs = [o.cpu() for o in mod(x.cuda(), gt.cuda())]
+    assert len(outs) == 5
+    for key, a, b in zip(("out", "mu_o", "logvar_o", "mu_p", "logvar_p"), outs, ref):
+        r = _rel(a, b)
+        print(f"{name}.{key}: rel err vs oracle {r:.3e}")
+        assert a.shape == b.shape and r < FEAT_TOL, (key, r)
+    assert float((torch.from_numpy(golden_sample(outs[0], z)) - torch.from_numpy(z["sample"])).abs().max()) < FEAT_TOL * float(z["absmax"])
+    for key, ours, gold in golden_latents(outs, z):
+        assert float(np.abs(ours - gold).max()) < FEAT_TOL * float(np.abs(gold).max()), key
+    with pytest.raises(AssertionError, match="groundtruth"):           # the reference's assertion (Predictor.py:316)
+        mod(x.cuda())
+    # the fixture tells the two latent samples apart: the prior-driven forward is far from this reference, our error is not
+    prior_ref = O.predictor_forward(sd, x, sd["observed_coor"], sd["predict_coor"], True, eps)
+    gap = float((prior_ref - ref[0]).abs().mean())
+    err = float((outs[0] - ref[0]).abs().mean())
+    print(f"{name}: mean |err| {err:.3e} vs mean |posterior-driven - prior-driven| {gap:.3e}")
+    assert err < 0.25 * gap
+    mod.posterior_decode = False                                       # back to the eval-mode branch: prior-driven, different output
+    prior = mod(x.cuda(), gt.cuda())[0].cpu()
+    assert float((prior - ref[0]).abs().mean()) > 0.75 * gap
+    mod.injected_eps = mod.injected_eps_p = None                       # sampled noise: two draws from the global generator, in the reference's order
+    mod.posterior_decode = True
+    torch.manual_seed(9)
+    mod(x.cuda(), gt.cuda())
+    a = torch.randn(1, device="cuda")
+    torch.manual_seed(9)
     torch.randn((x.shape[0], 512, 8, 8), device="cuda"); torch.randn((x.shape[0], 512, 8, 8), device="cuda")
     assert torch.equal(a, torch.randn(1, device="cuda"))
 

@@ -96,3 +96,47 @@ def test_rollout_uint8_host_output():
     assert torch.equal(model.to_pixels(frames).cpu(), P.renormalize_clamp(frames.cpu(), mean, std))
     back = model.from_pixels(ref_u8)
     assert back.shape == frames.shape and back.dtype == torch.float32
+
+
+@pytest.mark.parametrize("metric", ["psnr", "ssim"])
+def test_best_of_k_selection_vs_oracle(metric):
+    """npvp_b200.metrics.best_of_k (npvp_sample_scores + npvp_best_of_k): per-frame scores of K samples per clip against ONE
+    ground truth, mean over time, argmax, winner's frames - against the oracle built from the reference's PSNR / SSIM."""
+    from oracle import post_oracle as P
+    from npvp_b200.metrics import best_of_k
+    g = torch.Generator().manual_seed(5)
+    N, K, T, C, H, W = 3, 5, 4, 3, 64, 48
+    gt = torch.rand((N, T, C, H, W), generator=g)
+    noise = torch.rand((N, K, 1, 1, 1, 1), generator=g) * 0.3 + 0.02           # every sample a different distance from the truth
+    samples = (gt.unsqueeze(1) + noise * torch.randn((N, K, T, C, H, W), generator=g)).clamp(0, 1)
+    best_ref, idx_ref, mean_ref = P.best_of_k(samples, gt, metric)
+    best, idx, mean_scores, scores = best_of_k(samples.to(DEV), gt.to(DEV), metric)
+    assert scores.shape == (N, K, T) and idx.dtype == torch.int32
+    assert torch.equal(idx.cpu().long(), idx_ref)
+    assert float((mean_scores.cpu() - mean_ref).abs().max()) <= (1e-3 if metric == "psnr" else 1e-5)
+    assert torch.equal(best.cpu(), best_ref)
+    # the per-sample scores equal the plain metric kernels on the replicated ground truth
+    from npvp_b200.metrics import PSNR, SSIM
+    flat = samples.reshape(N * K * T, C, H, W).to(DEV)
+    rep = gt.unsqueeze(1).expand(N, K, T, C, H, W).reshape(N * K * T, C, H, W).contiguous().to(DEV)
+    plain = PSNR(flat, rep, mean_flag=False) if metric == "psnr" else SSIM()(flat, rep, mean_flag=False)
+    assert torch.equal(plain.reshape(N, K, T), scores)
+
+
+def test_predict_best_of_k_pipeline():
+    """NPVPInference.predict_best_of_k: 8 stochastic samples per clip (BASELINE config 3), best by PSNR against a ground truth that
+    IS one of the samples - the selection must find it, and the returned frames are that sample's, bit for bit."""
+    from npvp_b200.pipeline import build_from_config
+    from util_init import seeded_rand, stress_init_
+    model = build_from_config("BAIR_VFP_NPVP-S", device="cpu", seed=0)
+    stress_init_(model.predictor, 3)
+    model = model.cuda()
+    x = (seeded_rand((2, 2, 3, 64, 64), 5) * 2 - 1).cuda()
+    eps = torch.randn(16, 512, 8, 8, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    smp = model.predict_samples(x, 8, eps)
+    gt = torch.stack([smp[0, 5], smp[1, 2]])                                   # clip 0: sample 5 is the truth, clip 1: sample 2
+    best, idx, mean_scores = model.predict_best_of_k(x, gt, 8, "psnr", eps)
+    assert idx.tolist() == [5, 2] and mean_scores.shape == (2, 8)
+    assert torch.equal(best, gt)
+    _, idx_s, _ = model.predict_best_of_k(x, gt, 8, "ssim", eps)
+    assert idx_s.tolist() == [5, 2]
