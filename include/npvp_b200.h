@@ -205,17 +205,23 @@ int npvp_tokens_to_nchw(const float* x_f32, const void* x_bf16, float* out, int6
 
 /* ---- autoencoder ---------------------------------------------------------------------------
  * 7x7 stem: reflect-pad 3, conv (no bias) + folded BN + ReLU  (ResNetAutoEncoder.py:70-73).
- * x fp32 NCHW [frames,Cin,H,W]; w fp32 [49*Cin, Cout] (tap-major, BN scale folded); shift fp32 [Cout];
- * out bf16 NHWC [frames,H,W,Cout]. */
+ * x fp32 NCHW [frames,Cin,H,W]  OR  x_u8 uint8 pixels [frames,Cin,H,W] with the dataset's VidNormalize mean / std (host pointers,
+ * Cin values each): the stem then applies VidToTensor + VidNormalize itself, ((u8 / 255) - mean) / std in the reference's
+ * operation order (utils/dataset.py:835-858) - exactly one of x and x_u8 is non-NULL;
+ * w fp32 [49*Cin, Cout] (tap-major, BN scale folded); shift fp32 [Cout]; out bf16 NHWC [frames,H,W,Cout]. */
 int npvp_conv7x7_stem(const float* x, const float* w, const float* shift, void* out_bf16, int64_t frames, int Cin,
-                      int Cout, int H, int W, int fp16, void* stream);
+                      int Cout, int H, int W, int fp16, const void* x_u8, const float* norm_mean, const float* norm_std, void* stream);
 /* 7x7 head: reflect-pad 3, conv + bias + Tanh|Sigmoid (ResNetAutoEncoder.py:184-189).
  * x 16-bit [frames,H,W,Cin] (phase_major=1: stored [frames,H/2,W/2,4,Cin], the ConvT GEMM's native output), Cin 32 or 64;
  * w 16-bit, pre-packed as mma.sync B fragments [Cin/32][14 k-steps = (ky, 16-channel half)][NT = ceil(7 Cout / 8)][32 lanes][4]
  * of the matrix B[(ky,ci), n = kx*Cout + co] (see pack_head_weights in npvp_b200/_lib.py); Cout in [1,3]; bias fp32 [Cout];
- * out fp32 NCHW [frames,Cout,H,W]. */
+ * out fp32 NCHW [frames,Cout,H,W] (model space) and / or out_u8 uint8 NCHW: the pixel-space frame the reference writes to image
+ * files - VidReNormalize, clamp to [0,1], ToPILImage's trunc(255 v) (utils/dataset.py:860-886, utils/train_summary.py:243-248) -
+ * fused into the epilogue; pix_inv_std / pix_inv_mean (host pointers, Cout values: 1/std and -mean as npvp_frames_to_pixels
+ * takes them) are required with out_u8.  At least one of out / out_u8 is non-NULL. */
 int npvp_conv7x7_head(const void* x_bf16, const void* w, const float* bias, float* out, int64_t frames, int Cin,
-                      int Cout, int H, int W, int phase_major, int act, int fp16, void* stream);
+                      int Cout, int H, int W, int phase_major, int act, int fp16, void* out_u8, const float* pix_inv_std,
+                      const float* pix_inv_mean, void* stream);
 /* Patch gather for conv-as-GEMM: out[(f,oy,ox), (ky,kx,c)] = x[f, oy*stride - pad + ky, ox*stride - pad + kx, c].
  * x bf16 NHWC (or phase-major), out bf16 [frames*Ho*Wo, KH*KW*C]. */
 int npvp_im2col_nhwc(const void* x_bf16, void* out_bf16, int64_t frames, int H, int W, int C, int KH, int KW,

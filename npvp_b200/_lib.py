@@ -62,8 +62,8 @@ SIGNATURES = {
     "npvp_latent_reparam": [_vp, _i64, _vp, _vp, _i64, _i64, _vp],
     "npvp_nchw_to_tokens": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp],
     "npvp_tokens_to_nchw": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp],
-    "npvp_conv7x7_stem": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
-    "npvp_conv7x7_head": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "npvp_conv7x7_stem": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "npvp_conv7x7_head": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "npvp_im2col_nhwc": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "npvp_maxpool2x2_cols": [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _vp],
     "npvp_nonlocal_attention": [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -431,25 +431,45 @@ class Ops:
         self._call("npvp_tokens_to_nchw", xf, xb, out.data_ptr(), frames, Cc, HW, int(relu), _is_fp16(x), self._stream())
 
     # -- autoencoder ----------------------------------------------------------------------------
-    def conv7x7_stem(self, x, w, shift, out, Cin, Cout, H, W):
-        _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(shift, torch.float32, "shift"); _chk16(out, "out")
+    def conv7x7_stem(self, x, w, shift, out, Cin, Cout, H, W, norm=None):
+        """x: fp32 frames (frames, Cin, H, W), or uint8 pixels with ``norm`` = (mean, std) of VidNormalize: the stem normalises."""
+        _chk(w, torch.float32, "w"); _chk(shift, torch.float32, "shift"); _chk16(out, "out")
+        u8 = x.dtype == torch.uint8
+        if u8:
+            assert x.is_cuda and x.is_contiguous() and norm is not None and len(norm[0]) == Cin and len(norm[1]) == Cin
+            mean, std = self._host_f32(norm[0]), self._host_f32(norm[1])
+        else:
+            _chk(x, torch.float32, "x")
+            mean = std = None
+        esz = 1 if u8 else 4
         frames = x.numel() // (Cin * H * W)
         assert out.numel() == frames * H * W * Cout and w.shape == (49 * Cin, Cout)
         per = max(1, 65535 // (Cout // 32))
         for f0 in range(0, frames, per):      # grid.z limit
             n = min(per, frames - f0)
-            self._call("npvp_conv7x7_stem", x.data_ptr() + f0 * Cin * H * W * 4, w.data_ptr(), shift.data_ptr(),
-                       out.data_ptr() + f0 * H * W * Cout * 2, n, Cin, Cout, H, W, _is_fp16(out), self._stream())
+            ptr = x.data_ptr() + f0 * Cin * H * W * esz
+            self._call("npvp_conv7x7_stem", None if u8 else ptr, w.data_ptr(), shift.data_ptr(),
+                       out.data_ptr() + f0 * H * W * Cout * 2, n, Cin, Cout, H, W, _is_fp16(out), ptr if u8 else None, mean, std, self._stream())
 
-    def conv7x7_head(self, x, w, bias, out, Cin, Cout, H, W, phase_major, act):
-        """w: 16-bit weights packed by :func:`pack_head_weights` ([Cin/32, 14, NT, 32, 4])."""
+    def conv7x7_head(self, x, w, bias, out, Cin, Cout, H, W, phase_major, act, out_u8=None, renorm=None):
+        """w: 16-bit weights packed by :func:`pack_head_weights` ([Cin/32, 14, NT, 32, 4]).  ``out`` fp32 model-space frames and / or
+        ``out_u8`` pixel-space uint8 frames (``renorm`` = (mean, std) of VidReNormalize; fused VidReNormalize + clamp + uint8)."""
         _chk16(x, "x"); _chk16(w, "w", like=x); _chk(bias, torch.float32, "bias"); _chk(out, torch.float32, "out")
         frames = x.numel() // (Cin * H * W)
-        assert out.numel() == frames * Cout * H * W and tuple(w.shape) == (Cin // 32, 14, head_n_tiles(Cout), 32, 4)
+        assert out is not None or out_u8 is not None
+        assert out is None or out.numel() == frames * Cout * H * W
+        assert tuple(w.shape) == (Cin // 32, 14, head_n_tiles(Cout), 32, 4)
+        inv_std = inv_mean = None
+        if out_u8 is not None:
+            assert out_u8.is_cuda and out_u8.is_contiguous() and out_u8.dtype == torch.uint8 and out_u8.numel() == frames * Cout * H * W
+            assert renorm is not None and len(renorm[0]) == Cout and len(renorm[1]) == Cout
+            inv_std = self._host_f32([1.0 / float(v) for v in renorm[1]])
+            inv_mean = self._host_f32([-float(v) for v in renorm[0]])
         for f0 in range(0, frames, 65535):
             n = min(65535, frames - f0)
             self._call("npvp_conv7x7_head", x.data_ptr() + f0 * Cin * H * W * 2, w.data_ptr(), bias.data_ptr(),
-                       out.data_ptr() + f0 * Cout * H * W * 4, n, Cin, Cout, H, W, int(phase_major), int(act), _is_fp16(x), self._stream())
+                       None if out is None else out.data_ptr() + f0 * Cout * H * W * 4, n, Cin, Cout, H, W, int(phase_major), int(act), _is_fp16(x),
+                       None if out_u8 is None else out_u8.data_ptr() + f0 * Cout * H * W, inv_std, inv_mean, self._stream())
 
     def im2col(self, x, out, frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo, phase_major=False):
         _chk16(x, "x"); _chk16(out, "out", like=x)

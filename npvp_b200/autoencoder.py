@@ -95,11 +95,12 @@ class ResnetEncoder(_EngineModule):
         with self._on_device(x):
             return self._engine().run(x)
 
-    def forward_tokens(self, x):
-        """Engine-internal variant: returns channels-last features (N, T, h, w, C) without the NCHW copy."""
+    def forward_tokens(self, x, norm=None):
+        """Engine-internal variant: returns channels-last features (N, T, h, w, C) without the NCHW copy.  ``x`` may be uint8
+        pixels with ``norm`` = (mean, std): the stem kernel applies VidToTensor + VidNormalize itself."""
         self._guard(x)
         with self._on_device(x):
-            return self._engine().run(x, channels_last=True)
+            return self._engine().run(x, channels_last=True, norm=norm)
 
 
 class ResnetDecoder(_EngineModule):
@@ -130,8 +131,9 @@ class ResnetDecoder(_EngineModule):
         with self._on_device(x):
             return self._engine().run(x)
 
-    def forward_tokens(self, x_cl):
-        """Engine-internal variant: takes channels-last features (N, T, h, w, C)."""
+    def forward_tokens(self, x_cl, renorm=None, want_f32=True):
+        """Engine-internal variant: takes channels-last features (N, T, h, w, C).  ``renorm`` = (mean, std): also returns the
+        pixel-space uint8 frames written by the head kernel's fused epilogue -> (frames | None, frames_u8)."""
         self._guard(x_cl)
         with self._on_device(x_cl):
-            return self._engine().run(x_cl, channels_last=True)
+            return self._engine().run(x_cl, channels_last=True, renorm=renorm, want_f32=want_f32)

@@ -39,10 +39,12 @@ __device__ __forceinline__ void mma_16816_stem(float (&c)[4], const uint32_t (&a
   }
 }
 
+struct StemNorm { float mean[3], std[3]; };
+
 template <int CIN>
 __global__ void __launch_bounds__(256)
-conv7x7_stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
-                    h16* __restrict__ out, int Cout, int H, int W, int fp16) {
+conv7x7_stem_kernel(const float* __restrict__ x, const uint8_t* __restrict__ x_u8, StemNorm nrm, const float* __restrict__ w,
+                    const float* __restrict__ shift, h16* __restrict__ out, int Cout, int H, int W, int fp16) {
   __shared__ __align__(16) h16 tile[kStemTY + 6][kStemTW][4];        // 8 KB
   __shared__ __align__(16) h16 wb[7][2][4][8][16];                   // [ky][k-step][n-tile][n][k]  14 KB
   const int groups = Cout / 32;
@@ -54,7 +56,11 @@ conv7x7_stem_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     const int yy = reflect_idx(ty0 + r - 3, H), xx = reflect_idx(min(tx0 + c - 3, W + 2), W);
     float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) v[ci] = __ldg(x + (((size_t)f * CIN + ci) * H + yy) * W + xx);
+    for (int ci = 0; ci < CIN; ++ci) {
+      const size_t off = (((size_t)f * CIN + ci) * H + yy) * W + xx;
+      // uint8 pixels: VidToTensor + VidNormalize in the reference's operation order, ((u8 / 255) - mean) / std (post_kernels.cu)
+      v[ci] = x_u8 ? __fdiv_rn(__fsub_rn(__fdiv_rn((float)__ldg(x_u8 + off), 255.0f), nrm.mean[ci]), nrm.std[ci]) : __ldg(x + off);
+    }
     *reinterpret_cast<uint2*>(&tile[r][c][0]) = make_uint2(pack_h16x2(v[0], v[1], fp16), pack_h16x2(v[2], v[3], fp16));
   }
   // weights fp32 [(ky,kx,ci), Cout] -> B fragments: k = kx*4 + ci (kx = 7 and ci >= CIN are zero)
@@ -119,14 +125,19 @@ conv7x7_stem_kernel(const float* __restrict__ x, const float* __restrict__ w, co
 }
 
 extern "C" int npvp_conv7x7_stem(const float* x, const float* w, const float* shift, void* out_bf16, int64_t frames, int Cin,
-                                 int Cout, int H, int W, int fp16, void* stream) {
-  NPVP_REQUIRE(x && w && shift && out_bf16 && frames > 0, "npvp_conv7x7_stem: bad arguments");
+                                 int Cout, int H, int W, int fp16, const void* x_u8, const float* norm_mean, const float* norm_std,
+                                 void* stream) {
+  NPVP_REQUIRE((x != nullptr) != (x_u8 != nullptr), "npvp_conv7x7_stem: exactly one of x (fp32 frames) and x_u8 (uint8 pixels) must be given");
+  NPVP_REQUIRE(!x_u8 || (norm_mean && norm_std), "npvp_conv7x7_stem: uint8 input needs the VidNormalize mean / std (host pointers)");
+  NPVP_REQUIRE(w && shift && out_bf16 && frames > 0, "npvp_conv7x7_stem: bad arguments");
+  StemNorm nrm = {};
+  if (x_u8) for (int c = 0; c < Cin && c < 3; ++c) { nrm.mean[c] = norm_mean[c]; nrm.std[c] = norm_std[c]; }
   NPVP_REQUIRE(Cout % 32 == 0 && H >= 4 && W >= 4, "npvp_conv7x7_stem: Cout must be a multiple of 32, H/W >= 4");
   NPVP_REQUIRE(frames * (Cout / 32) <= 65535, "npvp_conv7x7_stem: too many frames per launch (%lld)", (long long)frames);
   dim3 grid((unsigned)(((H + kStemTY - 1) / kStemTY) * ((W + kStemTX - 1) / kStemTX)), 1, (unsigned)(frames * (Cout / 32)));
   cudaStream_t st = (cudaStream_t)stream;
-  if (Cin == 1) conv7x7_stem_kernel<1><<<grid, 256, 0, st>>>(x, w, shift, (h16*)out_bf16, Cout, H, W, fp16);
-  else if (Cin == 3) conv7x7_stem_kernel<3><<<grid, 256, 0, st>>>(x, w, shift, (h16*)out_bf16, Cout, H, W, fp16);
+  if (Cin == 1) conv7x7_stem_kernel<1><<<grid, 256, 0, st>>>(x, (const uint8_t*)x_u8, nrm, w, shift, (h16*)out_bf16, Cout, H, W, fp16);
+  else if (Cin == 3) conv7x7_stem_kernel<3><<<grid, 256, 0, st>>>(x, (const uint8_t*)x_u8, nrm, w, shift, (h16*)out_bf16, Cout, H, W, fp16);
   else NPVP_REQUIRE(false, "npvp_conv7x7_stem: Cin must be 1 or 3 (got %d)", Cin);
   NPVP_LAUNCH_CHECK("conv7x7_stem_kernel");
   return NPVP_OK;
@@ -174,10 +185,12 @@ constexpr int kHeadGroups = (kHeadCols + 15) / 16;             // 16-pixel mma r
 constexpr int kHeadTW = kHeadGroups * 16;                      // smem row pitch in pixels (80; the last 10 are never staged)
 constexpr int kHeadTileBytes = kHeadRows * kHeadTW * 64;       // 32 channels x 2 B per pixel
 
+struct HeadPix { float inv_std[3], inv_mean[3]; };
+
 template <int NT, bool FP16>
 __global__ void __launch_bounds__(256, 2)
 conv7x7_head_kernel(const h16* __restrict__ x, const uint2* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
-                    int Cin, int Cout, int H, int W, int phase_major, int act) {
+                    int Cin, int Cout, int H, int W, int phase_major, int act, uint8_t* __restrict__ out_u8, HeadPix pix) {
   constexpr int SST = NT * 8 + 1;                               // scratch row stride (floats), odd: conflict-free shift-sum
   static_assert(8 * kHeadTW * SST * 4 <= kHeadTileBytes, "Z scratch must fit in the tile it aliases");
   extern __shared__ __align__(128) uint8_t head_smem[];
@@ -250,13 +263,18 @@ conv7x7_head_kernel(const h16* __restrict__ x, const uint2* __restrict__ w, cons
 #pragma unroll
     for (int kx = 0; kx < 7; ++kx) v += S[(ox + kx) * SST + kx * Cout + co];
     v = (act == NPVP_ACT_TANH) ? tanhf(v) : (act == NPVP_ACT_SIGMOID ? 1.0f / (1.0f + expf(-v)) : v);
-    out[(((size_t)f * Cout + co) * H + oy) * W + tx0 + ox] = v;
+    const size_t o = (((size_t)f * Cout + co) * H + oy) * W + tx0 + ox;
+    if (out) out[o] = v;
+    if (out_u8) {   // VidReNormalize + clamp + ToPILImage in the reference's operation order (frames_to_pixels_kernel): bit-identical
+      const float p = fminf(fmaxf(__fsub_rn(__fdiv_rn(v, pix.inv_std[co]), pix.inv_mean[co]), 0.0f), 1.0f);
+      out_u8[o] = (uint8_t)__float2uint_rz(__fmul_rn(p, 255.0f));
+    }
   }
 }
 
 template <int NT, bool FP16>
 static int launch_head(const void* x, const void* w, const float* bias, float* out, int64_t frames, int Cin, int Cout, int H, int W,
-                       int phase_major, int act, cudaStream_t st) {
+                       int phase_major, int act, uint8_t* out_u8, const HeadPix& pix, cudaStream_t st) {
   const int smem = kHeadTileBytes + (Cin / 32) * 14 * NT * 32 * 8;
   static int attr_smem = 0;
   if (attr_smem < smem) {
@@ -265,14 +283,18 @@ static int launch_head(const void* x, const void* w, const float* bias, float* o
     attr_smem = smem;
   }
   dim3 grid((unsigned)(((H + kHeadTY - 1) / kHeadTY) * ((W + kHeadTX - 1) / kHeadTX)), 1, (unsigned)frames);
-  conv7x7_head_kernel<NT, FP16><<<grid, 256, smem, st>>>((const h16*)x, (const uint2*)w, bias, out, Cin, Cout, H, W, phase_major, act);
+  conv7x7_head_kernel<NT, FP16><<<grid, 256, smem, st>>>((const h16*)x, (const uint2*)w, bias, out, Cin, Cout, H, W, phase_major, act, out_u8, pix);
   NPVP_LAUNCH_CHECK("conv7x7_head_kernel");
   return NPVP_OK;
 }
 
 extern "C" int npvp_conv7x7_head(const void* x_bf16, const void* w, const float* bias, float* out, int64_t frames, int Cin,
-                                 int Cout, int H, int W, int phase_major, int act, int fp16, void* stream) {
-  NPVP_REQUIRE(x_bf16 && w && bias && out && frames > 0 && frames <= 65535, "npvp_conv7x7_head: bad arguments");
+                                 int Cout, int H, int W, int phase_major, int act, int fp16, void* out_u8, const float* pix_inv_std,
+                                 const float* pix_inv_mean, void* stream) {
+  NPVP_REQUIRE(x_bf16 && w && bias && (out || out_u8) && frames > 0 && frames <= 65535, "npvp_conv7x7_head: bad arguments");
+  NPVP_REQUIRE(!out_u8 || (pix_inv_std && pix_inv_mean), "npvp_conv7x7_head: the uint8 output needs the VidReNormalize constants (host pointers)");
+  HeadPix pix = {};
+  if (out_u8) for (int c = 0; c < Cout && c < 3; ++c) { pix.inv_std[c] = pix_inv_std[c]; pix.inv_mean[c] = pix_inv_mean[c]; }
   NPVP_REQUIRE(H >= 4 && W >= 4 && (!phase_major || (H % 2 == 0 && W % 2 == 0)), "npvp_conv7x7_head: H/W >= 4, even H/W for phase-major input");
   NPVP_REQUIRE(Cout >= 1 && Cout <= 3, "npvp_conv7x7_head: Cout must be in [1, 3] (got %d)", Cout);
   NPVP_REQUIRE(Cin == 32 || Cin == 64, "npvp_conv7x7_head: Cin must be 32 or 64 (got %d)", Cin);
@@ -281,8 +303,8 @@ extern "C" int npvp_conv7x7_head(const void* x_bf16, const void* w, const float*
   const int nt = (7 * Cout + 7) / 8;
 #define NPVP_HEAD_CASE(NTV)                                                                                                   \
   if (nt == NTV)                                                                                                              \
-    return fp16 ? launch_head<NTV, true>(x_bf16, w, bias, out, frames, Cin, Cout, H, W, phase_major, act, st)                 \
-                : launch_head<NTV, false>(x_bf16, w, bias, out, frames, Cin, Cout, H, W, phase_major, act, st);
+    return fp16 ? launch_head<NTV, true>(x_bf16, w, bias, out, frames, Cin, Cout, H, W, phase_major, act, (uint8_t*)out_u8, pix, st)  \
+                : launch_head<NTV, false>(x_bf16, w, bias, out, frames, Cin, Cout, H, W, phase_major, act, (uint8_t*)out_u8, pix, st);
   NPVP_HEAD_CASE(1)
   NPVP_HEAD_CASE(2)
   NPVP_HEAD_CASE(3)

@@ -123,15 +123,21 @@ class EncoderEngine:
         op.gemm(att, p.wo, bias=p.bo, act=ACT_RELU, alpha=p.gamma, res1=y, res2=x, out_bf16=out)
         return out
 
-    def run(self, x, channels_last=False):
-        """x: (N,T,Cin,H,W) fp32 -> (N,T,C,h,w) fp32, or channels-last (N,T,h,w,C) when ``channels_last``."""
+    def run(self, x, channels_last=False, norm=None):
+        """x: (N,T,Cin,H,W) fp32 -> (N,T,C,h,w) fp32, or channels-last (N,T,h,w,C) when ``channels_last``.
+        uint8 ``x`` (pixels as a video decoder delivers them) with ``norm`` = (mean, std): VidToTensor + VidNormalize
+        (utils/dataset.py:835-858) run inside the stem kernel - no fp32 copy of the input frames exists."""
         op, ws, mod = _lib.ops(), self.ws, self.mod
         N, T, Cin, H, W = x.shape
         assert Cin == self.cin, f"expected {self.cin} input channels, got {Cin}"
         frames = N * T
-        x = x.detach().to(torch.float32).contiguous()
+        if x.dtype == torch.uint8:
+            assert norm is not None, "uint8 frames need the dataset's (mean, std)"
+            x = x.detach().contiguous()
+        else:
+            x, norm = x.detach().to(torch.float32).contiguous(), None
         cur = ws.h16("stem", self.dt, frames * H * W, self.ngf)
-        op.conv7x7_stem(x, self.stem_w, self.stem_shift, cur, Cin, self.ngf, H, W)
+        op.conv7x7_stem(x, self.stem_w, self.stem_shift, cur, Cin, self.ngf, H, W, norm=norm)
         C = self.ngf
         cur = self._conv3x3(cur, frames, H, W, C, self.down[0], 2, PAD_ZERO, "down0", act=ACT_RELU)
         H, W, C = H // 2, W // 2, C * 2
@@ -191,8 +197,11 @@ class DecoderEngine:
             bias = bias + (scale * convt.bias.detach().float()).repeat(4)
         return _h(B.reshape(4 * Cout, 4 * Cin), dt), bias.contiguous(), Cin, Cout
 
-    def run(self, x, channels_last=False):
-        """x: (N,T,C,h,w) fp32, or channels-last (N,T,h,w,C) fp32/bf16 -> frames (N,T,Cimg,H,W) fp32."""
+    def run(self, x, channels_last=False, renorm=None, want_f32=True):
+        """x: (N,T,C,h,w) fp32, or channels-last (N,T,h,w,C) fp32/bf16 -> frames (N,T,Cimg,H,W) fp32.
+        ``renorm`` = (mean, std): the head kernel ALSO writes the pixel-space uint8 frames (VidReNormalize + clamp + ToPILImage's
+        truncation fused into its epilogue, utils/dataset.py:860-886, utils/train_summary.py:243-248) and the call returns
+        (frames | None, frames_u8); ``want_f32=False`` skips the fp32 frames."""
         op, ws = _lib.ops(), self.ws
         N, T = x.shape[0], x.shape[1]
         frames = N * T
@@ -219,6 +228,7 @@ class DecoderEngine:
                 op.im2col(cur, col, frames, H, W, Cin, 2, 2, 1, 0, PAD_ZERO, H, W, phase_major=phase)
                 op.gemm(col, w, bias=b, act=ACT_RELU, out_bf16=nxt)
             cur, H, W, phase = nxt, 2 * H, 2 * W, True
-        out = torch.empty(N, T, self.cout, H, W, dtype=torch.float32, device=self.device)
-        op.conv7x7_head(cur, self.head_w, self.head_b, out, self.head_cin, self.cout, H, W, phase, self.act)
-        return out
+        out = torch.empty(N, T, self.cout, H, W, dtype=torch.float32, device=self.device) if (want_f32 or renorm is None) else None
+        out_u8 = torch.empty(N, T, self.cout, H, W, dtype=torch.uint8, device=self.device) if renorm is not None else None
+        op.conv7x7_head(cur, self.head_w, self.head_b, out, self.head_cin, self.cout, H, W, phase, self.act, out_u8=out_u8, renorm=renorm)
+        return out if renorm is None else (out, out_u8)

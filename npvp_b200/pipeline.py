@@ -138,13 +138,22 @@ class NPVPInference(nn.Module):
         return rec_past, rec_future, pred
 
     # -- throughput path: Enc(context) -> Predictor -> Dec(predictions), channels-last in between ----
-    def _predict_eager(self, past_frames, eps):
+    def _norm_constants(self):
+        """(mean, std) of VidNormalize for uint8 input frames (utils/dataset.py:34-58, 846-858)."""
+        if self.cfg.AE.out_layer == "Sigmoid":
+            return self._renorm_constants()
+        return NORM.get(self.cfg.Dataset.name, RENORM[self.cfg.Dataset.name])
+
+    def _predict_eager(self, past_frames, eps, pixels_u8=False):
+        """``past_frames`` uint8: pixels, normalised inside the encoder stem.  ``pixels_u8``: the decoder head also writes the
+        pixel-space uint8 frames -> (frames, frames_u8)."""
         self.predictor.injected_eps = eps
         try:
-            self.predictor.prefetch_positional()       # side stream: overlaps with the frame encoder
-            feats = self.VPTR_Enc.forward_tokens(past_frames)
+            self.predictor.prefetch_positional()
+            norm = self._norm_constants() if past_frames.dtype == torch.uint8 else None
+            feats = self.VPTR_Enc.forward_tokens(past_frames, norm=norm)
             pred = self.predictor.forward_tokens(feats, out16=self.VPTR_Dec._engine().dt)
-            return self.VPTR_Dec.forward_tokens(pred)
+            return self.VPTR_Dec.forward_tokens(pred, renorm=self._renorm_constants() if pixels_u8 else None)
         finally:
             self.predictor.injected_eps = None
 
@@ -191,25 +200,28 @@ class NPVPInference(nn.Module):
         self._graphs = {} if enabled else None
         return self
 
-    def _graph_key(self, x):
+    def _graph_key(self, x, pixels_u8=False):
         p = self.predictor
-        return (tuple(x.shape), x.device, tuple(p.observed_coor.shape), tuple(p.predict_coor.shape), int(getattr(p, "_coor_clips", 0)),
+        return (tuple(x.shape), x.dtype == torch.uint8, bool(pixels_u8), x.device, tuple(p.observed_coor.shape), tuple(p.predict_coor.shape), int(getattr(p, "_coor_clips", 0)),
                 self.VPTR_Enc._weights_version(), self.VPTR_Dec._weights_version(), p._weights_version())
 
     @_on_model_device
-    def predict(self, past_frames, eps: Optional[torch.Tensor] = None):
-        """past_frames (N,To,Cimg,H,W) fp32 CUDA -> predicted frames (N,Tp,Cimg,H,W) fp32.
+    def predict(self, past_frames, eps: Optional[torch.Tensor] = None, pixels_u8: bool = False):
+        """past_frames (N,To,Cimg,H,W) CUDA -> predicted frames (N,Tp,Cimg,H,W) fp32 (model space, like the reference modules).
+        ``past_frames`` may be uint8 pixels (what a video decoder delivers): VidToTensor + VidNormalize then run inside the
+        encoder's stem kernel.  ``pixels_u8=True``: returns (frames, frames_u8) where frames_u8 are the pixel-space uint8
+        frames the reference would write to image files (VidReNormalize + clamp + ToPILImage, fused into the decoder head).
         ``eps``: optional injected latent noise (N,512,8,8) for NPVP-S (default: torch.randn like the reference)."""
         graphs = getattr(self, "_graphs", None)
         if graphs is None:
-            return self._predict_eager(past_frames, eps)
+            return self._predict_eager(past_frames, eps, pixels_u8)
         self.predictor._coords_ready()
-        key = self._graph_key(past_frames)
+        key = self._graph_key(past_frames, pixels_u8)
         g = graphs.pop(key, None)
         if g is None:
             while len(graphs) >= self.MAX_GRAPHS:            # evict the least recently used captured forward (and its pool)
                 graphs.pop(next(iter(graphs)))
-            g = _GraphedPredict(self, past_frames)
+            g = _GraphedPredict(self, past_frames, pixels_u8)
         graphs[key] = g                                       # (re-)insert as most recently used
         return g(past_frames, eps)
 
@@ -285,6 +297,7 @@ class NPVPInference(nn.Module):
                 gatherer = BlockGather(group, gather_dst, num_future)
         out, ctx, done, blk = None, past_frames, 0, 0
         assert last_block in ("truncate", "query")
+        want_u8 = as_u8 or (gatherer is not None and gather_dtype == torch.uint8)
         while done < num_future:
             eps = None if eps_list is None else eps_list[blk]
             take = min(Tp, num_future - done)
@@ -293,19 +306,19 @@ class NPVPInference(nn.Module):
                 saved = (p.predict_coor, p.TP)
                 p.predict_coor, p.TP = self._short_block_coor(take), take
                 try:
-                    pred = self.predict(ctx, eps)
+                    pred = self.predict(ctx, eps, pixels_u8=want_u8)
                 finally:
                     p.predict_coor, p.TP = saved
             else:
-                pred = self.predict(ctx, eps)                # may be a graph-owned buffer: copy out before the next block
+                pred = self.predict(ctx, eps, pixels_u8=want_u8)   # may be graph-owned buffers: copied out before the next block
+            if want_u8:                                      # pixel-space uint8 frames from the decoder head's fused epilogue
+                pred, pred_u8 = pred
             if out is None:
                 out = torch.empty((pred.shape[0], num_future) + tuple(pred.shape[2:]), dtype=pred.dtype, device=pred.device)
             out[:, done:done + take].copy_(pred[:, :take])
             src, s0 = out, done
-            if as_u8 or (gatherer is not None and gather_dtype == torch.uint8):
-                mean, std = self._renorm_constants()        # one kernel per block on the whole (N, Tp, C, H, W) prediction
-                out_u8 = torch.empty(pred.shape, dtype=torch.uint8, device=pred.device)
-                _lib.ops().frames_to_pixels(pred.contiguous(), mean, std, out_u8=out_u8)
+            if want_u8:
+                out_u8 = pred_u8.clone() if getattr(self, "_graphs", None) is not None else pred_u8   # graph-owned: the next block overwrites it
             if as_u8:
                 src, s0 = out_u8, 0
             if copy_stream is not None:                      # D2H of this block overlaps the next block's kernels
@@ -386,10 +399,10 @@ class _GraphedPredict:
     (``slots``): the NRMLP tables the captured kernels read are recomputed in place - eagerly, before the replay - when the
     predictor's coordinates have changed since the last call, so the graph does not depend on the timestamps."""
 
-    def __init__(self, model: NPVPInference, example: torch.Tensor):
-        self.model = model
+    def __init__(self, model: NPVPInference, example: torch.Tensor, pixels_u8: bool = False):
+        self.model, self.pixels_u8 = model, bool(pixels_u8)
         self.stochastic = bool(model.predictor.stochastic)
-        self.x = torch.empty_like(example, dtype=torch.float32).contiguous()
+        self.x = torch.empty_like(example, dtype=torch.uint8 if example.dtype == torch.uint8 else torch.float32).contiguous()
         self.x.copy_(example)
         n = example.shape[0]
         self.eps = torch.zeros((n, 512, 8, 8), device=example.device) if self.stochastic else None
@@ -409,7 +422,7 @@ class _GraphedPredict:
     def _run(self):
         self.eng._graph_slots = self.slots
         try:
-            return self.model._predict_eager(self.x, self.eps)
+            return self.model._predict_eager(self.x, self.eps, self.pixels_u8)
         finally:
             self.eng._graph_slots = None
 

@@ -285,21 +285,31 @@ class SpecOps:
             return x.reshape(frames, H, W, Cc)
         return x.reshape(frames, H // 2, W // 2, 2, 2, Cc).permute(0, 1, 3, 2, 4, 5).reshape(frames, H, W, Cc)
 
-    def conv7x7_stem(self, x, w, shift, out, Cin, Cout, H, W):
+    def conv7x7_stem(self, x, w, shift, out, Cin, Cout, H, W, norm=None):
         self.launches += 1
+        if x.dtype == torch.uint8:                 # VidToTensor + VidNormalize, reference operation order
+            m = torch.tensor([float(v) for v in norm[0]], dtype=torch.float32, device=x.device).view(Cin, 1, 1)
+            sdv = torch.tensor([float(v) for v in norm[1]], dtype=torch.float32, device=x.device).view(Cin, 1, 1)
+            x = (x.reshape(-1, Cin, H, W).to(torch.float32).div(255) - m) / sdv
         img = x.reshape(-1, Cin, H, W)
         wt = w.reshape(7, 7, Cin, Cout).permute(3, 2, 0, 1)
         o = F.conv2d(F.pad(img, (3, 3, 3, 3), mode="reflect"), wt, shift)
         out.copy_(torch.relu(o).permute(0, 2, 3, 1).reshape(out.shape).to(out.dtype))
 
-    def conv7x7_head(self, x, w, bias, out, Cin, Cout, H, W, phase_major, act):
+    def conv7x7_head(self, x, w, bias, out, Cin, Cout, H, W, phase_major, act, out_u8=None, renorm=None):
         self.launches += 1
         frames = x.numel() // (Cin * H * W)
         img = self._unphase(x.float(), frames, H, W, Cin, phase_major).permute(0, 3, 1, 2)
         from npvp_b200._lib import unpack_head_weights
         wt = unpack_head_weights(w, Cout).reshape(7, 7, Cin, Cout).permute(3, 2, 0, 1)   # 16-bit packed weights (mma B fragments)
-        o = F.conv2d(F.pad(img, (3, 3, 3, 3), mode="reflect"), wt, bias)
-        out.copy_(_act(o, act).reshape(out.shape))
+        o = _act(F.conv2d(F.pad(img, (3, 3, 3, 3), mode="reflect"), wt, bias), act)
+        if out is not None:
+            out.copy_(o.reshape(out.shape))
+        if out_u8 is not None:                      # VidReNormalize + clamp + ToPILImage (truncation), reference operation order
+            inv_std = torch.tensor([1.0 / float(v) for v in renorm[1]], dtype=torch.float32, device=o.device).view(1, Cout, 1, 1)
+            inv_mean = torch.tensor([-float(v) for v in renorm[0]], dtype=torch.float32, device=o.device).view(1, Cout, 1, 1)
+            p = ((o / inv_std) - inv_mean).clamp(0.0, 1.0)
+            out_u8.copy_(p.mul(255).to(torch.uint8).reshape(out_u8.shape))
 
     def im2col(self, x, out, frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo, phase_major=False):
         self.launches += 1

@@ -140,3 +140,53 @@ def test_predict_best_of_k_pipeline():
     assert torch.equal(best, gt)
     _, idx_s, _ = model.predict_best_of_k(x, gt, 8, "ssim", eps)
     assert idx_s.tolist() == [5, 2]
+
+
+@pytest.mark.parametrize("preset_name", ["KITTI_VFP_NPVP-S", "SMMNIST_VFP_NPVP-D", "KTH_Unified_NPVP-S"])
+def test_fused_pixel_ingest_and_epilogue(preset_name):
+    """uint8 frames in (VidToTensor + VidNormalize inside the encoder's stem kernel) and uint8 frames out
+    (VidReNormalize + clamp + ToPILImage's truncation inside the decoder's head kernel) are bit-identical to the stand-alone
+    conversion kernels, which are bit-identical to the reference transforms (test_pixels_bit_exact_vs_reference)."""
+    from npvp_b200.pipeline import build_from_config
+    from util_init import stress_init_
+    model = build_from_config(preset_name, device="cpu", seed=0)
+    stress_init_(model.VPTR_Enc, 1)
+    stress_init_(model.VPTR_Dec, 2)
+    model = model.cuda()
+    cfg = model.cfg
+    To, ch, hw = cfg.Dataset.num_past_frames, cfg.Dataset.img_channels, cfg.Dataset.img_size
+    if cfg.Predictor.rand_context:
+        model.predictor.reset_pos_coor(model.to_list, model.tp_list)
+    u8 = torch.randint(0, 256, (2, To, ch, hw, hw), dtype=torch.uint8, generator=torch.Generator().manual_seed(4)).cuda()
+    eps = torch.randn(2, 512, 8, 8, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    x = model.from_pixels(u8)                                         # stand-alone kernel (reference operation order)
+    # encoder: features of the uint8 frames == features of the normalised fp32 frames
+    assert torch.equal(model.VPTR_Enc.forward_tokens(u8, norm=model._norm_constants()), model.VPTR_Enc.forward_tokens(x))
+    # whole path, eager and captured: frames identical, fused uint8 == to_pixels(frames, uint8=True)
+    ref = model.predict(x, eps)
+    for graphs in (False, True):
+        model.use_cuda_graphs(graphs)
+        frames, frames_u8 = model.predict(u8, eps, pixels_u8=True)
+        assert frames_u8.dtype == torch.uint8 and torch.equal(frames, ref)
+        assert torch.equal(frames_u8, model.to_pixels(ref, uint8=True))
+    model.use_cuda_graphs(False)
+    only_u8 = model.VPTR_Dec.forward_tokens(model.predictor.forward_tokens(model.VPTR_Enc.forward_tokens(x), out16=model.VPTR_Dec._engine().dt),
+                                            renorm=model._renorm_constants(), want_f32=False)
+    assert only_u8[0] is None
+
+
+def test_rollout_uint8_host_buffers_use_fused_epilogue():
+    """rollout with a uint8 host input and a uint8 host output: pixels in, pixels out, equal to the fp32 rollout converted afterwards."""
+    from npvp_b200.pipeline import build_from_config
+    model = build_from_config("BAIR_VFP_NPVP-S", device="cuda", seed=0)
+    u8 = torch.randint(0, 256, (2, 2, 3, 64, 64), dtype=torch.uint8, generator=torch.Generator().manual_seed(4))
+    eps = [torch.randn(2, 512, 8, 8, device="cuda", generator=torch.Generator("cuda").manual_seed(i)) for i in range(3)]
+    ref = model.rollout(model.from_pixels(u8.cuda()), 28, eps, last_block="query")
+    ref_u8 = model.to_pixels(ref, uint8=True).cpu()
+    host_in, host_out = u8.pin_memory(), torch.empty((2, 28, 3, 64, 64), dtype=torch.uint8).pin_memory()
+    for graphs in (False, True):
+        model.use_cuda_graphs(graphs)
+        host_out.zero_()
+        out = model.rollout(host_in, 28, eps, out_host=host_out, last_block="query")
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref) and torch.equal(host_out, ref_u8)
