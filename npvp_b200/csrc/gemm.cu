@@ -847,6 +847,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   ptx::tc_fence_before();
+  __syncthreads();                                           // CTA-local: the TMEM address written by tcgen05.alloc is visible (racecheck-clean)
   cluster_sync_all();                                        // barriers of both CTAs are initialised before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
