@@ -41,8 +41,9 @@ __device__ __forceinline__ void mma_16816_stem(float (&c)[4], const uint32_t (&a
 
 struct StemNorm { float mean[3], std[3]; };
 
+// (r02 ncu: 139 registers allowed ONE 256-thread block per SM - 12% of the warp slots, 28% of the issue slots; capped at 128)
 template <int CIN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv7x7_stem_kernel(const float* __restrict__ x, const uint8_t* __restrict__ x_u8, StemNorm nrm, const float* __restrict__ w,
                     const float* __restrict__ shift, h16* __restrict__ out, int Cout, int H, int W, int fp16) {
   __shared__ __align__(16) h16 tile[kStemTY + 6][kStemTW][4];        // 8 KB
@@ -459,15 +460,23 @@ nonlocal_attention_kernel(const h16* __restrict__ q, int64_t ldq, const h16* __r
         mma_16816(sc[t], qa[ks], b0, b1, fp16);
       }
     }
-    // ---- online softmax (log2 domain) ----
+    // ---- online softmax: row maxima on the raw scores, p = 2^(s log2e - m log2e) as ONE FFMA + ONE MUFU per element.
+    // Only a ragged last key tile needs masking (r02 ncu at the 64x64 stage: 224 M warp instructions per launch, the
+    // per-element FMUL + 2 selects + FSUB of the first version were a quarter of them).
     float bm0 = -INFINITY, bm1 = -INFINITY;
+    if (nk < KT) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool dead = (8 * t + 2 * tig + e) >= nk;
+          if (dead) { sc[t][e] = -INFINITY; sc[t][2 + e] = -INFINITY; }
+        }
+    }
 #pragma unroll
     for (int t = 0; t < 8; ++t)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const bool dead = (8 * t + 2 * tig + e) >= nk;
-        sc[t][e] = dead ? -INFINITY : sc[t][e] * kLog2e;
-        sc[t][2 + e] = dead ? -INFINITY : sc[t][2 + e] * kLog2e;
         bm0 = fmaxf(bm0, sc[t][e]);
         bm1 = fmaxf(bm1, sc[t][2 + e]);
       }
@@ -475,7 +484,7 @@ nonlocal_attention_kernel(const h16* __restrict__ q, int64_t ldq, const h16* __r
     bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
     bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
     bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-    const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+    const float mn0 = fmaxf(m0, bm0 * kLog2e), mn1 = fmaxf(m1, bm1 * kLog2e);   // running maxima in the log2 domain
     const float c0 = ex2_approx(m0 - mn0), c1 = ex2_approx(m1 - mn1);     // 0 on the first tile (m = -inf)
     m0 = mn0; m1 = mn1;
     float s0 = 0.f, s1 = 0.f;
@@ -483,7 +492,7 @@ nonlocal_attention_kernel(const h16* __restrict__ q, int64_t ldq, const h16* __r
     for (int t = 0; t < 8; ++t)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const float p0 = ex2_approx(sc[t][e] - mn0), p1 = ex2_approx(sc[t][2 + e] - mn1);   // ex2(-inf) = 0 for dead keys
+        const float p0 = ex2_approx(fmaf(sc[t][e], kLog2e, -mn0)), p1 = ex2_approx(fmaf(sc[t][2 + e], kLog2e, -mn1));   // ex2(-inf) = 0 for dead keys
         sc[t][e] = p0; sc[t][2 + e] = p1;
         s0 += p0; s1 += p1;
       }
