@@ -138,6 +138,7 @@ class Ops:
                              "tcgen05_2cta": GEMM_TCGEN05_2CTA}[os.environ.get("NPVP_B200_GEMM", "auto")]
         self.lib.npvp_set_option(b"gemm_2cta", int(os.environ.get("NPVP_B200_GEMM_2CTA", "-1")))
         self.lib.npvp_set_option(b"gemm_epi_direct", int(os.environ.get("NPVP_B200_GEMM_EPI_DIRECT", "0")))
+        self.lib.npvp_set_option(b"ffn_mid16_mode", int(os.environ.get("NPVP_B200_FFN_MID16_MODE", "0")))
 
     # -- plumbing -------------------------------------------------------------------------------
     def _stream(self):

@@ -6,8 +6,8 @@
 // FMA pipe, not by HBM: ~54 FMA-pipe cycles per channel pair and pixel in packed fp32 (FFMA2 retires 64 lanes per clock)
 // = 64 us per 640 frames before any memory time.  Here
 //   * all element-wise math is half2 (HFMA2: 2 values per lane per issue slot at full rate), statistics stay fp32 / fp64;
-//   * GELU(x) = max(x, 0) - |x| 2^P3(|x|) with a cubic P3 (all coefficients negative: no overflow hazards), 8 issue slots
-//     per pair (3 HFMA2 + 2 MUFU.EX2 + PRMT + HMNMX2 + HFMA2); max |error| 1.0e-3 at |x| ~ 2.8 = one half ulp of the result;
+//   * GELU(x) = max(x, 0) - |x| 2^P2(|x|) with a quadratic P2 (all coefficients negative: no overflow hazards), 7 issue slots
+//     per pair (3 HFMA2 + 2 MUFU.EX2 + PRMT + HMNMX2); max |error| 1.4e-3 at |x| ~ 2.7 (half an ulp of the result is 1e-3);
 //   * h1 is read once and the result written once (4 B per element): a warp owns 64 channels (one pair per lane) of one
 //     frame; its 64 px x 64 ch tile (8 KB of shared memory) is filled by 16-byte cp.async one frame ahead, overwritten in
 //     place by the depthwise-conv output, and kept there while the LN2 statistics of the frame are gathered from the 32
@@ -29,11 +29,13 @@ constexpr int kTok = 64;
 constexpr int kCh = 2048;                  // hidden width (Spatial_FFN_hidden_ratio 4 x embed 512: NPVP's only one)
 constexpr int kChunkCh = 64;               // channels per warp / block (one half2 pair per lane)
 constexpr int kChunks = kCh / kChunkCh;    // 32 = number of partial statistics per frame = warp size
-constexpr int kWarps = 4;                  // frame streams per block (each with two 8 KB tiles)
-constexpr int kThreads = kWarps * 32;
+// Two schedules (template parameters TILES, WARPS of the kernel):
+//   <2, 4> (default): two 8 KB tiles per warp, per-warp software pipeline (below), 2 x 4 warps per SM
+//   <1, 8>          : one tile per warp, ph1 and ph2 of a frame back to back, 2 x 8 warps per SM whose frame periods are
+//                     staggered at kernel entry so that the rendezvous of one warp is covered by the others of its scheduler
 constexpr int kParamBytes = 2 * kTok * 32 * 8;            // [2 norms][64 px][32 pairs] (w2, b2) half2 x 2
-constexpr int kY2Bytes = kWarps * 2 * kTok * 32 * 4;      // [4 warps][2 tiles][64 px][32 pairs] half2
-constexpr int kSmemBytes = kParamBytes + kY2Bytes;        // 96 KB -> two blocks per SM
+constexpr int kTileBytes = kTok * 32 * 4;                 // [64 px][32 pairs] half2 = 8 KB
+constexpr int smem_bytes(int tiles, int warps) { return kParamBytes + warps * tiles * kTileBytes; }   // 96 KB -> two blocks per SM
 constexpr float kEps = 1e-5f;
 
 typedef uint32_t h2;                                       // packed half2 bits
@@ -50,19 +52,36 @@ __device__ __forceinline__ h2 h2_bcast(float v) {
 }
 __device__ __forceinline__ float2 h2_to_f2(h2 a) { return __half22float2(*reinterpret_cast<const __half2*>(&a)); }
 
-// log2(0.5 erfc(u / sqrt 2)) ~ P3(u) on [0, 6], weighted least squares on the GELU error u 2^P ln2 dP (max 1.0e-4 in exact
-// arithmetic, 1.0e-3 = half an ulp of the result once everything is rounded to half).  All four coefficients are negative,
-// so for large |x| the Horner chain runs monotonically to -inf and 2^P to 0: no clamp, no inf - inf.
-constexpr uint32_t kC3 = 0xA5F4A5F4u;   // -0.02325
-constexpr uint32_t kC2 = 0xB80AB80Au;   // -0.50492
-constexpr uint32_t kC1 = 0xBC7EBC7Eu;   // -1.12272
-constexpr uint32_t kC0 = 0xBC06BC06u;   // -1.00544
+// log2(0.5 erfc(u / sqrt 2)) ~ P2(u) = c2 u^2 + c1 u + c0, minimax on the GELU error u 2^P (4.4e-4 in exact arithmetic; 1.4e-3
+// max / 1.7e-4 mean once every step is rounded to half - the result's own rounding, half an ulp = 1e-3 at |x| ~ 3, dominates,
+// which is why the cubic, 1.0e-3 max / 0.9e-4 mean, buys nothing for its extra HFMA2).  All coefficients are negative, so
+// for large |x| the Horner chain runs monotonically to -inf and 2^P to 0: no clamp, no inf - inf.
+// Cost per PAIR: 3 HFMA2 + 2 MUFU.EX2.F16 + PRMT + HMNMX2 = 7 issue slots.  Measured on B200 (tools/ubench/hfma2.cu): HFMA2
+// issues at 0.5 / clk / sub-partition - two values per lane at half the instruction rate, i.e. the SAME 128 FMA lanes per clock
+// per SM as scalar FFMA or packed FFMA2 - and MUFU.EX2.F16 at 1 / 8 clk, so every HFMA2 saved is 2 pipe cycles: the
+// kernel's ceiling is the FMA pipe (~23 FMA-pipe instructions per pair and pixel), not issue slots and not HBM.
+constexpr uint32_t kC2 = 0xB8A9B8A9u;   // -0.58239
+constexpr uint32_t kC1 = 0xBC35BC35u;   // -1.05181
+constexpr uint32_t kC0 = 0xBC16BC16u;   // -1.02189
 __device__ __forceinline__ h2 gelu_h2(h2 x) {
   const h2 u = habs2(x);
-  h2 p = hfma2(u, kC3, kC2);
-  p = hfma2(p, u, kC1);
+  h2 p = hfma2(u, kC2, kC1);
   p = hfma2(p, u, kC0);
   return hfma2(hneg2(u), hex2(p), hmax2_0(x));
+}
+
+// the same GELU on N values, the N dependency chains advanced one step at a time
+template <int N>
+__device__ __forceinline__ void gelu_h2_xN(h2 (&x)[N]) {
+  h2 p[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = hfma2(habs2(x[i]), kC2, kC1);
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = hfma2(p[i], habs2(x[i]), kC0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = hex2(p[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = hfma2(hneg2(habs2(x[i])), p[i], hmax2_0(x[i]));
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -103,14 +122,16 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {           // n is a c
 // and the skew between the 32 SMs that share a frame are hidden by construction, not by occupancy.  (r02 ncu of the
 // unpipelined version with 16 warps per SM: all warps of an SM reach the rendezvous together, 37% of the stall samples in the
 // poll loop, 23% on the partial-statistics load at the head of a frame, 38% of the issue slots used.)
-__global__ void __launch_bounds__(kThreads, 2)
+template <int TILES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
 ffn_mid16_kernel(const __half* __restrict__ h1, const float2* __restrict__ part1, const uint2* __restrict__ ln_wb,
                  const __half* __restrict__ dw_w, const __half* __restrict__ dw_b, __half* __restrict__ out,
                  float2* __restrict__ xch, unsigned int* __restrict__ cnt, int frames) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint2* s_wb = reinterpret_cast<uint2*>(smem);                               // [2][64][32]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  h2* s_tiles = reinterpret_cast<h2*>(smem + kParamBytes) + warp * (2 * kTok * 32);   // [2 tiles][64 px][32 pairs] of this warp
+  constexpr int kWarps = WARPS, kThreads = WARPS * 32;
+  h2* s_tiles = reinterpret_cast<h2*>(smem + kParamBytes) + warp * (TILES * kTok * 32);   // [TILES][64 px][32 pairs] of this warp
   const int chunk = blockIdx.x;
   const int c0 = chunk * kChunkCh + 2 * lane;
 
@@ -161,44 +182,59 @@ ffn_mid16_kernel(const __half* __restrict__ h1, const float2* __restrict__ part1
     // bound by per-warp dependency latency (r02 ncu: 1.1 `wait` stall cycles per issue with 8 chains), not by issue slots
     h2 g[4][8];                                                      // GELU(LN1) rows, row r lives in g[r & 3]
     f32x2 s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
-    auto conv_row = [&](int orow) {                                  // conv output row from g rows orow - 1, orow, orow + 1: in place over h1
+    auto conv_rows = [&](int o0, int n) {                            // conv output rows o0 .. o0 + n - 1 (n <= 2), tap-major: 8 n independent chains
+      h2 acc[2][8];
 #pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        h2 acc = bias;
+      for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int iy = orow + ky - 1;
-          if (iy < 0 || iy > 7) continue;
+        for (int x = 0; x < 8; ++x) acc[j][x] = bias;
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int ix = x + kx - 1;
-            if (ix >= 0 && ix <= 7) acc = hfma2(g[iy & 3][ix], w[ky * 3 + kx], acc);
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (j >= n) continue;
+            const int iy = o0 + j + ky - 1;
+            if (iy < 0 || iy > 7) continue;
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+              const int ix = x + kx - 1;
+              if (ix >= 0 && ix <= 7) acc[j][x] = hfma2(g[iy & 3][ix], w[ky * 3 + kx], acc[j][x]);
+            }
           }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (j >= n) continue;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {                                // in place over h1 (row o0 + j <= the rows already consumed)
+          tile[((o0 + j) * 8 + x) * 32 + lane] = acc[j][x];
+          const float2 a = h2_to_f2(acc[j][x]);
+          const f32x2 a2 = pk2(a.x, a.y);
+          s2 = add2(s2, a2);
+          q2 = fma2(a2, a2, q2);
         }
-        tile[(orow * 8 + x) * 32 + lane] = acc;
-        const float2 a = h2_to_f2(acc);
-        const f32x2 a2 = pk2(a.x, a.y);
-        s2 = add2(s2, a2);
-        q2 = fma2(a2, a2, q2);
       }
     };
 #pragma unroll
     for (int rp = 0; rp < 4; ++rp) {
       cp_async_wait_dyn(6 - 2 * rp);                                 // image rows 0 .. 2 rp + 1 of this frame have landed
       __syncwarp();
+      h2 v[16];
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int r = 2 * rp + rr;
+      for (int i = 0; i < 16; ++i) v[i] = hfma2(tile[(rp * 16 + i) * 32 + lane], rs1, nm1);
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-          const uint2 wb = s_wb[(r * 8 + x) * 32 + lane];
-          g[r & 3][x] = gelu_h2(hfma2(hfma2(tile[(r * 8 + x) * 32 + lane], rs1, nm1), wb.x, wb.y));
-        }
+      for (int i = 0; i < 16; ++i) {
+        const uint2 wb = s_wb[(rp * 16 + i) * 32 + lane];
+        v[i] = hfma2(v[i], wb.x, wb.y);
       }
-      if (rp > 0) conv_row(2 * rp - 1);
-      conv_row(2 * rp);
+      gelu_h2_xN<16>(v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) g[(2 * rp + (i >> 3)) & 3][i & 7] = v[i];
+      if (rp > 0) conv_rows(2 * rp - 1, 2);
+      else conv_rows(0, 1);
     }
-    conv_row(7);
+    conv_rows(7, 1);
     float s_lo, s_hi, q_lo, q_hi;
     upk2(s2, s_lo, s_hi);
     upk2(q2, q_lo, q_hi);
@@ -236,12 +272,15 @@ ffn_mid16_kernel(const __half* __restrict__ h1, const float2* __restrict__ part1
     for (int r = 0; r < 8; r += 2) {                                 // two image rows (16 independent chains) per iteration
       h2 y[16];
 #pragma unroll
-      for (int x = 0; x < 16; ++x) y[x] = tile[(r * 8 + x) * 32];
+      for (int x = 0; x < 16; ++x) y[x] = hfma2(tile[(r * 8 + x) * 32], rs2, nm2);
 #pragma unroll
       for (int x = 0; x < 16; ++x) {
         const uint2 wb = wb2[(r * 8 + x) * 32];
-        dst[(size_t)(r * 8 + x) * (kCh / 2)] = gelu_h2(hfma2(hfma2(y[x], rs2, nm2), wb.x, wb.y));
+        y[x] = hfma2(y[x], wb.x, wb.y);
       }
+      gelu_h2_xN<16>(y);
+#pragma unroll
+      for (int x = 0; x < 16; ++x) dst[(size_t)(r * 8 + x) * (kCh / 2)] = y[x];
       __syncwarp();                                                  // every lane has read these rows of y2
       if (f_pre < frames) prefetch_row(f_pre, t, r);
       asm volatile("cp.async.commit_group;" ::: "memory");          // always: ph1 counts on 8 groups per ph2
@@ -254,6 +293,20 @@ ffn_mid16_kernel(const __half* __restrict__ h1, const float2* __restrict__ part1
     }
   };
 
+  if (TILES == 1) {
+    // single tile: ph1(f) | rendezvous | ph2(f) (refilling the tile with the next frame).  The warps of a block start their
+    // first frame one eighth of a frame period apart, so the rendezvous latency of one is hidden by its scheduler's others.
+    __nanosleep(1200u * (unsigned)warp);
+#pragma unroll 1
+    for (int f = f0; f < frames; f += stride) {
+      const float2 p1_now = p1;
+      if (f + stride < frames) p1 = __ldg(part1 + (size_t)(f + stride) * kChunks + lane);
+      phase1(f, 0, p1_now);
+      phase2(f, 0, f + stride);
+    }
+    cp_async_wait<0>();
+    return;
+  }
   int t = 0;
 #pragma unroll 1
   for (int f = f0;; f += stride, t ^= 1) {                            // f: frame of this step's ph1 (tile t); ph2 of the previous frame
@@ -277,24 +330,33 @@ ffn_mid16_kernel(const __half* __restrict__ h1, const float2* __restrict__ part1
   cp_async_wait<0>();
 }
 
-int g_mid16_lanes = -1;       // blockIdx.y extent that keeps the whole grid co-resident (0: kernel does not fit)
+int g_mid16_lanes[2] = {-1, -1};   // per schedule: blockIdx.y extent that keeps the whole grid co-resident (0: does not fit)
+int g_mid16_mode = 0;              // npvp_set_option("ffn_mid16_mode", m): 0 = <2 tiles, 4 warps> pipelined, 1 = <1 tile, 8 warps> staggered
+
+template <int TILES, int WARPS>
+int mid16_lanes_of() {
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaFuncSetAttribute(ffn_mid16_kernel<TILES, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(TILES, WARPS)) == cudaSuccess &&
+      cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffn_mid16_kernel<TILES, WARPS>, WARPS * 32, smem_bytes(TILES, WARPS)) == cudaSuccess)
+    return sms * per_sm / kChunks;
+  return 0;
+}
 
 void mid16_setup() {
-  if (g_mid16_lanes >= 0) return;
-  g_mid16_lanes = 0;
-  int dev = 0, sms = 0, per_sm = 0;
-  if (cudaFuncSetAttribute(ffn_mid16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) == cudaSuccess &&
-      cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffn_mid16_kernel, kThreads, kSmemBytes) == cudaSuccess)
-    g_mid16_lanes = sms * per_sm / kChunks;
+  if (g_mid16_lanes[0] >= 0) return;
+  g_mid16_lanes[0] = mid16_lanes_of<2, 4>();
+  g_mid16_lanes[1] = mid16_lanes_of<1, 8>();
   cudaGetLastError();
 }
 
 }  // namespace
 
+void npvp_set_ffn_mid16_mode(int m) { g_mid16_mode = m ? 1 : 0; }
+
 extern "C" int npvp_ffn_mid16_lanes(void) {
   mid16_setup();
-  return g_mid16_lanes;
+  return g_mid16_lanes[g_mid16_mode];
 }
 
 extern "C" int npvp_ffn_mid16(const void* h1_f16, const float* part1, const void* ln_wb_f16, const void* dw_w_f16, const void* dw_b_f16,
@@ -306,13 +368,18 @@ extern "C" int npvp_ffn_mid16(const void* h1_f16, const float* part1, const void
   NPVP_REQUIRE(((uintptr_t)xch & 255) == 0 && ((uintptr_t)ln_wb_f16 & 15) == 0 && ((uintptr_t)h1_f16 & 3) == 0 && ((uintptr_t)out_f16 & 3) == 0,
                "npvp_ffn_mid16: xch must be 256-byte aligned, parameters 16-byte aligned");
   mid16_setup();
-  NPVP_REQUIRE(g_mid16_lanes > 0, "npvp_ffn_mid16: the kernel does not fit on this device");
-  const int64_t want = (frames + kWarps - 1) / kWarps;
-  const int64_t lanes = want > g_mid16_lanes ? g_mid16_lanes : want;
+  const int mode = g_mid16_mode;
+  NPVP_REQUIRE(g_mid16_lanes[mode] > 0, "npvp_ffn_mid16: the kernel does not fit on this device");
+  const int warps = mode ? 8 : 4;
+  const int64_t want = (frames + warps - 1) / warps;
+  const int64_t lanes = want > g_mid16_lanes[mode] ? g_mid16_lanes[mode] : want;
   dim3 grid(kChunks, (unsigned)lanes);
-  ffn_mid16_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>((const __half*)h1_f16, (const float2*)part1, (const uint2*)ln_wb_f16,
-                                                                         (const __half*)dw_w_f16, (const __half*)dw_b_f16, (__half*)out_f16,
-                                                                         (float2*)xch, cnt, (int)frames);
+  if (mode)
+    ffn_mid16_kernel<1, 8><<<grid, 8 * 32, smem_bytes(1, 8), (cudaStream_t)stream>>>((const __half*)h1_f16, (const float2*)part1, (const uint2*)ln_wb_f16,
+        (const __half*)dw_w_f16, (const __half*)dw_b_f16, (__half*)out_f16, (float2*)xch, cnt, (int)frames);
+  else
+    ffn_mid16_kernel<2, 4><<<grid, 4 * 32, smem_bytes(2, 4), (cudaStream_t)stream>>>((const __half*)h1_f16, (const float2*)part1, (const uint2*)ln_wb_f16,
+        (const __half*)dw_w_f16, (const __half*)dw_b_f16, (__half*)out_f16, (float2*)xch, cnt, (int)frames);
   NPVP_LAUNCH_CHECK("ffn_mid16_kernel");
   return NPVP_OK;
 }

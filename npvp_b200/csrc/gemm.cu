@@ -1301,12 +1301,14 @@ extern "C" int npvp_conv_gemm_bf16(const void* x, int64_t frames, int H, int W, 
 
 
 void npvp_set_ffn_scalar(int v);   // predictor_kernels.cu
+void npvp_set_ffn_mid16_mode(int m);   // ffn_mid16.cu
 
 extern "C" int npvp_set_option(const char* name, int value) {
   NPVP_REQUIRE(name != nullptr, "npvp_set_option: null name");
   if (strcmp(name, "gemm_2cta") == 0) { g_use_2cta = value; return NPVP_OK; }
   if (strcmp(name, "gemm_epi_direct") == 0) { g_epi_direct = value; return NPVP_OK; }
   if (strcmp(name, "ffn_scalar") == 0) { npvp_set_ffn_scalar(value); return NPVP_OK; }
+  if (strcmp(name, "ffn_mid16_mode") == 0) { npvp_set_ffn_mid16_mode(value); return NPVP_OK; }
   NPVP_REQUIRE(false, "npvp_set_option: unknown option '%s'", name);
   return NPVP_ERR_INVALID;
 }
