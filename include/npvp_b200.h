@@ -39,7 +39,6 @@ extern "C" {
 #define NPVP_GEMM_AUTO 0
 #define NPVP_GEMM_TCGEN05 1 /* TMA-fed tcgen05.mma, TMEM accumulators */
 #define NPVP_GEMM_SIMT 2    /* CUDA-core reference path for debugging / odd shapes */
-#define NPVP_GEMM_TCGEN05_V1 3 /* first-generation (non-persistent, one tile per CTA) tcgen05 kernel, kept for A/B runs */
 #define NPVP_GEMM_TCGEN05_2CTA 4 /* cluster of 2 CTAs, tcgen05.mma.cta_group::2, 256x256 tiles */
 
 #define NPVP_PAD_ZERO 0
@@ -88,7 +87,7 @@ int npvp_set_option(const char* name, int value);
  * D[M,N] = A[M,K] (bf16, row stride lda) x W[N,K]^T (bf16, row stride ldw), fp32 accumulate.
  * Replaces every nn.Linear / 1x1 conv / MHA in- and out-projection on the path
  * (models/VidHRFormer.py:104,111,221,225,239,298,380,387; models/submodules.py:148-162,396-403)
- * and, together with npvp_im2col_nhwc, the 3x3 / strided / transposed convs of the autoencoder
+ * and, through npvp_conv_gemm_bf16, the 3x3 / strided / transposed convs of the autoencoder
  * (models/ResNetAutoEncoder.py:75-87,169-183,241,254; models/submodules.py:25). */
 int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                    const npvp_epilogue_t* ep, int backend, void* stream);
@@ -222,10 +221,6 @@ int npvp_conv7x7_stem(const float* x, const float* w, const float* shift, void* 
 int npvp_conv7x7_head(const void* x_bf16, const void* w, const float* bias, float* out, int64_t frames, int Cin,
                       int Cout, int H, int W, int phase_major, int act, int fp16, void* out_u8, const float* pix_inv_std,
                       const float* pix_inv_mean, void* stream);
-/* Patch gather for conv-as-GEMM: out[(f,oy,ox), (ky,kx,c)] = x[f, oy*stride - pad + ky, ox*stride - pad + kx, c].
- * x bf16 NHWC (or phase-major), out bf16 [frames*Ho*Wo, KH*KW*C]. */
-int npvp_im2col_nhwc(const void* x_bf16, void* out_bf16, int64_t frames, int H, int W, int C, int KH, int KW,
-                     int stride, int pad, int pad_mode, int Ho, int Wo, int phase_major, void* stream);
 /* 2x2/stride-2 max-pool of a column slice of a token matrix (NonLocalAttenion2D k/v pooling, submodules.py:151,158).
  * x bf16 [frames*H*W, ldx], columns [col0, col0+Cn) -> out bf16 [frames*(H/2)*(W/2), Cn]. */
 int npvp_maxpool2x2_cols(const void* x_bf16, int64_t ldx, int col0, int Cn, void* out_bf16, int64_t frames, int H,

@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
-GEMM_AUTO, GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_V1, GEMM_TCGEN05_2CTA = 0, 1, 2, 3, 4
+GEMM_AUTO, GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_2CTA = 0, 1, 2, 4
 PAD_ZERO, PAD_REFLECT, PAD_REPLICATE = 0, 1, 2
 ATTN_SPATIAL, ATTN_TEMPORAL = 0, 1
 
@@ -64,7 +64,6 @@ SIGNATURES = {
     "npvp_tokens_to_nchw": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp],
     "npvp_conv7x7_stem": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "npvp_conv7x7_head": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
-    "npvp_im2col_nhwc": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "npvp_maxpool2x2_cols": [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _vp],
     "npvp_nonlocal_attention": [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
 }
@@ -134,8 +133,7 @@ class Ops:
 
     def __init__(self, lib: Optional[C.CDLL] = None):
         self.lib = lib or load_library()
-        self.gemm_backend = {"auto": GEMM_AUTO, "tcgen05": GEMM_TCGEN05, "simt": GEMM_SIMT, "tcgen05_v1": GEMM_TCGEN05_V1,
-                             "tcgen05_2cta": GEMM_TCGEN05_2CTA}[os.environ.get("NPVP_B200_GEMM", "auto")]
+        self.gemm_backend = {"auto": GEMM_AUTO, "tcgen05": GEMM_TCGEN05, "simt": GEMM_SIMT, "tcgen05_2cta": GEMM_TCGEN05_2CTA}[os.environ.get("NPVP_B200_GEMM", "auto")]
         self.lib.npvp_set_option(b"gemm_2cta", int(os.environ.get("NPVP_B200_GEMM_2CTA", "-1")))
         self.lib.npvp_set_option(b"gemm_epi_direct", int(os.environ.get("NPVP_B200_GEMM_EPI_DIRECT", "0")))
         self.lib.npvp_set_option(b"ffn_mid16_mode", int(os.environ.get("NPVP_B200_FFN_MID16_MODE", "0")))
@@ -471,12 +469,6 @@ class Ops:
             self._call("npvp_conv7x7_head", x.data_ptr() + f0 * Cin * H * W * 2, w.data_ptr(), bias.data_ptr(),
                        None if out is None else out.data_ptr() + f0 * Cout * H * W * 4, n, Cin, Cout, H, W, int(phase_major), int(act), _is_fp16(x),
                        None if out_u8 is None else out_u8.data_ptr() + f0 * Cout * H * W, inv_std, inv_mean, self._stream())
-
-    def im2col(self, x, out, frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo, phase_major=False):
-        _chk16(x, "x"); _chk16(out, "out", like=x)
-        assert x.numel() == frames * H * W * Cc and out.shape == (frames * Ho * Wo, KH * KW * Cc)
-        self._call("npvp_im2col_nhwc", x.data_ptr(), out.data_ptr(), frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo,
-                   int(phase_major), self._stream())
 
     def maxpool2x2_cols(self, x, col0, Cn, out, frames, H, W):
         _chk16(x, "x", False); _chk16(out, "out", like=x)

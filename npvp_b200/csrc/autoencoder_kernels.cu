@@ -314,46 +314,6 @@ extern "C" int npvp_conv7x7_head(const void* x_bf16, const void* w, const float*
 }
 
 // ---------------------------------------------------------------------------------------------
-// patch gather (im2col) in 16-byte vectors of 8 channels
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-im2col_nhwc_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int64_t total_vec, int H, int W, int C, int KH, int KW,
-                   int stride, int pad, int pad_mode, int Ho, int Wo, int phase_major) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total_vec) return;
-  const int cv = C >> 3;
-  const int c8 = (int)(i % cv);
-  int64_t rest = i / cv;
-  const int tap = (int)(rest % (KH * KW));
-  rest /= (KH * KW);
-  const int ox = (int)(rest % Wo);
-  rest /= Wo;
-  const int oy = (int)(rest % Ho);
-  const int64_t f = rest / Ho;
-  int iy = oy * stride - pad + tap / KW, ix = ox * stride - pad + tap % KW;
-  bool valid = true;
-  if (pad_mode == NPVP_PAD_REFLECT) { iy = reflect_idx(iy, H); ix = reflect_idx(ix, W); }
-  else if (pad_mode == NPVP_PAD_REPLICATE) { iy = min(max(iy, 0), H - 1); ix = min(max(ix, 0), W - 1); }
-  else valid = (iy >= 0 && iy < H && ix >= 0 && ix < W);
-  uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  if (valid) v = __ldg(reinterpret_cast<const uint4*>(x + pixel_offset(f, iy, ix, H, W, phase_major) * C) + c8);
-  reinterpret_cast<uint4*>(out)[i] = v;
-}
-
-extern "C" int npvp_im2col_nhwc(const void* x_bf16, void* out_bf16, int64_t frames, int H, int W, int C, int KH, int KW, int stride,
-                                int pad, int pad_mode, int Ho, int Wo, int phase_major, void* stream) {
-  NPVP_REQUIRE(x_bf16 && out_bf16 && frames > 0, "npvp_im2col_nhwc: bad arguments");
-  NPVP_REQUIRE(C % 8 == 0 && KH > 0 && KW > 0 && stride > 0 && Ho > 0 && Wo > 0, "npvp_im2col_nhwc: C must be a multiple of 8");
-  NPVP_REQUIRE(!phase_major || (H % 2 == 0 && W % 2 == 0), "npvp_im2col_nhwc: phase-major input needs even H, W");
-  NPVP_REQUIRE(pad_mode == NPVP_PAD_ZERO || (pad < H && pad < W), "npvp_im2col_nhwc: reflect/replicate pad must be smaller than the image");
-  const int64_t total = frames * Ho * Wo * KH * KW * (C / 8);
-  im2col_nhwc_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x_bf16, (bf16*)out_bf16, total, H, W, C, KH, KW,
-                                                                                    stride, pad, pad_mode, Ho, Wo, phase_major);
-  NPVP_LAUNCH_CHECK("im2col_nhwc_kernel");
-  return NPVP_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
 // 2x2 max-pool of a column slice
 // ---------------------------------------------------------------------------------------------
 __global__ void maxpool2x2_cols_kernel(const h16* __restrict__ x, int64_t ldx, int col0, int Cn, h16* __restrict__ out,

@@ -131,17 +131,6 @@ __device__ __forceinline__ void stg256(void* dst, const uint32_t* v) {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5: epilogue
-
-template <int BN>
-struct GemmCfg {
-  static constexpr int kStages = (BN >= 256) ? 4 : 3;
-  static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;  // power of two >= 32 (BN is 64/128/256)
-};
 
 // Shared-memory matrix descriptor: K-major, 128B swizzle, 8-row groups 1024 B apart (SBO), version 1 (sm_100).
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
@@ -159,129 +148,6 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_f16kind(int M, int N, int fp16) {
   return (1u << 4) | (fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-
-template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    int64_t M, int64_t N, int64_t K, EpiParams ep) {
-  using Cfg = GemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment required by the 128B swizzle atoms
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + Cfg::kStages;
-  uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::kStages + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int m_blk = blockIdx.y, n_blk = blockIdx.x;
-  const int num_k_blocks = (int)((K + kBK - 1) / kBK);
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmap_a);
-    ptx::prefetch_tmap(&tmap_b);
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
-    }
-    ptx::mbar_init(tmem_full_bar, 1);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-        ptx::tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
-        ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, n_blk * BN);
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer (one thread) ----------------
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16kind(kBM, BN, ep.fp16);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
-        ptx::tc_fence_after();
-        const uint64_t adesc = make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
-        const uint64_t bdesc = make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
-#pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k) {
-          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
-          ptx::umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-        }
-        ptx::umma_commit(&empty_bar[stage]);     // frees this smem stage when the MMAs have read it
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-      }
-      ptx::umma_commit(tmem_full_bar);           // accumulator complete
-    }
-  } else {
-    // ---------------- epilogue: 4 warps, TMEM lane quadrant = warp % 4 ----------------
-    const int quad = warp & 3;
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
-    const int64_t m = (int64_t)m_blk * kBM + quad * 32 + lane;
-    const bool row_ok = m < M;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, r);
-      ptx::tmem_ld_wait();
-      const int64_t n0 = (int64_t)n_blk * BN + c;
-      if (row_ok && n0 < N) {
-        if (n0 + 32 <= N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = epi_value(ep, __uint_as_float(r[j]), m, n0 + j);
-          if (ep.out_f32) {
-            float4* dst = reinterpret_cast<float4*>(ep.out_f32 + m * ep.ld_out + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (ep.out_bf16) {
-            uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * ep.ld_out + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_h16x2(v[8 * j], v[8 * j + 1], ep.out_fp16), pack_h16x2(v[8 * j + 2], v[8 * j + 3], ep.out_fp16),
-                                  pack_h16x2(v[8 * j + 4], v[8 * j + 5], ep.out_fp16), pack_h16x2(v[8 * j + 6], v[8 * j + 7], ep.out_fp16));
-          }
-        } else {
-          for (int j = 0; j < 32 && n0 + j < N; ++j) {
-            const float v = epi_value(ep, __uint_as_float(r[j]), m, n0 + j);
-            if (ep.out_f32) ep.out_f32[m * ep.ld_out + n0 + j] = v;
-            if (ep.out_bf16) ep.out_bf16[m * ep.ld_out + n0 + j] = float_to_h16(v, ep.out_fp16);
-          }
-        }
-      }
-    }
-    ptx::tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
-  }
-}
-
 
 // =============================================================================================
 // tcgen05 GEMM kernel, v2: persistent + warp-specialised + double-buffered TMEM + coalesced, specialised epilogue
@@ -1042,29 +908,6 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_
   return NPVP_OK;
 }
 
-template <int BN>
-static int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
-                          const EpiParams& e, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (err != cudaSuccess) { npvp_set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
-    attr_set = true;
-  }
-  CUtensorMap ta, tb;
-  int rc = make_tmap_2d(&ta, A, M, K, lda, kBM, e.fp16);
-  if (rc) return rc;
-  rc = make_tmap_2d(&tb, W, N, K, ldw, BN, e.fp16);
-  if (rc) return rc;
-  NPVP_REQUIRE(ceil_div64(M, kBM) <= 65535, "gemm_tcgen05: M chunk too large");
-  dim3 grid((unsigned)ceil_div64(N, BN), (unsigned)ceil_div64(M, kBM));
-  gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K, e);
-  NPVP_LAUNCH_CHECK("gemm_tcgen05_kernel");
-  return NPVP_OK;
-}
-
-
 static int g_num_sms = 0;
 static int g_epi_direct = 0;   // npvp_set_option("gemm_epi_direct", 1): store 16-bit outputs straight from the accumulator layout (see epi_direct16)
 static int g_use_2cta = -1;     // npvp_set_option("gemm_2cta", v): 1 = always for N >= 256, 0 = never, -1 (default) = when K >= 1024
@@ -1228,15 +1071,18 @@ extern "C" int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   // AUTO: tensor path whenever the operands are TMA-expressible.  The choice must not depend on M (the batch), otherwise a
   // clip would be computed differently alone and inside a batch; TMA zero-fills boxes that overhang small operands.
   if (backend == NPVP_GEMM_AUTO)
-    backend = (tma_compatible(A, lda, W, ldw, K) && vec_ok) ? NPVP_GEMM_TCGEN05 : NPVP_GEMM_SIMT;   // K < 64: TMA zero-fills the k-block
-  if (backend == NPVP_GEMM_TCGEN05 || backend == NPVP_GEMM_TCGEN05_V1 || backend == NPVP_GEMM_TCGEN05_2CTA) {
+    backend = (tma_compatible(A, lda, W, ldw, K) && vec_ok && N % 4 == 0 &&
+               (!(ep->res1 || ep->res2) || (ep->ld_res % 4 == 0 && (uintptr_t)ep->res1 % 16 == 0 && (uintptr_t)ep->res2 % 16 == 0)))
+                  ? NPVP_GEMM_TCGEN05 : NPVP_GEMM_SIMT;   // K < 64: TMA zero-fills the k-block
+  if (backend == NPVP_GEMM_TCGEN05 || backend == NPVP_GEMM_TCGEN05_2CTA) {
     NPVP_REQUIRE(tma_compatible(A, lda, W, ldw, K) && vec_ok, "npvp_gemm_bf16: operands not 16-byte aligned / K,ld not multiples of 8 for the TMA path");
     const bool res_ok = (!(ep->res1 || ep->res2)) || (ep->ld_res % 4 == 0 && (uintptr_t)ep->res1 % 16 == 0 && (uintptr_t)ep->res2 % 16 == 0);
     if (backend == NPVP_GEMM_TCGEN05_2CTA) {
       NPVP_REQUIRE(N % 4 == 0 && res_ok, "npvp_gemm_bf16: 2-CTA path needs N %% 4 == 0 and 16-byte aligned residuals");
       return launch_tcgen05_2cta(A, lda, W, ldw, M, N, K, e, st);
     }
-    if (backend == NPVP_GEMM_TCGEN05 && N % 4 == 0 && res_ok) {       // persistent kernel; tile width never depends on M
+    NPVP_REQUIRE(N % 4 == 0 && res_ok, "npvp_gemm_bf16: the tcgen05 kernels need N %% 4 == 0 and 16-byte aligned residuals (use NPVP_GEMM_SIMT)");
+    {                                                                 // persistent kernel; tile width never depends on M
       // 2-CTA (cta_group::2) tiles pay off once the main loop dominates the tile: measured 1150 vs 1011 TFLOP/s at K = 2048,
       // 912 vs 1013 at K = 512 (M = 40960).  The choice depends on N and K only, never on M (batch invariance).
       if (N >= 256 && (g_use_2cta == 1 || (g_use_2cta < 0 && K >= 1024))) return launch_tcgen05_2cta(A, lda, W, ldw, M, N, K, e, st);
@@ -1244,8 +1090,6 @@ extern "C" int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
       if (N > 64) return launch_tcgen05_v2<128>(A, lda, W, ldw, M, N, K, e, st);
       return launch_tcgen05_v2<64>(A, lda, W, ldw, M, N, K, e, st);
     }
-    if (N > 64) return launch_tcgen05<128>(A, lda, W, ldw, M, N, K, e, st);
-    return launch_tcgen05<64>(A, lda, W, ldw, M, N, K, e, st);
   }
   NPVP_REQUIRE(backend == NPVP_GEMM_SIMT, "npvp_gemm_bf16: unknown backend %d", backend);
   dim3 grid((unsigned)ceil_div64(N, 64), (unsigned)ceil_div64(M, 64));

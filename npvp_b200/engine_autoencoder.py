@@ -1,9 +1,9 @@
 """Host-side drivers of the ResNet frame encoder / decoder (reference: models/ResNetAutoEncoder.py:51-261,
 models/submodules.py:9-180).
 
-Data layout in HBM: activations are bf16 channels-last [frames, H, W, C]; every 3x3 / strided / transposed
-convolution is a patch gather (``npvp_im2col_nhwc``) followed by a tensor-core GEMM whose epilogue applies the
-folded eval-mode BatchNorm, bias, ReLU, the non-local gamma and up to two residual adds.  A transposed conv
+Data layout in HBM: activations are 16-bit channels-last [frames, H, W, C]; every 3x3 / strided / transposed
+convolution is an implicit GEMM (``npvp_conv_gemm_bf16``: the patch gather happens inside the tensor-core kernel) whose
+epilogue applies the folded eval-mode BatchNorm, bias, ReLU, the non-local gamma and up to two residual adds.  A transposed conv
 (3x3, stride 2, pad 1, output_pad 1) is computed as ONE GEMM over the 2x2 input neighbourhood with N = 4*Cout
 enumerating the four output phases (9 live taps out of 16 blocks), leaving its output "phase-major"
 [frames, H, W, (py,px), Cout]; the next layer's gather reads that layout directly, so no pixel shuffle runs.
@@ -23,8 +23,6 @@ from .engine_predictor import _bn_fold, _f
 from .workspace import Workspace
 
 _PAD = {"reflect": PAD_REFLECT, "replicate": PAD_REPLICATE, "zero": PAD_ZERO}
-# NPVP_B200_CONV=im2col switches back to the explicit patch-matrix path (kept for A/B measurements)
-_IMPLICIT_GEMM = os.environ.get("NPVP_B200_CONV", "implicit") != "im2col"
 
 
 def ae_dtype() -> torch.dtype:
@@ -101,12 +99,7 @@ class EncoderEngine:
         w, b = wb
         if "out_f32" not in epi:
             epi["out_bf16"] = ws.h16(tag, self.dt, frames * Ho * Wo, w.shape[0])
-        if _IMPLICIT_GEMM:          # A operand gathered inside the GEMM (no patch matrix in HBM)
-            op.conv_gemm(x, w, frames, H, W, C, 3, 3, stride, 1, pad_mode, Ho, Wo, bias=b, **epi)
-        else:
-            col = ws.h16("col", self.dt, frames * Ho * Wo, 9 * C)
-            op.im2col(x, col, frames, H, W, C, 3, 3, stride, 1, pad_mode, Ho, Wo)
-            op.gemm(col, w, bias=b, **epi)
+        op.conv_gemm(x, w, frames, H, W, C, 3, 3, stride, 1, pad_mode, Ho, Wo, bias=b, **epi)   # A gathered inside the GEMM
         return epi.get("out_bf16", epi.get("out_f32"))
 
     def _f3d(self, x, frames, H, W, p: _F3D, tag):
@@ -221,12 +214,7 @@ class DecoderEngine:
         phase = False
         for i, (w, b, Cin, Cout) in enumerate(self.ups):
             nxt = ws.h16(f"up{i}", self.dt, frames * H * W, 4 * Cout)
-            if _IMPLICIT_GEMM:
-                op.conv_gemm(cur, w, frames, H, W, Cin, 2, 2, 1, 0, PAD_ZERO, H, W, phase, bias=b, act=ACT_RELU, out_bf16=nxt)
-            else:
-                col = ws.h16("col", self.dt, frames * H * W, 4 * Cin)
-                op.im2col(cur, col, frames, H, W, Cin, 2, 2, 1, 0, PAD_ZERO, H, W, phase_major=phase)
-                op.gemm(col, w, bias=b, act=ACT_RELU, out_bf16=nxt)
+            op.conv_gemm(cur, w, frames, H, W, Cin, 2, 2, 1, 0, PAD_ZERO, H, W, phase, bias=b, act=ACT_RELU, out_bf16=nxt)
             cur, H, W, phase = nxt, 2 * H, 2 * W, True
         out = torch.empty(N, T, self.cout, H, W, dtype=torch.float32, device=self.device) if (want_f32 or renorm is None) else None
         out_u8 = torch.empty(N, T, self.cout, H, W, dtype=torch.uint8, device=self.device) if renorm is not None else None

@@ -41,7 +41,7 @@ H16 = [torch.bfloat16, torch.float16]
 
 
 @pytest.mark.parametrize("dt", H16)
-@pytest.mark.parametrize("backend", [2, 1, 3, 4, 0])
+@pytest.mark.parametrize("backend", [2, 1, 4, 0])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_plain(op, spec, backend, M, N, K, dt):
     a, w = rn(M, K, seed=1, dtype=dt), rn(N, K, seed=2, scale=K ** -0.5, dtype=dt)
@@ -56,7 +56,7 @@ def test_gemm_plain(op, spec, backend, M, N, K, dt):
 
 
 @pytest.mark.parametrize("dt", H16)
-@pytest.mark.parametrize("backend", [2, 1, 3, 4])
+@pytest.mark.parametrize("backend", [2, 1, 4])
 def test_gemm_epilogues(op, spec, backend, dt):
     M, N, K = 384, 512, 1024
     a, w = rn(M, K, seed=1, dtype=dt), rn(N, K, seed=2, scale=K ** -0.5, dtype=dt)
@@ -311,19 +311,6 @@ def test_conv7x7_head(op, spec, Cin, Cout, HW, phase, act, dt):
     op.conv7x7_head(x, w, b, o1, Cin, Cout, HW, HW, phase, act)
     spec.conv7x7_head(x, w, b, o2, Cin, Cout, HW, HW, phase, act)
     assert float((o1 - o2).abs().max()) < 2e-4, float((o1 - o2).abs().max())
-
-
-@pytest.mark.parametrize("H,C,KH,stride,pad,mode,phase", [(16, 64, 3, 1, 1, 0, False), (16, 64, 3, 2, 1, 0, False), (8, 512, 3, 1, 1, 1, False),
-                                                          (8, 128, 3, 1, 1, 2, False), (16, 32, 2, 1, 0, 0, True), (8, 256, 2, 1, 0, 0, False)])
-def test_im2col(op, spec, H, C, KH, stride, pad, mode, phase):
-    frames = 3
-    x = rn(frames * H * H, C, seed=1, dtype=torch.bfloat16)
-    Ho = H // stride
-    o1 = torch.empty(frames * Ho * Ho, KH * KH * C, device=DEV, dtype=torch.bfloat16)
-    o2 = torch.empty_like(o1)
-    op.im2col(x, o1, frames, H, H, C, KH, KH, stride, pad, mode, Ho, Ho, phase)
-    spec.im2col(x, o2, frames, H, H, C, KH, KH, stride, pad, mode, Ho, Ho, phase)
-    assert torch.equal(o1, o2)
 
 
 @pytest.mark.parametrize("dt", H16)

@@ -13,7 +13,7 @@ def main():
               (M * 8, 128, 256, "bf16"), (M * 8, 64, 576, "bf16"), (M, 512, 512, "res"), (M, 512, 2048, "f32")]
     if os.environ.get("SHAPES"):
         shapes = [shapes[int(i)] for i in os.environ["SHAPES"].split(",")]
-    backends = [b for b in (("v1", 3), ("v2", 1), ("2cta", 4)) if os.environ.get("ONLY", b[0]) == b[0]]
+    backends = [b for b in (("v2", 1), ("2cta", 4)) if os.environ.get("ONLY", b[0]) == b[0]]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for (m, n, k, kind) in shapes:
         a = torch.randn(m, k, device=dev).to(torch.bfloat16)
