@@ -244,12 +244,19 @@ class GemmTimer:
                 # (SURVEY Appendix A.12), whatever the kernel multiplies.
                 flops *= 9.0 / 16.0
             self.records.append((e0, e1, flops, (M, w.shape[0], K)))
-        self._orig_conv = self.ops.conv_gemm
-        self.ops.gemm, self.ops.conv_gemm = timed, timed_conv
+        def timed_convt(x, w, frames, H, W, Cin, Cout, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._orig_convt(x, w, frames, H, W, Cin, Cout, **kw)
+            e1.record()
+            # npvp_convt_gemm_bf16 multiplies exactly the 9 live (phase, tap) blocks: 9 Cin Cout MACs per input pixel
+            self.records.append((e0, e1, 2.0 * frames * H * W * 9 * Cin * Cout, (frames * H * W, 4 * Cout, 4 * Cin)))
+        self._orig_conv, self._orig_convt = self.ops.conv_gemm, self.ops.convt_gemm
+        self.ops.gemm, self.ops.conv_gemm, self.ops.convt_gemm = timed, timed_conv, timed_convt
         return self
 
     def __exit__(self, *exc):
-        self.ops.gemm, self.ops.conv_gemm = self._orig, self._orig_conv
+        self.ops.gemm, self.ops.conv_gemm, self.ops.convt_gemm = self._orig, self._orig_conv, self._orig_convt
 
     def summary(self):
         torch.cuda.synchronize()

@@ -99,6 +99,20 @@ int npvp_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int64
 int npvp_conv_gemm_bf16(const void* x, int64_t frames, int H, int W, int C, int KH, int KW, int stride, int pad,
                         int pad_mode, int Ho, int Wo, int phase_major, const void* Wt, int64_t ldw, int64_t N,
                         const npvp_epilogue_t* ep, void* stream);
+/* (r02) When stride == 1, the padding is zero padding of (K-1)/2, C % 64 == 0 and 128-pixel tiles are whole rows or whole
+ * frames (W <= 128, 128 % W == 0, H*W % 128 == 0 or 128 % (H*W) == 0), npvp_conv_gemm_bf16 loads the A operand as SHIFTED
+ * WINDOWS of a 4-D tensor map (C, W, H, frames) with cp.async.bulk.tensor.4d - the TMA unit zero-fills the padding - and
+ * runs without gather warps; npvp_set_option("conv_tma", 0) switches back to the gather (A/B).
+ *
+ * Transposed convolution nn.ConvTranspose2d(Cin, Cout, 3, stride 2, padding 1, output_padding 1) + folded BatchNorm + ReLU
+ * (models/ResNetAutoEncoder.py:169-183) as ONE implicit GEMM over the 2x2 input neighbourhood:
+ *   out[f, 2y+py, 2x+px, co] = act( bias[(q,co)] + sum_{dy,dx,ci} x[f, y+dy, x+dx, ci] * Wt[(q,co), (dy,dx,ci)] ),
+ * output phases ordered q = (py,px) = (0,0), (0,1), (1,1), (1,0) so that every tap feeds a contiguous column range: only the
+ * 9 live (phase, tap) blocks of the 16 are loaded and multiplied.  x [frames,H,W,Cin] and out [frames,2H,2W,Cout] are plain
+ * channels-last 16-bit tensors (A tiles by TMA as above, pixel-shuffled stores in the epilogue).  Wt 16-bit [4*Cout, 4*Cin],
+ * bias fp32 [4*Cout]; Cin % 64 == 0, Cout % 32 == 0, W a power of two <= 128; ep: 16-bit output only, no residuals. */
+int npvp_convt_gemm_bf16(const void* x, int64_t frames, int H, int W, int Cin, const void* Wt, int64_t ldw, int Cout,
+                         const npvp_epilogue_t* ep, void* stream);
 /* fp32 CUDA-core GEMM for the tiny, precision-critical NRMLP (models/submodules.py:299-314). */
 int npvp_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                   const float* bias, int act, float* out, int64_t ldo, void* stream);

@@ -36,6 +36,7 @@ SIGNATURES = {
     "npvp_gemm_bf16": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _vp],
     "npvp_conv_gemm_bf16": [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _i64,
                             C.POINTER(Epilogue), _vp],
+    "npvp_convt_gemm_bf16": [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _i32, C.POINTER(Epilogue), _vp],
     "npvp_gemm_f32": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i32, _vp, _i64, _vp],
     "npvp_fourier_features": [_vp, _vp, _vp, _i64, _i32, _vp],
     "npvp_ln_posfuse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
@@ -137,6 +138,7 @@ class Ops:
         self.lib.npvp_set_option(b"gemm_2cta", int(os.environ.get("NPVP_B200_GEMM_2CTA", "-1")))
         self.lib.npvp_set_option(b"gemm_epi_direct", int(os.environ.get("NPVP_B200_GEMM_EPI_DIRECT", "0")))
         self.lib.npvp_set_option(b"ffn_mid16_mode", int(os.environ.get("NPVP_B200_FFN_MID16_MODE", "0")))
+        self.lib.npvp_set_option(b"conv_tma", int(os.environ.get("NPVP_B200_CONV_TMA", "1")))
 
     # -- plumbing -------------------------------------------------------------------------------
     def _stream(self):
@@ -209,6 +211,24 @@ class Ops:
                       int(bool(post_relu)), _is_fp16(x), 0, ld_out, ld_res)
         self._call("npvp_conv_gemm_bf16", x.data_ptr(), frames, H, W, Cc, KH, KW, stride, pad, pad_mode, Ho, Wo, int(phase_major),
                    w.data_ptr(), _rowmajor(w, "w"), N, C.byref(ep), self._stream())
+
+    @staticmethod
+    def convt_supported(H, W, Cin, Cout):
+        """geometry npvp_convt_gemm_bf16 accepts (include/npvp_b200.h)"""
+        HW = H * W
+        return (Cin % 64 == 0 and Cout % 32 == 0 and W <= 128 and (W & (W - 1)) == 0 and 128 % W == 0
+                and (HW % 128 == 0 or 128 % HW == 0))
+
+    def convt_gemm(self, x, w, frames, H, W, Cin, Cout, *, bias=None, act=ACT_NONE, out_bf16=None):
+        """ConvTranspose2d(3, s2, p1, op1): x 16-bit NHWC [frames*H*W, Cin], w 16-bit [(q,co), (dy,dx,ci)] with the phases
+        q = (0,0), (0,1), (1,1), (1,0) -> out 16-bit NHWC [frames*2H*2W, Cout]."""
+        _chk16(x, "x"); _chk16(w, "w", False, like=x); _chk(bias, torch.float32, "bias"); _chk16(out_bf16, "out_bf16", False, like=x)
+        assert x.numel() == frames * H * W * Cin and tuple(w.shape) == (4 * Cout, 4 * Cin)
+        assert out_bf16.is_contiguous() and out_bf16.numel() == frames * 4 * H * W * Cout
+        assert bias is None or bias.numel() == 4 * Cout
+        ep = Epilogue(_ptr(bias), None, None, None, _ptr(out_bf16), 1.0, int(act), 0, 0, 0, _is_fp16(x), 0, Cout, 0)
+        self._call("npvp_convt_gemm_bf16", x.data_ptr(), frames, H, W, Cin, w.data_ptr(), _rowmajor(w, "w"), Cout, C.byref(ep),
+                   self._stream())
 
     def gemm_f32(self, a, w, bias, act, out):
         for t, n in ((a, "a"), (w, "w"), (out, "out")):

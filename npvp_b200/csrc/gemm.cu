@@ -61,6 +61,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -203,6 +209,34 @@ struct ConvGather {
   const h16* x;
   int H, W, C, KH, KW, stride, pad, pad_mode, Ho, Wo, phase_major;
 };
+// CONV = 2 / 3: the A operand of a stride-1 zero-padded convolution (2) or of the 2x2-neighbourhood form of a transposed
+// convolution (3) is a SHIFTED WINDOW of the channels-last activations, i.e. a box of a 4-D tensor map (C, W, H, frames):
+// one cp.async.bulk.tensor.4d per k-block lands the 128 pixels x 64 channels of tap (ty, tx) in the same 128B-swizzled
+// layout as a dense A tile, pixels outside the frame are zero-filled by the TMA unit, and no gather warps exist
+// (r01/r02 profiles: the cp.async gather kept the tensor pipe 26-50 % busy and spent 40 % of the issue slots on addresses).
+// A tile is 128 consecutive pixels: whole rows of one frame (W <= 128, H*W % 128 == 0) or whole frames (128 % (H*W) == 0).
+// CONV = 3 additionally (i) skips the zero blocks of the transposed convolution: with the output phases ordered
+// q = (0,0), (0,1), (1,1), (1,0) along N, tap (dy,dx) feeds the CONTIGUOUS column range [lo, hi) x Cout given by
+// convt_cols(), so every tap is one MMA group with N = hi - lo accumulating into TMEM columns [lo, hi) - 9 of the 16
+// (phase, tap) blocks are computed, none is multiplied by zeros - and (ii) stores plain NHWC at double resolution
+// (pixel (2y+py, 2x+px)), which is what makes the NEXT layer's A operand TMA-loadable.
+struct TmaConv {
+  int taps, KW, pad, kb_per_tap;   // tap t = (t / KW, t % KW), source shift (ty - pad, tx - pad); k-blocks of 64 channels per tap
+  int HW, W;                        // pixels per frame / per row
+  int cout;                         // CONV = 3: output channels per phase (N = 4 * cout)
+  // Resident weights: when the live part of W fits beside >= 3 A stages (and N <= BN: one n-tile), the producer loads it ONCE
+  // per CTA - tap by tap, k-block by k-block, live rows only, `wbox` rows per TMA box - and the stage ring carries A alone.
+  // (r02 launch list: the last transposed conv and the 64-channel 3x3 conv spent 2.6 / 4.2 us per 128-pixel tile re-fetching
+  // the same 64 / 72 KB of weights from L2 - these layers are bound by the per-SM L2 ingest, not by the tensor pipe.)
+  int wres, wres_bytes, nst, wbox;
+};
+__device__ __forceinline__ void convt_cols(int t, int cout, int n0, int bn, int& lo, int& hi) {
+  const int a = t == 0 ? 0 : (t == 1 ? cout : 2 * cout);
+  const int b = (t == 0 || t == 2) ? 4 * cout : 3 * cout;
+  lo = max(a, n0) - n0;
+  hi = min(b, n0 + bn) - n0;
+}
+
 constexpr int kGatherThreads = 128;    // warps 2, 3 and (conv kernels only) the two extra warps 12, 13
 constexpr int kGatherRowsPerPass = kGatherThreads / 8;
 constexpr int kGatherLag = 2;          // cp.async groups kept in flight per thread before the stage is published
@@ -242,10 +276,34 @@ __device__ __forceinline__ void add_res(float4& q, const void* res, int is16, in
 // all eight swizzled LDS.128 and all residual loads are issued first, the math is straight-line, and the bounds checks
 // only predicate the loads / stores.  (r01: with a per-row `if` the compiler emitted one BSSY/BSYNC region per row, the
 // rows serialised at ~100 cycles each and the epilogue - not the 98 %-of-peak main loop - set the tile time.)
-template <int ACT, int RES, int OUT, bool FP16>
+// Residual operands of one chunk as they come from memory (compile-time RES > 0): loaded a whole chunk AHEAD of their use -
+// the first chunk of a tile before the wait for the accumulator, later ones while the previous chunk is being stored -
+// so that their latency never sits between tcgen05.ld and the stores.  (r02 ncu of the 3x3 conv + skip at 64 channels: 45 % of
+// the epilogue warps' samples were long-scoreboard stalls on these loads, 3.7 us per 128 x 64 tile.)
+template <int RES>
+struct ResRaw {
+  uint2 a[(RES == 2 || RES == 3) ? 8 : 1];
+  uint2 b[RES == 3 ? 8 : 1];
+  float4 f[RES == 1 ? 8 : 1];
+};
+template <int RES>
+__device__ __forceinline__ void load_res(ResRaw<RES>& rr, const EpiParams& ep, int sub_row, int64_t m_base, int64_t M, bool col_ok, int64_t n) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int64_t m = m_base + it * 4 + sub_row;
+    const bool ok = m < M && col_ok;
+    const int64_t roff = m * ep.ld_res + n;
+    if (RES == 1) rr.f[it] = ok ? *reinterpret_cast<const float4*>((const float*)ep.res1 + roff) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (RES == 2 || RES == 3) rr.a[it] = ok ? *reinterpret_cast<const uint2*>((const h16*)ep.res1 + roff) : make_uint2(0u, 0u);
+    if (RES == 3) rr.b[it] = ok ? *reinterpret_cast<const uint2*>((const h16*)ep.res2 + roff) : make_uint2(0u, 0u);
+  }
+}
+
+// `next()` runs between the last use of `rr` and the stores: it refills rr with the residuals of the chunk that follows.
+template <int ACT, int RES, int OUT, bool FP16, class Next>
 __device__ __forceinline__ void epi_chunk(uint32_t stg_addr, int sub_row, int chunk, int64_t m_base, int64_t M, bool col_ok,
                                           int64_t n, const float4 b4, float alpha, float relu_floor, const EpiParams& ep,
-                                          float& st_s, float& st_q) {
+                                          float& st_s, float& st_q, ResRaw<RES>& rr, Next&& next) {
   constexpr int fp16 = FP16 ? 1 : 0;
   float4 q[8];
 #pragma unroll
@@ -259,15 +317,19 @@ __device__ __forceinline__ void epi_chunk(uint32_t stg_addr, int sub_row, int ch
     for (int it = 0; it < 8; ++it) {
       const int64_t m = m_base + it * 4 + sub_row;
       rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < M && col_ok) {
+      if (RES == 1) rs[it] = rr.f[it];
+      if (RES == 2 || RES == 3) {
+        const float2 a = unpack_h16x2(rr.a[it].x, fp16), b = unpack_h16x2(rr.a[it].y, fp16);
+        rs[it] = make_float4(a.x, a.y, b.x, b.y);
+      }
+      if (RES == 3) {
+        const float2 a = unpack_h16x2(rr.b[it].x, fp16), b = unpack_h16x2(rr.b[it].y, fp16);
+        rs[it].x += a.x; rs[it].y += a.y; rs[it].z += b.x; rs[it].w += b.y;
+      }
+      if (RES < 0 && m < M && col_ok) {
         const int64_t roff = m * ep.ld_res + n;
-        if (RES == 1) add_res(rs[it], ep.res1, 0, fp16, roff);
-        if (RES == 2 || RES == 3) add_res(rs[it], ep.res1, 1, fp16, roff);
-        if (RES == 3) add_res(rs[it], ep.res2, 1, fp16, roff);
-        if (RES < 0) {
-          if (ep.res1) add_res(rs[it], ep.res1, ep.res1_bf16, fp16, roff);
-          if (ep.res2) add_res(rs[it], ep.res2, ep.res2_bf16, fp16, roff);
-        }
+        if (ep.res1) add_res(rs[it], ep.res1, ep.res1_bf16, fp16, roff);
+        if (ep.res2) add_res(rs[it], ep.res2, ep.res2_bf16, fp16, roff);
       }
     }
   }
@@ -285,6 +347,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t stg_addr, int sub_row, int ch
       st_q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, st_q))));
     }
   }
+  next();
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int64_t m = m_base + it * 4 + sub_row;
@@ -305,7 +368,9 @@ __device__ __forceinline__ void epi_chunk(uint32_t stg_addr, int sub_row, int ch
 // tcgen05.ld changes nothing - the kernel is bound by L2 traffic (operand re-reads + output sectors, ~235 sectors/clk on
 // every shape), not by how the epilogue moves data inside the SM.  Kept as an A/B switch, off by default.
 constexpr int kOutDirect16 = 3;
-template <int ACT, bool FP16>
+// LEAN: alpha == 1 and no post-ReLU floor (the caller checks) - two instructions per element less; with ACT == RELU the ReLU is
+// applied to the packed 16-bit pairs (rounding is monotonic and 0 is exact, so max(round(x), 0) == round(max(x, 0))).
+template <int ACT, bool FP16, bool LEAN = false>
 __device__ __forceinline__ void epi_direct16(const uint32_t (&r)[32], const float* __restrict__ bias_n0, float alpha, float relu_floor,
                                              h16* __restrict__ dst, bool row_ok, int act_rt) {
   constexpr int fp16 = FP16 ? 1 : 0;
@@ -314,10 +379,26 @@ __device__ __forceinline__ void epi_direct16(const uint32_t (&r)[32], const floa
   for (int j = 0; j < 8; ++j) {
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias_n0) b = __ldg(reinterpret_cast<const float4*>(bias_n0) + j);       // warp-uniform address: one L1 broadcast
-    const float v0 = fmaxf(act_ct<ACT>(__uint_as_float(r[4 * j + 0]) + b.x, act_rt) * alpha, relu_floor);
-    const float v1 = fmaxf(act_ct<ACT>(__uint_as_float(r[4 * j + 1]) + b.y, act_rt) * alpha, relu_floor);
-    const float v2 = fmaxf(act_ct<ACT>(__uint_as_float(r[4 * j + 2]) + b.z, act_rt) * alpha, relu_floor);
-    const float v3 = fmaxf(act_ct<ACT>(__uint_as_float(r[4 * j + 3]) + b.w, act_rt) * alpha, relu_floor);
+    if (LEAN && ACT == NPVP_ACT_RELU) {
+      p[2 * j] = pack_h16x2(__uint_as_float(r[4 * j + 0]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y, fp16);
+      p[2 * j + 1] = pack_h16x2(__uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w, fp16);
+      if (FP16) {
+        const __half2 z = __float2half2_rn(0.f);
+        *reinterpret_cast<__half2*>(&p[2 * j]) = __hmax2(*reinterpret_cast<__half2*>(&p[2 * j]), z);
+        *reinterpret_cast<__half2*>(&p[2 * j + 1]) = __hmax2(*reinterpret_cast<__half2*>(&p[2 * j + 1]), z);
+      } else {
+        const __nv_bfloat162 z = __float2bfloat162_rn(0.f);
+        *reinterpret_cast<__nv_bfloat162*>(&p[2 * j]) = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&p[2 * j]), z);
+        *reinterpret_cast<__nv_bfloat162*>(&p[2 * j + 1]) = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&p[2 * j + 1]), z);
+      }
+      continue;
+    }
+    float v0 = act_ct<ACT>(__uint_as_float(r[4 * j + 0]) + b.x, act_rt), v1 = act_ct<ACT>(__uint_as_float(r[4 * j + 1]) + b.y, act_rt);
+    float v2 = act_ct<ACT>(__uint_as_float(r[4 * j + 2]) + b.z, act_rt), v3 = act_ct<ACT>(__uint_as_float(r[4 * j + 3]) + b.w, act_rt);
+    if (!LEAN) {
+      v0 = fmaxf(v0 * alpha, relu_floor); v1 = fmaxf(v1 * alpha, relu_floor);
+      v2 = fmaxf(v2 * alpha, relu_floor); v3 = fmaxf(v3 * alpha, relu_floor);
+    }
     p[2 * j] = pack_h16x2(v0, v1, fp16);
     p[2 * j + 1] = pack_h16x2(v2, v3, fp16);
   }
@@ -328,9 +409,9 @@ __device__ __forceinline__ void epi_direct16(const uint32_t (&r)[32], const floa
 }
 
 template <int BN, int ACT, int RES, int OUT, int CONV>
-__global__ void __launch_bounds__(CONV ? kGemm2Threads + 64 : kGemm2Threads, 1)
+__global__ void __launch_bounds__(CONV == 1 ? kGemm2Threads + 64 : kGemm2Threads, 1)
 gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                       int64_t M, int64_t N, int64_t K, EpiParams ep, ConvGather cg) {
+                       int64_t M, int64_t N, int64_t K, EpiParams ep, ConvGather cg, TmaConv tc) {
   using Cfg = Gemm2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -343,6 +424,10 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;        // [2]
   uint64_t* tmem_empty_bar = bars + 2 * Cfg::kStages + 2;   // [2]
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::kStages + 4);
+  uint64_t* wres_bar = bars + 2 * Cfg::kStages + 5;         // CONV >= 2, resident weights
+  const bool wres = CONV >= 2 && tc.wres;
+  const int nst = wres ? tc.nst : Cfg::kStages;             // A-only stages behind the resident weights
+  uint8_t* const a_ring = wres ? smem + tc.wres_bytes : smem_a;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -354,8 +439,9 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    if (CONV >= 2) ptx::mbar_init(wres_bar, 1);
     for (int s = 0; s < Cfg::kStages; ++s) {
-      ptx::mbar_init(&full_bar[s], CONV ? 1 + kGatherThreads : 1);   // TMA thread (+ every gather thread in conv mode)
+      ptx::mbar_init(&full_bar[s], CONV == 1 ? 1 + kGatherThreads : 1);   // TMA thread (+ every gather thread in gather mode)
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -378,8 +464,43 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (wres) {                                                    // the live weight blocks, once per CTA
+        ptx::mbar_arrive_expect_tx(wres_bar, (uint32_t)tc.wres_bytes);
+        uint32_t off = 0;
+        for (int tp = 0; tp < tc.taps; ++tp) {
+          int lo = 0, hi = (int)N;
+          if (CONV == 3) convt_cols(tp, tc.cout, 0, (int)N, lo, hi);
+          for (int kc = 0; kc < tc.kb_per_tap; ++kc)
+            for (int r0 = lo; r0 < hi; r0 += tc.wbox) {
+              ptx::tma_load_2d(smem + off, &tmap_b, wres_bar, (tp * tc.kb_per_tap + kc) * kBK, r0);
+              off += (uint32_t)tc.wbox * 128u;
+            }
+        }
+      }
       for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
+        if (CONV >= 2) {
+          // shifted-window A tiles: tile = 128 consecutive pixels starting at row y0 of frame f0 (or whole frames from f0)
+          const int64_t m0 = (int64_t)m_blk * kBM;
+          const int f0 = (int)(m0 / tc.HW);
+          const int y0 = (int)(m0 - (int64_t)f0 * tc.HW) / tc.W;
+          for (int tp = 0; tp < tc.taps; ++tp) {
+            if (CONV == 3) {
+              int lo, hi;
+              convt_cols(tp, tc.cout, n_blk * BN, BN, lo, hi);
+              if (hi <= lo) continue;                                // this tap feeds none of the tile's output phases
+            }
+            const int ty = tp / tc.KW, tx = tp - ty * tc.KW;
+            for (int kc = 0; kc < tc.kb_per_tap; ++kc) {
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], wres ? Cfg::kABytes : Cfg::kStageBytes);
+              ptx::tma_load_4d(a_ring + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kc * kBK, tx - tc.pad, y0 + ty - tc.pad, f0);
+              if (!wres) ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], (tp * tc.kb_per_tap + kc) * kBK, n_blk * BN);
+              if (++stage == nst) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], CONV ? Cfg::kBBytes : Cfg::kStageBytes);
@@ -389,7 +510,7 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         }
       }
     }
-  } else if (CONV && (warp == 2 || warp == 3 || warp >= 12)) {
+  } else if (CONV == 1 && (warp == 2 || warp == 3 || warp >= 12)) {
     // ---------------- implicit-GEMM A gather (128 threads: warps 2, 3, 12, 13) ----------------
     // Lane layout: 8 lanes cover the 128 bytes of one A row (one 16-byte chunk each), 16 rows per pass, 8 passes per
     // k-block.  The producer is bound by the latency of its own instruction stream, not by memory: the first version
@@ -493,20 +614,52 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (wres) {
+        ptx::mbar_wait(wres_bar, 0);
+        ptx::tc_fence_after();
+      }
       for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t bdesc = make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
+        if (CONV >= 2) {
+          const int n_blk = (int)(t % n_tiles);
+          uint32_t started = 0;                                      // tap 0 covers every column of the tile: it initialises the accumulator
+          uint32_t woff = 0;                                         // resident weights: blocks lie in (tap, k-block) order, live rows only
+          for (int tp = 0; tp < tc.taps; ++tp) {
+            int lo = 0, hi = wres ? (int)N : BN;
+            if (CONV == 3) {
+              convt_cols(tp, tc.cout, n_blk * BN, wres ? (int)N : BN, lo, hi);
+              if (hi <= lo) continue;
+            }
+            const uint32_t idesc_t = (CONV == 3 || wres) ? make_idesc_f16kind(kBM, hi - lo, ep.fp16) : idesc;
+            for (int kc = 0; kc < tc.kb_per_tap; ++kc) {
+              ptx::mbar_wait(&full_bar[stage], phase);
+              ptx::tc_fence_after();
+              const uint64_t adesc = make_smem_desc_sw128(ptx::smem_u32(a_ring + stage * Cfg::kABytes));
+              const uint64_t bdesc = wres ? make_smem_desc_sw128(ptx::smem_u32(smem) + woff)
+                                          : make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes) + (uint32_t)lo * 128u);   // lo % 8 == 0: whole swizzle atoms
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k)
-            ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          ptx::umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+              for (int k = 0; k < kBK / kUmmaK; ++k)
+                ptx::umma_bf16(tmem_d + (uint32_t)lo, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_t, started | (uint32_t)k);
+              started = 1;
+              woff += (uint32_t)(hi - lo) * 128u;
+              ptx::umma_commit(&empty_bar[stage]);
+              if (++stage == nst) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else {
+          for (int kb = 0; kb < num_k_blocks; ++kb) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            const uint64_t adesc = make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
+            const uint64_t bdesc = make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k)
+              ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            ptx::umma_commit(&empty_bar[stage]);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
         }
         ptx::umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -525,6 +678,15 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const float alpha = ep.alpha;
     const float relu_floor = ep.post_relu ? 0.f : -INFINITY;
     constexpr int kColsPerWarp = BN / 2;
+    ResRaw<RES> rr;
+    int64_t rr_tile = -1;                                            // which (tile, tile column) rr holds
+    int rr_c = -1;
+    auto res_prefetch = [&](int64_t tt, int c) {                    // residuals of the chunk at tile column c of tile tt
+      rr_tile = tt; rr_c = c;
+      if (tt >= num_tiles) return;
+      const int64_t nn = (tt % n_tiles) * BN + c + chunk * 4;
+      load_res<RES>(rr, ep, sub_row, (tt / n_tiles) * kBM + quad * 32, M, nn < N, nn);
+    };
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
       // bias of the first column chunk: fetched BEFORE waiting for the accumulator, later chunks one iteration ahead, so the
@@ -533,6 +695,50 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int64_t nb = (int64_t)n_blk * BN + c + chunk * 4;
         return (has_bias && nb < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
+      if (CONV == 3) {
+        // Transposed conv: thread = input pixel m, a 32-column chunk = 32 channels of ONE output pixel (2y+py, 2x+px)
+        // (Cout % 32 == 0), i.e. 64 contiguous bytes per thread -> two 32-byte sector stores straight from the accumulator
+        // layout, no shared-memory transpose; the tcgen05.ld of chunk i+1 is in flight while chunk i is converted and stored.
+        // (r02 ncu: the staged epilogue spent 440 instructions per chunk on this layer - 128 input pixels produce 32 KB of
+        // output per tile against 640 clk of MMA work - and set the tile time; this path needs ~100.)
+        constexpr int kChunks = kColsPerWarp / 32;
+        const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp);
+        const int64_t m = (int64_t)m_blk * kBM + quad * 32 + lane;
+        const uint32_t cout = (uint32_t)tc.cout, mm = (uint32_t)m;
+        h16* drow = ep.out_bf16 + (size_t)cout * (size_t)(4u * mm - 2u * (mm & ((uint32_t)tc.W - 1u)));
+        const int nw = n_blk * BN + half * kColsPerWarp;
+        const bool lean = alpha == 1.f && !ep.post_relu;
+        ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+        ptx::tc_fence_after();
+        uint32_t r[2][32];
+        ptx::tmem_ld_32x32(t0, r[0]);
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+          ptx::tmem_ld_wait_regs(r[i & 1]);
+          if (i + 1 < kChunks) {
+            ptx::tmem_ld_32x32(t0 + 32 * (i + 1), r[(i + 1) & 1]);
+          } else {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          const uint32_t n0 = (uint32_t)(nw + 32 * i);
+          if ((int64_t)n0 < N) {                                     // warp-uniform
+            const uint32_t q = (n0 >= cout) + (n0 >= 2u * cout) + (n0 >= 3u * cout), co = n0 - q * cout;   // phases (0,0), (0,1), (1,1), (1,0)
+            h16* dst = drow + (q >> 1) * (2u * (uint32_t)tc.W * cout) + (((q + 1) >> 1) & 1u) * cout + co;
+            const float* bn = has_bias ? ep.bias + n0 : nullptr;
+            if (lean) {
+              if (fp16) epi_direct16<ACT, true, true>(r[i & 1], bn, alpha, relu_floor, dst, m < M, ep.act);
+              else      epi_direct16<ACT, false, true>(r[i & 1], bn, alpha, relu_floor, dst, m < M, ep.act);
+            } else {
+              if (fp16) epi_direct16<ACT, true>(r[i & 1], bn, alpha, relu_floor, dst, m < M, ep.act);
+              else      epi_direct16<ACT, false>(r[i & 1], bn, alpha, relu_floor, dst, m < M, ep.act);
+            }
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       if (OUT == kOutDirect16) {
         // software-pipelined: the tcgen05.ld of chunk i+1 is in flight while chunk i is converted and stored
         constexpr int kChunks = kColsPerWarp / 32;
@@ -564,6 +770,7 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         continue;
       }
       float4 b_next = load_bias(half * kColsPerWarp);
+      if (RES > 0 && (rr_tile != t || rr_c != half * kColsPerWarp)) res_prefetch(t, half * kColsPerWarp);   // (normally done by the previous tile's last chunk)
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const int64_t m_base = (int64_t)m_blk * kBM + quad * 32;
@@ -574,6 +781,7 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         if (c + 32 < (half + 1) * kColsPerWarp) b_next = load_bias(c + 32);
         const int64_t n0 = (int64_t)n_blk * BN + c;
         if (n0 >= N) break;                                          // warp-uniform
+        if (RES > 0 && (rr_tile != t || rr_c != c)) res_prefetch(t, c);   // not prefetched (a tile whose first chunk lay past N came in between)
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c), r);
         ptx::tmem_ld_wait();
@@ -583,9 +791,17 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         __syncwarp();
         const int64_t n = n0 + chunk * 4;
         const bool col_ok = n < N;                                   // N % 4 == 0 on this path
-        // (residuals may alias the output - in-place residual-stream update - so epi_chunk loads them before any store)
-        if (fp16) epi_chunk<ACT, RES, OUT, true>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep, st_s, st_q);
-        else      epi_chunk<ACT, RES, OUT, false>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep, st_s, st_q);
+        // (residuals may alias the output - in-place residual-stream update - so a chunk's residuals are loaded before any of
+        //  ITS stores; the prefetch of the following chunk reads other columns / another tile)
+        auto next = [&]() {
+          if (RES > 0) {
+            const int cn = c + 32;
+            if (cn < (half + 1) * kColsPerWarp && (int64_t)n_blk * BN + cn < N) res_prefetch(t, cn);
+            else res_prefetch(t + gridDim.x, half * kColsPerWarp);
+          }
+        };
+        if (fp16) epi_chunk<ACT, RES, OUT, true>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep, st_s, st_q, rr, next);
+        else      epi_chunk<ACT, RES, OUT, false>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep, st_s, st_q, rr, next);
         __syncwarp();
       }
       ptx::tc_fence_before();
@@ -776,6 +992,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const float alpha = ep.alpha;
     const float relu_floor = ep.post_relu ? 0.f : -INFINITY;
     constexpr int kColsPerWarp = BN / 2;
+    ResRaw<RES> rr;
+    int64_t rr_tile = -1;
+    int rr_c = -1;
+    auto res_prefetch = [&](int64_t tt, int c) {
+      rr_tile = tt; rr_c = c;
+      if (tt >= num_tiles) return;
+      const int64_t nn = (tt % n_tiles) * BN + c + chunk * 4;
+      load_res<RES>(rr, ep, sub_row, (tt / n_tiles) * 2 * kBM + (int64_t)rank * kBM + quad * 32, M, nn < N, nn);
+    };
     const uint32_t empty_remote[2] = {mapa_u32(ptx::smem_u32(&tmem_empty_bar[0]), 0), mapa_u32(ptx::smem_u32(&tmem_empty_bar[1]), 0)};
     for (int64_t t = pair; t < num_tiles; t += num_pairs) {
       const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
@@ -784,6 +1009,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         return (has_bias && nb < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
       float4 b_next = load_bias(half * kColsPerWarp);
+      if (RES > 0 && (rr_tile != t || rr_c != half * kColsPerWarp)) res_prefetch(t, half * kColsPerWarp);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const int64_t m_base = (int64_t)m_blk * 2 * kBM + (int64_t)rank * kBM + quad * 32;
@@ -794,6 +1020,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (c + 32 < (half + 1) * kColsPerWarp) b_next = load_bias(c + 32);
         const int64_t n0 = (int64_t)n_blk * BN + c;
         if (n0 >= N) break;
+        if (RES > 0 && (rr_tile != t || rr_c != c)) res_prefetch(t, c);
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c), r);
         ptx::tmem_ld_wait();
@@ -803,8 +1030,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         __syncwarp();
         const int64_t n = n0 + chunk * 4;
         const bool col_ok = n < N;
-        if (fp16) epi_chunk<ACT, RES, OUT, true>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep, st_s, st_q);
-        else      epi_chunk<ACT, RES, OUT, false>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep, st_s, st_q);
+        auto next = [&]() {
+          if (RES > 0) {
+            const int cn = c + 32;
+            if (cn < (half + 1) * kColsPerWarp && (int64_t)n_blk * BN + cn < N) res_prefetch(t, cn);
+            else res_prefetch(t + num_pairs, half * kColsPerWarp);
+          }
+        };
+        if (fp16) epi_chunk<ACT, RES, OUT, true>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep, st_s, st_q, rr, next);
+        else      epi_chunk<ACT, RES, OUT, false>(stg_addr, sub_row, chunk, m_base, M, col_ok, n, b4, alpha, relu_floor, ep, st_s, st_q, rr, next);
         __syncwarp();
       }
       ptx::tc_fence_before();
@@ -908,13 +1142,44 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_
   return NPVP_OK;
 }
 
+// 4-D 16-bit tensor map over channels-last activations [frames, H, W, C]: box = 64 channels x (bw x bh x bf = 128 pixels),
+// 128B swizzle, out-of-range pixels (the zero padding of the convolution, frames past the end) read as zeros.
+static int make_tmap_nhwc(CUtensorMap* map, const void* base, int64_t frames, int H, int W, int C, int fp16) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { npvp_set_error("cuTensorMapEncodeTiled entry point unavailable"); return NPVP_ERR_CUDA; }
+  const int HW = H * W;
+  const int bh = HW >= kBM ? kBM / W : H, bf = HW >= kBM ? 1 : kBM / HW;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)frames};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)HW * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)W, (cuuint32_t)bh, (cuuint32_t)bf};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { npvp_set_error("cuTensorMapEncodeTiled (NHWC) failed (%d): frames=%lld H=%d W=%d C=%d", (int)r, (long long)frames, H, W, C); return NPVP_ERR_CUDA; }
+  return NPVP_OK;
+}
+// geometry the shifted-window (TMA) A path can tile: 128-pixel tiles are whole rows of one frame or whole frames
+static bool tma_conv_geometry(int H, int W, int C) {
+  const int HW = H * W;
+  return C % kBK == 0 && W >= 1 && W <= kBM && kBM % W == 0 && (HW % kBM == 0 || kBM % HW == 0);
+}
+struct TmaConvHost {
+  TmaConv tc;
+  const void* x;
+  int64_t frames;
+  int H, W, C, convt;
+};
+
 static int g_num_sms = 0;
+static int g_conv_wres = 1;     // npvp_set_option("conv_wres", 0): TMA-window convolutions stream their weights with every A tile again (A/B switch)
+static int g_conv_tma = 1;      // npvp_set_option("conv_tma", 0): stride-1 zero-padded convolutions use the cp.async gather again (A/B switch)
 static int g_epi_direct = 0;   // npvp_set_option("gemm_epi_direct", 1): store 16-bit outputs straight from the accumulator layout (see epi_direct16)
 static int g_use_2cta = -1;     // npvp_set_option("gemm_2cta", v): 1 = always for N >= 256, 0 = never, -1 (default) = when K >= 1024
 
 template <int BN, int ACT, int RES, int OUT, int CONV>
 static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, int64_t M, int64_t N, int64_t K, const EpiParams& e,
-                          const ConvGather& cg, unsigned grid, cudaStream_t st) {
+                          const ConvGather& cg, const TmaConv& tc, unsigned grid, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -922,15 +1187,15 @@ static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, int64_t 
     if (err != cudaSuccess) { npvp_set_error("cudaFuncSetAttribute(v2, smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
     attr_set = true;
   }
-  gemm_tcgen05_v2_kernel<BN, ACT, RES, OUT, CONV><<<grid, CONV ? kGemm2Threads + 64 : kGemm2Threads, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K, e, cg);
-  NPVP_LAUNCH_CHECK(CONV ? "gemm_tcgen05_v2_kernel<conv>" : "gemm_tcgen05_v2_kernel");
+  gemm_tcgen05_v2_kernel<BN, ACT, RES, OUT, CONV><<<grid, CONV == 1 ? kGemm2Threads + 64 : kGemm2Threads, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K, e, cg, tc);
+  NPVP_LAUNCH_CHECK(CONV == 1 ? "gemm_tcgen05_v2_kernel<conv gather>" : (CONV ? "gemm_tcgen05_v2_kernel<conv tma>" : "gemm_tcgen05_v2_kernel"));
   return NPVP_OK;
 }
 
 // Epilogue specialisations used by the engines; anything else runs the run-time-flag instantiation <-1,-1,-1>.
 template <int BN>
 static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
-                             const EpiParams& e, cudaStream_t st, const ConvGather* conv = nullptr) {
+                             const EpiParams& e, cudaStream_t st, const ConvGather* conv = nullptr, const TmaConvHost* tmc = nullptr) {
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -940,7 +1205,26 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&tb, W, N, K, ldw, BN, e.fp16);
   if (rc) return rc;
-  if (conv) ta = tb;                                   // unused in conv mode (A is gathered), keep the parameter valid
+  TmaConv tc0 = tmc ? tmc->tc : TmaConv{};
+  if (tmc) {
+    if ((rc = make_tmap_nhwc(&ta, tmc->x, tmc->frames, tmc->H, tmc->W, tmc->C, e.fp16))) return rc;
+    // resident weights (see TmaConv): one n-tile, live W beside >= 3 A stages inside the stage ring's shared memory
+    using Cfg = Gemm2Cfg<BN>;
+    const int64_t live_rows = tmc->convt ? 9LL * tc0.cout : (int64_t)N * tc0.taps;          // summed over taps
+    const int64_t wbytes = live_rows * tc0.kb_per_tap * 128;
+    const int wbox = tmc->convt ? tc0.cout : (int)N;
+    const int64_t ring = (int64_t)Cfg::kStages * Cfg::kStageBytes;
+    tc0.wres = 0;
+    if (g_conv_wres && N <= BN && N % 16 == 0 && wbox <= 256 && wbytes + 3 * Cfg::kABytes <= ring && wbytes < (1 << 20)) {
+      tc0.wres = 1;
+      tc0.wres_bytes = (int)wbytes;
+      tc0.wbox = wbox;
+      const int64_t nst = (ring - wbytes) / Cfg::kABytes;
+      tc0.nst = (int)(nst < Cfg::kStages ? nst : Cfg::kStages);
+      if ((rc = make_tmap_2d(&tb, W, N, K, ldw, wbox, e.fp16))) return rc;                   // boxes of `wbox` weight rows
+    }
+  }
+  else if (conv) ta = tb;                              // unused in gather mode, keep the parameter valid
   else if ((rc = make_tmap_2d(&ta, A, M, K, lda, kBM, e.fp16))) return rc;
   const int64_t tiles = ceil_div64(M, kBM) * ceil_div64(N, BN);
   const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
@@ -948,31 +1232,45 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
   const int res = !e.res1 ? (e.res2 ? -1 : 0) : (!e.res2 ? (e.res1_bf16 ? 2 : 1) : ((e.res1_bf16 && e.res2_bf16) ? 3 : -1));
   const int out = (e.out_f32 && e.out_bf16) ? 2 : (e.out_f32 ? 1 : 0);
   const int act = e.act;
+  if (tmc) {
+    if (tmc->convt) {
+      if (act == NPVP_ACT_RELU && res == 0 && out == 0) return launch_v2_inst<BN, NPVP_ACT_RELU, 0, 0, 3>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
+      if (res == 0 && out == 0) return launch_v2_inst<BN, -1, 0, 0, 3>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
+      npvp_set_error("transposed conv: 16-bit output without residuals only");
+      return NPVP_ERR_INVALID;
+    }
+#define NPVP_V2_TCONV(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_, 2>(ta, tb, M, N, K, e, cg0, tc0, grid, st)
+    NPVP_V2_TCONV(NPVP_ACT_RELU, 0, 0);
+    NPVP_V2_TCONV(NPVP_ACT_RELU, 2, 0);
+    NPVP_V2_TCONV(NPVP_ACT_NONE, 2, 0);
+#undef NPVP_V2_TCONV
+    return launch_v2_inst<BN, -1, -1, -1, 2>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
+  }
   // 16-bit output without residuals: store straight from the accumulator layout when every 32-column chunk of a row is a
   // whole, 32-byte aligned run of sectors
   const bool direct = g_epi_direct && res == 0 && out == 0 && N % 32 == 0 && e.ld_out % 16 == 0 && ((uintptr_t)e.out_bf16 % 32) == 0;
   if (conv) {
-    if (direct && act == NPVP_ACT_RELU) return launch_v2_inst<BN, NPVP_ACT_RELU, 0, kOutDirect16, 1>(ta, tb, M, N, K, e, cg0, grid, st);
-#define NPVP_V2_CONV(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_, 1>(ta, tb, M, N, K, e, cg0, grid, st)
+    if (direct && act == NPVP_ACT_RELU) return launch_v2_inst<BN, NPVP_ACT_RELU, 0, kOutDirect16, 1>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
+#define NPVP_V2_CONV(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_, 1>(ta, tb, M, N, K, e, cg0, tc0, grid, st)
     NPVP_V2_CONV(NPVP_ACT_RELU, 0, 0);   // conv / transposed conv + BN + ReLU
     NPVP_V2_CONV(NPVP_ACT_RELU, 2, 0);   // F3D conv: ReLU(BN(conv)) + x
     NPVP_V2_CONV(NPVP_ACT_NONE, 2, 0);   // ResnetBlock second conv + skip
     NPVP_V2_CONV(NPVP_ACT_NONE, 2, 1);   // ... last block: fp32 tokens out
 #undef NPVP_V2_CONV
-    return launch_v2_inst<BN, -1, -1, -1, 1>(ta, tb, M, N, K, e, cg0, grid, st);
+    return launch_v2_inst<BN, -1, -1, -1, 1>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
   }
   if (e.frame_stats) {
     if (BN == 256 && act == NPVP_ACT_NONE && res == 0 && out == 0)
-      return launch_v2_inst<256, NPVP_ACT_NONE, 0, kOutStats16, 0>(ta, tb, M, N, K, e, cg0, grid, st);
+      return launch_v2_inst<256, NPVP_ACT_NONE, 0, kOutStats16, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
     npvp_set_error("gemm: frame_stats needs the 256-wide tile, act NONE, no residual, 16-bit output only");
     return NPVP_ERR_INVALID;
   }
   if (direct) {
-    if (act == NPVP_ACT_NONE) return launch_v2_inst<BN, NPVP_ACT_NONE, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, grid, st);
-    if (act == NPVP_ACT_GELU) return launch_v2_inst<BN, NPVP_ACT_GELU, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, grid, st);
-    if (act == NPVP_ACT_RELU) return launch_v2_inst<BN, NPVP_ACT_RELU, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, grid, st);
+    if (act == NPVP_ACT_NONE) return launch_v2_inst<BN, NPVP_ACT_NONE, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
+    if (act == NPVP_ACT_GELU) return launch_v2_inst<BN, NPVP_ACT_GELU, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
+    if (act == NPVP_ACT_RELU) return launch_v2_inst<BN, NPVP_ACT_RELU, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
   }
-#define NPVP_V2_CASE(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_, 0>(ta, tb, M, N, K, e, cg0, grid, st)
+#define NPVP_V2_CASE(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st)
   NPVP_V2_CASE(NPVP_ACT_NONE, 0, 0);   // projections -> 16-bit
   NPVP_V2_CASE(NPVP_ACT_GELU, 0, 0);   // linear1
   NPVP_V2_CASE(NPVP_ACT_RELU, 0, 0);   // conv + BN + ReLU
@@ -983,7 +1281,7 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
   NPVP_V2_CASE(NPVP_ACT_NONE, 2, 0);   // ResnetBlock second conv + skip
   NPVP_V2_CASE(NPVP_ACT_NONE, 2, 1);   // ... last block: fp32 tokens out
 #undef NPVP_V2_CASE
-  return launch_v2_inst<BN, -1, -1, -1, 0>(ta, tb, M, N, K, e, cg0, grid, st);
+  return launch_v2_inst<BN, -1, -1, -1, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
 }
 
 template <int ACT, int RES, int OUT>
@@ -1138,11 +1436,47 @@ extern "C" int npvp_conv_gemm_bf16(const void* x, int64_t frames, int H, int W, 
   EpiParams e = make_epi(ep);
   cudaStream_t st = (cudaStream_t)stream;
   NPVP_REQUIRE((int64_t)frames * H * W < 0xffffffffll && M < 0xffffffffll, "npvp_conv_gemm_bf16: more than 2^32 - 1 input or output pixels per launch");
+  if (g_conv_tma && stride == 1 && !phase_major && Ho == H && Wo == W && KH == 2 * pad + 1 && KW == 2 * pad + 1 &&
+      (pad_mode == NPVP_PAD_ZERO || pad == 0) && tma_conv_geometry(H, W, C)) {
+    // stride-1 "same" convolution with zero padding: shifted-window A tiles by TMA (no gather warps)
+    TmaConvHost h;
+    h.tc.taps = KH * KW; h.tc.KW = KW; h.tc.pad = pad; h.tc.kb_per_tap = C / kBK; h.tc.HW = H * W; h.tc.W = W; h.tc.cout = 0;
+    h.tc.wres = 0; h.tc.wres_bytes = 0; h.tc.nst = 0; h.tc.wbox = 0;
+    h.x = x; h.frames = frames; h.H = H; h.W = W; h.C = C; h.convt = 0;
+    if (N >= 256) return launch_tcgen05_v2<256>(nullptr, 0, Wt, ldw, M, N, K, e, st, nullptr, &h);
+    if (N > 64) return launch_tcgen05_v2<128>(nullptr, 0, Wt, ldw, M, N, K, e, st, nullptr, &h);
+    return launch_tcgen05_v2<64>(nullptr, 0, Wt, ldw, M, N, K, e, st, nullptr, &h);
+  }
   if (N >= 256 && C >= 64) return launch_tcgen05_v2<256>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);   // (C == 32 needs the 2-tap table)
   if (N > 64) return launch_tcgen05_v2<128>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);
   return launch_tcgen05_v2<64>(nullptr, 0, Wt, ldw, M, N, K, e, st, &cg);
 }
 
+
+// Transposed convolution ConvTranspose2d(3, stride 2, pad 1, output_pad 1) as ONE implicit GEMM over the 2x2 input
+// neighbourhood: out[f, 2y+py, 2x+px, co] = sum_{dy,dx,ci} x[f, y+dy, x+dx, ci] * Wt[(q(py,px), co), (dy,dx,ci)], phases ordered
+// q = (0,0), (0,1), (1,1), (1,0).  Only the 9 live (phase, tap) blocks are loaded and multiplied; x and out are plain NHWC.
+extern "C" int npvp_convt_gemm_bf16(const void* x, int64_t frames, int H, int W, int Cin, const void* Wt, int64_t ldw, int Cout,
+                                    const npvp_epilogue_t* ep, void* stream) {
+  NPVP_REQUIRE(x && Wt && ep && frames > 0, "npvp_convt_gemm_bf16: null pointer");
+  NPVP_REQUIRE(H > 0 && W > 0 && (W & (W - 1)) == 0 && tma_conv_geometry(H, W, Cin),
+               "npvp_convt_gemm_bf16: needs Cin %% 64 == 0, W a power of two <= 128 and frames tiled by 128-pixel blocks (H=%d W=%d Cin=%d)", H, W, Cin);
+  NPVP_REQUIRE(Cout > 0 && Cout % 32 == 0, "npvp_convt_gemm_bf16: Cout must be a multiple of 32 (got %d)", Cout);
+  const int64_t M = frames * H * W, N = 4LL * Cout, K = 4LL * Cin;
+  NPVP_REQUIRE(ldw >= K && ldw % 8 == 0 && (uintptr_t)Wt % 16 == 0 && (uintptr_t)x % 16 == 0, "npvp_convt_gemm_bf16: weight/activation alignment");
+  NPVP_REQUIRE(ep->out_bf16 && !ep->out_f32 && !ep->res1 && !ep->res2 && !ep->frame_stats && (uintptr_t)ep->out_bf16 % 16 == 0,
+               "npvp_convt_gemm_bf16: one 16-byte aligned 16-bit output, no residuals");
+  NPVP_REQUIRE(4 * M < 0xffffffffll, "npvp_convt_gemm_bf16: more than 2^32 - 1 output pixels per launch");
+  NPVP_REQUIRE((uintptr_t)ep->out_bf16 % 32 == 0, "npvp_convt_gemm_bf16: output must be 32-byte aligned (sector stores)");
+  EpiParams e = make_epi(ep);
+  TmaConvHost h;
+  h.tc.taps = 4; h.tc.KW = 2; h.tc.pad = 0; h.tc.kb_per_tap = Cin / kBK; h.tc.HW = H * W; h.tc.W = W; h.tc.cout = Cout;
+  h.tc.wres = 0; h.tc.wres_bytes = 0; h.tc.nst = 0; h.tc.wbox = 0;
+  h.x = x; h.frames = frames; h.H = H; h.W = W; h.C = Cin; h.convt = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N >= 256) return launch_tcgen05_v2<256>(nullptr, 0, Wt, ldw, M, N, K, e, st, nullptr, &h);
+  return launch_tcgen05_v2<128>(nullptr, 0, Wt, ldw, M, N, K, e, st, nullptr, &h);
+}
 
 void npvp_set_ffn_scalar(int v);   // predictor_kernels.cu
 void npvp_set_ffn_mid16_mode(int m);   // ffn_mid16.cu
@@ -1151,6 +1485,8 @@ extern "C" int npvp_set_option(const char* name, int value) {
   NPVP_REQUIRE(name != nullptr, "npvp_set_option: null name");
   if (strcmp(name, "gemm_2cta") == 0) { g_use_2cta = value; return NPVP_OK; }
   if (strcmp(name, "gemm_epi_direct") == 0) { g_epi_direct = value; return NPVP_OK; }
+  if (strcmp(name, "conv_tma") == 0) { g_conv_tma = value; return NPVP_OK; }
+  if (strcmp(name, "conv_wres") == 0) { g_conv_wres = value; return NPVP_OK; }
   if (strcmp(name, "ffn_scalar") == 0) { npvp_set_ffn_scalar(value); return NPVP_OK; }
   if (strcmp(name, "ffn_mid16_mode") == 0) { npvp_set_ffn_mid16_mode(value); return NPVP_OK; }
   NPVP_REQUIRE(false, "npvp_set_option: unknown option '%s'", name);

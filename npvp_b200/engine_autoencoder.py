@@ -163,32 +163,52 @@ class DecoderEngine:
         self.ws = Workspace(self.device)
         self.dt = ae_dtype()
         self.ups = []
-        for i in range(mod.n_downsampling):
-            convt, bn = mod.model[3 * i], mod.model[3 * i + 1]
-            self.ups.append(self._pack_convT(convt, bn, self.dt))
+        self.ups_sig = tuple((mod.model[3 * i].weight.shape[0], mod.model[3 * i].weight.shape[1]) for i in range(mod.n_downsampling))
+        self._ups_tma = None      # packed on first use: the layout depends on the feature-map size (see run)
         head = mod.model[3 * mod.n_downsampling + 1]
         self.head_w = _lib.pack_head_weights(_pack_conv7x7(head), self.dt)
         self.head_b = _f(head.bias)
         self.head_cin, self.cout = head.weight.shape[1], head.weight.shape[0]
         self.act = ACT_TANH if mod.out_layer == 'Tanh' else ACT_SIGMOID
 
+    # output phases (py,px) along N.  The gather path keeps the natural order and leaves its output phase-major; the TMA path
+    # (npvp_convt_gemm_bf16) orders them so that every tap feeds a contiguous column range (zero blocks skipped) and stores NHWC.
+    PHASES_GATHER = ((0, 0), (0, 1), (1, 0), (1, 1))
+    PHASES_TMA = ((0, 0), (0, 1), (1, 1), (1, 0))
+
     @staticmethod
-    def _pack_convT(convt: nn.ConvTranspose2d, bn: nn.BatchNorm2d, dt):
-        """ConvTranspose2d(3,s2,p1,op1) weight [Cin,Cout,3,3] -> bf16 [(py,px,co), (dy,dx,ci)] over the 2x2 input
-        neighbourhood: out[2a+py, 2b+px] = sum_{dy,dx} in[a+dy, b+dx] * w[ky(py,dy), kx(px,dx)], where
+    def _pack_convT(convt: nn.ConvTranspose2d, bn: nn.BatchNorm2d, dt, phases=PHASES_GATHER):
+        """ConvTranspose2d(3,s2,p1,op1) weight [Cin,Cout,3,3] -> 16-bit [(q,co), (dy,dx,ci)] over the 2x2 input
+        neighbourhood, q enumerating ``phases``: out[2a+py, 2b+px] = sum_{dy,dx} in[a+dy, b+dx] * w[ky(py,dy), kx(px,dx)], where
         (p=0,d=0)->k=1, (p=1,d=0)->k=2, (p=1,d=1)->k=0 and (p=0,d=1) is dead."""
         scale, shift = _bn_fold(bn)
         w = convt.weight.detach().float()                       # [Cin, Cout, 3, 3]
         Cin, Cout = w.shape[0], w.shape[1]
         tap = {(0, 0): 1, (1, 0): 2, (1, 1): 0}
-        B = torch.zeros(2, 2, Cout, 2, 2, Cin, dtype=torch.float32, device=w.device)
-        for (py, dy), ky in tap.items():
-            for (px, dx), kx in tap.items():
-                B[py, px, :, dy, dx, :] = (w[:, :, ky, kx] * scale[None, :]).t()
+        B = torch.zeros(4, Cout, 2, 2, Cin, dtype=torch.float32, device=w.device)
+        for q, (py, px) in enumerate(phases):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    if (py, dy) in tap and (px, dx) in tap:
+                        B[q, :, dy, dx, :] = (w[:, :, tap[(py, dy)], tap[(px, dx)]] * scale[None, :]).t()
         bias = shift.repeat(4)
         if convt.bias is not None:
             bias = bias + (scale * convt.bias.detach().float()).repeat(4)
         return _h(B.reshape(4 * Cout, 4 * Cin), dt), bias.contiguous(), Cin, Cout
+
+    def _packed_ups(self, H, W):
+        """(tma, [packed layers]): the TMA form when every layer's geometry allows it, else the gather form for all
+        (the two leave different activation layouts, so they are not mixed inside one chain)."""
+        op, mod = _lib.ops(), self.mod
+        tma, h, w = os.environ.get("NPVP_B200_CONVT", "tma") != "gather", H, W
+        for cin, cout in self.ups_sig:
+            tma = tma and op.convt_supported(h, w, cin, cout)
+            h, w = 2 * h, 2 * w
+        if self._ups_tma != tma:
+            phases = self.PHASES_TMA if tma else self.PHASES_GATHER
+            self.ups = [self._pack_convT(mod.model[3 * i], mod.model[3 * i + 1], self.dt, phases) for i in range(mod.n_downsampling)]
+            self._ups_tma = tma
+        return tma, self.ups
 
     def run(self, x, channels_last=False, renorm=None, want_f32=True):
         """x: (N,T,C,h,w) fp32, or channels-last (N,T,h,w,C) fp32/bf16 -> frames (N,T,Cimg,H,W) fp32.
@@ -210,12 +230,18 @@ class DecoderEngine:
             C, H, W = x.shape[2], x.shape[3], x.shape[4]
             cur = ws.h16("in", self.dt, frames * H * W, C)
             op.nchw_to_tokens(x.to(torch.float32).view(frames, C, H * W), out_bf16=cur.view(frames, H * W, C))
-        assert C == self.ups[0][2], f"decoder expects {self.ups[0][2]} feature channels, got {C}"
+        assert C == self.ups_sig[0][0], f"decoder expects {self.ups_sig[0][0]} feature channels, got {C}"
+        tma, ups = self._packed_ups(H, W)
         phase = False
-        for i, (w, b, Cin, Cout) in enumerate(self.ups):
-            nxt = ws.h16(f"up{i}", self.dt, frames * H * W, 4 * Cout)
-            op.conv_gemm(cur, w, frames, H, W, Cin, 2, 2, 1, 0, PAD_ZERO, H, W, phase, bias=b, act=ACT_RELU, out_bf16=nxt)
-            cur, H, W, phase = nxt, 2 * H, 2 * W, True
+        for i, (w, b, Cin, Cout) in enumerate(ups):
+            if tma:      # zero blocks skipped, A tiles by TMA, plain NHWC out
+                nxt = ws.h16(f"up{i}", self.dt, frames * 4 * H * W, Cout)
+                op.convt_gemm(cur, w, frames, H, W, Cin, Cout, bias=b, act=ACT_RELU, out_bf16=nxt)
+                cur, H, W = nxt, 2 * H, 2 * W
+            else:        # dense 2x2-neighbourhood GEMM with a cp.async gather, output left phase-major
+                nxt = ws.h16(f"up{i}", self.dt, frames * H * W, 4 * Cout)
+                op.conv_gemm(cur, w, frames, H, W, Cin, 2, 2, 1, 0, PAD_ZERO, H, W, phase, bias=b, act=ACT_RELU, out_bf16=nxt)
+                cur, H, W, phase = nxt, 2 * H, 2 * W, True
         out = torch.empty(N, T, self.cout, H, W, dtype=torch.float32, device=self.device) if (want_f32 or renorm is None) else None
         out_u8 = torch.empty(N, T, self.cout, H, W, dtype=torch.uint8, device=self.device) if renorm is not None else None
         op.conv7x7_head(cur, self.head_w, self.head_b, out, self.head_cin, self.cout, H, W, phase, self.act, out_u8=out_u8, renorm=renorm)

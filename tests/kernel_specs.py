@@ -82,6 +82,24 @@ class SpecOps:
         self.launches -= 1
         self.gemm(col, w, **epi)
 
+    @staticmethod
+    def convt_supported(H, W, Cin, Cout):
+        from npvp_b200._lib import Ops
+        return Ops.convt_supported(H, W, Cin, Cout)
+
+    def convt_gemm(self, x, w, frames, H, W, Cin, Cout, *, bias=None, act=ACT_NONE, out_bf16=None):
+        self.launches += 1
+        img = F.pad(x.float().reshape(frames, H, W, Cin), (0, 0, 0, 1, 0, 1))                  # zero row / column past the edge
+        nb = torch.stack([img[:, dy:dy + H, dx:dx + W, :] for dy in (0, 1) for dx in (0, 1)], dim=3)   # (f,H,W,(dy,dx),ci)
+        v = nb.reshape(frames * H * W, 4 * Cin) @ w.float().t()                                # columns (q, co)
+        if bias is not None:
+            v = v + bias
+        v = _act(v, act).reshape(frames, H, W, 4, Cout)
+        o = torch.empty(frames, H, 2, W, 2, Cout, dtype=torch.float32, device=x.device)
+        for q, (py, px) in enumerate(((0, 0), (0, 1), (1, 1), (1, 0))):
+            o[:, :, py, :, px, :] = v[:, :, :, q, :]
+        out_bf16.copy_(o.reshape(out_bf16.shape).clamp(-65504, 65504).to(out_bf16.dtype))
+
     def gemm_f32(self, a, w, bias, act, out):
         self.launches += 1
         v = a @ w.t()

@@ -358,6 +358,93 @@ def test_conv_gemm_implicit(op, spec, dt, frames, H, C, N, KH, stride, pad, mode
     close(outs[0], outs[1], 1e-2 if dt == torch.bfloat16 else 2e-3, "conv_gemm")
 
 
+@pytest.mark.parametrize("dt", H16)
+@pytest.mark.parametrize("frames,H,C,N,KH,epi", [
+    (3, 8, 128, 128, 3, "relu_res"),        # two 8x8 frames per 128-pixel tile, odd frame count (the last tile overhangs)
+    (2, 32, 64, 64, 3, "relu"),             # four rows per tile
+    (1, 128, 64, 64, 3, "relu_res"),        # one row per tile
+    (5, 16, 256, 256, 3, "res_f32"),        # run-time epilogue flags, several k-blocks per tap
+    (2, 16, 64, 512, 5, "relu"),            # 5x5 window: shifts of +-2
+    (300, 16, 64, 64, 3, "relu_res")])      # resident weights, many tiles per CTA (stage ring wraps)
+def test_conv_gemm_tma_window(op, spec, dt, frames, H, C, N, KH, epi):
+    """stride-1 zero-padded convolutions load their A operand as shifted TMA windows; compared with the spec AND with the gather path"""
+    pad = KH // 2
+    x = rn(frames * H * H, C, seed=1, dtype=dt)
+    K = KH * KH * C
+    w = rn(N, K, seed=2, scale=K ** -0.5, dtype=dt)
+    bias = rn(N, seed=3)
+    M = frames * H * H
+    res = rn(M, N, seed=4, dtype=dt)
+
+    def run(o):
+        if epi == "relu":
+            out = torch.empty(M, N, device=DEV, dtype=dt)
+            o.conv_gemm(x, w, frames, H, H, C, KH, KH, 1, pad, 0, H, H, False, act=1, out_bf16=out, bias=bias)
+        elif epi == "relu_res":
+            out = torch.empty(M, N, device=DEV, dtype=dt)
+            o.conv_gemm(x, w, frames, H, H, C, KH, KH, 1, pad, 0, H, H, False, act=1, res1=res, out_bf16=out, bias=bias)
+        else:
+            out = torch.empty(M, N, device=DEV)
+            o.conv_gemm(x, w, frames, H, H, C, KH, KH, 1, pad, 0, H, H, False, res1=res, post_relu=True, out_f32=out, bias=bias)
+        return out
+    o_tma, o_spec = run(op), run(spec)
+    op.lib.npvp_set_option(b"conv_tma", 0)
+    try:
+        o_gather = run(op)
+    finally:
+        op.lib.npvp_set_option(b"conv_tma", 1)
+    op.lib.npvp_set_option(b"conv_wres", 0)
+    try:
+        o_stream = run(op)
+    finally:
+        op.lib.npvp_set_option(b"conv_wres", 1)
+    close(o_tma, o_spec, 1e-2 if dt == torch.bfloat16 else 2e-3, "conv_gemm tma")
+    assert torch.equal(o_tma, o_gather), "TMA-window and gather paths must agree bitwise (same MMA order)"
+    assert torch.equal(o_tma, o_stream), "resident and streamed weights must agree bitwise"
+
+
+@pytest.mark.parametrize("dt", H16)
+@pytest.mark.parametrize("frames,H,Cin,Cout", [(3, 8, 512, 256), (2, 16, 256, 128), (3, 32, 128, 64), (2, 64, 64, 32), (5, 8, 128, 64),
+                                               (1, 16, 64, 96)])
+def test_convt_gemm(op, spec, dt, frames, H, Cin, Cout):
+    """transposed conv: live (phase, tap) blocks only, NHWC in / NHWC out; random dense weights in EVERY block of Wt so that a
+    wrongly skipped or wrongly included block shows (the kernel must ignore the 7 dead blocks, the spec zeroes them)"""
+    x = rn(frames * H * H, Cin, seed=1, dtype=dt)
+    w = rn(4 * Cout, 4 * Cin, seed=2, scale=(2.25 * Cin) ** -0.5, dtype=dt)
+    live = torch.zeros(4, 1, 4, 1, device=DEV)
+    for q, (py, px) in enumerate(((0, 0), (0, 1), (1, 1), (1, 0))):
+        for dy in range(py + 1):
+            for dx in range(px + 1):
+                live[q, 0, dy * 2 + dx, 0] = 1
+    w_live = (w.float().reshape(4, Cout, 4, Cin) * live).reshape(4 * Cout, 4 * Cin).to(dt)
+    bias = rn(4 * Cout, seed=3)
+    o1 = torch.full((frames * 4 * H * H, Cout), float("nan"), device=DEV, dtype=dt)
+    o2 = torch.empty_like(o1)
+    op.convt_gemm(x, w, frames, H, H, Cin, Cout, bias=bias, act=1, out_bf16=o1)       # dead blocks hold garbage: must not be read
+    spec.convt_gemm(x, w_live, frames, H, H, Cin, Cout, bias=bias, act=1, out_bf16=o2)
+    assert not torch.isnan(o1.float()).any(), "convt_gemm left output pixels unwritten"
+    close(o1, o2, 1e-2 if dt == torch.bfloat16 else 2e-3, "convt_gemm")
+    o3 = torch.empty_like(o1)
+    op.lib.npvp_set_option(b"conv_wres", 0)
+    try:
+        op.convt_gemm(x, w, frames, H, H, Cin, Cout, bias=bias, act=1, out_bf16=o3)
+    finally:
+        op.lib.npvp_set_option(b"conv_wres", 1)
+    assert torch.equal(o1, o3), "resident and streamed weights must agree bitwise"
+    # and against torch's own transposed convolution on a weight in the nn.ConvTranspose2d layout
+    wt = rn(Cin, Cout, 3, 3, seed=5, scale=(2.25 * Cin) ** -0.5).to(dt).float()
+    tap = {(0, 0): 1, (1, 0): 2, (1, 1): 0}
+    B = torch.zeros(4, Cout, 2, 2, Cin, device=DEV)
+    for q, (py, px) in enumerate(((0, 0), (0, 1), (1, 1), (1, 0))):
+        for dy in (0, 1):
+            for dx in (0, 1):
+                if (py, dy) in tap and (px, dx) in tap:
+                    B[q, :, dy, dx, :] = wt[:, :, tap[(py, dy)], tap[(px, dx)]].t()
+    op.convt_gemm(x, B.reshape(4 * Cout, 4 * Cin).to(dt), frames, H, H, Cin, Cout, bias=None, act=0, out_bf16=o1)
+    ref = torch.nn.functional.conv_transpose2d(x.float().reshape(frames, H, H, Cin).permute(0, 3, 1, 2), wt, stride=2, padding=1, output_padding=1)
+    close(o1, ref.permute(0, 2, 3, 1).reshape(o1.shape).to(dt), 1e-2 if dt == torch.bfloat16 else 2e-3, "convt_gemm vs conv_transpose2d")
+
+
 def test_deferred_residual_layernorms(op, spec):
     n, T = 2, 3
     rows = n * T * 64

@@ -39,6 +39,12 @@ class Rec(SpecOps):
             self.conv = False
 
 
+    def convt_gemm(self, x, w, frames, H, W, Cin, Cout, **k):
+        self.shapes[("convT 9/16", frames * H * W, 4 * Cout, 4 * Cin, f"act{k.get('act', 0)}/16")] += 1
+        self.launches_before = self.launches
+        return super().convt_gemm(x, w, frames, H, W, Cin, Cout, **k)
+
+
 def main(preset="Cityscapes_VFP_NPVP-S", clips=1, scale=64):
     rec = Rec()
     _lib.set_ops(rec)
