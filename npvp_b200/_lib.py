@@ -136,9 +136,10 @@ class Ops:
         self.lib = lib or load_library()
         self.gemm_backend = {"auto": GEMM_AUTO, "tcgen05": GEMM_TCGEN05, "simt": GEMM_SIMT, "tcgen05_2cta": GEMM_TCGEN05_2CTA}[os.environ.get("NPVP_B200_GEMM", "auto")]
         self.lib.npvp_set_option(b"gemm_2cta", int(os.environ.get("NPVP_B200_GEMM_2CTA", "-1")))
-        self.lib.npvp_set_option(b"gemm_epi_direct", int(os.environ.get("NPVP_B200_GEMM_EPI_DIRECT", "0")))
+        self.lib.npvp_set_option(b"gemm_epi_direct", int(os.environ.get("NPVP_B200_GEMM_EPI_DIRECT", "1")))
         self.lib.npvp_set_option(b"ffn_mid16_mode", int(os.environ.get("NPVP_B200_FFN_MID16_MODE", "0")))
         self.lib.npvp_set_option(b"conv_tma", int(os.environ.get("NPVP_B200_CONV_TMA", "1")))
+        self.lib.npvp_set_option(b"gemm_prefetch", int(os.environ.get("NPVP_B200_GEMM_PREFETCH", "1")))
 
     # -- plumbing -------------------------------------------------------------------------------
     def _stream(self):

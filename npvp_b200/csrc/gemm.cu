@@ -67,6 +67,10 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// L2 prefetch of a box (no shared memory, no barrier): the A rows a CTA will stream a few k-blocks from now
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c_inner), "r"(c_outer) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -89,6 +93,44 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// One 64-element k-block = four K=16 MMAs, issued from ONE asm statement.  Descriptors are passed as their low words
+// (start address >> 4 | LBO; the high word - SBO 1024 B, version 1, SWIZZLE_128B - is the constant 0x40004040) and advance by
+// 32 bytes (+2) per K step.  r02 timeline (tools/ubench/gemm_trace.cu): the issuing thread needed ~300 clk between the last MMA
+// of a k-block and the first of the next (per-MMA descriptor arithmetic, an ELECT loop per operand conversion, the barrier
+// round trip) while the tensor pipe only queues ~2 MMAs: 765 clk per k-block against 512 clk of tensor work.
+__device__ __forceinline__ void umma_f16_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pt;\n\t.reg .b64 da, db;\n\t.reg .b32 la, lb;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 pt, %5, %5;\n\t"
+      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "add.u32 la, %1, 2;\n\tadd.u32 lb, %2, 2;\n\tmov.b64 da, {la, %5};\n\tmov.b64 db, {lb, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 la, %1, 4;\n\tadd.u32 lb, %2, 4;\n\tmov.b64 da, {la, %5};\n\tmov.b64 db, {lb, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 la, %1, 6;\n\tadd.u32 lb, %2, 6;\n\tmov.b64 da, {la, %5};\n\tmov.b64 db, {lb, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+      : "memory");
+}
+// non-blocking phase test (mbarrier.try_wait may suspend the thread for a while when the phase is still open)
+__device__ __forceinline__ bool mbar_test(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok));
+  return ok != 0;
 }
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -120,6 +162,13 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
                :
                : "memory");
 }
+// 256-bit global load (sm_100: LDG.256): one full 32-byte sector per thread.  Plain (coherent) load: residuals may alias the output.
+__device__ __forceinline__ void ldg256(const void* src, uint32_t* v) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(src)
+               : "memory");
+}
 // 256-bit global store (sm_100: STG.256): one full 32-byte sector per thread
 __device__ __forceinline__ void stg256(void* dst, const uint32_t* v) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
@@ -128,6 +177,16 @@ __device__ __forceinline__ void stg256(void* dst, const uint32_t* v) {
 }
 
 }  // namespace ptx
+
+// Optional timeline instrumentation (tools/ubench/gemm_trace.cu compiles this file with -DNPVP_GEMM_TRACE): CTA 0 records
+// clock64() at the pipeline hand-offs.  Never compiled into the library.
+#ifdef NPVP_GEMM_TRACE
+__device__ long long g_trace[8][8192];
+__device__ int g_trace_n[8];
+#define NPVP_TRACE(slot) do { if (blockIdx.x == 0) { int i_ = g_trace_n[slot]; if (i_ < 8192) { g_trace[slot][i_] = clock64(); g_trace_n[slot] = i_ + 1; } } } while (0)
+#else
+#define NPVP_TRACE(slot) do { } while (0)
+#endif
 
 // =============================================================================================
 // tcgen05 GEMM kernel
@@ -139,6 +198,8 @@ constexpr int kBK = 64;
 constexpr int kUmmaK = 16;
 
 // Shared-memory matrix descriptor: K-major, 128B swizzle, 8-row groups 1024 B apart (SBO), version 1 (sm_100).
+// low word of the same descriptor (see umma_f16_x4)
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address, 16-byte units
@@ -229,6 +290,7 @@ struct TmaConv {
   // (r02 launch list: the last transposed conv and the 64-channel 3x3 conv spent 2.6 / 4.2 us per 128-pixel tile re-fetching
   // the same 64 / 72 KB of weights from L2 - these layers are bound by the per-SM L2 ingest, not by the tensor pipe.)
   int wres, wres_bytes, nst, wbox;
+  int pf;                           // dense (CONV = 0): L2 prefetch of the A boxes a few k-blocks ahead of the ring (npvp_set_option("gemm_prefetch"))
 };
 __device__ __forceinline__ void convt_cols(int t, int cout, int n0, int bn, int& lo, int& hi) {
   const int a = t == 0 ? 0 : (t == 1 ? cout : 2 * cout);
@@ -360,28 +422,63 @@ __device__ __forceinline__ void epi_chunk(uint32_t stg_addr, int sub_row, int ch
   }
 }
 
-// OUT == 3 (opt-in, npvp_set_option("gemm_epi_direct", 1)): 16-bit output without residuals, written straight from the
-// accumulator layout (thread = row, 32 consecutive columns): bias / activation / rounding in registers, then two 32-byte
-// sector stores per thread, tcgen05.ld of the next chunk in flight meanwhile.  No shared-memory transpose.
-// Measured r01 (tools/bench_gemm.py, M=40960): identical to the staged epilogue within noise on every shape (fc1 84.0 vs
-// 85.0 us).  The ablation that explains it: dropping the global stores takes fc1 from 84 to 65.5 us, dropping the
-// tcgen05.ld changes nothing - the kernel is bound by L2 traffic (operand re-reads + output sectors, ~235 sectors/clk on
-// every shape), not by how the epilogue moves data inside the SM.  Kept as an A/B switch, off by default.
-constexpr int kOutDirect16 = 3;
-// LEAN: alpha == 1 and no post-ReLU floor (the caller checks) - two instructions per element less; with ACT == RELU the ReLU is
-// applied to the packed 16-bit pairs (rounding is monotonic and 0 is exact, so max(round(x), 0) == round(max(x, 0))).
-template <int ACT, bool FP16, bool LEAN = false>
-__device__ __forceinline__ void epi_direct16(const uint32_t (&r)[32], const float* __restrict__ bias_n0, float alpha, float relu_floor,
-                                             h16* __restrict__ dst, bool row_ok, int act_rt) {
+// DIRECT epilogue (OUT >= kDirect; the default whenever alignment allows, npvp_set_option("gemm_epi_direct", 0) = staged):
+// everything happens in the accumulator layout - thread = row, a chunk = 32 consecutive columns of that row (64 B of 16-bit
+// or 128 B of fp32 output, whole 32-byte sectors) - with the tcgen05.ld of chunk i+1 in flight while chunk i is converted
+// and stored, residuals loaded a chunk ahead, and NO shared-memory transpose.
+// Why (r02 timeline, tools/ubench/gemm_trace.cu): shared memory is the contended resource of this kernel.  Per 64-wide k-block
+// a 128 x 256 tile has TMA write 48 KB and the tensor core read 48 KB - 750 clk of the 128 B/clk port against 512 clk of MMA -
+// and the staged epilogue added a 32 KB write + 32 KB read per 32 x 256 columns on top: 5900 clk per tile (7800 in the 2-CTA
+// kernel) against 4400 for this path.  alpha == 1 and no post-ReLU are required (host-side choice): the per-element work is
+// bias add, activation, residual adds, rounding.
+constexpr int kDirect = 8;
+template <int RES>
+struct ResD {                                    // residuals of one chunk of one row, as loaded (32-byte sector loads)
+  uint32_t a[(RES == 2 || RES == 3) ? 16 : 1];   // 32 x 16-bit
+  uint32_t b[RES == 3 ? 16 : 1];
+  uint32_t f[RES == 1 ? 32 : 1];                 // 32 x fp32
+};
+template <int RES>
+__device__ __forceinline__ void load_resd(ResD<RES>& rs, const EpiParams& ep, int64_t m, int64_t n0, bool ok) {
+  const int64_t off = m * ep.ld_res + n0;
+  if (!ok) {                                     // (values of masked rows are never stored)
+    return;
+  }
+  if (RES == 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ptx::ldg256((const float*)ep.res1 + off + 8 * j, rs.f + 8 * j);
+  }
+  if (RES == 2 || RES == 3) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) ptx::ldg256((const h16*)ep.res1 + off + 16 * j, rs.a + 8 * j);
+  }
+  if (RES == 3) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) ptx::ldg256((const h16*)ep.res2 + off + 16 * j, rs.b + 8 * j);
+  }
+}
+__device__ __forceinline__ void add_h16x4(float (&v)[4], uint32_t lo, uint32_t hi, int fp16) {
+  const float2 a = unpack_h16x2(lo, fp16), b = unpack_h16x2(hi, fp16);
+  v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
+}
+// OUTK: 0 16-bit, 1 fp32, 2 both, 4 16-bit + statistics.  `next()` runs after the last use of rs and before the stores.
+template <int ACT, int RES, int OUTK, bool FP16, class Next>
+__device__ __forceinline__ void epi_direct_chunk(const uint32_t (&r)[32], const float* __restrict__ bias_n0, ResD<RES>& rs, float* out32, h16* out16,
+                                                 bool row_ok, float& st_s, float& st_q, Next&& next) {
   constexpr int fp16 = FP16 ? 1 : 0;
-  uint32_t p[16];
+  constexpr bool W16 = OUTK == 0 || OUTK == 2 || OUTK == 4, W32 = OUTK == 1 || OUTK == 2;
+  uint32_t p[W16 ? 16 : 1];
+  float4 w[W32 ? 8 : 1];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias_n0) b = __ldg(reinterpret_cast<const float4*>(bias_n0) + j);       // warp-uniform address: one L1 broadcast
-    if (LEAN && ACT == NPVP_ACT_RELU) {
-      p[2 * j] = pack_h16x2(__uint_as_float(r[4 * j + 0]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y, fp16);
-      p[2 * j + 1] = pack_h16x2(__uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w, fp16);
+    float v[4] = {__uint_as_float(r[4 * j + 0]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y, __uint_as_float(r[4 * j + 2]) + b.z,
+                  __uint_as_float(r[4 * j + 3]) + b.w};
+    if (ACT == NPVP_ACT_RELU && RES == 0 && OUTK == 0) {
+      // ReLU on the packed 16-bit pairs: rounding is monotonic and 0 is exact, so max(round(x), 0) == round(max(x, 0))
+      p[2 * j] = pack_h16x2(v[0], v[1], fp16);
+      p[2 * j + 1] = pack_h16x2(v[2], v[3], fp16);
       if (FP16) {
         const __half2 z = __float2half2_rn(0.f);
         *reinterpret_cast<__half2*>(&p[2 * j]) = __hmax2(*reinterpret_cast<__half2*>(&p[2 * j]), z);
@@ -393,18 +490,76 @@ __device__ __forceinline__ void epi_direct16(const uint32_t (&r)[32], const floa
       }
       continue;
     }
-    float v0 = act_ct<ACT>(__uint_as_float(r[4 * j + 0]) + b.x, act_rt), v1 = act_ct<ACT>(__uint_as_float(r[4 * j + 1]) + b.y, act_rt);
-    float v2 = act_ct<ACT>(__uint_as_float(r[4 * j + 2]) + b.z, act_rt), v3 = act_ct<ACT>(__uint_as_float(r[4 * j + 3]) + b.w, act_rt);
-    if (!LEAN) {
-      v0 = fmaxf(v0 * alpha, relu_floor); v1 = fmaxf(v1 * alpha, relu_floor);
-      v2 = fmaxf(v2 * alpha, relu_floor); v3 = fmaxf(v3 * alpha, relu_floor);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = act_ct<ACT>(v[e], 0);
+    if (RES == 1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] += __uint_as_float(rs.f[4 * j + e]);
     }
-    p[2 * j] = pack_h16x2(v0, v1, fp16);
-    p[2 * j + 1] = pack_h16x2(v2, v3, fp16);
+    if (RES == 2) add_h16x4(v, rs.a[2 * j], rs.a[2 * j + 1], fp16);
+    if (RES == 3) {                              // (res1 + res2) first, like the staged epilogue: bit-identical results
+      float u[4] = {0.f, 0.f, 0.f, 0.f};
+      add_h16x4(u, rs.a[2 * j], rs.a[2 * j + 1], fp16);
+      add_h16x4(u, rs.b[2 * j], rs.b[2 * j + 1], fp16);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] += u[e];
+    }
+    if (OUTK == 4) {
+      st_s += (v[0] + v[1]) + (v[2] + v[3]);
+      st_q = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], fmaf(v[3], v[3], st_q))));
+    }
+    if (W32) w[j] = make_float4(v[0], v[1], v[2], v[3]);
+    if (W16) { p[2 * j] = pack_h16x2(v[0], v[1], fp16); p[2 * j + 1] = pack_h16x2(v[2], v[3], fp16); }
   }
+  next();
   if (row_ok) {
-    ptx::stg256(dst, p);
-    ptx::stg256(dst + 16, p + 8);
+    if (W32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ptx::stg256(out32 + 8 * j, reinterpret_cast<const uint32_t*>(&w[2 * j]));
+    }
+    if (W16) {
+      ptx::stg256(out16, p);
+      ptx::stg256(out16 + 16, p + 8);
+    }
+  }
+}
+// One tile of one epilogue warp: KCH chunks starting at TMEM address t0 / global column n_first of row m.
+//   out_off(n0): element offset of (m, n0) in the outputs;  release(): this warp's part of the accumulator is in registers;
+//   next_tile(): residuals of the first chunk of the warp's NEXT tile into rs (RES > 0).
+template <int KCH, int ACT, int RES, int OUTK, class OutOff, class Release, class NextTile>
+__device__ __forceinline__ void epi_direct_tile(uint32_t t0, int64_t m, bool row_ok, int64_t n_first, int64_t N, const EpiParams& ep, bool has_bias,
+                                                int fp16, ResD<RES>& rs, float& st_s, float& st_q, OutOff&& out_off, Release&& release,
+                                                NextTile&& next_tile) {
+  uint32_t r0[32], r1[32];
+  auto process = [&](const uint32_t (&r)[32], int i) {
+    const int64_t n0 = n_first + 32 * i;
+    if (n0 >= N) return;                                             // warp-uniform; N % 32 == 0 on this path
+    const int64_t off = out_off(n0);
+    float* o32 = ep.out_f32 ? ep.out_f32 + off : nullptr;
+    h16* o16 = ep.out_bf16 ? ep.out_bf16 + off : nullptr;
+    const float* bn = has_bias ? ep.bias + n0 : nullptr;
+    auto next = [&]() {
+      if (RES > 0) {
+        if (i + 1 < KCH && n0 + 32 < N) load_resd<RES>(rs, ep, m, n0 + 32, row_ok);
+        else next_tile();
+      }
+    };
+    if (fp16) epi_direct_chunk<ACT, RES, OUTK, true>(r, bn, rs, o32, o16, row_ok, st_s, st_q, next);
+    else      epi_direct_chunk<ACT, RES, OUTK, false>(r, bn, rs, o32, o16, row_ok, st_s, st_q, next);
+  };
+  ptx::tmem_ld_32x32(t0, r0);
+#pragma unroll 1
+  for (int i = 0; i < KCH; i += 2) {
+    ptx::tmem_ld_wait_regs(r0);
+    if (i + 1 < KCH) ptx::tmem_ld_32x32(t0 + 32 * (i + 1), r1);
+    else release();
+    process(r0, i);
+    if (i + 1 < KCH) {
+      ptx::tmem_ld_wait_regs(r1);
+      if (i + 2 < KCH) ptx::tmem_ld_32x32(t0 + 32 * (i + 2), r0);
+      else release();
+      process(r1, i + 1);
+    }
   }
 }
 
@@ -413,6 +568,8 @@ __global__ void __launch_bounds__(CONV == 1 ? kGemm2Threads + 64 : kGemm2Threads
 gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        int64_t M, int64_t N, int64_t K, EpiParams ep, ConvGather cg, TmaConv tc) {
   using Cfg = Gemm2Cfg<BN>;
+  constexpr bool DIRECT = OUT >= kDirect;
+  constexpr int OUTK = DIRECT ? OUT - kDirect : OUT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -461,9 +618,11 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t empty0 = ptx::smem_u32(empty_bar);
+      bool freed = false;                                            // empty_bar[stage] already seen complete (tested one k-block ahead)
       if (wres) {                                                    // the live weight blocks, once per CTA
         ptx::mbar_arrive_expect_tx(wres_bar, (uint32_t)tc.wres_bytes);
         uint32_t off = 0;
@@ -477,6 +636,15 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             }
         }
       }
+      // Dense A streams from HBM exactly once, so every first touch of an A box is a DRAM-latency load: with 4 stages (192 KB)
+      // in flight per SM the ring sustained ~60 B/clk against the 96 B/clk a 128 x 256 tile needs (r02 timeline: operands
+      // landed 2000-3000 clk after their stage was freed).  An L2 prefetch kPfDist k-blocks ahead of the ring turns those into
+      // L2 hits without spending shared memory.
+      constexpr int kPfDist = 8;
+      int64_t pf_t = blockIdx.x;
+      int pf_kb = 0;
+      auto pf_advance = [&]() { if (++pf_kb == num_k_blocks) { pf_kb = 0; pf_t += gridDim.x; } };
+      if (!CONV && tc.pf) for (int i = 0; i < kPfDist; ++i) pf_advance();
       for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
         if (CONV >= 2) {
@@ -492,21 +660,35 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             }
             const int ty = tp / tc.KW, tx = tp - ty * tc.KW;
             for (int kc = 0; kc < tc.kb_per_tap; ++kc) {
-              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (!freed) ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              NPVP_TRACE(0);
+              int ns = stage + 1;
+              uint32_t np = phase;
+              if (ns == nst) { ns = 0; np ^= 1; }
+              freed = ptx::mbar_test(empty0 + 8u * (uint32_t)ns, np ^ 1);
               ptx::mbar_arrive_expect_tx(&full_bar[stage], wres ? Cfg::kABytes : Cfg::kStageBytes);
               ptx::tma_load_4d(a_ring + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kc * kBK, tx - tc.pad, y0 + ty - tc.pad, f0);
               if (!wres) ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], (tp * tc.kb_per_tap + kc) * kBK, n_blk * BN);
-              if (++stage == nst) { stage = 0; phase ^= 1; }
+              stage = ns; phase = np;
             }
           }
           continue;
         }
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (!freed) ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          NPVP_TRACE(0);
+          int ns = stage + 1;
+          uint32_t np = phase;
+          if (ns == Cfg::kStages) { ns = 0; np ^= 1; }
+          freed = ptx::mbar_test(empty0 + 8u * (uint32_t)ns, np ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], CONV ? Cfg::kBBytes : Cfg::kStageBytes);
           if (!CONV) ptx::tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
           ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, n_blk * BN);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (!CONV && tc.pf) {
+            if (pf_t < num_tiles) ptx::tma_prefetch_2d(&tmap_a, pf_kb * kBK, (int)(pf_t / n_tiles) * kBM);
+            pf_advance();
+          }
+          stage = ns; phase = np;
         }
       }
     }
@@ -608,18 +790,24 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t idesc = make_idesc_f16kind(kBM, BN, ep.fp16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      // stage s: operands at a_lo0 + s * kAStep / b_lo0 + s * kBStep (descriptor low words), full / empty barriers 8 s bytes on
+      const uint32_t a_lo0 = smem_desc_lo(ptx::smem_u32(a_ring)), b_lo0 = smem_desc_lo(ptx::smem_u32(smem_b));
+      const uint32_t full0 = ptx::smem_u32(full_bar);
+      constexpr uint32_t kAStep = Cfg::kABytes >> 4, kBStep = Cfg::kBBytes >> 4;
+      bool landed = false;                                           // full_bar[stage] already seen complete (tested one k-block ahead)
       if (wres) {
         ptx::mbar_wait(wres_bar, 0);
         ptx::tc_fence_after();
       }
       for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
+        NPVP_TRACE(3);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         if (CONV >= 2) {
@@ -634,31 +822,35 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             }
             const uint32_t idesc_t = (CONV == 3 || wres) ? make_idesc_f16kind(kBM, hi - lo, ep.fp16) : idesc;
             for (int kc = 0; kc < tc.kb_per_tap; ++kc) {
-              ptx::mbar_wait(&full_bar[stage], phase);
+              if (!landed) ptx::mbar_wait(&full_bar[stage], phase);
+              NPVP_TRACE(1);
               ptx::tc_fence_after();
-              const uint64_t adesc = make_smem_desc_sw128(ptx::smem_u32(a_ring + stage * Cfg::kABytes));
-              const uint64_t bdesc = wres ? make_smem_desc_sw128(ptx::smem_u32(smem) + woff)
-                                          : make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes) + (uint32_t)lo * 128u);   // lo % 8 == 0: whole swizzle atoms
-#pragma unroll
-              for (int k = 0; k < kBK / kUmmaK; ++k)
-                ptx::umma_bf16(tmem_d + (uint32_t)lo, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_t, started | (uint32_t)k);
+              int ns = stage + 1;
+              uint32_t np = phase;
+              if (ns == nst) { ns = 0; np ^= 1; }
+              landed = ptx::mbar_test(full0 + 8u * (uint32_t)ns, np);   // the next stage's barrier: its round trip hides behind the MMA issue
+              const uint32_t b_lo = wres ? smem_desc_lo(ptx::smem_u32(smem) + woff) : b_lo0 + (uint32_t)stage * kBStep + (uint32_t)lo * 8u;   // lo % 8 == 0: whole swizzle atoms
+              ptx::umma_f16_x4(tmem_d + (uint32_t)lo, a_lo0 + (uint32_t)stage * kAStep, b_lo, idesc_t, started);
               started = 1;
               woff += (uint32_t)(hi - lo) * 128u;
               ptx::umma_commit(&empty_bar[stage]);
-              if (++stage == nst) { stage = 0; phase ^= 1; }
+              NPVP_TRACE(2);
+              stage = ns; phase = np;
             }
           }
         } else {
           for (int kb = 0; kb < num_k_blocks; ++kb) {
-            ptx::mbar_wait(&full_bar[stage], phase);
+            if (!landed) ptx::mbar_wait(&full_bar[stage], phase);
+            NPVP_TRACE(1);
             ptx::tc_fence_after();
-            const uint64_t adesc = make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
-            const uint64_t bdesc = make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
-#pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k)
-              ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            int ns = stage + 1;
+            uint32_t np = phase;
+            if (ns == Cfg::kStages) { ns = 0; np ^= 1; }
+            landed = ptx::mbar_test(full0 + 8u * (uint32_t)ns, np);     // the next stage's barrier: its round trip hides behind the MMA issue
+            ptx::umma_f16_x4(tmem_d, a_lo0 + (uint32_t)stage * kAStep, b_lo0 + (uint32_t)stage * kBStep, idesc, (uint32_t)kb);
             ptx::umma_commit(&empty_bar[stage]);
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            NPVP_TRACE(2);
+            stage = ns; phase = np;
           }
         }
         ptx::umma_commit(&tmem_full_bar[acc]);
@@ -679,6 +871,8 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const float relu_floor = ep.post_relu ? 0.f : -INFINITY;
     constexpr int kColsPerWarp = BN / 2;
     ResRaw<RES> rr;
+    ResD<RES> rd;                                                    // direct epilogue: residuals of the chunk about to be processed
+    int64_t rd_tile = -1;                                            // tile whose first chunk rd was loaded for
     int64_t rr_tile = -1;                                            // which (tile, tile column) rr holds
     int rr_c = -1;
     auto res_prefetch = [&](int64_t tt, int c) {                    // residuals of the chunk at tile column c of tile tt
@@ -695,75 +889,51 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int64_t nb = (int64_t)n_blk * BN + c + chunk * 4;
         return (has_bias && nb < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
-      if (CONV == 3) {
-        // Transposed conv: thread = input pixel m, a 32-column chunk = 32 channels of ONE output pixel (2y+py, 2x+px)
-        // (Cout % 32 == 0), i.e. 64 contiguous bytes per thread -> two 32-byte sector stores straight from the accumulator
-        // layout, no shared-memory transpose; the tcgen05.ld of chunk i+1 is in flight while chunk i is converted and stored.
-        // (r02 ncu: the staged epilogue spent 440 instructions per chunk on this layer - 128 input pixels produce 32 KB of
-        // output per tile against 640 clk of MMA work - and set the tile time; this path needs ~100.)
-        constexpr int kChunks = kColsPerWarp / 32;
-        const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp);
-        const int64_t m = (int64_t)m_blk * kBM + quad * 32 + lane;
-        const uint32_t cout = (uint32_t)tc.cout, mm = (uint32_t)m;
-        h16* drow = ep.out_bf16 + (size_t)cout * (size_t)(4u * mm - 2u * (mm & ((uint32_t)tc.W - 1u)));
-        const int nw = n_blk * BN + half * kColsPerWarp;
-        const bool lean = alpha == 1.f && !ep.post_relu;
-        ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
-        ptx::tc_fence_after();
-        uint32_t r[2][32];
-        ptx::tmem_ld_32x32(t0, r[0]);
-#pragma unroll
-        for (int i = 0; i < kChunks; ++i) {
-          ptx::tmem_ld_wait_regs(r[i & 1]);
-          if (i + 1 < kChunks) {
-            ptx::tmem_ld_32x32(t0 + 32 * (i + 1), r[(i + 1) & 1]);
-          } else {
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-          }
-          const uint32_t n0 = (uint32_t)(nw + 32 * i);
-          if ((int64_t)n0 < N) {                                     // warp-uniform
-            const uint32_t q = (n0 >= cout) + (n0 >= 2u * cout) + (n0 >= 3u * cout), co = n0 - q * cout;   // phases (0,0), (0,1), (1,1), (1,0)
-            h16* dst = drow + (q >> 1) * (2u * (uint32_t)tc.W * cout) + (((q + 1) >> 1) & 1u) * cout + co;
-            const float* bn = has_bias ? ep.bias + n0 : nullptr;
-            if (lean) {
-              if (fp16) epi_direct16<ACT, true, true>(r[i & 1], bn, alpha, relu_floor, dst, m < M, ep.act);
-              else      epi_direct16<ACT, false, true>(r[i & 1], bn, alpha, relu_floor, dst, m < M, ep.act);
-            } else {
-              if (fp16) epi_direct16<ACT, true>(r[i & 1], bn, alpha, relu_floor, dst, m < M, ep.act);
-              else      epi_direct16<ACT, false>(r[i & 1], bn, alpha, relu_floor, dst, m < M, ep.act);
-            }
-          }
-        }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        continue;
-      }
-      if (OUT == kOutDirect16) {
-        // software-pipelined: the tcgen05.ld of chunk i+1 is in flight while chunk i is converted and stored
+      if (DIRECT) {
+        // (CONV == 3, transposed conv: row m = input pixel, a chunk = 32 channels of ONE output pixel (2y+py, 2x+px) since
+        //  Cout % 32 == 0; column n0 = (phase q, co) with q enumerating (py,px) = (0,0), (0,1), (1,1), (1,0))
         constexpr int kChunks = kColsPerWarp / 32;
         const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp);
         const int64_t m = (int64_t)m_blk * kBM + quad * 32 + lane;
         const int64_t nw = (int64_t)n_blk * BN + half * kColsPerWarp;
-        h16* drow = ep.out_bf16 + m * ep.ld_out + nw;
-        ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
-        ptx::tc_fence_after();
-        uint32_t r[2][32];
-        ptx::tmem_ld_32x32(t0, r[0]);
-#pragma unroll
-        for (int i = 0; i < kChunks; ++i) {
-          ptx::tmem_ld_wait_regs(r[i & 1]);
-          if (i + 1 < kChunks) {
-            ptx::tmem_ld_32x32(t0 + 32 * (i + 1), r[(i + 1) & 1]);
-          } else {                                                   // this warp's part of the accumulator is in registers
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        auto out_off = [&](int64_t n0) -> int64_t {
+          if (CONV == 3) {
+            const uint32_t cout = (uint32_t)tc.cout, mm = (uint32_t)m, nn = (uint32_t)n0;
+            const uint32_t q = (nn >= cout) + (nn >= 2u * cout) + (nn >= 3u * cout), co = nn - q * cout;
+            return (int64_t)cout * (int64_t)(4u * mm - 2u * (mm & ((uint32_t)tc.W - 1u))) +
+                   (int64_t)((q >> 1) * (2u * (uint32_t)tc.W * cout) + (((q + 1) >> 1) & 1u) * cout + co);
           }
-          const int64_t n0 = nw + 32 * i;
-          if (n0 < N) {                                              // warp-uniform; N % 32 == 0 on this path
-            if (fp16) epi_direct16<ACT, true>(r[i & 1], has_bias ? ep.bias + n0 : nullptr, alpha, relu_floor, drow + 32 * i, m < M, ep.act);
-            else      epi_direct16<ACT, false>(r[i & 1], has_bias ? ep.bias + n0 : nullptr, alpha, relu_floor, drow + 32 * i, m < M, ep.act);
+          return m * ep.ld_out + n0;
+        };
+        auto release = [&]() {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        };
+        auto next_tile = [&]() {
+          const int64_t tn = t + gridDim.x;
+          rd_tile = tn;
+          if (tn < num_tiles) {
+            const int64_t mn = (tn / n_tiles) * kBM + quad * 32 + lane;
+            load_resd<RES>(rd, ep, mn, (tn % n_tiles) * BN + half * kColsPerWarp, mn < M);
+          }
+        };
+        if (RES > 0 && rd_tile != t) load_resd<RES>(rd, ep, m, nw, m < M && nw < N);   // first tile of this warp
+        float st_s = 0.f, st_q = 0.f;
+        ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+        if (threadIdx.x == 128) NPVP_TRACE(4);
+        ptx::tc_fence_after();
+        epi_direct_tile<kChunks, ACT, RES, OUTK>(t0, m, m < M, nw, N, ep, has_bias, fp16, rd, st_s, st_q, out_off, release, next_tile);
+        if (threadIdx.x == 128) NPVP_TRACE(5);
+        if (OUTK == kOutStats16) {
+          // this warp's 32 rows x 128 columns lie inside one 64-row frame: one (sum, sum of squares) slot per warp and tile
+          st_s = warp_sum(st_s);
+          st_q = warp_sum(st_q);
+          if (lane == 0 && (int64_t)m_blk * kBM + quad * 32 < M) {
+            const int64_t frame = (int64_t)m_blk * 2 + (quad >> 1);
+            const int slot = ((n_blk * 2 + half) << 1) + (quad & 1);
+            float2* dst = reinterpret_cast<float2*>(ep.frame_stats) + frame * (n_tiles * 4) + slot;
+            *dst = make_float2(st_s, st_q);
           }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -772,6 +942,7 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       float4 b_next = load_bias(half * kColsPerWarp);
       if (RES > 0 && (rr_tile != t || rr_c != half * kColsPerWarp)) res_prefetch(t, half * kColsPerWarp);   // (normally done by the previous tile's last chunk)
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      if (threadIdx.x == 128) NPVP_TRACE(4);
       ptx::tc_fence_after();
       const int64_t m_base = (int64_t)m_blk * kBM + quad * 32;
       float st_s = 0.f, st_q = 0.f;                                  // OUT == kOutStats16 only
@@ -807,6 +978,7 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (threadIdx.x == 128) NPVP_TRACE(5);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (OUT == kOutStats16) {
         // this warp's 32 rows x 128 columns lie inside one 64-row frame: one (sum, sum of squares) slot per warp and tile
@@ -878,6 +1050,22 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, 
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16_x4_2cta(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {   // see ptx::umma_f16_x4
+  asm volatile(
+      "{\n\t.reg .pred p, pt;\n\t.reg .b64 da, db;\n\t.reg .b32 la, lb;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 pt, %5, %5;\n\t"
+      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+      "add.u32 la, %1, 2;\n\tadd.u32 lb, %2, 2;\n\tmov.b64 da, {la, %5};\n\tmov.b64 db, {lb, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 la, %1, 4;\n\tadd.u32 lb, %2, 4;\n\tmov.b64 da, {la, %5};\n\tmov.b64 db, {lb, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 la, %1, 6;\n\tadd.u32 lb, %2, 6;\n\tmov.b64 da, {la, %5};\n\tmov.b64 db, {lb, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {     // arrives on `bar` in BOTH CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(ptx::smem_u32(bar)), "h"((uint16_t)3) : "memory");
@@ -889,6 +1077,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                          int64_t M, int64_t N, int64_t K, EpiParams ep) {
   using Cfg = Gemm3Cfg;
   constexpr int BN = Cfg::BN;
+  constexpr bool DIRECT = OUT >= kDirect;
+  constexpr int OUTK = DIRECT ? OUT - kDirect : OUT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -936,44 +1126,58 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   if (warp == 0) {
     // ---------------- TMA producer (both CTAs) ----------------
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t empty0 = ptx::smem_u32(empty_bar);
+      bool freed = false;                                            // empty_bar[stage] already seen complete (tested one k-block ahead)
       for (int64_t t = pair; t < num_tiles; t += num_pairs) {
         const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
         const int m_row = m_blk * 2 * kBM + (int)rank * kBM;
         const int n_row = n_blk * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (!freed) ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          NPVP_TRACE(0);
+          int ns = stage + 1;
+          uint32_t np = phase;
+          if (ns == Cfg::kStages) { ns = 0; np ^= 1; }
+          freed = ptx::mbar_test(empty0 + 8u * (uint32_t)ns, np ^ 1);
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_row);
           tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, n_row);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          stage = ns; phase = np;
         }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer (leader CTA only) ----------------
-    if (leader && lane == 0) {
+    if (leader && ptx::elect_one()) {
       const uint32_t idesc = make_idesc_f16kind(2 * kBM, BN, ep.fp16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t a_lo0 = smem_desc_lo(ptx::smem_u32(smem_a)), b_lo0 = smem_desc_lo(ptx::smem_u32(smem_b));
+      const uint32_t full0 = ptx::smem_u32(full_bar);
+      constexpr uint32_t kAStep = Cfg::kABytes >> 4, kBStep = Cfg::kBBytes >> 4;
+      bool landed = false;                                           // full_bar[stage] already seen complete (tested one k-block ahead)
       for (int64_t t = pair; t < num_tiles; t += num_pairs) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        NPVP_TRACE(3);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
+          if (!landed) ptx::mbar_wait(&full_bar[stage], phase);
+          NPVP_TRACE(1);
           ptx::tc_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t bdesc = make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
-#pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k)
-            umma_bf16_2cta(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          int ns = stage + 1;
+          uint32_t np = phase;
+          if (ns == Cfg::kStages) { ns = 0; np ^= 1; }
+          landed = ptx::mbar_test(full0 + 8u * (uint32_t)ns, np);
+          umma_f16_x4_2cta(tmem_d, a_lo0 + (uint32_t)stage * kAStep, b_lo0 + (uint32_t)stage * kBStep, idesc, (uint32_t)kb);
           umma_commit_2cta(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          NPVP_TRACE(2);
+          stage = ns; phase = np;
         }
         umma_commit_2cta(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -993,6 +1197,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const float relu_floor = ep.post_relu ? 0.f : -INFINITY;
     constexpr int kColsPerWarp = BN / 2;
     ResRaw<RES> rr;
+    ResD<RES> rd;                                                    // direct epilogue: residuals of the chunk about to be processed
+    int64_t rd_tile = -1;                                            // tile whose first chunk rd was loaded for
     int64_t rr_tile = -1;
     int rr_c = -1;
     auto res_prefetch = [&](int64_t tt, int c) {
@@ -1008,9 +1214,39 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int64_t nb = (int64_t)n_blk * BN + c + chunk * 4;
         return (has_bias && nb < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
+      if (DIRECT) {
+        constexpr int kChunks = kColsPerWarp / 32;
+        const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp);
+        const int64_t m = (int64_t)m_blk * 2 * kBM + (int64_t)rank * kBM + quad * 32 + lane;
+        const int64_t nw = (int64_t)n_blk * BN + half * kColsPerWarp;
+        auto out_off = [&](int64_t n0) -> int64_t { return m * ep.ld_out + n0; };
+        auto release = [&]() {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(empty_remote[acc]);     // the leader's barrier counts both CTAs' epilogue warps
+        };
+        auto next_tile = [&]() {
+          const int64_t tn = t + num_pairs;
+          rd_tile = tn;
+          if (tn < num_tiles) {
+            const int64_t mn = (tn / n_tiles) * 2 * kBM + (int64_t)rank * kBM + quad * 32 + lane;
+            load_resd<RES>(rd, ep, mn, (tn % n_tiles) * BN + half * kColsPerWarp, mn < M);
+          }
+        };
+        if (RES > 0 && rd_tile != t) load_resd<RES>(rd, ep, m, nw, m < M && nw < N);
+        float st_s = 0.f, st_q = 0.f;
+        ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+        if (threadIdx.x == 128) NPVP_TRACE(4);
+        ptx::tc_fence_after();
+        epi_direct_tile<kChunks, ACT, RES, OUTK>(t0, m, m < M, nw, N, ep, has_bias, fp16, rd, st_s, st_q, out_off, release, next_tile);
+        if (threadIdx.x == 128) NPVP_TRACE(5);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       float4 b_next = load_bias(half * kColsPerWarp);
       if (RES > 0 && (rr_tile != t || rr_c != half * kColsPerWarp)) res_prefetch(t, half * kColsPerWarp);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      if (threadIdx.x == 128) NPVP_TRACE(4);
       ptx::tc_fence_after();
       const int64_t m_base = (int64_t)m_blk * 2 * kBM + (int64_t)rank * kBM + quad * 32;
       float st_s = 0.f, st_q = 0.f;                                  // (frame statistics are a 1-CTA kernel feature)
@@ -1044,6 +1280,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(empty_remote[acc]);       // the leader's barrier counts both CTAs' epilogue warps
+      if (threadIdx.x == 128) NPVP_TRACE(5);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -1173,9 +1410,23 @@ struct TmaConvHost {
 
 static int g_num_sms = 0;
 static int g_conv_wres = 1;     // npvp_set_option("conv_wres", 0): TMA-window convolutions stream their weights with every A tile again (A/B switch)
+static int g_gemm_prefetch = 1; // npvp_set_option("gemm_prefetch", 0): no L2 prefetch of the A operand ahead of the TMA ring (A/B switch)
 static int g_conv_tma = 1;      // npvp_set_option("conv_tma", 0): stride-1 zero-padded convolutions use the cp.async gather again (A/B switch)
-static int g_epi_direct = 0;   // npvp_set_option("gemm_epi_direct", 1): store 16-bit outputs straight from the accumulator layout (see epi_direct16)
 static int g_use_2cta = -1;     // npvp_set_option("gemm_2cta", v): 1 = always for N >= 256, 0 = never, -1 (default) = when K >= 1024
+
+// The direct epilogue (see epi_direct_chunk) needs whole 32-column chunks, 32-byte aligned output and
+// residual rows, and alpha == 1 without a post-ReLU.
+static int g_epi_direct = 1;   // npvp_set_option("gemm_epi_direct", 0): always transpose through shared memory (A/B switch, identical results)
+static bool epi_direct_ok(const EpiParams& e, int64_t N) {
+  if (!g_epi_direct || N % 32 != 0 || e.alpha != 1.0f || e.post_relu) return false;
+  if (e.res1 && !e.res1_bf16) return false;      // fp32 residual rows: 128 B per thread in four sector requests measured slower (76.8 vs 56.3 us)
+  if (e.out_bf16 && (e.ld_out % 16 != 0 || (uintptr_t)e.out_bf16 % 32 != 0)) return false;
+  if (e.out_f32 && (e.ld_out % 8 != 0 || (uintptr_t)e.out_f32 % 32 != 0)) return false;
+  if (e.res1 && (e.res1_bf16 ? (e.ld_res % 16 != 0) : (e.ld_res % 8 != 0))) return false;
+  if (e.res2 && e.ld_res % 16 != 0) return false;
+  if (((uintptr_t)e.res1 | (uintptr_t)e.res2) % 32 != 0) return false;
+  return true;
+}
 
 template <int BN, int ACT, int RES, int OUT, int CONV>
 static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, int64_t M, int64_t N, int64_t K, const EpiParams& e,
@@ -1206,6 +1457,7 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
   int rc = make_tmap_2d(&tb, W, N, K, ldw, BN, e.fp16);
   if (rc) return rc;
   TmaConv tc0 = tmc ? tmc->tc : TmaConv{};
+  tc0.pf = g_gemm_prefetch;
   if (tmc) {
     if ((rc = make_tmap_nhwc(&ta, tmc->x, tmc->frames, tmc->H, tmc->W, tmc->C, e.fp16))) return rc;
     // resident weights (see TmaConv): one n-tile, live W beside >= 3 A stages inside the stage ring's shared memory
@@ -1233,25 +1485,27 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
   const int out = (e.out_f32 && e.out_bf16) ? 2 : (e.out_f32 ? 1 : 0);
   const int act = e.act;
   if (tmc) {
-    if (tmc->convt) {
-      if (act == NPVP_ACT_RELU && res == 0 && out == 0) return launch_v2_inst<BN, NPVP_ACT_RELU, 0, 0, 3>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
-      if (res == 0 && out == 0) return launch_v2_inst<BN, -1, 0, 0, 3>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
-      npvp_set_error("transposed conv: 16-bit output without residuals only");
+    if (tmc->convt) {                                   // always the direct epilogue (the pixel-shuffled NHWC store exists only there)
+      if (act == NPVP_ACT_RELU && res == 0 && out == 0) return launch_v2_inst<BN, NPVP_ACT_RELU, 0, kDirect, 3>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
+      if (act == NPVP_ACT_NONE && res == 0 && out == 0) return launch_v2_inst<BN, NPVP_ACT_NONE, 0, kDirect, 3>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
+      npvp_set_error("transposed conv: act NONE / RELU, 16-bit output without residuals only");
       return NPVP_ERR_INVALID;
     }
-#define NPVP_V2_TCONV(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_, 2>(ta, tb, M, N, K, e, cg0, tc0, grid, st)
+    const bool direct = epi_direct_ok(e, N);
+#define NPVP_V2_TCONV(A_, R_, O_) if (act == A_ && res == R_ && out == O_) { \
+      if (direct) return launch_v2_inst<BN, A_, R_, O_ + kDirect, 2>(ta, tb, M, N, K, e, cg0, tc0, grid, st); \
+      return launch_v2_inst<BN, A_, R_, O_, 2>(ta, tb, M, N, K, e, cg0, tc0, grid, st); }
     NPVP_V2_TCONV(NPVP_ACT_RELU, 0, 0);
     NPVP_V2_TCONV(NPVP_ACT_RELU, 2, 0);
     NPVP_V2_TCONV(NPVP_ACT_NONE, 2, 0);
 #undef NPVP_V2_TCONV
     return launch_v2_inst<BN, -1, -1, -1, 2>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
   }
-  // 16-bit output without residuals: store straight from the accumulator layout when every 32-column chunk of a row is a
-  // whole, 32-byte aligned run of sectors
-  const bool direct = g_epi_direct && res == 0 && out == 0 && N % 32 == 0 && e.ld_out % 16 == 0 && ((uintptr_t)e.out_bf16 % 32) == 0;
+  const bool direct = epi_direct_ok(e, N);
   if (conv) {
-    if (direct && act == NPVP_ACT_RELU) return launch_v2_inst<BN, NPVP_ACT_RELU, 0, kOutDirect16, 1>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
-#define NPVP_V2_CONV(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_, 1>(ta, tb, M, N, K, e, cg0, tc0, grid, st)
+#define NPVP_V2_CONV(A_, R_, O_) if (act == A_ && res == R_ && out == O_) { \
+      if (direct) return launch_v2_inst<BN, A_, R_, O_ + kDirect, 1>(ta, tb, M, N, K, e, cg0, tc0, grid, st); \
+      return launch_v2_inst<BN, A_, R_, O_, 1>(ta, tb, M, N, K, e, cg0, tc0, grid, st); }
     NPVP_V2_CONV(NPVP_ACT_RELU, 0, 0);   // conv / transposed conv + BN + ReLU
     NPVP_V2_CONV(NPVP_ACT_RELU, 2, 0);   // F3D conv: ReLU(BN(conv)) + x
     NPVP_V2_CONV(NPVP_ACT_NONE, 2, 0);   // ResnetBlock second conv + skip
@@ -1260,17 +1514,16 @@ static int launch_tcgen05_v2(const void* A, int64_t lda, const void* W, int64_t 
     return launch_v2_inst<BN, -1, -1, -1, 1>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
   }
   if (e.frame_stats) {
-    if (BN == 256 && act == NPVP_ACT_NONE && res == 0 && out == 0)
+    if (BN == 256 && act == NPVP_ACT_NONE && res == 0 && out == 0) {
+      if (direct) return launch_v2_inst<256, NPVP_ACT_NONE, 0, kOutStats16 + kDirect, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
       return launch_v2_inst<256, NPVP_ACT_NONE, 0, kOutStats16, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
+    }
     npvp_set_error("gemm: frame_stats needs the 256-wide tile, act NONE, no residual, 16-bit output only");
     return NPVP_ERR_INVALID;
   }
-  if (direct) {
-    if (act == NPVP_ACT_NONE) return launch_v2_inst<BN, NPVP_ACT_NONE, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
-    if (act == NPVP_ACT_GELU) return launch_v2_inst<BN, NPVP_ACT_GELU, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
-    if (act == NPVP_ACT_RELU) return launch_v2_inst<BN, NPVP_ACT_RELU, 0, kOutDirect16, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st);
-  }
-#define NPVP_V2_CASE(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_v2_inst<BN, A_, R_, O_, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st)
+#define NPVP_V2_CASE(A_, R_, O_) if (act == A_ && res == R_ && out == O_) { \
+    if (direct) return launch_v2_inst<BN, A_, R_, O_ + kDirect, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st); \
+    return launch_v2_inst<BN, A_, R_, O_, 0>(ta, tb, M, N, K, e, cg0, tc0, grid, st); }
   NPVP_V2_CASE(NPVP_ACT_NONE, 0, 0);   // projections -> 16-bit
   NPVP_V2_CASE(NPVP_ACT_GELU, 0, 0);   // linear1
   NPVP_V2_CASE(NPVP_ACT_RELU, 0, 0);   // conv + BN + ReLU
@@ -1317,7 +1570,10 @@ static int launch_tcgen05_2cta(const void* A, int64_t lda, const void* W, int64_
   const int res = !e.res1 ? (e.res2 ? -1 : 0) : (!e.res2 ? (e.res1_bf16 ? 2 : 1) : ((e.res1_bf16 && e.res2_bf16) ? 3 : -1));
   const int out = (e.out_f32 && e.out_bf16) ? 2 : (e.out_f32 ? 1 : 0);
   const int act = e.act;
-#define NPVP_V3_CASE(A_, R_, O_) if (act == A_ && res == R_ && out == O_) return launch_2cta_inst<A_, R_, O_>(ta, tb, M, N, K, e, grid, st)
+  const bool direct = epi_direct_ok(e, N);
+#define NPVP_V3_CASE(A_, R_, O_) if (act == A_ && res == R_ && out == O_) { \
+    if (direct) return launch_2cta_inst<A_, R_, O_ + kDirect>(ta, tb, M, N, K, e, grid, st); \
+    return launch_2cta_inst<A_, R_, O_>(ta, tb, M, N, K, e, grid, st); }
   NPVP_V3_CASE(NPVP_ACT_NONE, 0, 0);
   NPVP_V3_CASE(NPVP_ACT_GELU, 0, 0);
   NPVP_V3_CASE(NPVP_ACT_RELU, 0, 0);
@@ -1467,6 +1723,7 @@ extern "C" int npvp_convt_gemm_bf16(const void* x, int64_t frames, int H, int W,
   NPVP_REQUIRE(ep->out_bf16 && !ep->out_f32 && !ep->res1 && !ep->res2 && !ep->frame_stats && (uintptr_t)ep->out_bf16 % 16 == 0,
                "npvp_convt_gemm_bf16: one 16-byte aligned 16-bit output, no residuals");
   NPVP_REQUIRE(4 * M < 0xffffffffll, "npvp_convt_gemm_bf16: more than 2^32 - 1 output pixels per launch");
+  NPVP_REQUIRE(ep->alpha == 1.0f && !ep->post_relu, "npvp_convt_gemm_bf16: alpha must be 1 and post_relu 0");
   NPVP_REQUIRE((uintptr_t)ep->out_bf16 % 32 == 0, "npvp_convt_gemm_bf16: output must be 32-byte aligned (sector stores)");
   EpiParams e = make_epi(ep);
   TmaConvHost h;
@@ -1486,6 +1743,7 @@ extern "C" int npvp_set_option(const char* name, int value) {
   if (strcmp(name, "gemm_2cta") == 0) { g_use_2cta = value; return NPVP_OK; }
   if (strcmp(name, "gemm_epi_direct") == 0) { g_epi_direct = value; return NPVP_OK; }
   if (strcmp(name, "conv_tma") == 0) { g_conv_tma = value; return NPVP_OK; }
+  if (strcmp(name, "gemm_prefetch") == 0) { g_gemm_prefetch = value; return NPVP_OK; }
   if (strcmp(name, "conv_wres") == 0) { g_conv_wres = value; return NPVP_OK; }
   if (strcmp(name, "ffn_scalar") == 0) { npvp_set_ffn_scalar(value); return NPVP_OK; }
   if (strcmp(name, "ffn_mid16_mode") == 0) { npvp_set_ffn_mid16_mode(value); return NPVP_OK; }

@@ -76,22 +76,44 @@ def test_gemm_epilogues(op, spec, backend, dt):
 
 
 @pytest.mark.parametrize("dt", H16)
-@pytest.mark.parametrize("M,N,K,act", [(1000, 512, 512, 0), (384, 1024, 512, 2), (300, 128, 256, 1), (4096, 64, 576, 1)])
-def test_gemm_direct_epilogue_matches_staged(op, M, N, K, act, dt):
-    """The opt-in store-from-accumulator-layout epilogue (gemm_epi_direct) must be bit-identical to the staged one."""
+@pytest.mark.parametrize("backend", [1, 4])
+@pytest.mark.parametrize("M,N,K,kind", [(1000, 512, 512, "act0"), (384, 1024, 512, "gelu"), (300, 128, 256, "relu"), (4096, 64, 576, "relu"),
+                                        (1000, 512, 512, "res_f32_inplace"), (700, 512, 1024, "f32"), (900, 256, 512, "relu_res16"),
+                                        (640, 512, 128, "res16x2"), (520, 512, 512, "both")])
+def test_gemm_direct_epilogue_matches_staged(op, M, N, K, kind, dt, backend):
+    """The direct (accumulator-layout) epilogue - the default - must be bit-identical to the staged one for every epilogue family."""
     a, w = rn(M, K, seed=1, dtype=dt), rn(N, K, seed=2, scale=K ** -0.5, dtype=dt)
     bias = rn(N, seed=3)
+    r16a, r16b, r32 = rn(M, N, seed=4, dtype=dt), rn(M, N, seed=5, dtype=dt), rn(M, N, seed=6)
     outs = []
     try:
         for direct in (0, 1):
             op.lib.npvp_set_option(b"gemm_epi_direct", direct)
-            o = torch.zeros(M, N, device=DEV, dtype=dt)
-            op.gemm(a, w, bias=bias, act=act, out_bf16=o, backend=1)
+            o16 = torch.zeros(M, N, device=DEV, dtype=dt)
+            o32 = torch.zeros(M, N, device=DEV)
+            if kind == "act0":
+                op.gemm(a, w, bias=bias, out_bf16=o16, backend=backend)
+            elif kind == "gelu":
+                op.gemm(a, w, bias=bias, act=2, out_bf16=o16, backend=backend)
+            elif kind == "relu":
+                op.gemm(a, w, bias=bias, act=1, out_bf16=o16, backend=backend)
+            elif kind == "res_f32_inplace":
+                o32.copy_(r32)
+                op.gemm(a, w, bias=bias, res1=o32, out_f32=o32, backend=backend)
+            elif kind == "f32":
+                op.gemm(a, w, bias=bias, out_f32=o32, backend=backend)
+            elif kind == "relu_res16":
+                op.gemm(a, w, bias=bias, act=1, res1=r16a, out_bf16=o16, backend=backend)
+            elif kind == "res16x2":
+                op.gemm(a, w, bias=bias, act=1, res1=r16a, res2=r16b, out_bf16=o16, backend=backend)
+            else:
+                op.gemm(a, w, bias=bias, out_f32=o32, out_bf16=o16, backend=backend)
             torch.cuda.synchronize()
-            outs.append(o)
+            outs.append((o16, o32))
     finally:
-        op.lib.npvp_set_option(b"gemm_epi_direct", 0)
-    assert torch.equal(outs[0], outs[1])
+        op.lib.npvp_set_option(b"gemm_epi_direct", 1)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert float(outs[1][0].float().abs().max()) + float(outs[1][1].abs().max()) > 0
 
 
 @pytest.mark.parametrize("M,N,K", [(640, 2048, 512), (128, 256, 64), (1216, 512, 192)])
