@@ -231,7 +231,10 @@ int npvp_conv7x7_stem(const float* x, const float* w, const float* shift, void* 
  * out fp32 NCHW [frames,Cout,H,W] (model space) and / or out_u8 uint8 NCHW: the pixel-space frame the reference writes to image
  * files - VidReNormalize, clamp to [0,1], ToPILImage's trunc(255 v) (utils/dataset.py:860-886, utils/train_summary.py:243-248) -
  * fused into the epilogue; pix_inv_std / pix_inv_mean (host pointers, Cout values: 1/std and -mean as npvp_frames_to_pixels
- * takes them) are required with out_u8.  At least one of out / out_u8 is non-NULL. */
+ * takes them) are required with out_u8.  At least one of out / out_u8 is non-NULL.
+ * Plain NHWC input (phase_major = 0) with W <= 250 runs on tcgen05 (csrc/head_tc.cu: whole reflect-padded rows streamed once
+ * through a shared-memory ring by TMA, 7 taps x Cin/16 MMAs of M 128 x N 32 per 128 pixels); otherwise the mma.sync tile kernel.
+ * Same packed weights, same results to 2e-6; npvp_set_option("head_tc", 0) forces the tile kernel. */
 int npvp_conv7x7_head(const void* x_bf16, const void* w, const float* bias, float* out, int64_t frames, int Cin,
                       int Cout, int H, int W, int phase_major, int act, int fp16, void* out_u8, const float* pix_inv_std,
                       const float* pix_inv_mean, void* stream);

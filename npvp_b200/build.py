@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnpvp_b200.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
-SOURCES = ["api.cu", "gemm.cu", "predictor_kernels.cu", "ffn_mid16.cu", "attention.cu", "autoencoder_kernels.cu", "post_kernels.cu"]
+SOURCES = ["api.cu", "gemm.cu", "predictor_kernels.cu", "ffn_mid16.cu", "attention.cu", "autoencoder_kernels.cu", "head_tc.cu", "post_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -289,6 +289,10 @@ static int launch_head(const void* x, const void* w, const float* bias, float* o
   return NPVP_OK;
 }
 
+// head_tc.cu: the tcgen05 form (whole padded rows streamed through a shared-memory ring); 1 = geometry not covered
+int npvp_conv7x7_head_tc_try(const void* x, const void* w, const float* bias, float* out, int64_t frames, int Cin, int Cout, int H, int W,
+                             int act, int fp16, uint8_t* out_u8, const float* pix_inv_std, const float* pix_inv_mean, cudaStream_t st);
+
 extern "C" int npvp_conv7x7_head(const void* x_bf16, const void* w, const float* bias, float* out, int64_t frames, int Cin,
                                  int Cout, int H, int W, int phase_major, int act, int fp16, void* out_u8, const float* pix_inv_std,
                                  const float* pix_inv_mean, void* stream) {
@@ -301,6 +305,10 @@ extern "C" int npvp_conv7x7_head(const void* x_bf16, const void* w, const float*
   NPVP_REQUIRE(Cin == 32 || Cin == 64, "npvp_conv7x7_head: Cin must be 32 or 64 (got %d)", Cin);
   NPVP_REQUIRE((uintptr_t)w % 16 == 0 && (uintptr_t)x_bf16 % 16 == 0, "npvp_conv7x7_head: x / w must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  if (!phase_major) {
+    const int rc = npvp_conv7x7_head_tc_try(x_bf16, w, bias, out, frames, Cin, Cout, H, W, act, fp16, (uint8_t*)out_u8, pix_inv_std, pix_inv_mean, st);
+    if (rc <= 0) return rc;
+  }
   const int nt = (7 * Cout + 7) / 8;
 #define NPVP_HEAD_CASE(NTV)                                                                                                   \
   if (nt == NTV)                                                                                                              \

@@ -8,175 +8,10 @@
 //       tensor path and for shapes the TMA descriptors cannot express.
 //   npvp_gemm_f32  : fp32 CUDA-core GEMM for the NRMLP positional MLP (precision critical, tiny).
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <cuda.h>
 #include <string.h>
 
-// =============================================================================================
-// PTX wrappers
-// =============================================================================================
-namespace ptx {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a lost arrival traps (reported as a CUDA error) instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  long long t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 6000000000LL) {   // ~3 s at 2 GHz
-        printf("npvp gemm: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-        __trap();
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-// L2 prefetch of a box (no shared memory, no barrier): the A rows a CTA will stream a few k-blocks from now
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c_inner, int c_outer) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c_inner), "r"(c_outer) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 inputs, fp32 accumulate)
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// One 64-element k-block = four K=16 MMAs, issued from ONE asm statement.  Descriptors are passed as their low words
-// (start address >> 4 | LBO; the high word - SBO 1024 B, version 1, SWIZZLE_128B - is the constant 0x40004040) and advance by
-// 32 bytes (+2) per K step.  r02 timeline (tools/ubench/gemm_trace.cu): the issuing thread needed ~300 clk between the last MMA
-// of a k-block and the first of the next (per-MMA descriptor arithmetic, an ELECT loop per operand conversion, the barrier
-// round trip) while the tensor pipe only queues ~2 MMAs: 765 clk per k-block against 512 clk of tensor work.
-__device__ __forceinline__ void umma_f16_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, pt;\n\t.reg .b64 da, db;\n\t.reg .b32 la, lb;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.eq.b32 pt, %5, %5;\n\t"
-      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
-      "add.u32 la, %1, 2;\n\tadd.u32 lb, %2, 2;\n\tmov.b64 da, {la, %5};\n\tmov.b64 db, {lb, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
-      "add.u32 la, %1, 4;\n\tadd.u32 lb, %2, 4;\n\tmov.b64 da, {la, %5};\n\tmov.b64 db, {lb, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
-      "add.u32 la, %1, 6;\n\tadd.u32 lb, %2, 6;\n\tmov.b64 da, {la, %5};\n\tmov.b64 db, {lb, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
-      : "memory");
-}
-// non-blocking phase test (mbarrier.try_wait may suspend the thread for a while when the phase is still open)
-__device__ __forceinline__ bool mbar_test(uint32_t bar_addr, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar_addr), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok));
-  return ok != 0;
-}
-// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// wait::ld that also "redefines" the destination registers of an earlier tcgen05.ld, so the compiler can neither read
-// nor copy them before the wait when the load was issued a whole loop iteration ahead (software-pipelined epilogue)
-__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :
-               : "memory");
-}
-// 256-bit global load (sm_100: LDG.256): one full 32-byte sector per thread.  Plain (coherent) load: residuals may alias the output.
-__device__ __forceinline__ void ldg256(const void* src, uint32_t* v) {
-  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "l"(src)
-               : "memory");
-}
-// 256-bit global store (sm_100: STG.256): one full 32-byte sector per thread
-__device__ __forceinline__ void stg256(void* dst, const uint32_t* v) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
-               "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
-
-}  // namespace ptx
 
 // Optional timeline instrumentation (tools/ubench/gemm_trace.cu compiles this file with -DNPVP_GEMM_TRACE): CTA 0 records
 // clock64() at the pipeline hand-offs.  Never compiled into the library.
@@ -1348,21 +1183,6 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t lda, const TA* __restrict__ W
 // =============================================================================================
 // host side
 // =============================================================================================
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (PFN_encodeTiled)p;
-  }
-  return fn;
-}
 
 // 2-D bf16 tensor map: inner dim = K (contiguous), outer dim = rows; box = 64 x box_rows; 128B swizzle; OOB -> 0.
 static int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows, int fp16) {
@@ -1737,6 +1557,7 @@ extern "C" int npvp_convt_gemm_bf16(const void* x, int64_t frames, int H, int W,
 
 void npvp_set_ffn_scalar(int v);   // predictor_kernels.cu
 void npvp_set_ffn_mid16_mode(int m);   // ffn_mid16.cu
+void npvp_head_tc_enable(int v);       // head_tc.cu
 
 extern "C" int npvp_set_option(const char* name, int value) {
   NPVP_REQUIRE(name != nullptr, "npvp_set_option: null name");
@@ -1747,6 +1568,7 @@ extern "C" int npvp_set_option(const char* name, int value) {
   if (strcmp(name, "conv_wres") == 0) { g_conv_wres = value; return NPVP_OK; }
   if (strcmp(name, "ffn_scalar") == 0) { npvp_set_ffn_scalar(value); return NPVP_OK; }
   if (strcmp(name, "ffn_mid16_mode") == 0) { npvp_set_ffn_mid16_mode(value); return NPVP_OK; }
+  if (strcmp(name, "head_tc") == 0) { npvp_head_tc_enable(value); return NPVP_OK; }
   NPVP_REQUIRE(false, "npvp_set_option: unknown option '%s'", name);
   return NPVP_ERR_INVALID;
 }

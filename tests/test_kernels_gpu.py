@@ -336,6 +336,32 @@ def test_conv7x7_head(op, spec, Cin, Cout, HW, phase, act, dt):
 
 
 @pytest.mark.parametrize("dt", H16)
+@pytest.mark.parametrize("frames,Cin,Cout,H,W,act", [(3, 32, 3, 128, 128, 3), (5, 64, 3, 64, 64, 3), (40, 32, 3, 128, 128, 3), (3, 32, 3, 20, 36, 3),
+                                                     (300, 64, 1, 64, 64, 4), (2, 32, 2, 128, 160, 0), (1, 64, 3, 8, 8, 3), (9, 32, 1, 4, 250, 4)])
+def test_conv7x7_head_tcgen05_rows(op, spec, frames, Cin, Cout, H, W, act, dt):
+    """The row-streaming tcgen05 head (head_tc.cu; plain NHWC input) against the kernel specification and against the mma.sync
+    tile kernel on the same input: frame segments, ring wrap-around, rectangular and tiny frames, fused uint8 pixels."""
+    from npvp_b200._lib import pack_head_weights
+    x = rn(frames * H * W, Cin, seed=1, dtype=dt)
+    w, b = pack_head_weights(rn(49 * Cin, Cout, seed=2, scale=0.03), dt), rn(Cout, seed=3, scale=0.2)
+    ren = ([0.5] * Cout, [0.25] * Cout)
+    outs = []
+    for tc in (1, 0):
+        op.lib.npvp_set_option(b"head_tc", tc)
+        o, u = torch.empty(frames, Cout, H, W, device=DEV), torch.empty(frames, Cout, H, W, device=DEV, dtype=torch.uint8)
+        op.conv7x7_head(x, w, b, o, Cin, Cout, H, W, False, act, out_u8=u, renorm=ren)
+        outs.append((o, u))
+    op.lib.npvp_set_option(b"head_tc", 1)
+    o2 = torch.empty(frames, Cout, H, W, device=DEV)
+    spec.conv7x7_head(x, w, b, o2, Cin, Cout, H, W, False, act)
+    assert float((outs[0][0] - o2).abs().max()) < 2e-4, float((outs[0][0] - o2).abs().max())
+    assert float((outs[0][0] - outs[1][0]).abs().max()) < 1e-5
+    assert int((outs[0][1].int() - outs[1][1].int()).abs().max()) <= 1      # a 1e-6 difference can cross a truncation boundary
+    pix = ((outs[0][0] * torch.tensor(ren[1], device=DEV).view(1, -1, 1, 1) + torch.tensor(ren[0], device=DEV).view(1, -1, 1, 1)).clamp(0, 1) * 255).floor()
+    assert float((pix - outs[0][1].float()).abs().max()) <= 1
+
+
+@pytest.mark.parametrize("dt", H16)
 @pytest.mark.parametrize("C,H", [(64, 64), (128, 32), (256, 16), (512, 8)])
 def test_nonlocal_pieces(op, spec, C, H, dt):
     frames, dq, dv = 2, C // 8, C // 2
