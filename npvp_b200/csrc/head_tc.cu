@@ -22,10 +22,12 @@ namespace {
 
 constexpr int kHtRing = 16;            // input rows resident (a tile needs at most D + 7 of them, the rest is prefetch depth)
 constexpr int kHtMaxDup = 3;
-constexpr int kHtTmemBufs = 4;         // 32-column accumulators in flight
+constexpr int kHtTmemBufs = 8;         // 32-column accumulators in flight
 constexpr int kHtZRing = 384;          // Z rows kept for the shift-sum: three tiles
 constexpr int kHtZStride = 21;         // floats per Z row (7 kx * 3 co), odd: conflict-free row-per-thread writes and shifted reads
-constexpr int kHtThreads = 384;
+constexpr int kHtThreads = 512;        // warp 0 producer, 1 / 3 MMA issuers, 2 padding + TMEM, 4..15 epilogue
+constexpr int kHtEpiThreads = 384;     // 12 warps = 4 TMEM lane quadrants x 3 column groups; the output phase is one (position, channel) per thread
+constexpr int kHtMaxRows = 1280;       // stream rows per CTA (row table in shared memory)
 constexpr int kHtMaxSeg = 24;
 
 struct HeadTcPix { float inv_std[3], inv_mean[3]; };
@@ -57,17 +59,15 @@ __device__ __forceinline__ void ht_tma_load_3d(uint32_t smem_dst, const CUtensor
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(smem_dst), "l"(map), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void ht_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+__device__ __forceinline__ void ht_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr) : "memory");
 }
 // wait::ld that "redefines" the registers of a tcgen05.ld issued a loop iteration ahead (see tmem_ld_wait_regs in tc_ptx.cuh)
-__device__ __forceinline__ void ht_tmem_ld_wait16(uint32_t (&r)[16]) {
+__device__ __forceinline__ void ht_tmem_ld_wait8(uint32_t (&r)[8]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
                :: "memory");
 }
 // Tanh / Sigmoid from one ex2 and one reciprocal (absolute error < 3e-7: the frames are quantised to 8 bits downstream)
@@ -124,6 +124,7 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kHtTmemBufs);
   HtSeg* segs = reinterpret_cast<HtSeg*>(tmem_slot + 2);
   int* seg_count = reinterpret_cast<int*>(segs + kHtMaxSeg + 1);
+  int64_t* rowtab = reinterpret_cast<int64_t*>(seg_count + 2);   // [n_rows] output offset of (frame, channel 0, row y, column 0), -1: no output row
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // this CTA's output rows [o_begin, o_end) of the batch and its row stream
@@ -140,7 +141,7 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
     segs[ns].s0 = s; segs[ns].n = 0; segs[ns].f = 0; segs[ns].y0 = 0;     // sentinel: total stream rows
     *seg_count = ns;
     for (int i = 0; i < kHtRing; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&ready[i], 1); ptx::mbar_init(&freeb[i], 1); }
-    for (int i = 0; i < kHtTmemBufs; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < kHtTmemBufs; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], kHtEpiThreads / 32); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmap_x);
   }
@@ -152,9 +153,10 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
       const int i = threadIdx.x + u * kHtThreads;
-      const int ci = i % CIN, n = (i / CIN) % 32, ky = i / (CIN * 32);
+      const int ci = i % CIN, nn = (i / CIN) % 32, ky = i / (CIN * 32);
+      const int n = (nn >> 3) * 7 + (nn & 7);                       // accumulator column nn = 8 g + j holds GEMM column n = 7 g + j (j < 7, g < 3)
       v[u] = 0;
-      if (ky < 7 && n < p.NT * 8) {
+      if (ky < 7 && nn < 24 && (nn & 7) < 7 && n < 7 * Cout) {
         const int pass = ci >> 5, half = (ci >> 4) & 1, kk = ci & 15;
         const int tig = (kk & 7) >> 1, e = (kk & 1) + ((kk >> 3) << 1);
         v[u] = __ldg(p.w + ((((size_t)pass * 14 + ky * 2 + half) * p.NT + (n >> 3)) * 32 + (n & 7) * 4 + tig) * 4 + e);
@@ -180,6 +182,10 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
   // flattened positions [0, (n_rows - 6) * P) carry every valid output
   const int n_tiles = n_rows > 6 ? (int)(((int64_t)(n_rows - 6) * P + 127) / 128) : 0;
   const uint32_t ring_s = ptx::smem_u32(ring);
+  for (int k = 0; k < nseg; ++k)
+    for (int j = threadIdx.x; j < segs[k].n + 6; j += kHtThreads)
+      rowtab[segs[k].s0 + j] = j < segs[k].n ? (((int64_t)segs[k].f * Cout) * H + segs[k].y0 + j) * W : -1;
+  __syncthreads();
 
   // Every role below is ONE dependent instruction stream per tile or row, so the loops carry (slot, phase) pairs forward with
   // compares and adds only: a `% R` / `/ R` pair per row cost ~200 clk in the first version (r02 trace).
@@ -269,30 +275,29 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
       }
     }
   } else if (warp >= 4) {
-    // ---------------- epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves ----------------
-    const int ew = warp - 4, quad = warp & 3, half = ew >> 2;
+    // ---------------- epilogue: 12 warps = 4 TMEM lane quadrants x 3 column groups (8 accumulator columns = 7 GEMM columns each) ----------------
+    const int ew = warp - 4, quad = warp & 3, grp = ew >> 2;
     const int m = quad * 32 + lane;                               // tile row held by this thread after tcgen05.ld
-    const int e = ew * 32 + lane, m2 = e & 127, cg = e >> 7;      // output phase: position m2 of the window, channel group cg
-    const int co_lo = cg ? (Cout + 1) / 2 : 0, co_hi = cg ? Cout : (Cout + 1) / 2;
-    const float bias0 = co_lo < co_hi ? __ldg(p.bias + co_lo) : 0.f, bias1 = co_lo + 1 < co_hi ? __ldg(p.bias + co_lo + 1) : 0.f;
-    const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + half * 16;
-    const uint32_t zs_s = ptx::smem_u32(zs);
+    const int e = ew * 32 + lane, m2 = e & 127, co = e >> 7;      // output phase: position m2 of the window, channel co
+    const float bias = co < Cout ? __ldg(p.bias + co) : 0.f;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + grp * 8;
+    const uint32_t zs_s = ptx::smem_u32(zs), rt_s = ptx::smem_u32(rowtab);
+    const size_t plane = (size_t)co * H * W;
     // incremental coordinates (no division in the tile loop): the window of tile t holds the flattened positions 128 t + m2 - 6
     int s = 0, xo = m2 - 6 - 128;                                 // stream row / column of this thread's position, one tile behind
     int zb = (m2 - 6 - 128 + 2 * kHtZRing) % kHtZRing;            // its row in the Z ring
     int zw = (m + kHtZRing - 128) % kHtZRing;                     // Z ring row this thread writes
-    int cur = 0, seg_s0 = segs[0].s0, seg_n = segs[0].n, seg_f = segs[0].f, seg_y0 = segs[0].y0, seg_next = segs[1].s0;
     int fr_row = 0, fr_off = 0, fr_slot = 0;                      // (thread 128) rows released so far, position of the next tile
     uint32_t tf_par = 0;
-    uint32_t r[16];
+    uint32_t r[8];
     if (n_tiles > 0) {
       ht_wait(&tfull[0], 0);
       ptx::tc_fence_after();
-      ht_tmem_ld16(t_addr, r);
+      ht_tmem_ld8(t_addr, r);
     }
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t % kHtTmemBufs;
-      ht_tmem_ld_wait16(r);
+      ht_tmem_ld_wait8(r);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ht_mbar_arrive(&tempty[buf]);
@@ -304,48 +309,35 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
       }
       zw += 128; if (zw >= kHtZRing) zw -= kHtZRing;
       {
-        const uint32_t zr = zs_s + (uint32_t)(zw * kHtZStride + half * 16) * 4;
-        if (half == 0) {
+        const uint32_t zr = zs_s + (uint32_t)(zw * kHtZStride + grp * 7) * 4;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) ht_sts(zr + c * 4, __uint_as_float(r[c]));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 5; ++c) ht_sts(zr + c * 4, __uint_as_float(r[c]));
-        }
+        for (int c = 0; c < 7; ++c) ht_sts(zr + c * 4, __uint_as_float(r[c]));
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kHtEpiThreads) : "memory");
       // the next accumulator is requested before the output phase when it is already complete (its latency hides under the phase)
       const int nbuf = (t + 1) % kHtTmemBufs;
       if (nbuf == 0) tf_par ^= 1;
       bool next_issued = false;
       if (t + 1 < n_tiles && ptx::mbar_test(ptx::smem_u32(&tfull[nbuf]), tf_par)) {
         ptx::tc_fence_after();
-        ht_tmem_ld16(t_addr + nbuf * 32, r);
+        ht_tmem_ld8(t_addr + nbuf * 32, r);
         next_issued = true;
       }
       // outputs of the flattened positions [128 t - 6, 128 t + 122): every Z row they read is in the ring now
       xo += 128; while (xo >= P) { xo -= P; ++s; }
       zb += 128; if (zb >= kHtZRing) zb -= kHtZRing;
-      bool live = xo >= 0 && xo < W;
-      if (live) {
-        while (cur < nseg && s >= seg_next) { ++cur; seg_s0 = segs[cur].s0; seg_n = segs[cur].n; seg_f = segs[cur].f; seg_y0 = segs[cur].y0; seg_next = segs[cur + 1].s0; }
-        live = cur < nseg && s - seg_s0 < seg_n;                  // not a row that mixes two segments
-      }
-      if (live) {
-        const int y = seg_y0 + (s - seg_s0);
-        const size_t obase = (((size_t)seg_f * Cout) * H + y) * W + xo;
-        uint32_t zi[7];
+      if (xo >= 0 && xo < W && co < Cout && s < n_rows) {
+        long long rb;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(rb) : "r"(rt_s + (uint32_t)s * 8) : "memory");
+        if (rb >= 0) {                                            // not a row that mixes two frame segments
+          float v = bias;
 #pragma unroll
-        for (int kx = 0; kx < 7; ++kx) { const int i = zb + kx; zi[kx] = zs_s + (uint32_t)((i >= kHtZRing ? i - kHtZRing : i) * kHtZStride + kx * Cout) * 4; }
-#pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-          const int co = co_lo + ci;
-          if (co >= co_hi) break;
-          float v = ci ? bias1 : bias0;
-#pragma unroll
-          for (int kx = 0; kx < 7; ++kx) v += ht_lds(zi[kx] + co * 4);
+          for (int kx = 0; kx < 7; ++kx) {
+            const int i = zb + kx;
+            v += ht_lds(zs_s + (uint32_t)((i >= kHtZRing ? i - kHtZRing : i) * kHtZStride + kx * Cout + co) * 4);
+          }
           v = (p.act == NPVP_ACT_TANH) ? ht_tanh(v) : (p.act == NPVP_ACT_SIGMOID ? ht_sigmoid(v) : v);
-          const size_t oi = obase + (size_t)co * H * W;
+          const size_t oi = (size_t)rb + plane + xo;
           if (p.out) p.out[oi] = v;
           if (p.out_u8) {   // VidReNormalize + clamp + ToPILImage in the reference's operation order (frames_to_pixels_kernel): bit-identical
             const float px = fminf(fmaxf(__fsub_rn(__fdiv_rn(v, p.pix.inv_std[co]), p.pix.inv_mean[co]), 0.0f), 1.0f);
@@ -356,7 +348,7 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
       if (t + 1 < n_tiles && !next_issued) {
         ht_wait(&tfull[nbuf], tf_par);
         ptx::tc_fence_after();
-        ht_tmem_ld16(t_addr + nbuf * 32, r);
+        ht_tmem_ld8(t_addr + nbuf * 32, r);
       }
     }
   }
@@ -385,7 +377,7 @@ int npvp_conv7x7_head_tc_try(const void* x, const void* w, const float* bias, fl
   const int PIXB = Cin * 2;
   const int P = (W + 6 + 7) / 8 * 8;
   const int D = (P - 8 + 127) / P;
-  const int fixed = 7 * 32 * PIXB + kHtZRing * kHtZStride * 4 + 16 + (3 * kHtRing + 2 * kHtTmemBufs) * 8 + 16 + (kHtMaxSeg + 1) * 16 + 16 + 1024;
+  const int fixed = 7 * 32 * PIXB + kHtZRing * kHtZStride * 4 + 16 + (3 * kHtRing + 2 * kHtTmemBufs) * 8 + 16 + (kHtMaxSeg + 1) * 16 + 16 + kHtMaxRows * 8 + 1024;
   const int R = min(kHtRing, (max_smem - fixed) / (P * PIXB) - D);
   if (D > kHtMaxDup || R < D + 8) return 1;
   const int smem = fixed + (R + D) * P * PIXB;
@@ -410,6 +402,7 @@ int npvp_conv7x7_head_tc_try(const void* x, const void* w, const float* bias, fl
   // one CTA per SM when there is enough work (>= 16 output rows each); more CTAs only to bound the frame segments of a CTA
   int64_t grid = min((int64_t)num_sms, max((int64_t)1, p.total_rows / 16));
   grid = max(grid, (frames + kHtMaxSeg - 5) / (kHtMaxSeg - 4));
+  grid = max(grid, (p.total_rows + 1023) / 1024);               // stream rows per CTA <= 1024 + 6 per segment <= kHtMaxRows
   auto kern = Cin == 64 ? conv7x7_head_tc_kernel<64> : conv7x7_head_tc_kernel<32>;
   static int attr[2] = {0, 0};
   if (attr[Cin == 64] < smem) {
