@@ -298,6 +298,10 @@ class MemTimer:
             "add_ln_posfuse": lambda a, k: 2 * B(a[0]) + B(a[1]) + B(a[7]) + B(a[8]),
             "layernorm_rows": lambda a, k: B(a[0]) + B(k.get("out_f32")) + B(k.get("out_bf16")),
             "add_layernorm_rows": lambda a, k: 2 * B(a[0]) + B(a[1]) + B(k.get("out_f32")) + B(k.get("out_bf16")),
+            # autoencoder ends (7x7 convolutions, 154 MFLOP per frame each - far below the tensor roofline, so HBM is their bound):
+            # head = 16-bit NHWC features in, fp32 (+ uint8) frames out; stem = fp32 / uint8 frames in, 16-bit NHWC features out
+            "conv7x7_head": lambda a, k: B(a[0]) + B(a[3]) + B(k.get("out_u8")),
+            "conv7x7_stem": lambda a, k: B(a[0]) + B(a[3]),
         }
 
     def __enter__(self):

@@ -403,6 +403,7 @@ int npvp_conv7x7_head_tc_try(const void* x, const void* w, const float* bias, fl
   int64_t grid = min((int64_t)num_sms, max((int64_t)1, p.total_rows / 16));
   grid = max(grid, (frames + kHtMaxSeg - 5) / (kHtMaxSeg - 4));
   grid = max(grid, (p.total_rows + 1023) / 1024);               // stream rows per CTA <= 1024 + 6 per segment <= kHtMaxRows
+  if (grid > num_sms) grid = (grid + num_sms - 1) / num_sms * num_sms;   // whole waves
   auto kern = Cin == 64 ? conv7x7_head_tc_kernel<64> : conv7x7_head_tc_kernel<32>;
   static int attr[2] = {0, 0};
   if (attr[Cin == 64] < smem) {

@@ -320,7 +320,8 @@ class SpecOps:
         img = self._unphase(x.float(), frames, H, W, Cin, phase_major).permute(0, 3, 1, 2)
         from npvp_b200._lib import unpack_head_weights
         wt = unpack_head_weights(w, Cout).reshape(7, 7, Cin, Cout).permute(3, 2, 0, 1)   # 16-bit packed weights (mma B fragments)
-        o = _act(F.conv2d(F.pad(img, (3, 3, 3, 3), mode="reflect"), wt, bias), act)
+        with torch.backends.cudnn.flags(enabled=False):     # cuDNN finds no engine for some thin frames (H = 4, W = 250); the native kernel always works
+            o = _act(F.conv2d(F.pad(img, (3, 3, 3, 3), mode="reflect"), wt, bias), act)
         if out is not None:
             out.copy_(o.reshape(out.shape))
         if out_u8 is not None:                      # VidReNormalize + clamp + ToPILImage (truncation), reference operation order
