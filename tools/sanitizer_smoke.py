@@ -122,6 +122,17 @@ def main():
     spec.conv7x7_head(t2, hw, hb, f2, 32, 3, 32, 32, True, 3, out_u8=g2, renorm=norm)
     close(f1, f2, 5e-3, "conv7x7 head (phase-major input)")
     assert int((g1.int() - g2.int()).abs().max()) <= 1
+    # tcgen05 row-streaming head (plain NHWC input): TMA row ring with wrap-around copies, generic-proxy padding writes,
+    # two MMA issuers, 12 epilogue warps; 5 frames x 40 rows over 12 CTAs = several frame segments per CTA
+    for cin_h in (32, 64):
+        t3 = rn(5 * 40 * 48, cin_h, seed=53, dtype=dt)
+        hw3 = _lib.pack_head_weights(rn(49 * cin_h, 3, seed=54, scale=0.05), dt)
+        f3, f4 = torch.empty(5, 3, 40, 48, device=DEV), torch.empty(5, 3, 40, 48, device=DEV)
+        g3, g4 = torch.empty(5, 3, 40, 48, dtype=torch.uint8, device=DEV), torch.empty(5, 3, 40, 48, dtype=torch.uint8, device=DEV)
+        op.conv7x7_head(t3, hw3, hb, f3, cin_h, 3, 40, 48, False, 3, out_u8=g3, renorm=norm)
+        spec.conv7x7_head(t3, hw3, hb, f4, cin_h, 3, 40, 48, False, 3, out_u8=g4, renorm=norm)
+        close(f3, f4, 5e-3, f"conv7x7 head on tcgen05 (NHWC input, Cin {cin_h})")
+        assert int((g3.int() - g4.int()).abs().max()) <= 1
     q, kv = rn(2 * 256, 8, seed=51, dtype=dt), rn(2 * 64, 40, seed=52, dtype=dt)
     n1, n2 = torch.empty(2 * 256, 32, dtype=dt, device=DEV), torch.empty(2 * 256, 32, dtype=dt, device=DEV)
     op.nonlocal_attention(q, kv, n1, 2, 256, 64, 8, 32)
