@@ -45,13 +45,27 @@ struct StemNorm { float mean[3], std[3]; };
 template <int CIN>
 __global__ void __launch_bounds__(256, 2)
 conv7x7_stem_kernel(const float* __restrict__ x, const uint8_t* __restrict__ x_u8, StemNorm nrm, const float* __restrict__ w,
-                    const float* __restrict__ shift, h16* __restrict__ out, int Cout, int H, int W, int fp16) {
+                    const float* __restrict__ shift, h16* __restrict__ out, int Cout, int H, int W, int fp16, int tiles_per_block) {
   __shared__ __align__(16) h16 tile[kStemTY + 6][kStemTW][4];        // 8 KB
   __shared__ __align__(16) h16 wb[7][2][4][8][16];                   // [ky][k-step][n-tile][n][k]  14 KB
   const int groups = Cout / 32;
   const int f = blockIdx.z / groups, cg = blockIdx.z % groups;       // 32 output channels per block
-  const int tiles_x = (W + kStemTX - 1) / kStemTX;
-  const int ty0 = (blockIdx.x / tiles_x) * kStemTY, tx0 = (blockIdx.x % tiles_x) * kStemTX;
+  const int tiles_x = (W + kStemTX - 1) / kStemTX, tiles_y = (H + kStemTY - 1) / kStemTY;
+  const int tx0 = (blockIdx.x % tiles_x) * kStemTX;
+  // weights fp32 [(ky,kx,ci), Cout] -> B fragments: k = kx*4 + ci (kx = 7 and ci >= CIN are zero).  Once per block: the repack
+  // (28 strided loads per thread) was 40 % of the instructions when every 8 x 64 tile did it, so a block now walks
+  // tiles_per_block vertically adjacent tiles (as many as keep >= 2 blocks per SM busy).
+  for (int i = threadIdx.x; i < 7 * 2 * 4 * 8 * 16; i += 256) {
+    const int k = i & 15, n = (i >> 4) & 7, nt = (i >> 7) & 3, ks = (i >> 9) & 1, ky = i >> 10;
+    const int kk = ks * 16 + k, kx = kk >> 2, ci = kk & 3;
+    const float v = (kx < 7 && ci < CIN) ? __ldg(w + ((size_t)(ky * 7 + kx) * CIN + ci) * Cout + cg * 32 + nt * 8 + n) : 0.f;
+    (&wb[0][0][0][0][0])[i] = float_to_h16(v, fp16);
+  }
+  const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int tyb0 = (blockIdx.x / tiles_x) * tiles_per_block;
+  for (int tyb = tyb0; tyb < min(tyb0 + tiles_per_block, tiles_y); ++tyb) {
+  const int ty0 = tyb * kStemTY;
+  if (tyb != tyb0) __syncthreads();                                  // every warp is done with the previous tile
   for (int i = threadIdx.x; i < (kStemTY + 6) * kStemTW; i += 256) {
     const int r = i / kStemTW, c = i % kStemTW;
     const int yy = reflect_idx(ty0 + r - 3, H), xx = reflect_idx(min(tx0 + c - 3, W + 2), W);
@@ -64,15 +78,7 @@ conv7x7_stem_kernel(const float* __restrict__ x, const uint8_t* __restrict__ x_u
     }
     *reinterpret_cast<uint2*>(&tile[r][c][0]) = make_uint2(pack_h16x2(v[0], v[1], fp16), pack_h16x2(v[2], v[3], fp16));
   }
-  // weights fp32 [(ky,kx,ci), Cout] -> B fragments: k = kx*4 + ci (kx = 7 and ci >= CIN are zero)
-  for (int i = threadIdx.x; i < 7 * 2 * 4 * 8 * 16; i += 256) {
-    const int k = i & 15, n = (i >> 4) & 7, nt = (i >> 7) & 3, ks = (i >> 9) & 1, ky = i >> 10;
-    const int kk = ks * 16 + k, kx = kk >> 2, ci = kk & 3;
-    const float v = (kx < 7 && ci < CIN) ? __ldg(w + ((size_t)(ky * 7 + kx) * CIN + ci) * Cout + cg * 32 + nt * 8 + n) : 0.f;
-    (&wb[0][0][0][0][0])[i] = float_to_h16(v, fp16);
-  }
   __syncthreads();
-  const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
   float acc[4][4][4];
 #pragma unroll
   for (int g = 0; g < 4; ++g)
@@ -123,6 +129,7 @@ conv7x7_stem_kernel(const float* __restrict__ x, const uint8_t* __restrict__ x_u
         }
       }
   }
+  }
 }
 
 extern "C" int npvp_conv7x7_stem(const float* x, const float* w, const float* shift, void* out_bf16, int64_t frames, int Cin,
@@ -135,10 +142,14 @@ extern "C" int npvp_conv7x7_stem(const float* x, const float* w, const float* sh
   if (x_u8) for (int c = 0; c < Cin && c < 3; ++c) { nrm.mean[c] = norm_mean[c]; nrm.std[c] = norm_std[c]; }
   NPVP_REQUIRE(Cout % 32 == 0 && H >= 4 && W >= 4, "npvp_conv7x7_stem: Cout must be a multiple of 32, H/W >= 4");
   NPVP_REQUIRE(frames * (Cout / 32) <= 65535, "npvp_conv7x7_stem: too many frames per launch (%lld)", (long long)frames);
-  dim3 grid((unsigned)(((H + kStemTY - 1) / kStemTY) * ((W + kStemTX - 1) / kStemTX)), 1, (unsigned)(frames * (Cout / 32)));
+  const int tiles_y = (H + kStemTY - 1) / kStemTY, tiles_x = (W + kStemTX - 1) / kStemTX;
+  // vertically adjacent tiles per block: as many as still leave ~2 blocks per SM (296 on a B200) in flight
+  int tpb = (int)((frames * (Cout / 32) * tiles_x * tiles_y) / 296);
+  tpb = tpb < 1 ? 1 : (tpb > tiles_y ? tiles_y : tpb);
+  dim3 grid((unsigned)(((tiles_y + tpb - 1) / tpb) * tiles_x), 1, (unsigned)(frames * (Cout / 32)));
   cudaStream_t st = (cudaStream_t)stream;
-  if (Cin == 1) conv7x7_stem_kernel<1><<<grid, 256, 0, st>>>(x, (const uint8_t*)x_u8, nrm, w, shift, (h16*)out_bf16, Cout, H, W, fp16);
-  else if (Cin == 3) conv7x7_stem_kernel<3><<<grid, 256, 0, st>>>(x, (const uint8_t*)x_u8, nrm, w, shift, (h16*)out_bf16, Cout, H, W, fp16);
+  if (Cin == 1) conv7x7_stem_kernel<1><<<grid, 256, 0, st>>>(x, (const uint8_t*)x_u8, nrm, w, shift, (h16*)out_bf16, Cout, H, W, fp16, tpb);
+  else if (Cin == 3) conv7x7_stem_kernel<3><<<grid, 256, 0, st>>>(x, (const uint8_t*)x_u8, nrm, w, shift, (h16*)out_bf16, Cout, H, W, fp16, tpb);
   else NPVP_REQUIRE(false, "npvp_conv7x7_stem: Cin must be 1 or 3 (got %d)", Cin);
   NPVP_LAUNCH_CHECK("conv7x7_stem_kernel");
   return NPVP_OK;

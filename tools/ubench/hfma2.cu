@@ -40,6 +40,19 @@ __global__ void __launch_bounds__(512) k(unsigned* out, unsigned a, unsigned b, 
       }
     }
   }
+  else if (MODE == 4 || MODE == 5 || MODE == 6) {   // HFMA2 interleaved with scalar FFMA (4: 1:1, 5: 2:1) or FFMA alone (6): do the two share one pipe?
+    float fa = __uint_as_float(a), fb = __uint_as_float(b);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (MODE != 6) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+        if (MODE == 5) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(a), "r"(b));
+        asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+r"(x[8 + i]) : "r"(__float_as_uint(fa)), "r"(__float_as_uint(fb)));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] ^= y[i];
+  }
   unsigned s = 0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) s ^= x[i];
@@ -72,5 +85,8 @@ int main() {
   run<1>("HFMA2 distinct operands", 1 << 13, 16);
   run<2>("ex2.f16x2 (2 MUFU+PRMT)", 1 << 12, 16 * 3);
   run<3>("mix 6 HFMA2 : 1 ex2.f16x2", 1 << 12, 16 * 9);
+  run<6>("FFMA alone (8 chains)  ", 1 << 13, 8);
+  run<4>("mix 1 HFMA2 : 1 FFMA   ", 1 << 13, 16);
+  run<5>("mix 2 HFMA2 : 1 FFMA   ", 1 << 13, 24);
   return 0;
 }
