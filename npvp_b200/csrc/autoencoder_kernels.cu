@@ -146,6 +146,7 @@ extern "C" int npvp_conv7x7_stem(const float* x, const float* w, const float* sh
   // vertically adjacent tiles per block: as many as still leave ~2 blocks per SM (296 on a B200) in flight
   int tpb = (int)((frames * (Cout / 32) * tiles_x * tiles_y) / 296);
   tpb = tpb < 1 ? 1 : (tpb > tiles_y ? tiles_y : tpb);
+  tpb = (tiles_y + (tiles_y + tpb - 1) / tpb - 1) / ((tiles_y + tpb - 1) / tpb);     // equal shares for the blocks of a column
   dim3 grid((unsigned)(((tiles_y + tpb - 1) / tpb) * tiles_x), 1, (unsigned)(frames * (Cout / 32)));
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 1) conv7x7_stem_kernel<1><<<grid, 256, 0, st>>>(x, (const uint8_t*)x_u8, nrm, w, shift, (h16*)out_bf16, Cout, H, W, fp16, tpb);

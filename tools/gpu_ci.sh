@@ -9,6 +9,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
     --log-file gpurun_out/ci_launches.csv python bench.py --profile --clips 64 > gpurun_out/ci_ncu_launches.log 2>&1
 # the largest GEMM family of the step: fc1 of the conv-FFN with the frame-statistics epilogue (M = 40960, N = 2048, K = 512)
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base demangled \
-    -k regex:"v2_kernel<\(int\)256, \(int\)0, \(int\)0, \(int\)4, \(int\)0>" -s 8 -c 2 \
+    -k regex:"v2_kernel<\(int\)256, \(int\)0, \(int\)0, \(int\)12, \(int\)0>" -s 8 -c 2 \
     -f -o gpurun_out/ci_gemm_full python bench.py --profile --clips 64 > gpurun_out/ci_ncu_full.log 2>&1
 timeout 200 python tools/bench_configs.py --faithful > gpurun_out/ci_faithful.md 2>&1
