@@ -40,12 +40,14 @@ struct HeadTcParams {
   int64_t total_rows;    // frames * H
   int H, W, P, D, R, Cout, NT, act, fp16;   // P padded row pitch (pixels), D rows mirrored behind the ring, R ring rows
   HeadTcPix pix;
+  int wait_mode;
 };
 
-// Spin on the non-blocking phase test: mbarrier.try_wait parks the thread with a coarse wake-up, and this pipeline chains three
-// waits per row (free -> TMA -> padding -> MMA), which made the chain latency, not any unit, the limit (r02 trace: 2200 clk per
-// tile in the MMA thread with every row long resident).  Bounded: a lost arrival traps instead of hanging the GPU.
-__device__ __forceinline__ void ht_wait(uint64_t* bar, uint32_t parity) {
+// Waits: mode 1 = mbarrier.try_wait (the hardware parks the warp), mode 0 = spin on the non-blocking phase test.  A spinning
+// producer / padding / issuer warp shares its scheduler with three epilogue warps and competes for their issue slots.
+// Bounded either way: a lost arrival traps instead of hanging the GPU.  (npvp_set_option("head_tc_wait", m), A/B switch.)
+__device__ __forceinline__ void ht_wait(uint64_t* bar, uint32_t parity, int mode) {
+  if (mode) { ptx::mbar_wait(bar, parity); return; }
   const uint32_t a = ptx::smem_u32(bar);
   uint32_t spins = 0;
   while (!ptx::mbar_test(a, parity)) {
@@ -73,14 +75,39 @@ __device__ __forceinline__ void ht_tmem_ld_wait8(uint32_t (&r)[8]) {
 // Tanh / Sigmoid from one ex2 and one reciprocal (absolute error < 3e-7: the frames are quantised to 8 bits downstream)
 __device__ __forceinline__ float ht_tanh(float x) { return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(x * 2.885390081777927f)), 1.0f); }
 __device__ __forceinline__ float ht_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
-__device__ __forceinline__ void ht_umma(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %5, 0;\n\t"
-      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
-      : "memory");
+// All K steps of one tap (KSTEPS = 2 for Cin 32, 4 for Cin 64) from ONE asm statement: descriptors are assembled inside it from
+// their low words (+2 = 32 bytes per K step) and a constant high word, so the compiler emits no per-operand uniform-register
+// shuffles between the MMAs (r02 ncu: with one statement per MMA and a `lane == 0` branch the two issuing threads were busy 100 % of
+// the time - ELECT / R2UR.BROADCAST sequences around every tcgen05.mma - and the tensor pipe only 75 %).
+template <int KSTEPS>
+__device__ __forceinline__ void ht_umma_tap(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  if (KSTEPS == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p, pt;\n\t.reg .b64 da, db;\n\t.reg .b32 la, lb;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.b32 pt, %3, %3;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "add.u32 la, %1, 2;\n\tadd.u32 lb, %2, 2;\n\tmov.b64 da, {la, %3};\n\tmov.b64 db, {lb, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, pt;\n\t.reg .b64 da, db;\n\t.reg .b32 la, lb;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.b32 pt, %3, %3;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "add.u32 la, %1, 2;\n\tadd.u32 lb, %2, 2;\n\tmov.b64 da, {la, %3};\n\tmov.b64 db, {lb, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+        "add.u32 la, %1, 4;\n\tadd.u32 lb, %2, 4;\n\tmov.b64 da, {la, %3};\n\tmov.b64 db, {lb, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+        "add.u32 la, %1, 6;\n\tadd.u32 lb, %2, 6;\n\tmov.b64 da, {la, %3};\n\tmov.b64 db, {lb, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ int ht_reflect(int i, int n) {       // ReflectionPad2d
   if (i < 0) i = -i;
@@ -191,13 +218,13 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
   // compares and adds only: a `% R` / `/ R` pair per row cost ~200 clk in the first version (r02 trace).
   if (warp == 0) {
     // ---------------- TMA producer: one box per stream row (two for the rows mirrored behind the ring) ----------------
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int seg = 0, seg_next = segs[1].s0, f = segs[0].f, yrel = segs[0].y0 - 3, slot = 0;
       uint32_t wrapped = 0, par = 0;                              // par: parity of the phase of freeb[slot] that frees it for this use
       for (int s = 0; s < n_rows; ++s) {
         if (s >= seg_next) { ++seg; seg_next = segs[seg + 1].s0; f = segs[seg].f; yrel = segs[seg].y0 - 3; }
         const int yy = ht_reflect(yrel++, H);
-        if (wrapped) ht_wait(&freeb[slot], par);
+        if (wrapped) ht_wait(&freeb[slot], par, p.wait_mode);
         const bool dup = slot < D;
         ptx::mbar_arrive_expect_tx(&full[slot], dup ? 2 * row_bytes : row_bytes);
         ht_tma_load_3d(ring_s + slot * row_bytes, &tmap_x, &full[slot], 0, -3, f * H + yy);
@@ -213,7 +240,7 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
     int slot = 0;
     uint32_t par = 0;
     for (int s = 0; s < n_rows; ++s) {
-      ht_wait(&full[slot], par);
+      ht_wait(&full[slot], par, p.wait_mode);
       if (j < 6) {
         for (int rep = 0; rep < (slot < D ? 2 : 1); ++rep) {
           const uint32_t row = ring_s + (uint32_t)(rep ? R + slot : slot) * row_bytes;
@@ -235,7 +262,7 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
     // ---------------- two MMA issuers, alternate tiles: per tile 7 taps x KSTEPS MMAs (M 128, N 32, K 16) ----------------
     // (tools/ubench/umma_shapes.cu: an MMA of N <= 64 occupies the tensor pipe for 61 clk whatever its N, so a tile is 14 x 61 clk;
     //  one issuer spent another ~1700 clk per tile on barriers and commits - two issuers keep the pipe fed)
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const int me = warp >> 1;                                   // 0 / 1
       const uint32_t idesc = ht_idesc(128, 32, p.fp16);
       const uint32_t hi = (uint32_t)(ht_desc<PIXB>(0) >> 32);
@@ -251,12 +278,12 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
         while (o2 >= P) { o2 -= P; ++r_last; }
         r_last = min(r_last, n_rows - 1);
         while (rows_ready <= r_last) {
-          ht_wait(&ready[rdy_slot], rdy_par);
+          ht_wait(&ready[rdy_slot], rdy_par, p.wait_mode);
           ++rows_ready;
           if (++rdy_slot == R) { rdy_slot = 0; rdy_par ^= 1; }
         }
         const int buf = t % kHtTmemBufs;
-        if (t >= kHtTmemBufs) ht_wait(&tempty[buf], te_par);
+        if (t >= kHtTmemBufs) ht_wait(&tempty[buf], te_par, p.wait_mode);
         if (buf >= kHtTmemBufs - 2 && t >= kHtTmemBufs) te_par ^= 1;   // this issuer's last buffer of a round
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * 32;
@@ -266,8 +293,7 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
         for (int ky = 0; ky < 7; ++ky) {
           const uint32_t a_lo = a_off + (uint32_t)slot * row16, b_lo = b_base + ky * (32 * PIXB / 16);
           if (++slot == R) slot = 0;
-#pragma unroll
-          for (int k = 0; k < KSTEPS; ++k) ht_umma(d_tmem, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, (ky | k) ? 1u : 0u);
+          ht_umma_tap<KSTEPS>(d_tmem, a_lo, b_lo, hi, idesc, ky ? 1u : 0u);
         }
         ptx::umma_commit(&tfull[buf]);
         off += 256;
@@ -291,7 +317,7 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
     uint32_t tf_par = 0;
     uint32_t r[8];
     if (n_tiles > 0) {
-      ht_wait(&tfull[0], 0);
+      ht_wait(&tfull[0], 0, p.wait_mode);
       ptx::tc_fence_after();
       ht_tmem_ld8(t_addr, r);
     }
@@ -346,7 +372,7 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
         }
       }
       if (t + 1 < n_tiles && !next_issued) {
-        ht_wait(&tfull[nbuf], tf_par);
+        ht_wait(&tfull[nbuf], tf_par, p.wait_mode);
         ptx::tc_fence_after();
         ht_tmem_ld8(t_addr + nbuf * 32, r);
       }
@@ -357,11 +383,13 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
   if (warp == 2) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, kHtTmemBufs * 32); }
 }
 
+int g_head_tc_wait = 1;
 int g_head_tc = 1;    // npvp_set_option("head_tc", 0): always the mma.sync head kernel (A/B switch)
 
 }  // namespace
 
 void npvp_head_tc_enable(int v) { g_head_tc = v; }
+void npvp_head_tc_wait(int v) { g_head_tc_wait = v ? 1 : 0; }
 
 // Returns NPVP_OK after launching, or 1 when the geometry is not covered (the caller runs the mma.sync kernel).
 int npvp_conv7x7_head_tc_try(const void* x, const void* w, const float* bias, float* out, int64_t frames, int Cin, int Cout, int H, int W,
@@ -397,6 +425,7 @@ int npvp_conv7x7_head_tc_try(const void* x, const void* w, const float* bias, fl
   HeadTcParams p = {};
   p.w = (const h16*)w; p.bias = bias; p.out = out; p.out_u8 = out_u8;
   p.total_rows = frames * H;
+  p.wait_mode = g_head_tc_wait;
   p.H = H; p.W = W; p.P = P; p.D = D; p.R = R; p.Cout = Cout; p.NT = (7 * Cout + 7) / 8; p.act = act; p.fp16 = fp16;
   if (out_u8) for (int c = 0; c < Cout && c < 3; ++c) { p.pix.inv_std[c] = pix_inv_std[c]; p.pix.inv_mean[c] = pix_inv_mean[c]; }
   // one CTA per SM when there is enough work (>= 16 output rows each); more CTAs only to bound the frame segments of a CTA
