@@ -49,18 +49,16 @@ def main():
 
 def timing(op):
     # timing, L2 flushed between launches
-    frames, Cin, Cout, H, W = int(os.environ.get('HEAD_FRAMES', '640')), 32, 3, 128, 128
+    frames = int(os.environ.get('HEAD_FRAMES', '640'))
+    Cin, Cout, H, W = (int(v) for v in os.environ.get('HEAD_SHAPE', '32,3,128,128').split(','))
     x = torch.randn(frames * H * W, Cin, device=DEV).half()
     w = pack_head_weights(torch.randn(49 * Cin, Cout, device=DEV) * 0.03, torch.float16)
     b = torch.randn(Cout, device=DEV) * 0.2
     out = torch.empty(frames, Cout, H, W, device=DEV)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
-    for tc in ((1, 1, 1, 1) if '--time-only' in sys.argv else (0, 1)):
+    for tc in (0, 1, 0, 1):
         op.lib.npvp_set_option(b"head_tc", tc)
         wm = int(os.environ.get('HEAD_WAIT', '1'))
-        if '--time-only' in sys.argv:
-            wm = flip = 1 - globals().get('_flip', 1)
-            globals()['_flip'] = flip
         op.lib.npvp_set_option(b"head_tc_wait", wm)
         ts = []
         for it in range(6):
@@ -73,7 +71,7 @@ def timing(op):
             ts.append(e0.elapsed_time(e1) * 1e3)
         t = sorted(ts[1:])[len(ts[1:]) // 2]
         gb = (x.numel() * 2 + out.numel() * 4) / 1e9
-        print(f"head_tc={tc} wait_mode={wm}: {t:.1f} us per {frames} frames  ({gb / t * 1e6:.0f} GB/s algorithmic)")
+        print(f"head_tc={tc} wait_mode={wm}: {t:.1f} us per {frames} frames of {H}x{W}, Cin {Cin} Cout {Cout}  ({gb / t * 1e6:.0f} GB/s algorithmic)")
     op.lib.npvp_set_option(b"head_tc", 1)
 
 
