@@ -19,7 +19,7 @@ PAD_ZERO, PAD_REFLECT, PAD_REPLICATE = 0, 1, 2
 ATTN_SPATIAL, ATTN_TEMPORAL = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnpvp_b200.so")
+LIB_PATH = os.environ.get("NPVP_B200_LIB") or os.path.join(_HERE, "libnpvp_b200.so")   # NPVP_B200_LIB: another build of the same C-ABI (same-box A/B runs)
 
 _i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
 
