@@ -141,6 +141,7 @@ class Ops:
         self.lib.npvp_set_option(b"conv_tma", int(os.environ.get("NPVP_B200_CONV_TMA", "1")))
         self.lib.npvp_set_option(b"gemm_prefetch", int(os.environ.get("NPVP_B200_GEMM_PREFETCH", "1")))
         self.lib.npvp_set_option(b"head_tc", int(os.environ.get("NPVP_B200_HEAD_TC", "1")))
+        self.lib.npvp_set_option(b"stem_tc", int(os.environ.get("NPVP_B200_STEM_TC", "1")))
 
     # -- plumbing -------------------------------------------------------------------------------
     def _stream(self):

@@ -132,6 +132,10 @@ conv7x7_stem_kernel(const float* __restrict__ x, const uint8_t* __restrict__ x_u
   }
 }
 
+// head_tc.cu: the tcgen05 form of the stem (im2col row blocks built once per input row in a shared-memory ring); 1 = geometry not covered
+int npvp_conv7x7_stem_tc_try(const float* x, const uint8_t* x_u8, const float* mean, const float* stdv, const float* w, const float* shift, void* out,
+                             int64_t frames, int Cin, int Cout, int H, int W, int fp16, cudaStream_t st);
+
 extern "C" int npvp_conv7x7_stem(const float* x, const float* w, const float* shift, void* out_bf16, int64_t frames, int Cin,
                                  int Cout, int H, int W, int fp16, const void* x_u8, const float* norm_mean, const float* norm_std,
                                  void* stream) {
@@ -141,6 +145,10 @@ extern "C" int npvp_conv7x7_stem(const float* x, const float* w, const float* sh
   StemNorm nrm = {};
   if (x_u8) for (int c = 0; c < Cin && c < 3; ++c) { nrm.mean[c] = norm_mean[c]; nrm.std[c] = norm_std[c]; }
   NPVP_REQUIRE(Cout % 32 == 0 && H >= 4 && W >= 4, "npvp_conv7x7_stem: Cout must be a multiple of 32, H/W >= 4");
+  {
+    const int rc = npvp_conv7x7_stem_tc_try(x, (const uint8_t*)x_u8, norm_mean, norm_std, w, shift, out_bf16, frames, Cin, Cout, H, W, fp16, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
   NPVP_REQUIRE(frames * (Cout / 32) <= 65535, "npvp_conv7x7_stem: too many frames per launch (%lld)", (long long)frames);
   const int tiles_y = (H + kStemTY - 1) / kStemTY, tiles_x = (W + kStemTX - 1) / kStemTX;
   // vertically adjacent tiles per block: as many as still leave ~2 blocks per SM (296 on a B200) in flight

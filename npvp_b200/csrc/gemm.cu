@@ -1559,6 +1559,7 @@ void npvp_set_ffn_scalar(int v);   // predictor_kernels.cu
 void npvp_set_ffn_mid16_mode(int m);   // ffn_mid16.cu
 void npvp_head_tc_enable(int v);       // head_tc.cu
 void npvp_head_tc_wait(int v);         // head_tc.cu
+void npvp_stem_tc_enable(int v);       // head_tc.cu
 
 extern "C" int npvp_set_option(const char* name, int value) {
   NPVP_REQUIRE(name != nullptr, "npvp_set_option: null name");
@@ -1571,6 +1572,7 @@ extern "C" int npvp_set_option(const char* name, int value) {
   if (strcmp(name, "ffn_mid16_mode") == 0) { npvp_set_ffn_mid16_mode(value); return NPVP_OK; }
   if (strcmp(name, "head_tc") == 0) { npvp_head_tc_enable(value); return NPVP_OK; }
   if (strcmp(name, "head_tc_wait") == 0) { npvp_head_tc_wait(value); return NPVP_OK; }
+  if (strcmp(name, "stem_tc") == 0) { npvp_stem_tc_enable(value); return NPVP_OK; }
   NPVP_REQUIRE(false, "npvp_set_option: unknown option '%s'", name);
   return NPVP_ERR_INVALID;
 }

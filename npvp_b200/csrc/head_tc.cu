@@ -66,6 +66,12 @@ __device__ __forceinline__ void ht_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void ht_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+}
 // wait::ld that "redefines" the registers of a tcgen05.ld issued a loop iteration ahead (see tmem_ld_wait_regs in tc_ptx.cuh)
 __device__ __forceinline__ void ht_tmem_ld_wait8(uint32_t (&r)[8]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -383,6 +389,249 @@ conv7x7_head_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadTcP
   if (warp == 2) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, kHtTmemBufs * 32); }
 }
 
+// =============================================================================================
+// 7x7 reflect-padded STEM convolution (Cin = 1 / 3 -> Cout = 32 / 64, folded BN + ReLU; ResNetAutoEncoder.py:62-66) on tcgen05
+// =============================================================================================
+// Same flattened-row scheme as the head above, with the roles of the taps swapped: the 7 horizontal taps x 4 padded channels are
+// the K = 32 of one kernel row (the last 4 hit zero weights), so the A row of position x' for input row r is the 64 contiguous
+// bytes "pixels x' .. x'+7" of the staged 16-bit row - an overlapping window no tensor map can express.  Four builder warps
+// convert each input row once (fp32 planes or uint8 pixels -> 4-channel 16-bit pixels, reflection resolved in the index) and
+// write its im2col block (P positions x 64 B, 64-byte swizzle) into the ring; the block serves all seven vertical taps as the
+// same window one row pitch further down, exactly like the head.  N = Cout, so the accumulator IS the output: the epilogue adds the
+// folded shift, applies ReLU and stores 16-bit NHWC (a thread owns a position: 32 / 64 contiguous bytes, a warp 1 / 2 KB).
+// The mma.sync stem (autoencoder_kernels.cu) ran at 0.13 of the HBM roofline (212-237 us per 128 Cityscapes frames).
+constexpr int kStBuilders = 8;          // warps 0, 2, 12..17 build rows (round robin); 1 / 3 issue MMAs; 4..11 epilogue
+constexpr int kStThreads = 576;
+constexpr int kStTmemBufs = 4;
+
+struct StemTcParams {
+  const float* x;        // fp32 frames [frames, CIN, H, W] or
+  const uint8_t* x_u8;   // uint8 pixels (VidToTensor + VidNormalize in the builder, reference operation order)
+  float mean[3], std[3];
+  const float* w;        // fp32 [(ky, kx, ci), Cout], BN scale folded
+  const float* shift;    // fp32 [Cout]
+  h16* out;              // 16-bit NHWC [frames, H, W, Cout]
+  int64_t total_rows;
+  int H, W, P, D, R, fp16, wait_mode;
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kStThreads, 1)
+conv7x7_stem_tc_kernel(const StemTcParams p) {
+  constexpr int PIXB = 64;                                        // K = 32 16-bit values per position and kernel row
+  extern __shared__ __align__(1024) uint8_t st_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)st_smem_raw + 1023) & ~(uintptr_t)1023);
+  const int P = p.P, D = p.D, R = p.R, H = p.H, W = p.W;
+  const uint32_t row_bytes = (uint32_t)P * PIXB;
+  uint8_t* ring = smem;                                           // [R + D rows][P positions][64 B], swizzled
+  uint8_t* wsm = ring + (size_t)(R + D) * row_bytes;              // [7 ky][COUT n][64 B], swizzled
+  uint8_t* stage = wsm + 7 * COUT * PIXB;                         // [kStBuilders][P + 8 pixels][8 B]
+  const int stage_pitch = (P + 8) * 8;
+  uint64_t* ready = reinterpret_cast<uint64_t*>(stage + kStBuilders * stage_pitch);   // row built     [kHtRing]
+  uint64_t* freeb = ready + kHtRing;                              // row consumed  [kHtRing]
+  uint64_t* tfull = freeb + kHtRing;                              // [kStTmemBufs]
+  uint64_t* tempty = tfull + kStTmemBufs;                         // [kStTmemBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kStTmemBufs);
+  HtSeg* segs = reinterpret_cast<HtSeg*>(tmem_slot + 2);
+  int* seg_count = reinterpret_cast<int*>(segs + kHtMaxSeg + 1);
+  int64_t* rowtab = reinterpret_cast<int64_t*>(seg_count + 2);    // [n_rows] element offset of (frame, y, 0, 0) in out, -1: no output row
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t o_begin = p.total_rows * blockIdx.x / gridDim.x, o_end = p.total_rows * (blockIdx.x + 1) / gridDim.x;
+  if (threadIdx.x == 0) {
+    int ns = 0, s = 0;
+    for (int64_t o = o_begin; o < o_end && ns < kHtMaxSeg;) {
+      const int y = (int)(o % H);
+      const int n = (int)min((int64_t)(H - y), o_end - o);
+      segs[ns].s0 = s; segs[ns].n = n; segs[ns].f = (int)(o / H); segs[ns].y0 = y;
+      s += n + 6; o += n; ++ns;
+    }
+    segs[ns].s0 = s; segs[ns].n = 0; segs[ns].f = 0; segs[ns].y0 = 0;
+    *seg_count = ns;
+    for (int i = 0; i < kHtRing; ++i) { ptx::mbar_init(&ready[i], 1); ptx::mbar_init(&freeb[i], 1); }
+    for (int i = 0; i < kStTmemBufs; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 8); }
+    ptx::fence_barrier_init();
+  }
+  // B operand: row n = output channel, K index k = kx * 4 + ci (kx = 7 and ci >= CIN are zero), one 64-byte swizzle row per (ky, n)
+  {
+    const uint32_t w_s = ptx::smem_u32(wsm);
+    for (int i = threadIdx.x; i < 7 * COUT * 32; i += kStThreads) {
+      const int k = i & 31, n = (i >> 5) % COUT, ky = i / (32 * COUT);
+      const int kx = k >> 2, ci = k & 3;
+      const float v = (kx < 7 && ci < CIN) ? __ldg(p.w + ((size_t)(ky * 7 + kx) * CIN + ci) * COUT + n) : 0.f;
+      const int r = ky * COUT + n, c = k >> 3;
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(w_s + (uint32_t)r * PIXB + ((c ^ ((r >> 1) & 3)) << 4) + (k & 7) * 2), "h"(float_to_h16(v, p.fp16)) : "memory");
+    }
+  }
+  ptx::fence_proxy_async();
+  if (warp == 3) { ptx::tmem_alloc(tmem_slot, kStTmemBufs * COUT); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nseg = *seg_count;
+  const int n_rows = segs[nseg].s0;
+  const int n_tiles = n_rows > 6 ? (int)(((int64_t)(n_rows - 6) * P + 127) / 128) : 0;
+  const uint32_t ring_s = ptx::smem_u32(ring);
+  for (int k = 0; k < nseg; ++k)
+    for (int j = threadIdx.x; j < segs[k].n + 6; j += kStThreads)
+      rowtab[segs[k].s0 + j] = j < segs[k].n ? ((int64_t)segs[k].f * H + segs[k].y0 + j) * W * COUT : -1;
+  __syncthreads();
+
+  const int builder = warp == 0 ? 0 : (warp == 2 ? 1 : (warp >= 12 ? warp - 10 : -1));
+  if (builder >= 0) {
+    // ---------------- row builders: stream row s = builder, builder + kStBuilders, ... ----------------
+    // The pixels of a builder's NEXT row are requested before it writes the current row's im2col block, so the DRAM latency of
+    // the fp32 / uint8 frames hides behind ~250 shared-memory instructions (first version: 4 builders, load -> convert -> build
+    // in sequence = 9 k clk per row and builder, the tensor pipe waiting: 168 us per 148 frames).
+    const uint32_t stg_s = ptx::smem_u32(stage) + (uint32_t)(builder * stage_pitch);
+    constexpr int kLoads = (256 + 8 + 31) / 32;                   // staged pixels per lane, P <= 256
+    float raw[kLoads][CIN];
+    int seg = 0;
+    auto load_row = [&](int s) {
+      while (s >= segs[seg + 1].s0) ++seg;
+      const int f = segs[seg].f;
+      const int yy = ht_reflect(segs[seg].y0 - 3 + (s - segs[seg].s0), H);
+      // staged pixel i is image column reflect(i - 3); columns past the right padding repeat the last one (they only meet zero weights)
+#pragma unroll
+      for (int u = 0; u < kLoads; ++u) {
+        const int i = lane + 32 * u;
+        if (i < P + 8) {
+          const int xx = ht_reflect(min(i - 3, W + 2), W);
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) {
+            const size_t off = (((size_t)f * CIN + ci) * H + yy) * W + xx;
+            raw[u][ci] = p.x_u8 ? (float)__ldg(p.x_u8 + off) : __ldg(p.x + off);
+          }
+        }
+      }
+    };
+    if (builder < n_rows) load_row(builder);
+    for (int s = builder; s < n_rows; s += kStBuilders) {
+      const int slot = s % R, use = s / R;
+      __syncwarp();                                               // the previous row's im2col reads of the staging row are done
+#pragma unroll
+      for (int u = 0; u < kLoads; ++u) {
+        const int i = lane + 32 * u;
+        if (i < P + 8) {
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci)     // uint8 pixels: VidToTensor + VidNormalize in the reference's operation order
+            v[ci] = p.x_u8 ? __fdiv_rn(__fsub_rn(__fdiv_rn(raw[u][ci], 255.0f), p.mean[ci]), p.std[ci]) : raw[u][ci];
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(stg_s + (uint32_t)i * 8), "r"(pack_h16x2(v[0], v[1], p.fp16)), "r"(pack_h16x2(v[2], v[3], p.fp16)) : "memory");
+        }
+      }
+      __syncwarp();
+      if (s + kStBuilders < n_rows) load_row(s + kStBuilders);
+      if (use > 0) ht_wait(&freeb[slot], (use - 1) & 1, p.wait_mode);
+      // im2col block: 16-byte chunk c of position x' = staged pixels x' + 2c, x' + 2c + 1
+      for (int rep = 0; rep < (slot < D ? 2 : 1); ++rep) {
+        const uint32_t row = ring_s + (uint32_t)(rep ? R + slot : slot) * row_bytes;
+        for (int idx = lane; idx < P * 4; idx += 32) {
+          const int xp = idx >> 2, c = idx & 3;
+          uint32_t a0, a1, a2, a3;
+          const uint32_t src = stg_s + (uint32_t)(xp + 2 * c) * 8;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(src) : "memory");
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a2), "=r"(a3) : "r"(src + 8) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (uint32_t)xp * PIXB + ((c ^ ((xp >> 1) & 3)) << 4)), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
+        }
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ht_mbar_arrive(&ready[slot]);
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ---------------- two MMA issuers, alternate tiles: 7 taps x 2 MMAs (M 128, N COUT, K 16) ----------------
+    if (ptx::elect_one()) {
+      const int me = warp >> 1;
+      const uint32_t idesc = ht_idesc(128, COUT, p.fp16);
+      const uint32_t hi = (uint32_t)(ht_desc<PIXB>(0) >> 32);
+      const uint32_t a_base = (uint32_t)ht_desc<PIXB>(ring_s), b_base = (uint32_t)ht_desc<PIXB>(ptx::smem_u32(wsm));
+      const uint32_t row16 = row_bytes >> 4;
+      int rows_ready = 0, rdy_slot = 0;
+      uint32_t rdy_par = 0;
+      int r0 = 0, off = 0, slot0 = 0;
+      if (me) { off = 128; while (off >= P) { off -= P; ++r0; if (++slot0 == R) slot0 = 0; } }
+      uint32_t te_par = 0;
+      for (int t = me; t < n_tiles; t += 2) {
+        int r_last = r0 + 6, o2 = off + 127;
+        while (o2 >= P) { o2 -= P; ++r_last; }
+        r_last = min(r_last, n_rows - 1);
+        while (rows_ready <= r_last) {
+          ht_wait(&ready[rdy_slot], rdy_par, p.wait_mode);
+          ++rows_ready;
+          if (++rdy_slot == R) { rdy_slot = 0; rdy_par ^= 1; }
+        }
+        const int buf = t % kStTmemBufs;
+        if (t >= kStTmemBufs) ht_wait(&tempty[buf], te_par, p.wait_mode);
+        if (buf >= kStTmemBufs - 2 && t >= kStTmemBufs) te_par ^= 1;
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * COUT;
+        const uint32_t a_off = a_base + (uint32_t)off * (PIXB / 16);
+        int slot = slot0;
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+          const uint32_t a_lo = a_off + (uint32_t)slot * row16, b_lo = b_base + ky * (COUT * PIXB / 16);
+          if (++slot == R) slot = 0;
+          ht_umma_tap<2>(d_tmem, a_lo, b_lo, hi, idesc, ky ? 1u : 0u);
+        }
+        ptx::umma_commit(&tfull[buf]);
+        off += 256;
+        while (off >= P) { off -= P; ++r0; if (++slot0 == R) slot0 = 0; }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ---------------- epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves; a thread owns one position ----------------
+    constexpr int CW = COUT / 2;                                  // channels per warp: 16 / 32
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int m = quad * 32 + lane;
+    float sh[CW];
+#pragma unroll
+    for (int c = 0; c < CW; ++c) sh[c] = __ldg(p.shift + half * CW + c);
+    const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + half * CW;
+    const uint32_t rt_s = ptx::smem_u32(rowtab);
+    int s = 0, xo = m - 128;                                      // stream row / column of this thread's position, one tile behind
+    int fr_row = 0, fr_off = 0, fr_slot = 0;
+    uint32_t tf_par = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int buf = t % kStTmemBufs;
+      if (t && buf == 0) tf_par ^= 1;
+      ht_wait(&tfull[buf], tf_par, p.wait_mode);
+      ptx::tc_fence_after();
+      uint32_t r[CW];
+      if (CW == 16) ht_tmem_ld16(t_addr + buf * COUT, reinterpret_cast<uint32_t(&)[16]>(r));
+      else ptx::tmem_ld_32x32(t_addr + buf * COUT, reinterpret_cast<uint32_t(&)[32]>(r));
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ht_mbar_arrive(&tempty[buf]);
+      if (threadIdx.x == 128) {                                   // every MMA of the tiles <= t has completed: rows in front of tile t + 1 are free
+        fr_off += 128;
+        while (fr_off >= P) { fr_off -= P; if (fr_row < n_rows) ht_mbar_arrive(&freeb[fr_slot]); ++fr_row; if (++fr_slot == R) fr_slot = 0; }
+      }
+      xo += 128; while (xo >= P) { xo -= P; ++s; }
+      if (xo < W && s < n_rows) {
+        long long rb;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(rb) : "r"(rt_s + (uint32_t)s * 8) : "memory");
+        if (rb >= 0) {
+          uint32_t pk[CW / 2];
+#pragma unroll
+          for (int c = 0; c < CW / 2; ++c)
+            pk[c] = pack_h16x2(fmaxf(__uint_as_float(r[2 * c]) + sh[2 * c], 0.f), fmaxf(__uint_as_float(r[2 * c + 1]) + sh[2 * c + 1], 0.f), p.fp16);
+          h16* dst = p.out + (size_t)rb + (size_t)xo * COUT + half * CW;
+#pragma unroll
+          for (int c = 0; c < CW / 8; ++c)
+            *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 3) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, kStTmemBufs * COUT); }
+}
+
+int g_stem_tc = 1;    // npvp_set_option("stem_tc", 0): always the mma.sync stem kernel (A/B switch)
 int g_head_tc_wait = 1;
 int g_head_tc = 1;    // npvp_set_option("head_tc", 0): always the mma.sync head kernel (A/B switch)
 
@@ -442,5 +691,47 @@ int npvp_conv7x7_head_tc_try(const void* x, const void* w, const float* bias, fl
   }
   kern<<<(unsigned)grid, kHtThreads, smem, st>>>(tm, p);
   NPVP_LAUNCH_CHECK("conv7x7_head_tc_kernel");
+  return NPVP_OK;
+}
+
+void npvp_stem_tc_enable(int v) { g_stem_tc = v; }
+
+// Returns NPVP_OK after launching, or 1 when the geometry is not covered (the caller runs the mma.sync kernel).
+int npvp_conv7x7_stem_tc_try(const float* x, const uint8_t* x_u8, const float* mean, const float* stdv, const float* w, const float* shift, void* out,
+                             int64_t frames, int Cin, int Cout, int H, int W, int fp16, cudaStream_t st) {
+  if (!g_stem_tc || (Cin != 1 && Cin != 3) || (Cout != 32 && Cout != 64) || W + 6 > 256 || H < 4 || W < 4 || frames * (int64_t)H >= (1ll << 31)) return 1;
+  static int num_sms = 0, max_smem = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  }
+  const int P = (W + 6 + 7) / 8 * 8;
+  const int D = (P - 8 + 127) / P;
+  const int fixed = 7 * Cout * 64 + kStBuilders * (P + 8) * 8 + (2 * kHtRing + 2 * kStTmemBufs) * 8 + 16 + (kHtMaxSeg + 1) * 16 + 16 + kHtMaxRows * 8 + 1024;
+  const int R = min(kHtRing, (max_smem - fixed) / (P * 64) - D);
+  if (D > kHtMaxDup || R < D + 8) return 1;
+  const int smem = fixed + (R + D) * P * 64;
+  StemTcParams p = {};
+  p.x = x; p.x_u8 = x_u8; p.w = w; p.shift = shift; p.out = (h16*)out;
+  if (x_u8) for (int c = 0; c < Cin; ++c) { p.mean[c] = mean[c]; p.std[c] = stdv[c]; }
+  p.total_rows = frames * H;
+  p.H = H; p.W = W; p.P = P; p.D = D; p.R = R; p.fp16 = fp16; p.wait_mode = g_head_tc_wait;
+  int64_t grid = min((int64_t)num_sms, max((int64_t)1, p.total_rows / 16));
+  grid = max(grid, (frames + kHtMaxSeg - 5) / (kHtMaxSeg - 4));
+  grid = max(grid, (p.total_rows + 1023) / 1024);
+  if (grid > num_sms) grid = (grid + num_sms - 1) / num_sms * num_sms;
+  void (*kern)(const StemTcParams) = Cin == 1 ? (Cout == 32 ? conv7x7_stem_tc_kernel<1, 32> : conv7x7_stem_tc_kernel<1, 64>)
+                                              : (Cout == 32 ? conv7x7_stem_tc_kernel<3, 32> : conv7x7_stem_tc_kernel<3, 64>);
+  static int attr[4] = {0, 0, 0, 0};
+  const int ki = (Cin == 3) * 2 + (Cout == 64);
+  if (attr[ki] < smem) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) { npvp_set_error("conv7x7_stem_tc: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(err)); return NPVP_ERR_CUDA; }
+    attr[ki] = smem;
+  }
+  kern<<<(unsigned)grid, kStThreads, smem, st>>>(p);
+  NPVP_LAUNCH_CHECK("conv7x7_stem_tc_kernel");
   return NPVP_OK;
 }

@@ -311,7 +311,8 @@ class SpecOps:
             x = (x.reshape(-1, Cin, H, W).to(torch.float32).div(255) - m) / sdv
         img = x.reshape(-1, Cin, H, W)
         wt = w.reshape(7, 7, Cin, Cout).permute(3, 2, 0, 1)
-        o = F.conv2d(F.pad(img, (3, 3, 3, 3), mode="reflect"), wt, shift)
+        with torch.backends.cudnn.flags(enabled=False):     # see conv7x7_head
+            o = F.conv2d(F.pad(img, (3, 3, 3, 3), mode="reflect"), wt, shift)
         out.copy_(torch.relu(o).permute(0, 2, 3, 1).reshape(out.shape).to(out.dtype))
 
     def conv7x7_head(self, x, w, bias, out, Cin, Cout, H, W, phase_major, act, out_u8=None, renorm=None):

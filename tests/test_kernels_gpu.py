@@ -323,6 +323,32 @@ def test_conv7x7_stem(op, spec, Cin, Cout, HW, dt):
 
 
 @pytest.mark.parametrize("dt", H16)
+@pytest.mark.parametrize("frames,Cin,Cout,H,W,u8", [(3, 3, 32, 128, 128, False), (5, 1, 64, 64, 64, False), (40, 3, 32, 128, 128, True), (3, 3, 64, 20, 36, False),
+                                                    (300, 1, 64, 64, 64, True), (2, 3, 32, 128, 160, False), (1, 1, 32, 8, 8, False), (9, 3, 32, 4, 250, True)])
+def test_conv7x7_stem_tcgen05_rows(op, spec, frames, Cin, Cout, H, W, u8, dt):
+    """The row-streaming tcgen05 stem (head_tc.cu: im2col row blocks built once per input row, Cout 32 / 64) against the kernel
+    specification and the mma.sync tile kernel: fp32 and uint8 input, frame segments, ring wrap-around, rectangular / tiny frames."""
+    g = torch.Generator().manual_seed(5)
+    if u8:
+        x = torch.randint(0, 256, (frames, Cin, H, W), generator=g, dtype=torch.uint8).to(DEV)
+        norm = ([0.4 + 0.05 * c for c in range(Cin)], [0.25 + 0.02 * c for c in range(Cin)])
+    else:
+        x, norm = rn(frames, Cin, H, W, seed=1), None
+    w, sh = rn(49 * Cin, Cout, seed=2, scale=0.1), rn(Cout, seed=3, scale=0.2)
+    outs = []
+    for tc in (1, 0):
+        op.lib.npvp_set_option(b"stem_tc", tc)
+        o = torch.empty(frames * H * W, Cout, device=DEV, dtype=dt)
+        op.conv7x7_stem(x, w, sh, o, Cin, Cout, H, W, norm=norm)
+        outs.append(o)
+    op.lib.npvp_set_option(b"stem_tc", 1)
+    o2 = torch.empty_like(outs[0])
+    spec.conv7x7_stem(x, w, sh, o2, Cin, Cout, H, W, norm=norm)
+    close(outs[0], o2, 1e-2, "conv7x7_stem tcgen05")
+    close(outs[0], outs[1], 4e-3, "conv7x7_stem tcgen05 vs mma.sync")     # one 16-bit rounding of the output apart at most
+
+
+@pytest.mark.parametrize("dt", H16)
 @pytest.mark.parametrize("Cin,Cout,HW,phase,act", [(32, 3, 128, True, 3), (64, 1, 64, True, 4), (32, 3, 48, False, 3), (64, 3, 64, True, 3),
                                                   (32, 2, 36, False, 0), (64, 1, 76, False, 4)])
 def test_conv7x7_head(op, spec, Cin, Cout, HW, phase, act, dt):
