@@ -221,7 +221,9 @@ int npvp_tokens_to_nchw(const float* x_f32, const void* x_bf16, float* out, int6
  * x fp32 NCHW [frames,Cin,H,W]  OR  x_u8 uint8 pixels [frames,Cin,H,W] with the dataset's VidNormalize mean / std (host pointers,
  * Cin values each): the stem then applies VidToTensor + VidNormalize itself, ((u8 / 255) - mean) / std in the reference's
  * operation order (utils/dataset.py:835-858) - exactly one of x and x_u8 is non-NULL;
- * w fp32 [49*Cin, Cout] (tap-major, BN scale folded); shift fp32 [Cout]; out bf16 NHWC [frames,H,W,Cout]. */
+ * w fp32 [49*Cin, Cout] (tap-major, BN scale folded); shift fp32 [Cout]; out bf16 NHWC [frames,H,W,Cout].
+ * Cout 32 / 64 with W <= 250 runs on tcgen05 (csrc/head_tc.cu: im2col row blocks built once per input row in a shared-memory ring,
+ * 7 taps x 2 MMAs of M 128 x N Cout per 128 positions); otherwise the mma.sync tile kernel.  npvp_set_option("stem_tc", 0) forces the latter. */
 int npvp_conv7x7_stem(const float* x, const float* w, const float* shift, void* out_bf16, int64_t frames, int Cin,
                       int Cout, int H, int W, int fp16, const void* x_u8, const float* norm_mean, const float* norm_std, void* stream);
 /* 7x7 head: reflect-pad 3, conv + bias + Tanh|Sigmoid (ResNetAutoEncoder.py:184-189).
