@@ -104,6 +104,11 @@ def main():
     op.conv7x7_stem(u8, ws, sh, s1, 3, 32, 32, 32, norm=norm)
     spec.conv7x7_stem(u8, ws, sh, s2, 3, 32, 32, 32, norm=norm)
     close(s1, s2, 5e-3, "conv7x7 stem, uint8 ingest")
+    op.lib.npvp_set_option(b"stem_tc", 0)            # the calls above ran the tcgen05 row-streaming stem; this one the mma.sync tile kernel
+    op.conv7x7_stem(xs, ws, sh, s1, 3, 32, 32, 32)
+    op.lib.npvp_set_option(b"stem_tc", 1)
+    spec.conv7x7_stem(xs, ws, sh, s2, 3, 32, 32, 32)
+    close(s1, s2, 5e-3, "conv7x7 stem (mma.sync tile kernel)")
     wc = rn(64, 9 * 32, seed=44, scale=0.06, dtype=dt)
     c1, c2 = torch.empty(2 * 16 * 16, 64, dtype=dt, device=DEV), torch.empty(2 * 16 * 16, 64, dtype=dt, device=DEV)
     op.conv_gemm(s2, wc, 2, 32, 32, 32, 3, 3, 2, 1, 0, 16, 16, bias=rn(64, seed=45), act=1, out_bf16=c1)
