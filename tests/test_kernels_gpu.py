@@ -387,6 +387,33 @@ def test_conv7x7_head_tcgen05_rows(op, spec, frames, Cin, Cout, H, W, act, dt):
     assert float((pix - outs[0][1].float()).abs().max()) <= 1
 
 
+def test_conv7x7_tcgen05_more_blocks_than_sms(op):
+    """Batches whose row tables would overflow get more CTAs than SMs (whole waves): 1250 frames of 128 x 128 = 160 000 output rows.
+    Head and stem, tcgen05 against the mma.sync tile kernels on the same input."""
+    from npvp_b200._lib import pack_head_weights
+    frames, H, W = 1250, 128, 128
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(frames * H * W, 32, generator=g) * 0.7).to(DEV).half()
+    w, b = pack_head_weights(rn(49 * 32, 3, seed=2, scale=0.03), torch.float16), rn(3, seed=3, scale=0.2)
+    o = []
+    for tc in (1, 0):
+        op.lib.npvp_set_option(b"head_tc", tc)
+        o.append(torch.empty(frames, 3, H, W, device=DEV))
+        op.conv7x7_head(x, w, b, o[-1], 32, 3, H, W, False, 3)
+    op.lib.npvp_set_option(b"head_tc", 1)
+    assert float((o[0] - o[1]).abs().max()) < 1e-5
+    del x, o
+    xs = torch.randint(0, 256, (frames, 3, H, W), generator=g, dtype=torch.uint8).to(DEV)
+    ws, sh = rn(147, 32, seed=4, scale=0.1), rn(32, seed=5, scale=0.2)
+    o = []
+    for tc in (1, 0):
+        op.lib.npvp_set_option(b"stem_tc", tc)
+        o.append(torch.empty(frames * H * W, 32, device=DEV, dtype=torch.float16))
+        op.conv7x7_stem(xs, ws, sh, o[-1], 3, 32, H, W, norm=([0.4, 0.45, 0.5], [0.25, 0.27, 0.29]))
+    op.lib.npvp_set_option(b"stem_tc", 1)
+    close(o[0], o[1], 4e-3, "stem, 1250 frames")
+
+
 @pytest.mark.parametrize("dt", H16)
 @pytest.mark.parametrize("C,H", [(64, 64), (128, 32), (256, 16), (512, 8)])
 def test_nonlocal_pieces(op, spec, C, H, dt):
