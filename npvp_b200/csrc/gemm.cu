@@ -298,7 +298,7 @@ __device__ __forceinline__ void add_h16x4(float (&v)[4], uint32_t lo, uint32_t h
 }
 // OUTK: 0 16-bit, 1 fp32, 2 both, 4 16-bit + statistics.  `next()` runs after the last use of rs and before the stores.
 template <int ACT, int RES, int OUTK, bool FP16, class Next>
-__device__ __forceinline__ void epi_direct_chunk(const uint32_t (&r)[32], const float* __restrict__ bias_n0, ResD<RES>& rs, float* out32, h16* out16,
+__device__ __forceinline__ void epi_direct_chunk(const uint32_t (&r)[32], uint32_t bias_s, ResD<RES>& rs, float* out32, h16* out16,
                                                  bool row_ok, float& st_s, float& st_q, Next&& next) {
   constexpr int fp16 = FP16 ? 1 : 0;
   constexpr bool W16 = OUTK == 0 || OUTK == 2 || OUTK == 4, W32 = OUTK == 1 || OUTK == 2;
@@ -307,7 +307,7 @@ __device__ __forceinline__ void epi_direct_chunk(const uint32_t (&r)[32], const 
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias_n0) b = __ldg(reinterpret_cast<const float4*>(bias_n0) + j);       // warp-uniform address: one L1 broadcast
+    if (bias_s) b = lds128(bias_s + 16u * j);                                   // the warp's bias slice, cached in its staging area (broadcast read)
     float v[4] = {__uint_as_float(r[4 * j + 0]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y, __uint_as_float(r[4 * j + 2]) + b.z,
                   __uint_as_float(r[4 * j + 3]) + b.w};
     if (ACT == NPVP_ACT_RELU && RES == 0 && OUTK == 0) {
@@ -362,7 +362,7 @@ __device__ __forceinline__ void epi_direct_chunk(const uint32_t (&r)[32], const 
 //   out_off(n0): element offset of (m, n0) in the outputs;  release(): this warp's part of the accumulator is in registers;
 //   next_tile(): residuals of the first chunk of the warp's NEXT tile into rs (RES > 0).
 template <int KCH, int ACT, int RES, int OUTK, class OutOff, class Release, class NextTile>
-__device__ __forceinline__ void epi_direct_tile(uint32_t t0, int64_t m, bool row_ok, int64_t n_first, int64_t N, const EpiParams& ep, bool has_bias,
+__device__ __forceinline__ void epi_direct_tile(uint32_t t0, int64_t m, bool row_ok, int64_t n_first, int64_t N, const EpiParams& ep, uint32_t bias_s,
                                                 int fp16, ResD<RES>& rs, float& st_s, float& st_q, OutOff&& out_off, Release&& release,
                                                 NextTile&& next_tile) {
   uint32_t r0[32], r1[32];
@@ -372,15 +372,15 @@ __device__ __forceinline__ void epi_direct_tile(uint32_t t0, int64_t m, bool row
     const int64_t off = out_off(n0);
     float* o32 = ep.out_f32 ? ep.out_f32 + off : nullptr;
     h16* o16 = ep.out_bf16 ? ep.out_bf16 + off : nullptr;
-    const float* bn = has_bias ? ep.bias + n0 : nullptr;
     auto next = [&]() {
       if (RES > 0) {
         if (i + 1 < KCH && n0 + 32 < N) load_resd<RES>(rs, ep, m, n0 + 32, row_ok);
         else next_tile();
       }
     };
-    if (fp16) epi_direct_chunk<ACT, RES, OUTK, true>(r, bn, rs, o32, o16, row_ok, st_s, st_q, next);
-    else      epi_direct_chunk<ACT, RES, OUTK, false>(r, bn, rs, o32, o16, row_ok, st_s, st_q, next);
+    const uint32_t bs = bias_s ? bias_s + 128u * (uint32_t)i : 0u;
+    if (fp16) epi_direct_chunk<ACT, RES, OUTK, true>(r, bs, rs, o32, o16, row_ok, st_s, st_q, next);
+    else      epi_direct_chunk<ACT, RES, OUTK, false>(r, bs, rs, o32, o16, row_ok, st_s, st_q, next);
   };
   ptx::tmem_ld_32x32(t0, r0);
 #pragma unroll 1
@@ -707,6 +707,7 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     constexpr int kColsPerWarp = BN / 2;
     ResRaw<RES> rr;
     ResD<RES> rd;                                                    // direct epilogue: residuals of the chunk about to be processed
+    int bias_blk = -1;                                               // n-block whose bias slice the staging area holds (direct epilogue)
     int64_t rd_tile = -1;                                            // tile whose first chunk rd was loaded for
     int64_t rr_tile = -1;                                            // which (tile, tile column) rr holds
     int rr_c = -1;
@@ -755,10 +756,24 @@ gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         };
         if (RES > 0 && rd_tile != t) load_resd<RES>(rd, ep, m, nw, m < M && nw < N);   // first tile of this warp
         float st_s = 0.f, st_q = 0.f;
+        // The warp's bias slice (kColsPerWarp floats) lives in its (otherwise unused) staging area and is refreshed only when the
+        // tile's n-block changes: the direct layout needs 32 bias values per thread and chunk, and eight warp-uniform LDG.128 per
+        // chunk were the top stall of the store-bound epilogues (r02 ncu of the last transposed conv: 22 % of the samples on the
+        // FADDs that consume them).
+        if (has_bias && n_blk != bias_blk) {
+          __syncwarp();
+          if (lane * 4 < kColsPerWarp) {
+            const int64_t nb = nw + lane * 4;
+            const float4 b = nb < N ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sts128(stg_addr + 16u * (uint32_t)lane, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+          }
+          __syncwarp();
+          bias_blk = n_blk;
+        }
         ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
         if (threadIdx.x == 128) NPVP_TRACE(4);
         ptx::tc_fence_after();
-        epi_direct_tile<kChunks, ACT, RES, OUTK>(t0, m, m < M, nw, N, ep, has_bias, fp16, rd, st_s, st_q, out_off, release, next_tile);
+        epi_direct_tile<kChunks, ACT, RES, OUTK>(t0, m, m < M, nw, N, ep, has_bias ? stg_addr : 0u, fp16, rd, st_s, st_q, out_off, release, next_tile);
         if (threadIdx.x == 128) NPVP_TRACE(5);
         if (OUTK == kOutStats16) {
           // this warp's 32 rows x 128 columns lie inside one 64-row frame: one (sum, sum of squares) slot per warp and tile
@@ -1033,6 +1048,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     constexpr int kColsPerWarp = BN / 2;
     ResRaw<RES> rr;
     ResD<RES> rd;                                                    // direct epilogue: residuals of the chunk about to be processed
+    int bias_blk = -1;                                               // n-block whose bias slice the staging area holds (direct epilogue)
     int64_t rd_tile = -1;                                            // tile whose first chunk rd was loaded for
     int64_t rr_tile = -1;
     int rr_c = -1;
@@ -1070,10 +1086,24 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         };
         if (RES > 0 && rd_tile != t) load_resd<RES>(rd, ep, m, nw, m < M && nw < N);
         float st_s = 0.f, st_q = 0.f;
+        // The warp's bias slice (kColsPerWarp floats) lives in its (otherwise unused) staging area and is refreshed only when the
+        // tile's n-block changes: the direct layout needs 32 bias values per thread and chunk, and eight warp-uniform LDG.128 per
+        // chunk were the top stall of the store-bound epilogues (r02 ncu of the last transposed conv: 22 % of the samples on the
+        // FADDs that consume them).
+        if (has_bias && n_blk != bias_blk) {
+          __syncwarp();
+          if (lane * 4 < kColsPerWarp) {
+            const int64_t nb = nw + lane * 4;
+            const float4 b = nb < N ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sts128(stg_addr + 16u * (uint32_t)lane, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+          }
+          __syncwarp();
+          bias_blk = n_blk;
+        }
         ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
         if (threadIdx.x == 128) NPVP_TRACE(4);
         ptx::tc_fence_after();
-        epi_direct_tile<kChunks, ACT, RES, OUTK>(t0, m, m < M, nw, N, ep, has_bias, fp16, rd, st_s, st_q, out_off, release, next_tile);
+        epi_direct_tile<kChunks, ACT, RES, OUTK>(t0, m, m < M, nw, N, ep, has_bias ? stg_addr : 0u, fp16, rd, st_s, st_q, out_off, release, next_tile);
         if (threadIdx.x == 128) NPVP_TRACE(5);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
