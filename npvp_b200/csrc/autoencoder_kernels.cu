@@ -388,6 +388,17 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
   }
 }
+// K = 8 form for dq = 8 (the 64 x 64 stage): half the tensor-pipe work of the zero-padded m16n8k16 - the kernel issues 24 HMMA per
+// 64-key tile and warp there, and ncu shows math_pipe_throttle next to a MUFU pipe that is only 44 % busy
+__device__ __forceinline__ void mma_1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0, int fp16) {
+  if (fp16) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+  }
+}
 __device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
   const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
@@ -468,7 +479,8 @@ nonlocal_attention_kernel(const h16* __restrict__ q, int64_t ldq, const h16* __r
 #pragma unroll
       for (int ks = 0; ks < QK_STEPS; ++ks) {
         const uint32_t b0 = krow[8 * ks + tig];
-        const uint32_t b1 = (DQ >= 16) ? krow[8 * ks + 4 + tig] : 0u;
+        if (DQ < 16) { mma_1688(sc[t], qa[ks][0], qa[ks][1], b0, fp16); continue; }
+        const uint32_t b1 = krow[8 * ks + 4 + tig];
         mma_16816(sc[t], qa[ks], b0, b1, fp16);
       }
     }
