@@ -1,5 +1,8 @@
-// 7x7 reflect-padded head convolution (Cin = 32 / 64 -> Cout <= 3, ResNetAutoEncoder.py:184-189) on tcgen05.
+// The two 7x7 reflect-padded convolutions at the ends of the autoencoder on tcgen05: the HEAD (Cin = 32 / 64 -> Cout <= 3,
+// ResNetAutoEncoder.py:184-189; first kernel of this file) and the STEM (Cin = 1 / 3 -> Cout = 32 / 64, ResNetAutoEncoder.py:62-66;
+// second kernel, same flattened-row scheme with the taps' roles swapped - see its own header below).
 //
+// ---- head ----
 // The mma.sync head (autoencoder_kernels.cu) stages an 8 x 64 output tile, computes, stores: 673 us per 640 Cityscapes frames
 // against 125 us of HBM time (r02 ncu: 30 % issue-active, the tile load and the HMMA chain never overlap).  This kernel
 // streams whole padded image rows through a shared-memory ring and keeps the same algebra
