@@ -518,7 +518,7 @@ def run_ours(args):
                        "cuda_graphs": bool(args.graphs)},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
-                    "steps": e2e_steps, "api": "NPVPInference.rollout(host_in, 28, out_host=host_out, last_block='query', wait_output=False): pinned host tensors, D2H overlapped per AR block; the tail copy of a call overlaps the next call, device synchronised before the clock stops",
+                    "steps": e2e_steps, "api": "NPVPInference.rollout(host_in, 28, out_host=host_out, last_block='query', wait_output=False): pinned host tensors; H2D of the context frames on an upload stream of its own (under the previous call's kernels), D2H overlapped per AR block, the tail copy of a call overlaps the next call; device synchronised before the clock stops",
                     "uint8_pixels": None if e2e_u8_ms is None else {
                         "value": frames_step * e2e_steps / (e2e_u8_ms * 1e-3), "d2h_bytes_per_step": host_out_u8.numel(),
                         "note": "same call with a uint8 out_host: frames leave the device as pixel-space bytes"}},

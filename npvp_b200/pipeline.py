@@ -267,7 +267,17 @@ class NPVPInference(nn.Module):
         ``torch.uint8`` (pixel-space frames like ``to_pixels(uint8=True)``: a quarter of the bytes)."""
         dev = next(self.parameters()).device
         if not past_frames.is_cuda:
-            past_frames = past_frames.to(dev, non_blocking=True)
+            # upload on a stream of its own that waits for nothing: when calls are issued back to back (a serving loop) the copy of
+            # this call's context overlaps the kernels of the previous call instead of sitting in front of the stem
+            # (25 MB = ~1.2 ms of a 47 ms step).  ``self.input_consumed`` says when the host buffer may be overwritten.
+            cur = torch.cuda.current_stream(dev)
+            up = self.__dict__.setdefault("_upload_stream", torch.cuda.Stream(device=dev))
+            with torch.cuda.stream(up):
+                past_frames = past_frames.to(dev, non_blocking=True)
+                self.input_consumed = torch.cuda.Event()
+                self.input_consumed.record(up)
+            past_frames.record_stream(cur)
+            cur.wait_event(self.input_consumed)
         p = self.predictor
         p._coords_ready()
         if int(getattr(p, "_coor_clips", 0)):
